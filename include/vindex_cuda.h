@@ -1,0 +1,289 @@
+/*
+ * vindex_cuda.h -- C ABI of libvindex_b200: the B200-native (sm_100a) implementation of
+ * gifton/VectorIndex's batched search hot path.
+ *
+ * Conventions (same as the reference's C module Sources/CPQEncode/include/cpq_encode.h and its
+ * @_cdecl exports Sources/VectorIndex/Operations/Scoring/CABIBridge.swift:5-30):
+ *   - plain C, caller-owned row-major buffers, `int64_t n`, `int d, m, ks`, nullable option structs;
+ *   - every pointer may be a HOST pointer or a CUDA DEVICE pointer (detected per call).  Host inputs
+ *     are copied to HBM, host outputs are copied back and the call returns after they are valid;
+ *   - new entry points return an int status: 0 = ok, negative = error.  The first five codes are the
+ *     reference's KMeansMBStatus (Sources/VectorIndex/Kernels/KMeansMiniBatchKernel.swift:131-138);
+ *     nothing aborts; vix_last_error() describes the failure;
+ *   - there is NO CPU fallback: without a usable CUDA device every entry point returns
+ *     VIX_ERR_NO_DEVICE;
+ *   - thread-safe: stateless entry points are re-entrant; index handles serialise internally.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to
+ * /root/reference/Sources/VectorIndex unless another root is given).
+ */
+#ifndef VINDEX_CUDA_H
+#define VINDEX_CUDA_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "cpq_encode.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Status, metrics, orderings                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+typedef enum {
+    VIX_OK                 = 0,
+    VIX_ERR_INVALID_DIM    = -1,   /* KMeansMBStatus.invalidDim    */
+    VIX_ERR_INVALID_K      = -2,   /* KMeansMBStatus.invalidK      */
+    VIX_ERR_NULL_PTR       = -3,   /* KMeansMBStatus.nullPtr       */
+    VIX_ERR_INVALID_LAYOUT = -4,   /* KMeansMBStatus.invalidLayout */
+    VIX_ERR_INVALID_PARAM  = -5,   /* VectorIndexError(.invalidParameter)  */
+    VIX_ERR_NOT_TRAINED    = -6,   /* index used before train / set_* */
+    VIX_ERR_EMPTY_INPUT    = -7,   /* VectorIndexError(.emptyInput)        */
+    VIX_ERR_CONTRACT       = -8,   /* VectorIndexError(.contractViolation) */
+    VIX_ERR_UNSUPPORTED    = -9,
+    VIX_ERR_CUDA           = -100,
+    VIX_ERR_NO_DEVICE      = -101,
+    VIX_ERR_OOM            = -102,
+    VIX_NO_CONVERGENCE     = 1     /* KMeansMBStatus.noConvergence */
+} vix_status;
+
+/* SupportedDistanceMetric subset on the hot path: euclidean, dotProduct (ScoreBlock.swift:24-70) */
+typedef enum { VIX_METRIC_L2 = 0, VIX_METRIC_IP = 1 } vix_metric;
+
+/* HeapOrdering (Operations/Selection/TopK.swift:8-31): ties always go to the smaller id */
+typedef enum { VIX_ORDER_MIN = 0, VIX_ORDER_MAX = 1 } vix_ordering;
+
+#define VIX_MAX_K 512      /* largest k / nprobe served by the fused selection kernels */
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Library / context                                                                                */
+/* ------------------------------------------------------------------------------------------------ */
+int         vix_version(void);
+const char* vix_last_error(void);            /* thread-local description of the last failure       */
+void        vix_clear_error(void);           /* reset it (the void cpq_* calls report only through it) */
+int         vix_device_count(void);
+int         vix_set_device(int device);      /* cudaSetDevice for the calling thread               */
+int         vix_set_stream(void* cuda_stream);  /* thread-local stream (NULL = legacy default)     */
+int         vix_set_async(int enabled);      /* 1: do not synchronise when all outputs are device ptrs */
+int         vix_synchronize(void);           /* wait for the calling thread's stream               */
+int64_t     vix_kernel_launches(int reset);  /* kernels launched by this thread (bench bookkeeping) */
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a1-a3  Flat scoring.  Replaces @_cdecl l2sqr_f32_block / ip_f32_block                            */
+/* (Operations/Scoring/CABIBridge.swift:5-30; kernels L2SqrKernel.swift:78-138, InnerProduct.swift: */
+/* 8-101).  out[i] = L2^2(q, xb[i]) (no sqrt) or <q, xb[i]>.  q_norm = NaN means "absent";          */
+/* algorithm selection as the reference: dot-trick iff norms are given or d >= 256.                 */
+/* ------------------------------------------------------------------------------------------------ */
+int vix_l2sqr_f32_block(const float* q, const float* xb, int64_t n, int d, float* out,
+                        const float* xb_norm, float q_norm);
+int vix_ip_f32_block(const float* q, const float* xb, int64_t n, int d, float* out);
+
+/* Norms.l2NormSquared per row (Operations/Support/Norms.swift:105-130; IVFIndex.swift:470-485) */
+int vix_row_norms_f32(const float* x, int64_t n, int d, float* out);
+
+/* a1-a4  Batched exact search = ScoreBlock.run + selectTopK + API distance mapping
+ * (FlatIndexOptimized.swift:390-477) for nq queries at once, top-k fused into the scan (no [nq x n]
+ * matrix is written).  ids are base row indices.  out_dist: L2 => sqrt(L2^2), IP => -dot.
+ * Rows with fewer than k results are padded with id -1 / NaN.  k <= VIX_MAX_K. */
+int vix_flat_search_f32(const float* queries, int64_t nq, const float* xb, int64_t n, int d,
+                        int metric, int k, float* out_dist, int64_t* out_ids);
+
+/* a4  selectTopK (Operations/Selection/TopK.swift:127-151): k best of n (score, id); ids == NULL
+ * => 0..n-1; outputs best -> worst (extractSorted); *out_count = min(k, n). */
+int vix_select_topk_f32(const float* scores, const int32_t* ids, int64_t n, int k, int ordering,
+                        float* out_scores, int32_t* out_ids, int* out_count);
+
+/* a5  mergeTopK (Operations/Selection/TopKMerge.swift:11-61): nlists best->worst lists stored as
+ * rows of [nlists x list_stride] with lens[l] valid entries, for `batch` independent queries
+ * (scores/ids are [batch x nlists x list_stride], lens [batch x nlists]); ties: smaller id, then
+ * smaller list index.  Outputs [batch x k] padded with id -1 / NaN.  This is also the multi-GPU
+ * reduction applied to the all-gathered per-rank results. */
+int vix_merge_topk_f32(const float* scores, const int64_t* ids, const int32_t* lens, int64_t batch,
+                       int nlists, int list_stride, int k, int ordering,
+                       float* out_scores, int64_t* out_ids);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a6-a9  Coarse quantiser                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+/* CentroidBatchScore.run (Kernels/CentroidBatchScore.swift:39-88): out[q x kc], smaller is better:
+ * L2 => ||c||^2 - 2<q,c> (||q||^2 omitted), IP => -<q,c>.  centroid_norms may be NULL (computed). */
+int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* centroids, int kc,
+                                 int d, int metric, const float* centroid_norms, float* out);
+
+/* ivf_select_nprobe_batch_f32 (Kernels/IVFSelect.swift:242-315) with the batchSearch ordering
+ * (IVFIndex.swift:593-595, 905-927): per query the nprobe best lists by (score asc, index asc);
+ * list_ids_out[b x nprobe] int32, padded with -1 (scores NaN) beyond min(nprobe, kc);
+ * disabled_lists: optional bitmask, bit i set => list i skipped (IVFSelect.swift:366-395). */
+int vix_ivf_select_nprobe_batch_f32(const float* Q, int64_t b, int d, const float* centroids, int kc,
+                                    int metric, int nprobe, const float* centroid_norms,
+                                    const uint64_t* disabled_lists,
+                                    int32_t* list_ids_out, float* list_scores_out);
+
+/* _vi_km12_assignAOS over all rows (Kernels/KMeansMiniBatchKernel.swift:341-359, 689-706):
+ * assign_out[i] = argmin_c L2^2(x_i, C_c), tie -> lower c; BIT-EXACT with the reference's 8-lane
+ * summation order.  dist_out optional. */
+int vix_ivf_assign_f32(const float* x, int64_t n, int d, const float* centroids, int kc,
+                       int32_t* assign_out, float* dist_out);
+
+/* metric-aware list assignment of IVFIndex.optimize for dot-product indexes
+ * (IVFIndex.swift:376-435): first-min argmin of the CentroidBatchScore row. */
+int vix_ivf_assign_metric_f32(const float* x, int64_t n, int d, const float* centroids, int kc,
+                              int metric, const float* centroid_norms, int32_t* assign_out);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a13  PQ look-up tables (Operations/Quantization/PQLUT.swift)                                     */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int  use_dot_trick;     /* -1 auto (centroid_norms given && ks >= 64), 0, 1   (PQLutOpts.useDotTrick) */
+    bool include_q_norm;    /* default true                                      (includeQNorm)          */
+    bool strict_fp;         /* scalar sequential sums instead of the 8-lane order (strictFP)             */
+} vix_pq_lut_opts;
+
+/* pq_lut_batch_l2_f32 (PQLUT.swift:392-465) / pq_lut_l2_f32 (:191-261) for nq queries:
+ * luts[nq x m x ks]. */
+int vix_pq_lut_batch_l2_f32(const float* queries, int64_t nq, int d, int m, int ks,
+                            const float* codebooks, float* luts, const float* centroid_norms,
+                            const vix_pq_lut_opts* opts);
+
+/* pq_lut_residual_l2_f32 (PQLUT.swift:266-386) for nq (query, coarse centroid) pairs:
+ * coarse_ids[nq] indexes coarse_centroids[kc x d]; luts[nq x m x ks]. */
+int vix_pq_lut_residual_l2_f32(const float* queries, const int32_t* coarse_ids, int64_t nq, int d,
+                               const float* coarse_centroids, int m, int ks, const float* codebooks,
+                               float* luts, const float* centroid_norms, const vix_pq_lut_opts* opts);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a14  ADC scan (Operations/Quantization/ADCScan.swift:99-149)                                     */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int   layout;            /* 0 = AoS [n][m], 1 = interleavedBlock [n/g][m][g]  (ADCLayout) */
+    int   group_size;        /* g for layout 1                                                 */
+    int   stride;            /* AoS row stride in bytes, 0 => m (u8) or m/2 (u4)               */
+    float add_bias;          /* added after the accumulator sum                                */
+    bool  strict_fp;         /* Kahan summation when m >= 64                                   */
+} vix_adc_scan_opts;
+
+/* out[i] = sum_j lut[j*ks + code(i,j)] + bias, reference accumulation order (4 accumulators for u8,
+ * sequential for u4, Kahan when strict_fp && m >= 64).  ks must be 256 (u8) / 16 (u4). */
+int vix_adc_scan_u8(const uint8_t* codes, int64_t n, int m, int ks, const float* lut, float* out,
+                    const vix_adc_scan_opts* opts);
+int vix_adc_scan_u4(const uint8_t* codes, int64_t n, int m, int ks, const float* lut, float* out,
+                    const vix_adc_scan_opts* opts);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a10 / a12  Trainers                                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int      batch_size;          /* KMeansMBConfig.batchSize   (default 1024)                 */
+    int      epochs;              /* KMeansMBConfig.epochs      (default 10)                   */
+    float    tol;                 /* KMeansMBConfig.tol         (default 1e-4)                 */
+    uint64_t seed;                /* KMeansMBConfig.seed                                       */
+    uint64_t stream_id;           /* KMeansMBConfig.streamID                                   */
+    bool     compute_assignments; /* KMeansMBConfig.computeAssignments                         */
+    int      mode;                /* 0 = reference-parity (replays RNG + quirks of finding 6),
+                                     1 = sane (Lloyd on a sample, standard empty-cluster split) */
+} vix_kmeans_cfg;
+
+/* kmeansPlusPlusSeed (Kernels/KMeansSeeding.swift:167-292) */
+int vix_kmeanspp_seed_f32(const float* data, int64_t n, int d, int k, uint64_t seed, uint64_t stream_id,
+                          float* centroids_out, int64_t* chosen_out);
+
+/* kmeans_minibatch_f32 (Kernels/KMeansMiniBatchKernel.swift:401-724); init_centroids NULL =>
+ * k-means++ with cfg.seed.  assign_out optional [n]. */
+int vix_kmeans_minibatch_f32(const float* x, int64_t n, int d, int kc, const float* init_centroids,
+                             const vix_kmeans_cfg* cfg, float* centroids_out, int32_t* assign_out);
+
+typedef struct {
+    int      algorithm;      /* 0 lloyd, 1 minibatch            (PQTrainConfig.algo)        */
+    int      max_iters;      /* default 25                                                  */
+    float    tol;            /* default 1e-4                                                */
+    int      batch_size;     /* default 1024                                                */
+    int64_t  sample_n;       /* default 0 (all rows)                                        */
+    uint64_t seed;           /* default 42                                                  */
+    int      stream_id;      /* default 0                                                   */
+    int      empty_policy;   /* 0 split, 1 reseed, 2 ignore                                 */
+    int      mode;           /* 0 = reference-parity, 1 = sane                              */
+} vix_pq_train_cfg;
+
+/* pq_train_f32 (Kernels/PQTrain.swift:83-388).  coarse_centroids/assignments both NULL or both
+ * given (residual training).  codebooks_out[m x ks x dsub], centroid_norms_out[m x ks] optional. */
+int vix_pq_train_f32(const float* x, int64_t n, int d, int m, int ks, const float* coarse_centroids,
+                     const int32_t* assignments, const vix_pq_train_cfg* cfg, float* codebooks_out,
+                     float* centroid_norms_out);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* a15  Index handles: build / train / add / search with device-resident state.                     */
+/* Mirrors VectorIndexProtocol (IndexProtocols.swift:50-103) for FlatIndex(Optimized), IVFIndex     */
+/* (IVF-Flat) and the IVF-PQ composition of docs/kernel-specs/DONE_22_adc_scan.md:831-881.          */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct vix_index vix_index_t;
+
+typedef enum { VIX_INDEX_FLAT = 0, VIX_INDEX_IVF_FLAT = 1, VIX_INDEX_IVF_PQ = 2 } vix_index_kind;
+
+typedef struct {
+    int kind;          /* vix_index_kind                                                      */
+    int d;             /* dimension                                                           */
+    int metric;        /* vix_metric                                                          */
+    int nlist;         /* IVFIndex.Configuration.nlist (default 256), clamped to n at train   */
+    int nprobe;        /* IVFIndex.Configuration.nprobe (default 8)                           */
+    int m;             /* PQ sub-quantisers (IVF_PQ)                                          */
+    int ks;            /* PQ codebook size, 256                                               */
+    int shard_rank;    /* multi-GPU: this rank ...                                            */
+    int shard_world;   /* ... of shard_world ranks (lists / row ranges are partitioned); 0/1 = no sharding */
+} vix_index_params;
+
+void vix_index_params_default(vix_index_params* p);
+int  vix_index_create(const vix_index_params* p, vix_index_t** out);
+void vix_index_destroy(vix_index_t* h);
+
+/* optimize(): coarse k-means (+ PQ codebooks on residuals) from a training sample */
+int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_cfg* kcfg,
+                    const vix_pq_train_cfg* pcfg);
+/* stage-wise parity / import: install externally trained parameters */
+int vix_index_set_coarse(vix_index_t* h, const float* centroids, int kc);
+int vix_index_set_codebooks(vix_index_t* h, const float* codebooks, const float* centroid_norms);
+int vix_index_get_coarse(vix_index_t* h, float* centroids_out, int* kc_out);
+int vix_index_get_codebooks(vix_index_t* h, float* codebooks_out, float* centroid_norms_out);
+
+/* batchInsert: ids NULL => consecutive ids continuing from the current count */
+int vix_index_add(vix_index_t* h, const float* x, const int64_t* ids, int64_t n);
+/* import of prebuilt inverted lists in the reference's AoS list format (Kernels/IVFAppend.swift:
+ * 220-236): CSR offsets[kc+1], codes[N x m], ids[N] */
+int vix_index_import_lists(vix_index_t* h, const int64_t* list_offsets, const uint8_t* codes,
+                           const int64_t* ids);
+int64_t vix_index_count(vix_index_t* h);       /* vectors stored on THIS shard */
+int     vix_index_list_sizes(vix_index_t* h, int64_t* sizes_out /* [nlist] */);
+int     vix_index_export_lists(vix_index_t* h, int64_t* list_offsets, uint8_t* codes, int64_t* ids,
+                               int32_t* assignments_in_add_order /* nullable */);
+int     vix_index_clear(vix_index_t* h);
+
+/* batchSearch: out_dist/out_ids [nq x k] ascending by API distance, padded with id -1 / NaN.
+ * nprobe <= 0 => the index's configured nprobe.  k <= 0 => VIX_OK with nothing written
+ * (IVFIndex.swift:866).  With sharding the result is this shard's local top-k (merge with
+ * vix_merge_topk_f32 after an all-gather). */
+int vix_index_search(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
+                     float* out_dist, int64_t* out_ids);
+
+/* stage outputs for parity tests and profiling */
+typedef struct {
+    int64_t codes_scanned;        /* sum over (query, probed owned list) of list length          */
+    int64_t code_bytes_scanned;   /* codes_scanned * m  == algorithmic ADC bytes      */
+    float   ms_coarse;            /* CUDA-event time of the probe-selection stage                 */
+    float   ms_scan;              /* ... of the LUT + ADC + top-k stage                           */
+    float   ms_total;
+} vix_search_stats;
+int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
+                        float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,
+                        vix_search_stats* stats /* nullable */);
+
+/* a16  AccelerableIndex-shaped convenience (AccelerableIndex.swift:15-127): candidates [c x d]
+ * contiguous in, (indices into candidates, distances) out, per query. */
+int vix_accel_rank_candidates_f32(const float* queries, int64_t nq, const float* candidates, int64_t c,
+                                  int d, int metric, int k, int32_t* out_indices, float* out_distances);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINDEX_CUDA_H */

@@ -1,0 +1,449 @@
+"""GPU parity: every call goes through the C ABI of libvindex_b200.so and is compared with the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star): PQ codes and IVF list assignments bit-exact;
+distances within 1e-5 relative; top-k id sets equal except at ties inside that tolerance.  Where the GPU
+kernel restates the reference's summation order (flat scan, probe scores, LUT, materialising ADC) the
+comparison is bit-exact as well."""
+import numpy as np
+import pytest
+
+from conftest import parity_fixture
+from vectorindex_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star: fp32 relative tolerance for distances
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_topk_close(gd, gi, od, oi, rtol=RTOL, atol=0.0):
+    """id sets equal except at ties within tolerance; distances within tolerance."""
+    assert gd.shape == od.shape
+    for r in range(gd.shape[0]):
+        ov = oi[r] >= 0
+        gv = gi[r] >= 0
+        assert ov.sum() == gv.sum(), f"row {r}: {gv.sum()} results vs oracle {ov.sum()}"
+        if ov.sum() == 0:
+            continue
+        np.testing.assert_allclose(gd[r][gv], od[r][ov], rtol=rtol, atol=atol, err_msg=f"row {r} distances")
+        omap = dict(zip(oi[r][ov].tolist(), od[r][ov].tolist()))
+        kth = od[r][ov][-1]
+        for i, dist in zip(gi[r][gv].tolist(), gd[r][gv].tolist()):
+            if i in omap:
+                assert abs(dist - omap[i]) <= rtol * abs(omap[i]) + atol, f"row {r} id {i}: {dist} vs {omap[i]}"
+            else:   # boundary tie inside the tolerance
+                assert abs(dist - kth) <= 4 * rtol * abs(kth) + atol, f"row {r}: id {i} not in oracle set ({dist} vs kth {kth})"
+
+
+# ------------------------------------------------------------------------------------------------ PQ encode
+ENC_SHAPES = [(1000, 64, 8), (777, 48, 6), (300, 40, 4), (513, 96, 48), (260, 128, 16), (100, 24, 24)]
+
+
+@pytest.mark.parametrize("n,d,m", ENC_SHAPES)
+def test_pq_encode_bit_exact_all_entry_points(oracle, vk, n, d, m):
+    rng = np.random.default_rng(n + d)
+    ks, kc, dsub = 256, 7, d // m
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    cb = (rng.standard_normal(m * ks * dsub) * 0.7).astype(np.float32)
+    coarse = (rng.standard_normal((kc, d)) * 0.5).astype(np.float32)
+    assign = rng.integers(0, kc, n).astype(np.int32)
+    csq = oracle.pq_centroid_sq(cb, m, ks, dsub, swift=True)
+    nodot = _lib.PQEncodeOpts(0, False, False, 8, 0, 0, 0)
+    assert np.array_equal(vk.pq_encode_u8_f32(x, cb, m), oracle.pq_encode_u8(x, cb, m, ks, use_dot=True))
+    assert np.array_equal(vk.pq_encode_u8_f32(x, cb, m, opts=nodot), oracle.pq_encode_u8(x, cb, m, ks, use_dot=False))
+    assert np.array_equal(vk.pq_encode_u8_f32_withCSQ(x, cb, csq, m), oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq))
+    assert np.array_equal(vk.pq_encode_residual_u8_f32(x, cb, coarse, assign, m),
+                          oracle.pq_encode_u8(x, cb, m, ks, coarse=coarse, assign_=assign, use_dot=True))
+    assert np.array_equal(vk.pq_encode_residual_u8_f32(x, cb, coarse, assign, m, opts=nodot),
+                          oracle.pq_encode_u8(x, cb, m, ks, coarse=coarse, assign_=assign, use_dot=False))
+    assert np.array_equal(vk.pq_encode_residual_u8_f32_withCSQ(x, cb, csq, coarse, assign, m),
+                          oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq, coarse=coarse, assign_=assign))
+    if m % 2 == 0:
+        cb4 = (rng.standard_normal(m * 16 * dsub) * 0.7).astype(np.float32)
+        assert np.array_equal(vk.pq_encode_u4_f32(x, cb4, m), oracle.pq_encode_u4(x, cb4, m, 16))
+        assert np.array_equal(vk.pq_encode_residual_u4_f32(x, cb4, coarse, assign, m),
+                              oracle.pq_encode_u4(x, cb4, m, 16, coarse=coarse, assign_=assign))
+
+
+def test_pq_encode_reference_fixture_and_layouts(oracle, vk):
+    """fixture of PQEncodeParity_AoS_C_vs_Swift_Tests.swift:5-31 against the compiled reference encoder,
+    including the SoA-blocked and interleaved output layouts (pq_encode.c:260-276)."""
+    x, cb, coarse, assign = parity_fixture(n=70)
+    csq = oracle.pq_centroid_sq(cb, 8, 256, 4, swift=False)
+    got = vk.pq_encode_u8_f32_withCSQ(x, cb, csq, 8)
+    assert got[0].tolist() == [212, 186, 160, 117, 255, 154, 186, 249]
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    assert np.array_equal(got, oracle.ref_encode("cpq_encode_u8_f32_with_csq", x, cb, 8, 256, centroid_sq=csq))
+    n, m = x.shape[0], 8
+    for layout, B, g in ((1, 64, 0), (1, 16, 0), (2, 0, 8), (2, 0, 4)):
+        o = _lib.PQEncodeOpts(layout, True, False, 8, 0, B, g)
+        ro = oracle.PQEncodeOpts(layout, True, False, 8, 0, B, g)
+        ours = np.asarray(vk.pq_encode_u8_f32(x, cb, m, opts=o)).reshape(-1)
+        Bq, gq = (B or 64), (g or 8)
+        size = m * ((n + Bq - 1) // Bq) * Bq if layout == 1 else ((n + gq - 1) // gq) * m * gq
+        ref = np.zeros(size, dtype=np.uint8)
+        import ctypes as C
+        L = oracle.ref_lib()
+        L.cpq_encode_u8_f32.restype = None
+        L.cpq_encode_u8_f32(x.ctypes.data_as(oracle.f32p), C.c_int64(n), C.c_int(x.shape[1]), C.c_int(m), C.c_int(256),
+                            cb.ctypes.data_as(oracle.f32p), ref.ctypes.data_as(oracle.u8p), C.byref(ro))
+        assert np.array_equal(ours[:size], ref), f"layout {layout} B={B} g={g}"
+
+
+def test_pq_encode_empty_and_device_pointers(oracle, vk):
+    import torch
+    rng = np.random.default_rng(3)
+    d, m = 32, 4
+    cb = rng.standard_normal(m * 256 * 8).astype(np.float32)
+    assert vk.pq_encode_u8_f32(np.zeros((0, d), np.float32), cb, m).shape == (0, m)
+    x = rng.standard_normal((500, d)).astype(np.float32)
+    want = oracle.pq_encode_u8(x, cb, m, 256, use_dot=True)
+    got = vk.pq_encode_u8_f32(torch.from_numpy(x).cuda(), torch.from_numpy(cb).cuda(), m)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------ assignment
+@pytest.mark.parametrize("n,kc,d", [(3000, 100, 128), (2500, 257, 96), (1000, 33, 37), (700, 5, 8), (300, 70, 768)])
+def test_ivf_assign_bit_exact(oracle, vk, n, kc, d):
+    rng = np.random.default_rng(n + kc)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    c = x[rng.choice(n, kc, replace=False)] + (rng.standard_normal((kc, d)) * 0.1).astype(np.float32)
+    oa, od = oracle.assign(x, c)
+    ga, gd = vk.ivf_assign_f32(x, c, return_dist=True)
+    assert np.array_equal(ga, oa)
+    assert np.array_equal(bits(gd), bits(od))
+
+
+def test_ivf_assign_ties_go_to_lower_index(oracle, vk):
+    """heavy ties: integer-valued SIFT-like data and duplicated centroids (KMeansMiniBatchKernel.swift:352)."""
+    from vectorindex_b200 import datagen
+    x = datagen.sift_like(4000, 32, 50, 77)
+    c = np.concatenate([x[:40], x[:40], x[100:120]]).astype(np.float32)   # centroids 40..79 duplicate 0..39
+    oa, _ = oracle.assign(x, c)
+    ga = vk.ivf_assign_f32(x, c)
+    assert np.array_equal(ga, oa)
+    assert (ga[:40] == np.arange(40)).all()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_ivf_assign_metric(oracle, vk, metric):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1500, 64)).astype(np.float32)
+    c = rng.standard_normal((90, 64)).astype(np.float32)
+    assert np.array_equal(vk.ivf_assign_metric_f32(x, c, metric), oracle.assign_metric(x, c, metric))
+
+
+# ------------------------------------------------------------------------------------------------ flat scan
+@pytest.mark.parametrize("n,d,nq,k,metric", [(5000, 128, 70, 10, 0), (3000, 256, 33, 10, 0), (4000, 100, 17, 5, 1),
+                                            (2000, 768, 20, 10, 1), (900, 37, 9, 32, 0), (20, 16, 4, 50, 0)])
+def test_flat_search_matches_reference_kernels(oracle, vk, n, d, nq, k, metric):
+    rng = np.random.default_rng(n + d + k)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    od, oi, _ = oracle.flat_search(q, xb, k, metric)
+    gd, gi = vk.flat_search_f32(q, xb, k, metric)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(bits(gd), bits(od))
+
+
+def test_flat_search_bench_fixture_and_ties(oracle, vk):
+    """reference benchmark recipe (unit-norm LCG vectors, seeds 123/321) + duplicated rows (ties -> smaller id)."""
+    from vectorindex_b200 import datagen
+    xb = datagen.bench_vectors(3000, 128, 123)
+    xb = np.concatenate([xb, xb[:500]])            # rows 3000.. duplicate rows 0..499
+    q = datagen.bench_vectors(40, 128, 321)
+    q[:5] = xb[:5]
+    od, oi, _ = oracle.flat_search(q, xb, 10, 0)
+    gd, gi = vk.flat_search_f32(q, xb, 10, 0)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    assert gi[0, 0] == 0 and gi[0, 1] == 3000
+
+
+def test_flat_search_edge_cases(vk):
+    q = np.zeros((3, 8), dtype=np.float32)
+    d, i = vk.flat_search_f32(q, np.zeros((0, 8), np.float32), 4)
+    assert (i == -1).all() and np.isnan(d).all()
+    d, i = vk.flat_search_f32(q, np.ones((5, 8), np.float32), 0)
+    assert d.shape == (3, 0)
+    from vectorindex_b200 import VectorIndexError
+    with pytest.raises(VectorIndexError):
+        vk.flat_search_f32(q, np.ones((5, 9), np.float32), 2)
+
+
+def test_block_scores_and_norms(oracle, vk):
+    rng = np.random.default_rng(11)
+    for d in (16, 100, 128, 256, 300):
+        xb = rng.standard_normal((700, d)).astype(np.float32)
+        q = rng.standard_normal(d).astype(np.float32)
+        assert np.array_equal(bits(vk.l2sqr_f32_block(q, xb)), bits(oracle.l2sqr_block(q, xb)))
+        assert np.array_equal(bits(vk.ip_f32_block(q, xb)), bits(oracle.ip_block(q, xb)))
+        xn = oracle.centroid_norms(xb)
+        assert np.array_equal(bits(vk.row_norms_f32(xb)), bits(xn))
+        assert np.array_equal(bits(vk.l2sqr_f32_block(q, xb, xb_norm=xn)), bits(oracle.l2sqr_block(q, xb, xb_norm=xn)))
+
+
+# ------------------------------------------------------------------------------------------------ selection
+def test_select_and_merge_topk(oracle, vk):
+    rng = np.random.default_rng(2)
+    s = np.round(rng.standard_normal(50000) * 50).astype(np.float32)       # many ties
+    for k, order in ((10, 0), (100, 1), (1, 0)):
+        os_, oi = oracle.select_topk(s, k, order)
+        gs, gi = vk.selectTopK(s, k, order)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gs), bits(os_))
+    gs, gi = vk.selectTopK(np.array([5, 3, 8, 1, 9], np.float32), 3, 1, ids=np.arange(10, 15, dtype=np.int32))
+    assert gs.tolist() == [9, 8, 5] and gi.tolist() == [14, 12, 10]          # TelemetryRecorderTests.swift:229-241
+    # merge of 3 sorted lists per row
+    batch, nl, st, k = 6, 3, 8, 10
+    sc = np.sort(np.round(rng.standard_normal((batch, nl, st)) * 3), axis=2).astype(np.float32)
+    ids = rng.permutation(batch * nl * st).reshape(batch, nl, st).astype(np.int64)
+    lens = rng.integers(0, st + 1, (batch, nl)).astype(np.int32)
+    gs, gi = vk.mergeTopK(sc, ids, k, 0, lens)
+    for b in range(batch):
+        lists = []
+        for l in range(nl):
+            n_ = lens[b, l]
+            o = np.lexsort((ids[b, l, :n_], sc[b, l, :n_]))
+            lists.append((sc[b, l, :n_][o], ids[b, l, :n_][o].astype(np.int32)))
+        ms, mi = oracle.merge_topk(lists, k, 0)
+        assert gi[b, :mi.size].tolist() == mi.tolist() and (gi[b, mi.size:] == -1).all()
+        assert np.array_equal(bits(gs[b, :ms.size]), bits(ms))
+
+
+# ------------------------------------------------------------------------------------------------ coarse probing
+@pytest.mark.parametrize("metric", [0, 1])
+def test_centroid_scores_and_probe_selection(oracle, vk, metric):
+    rng = np.random.default_rng(9)
+    q = rng.standard_normal((150, 96)).astype(np.float32)
+    c = rng.standard_normal((300, 96)).astype(np.float32)
+    c[200:230] = c[10:40]                                                  # duplicated centroids => score ties
+    assert np.array_equal(bits(vk.centroid_batch_score(q, c, metric)), bits(oracle.centroid_batch_score(q, c, metric)))
+    oi, os_ = oracle.probe_select_batch(q, c, 32, metric)
+    gi, gs = vk.ivf_select_nprobe_batch_f32(q, c, 32, metric)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gs), bits(os_))
+
+
+def test_probe_selection_pins_and_padding(oracle, vk):
+    cents = np.ones((50, 8), dtype=np.float32)                              # IVFSelectTests.swift:305-347
+    gi, _ = vk.ivf_select_nprobe_batch_f32(np.zeros((2, 8), np.float32), cents, 20)
+    assert gi[0].tolist() == list(range(20))
+    gi, gs = vk.ivf_select_nprobe_batch_f32(np.zeros((2, 8), np.float32), cents[:5], 8)   # nprobe > kc
+    assert gi[1].tolist() == [0, 1, 2, 3, 4, -1, -1, -1] and np.isnan(gs[1, 5:]).all()
+    mask = np.array([0b10110], dtype=np.uint64)                            # lists 1, 2, 4 disabled
+    gi, _ = vk.ivf_select_nprobe_batch_f32(np.zeros((1, 8), np.float32), cents[:6], 3, disabled_lists=mask)
+    assert gi[0].tolist() == [0, 3, 5]
+
+
+# ------------------------------------------------------------------------------------------------ LUT + ADC
+@pytest.mark.parametrize("d,m", [(128, 16), (96, 48), (768, 64), (40, 4)])
+def test_pq_lut_bit_exact(oracle, vk, d, m):
+    rng = np.random.default_rng(d)
+    ks, dsub, nq, kc = 256, d // m, 5, 9
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    cb = rng.standard_normal(m * ks * dsub).astype(np.float32)
+    coarse = rng.standard_normal((kc, d)).astype(np.float32)
+    cids = rng.integers(0, kc, nq).astype(np.int32)
+    cn = oracle.pq_centroid_sq(cb, m, ks, dsub, swift=False)
+    for norms, use_dot, incq, strict in ((None, -1, True, False), (cn, -1, True, False), (cn, 1, False, False),
+                                         (cn, 0, True, False), (None, -1, True, True), (cn, -1, True, True)):
+        o = _lib.PQLutOpts(use_dot, incq, strict)
+        g = vk.pq_lut_batch_l2_f32(q, cb, m, ks, norms, o)
+        gr = vk.pq_lut_residual_l2_f32(q, cids, coarse, cb, m, ks, norms, o)
+        for i in range(nq):
+            want = oracle.pq_lut_l2(q[i], cb, m, ks, norms, use_dot, incq, strict)
+            assert np.array_equal(bits(g[i]), bits(want)), (use_dot, incq, strict)
+            wr = oracle.pq_lut_residual_l2(q[i], coarse[cids[i]], cb, m, ks, norms, use_dot, incq, strict)
+            assert np.array_equal(bits(gr[i]), bits(wr)), ("res", use_dot, incq, strict)
+
+
+def test_adc_scan_bit_exact(oracle, vk):
+    rng = np.random.default_rng(4)
+    for m in (16, 18, 64):
+        n = 3000
+        codes = rng.integers(0, 256, (n, m)).astype(np.uint8)
+        lut = rng.random((m, 256)).astype(np.float32)
+        assert np.array_equal(bits(vk.adc_scan_u8(codes, lut, m)), bits(oracle.adc_scan_u8(codes, lut, m)))
+        o = _lib.ADCScanOpts(0, 0, 0, 0.375, True)
+        assert np.array_equal(bits(vk.adc_scan_u8(codes, lut, m, opts=o)),
+                              bits(oracle.adc_scan_u8(codes, lut, m, bias=0.375, strict_fp=True)))
+        pad = np.zeros((n, m + 5), dtype=np.uint8)
+        pad[:, :m] = codes
+        o = _lib.ADCScanOpts(0, 0, m + 5, 0.0, False)
+        assert np.array_equal(bits(vk.adc_scan_u8(pad, lut, m, opts=o)), bits(oracle.adc_scan_u8(codes, lut, m)))
+        # u4
+        c4 = rng.integers(0, 256, (n, m // 2)).astype(np.uint8)
+        lut4 = rng.random((m, 16)).astype(np.float32)
+        assert np.array_equal(bits(vk.adc_scan_u4(c4, lut4, m)), bits(oracle.adc_scan_u4(c4, lut4, m)))
+        o = _lib.ADCScanOpts(0, 0, 0, 1.5, True)
+        assert np.array_equal(bits(vk.adc_scan_u4(c4, lut4, m, opts=o)),
+                              bits(oracle.adc_scan_u4(c4, lut4, m, bias=1.5, strict_fp=True)))
+    # interleavedBlock (ADCScan.swift:288-379): one sequential accumulator per vector
+    n, m, g = 103, 16, 8
+    codes = rng.integers(0, 256, (n, m)).astype(np.uint8)
+    lut = rng.random((m, 256)).astype(np.float32)
+    inter = np.zeros(((n + g - 1) // g) * m * g, dtype=np.uint8)
+    for i in range(n):
+        for j in range(m):
+            inter[(i // g) * m * g + j * g + i % g] = codes[i, j]
+    want = np.zeros(n, dtype=np.float32)
+    for j in range(m):
+        want = (want + lut[j, codes[:, j]]).astype(np.float32)
+    got = vk.adc_scan_u8(inter, lut, m, opts=_lib.ADCScanOpts(1, g, 0, 0.0, False), n=n)
+    assert np.array_equal(bits(got), bits(want))
+    assert vk.adc_scan_u8(np.zeros((0, 16), np.uint8), lut, 16).shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------------ indexes
+def _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed, sift=False, unit=False):
+    from vectorindex_b200 import datagen
+    rng = np.random.default_rng(seed)
+    if sift:
+        x = datagen.sift_like(n + nq, d, max(kc // 2, 4), seed)
+    else:
+        x = datagen.clustered_unit(n + nq, d, max(kc // 2, 4), seed) if unit else \
+            (rng.standard_normal((n + nq, d)) + 3 * rng.standard_normal((max(kc // 2, 4), d))[rng.integers(0, max(kc // 2, 4), n + nq)]).astype(np.float32)
+    xb, q = np.ascontiguousarray(x[:n]), np.ascontiguousarray(x[n:])
+    coarse = np.ascontiguousarray(xb[rng.choice(n, kc, replace=False)])
+    asg, _ = oracle.assign(xb, coarse)
+    rc, cb, norms, _ = oracle.pq_train(xb[:2000], m, 256, coarse=coarse, assign_=asg[:2000], max_iters=4, sample_n=0)
+    assert rc == 0
+    return xb, q, coarse, cb, norms
+
+
+@pytest.mark.parametrize("n,d,m,kc,nprobe,metric,kind", [
+    (20000, 128, 16, 64, 8, 0, "sift"),      # C3-shaped, fast path m=16
+    (12000, 96, 48, 50, 6, 0, "unit"),       # C5-shaped, m=48 (dsub=2)
+    (8000, 64, 8, 30, 5, 0, "gauss"),        # generic m (not a multiple of 16)
+    (8000, 128, 32, 40, 40, 0, "gauss"),     # nprobe == kc: exhaustive
+    (9000, 128, 64, 32, 6, 1, "unit"),       # C4-shaped inner product, m=64
+])
+def test_ivfpq_index_stagewise_parity(oracle, n, d, m, kc, nprobe, metric, kind):
+    from vectorindex_b200.index import IVFPQIndex
+    nq, k = 64, 10
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=n + m, sift=(kind == "sift"),
+                                                   unit=(kind == "unit"))
+    idx = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    ids = (np.arange(n, dtype=np.int64) * 3 + 7)                       # non-trivial external ids, ascending
+    idx.batch_insert(xb[: n // 2], ids[: n // 2])
+    idx.batch_insert(xb[n // 2:], ids[n // 2:])                        # two adds: lists must merge
+    assert idx.count == n
+    off, codes, lids, asg = idx.export_lists()
+    # list assignment + codes: bit-exact
+    oasg = oracle.assign(xb, coarse)[0] if metric == 0 else oracle.assign_metric(xb, coarse, metric)
+    assert np.array_equal(asg, oasg)
+    ocodes = oracle.pq_encode_u8(xb, cb, m, 256, centroid_sq=norms.reshape(-1), coarse=coarse, assign_=oasg)
+    ooff, order = oracle.build_lists(oasg, kc)
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(lids, ids[order])
+    assert np.array_equal(codes, ocodes[order])
+    assert np.array_equal(idx.list_sizes(), np.diff(ooff))
+    # search: probes exact, distances 1e-5, id sets up to ties
+    od, oi, op = oracle.ivfpq_search(q, coarse, cb, norms, off, codes, lids, m, 256, nprobe, k, metric)
+    gd, gi, gp = idx.batch_search(q, k, return_probes=True)
+    assert np.array_equal(gp, op)
+    scale = float(np.nanmax(np.abs(od)))
+    assert_topk_close(gd, gi, od, oi, rtol=RTOL, atol=RTOL * scale * (1.0 if metric == 1 else 0.0))
+    # import path: a second index fed the exported lists answers identically
+    idx2 = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    idx2.set_coarse(coarse)
+    idx2.set_codebooks(cb, norms)
+    idx2.import_lists(off, codes, lids)
+    gd2, gi2 = idx2.batch_search(q, k)
+    assert np.array_equal(gi2, gi) and np.array_equal(bits(gd2), bits(gd))
+
+
+def test_ivfpq_edge_cases(oracle):
+    from vectorindex_b200.index import IVFPQIndex
+    from vectorindex_b200 import VectorIndexError
+    d, m, kc = 32, 16, 8
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, 3000, d, m, kc, 5, seed=1)
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=3, m=m)
+    with pytest.raises(VectorIndexError) as e:
+        idx.batch_insert(xb)
+    assert e.value.kind == "notTrained"
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    gd, gi = idx.batch_search(q, 4)                                    # empty index
+    assert (gi == -1).all() and np.isnan(gd).all()
+    idx.batch_insert(xb[:6])                                           # fewer vectors than k, ragged lists
+    gd, gi = idx.batch_search(q, 10, nprobe=kc)
+    assert ((gi >= 0).sum(axis=1) == 6).all()
+    assert idx.batch_search(q, 0)[0].shape == (5, 0)                   # k <= 0 => [] (IVFIndex.swift:866)
+    gd, gi = idx.batch_search(q, 3, nprobe=20)                         # nprobe > kc is clamped by padding
+    assert (gi >= 0).all()
+    with pytest.raises(VectorIndexError):
+        idx.batch_search(np.zeros((2, d + 1), np.float32), 3)          # dimension mismatch throws
+    with pytest.raises(VectorIndexError):
+        idx.batch_insert(xb[:2], np.array([-1, 5], dtype=np.int64))    # ids must fit the reference's id type
+    assert idx.search(q[0], 2)[0][0] >= 0
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_ivfflat_and_flat_index(oracle, metric):
+    from vectorindex_b200.index import FlatIndex, IVFIndex
+    rng = np.random.default_rng(8)
+    n, d, kc, nq, k, nprobe = 6000, 48, 40, 30, 10, 6
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    coarse = np.ascontiguousarray(xb[rng.choice(n, kc, replace=False)])
+    ids = np.arange(n, dtype=np.int64) + 100
+    ivf = IVFIndex(d, metric, nlist=kc, nprobe=nprobe)
+    ivf.set_coarse(coarse)
+    ivf.batch_insert(xb, ids)
+    asg = oracle.assign(xb, coarse)[0] if metric == 0 else oracle.assign_metric(xb, coarse, metric)
+    off, order = oracle.build_lists(asg, kc)
+    od, oi = oracle.ivfflat_search(q, coarse, off, xb[order], ids[order], nprobe, k, metric)
+    gd, gi = ivf.batch_search(q, k)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    flat = FlatIndex(d, metric)
+    flat.batch_insert(xb, ids)
+    fd, fi = flat.batch_search(q, k)
+    od, oi, _ = oracle.flat_search(q, xb, k, metric)
+    assert np.array_equal(fi, oi + 100) and np.array_equal(bits(fd), bits(od))
+
+
+def test_device_resident_search_equals_host_path(oracle):
+    import torch
+    from vectorindex_b200.index import IVFPQIndex
+    d, m, kc = 64, 16, 16
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, 5000, d, m, kc, 40, seed=21)
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=4, m=m)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    idx.batch_insert(torch.from_numpy(xb).cuda())
+    hd, hi = idx.batch_search(q, 10)
+    dd, di = idx.batch_search(torch.from_numpy(q).cuda(), 10)
+    assert dd.is_cuda and np.array_equal(di.cpu().numpy(), hi) and np.array_equal(bits(dd.cpu().numpy()), bits(hd))
+
+
+def test_gpu_training_builds_a_working_index(oracle):
+    """mode-1 trainers (deterministic Lloyd): the trained IVF-PQ index reaches a sane recall and two
+    trainings give bit-identical parameters (rank-to-rank reproducibility for the sharded build)."""
+    from vectorindex_b200 import datagen
+    from vectorindex_b200.index import IVFPQIndex
+    n, d, m, kc, nq, k = 30000, 64, 16, 64, 100, 10
+    x = datagen.clustered_unit(n + nq, d, 200, 5)
+    xb, q = x[:n], x[n:]
+    params = []
+    for _ in range(2):
+        idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=16, m=m)
+        idx.optimize(xb)
+        params.append((idx.get_coarse(), idx.get_codebooks()[0]))
+    assert np.array_equal(bits(params[0][0]), bits(params[1][0]))
+    assert np.array_equal(bits(params[0][1]), bits(params[1][1]))
+    idx.batch_insert(xb)
+    sizes = idx.list_sizes()
+    assert sizes.sum() == n and (sizes > 0).sum() >= kc * 0.9
+    gd, gi = idx.batch_search(q, k)
+    _, ti, _ = oracle.flat_search(q, xb, k, 0)
+    recall = np.mean([len(set(gi[r]) & set(ti[r])) / k for r in range(nq)])
+    assert recall > 0.5, recall
+    # and the oracle, fed the same trained parameters and lists, agrees with the GPU search
+    off, codes, lids, _ = idx.export_lists()
+    cb, norms = idx.get_codebooks()
+    od, oi, _ = oracle.ivfpq_search(q, idx.get_coarse(), cb, norms, off, codes, lids, m, 256, 16, k, 0)
+    assert_topk_close(gd, gi, od, oi)

@@ -1,0 +1,152 @@
+"""The oracle pinned against everything the reference's own tests hold for this path:
+
+  E1  the reference's C encoder, compiled unmodified (oracle/_ref), on the fixture of
+      Tests/VectorIndexTests/PQEncodeParity_AoS_C_vs_Swift_Tests.swift:5-31
+  E2  the bit-level golden vector of Tests/VectorIndexTests/PQTrainTests.swift:724-817
+  E3  the published IVF recall 0.9565000000000008 (.bench/post-phase3/ivf_search.json:54)
+  +   tie-break pins: TelemetryRecorderTests.swift:229-241, IVFSelectTests.swift:305-347,
+      IVFListVecsReaderRerankTests.swift:66-126 (tie -> smaller id)
+"""
+import numpy as np
+import pytest
+
+from conftest import parity_fixture
+from vectorindex_b200 import datagen
+
+
+def test_e1_reference_encoder_fixture(oracle):
+    x, cb, coarse, assign = parity_fixture()
+    csq = oracle.pq_centroid_sq(cb, 8, 256, 4, swift=False)
+    ours = oracle.pq_encode_u8(x, cb, 8, 256, centroid_sq=csq)
+    assert ours[0].tolist() == [212, 186, 160, 117, 255, 154, 186, 249]
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = oracle.ref_encode("cpq_encode_u8_f32_with_csq", x, cb, 8, 256, centroid_sq=csq)
+    assert np.array_equal(ref, ours)
+    # direct path == dot path on this fixture (PQEncodeParity...:61), OpenMP build identical
+    opts = oracle.PQEncodeOpts(0, False, False, 8, 0, 0, 0)
+    assert np.array_equal(oracle.ref_encode("cpq_encode_u8_f32", x, cb, 8, 256, opts=opts), ref)
+    assert np.array_equal(oracle.ref_encode("cpq_encode_u8_f32_with_csq", x, cb, 8, 256, centroid_sq=csq, omp=True), ref)
+
+
+@pytest.mark.parametrize("variant", ["u8", "u8_nodot", "u8_csq", "res", "res_csq", "res_nodot", "u4", "res_u4"])
+def test_oracle_encoder_equals_reference_encoder(oracle, variant):
+    """our C restatement of pq_encode.c vs the compiled reference, every entry point, random data."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    n, d, m, kc = 300, 48, 6, 5
+    u4 = variant.endswith("u4")
+    ks = 16 if u4 else 256
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    cb = rng.standard_normal((m * ks * (d // m))).astype(np.float32)
+    coarse = rng.standard_normal((kc, d)).astype(np.float32) * np.float32(0.5)
+    assign = rng.integers(0, kc, n).astype(np.int32)
+    csq = oracle.pq_centroid_sq(cb, m, ks, d // m, swift=True)
+    nodot = oracle.PQEncodeOpts(0, False, False, 8, 0, 0, 0)
+    if variant == "u8":
+        a = oracle.ref_encode("cpq_encode_u8_f32", x, cb, m, ks)
+        b = oracle.pq_encode_u8(x, cb, m, ks, use_dot=True)
+    elif variant == "u8_nodot":
+        a = oracle.ref_encode("cpq_encode_u8_f32", x, cb, m, ks, opts=nodot)
+        b = oracle.pq_encode_u8(x, cb, m, ks, use_dot=False)
+    elif variant == "u8_csq":
+        a = oracle.ref_encode("cpq_encode_u8_f32_with_csq", x, cb, m, ks, centroid_sq=csq)
+        b = oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq)
+    elif variant == "res":
+        a = oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=coarse, assign_=assign)
+        b = oracle.pq_encode_u8(x, cb, m, ks, coarse=coarse, assign_=assign, use_dot=True)
+    elif variant == "res_nodot":
+        a = oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=coarse, assign_=assign, opts=nodot)
+        b = oracle.pq_encode_u8(x, cb, m, ks, coarse=coarse, assign_=assign, use_dot=False)
+    elif variant == "res_csq":
+        a = oracle.ref_encode("cpq_encode_residual_u8_f32_with_csq", x, cb, m, ks, centroid_sq=csq, coarse=coarse,
+                              assign_=assign)
+        b = oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq, coarse=coarse, assign_=assign)
+    elif variant == "u4":
+        a = oracle.ref_encode("cpq_encode_u4_f32", x, cb, m, ks, packed_u4=True)
+        b = oracle.pq_encode_u4(x, cb, m, ks)
+    else:
+        a = oracle.ref_encode("cpq_encode_residual_u4_f32", x, cb, m, ks, coarse=coarse, assign_=assign, packed_u4=True)
+        b = oracle.pq_encode_u4(x, cb, m, ks, coarse=coarse, assign_=assign)
+    assert np.array_equal(a, b)
+
+
+def test_e2_pq_streaming_train_golden_bits(oracle):
+    """PQTrainTests.swift:724-817: ks=16, d=16, m=2, n=40 in two chunks, LCG fill, seed 42, minibatch,
+    maxIters 10, batch 512 => codebooks[0..3] bit patterns."""
+    ks, d, m, n = 16, 16, 2, 40
+    full = datagen.lcg24_floats(0x5773_7EA1_1234_5678, n * d)[0].reshape(n, d)
+    chunks = [full[:20], full[20:]]
+    rc, cb = oracle.pq_train_streaming(chunks, d, m, ks, seed=42, algorithm=1, max_iters=10, batch_size=512)
+    assert rc == 0
+    got = cb.reshape(-1)[:4]
+    want = np.array([0.7648039, -0.5310464, -0.7147653, 0.30723625], dtype=np.float32)
+    assert got.view(np.uint32).tolist() == want.view(np.uint32).tolist()
+    assert np.isfinite(cb).all()
+
+
+def test_e3_ivf_end_to_end_recall(oracle):
+    """bench recipe (main.swift:267-268,535-548): n=5000, d=384, nlist=64, nprobe=4, q=200, k=10, seeds
+    123/321; IVFIndex.optimize (sorted String ids, k-means++ seed 42, mini-batch 1024 x 20 epochs) +
+    search; published recallAvg = 0.9565000000000008 (.bench/post-phase3/ivf_search.json:54)."""
+    n, d, nq, k, nlist, nprobe = 5000, 384, 200, 10, 64, 4
+    base = datagen.bench_vectors(n, d, 123)
+    qs = datagen.bench_vectors(nq, d, 321)
+    order = sorted(range(n), key=lambda i: "id%d" % i)          # IVFIndex.swift:325
+    xs = base[order]
+    cents, _ = oracle.kmeanspp_seed(xs, nlist, seed=42)
+    rc, cents, asg, info = oracle.kmeans_minibatch(xs, nlist, init=cents, batch_size=1024, epochs=20, tol=1e-4,
+                                                   seed=42, compute_assignments=True)
+    assert rc == 0 and info["epochs"] == 2
+    assert info["empties"].tolist() == [0, 1, 11, 34, 46, 53, 54, 57, 58, 58]
+    sizes = np.bincount(asg, minlength=nlist)
+    assert sorted(sizes[sizes > 0].tolist(), reverse=True) == [1748, 1450, 1316, 301, 148, 36, 1]
+
+    def seqdist(q, X):                                            # sequential fp32 sum (stands in for VectorCore)
+        acc = np.zeros(X.shape[0], dtype=np.float32)
+        for j in range(X.shape[1]):
+            df = (q[j] - X[:, j]).astype(np.float32)
+            acc = (acc + df * df).astype(np.float32)
+        return acc
+
+    rec, ncand = [], []
+    for qi in range(nq):
+        q = qs[qi]
+        sc = oracle.l2sqr_block(q, cents)                         # single-query path: L2Sqr dot-trick (d >= 256)
+        probes = sorted(range(nlist), key=lambda c: (sc[c], c))[:nprobe]      # IVFIndex.swift:593-595
+        idx = np.nonzero(np.isin(asg, probes))[0]
+        ncand.append(idx.size)
+        dd = seqdist(q, xs[idx])
+        top = idx[np.lexsort((idx, dd))[:k]]
+        bf = seqdist(q, xs)
+        gt = np.lexsort((np.arange(n), bf))[:k]
+        rec.append(len(set(top.tolist()) & set(gt.tolist())) / k)
+    s = 0.0
+    for r in rec:
+        s += r
+    assert repr(s / nq) == "0.9565000000000008"
+    assert abs(np.mean(ncand) - 4680.8) < 0.05
+
+
+def test_topk_max_tie_pin(oracle):
+    """TelemetryRecorderTests.swift:229-241: top-3 .max of [5,3,8,1,9] with ids 10..14."""
+    s, i = oracle.select_topk(np.array([5, 3, 8, 1, 9], dtype=np.float32), 3, oracle.ORDER_MAX,
+                              ids=np.arange(10, 15, dtype=np.int32))
+    assert s.tolist() == [9, 8, 5] and i.tolist() == [14, 12, 10]
+
+
+def test_probe_identical_centroids_pin(oracle):
+    """IVFSelectTests.swift:305-347: 50 identical centroids => ids 0..19 in order."""
+    cents = np.ones((50, 8), dtype=np.float32)
+    q = np.zeros((1, 8), dtype=np.float32)
+    idx, _ = oracle.probe_select_batch(q, cents, 20)
+    assert idx[0].tolist() == list(range(20))
+
+
+def test_topk_min_tie_smaller_id(oracle):
+    s, i = oracle.select_topk(np.array([1, 0, 0, 0, 2], dtype=np.float32), 2, oracle.ORDER_MIN)
+    assert i.tolist() == [1, 2]
+    ms, mi = oracle.merge_topk([(np.array([0.0, 1.0], np.float32), np.array([7, 1], np.int32)),
+                                (np.array([0.0, 0.5], np.float32), np.array([3, 9], np.int32))], 3)
+    assert mi.tolist() == [3, 7, 9]

@@ -1,0 +1,1002 @@
+// vix_index.cu -- device-resident index handles (Flat, IVF-Flat, IVF-PQ) and the fused IVF-PQ search.
+//
+// Search pipeline of an IVF-PQ index (the composition of /root/reference/docs/kernel-specs/
+// DONE_22_adc_scan.md:831-881: ivf_select_nprobe -> pq_lut_residual_l2 -> adc_scan_u8 -> selectTopK
+// -> mergeTopK), restructured for B200:
+//
+//   1. probe selection   probe_select_device (vix_scoring.cu) / the tcgen05 path (vix_gemm.cu)
+//   2. ivfpq_scan_kernel one persistent CTA per query at a time:
+//        - builds ONE query-only table  T[j][c] = -2 <q_j, cb_j[c]>   (IP: <q_j, cb_j[c]>)
+//          instead of one residual LUT per probed list.  With x^ = c_l + r^ (r^ = decoded residual):
+//             ||q - x^||^2 = ||q - c_l||^2  +  (||r^||^2 + 2 <c_l, r^>)  -  2 <q, r^>
+//                            bias (per probe)   t_x (per stored vector,       sum_j T[j][code_j]
+//                                                  precomputed at add time)
+//          which is algebraically the reference's sum_j ||(q - c_l)_j - cb_j[code_j]||^2 (PQLUT.swift:
+//          266-386 + ADCScan.swift:244-279) and agrees with it to fp32 rounding (tolerance 1e-5, tested).
+//        - streams the probed lists' codes with 128-bit loads (one stored vector per thread, 32-slot
+//          aligned chunks per warp) and looks the m codes up in shared memory;
+//        - selects the k best in per-warp shared-memory queues keyed (score, id) and merges the
+//          warps' queues at the end of the query: no distance array ever reaches HBM.
+//
+// Shared-memory bank conflicts are removed by construction: the table is stored transposed,
+// T[c][rep][j] with a pitch that is a multiple of 32 words, so the bank of a lookup depends only on
+// (rep, j); codes are stored "rotated" -- byte i of slot g holds the code of sub-quantiser
+// (i & ~15) | ((i ^ g) & 15) -- so the 16 lanes of a half-warp (16 consecutive slots) always ask for
+// 16 different j, and the two half-warps use the two replicas (rep).  Every warp-wide lookup is a
+// single conflict-free wavefront whatever the codes are.
+#include "vix_common.cuh"
+#include "vix_topk.cuh"
+#include "vix_exact.cuh"
+
+#include <cub/cub.cuh>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace vix {
+
+// entry points of the other translation units
+int pq_encode_device(const float* x, int64_t n, int d, int m, int ks, const float* cb, const float* csq,
+                     const float* coarse, const int32_t* assign, uint8_t* codes, int use_dot, int layout,
+                     int B, int g, int u4);
+int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                       const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
+int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
+                        const float* cnorm, const uint64_t* disabled, int32_t* out_idx, float* out_scores);
+int ivf_assign_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
+int ivf_assign_metric_device(const float* x, int64_t n, int d, const float* c, int kc, int metric,
+                             const float* cnorm, int32_t* assign);
+int row_norms_device(const float* x, int64_t n, int d, float* out);
+int train_coarse_device(const float* x, int64_t n, int d, int kc, int metric, const vix_kmeans_cfg* cfg,
+                        float* centroids_out);
+int train_pq_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
+                    const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
+int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
+                             const float* cnorm, int32_t* out_idx, float* out_scores);
+
+// ------------------------------------------------------------------------------------------------
+// growable device buffer
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t size = 0, cap = 0;
+    int reserve(size_t n, bool keep) {
+        if (n <= cap) return VIX_OK;
+        size_t ncap = cap ? cap : 1024;
+        while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+        T* np = nullptr;
+        VIX_CUDA(cudaMalloc(reinterpret_cast<void**>(&np), ncap * sizeof(T)));
+        if (keep && ptr && size)
+            VIX_CUDA(cudaMemcpyAsync(np, ptr, size * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
+        if (ptr) { VIX_CUDA(cudaStreamSynchronize(ctx().stream)); cudaFree(ptr); }
+        ptr = np; cap = ncap;
+        return VIX_OK;
+    }
+    int resize(size_t n, bool keep = true) {
+        VIX_TRY(reserve(n, keep));
+        size = n;
+        return VIX_OK;
+    }
+    int assign_from(const T* src, size_t n) {   // src: host or device
+        VIX_TRY(resize(n, false));
+        if (n) VIX_CUDA(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyDefault, ctx().stream));
+        return VIX_OK;
+    }
+    void free_all() { if (ptr) cudaFree(ptr); ptr = nullptr; size = cap = 0; }
+    ~DevBuf() { free_all(); }
+};
+
+}  // namespace vix
+
+using namespace vix;
+
+struct vix_index {
+    vix_index_params p;
+    std::mutex mu;
+    int kc = 0;                         // trained coarse centroids (nlist clamped to the training set)
+    DevBuf<float> coarse, coarse_norms; // [kc x d], Norms.l2NormSquared per row
+    DevBuf<float> codebooks, cb_norms;  // [m x ks x dsub], [m x ks]
+    bool has_coarse = false, has_pq = false;
+    // rows in add order
+    int64_t n = 0;
+    DevBuf<float> vecs;                 // FLAT / IVF_FLAT: [n x d]
+    DevBuf<int64_t> ids;                // [n]
+    DevBuf<int32_t> assign;             // IVF: [n]
+    DevBuf<uint8_t> codes;              // IVF_PQ: [n x m] AoS (the reference's interchange format)
+    // inverted lists, rebuilt lazily after adds ("slots": rows sorted by list, list starts 32-aligned)
+    bool dirty = true;
+    int64_t nslots = 0;
+    DevBuf<int64_t> list_off;           // [kc + 1] slot offsets (32-aligned)
+    DevBuf<int32_t> list_len;           // [kc]
+    DevBuf<int32_t> slot_row;           // [nslots] add-order row of a slot, -1 for padding
+    DevBuf<uint8_t> slot_codes;         // [nslots x m] rotated codes
+    DevBuf<float> slot_tx;              // [nslots]  ||r^||^2 + 2<c, r^>  (L2) / 0 (IP)
+    DevBuf<int64_t> slot_ids;           // [nslots]
+    DevBuf<float> slot_vecs;            // IVF_FLAT: [nslots x d]
+    int rot = 1;                        // 16 when m % 16 == 0 (conflict-free layout), else 1
+};
+
+namespace vix {
+
+// ------------------------------------------------------------------------------------------------
+// list building
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(int32_t* a, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int32_t)i;
+}
+
+__global__ void hist_kernel(const int32_t* __restrict__ assign, int64_t n, int kc, int32_t* __restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int a = assign[i];
+        if (a >= 0 && a < kc) atomicAdd(len + a, 1);
+    }
+}
+
+// single CTA: off[l+1] = off[l] + roundup32(len[l]); also unpadded offsets (CSR of the sorted rows)
+__global__ void offsets_kernel(const int32_t* __restrict__ len, int kc, int64_t* __restrict__ off,
+                               int64_t* __restrict__ off_raw) {
+    __shared__ int64_t s_pad[1024], s_raw[1024];
+    __shared__ int64_t carry_pad, carry_raw;
+    if (threadIdx.x == 0) { carry_pad = 0; carry_raw = 0; off[0] = 0; off_raw[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < kc; base += 1024) {
+        int l = base + threadIdx.x;
+        int64_t v = (l < kc) ? len[l] : 0;
+        int64_t vp = (v + 31) & ~31LL;
+        s_pad[threadIdx.x] = vp; s_raw[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {     // Hillis-Steele inclusive scan
+            int64_t a = 0, b = 0;
+            if ((int)threadIdx.x >= o) { a = s_pad[threadIdx.x - o]; b = s_raw[threadIdx.x - o]; }
+            __syncthreads();
+            s_pad[threadIdx.x] += a; s_raw[threadIdx.x] += b;
+            __syncthreads();
+        }
+        if (l < kc) { off[l + 1] = carry_pad + s_pad[threadIdx.x]; off_raw[l + 1] = carry_raw + s_raw[threadIdx.x]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_pad += s_pad[1023]; carry_raw += s_raw[1023]; }
+        __syncthreads();
+    }
+}
+
+// slot_row[off[l] + r] = sorted_rows[off_raw[l] + r]
+__global__ void place_rows_kernel(const int32_t* __restrict__ sorted_rows, const int32_t* __restrict__ sorted_lists,
+                                  int64_t n, const int64_t* __restrict__ off, const int64_t* __restrict__ off_raw,
+                                  int32_t* __restrict__ slot_row) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = sorted_lists[i];
+    slot_row[off[l] + (i - off_raw[l])] = sorted_rows[i];
+}
+
+// Fill one slot: rotated codes, id, t_x.  One warp per slot (lanes split the sub-quantisers).
+__global__ void __launch_bounds__(256)
+fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const uint8_t* __restrict__ codes,
+                     const int64_t* __restrict__ ids, const int32_t* __restrict__ assign,
+                     const float* __restrict__ coarse, const float* __restrict__ codebooks, int d, int m, int ks,
+                     int rot, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
+                     float* __restrict__ slot_tx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= nslots) return;
+    const int row = slot_row[g];
+    const int dsub = d / m;
+    if (row < 0) {
+        for (int i = lane; i < m; i += 32) slot_codes[g * (int64_t)m + i] = 0;
+        if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
+        return;
+    }
+    const uint8_t* src = codes + (int64_t)row * m;
+    const float* c = coarse + (int64_t)assign[row] * d;
+    double acc = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const int j = (rot > 1) ? ((i & ~(rot - 1)) | ((i ^ (int)(g & (rot - 1))) & (rot - 1))) : i;
+        slot_codes[g * (int64_t)m + i] = src[j];
+    }
+    if (metric == VIX_METRIC_L2) {
+        for (int j = lane; j < m; j += 32) {
+            const float* cw = codebooks + ((size_t)j * ks + src[j]) * dsub;
+            const float* cj = c + (size_t)j * dsub;
+            for (int e = 0; e < dsub; ++e) {
+                double r = (double)cw[e];
+                acc += r * r + 2.0 * (double)cj[e] * r;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    }
+    if (lane == 0) { slot_ids[g] = ids[row]; slot_tx[g] = (float)acc; }
+}
+
+__global__ void fill_slots_flat_kernel(const int32_t* __restrict__ slot_row, int64_t nslots,
+                                       const float* __restrict__ vecs, const int64_t* __restrict__ ids, int d,
+                                       float* __restrict__ slot_vecs, int64_t* __restrict__ slot_ids) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= nslots) return;
+    const int row = slot_row[g];
+    for (int e = lane; e < d; e += 32) slot_vecs[g * (int64_t)d + e] = row >= 0 ? vecs[(int64_t)row * d + e] : 0.0f;
+    if (lane == 0) slot_ids[g] = row >= 0 ? ids[row] : -1;
+}
+
+static int build_lists(vix_index* h) {
+    const int kc = h->kc;
+    const int64_t n = h->n;
+    cudaStream_t s = ctx().stream;
+    VIX_TRY(h->list_len.resize((size_t)kc, false));
+    VIX_TRY(h->list_off.resize((size_t)kc + 1, false));
+    VIX_CUDA(cudaMemsetAsync(h->list_len.ptr, 0, (size_t)kc * 4, s));
+    Scratch<int64_t> off_raw;
+    VIX_TRY(off_raw.alloc((size_t)kc + 1));
+    if (n > 0) {
+        hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->assign.ptr, n, kc, h->list_len.ptr);
+        VIX_LAUNCH_CHECK();
+    }
+    offsets_kernel<<<1, 1024, 0, s>>>(h->list_len.ptr, kc, h->list_off.ptr, off_raw.ptr);
+    VIX_LAUNCH_CHECK();
+    int64_t nslots = 0;
+    VIX_CUDA(cudaMemcpyAsync(&nslots, h->list_off.ptr + kc, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    h->nslots = nslots;
+    VIX_TRY(h->slot_row.resize((size_t)nslots, false));
+    VIX_TRY(h->slot_ids.resize((size_t)nslots, false));
+    if (nslots > 0) VIX_CUDA(cudaMemsetAsync(h->slot_row.ptr, 0xFF, (size_t)nslots * 4, s));
+    if (n > 0) {
+        // stable sort of rows by list: radix sort over the list-id bits
+        Scratch<int32_t> rows_in, rows_out, lists_out;
+        VIX_TRY(rows_in.alloc((size_t)n));
+        VIX_TRY(rows_out.alloc((size_t)n));
+        VIX_TRY(lists_out.alloc((size_t)n));
+        iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows_in.ptr, n);
+        VIX_LAUNCH_CHECK();
+        int bits = 1;
+        while ((1LL << bits) < kc) ++bits;
+        size_t tmp_bytes = 0;
+        VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->assign.ptr, lists_out.ptr, rows_in.ptr,
+                                                 rows_out.ptr, (int)n, 0, bits, s));
+        Scratch<unsigned char> tmp;
+        VIX_TRY(tmp.alloc(tmp_bytes + 16));
+        VIX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, h->assign.ptr, lists_out.ptr, rows_in.ptr,
+                                                 rows_out.ptr, (int)n, 0, bits, s));
+        ctx().launches += 1;
+        place_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows_out.ptr, lists_out.ptr, n, h->list_off.ptr,
+                                                                     off_raw.ptr, h->slot_row.ptr);
+        VIX_LAUNCH_CHECK();
+    }
+    if (h->p.kind == VIX_INDEX_IVF_PQ) {
+        const int m = h->p.m;
+        h->rot = (m % 16 == 0) ? 16 : 1;
+        VIX_TRY(h->slot_codes.resize((size_t)nslots * m + 16, false));
+        VIX_TRY(h->slot_tx.resize((size_t)nslots, false));
+        if (nslots > 0) {
+            int64_t threads = nslots * 32;
+            fill_slots_pq_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                h->slot_row.ptr, nslots, h->codes.ptr, h->ids.ptr, h->assign.ptr, h->coarse.ptr, h->codebooks.ptr,
+                h->p.d, m, h->p.ks, h->rot, h->p.metric, h->slot_codes.ptr, h->slot_ids.ptr, h->slot_tx.ptr);
+            VIX_LAUNCH_CHECK();
+        }
+    } else {
+        VIX_TRY(h->slot_vecs.resize((size_t)nslots * h->p.d, false));
+        if (nslots > 0) {
+            int64_t threads = nslots * 32;
+            fill_slots_flat_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                h->slot_row.ptr, nslots, h->vecs.ptr, h->ids.ptr, h->p.d, h->slot_vecs.ptr, h->slot_ids.ptr);
+            VIX_LAUNCH_CHECK();
+        }
+    }
+    h->dirty = false;
+    return VIX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused IVF-PQ scan
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+    const float* queries; int64_t nq; int d, m, ks, dsub;
+    const int32_t* probes; int nprobe;            // [nq x nprobe], -1 padded
+    const float* coarse;                          // [kc x d]
+    const float* codebooks;                       // [m x ks x dsub]
+    const int64_t* list_off; const int32_t* list_len;
+    const uint8_t* slot_codes; const float* slot_tx; const int64_t* slot_ids;
+    int metric, k, Pw, P2;
+    float* out_dist; int64_t* out_ids;            // [nq x k]
+    unsigned long long* scanned;                  // optional: total list entries visited
+};
+
+// (a & b) | c in one LOP3 (the compiler otherwise re-associates the OR into an IMAD)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+constexpr int kScanWarps = 8;
+constexpr int kScanThreads = kScanWarps * 32;
+
+// M16 = m / 16 (compile-time for the conflict-free layout); M16 == 0: generic m, plain [j][c] table.
+template <int M16>
+__global__ void __launch_bounds__(kScanThreads)
+ivfpq_scan_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = M16 > 0 ? 16 * M16 : a.m;
+    const int pitch = M16 > 0 ? 2 * m : 1;                      // floats per code row of the table
+    float* s_lut = reinterpret_cast<float*>(smem_raw);          // fast: [256][2][m] ; generic: [m][256]
+    float* s_q = s_lut + (M16 > 0 ? (size_t)256 * pitch : (size_t)m * 256);   // [d]
+    float* s_bias = s_q + a.d;                                  // [nprobe]
+    int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);   // [nprobe]   first slot / 32
+    int* s_len = s_start + a.nprobe;                            // [nprobe]
+    int* s_pref = s_len + a.nprobe;                             // [nprobe + 1] chunk prefix
+    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_pref + a.nprobe + 1) + 15) & ~(uintptr_t)15);
+    u64* s_merge = s_wq + (size_t)kScanWarps * a.Pw;            // [P2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int order_max = (a.metric == VIX_METRIC_IP);
+    const float lut_scale = order_max ? 1.0f : -2.0f;
+    u64* wq = s_wq + (size_t)warp * a.Pw;
+    unsigned long long scanned_local = 0;
+
+    // per-lane constants of the rotated layout
+    const int r16 = lane & 15, rep = lane >> 4;
+    int pre4[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) pre4[b] = 4 * (rep * m + ((b ^ r16) & 15));
+
+    for (int64_t qi = blockIdx.x; qi < a.nq; qi += gridDim.x) {
+        __syncthreads();   // previous query fully drained
+        // ---- prologue: query, probe table, bias, LUT ----
+        for (int e = tid; e < a.d; e += kScanThreads) s_q[e] = a.queries[qi * (int64_t)a.d + e];
+        if (tid < a.nprobe) {
+            const int l = a.probes[qi * (int64_t)a.nprobe + tid];
+            s_start[tid] = l >= 0 ? (int)(a.list_off[l] >> 5) : 0;
+            s_len[tid] = l >= 0 ? a.list_len[l] : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int p = 0; p < a.nprobe; ++p) { s_pref[p] = acc; acc += (s_len[p] + 31) >> 5; }
+            s_pref[a.nprobe] = acc;
+        }
+        for (int p = warp; p < a.nprobe; p += kScanWarps) {
+            const int l = a.probes[qi * (int64_t)a.nprobe + p];
+            float part = 0.0f;
+            if (l >= 0) {
+                const float* c = a.coarse + (int64_t)l * a.d;
+                if (order_max) for (int e = lane; e < a.d; e += 32) part = fmaf(s_q[e], c[e], part);
+                else for (int e = lane; e < a.d; e += 32) { float df = s_q[e] - c[e]; part = fmaf(df, df, part); }
+            }
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+            if (lane == 0) s_bias[p] = part;
+        }
+        {
+            const int dsub = a.dsub;
+            const int total = m * 256;
+            for (int e = tid; e < total; e += kScanThreads) {
+                const int c = e / m, j = e - c * m;
+                const float* cw = a.codebooks + ((size_t)j * 256 + c) * dsub;
+                const float* qj = s_q + j * dsub;
+                float dot = 0.0f;
+                for (int t = 0; t < dsub; ++t) dot = fmaf(qj[t], __ldg(cw + t), dot);
+                const float v = lut_scale * dot;
+                if (M16 > 0) { s_lut[(size_t)c * pitch + j] = v; s_lut[(size_t)c * pitch + m + j] = v; }
+                else s_lut[(size_t)j * 256 + c] = v;
+            }
+        }
+        for (int i = lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
+        __syncthreads();
+
+        // ---- scan: warp-strided over 32-slot chunks of the probed lists ----
+        const int nchunks = s_pref[a.nprobe];
+        int cnt = 0;
+        float thr_s = order_max ? -INFINITY : INFINITY;
+        int p = 0;
+        for (int ch = warp; ch < nchunks; ch += kScanWarps) {
+            while (ch >= s_pref[p + 1]) ++p;
+            const int within = (ch - s_pref[p]) * 32 + lane;
+            const bool valid = within < s_len[p];
+            const int64_t g = ((int64_t)s_start[p] << 5) + within;
+            float sum = 0.0f;
+            if (M16 > 0) {
+                uint4 w[M16 > 0 ? M16 : 1];
+                const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + g * (int64_t)m);
+#pragma unroll
+                for (int c = 0; c < M16; ++c) w[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+                const float tx = valid ? __ldg(a.slot_tx + g) : 0.0f;
+                const char* lut_b = reinterpret_cast<const char*>(s_lut);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < M16; ++c) {
+                    const uint32_t ww[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint32_t x = ww[q4];
+                        const int b = 4 * q4;
+                        constexpr int pb = 4 * 2 * 16 * (M16 > 0 ? M16 : 1);   // bytes per code row
+                        constexpr bool pow2 = (pb & (pb - 1)) == 0;
+                        if (pow2) {
+                            // code * pb is a shifted byte and pre4 < pb: one shift + one LOP3 (and|or) per address
+                            constexpr int sh = (pb == 128) ? 7 : (pb == 256 ? 8 : 9);
+                            constexpr uint32_t mask = 0xFFu << sh;
+                            const uint32_t a0 = and_or(x << sh, mask, (uint32_t)pre4[b + 0]);
+                            const uint32_t a1 = and_or(sh >= 8 ? (x << (sh - 8)) : (x >> (8 - sh)), mask, (uint32_t)pre4[b + 1]);
+                            const uint32_t a2 = and_or(x >> (16 - sh), mask, (uint32_t)pre4[b + 2]);
+                            const uint32_t a3 = and_or(x >> (24 - sh), mask, (uint32_t)pre4[b + 3]);
+                            s0 += *reinterpret_cast<const float*>(lut_b + a0 + 64 * c);
+                            s1 += *reinterpret_cast<const float*>(lut_b + a1 + 64 * c);
+                            s2 += *reinterpret_cast<const float*>(lut_b + a2 + 64 * c);
+                            s3 += *reinterpret_cast<const float*>(lut_b + a3 + 64 * c);
+                        } else {
+                            s0 += *reinterpret_cast<const float*>(lut_b + (x & 0xFF) * pb + pre4[b + 0] + 64 * c);
+                            s1 += *reinterpret_cast<const float*>(lut_b + ((x >> 8) & 0xFF) * pb + pre4[b + 1] + 64 * c);
+                            s2 += *reinterpret_cast<const float*>(lut_b + ((x >> 16) & 0xFF) * pb + pre4[b + 2] + 64 * c);
+                            s3 += *reinterpret_cast<const float*>(lut_b + (x >> 24) * pb + pre4[b + 3] + 64 * c);
+                        }
+                    }
+                }
+                sum = (s_bias[p] + tx) + ((s0 + s1) + (s2 + s3));
+            } else {
+                const uint8_t* src = a.slot_codes + g * (int64_t)m;
+                float s0 = 0.f;
+                if (valid) for (int j = 0; j < m; ++j) s0 += s_lut[(size_t)j * 256 + src[j]];
+                const float tx = valid ? a.slot_tx[g] : 0.0f;
+                sum = (s_bias[p] + tx) + s0;
+            }
+            if (valid) ++scanned_local;
+            const bool pass = valid && (order_max ? !(sum < thr_s) : !(sum > thr_s));
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
+            if (ball) {
+                if (pass) {
+                    const uint32_t id = (uint32_t)a.slot_ids[g];
+                    wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = make_key(sum, id, order_max);
+                }
+                cnt += __popc(ball);
+                __syncwarp();
+                if (cnt + 32 > a.Pw - a.k) {
+                    for (int i = a.k + cnt + lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
+                    __syncwarp();
+                    bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
+                    cnt = 0;
+                    const u64 t = wq[a.k - 1];
+                    if (t != kEmptyKey) thr_s = key_score(t, order_max);
+                }
+            }
+        }
+        // ---- epilogue: flush warp queues, merge, write ----
+        if (cnt > 0) {
+            for (int i = a.k + cnt + lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
+            __syncwarp();
+            bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
+        }
+        __syncwarp();
+        for (int i = lane; i < a.k; i += 32) s_merge[warp * a.k + i] = wq[i];
+        for (int i = kScanWarps * a.k + tid; i < a.P2; i += kScanThreads) s_merge[i] = kEmptyKey;
+        __syncthreads();
+        bitonic_sort_keys<false>(s_merge, a.P2, tid, kScanThreads);
+        for (int i = tid; i < a.k; i += kScanThreads) {
+            const u64 key = s_merge[i];
+            const size_t o = (size_t)qi * a.k + i;
+            if (key == kEmptyKey) { a.out_dist[o] = __int_as_float(0x7fc00000); a.out_ids[o] = -1; }
+            else {
+                const float sc = key_score(key, order_max);
+                a.out_dist[o] = order_max ? -sc : sc;     // IP: API distance = -score (DistanceUtils.swift:40-46)
+                a.out_ids[o] = (int64_t)key_id(key);
+            }
+        }
+    }
+    if (a.scanned) {
+        for (int o = 16; o > 0; o >>= 1) scanned_local += __shfl_xor_sync(0xFFFFFFFFu, scanned_local, o);
+        if (lane == 0 && scanned_local) atomicAdd(a.scanned, scanned_local);
+    }
+}
+
+static size_t scan_smem_bytes(const ScanArgs& a, bool fast) {
+    size_t s = (fast ? (size_t)256 * 2 * a.m : (size_t)a.m * 256) * 4;
+    s += (size_t)a.d * 4 + (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16;
+    s += (size_t)kScanWarps * a.Pw * 8 + (size_t)a.P2 * 8;
+    return s;
+}
+
+static int launch_scan(ScanArgs& a) {
+    a.Pw = next_pow2(a.k + 32);
+    a.P2 = next_pow2(kScanWarps * a.k);
+    const bool fast = (a.m % 16 == 0) && (a.m / 16 >= 1) && (a.m / 16 <= 4);
+    const size_t smem = scan_smem_bytes(a, fast);
+    VIX_REQUIRE(smem <= 227 * 1024, VIX_ERR_UNSUPPORTED,
+                "ivfpq scan: m = %d, k = %d, nprobe = %d need %zu bytes of shared memory", a.m, a.k, a.nprobe, smem);
+    VIX_REQUIRE(a.nprobe <= kScanThreads, VIX_ERR_INVALID_K, "ivfpq scan: nprobe > %d", kScanThreads);
+    void (*kern)(ScanArgs) = nullptr;
+    if (!fast) kern = ivfpq_scan_kernel<0>;
+    else if (a.m == 16) kern = ivfpq_scan_kernel<1>;
+    else if (a.m == 32) kern = ivfpq_scan_kernel<2>;
+    else if (a.m == 48) kern = ivfpq_scan_kernel<3>;
+    else kern = ivfpq_scan_kernel<4>;
+    VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    VIX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)num_sms() * occ;
+    if (grid > a.nq) grid = a.nq;
+    kern<<<(unsigned)grid, kScanThreads, smem, ctx().stream>>>(a);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
+// IVF-Flat candidate scan (IVFIndex.swift:1023-1039): exact distance per candidate of the probed
+// lists in the reference's order (Direct16 / Ip4), API distance (sqrt / negate), (distance, id) order.
+__global__ void __launch_bounds__(256)
+ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const int32_t* __restrict__ probes,
+                    int nprobe, const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
+                    const float* __restrict__ slot_vecs, const int64_t* __restrict__ slot_ids, int metric, int k,
+                    int P, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    float* s_q = reinterpret_cast<float*>(keys + P);
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    for (int64_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < d; e += blockDim.x) s_q[e] = queries[qi * (int64_t)d + e];
+        BlockQueue q{keys, &s_cnt, &s_thr, k, P};
+        q.init();
+        for (int p = 0; p < nprobe; ++p) {
+            const int l = probes[qi * (int64_t)nprobe + p];
+            if (l < 0) continue;
+            const int64_t b = list_off[l];
+            const int len = list_len[l];
+            for (int base = 0; base < len; base += blockDim.x) {
+                q.flush_if_needed(blockDim.x);
+                const int i = base + threadIdx.x;
+                if (i < len) {
+                    const float* v = slot_vecs + (b + i) * (int64_t)d;
+                    float dist = (metric == VIX_METRIC_L2) ? __fsqrt_rn(exact_pair<SpecDirect16L2>(s_q, v, d))
+                                                           : -exact_pair<SpecIp4>(s_q, v, d);
+                    q.push(make_key(dist, (uint32_t)slot_ids[b + i], 0));
+                }
+            }
+        }
+        q.flush();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const u64 key = keys[i];
+            const size_t o = (size_t)qi * k + i;
+            if (key == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
+            else { out_dist[o] = key_score(key, 0); out_ids[o] = (int64_t)key_id(key); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side index logic
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_ids_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ ids,
+                                  int64_t* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rows[i] >= 0 ? ids[rows[i]] : -1;
+}
+
+// PQTrain.swift:299-307: centroid norms as a strictly sequential sum of squares
+__global__ void seq_norms_kernel(const float* __restrict__ c, int64_t rows, int dsub, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    float s = 0.0f;
+    for (int e = 0; e < dsub; ++e) s = __fadd_rn(s, __fmul_rn(c[i * dsub + e], c[i * dsub + e]));
+    out[i] = s;
+}
+
+static int check_ids_host(const int64_t* ids, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        VIX_REQUIRE(ids[i] >= 0 && ids[i] < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM,
+                    "ids must lie in [0, 2^32 - 1) (the reference's TopK id type is Int32, TopK.swift:59); got %lld",
+                    (long long)ids[i]);
+    return VIX_OK;
+}
+
+__global__ void iota64_kernel(int64_t* a, int64_t n, int64_t start) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = start + i;
+}
+
+static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, int64_t n) {
+    const int d = h->p.d;
+    cudaStream_t s = ctx().stream;
+    if (n == 0) return VIX_OK;
+    VIX_REQUIRE(h->n + n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "index shard limited to 2^31 - 1 rows");
+    if (h->p.kind != VIX_INDEX_FLAT)
+        VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "index_add: coarse quantiser not trained / set");
+    if (h->p.kind == VIX_INDEX_IVF_PQ)
+        VIX_REQUIRE(h->has_pq, VIX_ERR_NOT_TRAINED, "index_add: PQ codebooks not trained / set");
+    if (ids && !is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    if (!ids) VIX_REQUIRE(h->n + n < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM, "automatic ids exceed 2^32 - 1");
+
+    const int64_t n0 = h->n;
+    VIX_TRY(h->ids.resize((size_t)(n0 + n)));
+    if (ids) VIX_CUDA(cudaMemcpyAsync(h->ids.ptr + n0, ids, (size_t)n * 8, cudaMemcpyDefault, s));
+    else { iota64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->ids.ptr + n0, n, n0); VIX_LAUNCH_CHECK(); }
+
+    if (h->p.kind == VIX_INDEX_FLAT || h->p.kind == VIX_INDEX_IVF_FLAT) {
+        VIX_TRY(h->vecs.resize((size_t)(n0 + n) * d));
+        VIX_CUDA(cudaMemcpyAsync(h->vecs.ptr + (size_t)n0 * d, x, (size_t)n * d * 4, cudaMemcpyDefault, s));
+    }
+    if (h->p.kind != VIX_INDEX_FLAT) {
+        VIX_TRY(h->assign.resize((size_t)(n0 + n)));
+        if (h->p.kind == VIX_INDEX_IVF_PQ) VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->p.m));
+        // chunked so that host inputs of any size stage through a bounded device buffer
+        const int64_t chunk = 1 << 20;
+        Scratch<float> stage;
+        const bool host_x = !is_device_ptr(x);
+        if (host_x && h->p.kind == VIX_INDEX_IVF_PQ) VIX_TRY(stage.alloc((size_t)(n < chunk ? n : chunk) * d));
+        for (int64_t b = 0; b < n; b += chunk) {
+            const int64_t cn = (n - b < chunk) ? (n - b) : chunk;
+            const float* xc;
+            if (h->p.kind == VIX_INDEX_IVF_FLAT) xc = h->vecs.ptr + (size_t)(n0 + b) * d;
+            else if (host_x) {
+                VIX_CUDA(cudaMemcpyAsync(stage.ptr, x + (size_t)b * d, (size_t)cn * d * 4, cudaMemcpyHostToDevice, s));
+                xc = stage.ptr;
+            } else xc = x + (size_t)b * d;
+            int32_t* ac = h->assign.ptr + n0 + b;
+            // list assignment: euclidean => _vi_km12_assignAOS (IVFIndex.swift:362-375);
+            // dot product => first-min of the CentroidBatchScore row (IVFIndex.swift:376-435)
+            if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_device(xc, cn, d, h->coarse.ptr, h->kc, ac, nullptr));
+            else VIX_TRY(ivf_assign_metric_device(xc, cn, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, ac));
+            if (h->p.kind == VIX_INDEX_IVF_PQ) {
+                // pq_encode_residual_u8_f32 with default opts => C ..._with_csq (PQEncode.swift:247-286)
+                VIX_TRY(pq_encode_device(xc, cn, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr,
+                                         ac, h->codes.ptr + (size_t)(n0 + b) * h->p.m, 1, PQ_LAYOUT_AOS, 64, 8, 0));
+            }
+        }
+    }
+    h->n = n0 + n;
+    h->dirty = true;
+    return finish(true);
+}
+
+static int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
+                               int64_t* out_ids, int32_t* out_probes, vix_search_stats* stats) {
+    const int d = h->p.d;
+    cudaStream_t s = ctx().stream;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (k <= 0 || nq <= 0) return VIX_OK;                      // IVFIndex.swift:866
+    VIX_REQUIRE(queries && out_dist && out_ids, VIX_ERR_NULL_PTR, "index_search: null pointer");
+    VIX_REQUIRE(k <= VIX_MAX_K, VIX_ERR_INVALID_K, "index_search: k > %d", VIX_MAX_K);
+    In<float> dq;
+    Out<float> dd;
+    Out<int64_t> di;
+    Out<int32_t> dp;
+    VIX_TRY(dq.stage(queries, (size_t)nq * d));
+    VIX_TRY(dd.stage(out_dist, (size_t)nq * k));
+    VIX_TRY(di.stage(out_ids, (size_t)nq * k));
+
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (stats) for (auto& e : ev) VIX_CUDA(cudaEventCreate(&e));
+    if (stats) VIX_CUDA(cudaEventRecord(ev[0], s));
+
+    if (h->p.kind == VIX_INDEX_FLAT || !h->has_coarse) {
+        // un-optimised IVF => linear scan (IVFIndex.swift:820-832)
+        VIX_REQUIRE(h->p.kind != VIX_INDEX_IVF_PQ, VIX_ERR_NOT_TRAINED, "index_search: IVF-PQ index is not trained");
+        Scratch<int64_t> rows;
+        VIX_TRY(rows.alloc((size_t)nq * k));
+        VIX_TRY(flat_search_device(dq.dev, nq, h->vecs.ptr, h->n, d, h->p.metric, k, nullptr, dd.dev, rows.ptr, false));
+        // row index -> user id
+        gather_ids_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, s>>>(rows.ptr, h->ids.ptr, di.dev, nq * (int64_t)k);
+        VIX_LAUNCH_CHECK();
+        if (stats) { VIX_CUDA(cudaEventRecord(ev[1], s)); VIX_CUDA(cudaEventRecord(ev[2], s)); }
+    } else {
+        if (nprobe <= 0) nprobe = h->p.nprobe;
+        VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "index_search: nprobe must be > 0");
+        if (h->dirty) VIX_TRY(build_lists(h));
+        VIX_TRY(dp.stage(out_probes, out_probes ? (size_t)nq * nprobe : 0));
+        Scratch<int32_t> probes;
+        int32_t* pp = dp.dev;
+        if (!pp) { VIX_TRY(probes.alloc((size_t)nq * nprobe)); pp = probes.ptr; }
+        VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
+                                         h->coarse_norms.ptr, pp, nullptr));
+        if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
+        Scratch<unsigned long long> scanned;
+        if (stats) { VIX_TRY(scanned.alloc(1)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 8, s)); }
+        if (h->p.kind == VIX_INDEX_IVF_PQ) {
+            ScanArgs a{};
+            a.queries = dq.dev; a.nq = nq; a.d = d; a.m = h->p.m; a.ks = h->p.ks; a.dsub = d / h->p.m;
+            a.probes = pp; a.nprobe = nprobe; a.coarse = h->coarse.ptr; a.codebooks = h->codebooks.ptr;
+            a.list_off = h->list_off.ptr; a.list_len = h->list_len.ptr;
+            a.slot_codes = h->slot_codes.ptr; a.slot_tx = h->slot_tx.ptr; a.slot_ids = h->slot_ids.ptr;
+            a.metric = h->p.metric; a.k = k; a.out_dist = dd.dev; a.out_ids = di.dev;
+            a.scanned = stats ? scanned.ptr : nullptr;
+            VIX_TRY(launch_scan(a));
+        } else {
+            const int P = next_pow2(k + 256);
+            const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+            VIX_CUDA(cudaFuncSetAttribute(ivfflat_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int64_t grid = (int64_t)num_sms() * 4;
+            if (grid > nq) grid = nq;
+            ivfflat_scan_kernel<<<(unsigned)grid, 256, smem, s>>>(dq.dev, nq, d, pp, nprobe, h->list_off.ptr,
+                                                                 h->list_len.ptr, h->slot_vecs.ptr, h->slot_ids.ptr,
+                                                                 h->p.metric, k, P, dd.dev, di.dev);
+            VIX_LAUNCH_CHECK();
+        }
+        if (stats) {
+            VIX_CUDA(cudaEventRecord(ev[2], s));
+            unsigned long long sc = 0;
+            VIX_CUDA(cudaMemcpyAsync(&sc, scanned.ptr, 8, cudaMemcpyDeviceToHost, s));
+            VIX_CUDA(cudaStreamSynchronize(s));
+            stats->codes_scanned = (int64_t)sc;
+            stats->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->p.m : d * 4);
+        }
+        VIX_TRY(dp.commit());
+    }
+    VIX_TRY(dd.commit());
+    VIX_TRY(di.commit());
+    int rc = finish(true);
+    if (stats) {
+        VIX_CUDA(cudaEventSynchronize(ev[2]));
+        cudaEventElapsedTime(&stats->ms_coarse, ev[0], ev[1]);
+        cudaEventElapsedTime(&stats->ms_scan, ev[1], ev[2]);
+        cudaEventElapsedTime(&stats->ms_total, ev[0], ev[2]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    return rc;
+}
+
+// gather rows of the sorted list layout back to add order / CSR export
+__global__ void export_lists_kernel(const int32_t* __restrict__ slot_row, const int64_t* __restrict__ off,
+                                    const int32_t* __restrict__ len, int kc, const uint8_t* __restrict__ codes,
+                                    const int64_t* __restrict__ ids, int m, int64_t* __restrict__ off_out,
+                                    uint8_t* __restrict__ codes_out, int64_t* __restrict__ ids_out,
+                                    const int64_t* __restrict__ off_raw) {
+    const int l = blockIdx.x;
+    if (l >= kc) return;
+    const int64_t b = off[l], o = off_raw[l];
+    for (int i = threadIdx.x; i < len[l]; i += blockDim.x) {
+        const int row = slot_row[b + i];
+        if (ids_out) ids_out[o + i] = ids[row];
+        if (codes_out) for (int j = 0; j < m; ++j) codes_out[(o + i) * (int64_t)m + j] = codes[(int64_t)row * m + j];
+    }
+    if (threadIdx.x == 0 && off_out) { off_out[l] = o; if (l == kc - 1) off_out[kc] = off_raw[kc]; }
+}
+
+__global__ void raw_offsets_kernel(const int32_t* __restrict__ len, int kc, int64_t* __restrict__ off_raw) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t acc = 0;
+        for (int l = 0; l < kc; ++l) { off_raw[l] = acc; acc += len[l]; }
+        off_raw[kc] = acc;
+    }
+}
+
+__global__ void expand_assign_kernel(const int64_t* __restrict__ off, int kc, int32_t* __restrict__ assign) {
+    const int l = blockIdx.x;
+    if (l >= kc) return;
+    for (int64_t i = off[l] + threadIdx.x; i < off[l + 1]; i += blockDim.x) assign[i] = l;
+}
+
+}  // namespace vix
+
+extern "C" {
+
+void vix_index_params_default(vix_index_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->kind = VIX_INDEX_IVF_PQ; p->d = 0; p->metric = VIX_METRIC_L2;
+    p->nlist = 256; p->nprobe = 8;           // IVFIndex.Configuration (IVFIndex.swift:15-22)
+    p->m = 16; p->ks = 256; p->shard_rank = 0; p->shard_world = 1;
+}
+
+int vix_index_create(const vix_index_params* p, vix_index_t** out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(p && out, VIX_ERR_NULL_PTR, "vix_index_create: null pointer");
+    VIX_REQUIRE(p->d > 0, VIX_ERR_INVALID_DIM, "vix_index_create: d must be > 0");
+    VIX_REQUIRE(p->kind >= VIX_INDEX_FLAT && p->kind <= VIX_INDEX_IVF_PQ, VIX_ERR_INVALID_PARAM, "vix_index_create: kind");
+    VIX_REQUIRE(p->metric == VIX_METRIC_L2 || p->metric == VIX_METRIC_IP, VIX_ERR_INVALID_PARAM,
+                "vix_index_create: metric must be L2 or IP");
+    if (p->kind != VIX_INDEX_FLAT) VIX_REQUIRE(p->nlist > 0, VIX_ERR_INVALID_K, "vix_index_create: nlist must be > 0");
+    if (p->kind == VIX_INDEX_IVF_PQ) {
+        VIX_REQUIRE(p->m > 0 && p->d % p->m == 0, VIX_ERR_INVALID_DIM, "vix_index_create: d %% m != 0");
+        VIX_REQUIRE(p->ks == 256, VIX_ERR_INVALID_K, "vix_index_create: ks must be 256");
+    }
+    vix_index* h = new (std::nothrow) vix_index();
+    VIX_REQUIRE(h, VIX_ERR_OOM, "vix_index_create: out of host memory");
+    h->p = *p;
+    if (h->p.nprobe <= 0) h->p.nprobe = 8;
+    *out = h;
+    return VIX_OK;
+}
+
+void vix_index_destroy(vix_index_t* h) {
+    if (!h) return;
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int vix_index_set_coarse(vix_index_t* h, const float* centroids, int kc) {
+    VIX_REQUIRE(h && centroids, VIX_ERR_NULL_PTR, "vix_index_set_coarse: null pointer");
+    VIX_REQUIRE(kc > 0, VIX_ERR_INVALID_K, "vix_index_set_coarse: kc must be > 0");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->n == 0, VIX_ERR_CONTRACT, "vix_index_set_coarse: index already holds vectors");
+    h->kc = kc;
+    VIX_TRY(h->coarse.assign_from(centroids, (size_t)kc * h->p.d));
+    VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
+    VIX_TRY(row_norms_device(h->coarse.ptr, kc, h->p.d, h->coarse_norms.ptr));   // IVFIndex.swift:470-485
+    h->has_coarse = true;
+    h->dirty = true;
+    return finish(true);
+}
+
+int vix_index_set_codebooks(vix_index_t* h, const float* codebooks, const float* centroid_norms) {
+    VIX_REQUIRE(h && codebooks, VIX_ERR_NULL_PTR, "vix_index_set_codebooks: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind == VIX_INDEX_IVF_PQ, VIX_ERR_INVALID_PARAM, "vix_index_set_codebooks: not an IVF-PQ index");
+    VIX_REQUIRE(h->n == 0, VIX_ERR_CONTRACT, "vix_index_set_codebooks: index already holds vectors");
+    const int m = h->p.m, ks = h->p.ks, dsub = h->p.d / m;
+    VIX_TRY(h->codebooks.assign_from(codebooks, (size_t)m * ks * dsub));
+    if (centroid_norms) VIX_TRY(h->cb_norms.assign_from(centroid_norms, (size_t)m * ks));
+    else {
+        // PQTrain.swift:299-307: sequential sum of squares per centroid
+        VIX_TRY(h->cb_norms.resize((size_t)m * ks, false));
+        seq_norms_kernel<<<(unsigned)((m * ks + 127) / 128), 128, 0, ctx().stream>>>(h->codebooks.ptr, (int64_t)m * ks, dsub,
+                                                                                      h->cb_norms.ptr);
+        VIX_LAUNCH_CHECK();
+    }
+    h->has_pq = true;
+    return finish(true);
+}
+
+int vix_index_get_coarse(vix_index_t* h, float* centroids_out, int* kc_out) {
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_get_coarse: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_get_coarse: not trained");
+    if (kc_out) *kc_out = h->kc;
+    if (centroids_out) {
+        VIX_CUDA(cudaMemcpyAsync(centroids_out, h->coarse.ptr, (size_t)h->kc * h->p.d * 4, cudaMemcpyDefault, ctx().stream));
+        return finish(true);
+    }
+    return VIX_OK;
+}
+
+int vix_index_get_codebooks(vix_index_t* h, float* codebooks_out, float* centroid_norms_out) {
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_get_codebooks: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->has_pq, VIX_ERR_NOT_TRAINED, "vix_index_get_codebooks: not trained");
+    const size_t cnt = (size_t)h->p.ks * h->p.d;
+    if (codebooks_out) VIX_CUDA(cudaMemcpyAsync(codebooks_out, h->codebooks.ptr, cnt * 4, cudaMemcpyDefault, ctx().stream));
+    if (centroid_norms_out)
+        VIX_CUDA(cudaMemcpyAsync(centroid_norms_out, h->cb_norms.ptr, (size_t)h->p.m * h->p.ks * 4, cudaMemcpyDefault,
+                                 ctx().stream));
+    return finish(true);
+}
+
+int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_cfg* kcfg, const vix_pq_train_cfg* pcfg) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && x, VIX_ERR_NULL_PTR, "vix_index_train: null pointer");
+    VIX_REQUIRE(n > 0, VIX_ERR_EMPTY_INPUT, "vix_index_train: empty training set");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->p.kind == VIX_INDEX_FLAT) return VIX_OK;
+    VIX_REQUIRE(h->n == 0, VIX_ERR_CONTRACT, "vix_index_train: index already holds vectors");
+    const int d = h->p.d;
+    In<float> dx;
+    VIX_TRY(dx.stage(x, (size_t)n * d));
+    const int kc = (int)(h->p.nlist < n ? h->p.nlist : n);          // nlist clamped to n (IVFIndex.swift:320)
+    VIX_TRY(h->coarse.resize((size_t)kc * d, false));
+    VIX_TRY(train_coarse_device(dx.dev, n, d, kc, h->p.metric, kcfg, h->coarse.ptr));
+    h->kc = kc;
+    VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
+    VIX_TRY(row_norms_device(h->coarse.ptr, kc, d, h->coarse_norms.ptr));
+    h->has_coarse = true;
+    if (h->p.kind == VIX_INDEX_IVF_PQ) {
+        Scratch<int32_t> asg;
+        VIX_TRY(asg.alloc((size_t)n));
+        if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_device(dx.dev, n, d, h->coarse.ptr, kc, asg.ptr, nullptr));
+        else VIX_TRY(ivf_assign_metric_device(dx.dev, n, d, h->coarse.ptr, kc, h->p.metric, nullptr, asg.ptr));
+        const int m = h->p.m, ks = h->p.ks;
+        VIX_TRY(h->codebooks.resize((size_t)ks * d, false));
+        VIX_TRY(h->cb_norms.resize((size_t)m * ks, false));
+        VIX_TRY(train_pq_device(dx.dev, n, d, m, ks, h->coarse.ptr, asg.ptr, pcfg, h->codebooks.ptr, h->cb_norms.ptr));
+        h->has_pq = true;
+    }
+    h->dirty = true;
+    return finish(true);
+}
+
+int vix_index_add(vix_index_t* h, const float* x, const int64_t* ids, int64_t n) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && (x || n == 0), VIX_ERR_NULL_PTR, "vix_index_add: null pointer");
+    VIX_REQUIRE(n >= 0, VIX_ERR_INVALID_PARAM, "vix_index_add: n < 0");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return index_add_locked(h, x, ids, n);
+}
+
+int vix_index_import_lists(vix_index_t* h, const int64_t* list_offsets, const uint8_t* codes, const int64_t* ids) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && list_offsets && codes && ids, VIX_ERR_NULL_PTR, "vix_index_import_lists: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind == VIX_INDEX_IVF_PQ, VIX_ERR_INVALID_PARAM, "vix_index_import_lists: not an IVF-PQ index");
+    VIX_REQUIRE(h->has_coarse && h->has_pq, VIX_ERR_NOT_TRAINED, "vix_index_import_lists: set coarse + codebooks first");
+    VIX_REQUIRE(!is_device_ptr(list_offsets), VIX_ERR_INVALID_PARAM, "vix_index_import_lists: list_offsets must be a host pointer");
+    const int kc = h->kc;
+    const int64_t n = list_offsets[kc];
+    VIX_REQUIRE(list_offsets[0] == 0 && n >= 0 && n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "vix_index_import_lists: bad offsets");
+    for (int l = 0; l < kc; ++l)
+        VIX_REQUIRE(list_offsets[l + 1] >= list_offsets[l], VIX_ERR_INVALID_PARAM, "vix_index_import_lists: offsets not monotone");
+    if (!is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    VIX_TRY(h->codes.assign_from(codes, (size_t)n * h->p.m));
+    VIX_TRY(h->ids.assign_from(ids, (size_t)n));
+    VIX_TRY(h->assign.resize((size_t)n, false));
+    Scratch<int64_t> doff;
+    VIX_TRY(doff.alloc((size_t)kc + 1));
+    VIX_CUDA(cudaMemcpyAsync(doff.ptr, list_offsets, (size_t)(kc + 1) * 8, cudaMemcpyHostToDevice, ctx().stream));
+    expand_assign_kernel<<<kc, 128, 0, ctx().stream>>>(doff.ptr, kc, h->assign.ptr);
+    VIX_LAUNCH_CHECK();
+    h->n = n;
+    h->dirty = true;
+    return finish(true);
+}
+
+int64_t vix_index_count(vix_index_t* h) {
+    if (!h) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return h->n;
+}
+
+int vix_index_list_sizes(vix_index_t* h, int64_t* sizes_out) {
+    VIX_REQUIRE(h && sizes_out, VIX_ERR_NULL_PTR, "vix_index_list_sizes: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_list_sizes: not trained");
+    if (h->dirty) VIX_TRY(build_lists(h));
+    std::vector<int32_t> len((size_t)h->kc);
+    VIX_CUDA(cudaMemcpyAsync(len.data(), h->list_len.ptr, (size_t)h->kc * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    VIX_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (int l = 0; l < h->kc; ++l) sizes_out[l] = len[l];
+    return VIX_OK;
+}
+
+int vix_index_export_lists(vix_index_t* h, int64_t* list_offsets, uint8_t* codes, int64_t* ids,
+                           int32_t* assignments_in_add_order) {
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_export_lists: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_export_lists: not trained");
+    if (h->dirty) VIX_TRY(build_lists(h));
+    const int kc = h->kc, m = h->p.m;
+    const int64_t n = h->n;
+    Scratch<int64_t> off_raw;
+    VIX_TRY(off_raw.alloc((size_t)kc + 1));
+    raw_offsets_kernel<<<1, 32, 0, ctx().stream>>>(h->list_len.ptr, kc, off_raw.ptr);
+    VIX_LAUNCH_CHECK();
+    Out<int64_t> doff, dids;
+    Out<uint8_t> dcodes;
+    VIX_TRY(doff.stage(list_offsets, list_offsets ? (size_t)kc + 1 : 0));
+    const bool want_codes = codes && h->p.kind == VIX_INDEX_IVF_PQ;
+    VIX_TRY(dcodes.stage(want_codes ? codes : nullptr, want_codes ? (size_t)n * m : 0));
+    VIX_TRY(dids.stage(ids, ids ? (size_t)n : 0));
+    export_lists_kernel<<<kc, 128, 0, ctx().stream>>>(h->slot_row.ptr, h->list_off.ptr, h->list_len.ptr, kc,
+                                                     h->codes.ptr, h->ids.ptr, m, doff.dev, dcodes.dev, dids.dev,
+                                                     off_raw.ptr);
+    VIX_LAUNCH_CHECK();
+    VIX_TRY(doff.commit());
+    VIX_TRY(dcodes.commit());
+    VIX_TRY(dids.commit());
+    if (assignments_in_add_order && n > 0)
+        VIX_CUDA(cudaMemcpyAsync(assignments_in_add_order, h->assign.ptr, (size_t)n * 4, cudaMemcpyDefault, ctx().stream));
+    return finish(true);
+}
+
+int vix_index_clear(vix_index_t* h) {
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_clear: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->n = 0;
+    h->vecs.size = h->ids.size = h->assign.size = h->codes.size = 0;
+    h->dirty = true;
+    return VIX_OK;
+}
+
+int vix_index_search(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
+                     int64_t* out_ids) {
+    return vix_index_search_ex(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr);
+}
+
+int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
+                        int64_t* out_ids, int32_t* out_probes, vix_search_stats* stats) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_search: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, out_probes, stats);
+}
+
+}  // extern "C"
