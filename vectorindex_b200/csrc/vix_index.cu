@@ -116,6 +116,9 @@ struct vix_index {
     DevBuf<int64_t> slot_ids;           // [nslots]
     DevBuf<float> slot_vecs;            // IVF_FLAT: [nslots x d]
     int rot = 1;                        // 16 when m % 16 == 0 (conflict-free layout), else 1
+    // search_ex(stats): events and counter are created once per handle
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    DevBuf<unsigned long long> scanned;
 };
 
 namespace vix {
@@ -667,8 +670,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
     VIX_TRY(dd.stage(out_dist, (size_t)nq * k));
     VIX_TRY(di.stage(out_ids, (size_t)nq * k));
 
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    if (stats) for (auto& e : ev) VIX_CUDA(cudaEventCreate(&e));
+    cudaEvent_t* ev = h->ev;
+    if (stats && !ev[0]) for (int e = 0; e < 3; ++e) VIX_CUDA(cudaEventCreate(&ev[e]));
     if (stats) VIX_CUDA(cudaEventRecord(ev[0], s));
 
     if (h->p.kind == VIX_INDEX_FLAT || !h->has_coarse) {
@@ -692,8 +695,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
                                          h->coarse_norms.ptr, pp, nullptr));
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
-        Scratch<unsigned long long> scanned;
-        if (stats) { VIX_TRY(scanned.alloc(1)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 8, s)); }
+        DevBuf<unsigned long long>& scanned = h->scanned;
+        if (stats) { VIX_TRY(scanned.resize(1, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 8, s)); }
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
             ScanArgs a{};
             a.queries = dq.dev; a.nq = nq; a.d = d; a.m = h->p.m; a.ks = h->p.ks; a.dsub = d / h->p.m;
@@ -732,7 +735,6 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         cudaEventElapsedTime(&stats->ms_coarse, ev[0], ev[1]);
         cudaEventElapsedTime(&stats->ms_scan, ev[1], ev[2]);
         cudaEventElapsedTime(&stats->ms_total, ev[0], ev[2]);
-        for (auto& e : ev) cudaEventDestroy(e);
     }
     return rc;
 }
@@ -803,6 +805,7 @@ int vix_index_create(const vix_index_params* p, vix_index_t** out) {
 void vix_index_destroy(vix_index_t* h) {
     if (!h) return;
     cudaDeviceSynchronize();
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
 }
 

@@ -243,31 +243,53 @@ class ShardedIVFPQIndex:
             idl = torch.as_tensor(idl, device=vectors.device)
         self.local.batch_insert(vectors[b:e], idl)
 
+    @classmethod
+    def wrap(cls, local_index, group=None):
+        """Sharded view over an already built per-rank IVFPQIndex."""
+        import torch.distributed as dist
+        self = cls.__new__(cls)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = local_index
+        return self
+
     def batch_search(self, queries, k, nprobe=0):
+        """Replicated queries -> local fused scan -> ONE all-gather of the packed per-rank (distance, id)
+        lists -> mergeTopK kernel.  Host (numpy) queries are staged to the device once and only the merged
+        [nq x k] result returns to the host."""
         import torch
         import torch.distributed as dist
-        d_loc, i_loc = self.local.batch_search(queries, k, nprobe)
         if self.world == 1:
-            return d_loc, i_loc
-        was_numpy = not _lib._is_torch(d_loc)
-        if was_numpy:
-            backend = dist.get_backend(self.group)
-            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-            d_loc = torch.from_numpy(d_loc).to(dev)
-            i_loc = torch.from_numpy(i_loc).to(dev)
+            return self.local.batch_search(queries, k, nprobe)
+        was_numpy = not _lib._is_torch(queries)
+        nccl = dist.get_backend(self.group) == "nccl"
+        if was_numpy and nccl:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            queries = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(dev, non_blocking=True)
+        d_loc, i_loc = self.local.batch_search(queries, k, nprobe)
+        md, mi = self.gather_merge(d_loc, i_loc, k)
+        if was_numpy and _lib._is_torch(md):
+            md, mi = md.cpu().numpy(), mi.cpu().numpy()
+        return md, mi
+
+    def gather_merge(self, d_loc, i_loc, k):
+        """all-gather + merge of per-rank [nq x k] results (torch tensors or numpy arrays)."""
+        import torch
+        import torch.distributed as dist
+        if not _lib._is_torch(d_loc):
+            d_loc, i_loc = torch.from_numpy(d_loc), torch.from_numpy(i_loc)
+            if dist.get_backend(self.group) == "nccl":
+                dev = torch.device("cuda", torch.cuda.current_device())
+                d_loc, i_loc = d_loc.to(dev), i_loc.to(dev)
         nq = d_loc.shape[0]
         d_all = torch.empty((self.world, nq, k), dtype=d_loc.dtype, device=d_loc.device)
         i_all = torch.empty((self.world, nq, k), dtype=i_loc.dtype, device=i_loc.device)
         dist.all_gather_into_tensor(d_all, d_loc.contiguous(), group=self.group)
         dist.all_gather_into_tensor(i_all, i_loc.contiguous(), group=self.group)
         if d_all.is_cuda:
-            md, mi = merge_shard_results(d_all, i_all, k)
-        else:
-            md, mi = merge_shard_results_host(d_all.numpy(), i_all.numpy(), k)
-        if was_numpy:
-            md = md.cpu().numpy() if _lib._is_torch(md) else md
-            mi = mi.cpu().numpy() if _lib._is_torch(mi) else mi
-        return md, mi
+            return merge_shard_results(d_all, i_all, k)
+        return merge_shard_results_host(d_all.numpy(), i_all.numpy(), k)
 
 
 def merge_shard_results_host(dist_all, ids_all, k):
