@@ -24,7 +24,6 @@ import ctypes as C
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -57,65 +56,63 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock + throttle reasons DURING the measured region, sampled by an `nvidia-smi -lms` child process
-    (the recipe of B200_PROFILING.md).  In-process NVML polling is avoided on purpose: every NVML query takes
-    the driver lock that kernel launches need and slowed a 6 ms step tenfold."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    """SM clock + throttle reasons DURING the timed region.  The K timed steps are enqueued asynchronously;
+    while the GPU works through them the host polls NVML from the main thread (a few samples, 10 ms apart).
+    NVML queries take the driver lock that CUDA API calls need, so polling from a second thread (or an
+    `nvidia-smi -lms` child) while the host is still launching stalls the launches -- measured: a 6 ms step
+    became 60 ms.  Polling only after everything is enqueued perturbs nothing."""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, device_index: int, period_ms: int = 100):
-        import subprocess
-        import tempfile
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = device_index
-        if vis:
-            parts = vis.split(",")
-            if device_index < len(parts) and parts[device_index].strip().isdigit():
-                phys = int(parts[device_index])
-        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, device_index: int):
+        self.clocks, self.power, self.reasons, self.max_mhz, self.nv = [], [], set(), None, None
+        if os.environ.get("VIX_BENCH_NO_CLOCKS"):
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(phys), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", str(period_ms)], stdout=self.out, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = device_index
+            if vis:
+                parts = vis.split(",")
+                if device_index < len(parts) and parts[device_index].strip().isdigit():
+                    phys = int(parts[device_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
         except Exception as e:  # noqa: BLE001
-            log(f"[bench] nvidia-smi unavailable: {e}")
+            log(f"[bench] NVML unavailable: {e}")
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.clocks.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            try:
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] NVML sample failed: {e}")
+
+    def poll_until(self, done, period_s=0.01, max_samples=64):
+        """Sample while `done()` is false (at least once)."""
+        self.sample()
+        while not done() and len(self.clocks) < max_samples:
+            time.sleep(period_s)
+            self.sample()
 
     def stop(self):
-        if self.p:
-            self.p.terminate()
-            try:
-                self.p.wait(timeout=5)
-            except Exception:  # noqa: BLE001
-                self.p.kill()
-            self.p = None
+        pass
 
     def summary(self):
-        self.stop()
-        clocks, power, reasons, mx = [], [], set(), None
-        try:
-            self.out.flush()
-            for ln in open(self.out.name):
-                f = [t.strip() for t in ln.split(",")]
-                if len(f) < 7 or not f[0].replace(".", "").isdigit():
-                    continue
-                clocks.append(float(f[0]))
-                mx = float(f[1])
-                try:
-                    power.append(float(f[2]))
-                except ValueError:
-                    pass
-                for name, v in zip(self.NAMES, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.out.name)
-        except Exception as e:  # noqa: BLE001
-            log(f"[bench] clock log unreadable: {e}")
-        # "under load" = samples taken while the GPU drew more than idle power
-        hot = [c for c, w in zip(clocks, power) if w > 250.0] if len(power) == len(clocks) else clocks
-        use = hot if hot else clocks
-        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(clocks), "samples_under_load": len(hot), "power_w_max": max(power) if power else None}
+        return {"sm_mhz": float(np.median(self.clocks)) if self.clocks else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.clocks),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------ data
@@ -282,6 +279,7 @@ def main():
     torch.cuda.set_stream(stream)
     _lib.check(L.vix_set_stream(C.c_void_p(stream.cuda_stream)))
 
+    clk = ClockSampler(local_rank)                                   # started early: see ClockSampler.summary
     synth = Synth(cfg, dev)
     eff_world = world if args.impl == "ours" else 1
     bcast = (lambda t: dist.broadcast(t, 0)) if dist else None
@@ -317,6 +315,7 @@ def main():
                 "config": base_cfg, "cpu_baseline": info,
                 "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
+        clk.stop()
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -331,7 +330,8 @@ def main():
     qp, dp, ip = _lib.ptr(q_dev), _lib.ptr(out_d), _lib.ptr(out_i)
 
     def step_device():
-        _lib.check(L.vix_index_search_ex(idx._h, qp, C.c_int64(nq), C.c_int(k), C.c_int(0), dp, ip, None, C.byref(st)))
+        # asynchronous: nothing here waits for the GPU (stage events are traced inside the library)
+        _lib.check(L.vix_index_search(idx._h, qp, C.c_int64(nq), C.c_int(k), C.c_int(0), dp, ip))
         if world == 1:
             return out_d, out_i
         dist.all_gather_into_tensor(all_d, out_d)
@@ -343,28 +343,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    clk = ClockSampler(local_rank)
     for _ in range(W):
         res_d, res_i = step_device()
     barrier()
+    _lib.check(L.vix_index_trace(idx._h, K))
     L.vix_kernel_launches(1)
-    scan_ms = coarse_ms = 0.0
-    scan_bytes = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profile:
         torch.cuda.profiler.start()
     e0.record()
     for _ in range(K):
         res_d, res_i = step_device()
-        scan_ms += st.ms_scan
-        coarse_ms += st.ms_coarse
-        scan_bytes += st.code_bytes_scanned
     e1.record()
+    clk.poll_until(e1.query)                                         # GPU still busy with the queued steps
     barrier()
     if args.profile:
         torch.cuda.profiler.stop()
     launches = int(L.vix_kernel_launches(0))
     ms_total = e0.elapsed_time(e1)
+    scan_ms = coarse_ms = 0.0
+    scan_bytes = 0
+    for i in range(K):
+        _lib.check(L.vix_index_trace_get(idx._h, i, C.byref(st)))
+        scan_ms += st.ms_scan
+        coarse_ms += st.ms_coarse
+        scan_bytes += st.code_bytes_scanned
+    _lib.check(L.vix_index_trace(idx._h, 0))
 
     # ---- end to end through the public API with pinned host buffers
     _lib.check(L.vix_set_async(0))
@@ -382,7 +386,6 @@ def main():
         h_d, h_i = api()
     barrier()
     e2e_s = (time.perf_counter() - t0) * (K if args.profile else 1)
-    clk.stop()
 
     times = torch.tensor([ms_total, e2e_s * 1e3, scan_ms, coarse_ms, float(scan_bytes)], dtype=torch.float64, device=dev)
     if dist:
@@ -409,6 +412,7 @@ def main():
     assert np.array_equal(np.asarray(h_i), res_i.cpu().numpy()), "host-path ids differ from the device-path ids"
 
     if rank != 0:
+        clk.stop()
         if dist:
             dist.barrier()
             dist.destroy_process_group()

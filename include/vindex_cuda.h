@@ -278,6 +278,13 @@ int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k,
                         float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,
                         vix_search_stats* stats /* nullable */);
 
+/* Stage timing without host synchronisation (bench / profiling): after vix_index_trace(h, capacity) the
+ * next `capacity` searches WITHOUT a stats struct record their stage events and scanned-code count on
+ * the stream and return asynchronously; vix_index_trace_get(h, i, &st) waits for call i and reads them
+ * back.  capacity 0 switches tracing off. */
+int vix_index_trace(vix_index_t* h, int capacity);
+int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out);
+
 /* a16  AccelerableIndex-shaped convenience (AccelerableIndex.swift:15-127): candidates [c x d]
  * contiguous in, (indices into candidates, distances) out, per query. */
 int vix_accel_rank_candidates_f32(const float* queries, int64_t nq, const float* candidates, int64_t c,

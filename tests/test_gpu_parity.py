@@ -315,7 +315,11 @@ def _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed, sift=False, unit=False):
 @pytest.mark.parametrize("n,d,m,kc,nprobe,metric,kind", [
     (20000, 128, 16, 64, 8, 0, "sift"),      # C3-shaped, fast path m=16
     (12000, 96, 48, 50, 6, 0, "unit"),       # C5-shaped, m=48 (dsub=2)
-    (8000, 64, 8, 30, 5, 0, "gauss"),        # generic m (not a multiple of 16)
+    (8000, 64, 8, 30, 5, 0, "gauss"),        # m=8: four vector blocks per warp pass
+    (6000, 48, 12, 20, 5, 0, "gauss"),       # generic m (not 32 F + {0, 8, 16}): AoS fallback kernel
+    (6000, 160, 80, 24, 5, 0, "gauss"),      # m=80 = 2 full passes + 16 left over (two 64 KB tables)
+    (6000, 192, 96, 24, 5, 1, "unit"),       # m=96 inner product
+    (5000, 256, 128, 16, 4, 0, "gauss"),     # m=128: largest table
     (8000, 128, 32, 40, 40, 0, "gauss"),     # nprobe == kc: exhaustive
     (9000, 128, 64, 32, 6, 1, "unit"),       # C4-shaped inner product, m=64
 ])

@@ -5,28 +5,16 @@
 // -> mergeTopK), restructured for B200:
 //
 //   1. probe selection   probe_select_device (vix_scoring.cu) / the tcgen05 path (vix_gemm.cu)
-//   2. ivfpq_scan_kernel one persistent CTA per query at a time:
-//        - builds ONE query-only table  T[j][c] = -2 <q_j, cb_j[c]>   (IP: <q_j, cb_j[c]>)
-//          instead of one residual LUT per probed list.  With x^ = c_l + r^ (r^ = decoded residual):
-//             ||q - x^||^2 = ||q - c_l||^2  +  (||r^||^2 + 2 <c_l, r^>)  -  2 <q, r^>
-//                            bias (per probe)   t_x (per stored vector,       sum_j T[j][code_j]
-//                                                  precomputed at add time)
-//          which is algebraically the reference's sum_j ||(q - c_l)_j - cb_j[code_j]||^2 (PQLUT.swift:
-//          266-386 + ADCScan.swift:244-279) and agrees with it to fp32 rounding (tolerance 1e-5, tested).
-//        - streams the probed lists' codes with 128-bit loads (one stored vector per thread, 32-slot
-//          aligned chunks per warp) and looks the m codes up in shared memory;
-//        - selects the k best in per-warp shared-memory queues keyed (score, id) and merges the
-//          warps' queues at the end of the query: no distance array ever reaches HBM.
+//   2. locality order    queries sorted by their first probed list (one small radix sort)
+//   3. fused scan        vix_ivfpq_scan.cu: query-only LUT + ADC over the probed lists + top-k
 //
-// Shared-memory bank conflicts are removed by construction: the table is stored transposed,
-// T[c][rep][j] with a pitch that is a multiple of 32 words, so the bank of a lookup depends only on
-// (rep, j); codes are stored "rotated" -- byte i of slot g holds the code of sub-quantiser
-// (i & ~15) | ((i ^ g) & 15) -- so the 16 lanes of a half-warp (16 consecutive slots) always ask for
-// 16 different j, and the two half-warps use the two replicas (rep).  Every warp-wide lookup is a
-// single conflict-free wavefront whatever the codes are.
+// This file owns the device-resident state: rows in add order (AoS codes, the reference's interchange
+// format) and the scan layout derived from them (lists padded to whole blocks of 32 vectors, codes
+// transposed inside each block, per-vector term t_x = ||r^||^2 + 2 <c, r^>).
 #include "vix_common.cuh"
 #include "vix_topk.cuh"
 #include "vix_exact.cuh"
+#include "vix_scan.cuh"
 
 #include <cub/cub.cuh>
 
@@ -111,14 +99,20 @@ struct vix_index {
     DevBuf<int64_t> list_off;           // [kc + 1] slot offsets (32-aligned)
     DevBuf<int32_t> list_len;           // [kc]
     DevBuf<int32_t> slot_row;           // [nslots] add-order row of a slot, -1 for padding
-    DevBuf<uint8_t> slot_codes;         // [nslots x m] rotated codes
+    DevBuf<uint8_t> slot_codes;         // [nslots x m] scan layout (vix_scan.cuh)
     DevBuf<float> slot_tx;              // [nslots]  ||r^||^2 + 2<c, r^>  (L2) / 0 (IP)
     DevBuf<int64_t> slot_ids;           // [nslots]
     DevBuf<float> slot_vecs;            // IVF_FLAT: [nslots x d]
-    int rot = 1;                        // 16 when m % 16 == 0 (conflict-free layout), else 1
+    DevBuf<float> codebooks_t;          // [ks x m x dsub] code-major copy of the codebooks
+    DevBuf<int> work_counter;           // scan work queue head
+    int align = 32;                     // list granularity in slots (ScanLayout::align)
     // search_ex(stats): events and counter are created once per handle
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> scanned;
+    // vix_index_trace(): per-call stage events recorded WITHOUT synchronising (read back afterwards)
+    std::vector<cudaEvent_t> trace_ev;  // 3 per traced call
+    DevBuf<unsigned long long> trace_scanned;
+    int trace_cap = 0, trace_n = 0;
 };
 
 namespace vix {
@@ -139,8 +133,8 @@ __global__ void hist_kernel(const int32_t* __restrict__ assign, int64_t n, int k
     }
 }
 
-// single CTA: off[l+1] = off[l] + roundup32(len[l]); also unpadded offsets (CSR of the sorted rows)
-__global__ void offsets_kernel(const int32_t* __restrict__ len, int kc, int64_t* __restrict__ off,
+// single CTA: off[l+1] = off[l] + roundup(len[l], align); also unpadded offsets (CSR of the sorted rows)
+__global__ void offsets_kernel(const int32_t* __restrict__ len, int kc, int align, int64_t* __restrict__ off,
                                int64_t* __restrict__ off_raw) {
     __shared__ int64_t s_pad[1024], s_raw[1024];
     __shared__ int64_t carry_pad, carry_raw;
@@ -149,7 +143,7 @@ __global__ void offsets_kernel(const int32_t* __restrict__ len, int kc, int64_t*
     for (int base = 0; base < kc; base += 1024) {
         int l = base + threadIdx.x;
         int64_t v = (l < kc) ? len[l] : 0;
-        int64_t vp = (v + 31) & ~31LL;
+        int64_t vp = (v + align - 1) / align * align;
         s_pad[threadIdx.x] = vp; s_raw[threadIdx.x] = v;
         __syncthreads();
         for (int o = 1; o < 1024; o <<= 1) {     // Hillis-Steele inclusive scan
@@ -176,30 +170,30 @@ __global__ void place_rows_kernel(const int32_t* __restrict__ sorted_rows, const
     slot_row[off[l] + (i - off_raw[l])] = sorted_rows[i];
 }
 
-// Fill one slot: rotated codes, id, t_x.  One warp per slot (lanes split the sub-quantisers).
+// Fill one slot: codes in the scan layout, id, t_x.  One warp per slot (lanes split the sub-quantisers).
+// transposed != 0: byte (j, v) of the 32-slot block at blk * 32 * m + j * 32 + v; else AoS rows.
 __global__ void __launch_bounds__(256)
 fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const uint8_t* __restrict__ codes,
                      const int64_t* __restrict__ ids, const int32_t* __restrict__ assign,
                      const float* __restrict__ coarse, const float* __restrict__ codebooks, int d, int m, int ks,
-                     int rot, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
+                     int transposed, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
                      float* __restrict__ slot_tx) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= nslots) return;
     const int row = slot_row[g];
     const int dsub = d / m;
+    uint8_t* dst = transposed ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) : slot_codes + g * (int64_t)m;
+    const int dstride = transposed ? 32 : 1;
     if (row < 0) {
-        for (int i = lane; i < m; i += 32) slot_codes[g * (int64_t)m + i] = 0;
+        for (int j = lane; j < m; j += 32) dst[(int64_t)j * dstride] = 0;
         if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
         return;
     }
     const uint8_t* src = codes + (int64_t)row * m;
     const float* c = coarse + (int64_t)assign[row] * d;
     double acc = 0.0;
-    for (int i = lane; i < m; i += 32) {
-        const int j = (rot > 1) ? ((i & ~(rot - 1)) | ((i ^ (int)(g & (rot - 1))) & (rot - 1))) : i;
-        slot_codes[g * (int64_t)m + i] = src[j];
-    }
+    for (int j = lane; j < m; j += 32) dst[(int64_t)j * dstride] = src[j];
     if (metric == VIX_METRIC_L2) {
         for (int j = lane; j < m; j += 32) {
             const float* cw = codebooks + ((size_t)j * ks + src[j]) * dsub;
@@ -238,7 +232,8 @@ static int build_lists(vix_index* h) {
         hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->assign.ptr, n, kc, h->list_len.ptr);
         VIX_LAUNCH_CHECK();
     }
-    offsets_kernel<<<1, 1024, 0, s>>>(h->list_len.ptr, kc, h->list_off.ptr, off_raw.ptr);
+    h->align = (h->p.kind == VIX_INDEX_IVF_PQ) ? scan_layout(h->p.m).align : 32;
+    offsets_kernel<<<1, 1024, 0, s>>>(h->list_len.ptr, kc, h->align, h->list_off.ptr, off_raw.ptr);
     VIX_LAUNCH_CHECK();
     int64_t nslots = 0;
     VIX_CUDA(cudaMemcpyAsync(&nslots, h->list_off.ptr + kc, 8, cudaMemcpyDeviceToHost, s));
@@ -271,14 +266,14 @@ static int build_lists(vix_index* h) {
     }
     if (h->p.kind == VIX_INDEX_IVF_PQ) {
         const int m = h->p.m;
-        h->rot = (m % 16 == 0) ? 16 : 1;
+        const int transposed = scan_layout(m).fast ? 1 : 0;
         VIX_TRY(h->slot_codes.resize((size_t)nslots * m + 16, false));
         VIX_TRY(h->slot_tx.resize((size_t)nslots, false));
         if (nslots > 0) {
             int64_t threads = nslots * 32;
             fill_slots_pq_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
                 h->slot_row.ptr, nslots, h->codes.ptr, h->ids.ptr, h->assign.ptr, h->coarse.ptr, h->codebooks.ptr,
-                h->p.d, m, h->p.ks, h->rot, h->p.metric, h->slot_codes.ptr, h->slot_ids.ptr, h->slot_tx.ptr);
+                h->p.d, m, h->p.ks, transposed, h->p.metric, h->slot_codes.ptr, h->slot_ids.ptr, h->slot_tx.ptr);
             VIX_LAUNCH_CHECK();
         }
     } else {
@@ -295,234 +290,30 @@ static int build_lists(vix_index* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The fused IVF-PQ scan
+// query order for the scan: work item -> query, sorted by first probed list (L2 locality)
 // ------------------------------------------------------------------------------------------------
-struct ScanArgs {
-    const float* queries; int64_t nq; int d, m, ks, dsub;
-    const int32_t* probes; int nprobe;            // [nq x nprobe], -1 padded
-    const float* coarse;                          // [kc x d]
-    const float* codebooks;                       // [m x ks x dsub]
-    const int64_t* list_off; const int32_t* list_len;
-    const uint8_t* slot_codes; const float* slot_tx; const int64_t* slot_ids;
-    int metric, k, Pw, P2;
-    float* out_dist; int64_t* out_ids;            // [nq x k]
-    unsigned long long* scanned;                  // optional: total list entries visited
-};
-
-// (a & b) | c in one LOP3 (the compiler otherwise re-associates the OR into an IMAD)
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+__global__ void first_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe,
+                                   int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { const int l = probes[i * nprobe]; keys[i] = l < 0 ? 0x7FFFFFFF : l; vals[i] = (int32_t)i; }
 }
 
-constexpr int kScanWarps = 8;
-constexpr int kScanThreads = kScanWarps * 32;
-
-// M16 = m / 16 (compile-time for the conflict-free layout); M16 == 0: generic m, plain [j][c] table.
-template <int M16>
-__global__ void __launch_bounds__(kScanThreads)
-ivfpq_scan_kernel(ScanArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int m = M16 > 0 ? 16 * M16 : a.m;
-    const int pitch = M16 > 0 ? 2 * m : 1;                      // floats per code row of the table
-    float* s_lut = reinterpret_cast<float*>(smem_raw);          // fast: [256][2][m] ; generic: [m][256]
-    float* s_q = s_lut + (M16 > 0 ? (size_t)256 * pitch : (size_t)m * 256);   // [d]
-    float* s_bias = s_q + a.d;                                  // [nprobe]
-    int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);   // [nprobe]   first slot / 32
-    int* s_len = s_start + a.nprobe;                            // [nprobe]
-    int* s_pref = s_len + a.nprobe;                             // [nprobe + 1] chunk prefix
-    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_pref + a.nprobe + 1) + 15) & ~(uintptr_t)15);
-    u64* s_merge = s_wq + (size_t)kScanWarps * a.Pw;            // [P2]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int order_max = (a.metric == VIX_METRIC_IP);
-    const float lut_scale = order_max ? 1.0f : -2.0f;
-    u64* wq = s_wq + (size_t)warp * a.Pw;
-    unsigned long long scanned_local = 0;
-
-    // per-lane constants of the rotated layout
-    const int r16 = lane & 15, rep = lane >> 4;
-    int pre4[16];
-#pragma unroll
-    for (int b = 0; b < 16; ++b) pre4[b] = 4 * (rep * m + ((b ^ r16) & 15));
-
-    for (int64_t qi = blockIdx.x; qi < a.nq; qi += gridDim.x) {
-        __syncthreads();   // previous query fully drained
-        // ---- prologue: query, probe table, bias, LUT ----
-        for (int e = tid; e < a.d; e += kScanThreads) s_q[e] = a.queries[qi * (int64_t)a.d + e];
-        if (tid < a.nprobe) {
-            const int l = a.probes[qi * (int64_t)a.nprobe + tid];
-            s_start[tid] = l >= 0 ? (int)(a.list_off[l] >> 5) : 0;
-            s_len[tid] = l >= 0 ? a.list_len[l] : 0;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int p = 0; p < a.nprobe; ++p) { s_pref[p] = acc; acc += (s_len[p] + 31) >> 5; }
-            s_pref[a.nprobe] = acc;
-        }
-        for (int p = warp; p < a.nprobe; p += kScanWarps) {
-            const int l = a.probes[qi * (int64_t)a.nprobe + p];
-            float part = 0.0f;
-            if (l >= 0) {
-                const float* c = a.coarse + (int64_t)l * a.d;
-                if (order_max) for (int e = lane; e < a.d; e += 32) part = fmaf(s_q[e], c[e], part);
-                else for (int e = lane; e < a.d; e += 32) { float df = s_q[e] - c[e]; part = fmaf(df, df, part); }
-            }
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-            if (lane == 0) s_bias[p] = part;
-        }
-        {
-            const int dsub = a.dsub;
-            const int total = m * 256;
-            for (int e = tid; e < total; e += kScanThreads) {
-                const int c = e / m, j = e - c * m;
-                const float* cw = a.codebooks + ((size_t)j * 256 + c) * dsub;
-                const float* qj = s_q + j * dsub;
-                float dot = 0.0f;
-                for (int t = 0; t < dsub; ++t) dot = fmaf(qj[t], __ldg(cw + t), dot);
-                const float v = lut_scale * dot;
-                if (M16 > 0) { s_lut[(size_t)c * pitch + j] = v; s_lut[(size_t)c * pitch + m + j] = v; }
-                else s_lut[(size_t)j * 256 + c] = v;
-            }
-        }
-        for (int i = lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
-        __syncthreads();
-
-        // ---- scan: warp-strided over 32-slot chunks of the probed lists ----
-        const int nchunks = s_pref[a.nprobe];
-        int cnt = 0;
-        float thr_s = order_max ? -INFINITY : INFINITY;
-        int p = 0;
-        for (int ch = warp; ch < nchunks; ch += kScanWarps) {
-            while (ch >= s_pref[p + 1]) ++p;
-            const int within = (ch - s_pref[p]) * 32 + lane;
-            const bool valid = within < s_len[p];
-            const int64_t g = ((int64_t)s_start[p] << 5) + within;
-            float sum = 0.0f;
-            if (M16 > 0) {
-                uint4 w[M16 > 0 ? M16 : 1];
-                const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + g * (int64_t)m);
-#pragma unroll
-                for (int c = 0; c < M16; ++c) w[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-                const float tx = valid ? __ldg(a.slot_tx + g) : 0.0f;
-                const char* lut_b = reinterpret_cast<const char*>(s_lut);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int c = 0; c < M16; ++c) {
-                    const uint32_t ww[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint32_t x = ww[q4];
-                        const int b = 4 * q4;
-                        constexpr int pb = 4 * 2 * 16 * (M16 > 0 ? M16 : 1);   // bytes per code row
-                        constexpr bool pow2 = (pb & (pb - 1)) == 0;
-                        if (pow2) {
-                            // code * pb is a shifted byte and pre4 < pb: one shift + one LOP3 (and|or) per address
-                            constexpr int sh = (pb == 128) ? 7 : (pb == 256 ? 8 : 9);
-                            constexpr uint32_t mask = 0xFFu << sh;
-                            const uint32_t a0 = and_or(x << sh, mask, (uint32_t)pre4[b + 0]);
-                            const uint32_t a1 = and_or(sh >= 8 ? (x << (sh - 8)) : (x >> (8 - sh)), mask, (uint32_t)pre4[b + 1]);
-                            const uint32_t a2 = and_or(x >> (16 - sh), mask, (uint32_t)pre4[b + 2]);
-                            const uint32_t a3 = and_or(x >> (24 - sh), mask, (uint32_t)pre4[b + 3]);
-                            s0 += *reinterpret_cast<const float*>(lut_b + a0 + 64 * c);
-                            s1 += *reinterpret_cast<const float*>(lut_b + a1 + 64 * c);
-                            s2 += *reinterpret_cast<const float*>(lut_b + a2 + 64 * c);
-                            s3 += *reinterpret_cast<const float*>(lut_b + a3 + 64 * c);
-                        } else {
-                            s0 += *reinterpret_cast<const float*>(lut_b + (x & 0xFF) * pb + pre4[b + 0] + 64 * c);
-                            s1 += *reinterpret_cast<const float*>(lut_b + ((x >> 8) & 0xFF) * pb + pre4[b + 1] + 64 * c);
-                            s2 += *reinterpret_cast<const float*>(lut_b + ((x >> 16) & 0xFF) * pb + pre4[b + 2] + 64 * c);
-                            s3 += *reinterpret_cast<const float*>(lut_b + (x >> 24) * pb + pre4[b + 3] + 64 * c);
-                        }
-                    }
-                }
-                sum = (s_bias[p] + tx) + ((s0 + s1) + (s2 + s3));
-            } else {
-                const uint8_t* src = a.slot_codes + g * (int64_t)m;
-                float s0 = 0.f;
-                if (valid) for (int j = 0; j < m; ++j) s0 += s_lut[(size_t)j * 256 + src[j]];
-                const float tx = valid ? a.slot_tx[g] : 0.0f;
-                sum = (s_bias[p] + tx) + s0;
-            }
-            if (valid) ++scanned_local;
-            const bool pass = valid && (order_max ? !(sum < thr_s) : !(sum > thr_s));
-            const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
-            if (ball) {
-                if (pass) {
-                    const uint32_t id = (uint32_t)a.slot_ids[g];
-                    wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = make_key(sum, id, order_max);
-                }
-                cnt += __popc(ball);
-                __syncwarp();
-                if (cnt + 32 > a.Pw - a.k) {
-                    for (int i = a.k + cnt + lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
-                    __syncwarp();
-                    bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
-                    cnt = 0;
-                    const u64 t = wq[a.k - 1];
-                    if (t != kEmptyKey) thr_s = key_score(t, order_max);
-                }
-            }
-        }
-        // ---- epilogue: flush warp queues, merge, write ----
-        if (cnt > 0) {
-            for (int i = a.k + cnt + lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
-            __syncwarp();
-            bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
-        }
-        __syncwarp();
-        for (int i = lane; i < a.k; i += 32) s_merge[warp * a.k + i] = wq[i];
-        for (int i = kScanWarps * a.k + tid; i < a.P2; i += kScanThreads) s_merge[i] = kEmptyKey;
-        __syncthreads();
-        bitonic_sort_keys<false>(s_merge, a.P2, tid, kScanThreads);
-        for (int i = tid; i < a.k; i += kScanThreads) {
-            const u64 key = s_merge[i];
-            const size_t o = (size_t)qi * a.k + i;
-            if (key == kEmptyKey) { a.out_dist[o] = __int_as_float(0x7fc00000); a.out_ids[o] = -1; }
-            else {
-                const float sc = key_score(key, order_max);
-                a.out_dist[o] = order_max ? -sc : sc;     // IP: API distance = -score (DistanceUtils.swift:40-46)
-                a.out_ids[o] = (int64_t)key_id(key);
-            }
-        }
-    }
-    if (a.scanned) {
-        for (int o = 16; o > 0; o >>= 1) scanned_local += __shfl_xor_sync(0xFFFFFFFFu, scanned_local, o);
-        if (lane == 0 && scanned_local) atomicAdd(a.scanned, scanned_local);
-    }
-}
-
-static size_t scan_smem_bytes(const ScanArgs& a, bool fast) {
-    size_t s = (fast ? (size_t)256 * 2 * a.m : (size_t)a.m * 256) * 4;
-    s += (size_t)a.d * 4 + (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16;
-    s += (size_t)kScanWarps * a.Pw * 8 + (size_t)a.P2 * 8;
-    return s;
-}
-
-static int launch_scan(ScanArgs& a) {
-    a.Pw = next_pow2(a.k + 32);
-    a.P2 = next_pow2(kScanWarps * a.k);
-    const bool fast = (a.m % 16 == 0) && (a.m / 16 >= 1) && (a.m / 16 <= 4);
-    const size_t smem = scan_smem_bytes(a, fast);
-    VIX_REQUIRE(smem <= 227 * 1024, VIX_ERR_UNSUPPORTED,
-                "ivfpq scan: m = %d, k = %d, nprobe = %d need %zu bytes of shared memory", a.m, a.k, a.nprobe, smem);
-    VIX_REQUIRE(a.nprobe <= kScanThreads, VIX_ERR_INVALID_K, "ivfpq scan: nprobe > %d", kScanThreads);
-    void (*kern)(ScanArgs) = nullptr;
-    if (!fast) kern = ivfpq_scan_kernel<0>;
-    else if (a.m == 16) kern = ivfpq_scan_kernel<1>;
-    else if (a.m == 32) kern = ivfpq_scan_kernel<2>;
-    else if (a.m == 48) kern = ivfpq_scan_kernel<3>;
-    else kern = ivfpq_scan_kernel<4>;
-    VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    VIX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
-    if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)num_sms() * occ;
-    if (grid > a.nq) grid = a.nq;
-    kern<<<(unsigned)grid, kScanThreads, smem, ctx().stream>>>(a);
+static int query_order(const int32_t* probes, int64_t nq, int nprobe, int kc, Scratch<int32_t>& order) {
+    cudaStream_t s = ctx().stream;
+    Scratch<int32_t> keys, keys_out, vals;
+    VIX_TRY(keys.alloc((size_t)nq));
+    VIX_TRY(keys_out.alloc((size_t)nq));
+    VIX_TRY(vals.alloc((size_t)nq));
+    VIX_TRY(order.alloc((size_t)nq));
+    first_probe_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(probes, nq, nprobe, keys.ptr, vals.ptr);
     VIX_LAUNCH_CHECK();
+    size_t tmp_bytes = 0;
+    VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_out.ptr, vals.ptr, order.ptr, (int)nq, 0, 31, s));
+    Scratch<unsigned char> tmp;
+    VIX_TRY(tmp.alloc(tmp_bytes + 16));
+    VIX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_out.ptr, vals.ptr, order.ptr, (int)nq, 0, 31, s));
+    ctx().launches += 1;
+    (void)kc;
     return VIX_OK;
 }
 
@@ -585,6 +376,26 @@ __global__ void seq_norms_kernel(const float* __restrict__ c, int64_t rows, int 
     float s = 0.0f;
     for (int e = 0; e < dsub; ++e) s = __fadd_rn(s, __fmul_rn(c[i * dsub + e], c[i * dsub + e]));
     out[i] = s;
+}
+
+// codebooks [m][ks][dsub] -> code-major copy [ks][m][dsub] (coalesced LUT build of the scan)
+__global__ void transpose_codebooks_kernel(const float* __restrict__ cb, int m, int ks, int dsub, float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)m * ks * dsub) return;
+    const int t = (int)(e % dsub);
+    const int64_t r = e / dsub;
+    const int j = (int)(r % m), c = (int)(r / m);
+    out[e] = cb[((size_t)j * ks + c) * dsub + t];
+}
+
+static int update_codebooks_t(vix_index* h) {
+    const int m = h->p.m, ks = h->p.ks, dsub = h->p.d / m;
+    const int64_t total = (int64_t)m * ks * dsub;
+    VIX_TRY(h->codebooks_t.resize((size_t)total, false));
+    transpose_codebooks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(h->codebooks.ptr, m, ks, dsub,
+                                                                                          h->codebooks_t.ptr);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
 }
 
 static int check_ids_host(const int64_t* ids, int64_t n) {
@@ -672,7 +483,10 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
 
     cudaEvent_t* ev = h->ev;
     if (stats && !ev[0]) for (int e = 0; e < 3; ++e) VIX_CUDA(cudaEventCreate(&ev[e]));
+    const bool traced = !stats && h->trace_n < h->trace_cap;
+    cudaEvent_t* tev = traced ? &h->trace_ev[3 * (size_t)h->trace_n] : nullptr;
     if (stats) VIX_CUDA(cudaEventRecord(ev[0], s));
+    if (traced) VIX_CUDA(cudaEventRecord(tev[0], s));
 
     if (h->p.kind == VIX_INDEX_FLAT || !h->has_coarse) {
         // un-optimised IVF => linear scan (IVFIndex.swift:820-832)
@@ -684,6 +498,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         gather_ids_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, s>>>(rows.ptr, h->ids.ptr, di.dev, nq * (int64_t)k);
         VIX_LAUNCH_CHECK();
         if (stats) { VIX_CUDA(cudaEventRecord(ev[1], s)); VIX_CUDA(cudaEventRecord(ev[2], s)); }
+        if (traced) { VIX_CUDA(cudaEventRecord(tev[1], s)); VIX_CUDA(cudaEventRecord(tev[2], s)); }
     } else {
         if (nprobe <= 0) nprobe = h->p.nprobe;
         VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "index_search: nprobe must be > 0");
@@ -695,6 +510,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
                                          h->coarse_norms.ptr, pp, nullptr));
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
+        if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
         DevBuf<unsigned long long>& scanned = h->scanned;
         if (stats) { VIX_TRY(scanned.resize(1, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 8, s)); }
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
@@ -704,8 +520,16 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.list_off = h->list_off.ptr; a.list_len = h->list_len.ptr;
             a.slot_codes = h->slot_codes.ptr; a.slot_tx = h->slot_tx.ptr; a.slot_ids = h->slot_ids.ptr;
             a.metric = h->p.metric; a.k = k; a.out_dist = dd.dev; a.out_ids = di.dev;
-            a.scanned = stats ? scanned.ptr : nullptr;
-            VIX_TRY(launch_scan(a));
+            a.scanned = stats ? scanned.ptr : (traced ? h->trace_scanned.ptr + h->trace_n : nullptr);
+            a.codebooks_t = h->codebooks_t.ptr;
+            VIX_TRY(h->work_counter.resize(1, false));
+            a.work_counter = h->work_counter.ptr;
+            Scratch<int32_t> order;
+            if (scan_layout(a.m).fast && nq > 2 * num_sms()) {
+                VIX_TRY(query_order(pp, nq, nprobe, h->kc, order));
+                a.order = order.ptr;
+            }
+            VIX_TRY(launch_ivfpq_scan(a));
         } else {
             const int P = next_pow2(k + 256);
             const size_t smem = (size_t)P * 8 + (size_t)d * 4;
@@ -717,6 +541,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
                                                                  h->p.metric, k, P, dd.dev, di.dev);
             VIX_LAUNCH_CHECK();
         }
+        if (traced) VIX_CUDA(cudaEventRecord(tev[2], s));
         if (stats) {
             VIX_CUDA(cudaEventRecord(ev[2], s));
             unsigned long long sc = 0;
@@ -729,7 +554,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
     }
     VIX_TRY(dd.commit());
     VIX_TRY(di.commit());
-    int rc = finish(true);
+    if (traced) h->trace_n += 1;
+    int rc = finish(dd.is_host() || di.is_host() || dp.is_host() || stats != nullptr);
     if (stats) {
         VIX_CUDA(cudaEventSynchronize(ev[2]));
         cudaEventElapsedTime(&stats->ms_coarse, ev[0], ev[1]);
@@ -806,6 +632,7 @@ void vix_index_destroy(vix_index_t* h) {
     if (!h) return;
     cudaDeviceSynchronize();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->trace_ev) if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -838,6 +665,7 @@ int vix_index_set_codebooks(vix_index_t* h, const float* codebooks, const float*
                                                                                       h->cb_norms.ptr);
         VIX_LAUNCH_CHECK();
     }
+    VIX_TRY(update_codebooks_t(h));
     h->has_pq = true;
     return finish(true);
 }
@@ -892,6 +720,7 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
         VIX_TRY(h->codebooks.resize((size_t)ks * d, false));
         VIX_TRY(h->cb_norms.resize((size_t)m * ks, false));
         VIX_TRY(train_pq_device(dx.dev, n, d, m, ks, h->coarse.ptr, asg.ptr, pcfg, h->codebooks.ptr, h->cb_norms.ptr));
+        VIX_TRY(update_codebooks_t(h));
         h->has_pq = true;
     }
     h->dirty = true;
@@ -986,6 +815,42 @@ int vix_index_clear(vix_index_t* h) {
     h->n = 0;
     h->vecs.size = h->ids.size = h->assign.size = h->codes.size = 0;
     h->dirty = true;
+    return VIX_OK;
+}
+
+int vix_index_trace(vix_index_t* h, int capacity) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_trace: null handle");
+    VIX_REQUIRE(capacity >= 0 && capacity <= 65536, VIX_ERR_INVALID_PARAM, "vix_index_trace: capacity");
+    std::lock_guard<std::mutex> lk(h->mu);
+    while ((int)h->trace_ev.size() < 3 * capacity) {
+        cudaEvent_t e = nullptr;
+        VIX_CUDA(cudaEventCreate(&e));
+        h->trace_ev.push_back(e);
+    }
+    if (capacity > 0) {
+        VIX_TRY(h->trace_scanned.resize((size_t)capacity, false));
+        VIX_CUDA(cudaMemsetAsync(h->trace_scanned.ptr, 0, (size_t)capacity * 8, ctx().stream));
+    }
+    h->trace_cap = capacity;
+    h->trace_n = 0;
+    return VIX_OK;
+}
+
+int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out) {
+    VIX_REQUIRE(h && out, VIX_ERR_NULL_PTR, "vix_index_trace_get: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(i >= 0 && i < h->trace_n, VIX_ERR_INVALID_PARAM, "vix_index_trace_get: %d of %d traced calls", i, h->trace_n);
+    memset(out, 0, sizeof(*out));
+    cudaEvent_t* ev = &h->trace_ev[3 * (size_t)i];
+    VIX_CUDA(cudaEventSynchronize(ev[2]));
+    unsigned long long sc = 0;
+    VIX_CUDA(cudaMemcpy(&sc, h->trace_scanned.ptr + i, 8, cudaMemcpyDeviceToHost));
+    out->codes_scanned = (int64_t)sc;
+    out->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->p.m : h->p.d * 4);
+    cudaEventElapsedTime(&out->ms_coarse, ev[0], ev[1]);
+    cudaEventElapsedTime(&out->ms_scan, ev[1], ev[2]);
+    cudaEventElapsedTime(&out->ms_total, ev[0], ev[2]);
     return VIX_OK;
 }
 

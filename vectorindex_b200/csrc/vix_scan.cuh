@@ -1,0 +1,37 @@
+// vix_scan.cuh -- interface between the index handles (vix_index.cu) and the fused IVF-PQ scan
+// (vix_ivfpq_scan.cu).
+#pragma once
+
+#include "vix_common.cuh"
+
+namespace vix {
+
+struct ScanArgs {
+    const float* queries; int64_t nq; int d, m, ks, dsub;
+    const int32_t* probes; int nprobe;            // [nq x nprobe], -1 padded
+    const int32_t* order;                         // optional [nq]: work item -> query (locality order)
+    int* work_counter;                            // device int, zeroed by the launcher
+    const float* coarse;                          // [kc x d]
+    const float* codebooks;                       // [m x ks x dsub]
+    const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
+    const int64_t* list_off; const int32_t* list_len;
+    const uint8_t* slot_codes; const float* slot_tx; const int64_t* slot_ids;
+    int metric, k, Pw, P2;
+    float* out_dist; int64_t* out_ids;            // [nq x k]
+    unsigned long long* scanned;                  // optional: total list entries visited
+};
+
+// How the inverted lists are laid out for a given m.
+//   fast:  lists start at multiples of `align` slots; inside every 32-slot block the codes are stored
+//          transposed, [sub-quantiser][vector] (32 bytes per sub-quantiser);
+//   else:  plain AoS rows, lists 32-aligned.
+struct ScanLayout {
+    bool fast;
+    int ng;       // 32-slot blocks a warp works on at once
+    int align;    // list start / padded length granularity in slots (32 * ng)
+};
+ScanLayout scan_layout(int m);
+
+int launch_ivfpq_scan(ScanArgs& a);
+
+}  // namespace vix

@@ -702,7 +702,7 @@ int vix_merge_topk_f32(const float* scores, const int64_t* ids, const int32_t* l
                                dos.dev, doi.dev));
     VIX_TRY(dos.commit());
     VIX_TRY(doi.commit());
-    return finish(true);
+    return finish(dos.is_host() || doi.is_host());
 }
 
 int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* centroids, int kc, int d, int metric,
