@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvindex_b200.so")
+LIB_PATH = os.environ.get("VIX_LIB_PATH") or os.path.join(_HERE, "libvindex_b200.so")   # override: kernel A/B experiments
 
 VIX_OK = 0
 METRIC_L2, METRIC_IP = 0, 1

@@ -9,8 +9,8 @@
 //   3. fused scan        vix_ivfpq_scan.cu: query-only LUT + ADC over the probed lists + top-k
 //
 // This file owns the device-resident state: rows in add order (AoS codes, the reference's interchange
-// format) and the scan layout derived from them (lists padded to whole blocks of 32 vectors, codes
-// transposed inside each block, per-vector term t_x = ||r^||^2 + 2 <c, r^>).
+// format) and the scan layout derived from them (lists padded to whole chunks of 32 slots, codes
+// rotated inside each group of 16 sub-quantisers, per-vector term t_x = ||r^||^2 + 2 <c, r^>).
 #include "vix_common.cuh"
 #include "vix_topk.cuh"
 #include "vix_exact.cuh"
@@ -170,30 +170,32 @@ __global__ void place_rows_kernel(const int32_t* __restrict__ sorted_rows, const
     slot_row[off[l] + (i - off_raw[l])] = sorted_rows[i];
 }
 
-// Fill one slot: codes in the scan layout, id, t_x.  One warp per slot (lanes split the sub-quantisers).
-// transposed != 0: byte (j, v) of the 32-slot block at blk * 32 * m + j * 32 + v; else AoS rows.
+// Fill one slot: codes in the scan layout (vix_scan.cuh), id, t_x.  One warp per slot (lanes split the
+// sub-quantisers).  rotated != 0: byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15).
 __global__ void __launch_bounds__(256)
 fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const uint8_t* __restrict__ codes,
                      const int64_t* __restrict__ ids, const int32_t* __restrict__ assign,
                      const float* __restrict__ coarse, const float* __restrict__ codebooks, int d, int m, int ks,
-                     int transposed, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
+                     int rotated, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
                      float* __restrict__ slot_tx) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= nslots) return;
     const int row = slot_row[g];
     const int dsub = d / m;
-    uint8_t* dst = transposed ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) : slot_codes + g * (int64_t)m;
-    const int dstride = transposed ? 32 : 1;
+    uint8_t* dst = slot_codes + g * (int64_t)m;
     if (row < 0) {
-        for (int j = lane; j < m; j += 32) dst[(int64_t)j * dstride] = 0;
+        for (int b = lane; b < m; b += 32) dst[b] = 0;
         if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
         return;
     }
     const uint8_t* src = codes + (int64_t)row * m;
     const float* c = coarse + (int64_t)assign[row] * d;
     double acc = 0.0;
-    for (int j = lane; j < m; j += 32) dst[(int64_t)j * dstride] = src[j];
+    for (int b = lane; b < m; b += 32) {
+        const int j = rotated ? ((b & ~15) | ((b ^ (int)(g & 15)) & 15)) : b;
+        dst[b] = src[j];
+    }
     if (metric == VIX_METRIC_L2) {
         for (int j = lane; j < m; j += 32) {
             const float* cw = codebooks + ((size_t)j * ks + src[j]) * dsub;
@@ -266,14 +268,14 @@ static int build_lists(vix_index* h) {
     }
     if (h->p.kind == VIX_INDEX_IVF_PQ) {
         const int m = h->p.m;
-        const int transposed = scan_layout(m).fast ? 1 : 0;
+        const int rotated = scan_layout(m).fast ? 1 : 0;
         VIX_TRY(h->slot_codes.resize((size_t)nslots * m + 16, false));
         VIX_TRY(h->slot_tx.resize((size_t)nslots, false));
         if (nslots > 0) {
             int64_t threads = nslots * 32;
             fill_slots_pq_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
                 h->slot_row.ptr, nslots, h->codes.ptr, h->ids.ptr, h->assign.ptr, h->coarse.ptr, h->codebooks.ptr,
-                h->p.d, m, h->p.ks, transposed, h->p.metric, h->slot_codes.ptr, h->slot_ids.ptr, h->slot_tx.ptr);
+                h->p.d, m, h->p.ks, rotated, h->p.metric, h->slot_codes.ptr, h->slot_ids.ptr, h->slot_tx.ptr);
             VIX_LAUNCH_CHECK();
         }
     } else {
@@ -522,7 +524,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.metric = h->p.metric; a.k = k; a.out_dist = dd.dev; a.out_ids = di.dev;
             a.scanned = stats ? scanned.ptr : (traced ? h->trace_scanned.ptr + h->trace_n : nullptr);
             a.codebooks_t = h->codebooks_t.ptr;
-            VIX_TRY(h->work_counter.resize(1, false));
+            VIX_TRY(h->work_counter.resize(2, false));
             a.work_counter = h->work_counter.ptr;
             Scratch<int32_t> order;
             if (scan_layout(a.m).fast && nq > 2 * num_sms()) {

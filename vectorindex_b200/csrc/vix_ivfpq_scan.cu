@@ -2,7 +2,7 @@
 //
 // Reference composition: pq_lut_residual_l2_f32 -> adc_scan_u8 -> selectTopK -> mergeTopK
 // (/root/reference/docs/kernel-specs/DONE_22_adc_scan.md:831-881; PQLUT.swift:266-386;
-// ADCScan.swift:190-283; TopK.swift:54-176).  One persistent CTA serves one query at a time:
+// ADCScan.swift:190-283; TopK.swift:54-176).  One persistent CTA per SM serves one query at a time:
 //
 //   ||q - x^||^2 = ||q - c_l||^2 + (||r^||^2 + 2<c_l, r^>) - 2<q, r^>,   x^ = c_l + r^
 //                  bias (per probe)  t_x (per stored vector)     sum_j T[j][code_j],  T = -2<q_j, cb_j[.]>
@@ -10,335 +10,466 @@
 // so ONE table per query serves every probed list (the reference builds one residual LUT per
 // (query, list)); the result agrees with the reference's sum to fp32 rounding (1e-5, tested).
 //
-// The scan is bound by shared-memory look-ups (one per code byte; an SM retires 32 per clock), so the
-// kernel is organised to spend exactly one conflict-free LDS and two other instructions per byte:
+// The scan is bound by shared-memory look-ups (one per code byte; an SM retires 32 per clock, which at
+// 1.9 GHz x 148 SMs is just above the HBM rate of the code stream), so the kernel spends exactly one
+// conflict-free LDS, one PRMT and one FADD per code byte and nothing else in the inner loop:
 //
-//   * "lane = sub-quantiser": a warp owns 32 stored vectors at a time and lane l looks up
-//     sub-quantiser 32 f + l of every one of them, accumulating 32 running sums (one per vector) in
-//     registers.  The table is stored code-major, T[code][64 slots] (256 B per code), and lane l only
-//     ever touches slot l (or l + 32): its bank is its lane id, so EVERY warp-wide look-up is a single
-//     wavefront whatever the codes are.
-//   * the byte offset code * 256 + 4 * lane is ONE byte-permute (PRMT) of the packed code word and a
-//     per-lane constant; the slot half / table index is the LDS immediate.
-//   * the 32 x 32 partial sums are transposed with a butterfly of shuffles (31 SHFL per 1024 look-ups)
-//     so that lane v ends up with the distance of vector v.
-//   * codes are stored per list in blocks of 32 vectors, transposed to [sub-quantiser][vector] (32 B
-//     per sub-quantiser), so a lane's 32 codes are two 128-bit loads and a warp reads 1 KB
-//     contiguously; the next pass is prefetched into registers while the current one is looked up.
-//   * m = 32 F + R sub-quantisers (R in {0, 8, 16}): the R left-over sub-quantisers are handled by
-//     splitting the warp into 32 / R lane groups that work on 32 / R different vector blocks at once
-//     (their table slots are replicated so the bank == lane rule still holds).
+//   * one stored vector per lane (no cross-lane reduction); a warp streams 32-slot chunks of the probed
+//     lists with 128-bit loads, the next chunk prefetched into registers;
+//   * the table is code-major, T[code][64 slots] (256 B per code, 64 KB per table, one table per 32
+//     sub-quantisers).  A 32-slot half row holds ONE group of 16 sub-quantisers twice (replica 0 | 1);
+//     codes are stored "rotated" -- byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15) -- so
+//     at byte position b the 16 lanes of a half-warp ask for 16 different sub-quantisers and the two
+//     half-warps use the two replicas: every warp-wide look-up touches 32 different banks whatever the
+//     codes are;
+//   * the tables start at a 64 KB-aligned SHARED address, so the complete LDS address
+//     (table | code << 8 | 4 * slot) is ONE byte-permute of the packed code word with a per-lane
+//     constant; the group / table select is the LDS immediate.
 //
-// Top-k: per-warp shared-memory queues keyed (score, id) with a CTA-wide acceptance threshold, merged at
-// the end of the query; no distance array ever reaches HBM.  Queries are handed out by an atomic
-// counter in an order sorted by first probed list, so CTAs running concurrently scan neighbouring
-// lists and share them through L2.
+// Top-k: per-warp shared-memory queues keyed (score, id) with a CTA-wide acceptance threshold; at the end
+// of a query every warp publishes its k best and warp 0 merges them while the other warps already build
+// the next query's table.  No distance array ever reaches HBM.  Queries are handed out by an atomic
+// counter in an order sorted by first probed list, so CTAs running concurrently scan neighbouring lists
+// and share them through L2.
 #include "vix_common.cuh"
 #include "vix_topk.cuh"
 #include "vix_scan.cuh"
 
 namespace vix {
 
-constexpr int kScanWarps = 8;
+#ifndef VIX_SCAN_THREADS
+#define VIX_SCAN_THREADS 512
+#endif
+#ifndef VIX_SCAN_FN
+#define VIX_SCAN_FN __noinline__
+#endif
+constexpr int kFastThreads = VIX_SCAN_THREADS;   // one CTA per SM
+constexpr int kScanWarps = 8;              // generic kernel
 constexpr int kScanThreads = kScanWarps * 32;
 
-template <int F_, int R_>
-struct ScanShape {
-    static constexpr int F = F_, R = R_;
-    static constexpr int M = 32 * F + R;
-    static constexpr int NG = (R == 0) ? 1 : 32 / R;             // vector blocks per chunk
-    static constexpr int CH = 32 * NG;                           // slots per chunk
-    static constexpr int NPASS = NG * F + (R ? 1 : 0);
-    static constexpr int SLOTS = 32 * (F + (R ? 1 : 0));
-    static constexpr int NTAB = (SLOTS + 63) / 64;               // 64 KB tables
-    static_assert(R == 0 || R == 8 || R == 16, "m = 32 F + R with R in {0, 8, 16}");
-    static_assert(R != 8 || F == 0, "R = 8 only for m = 8");
-};
-
-// byte offset of table slot s for the LDS immediate
-__host__ __device__ constexpr int slot_imm(int s) { return (s >> 6) * 65536 + (s & 63) * 4; }
-
-// acc[v] += T[code of vector v][slot column IMM] for the 32 vectors of one block
 template <int IMM>
-__device__ __forceinline__ void lookup32(const uint4& w0, const uint4& w1, const char* __restrict__ lut_b,
-                                         uint32_t laneconst, float (&acc)[32]) {
-    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+__device__ __forceinline__ float lds_imm(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+// one group of 16 sub-quantisers: 16 look-ups of one lane, 4 running sums
+template <int T>
+__device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[16], float& s0, float& s1, float& s2,
+                                         float& s3) {
+    constexpr int IMM = (T & 1) * 128 + (T >> 1) * 65536;
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int v = 0; v < 32; ++v) {
-        // bytes: [0] = 4 * lane, [1] = code, [2] = [3] = 0   ->   code * 256 + 4 * lane
-        const uint32_t off = __byte_perm(w[v >> 2], laneconst, 0x6504 | ((v & 3) << 4));
-        acc[v] += *reinterpret_cast<const float*>(lut_b + off + IMM);
+    for (int i = 0; i < 4; ++i) {
+        // result bytes: [0] = 4 * slot (lane constant), [1] = code, [2..3] = table address >> 16
+        s0 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 0], 0x7604));
+        s1 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 1], 0x7614));
+        s2 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 2], 0x7624));
+        s3 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 3], 0x7634));
     }
 }
 
-// Butterfly transpose-reduce over groups of GROUP lanes: afterwards acc[0 .. 32/GROUP) of lane l hold the
-// group totals of vectors (32/GROUP) * (l % GROUP) + i.
-template <int N, int O>
-struct Butterfly {
-    __device__ __forceinline__ static void run(float (&acc)[32], int lane) {
-        const bool upper = (lane & O) != 0;
+template <int G>
+__device__ __forceinline__ void load_codes(uint4 (&w)[G], const uint8_t* __restrict__ codes, int64_t g, bool valid) {
+    const uint4* src = reinterpret_cast<const uint4*>(codes + g * (int64_t)(16 * G));
 #pragma unroll
-        for (int i = 0; i < N / 2; ++i) {
-            const float send = upper ? acc[i] : acc[i + N / 2];
-            const float keep = upper ? acc[i + N / 2] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, O);
-        }
-        Butterfly<N / 2, O / 2>::run(acc, lane);
-    }
-};
-template <int N>
-struct Butterfly<N, 0> {
-    __device__ __forceinline__ static void run(float (&)[32], int) {}
-};
-
-struct ChunkPos {
-    int p;            // probe index
-    int within;       // first slot of the chunk inside the list
-    int64_t g0;       // first slot of the chunk (global)
-};
-
-template <typename S>
-__device__ __forceinline__ const uint4* pass_ptr(const uint8_t* __restrict__ codes, int64_t g0, int ps, int lane) {
-    // pass ps < NG*F: block ps / F, sub-quantiser row 32 (ps % F) + lane; last pass: the R left-overs
-    int blk, row;
-    if (S::F > 0 && ps < S::NG * S::F) { blk = ps / (S::F > 0 ? S::F : 1); row = 32 * (ps % (S::F > 0 ? S::F : 1)) + lane; }
-    else { blk = lane / (S::R ? S::R : 32); row = 32 * S::F + lane % (S::R ? S::R : 32); }
-    return reinterpret_cast<const uint4*>(codes + ((g0 >> 5) + blk) * (int64_t)(32 * S::M) + (int64_t)row * 32);
+    for (int c = 0; c < G; ++c) w[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
 }
 
-template <int F, int R>
-__global__ void __launch_bounds__(kScanThreads, (ScanShape<F, R>::NTAB == 1) ? 2 : 1)
-ivfpq_scan_kernel(ScanArgs a) {
-    using S = ScanShape<F, R>;
-    constexpr int m = S::M;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_lut = reinterpret_cast<float*>(smem_raw);                    // NTAB x [256][64]
-    float* s_q = s_lut + (size_t)S::NTAB * 16384;                         // [d]
-    float* s_bias = s_q + a.d;                                            // [nprobe]
-    int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);             // [nprobe]  first slot / 32
-    int* s_len = s_start + a.nprobe;                                      // [nprobe]
-    int* s_pref = s_len + a.nprobe;                                       // [nprobe + 1] chunk prefix
-    int* s_misc = s_pref + a.nprobe + 1;                                  // [0] work item, [1] CTA threshold
-    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_misc + 2) + 15) & ~(uintptr_t)15);
-    u64* s_merge = s_wq + (size_t)kScanWarps * a.Pw;                      // [P2]
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
+    return __shfl_xor_sync(0xFFFFFFFFu, v, o);
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int order_max = (a.metric == VIX_METRIC_IP);
-    const float lut_scale = order_max ? 1.0f : -2.0f;
-    u64* wq = s_wq + (size_t)warp * a.Pw;
-    const char* lut_b = reinterpret_cast<const char*>(s_lut);
-    const uint32_t laneconst = 4u * lane;
-    unsigned long long scanned_local = 0;
-    volatile uint32_t* cta_thr = reinterpret_cast<volatile uint32_t*>(s_misc + 1);
+// per-probe term of the decomposition: ||q - c_l||^2 (L2) or <q, c_l> (IP); one warp per (query, probe)
+__global__ void __launch_bounds__(256)
+probe_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
+                  int64_t npairs, int nprobe, int d, int order_max, float* __restrict__ bias) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= npairs) return;
+    const int l = probes[w];
+    float part = 0.0f;
+    if (l >= 0) {
+        const float* q = queries + (w / nprobe) * (int64_t)d;
+        const float* c = coarse + (int64_t)l * d;
+        if (order_max) for (int e = lane; e < d; e += 32) part = fmaf(__ldg(q + e), __ldg(c + e), part);
+        else for (int e = lane; e < d; e += 32) { const float df = __ldg(q + e) - __ldg(c + e); part = fmaf(df, df, part); }
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if (lane == 0) bias[w] = part;
+}
 
-    for (;;) {
-        __syncthreads();                                   // previous query fully drained
-        if (tid == 0) s_misc[0] = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int item = s_misc[0];
-        if (item >= a.nq) break;
-        const int64_t qi = a.order ? a.order[item] : item;
-
-        // ---- prologue: query, probe table, bias, LUT ----
-        for (int e = tid; e < a.d; e += kScanThreads) s_q[e] = a.queries[qi * (int64_t)a.d + e];
-        if (tid < a.nprobe) {
-            const int l = a.probes[qi * (int64_t)a.nprobe + tid];
-            s_start[tid] = l >= 0 ? (int)(a.list_off[l] >> 5) : 0;
-            s_len[tid] = l >= 0 ? a.list_len[l] : 0;
-        }
-        if (tid == 0) *cta_thr = 0xFFFFFFFFu;
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int p = 0; p < a.nprobe; ++p) { s_pref[p] = acc; acc += (s_len[p] + S::CH - 1) / S::CH; }
-            s_pref[a.nprobe] = acc;
-        }
-        for (int p = warp; p < a.nprobe; p += kScanWarps) {
-            const int l = a.probes[qi * (int64_t)a.nprobe + p];
-            float part = 0.0f;
-            if (l >= 0) {
-                const float* c = a.coarse + (int64_t)l * a.d;
-                if (order_max) for (int e = lane; e < a.d; e += 32) part = fmaf(s_q[e], c[e], part);
-                else for (int e = lane; e < a.d; e += 32) { float df = s_q[e] - c[e]; part = fmaf(df, df, part); }
-            }
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-            if (lane == 0) s_bias[p] = part;
-        }
-        {
-            // T[c][slot(j)] = scale * <q_j, cb_j[c]>; codebooks_t is [256][m][dsub] so that consecutive
-            // threads read consecutive memory and write consecutive banks
-            const int dsub = a.dsub;
-            for (int e = tid; e < m * 256; e += kScanThreads) {
-                const int c = e / m, j = e - c * m;
-                const float* cw = a.codebooks_t + (size_t)e * dsub;
-                const float* qj = s_q + j * dsub;
-                float dot = 0.0f;
-                for (int t = 0; t < dsub; ++t) dot = fmaf(qj[t], __ldg(cw + t), dot);
-                const float v = lut_scale * dot;
-                if (j < 32 * F) {
-                    s_lut[(j >> 6) * 16384 + c * 64 + (j & 63)] = v;
-                } else {
+// k-th smallest (0-based rank kth) of one 32-bit key per lane: bitonic network over the warp
+__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
 #pragma unroll
-                    for (int t = 0; t < S::NG; ++t) {
-                        const int s = j + t * R;
-                        s_lut[(s >> 6) * 16384 + c * 64 + (s & 63)] = v;
-                    }
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
+            const bool up = (lane & size) == 0 || size == 32;
+            const bool lower = (lane & stride) == 0;
+            v = (lower == up) ? min(v, other) : max(v, other);
+        }
+    }
+    return __shfl_sync(0xFFFFFFFFu, v, kth);
+}
+
+// ---- per-query prologue / epilogue pieces, kept out of line so that the scan loop owns the registers ----
+
+// warp 0: the k best of the n published candidates.  Keys are unique, so "the smallest key greater than
+// the last one taken" walks them in order without mutating anything.
+__device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int n, int k, int order_max, int64_t qi,
+                                              float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    uint32_t last_hi = 0, last_lo = 0;
+    bool first = true;
+    for (int i = 0; i < k; ++i) {
+        uint32_t mh = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
+        for (int t = lane; t < n; t += 32) {
+            const u64 key = s_cand[t];
+            const uint32_t kh = (uint32_t)(key >> 32), kl = (uint32_t)key;
+            const bool after = first || kh > last_hi || (kh == last_hi && kl > last_lo);
+            if (after && (kh < mh || (kh == mh && kl < ml))) { mh = kh; ml = kl; }
+        }
+        const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
+        const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
+        const u64 mn = ((u64)gh << 32) | gl;
+        if (lane == 0) {
+            const size_t o = (size_t)qi * k + i;
+            if (mn == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
+            else {
+                const float sc = key_score(mn, order_max);
+                out_dist[o] = order_max ? -sc : sc;   // IP: API distance = -score (DistanceUtils.swift:40-46)
+                out_ids[o] = (int64_t)key_id(mn);
+            }
+        }
+        last_hi = gh; last_lo = gl; first = false;
+    }
+}
+
+// warp 1: probe table, bias and exclusive prefix of chunk counts, all inside one warp; loads batched
+__device__ VIX_SCAN_FN void build_probe_table(const int32_t* __restrict__ qprobes, const float* __restrict__ qbias,
+                                               int nprobe, const int64_t* __restrict__ list_off,
+                                               const int32_t* __restrict__ list_len, int* s_start, int* s_len,
+                                               int* s_pref, float* s_bias) {
+    const int lane = threadIdx.x & 31;
+    int lv[8], lenv[8];
+    int64_t offv[8];
+    float bv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int p = 32 * it + lane;
+        lv[it] = (p < nprobe) ? __ldg(qprobes + p) : -1;
+        bv[it] = (p < nprobe) ? __ldg(qbias + p) : 0.0f;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        offv[it] = 0; lenv[it] = 0;
+        if (lv[it] >= 0) { offv[it] = __ldg(list_off + lv[it]); lenv[it] = __ldg(list_len + lv[it]); }
+    }
+    int carry = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        if (32 * it < nprobe) {
+            const int p = 32 * it + lane;
+            const int nch = (lenv[it] + 31) >> 5;
+            int inc = nch;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            if (p < nprobe) {
+                s_start[p] = (int)(offv[it] >> 5); s_len[p] = lenv[it]; s_pref[p] = carry + inc - nch;
+                s_bias[p] = bv[it];
+            }
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+    }
+    if (lane == 0) s_pref[nprobe] = carry;
+}
+
+// warps 2..: T[c][slot(j)] = scale * <q_j, cb_j[c]>.  Thread t of the `nthr` builders owns ONE sub-quantiser
+// j = t % M (its query slice stays in registers) and walks the codes c = t / M, t / M + nthr / M, ...;
+// codebooks_t is [256][M][dsub], so the M threads of a code read consecutive memory.  Four codes per thread
+// are in flight.  The two replicas of an entry are written in opposite order by the two half-warps, so a
+// warp-wide store touches 32 different banks.
+template <int M>
+__device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __restrict__ q,
+                                      const float* __restrict__ codebooks_t, int dsub, float lut_scale, int t, int nthr) {
+    const int ngroups = nthr / M;
+    if (t >= ngroups * M) return;
+    const int j = t % M, c0 = t / M;
+    const int rep_first = (threadIdx.x & 31) >> 4;
+    const int t16 = j >> 4;
+    float* col = s_lut + (t16 >> 1) * 16384 + (t16 & 1) * 32 + (j & 15);
+    float* colA = col + 16 * rep_first;
+    float* colB = col + 16 * (rep_first ^ 1);
+    constexpr int U = 4;
+    if (dsub <= 16) {
+        float qv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) qv[e] = (e < dsub) ? __ldg(q + j * dsub + e) * lut_scale : 0.0f;
+        for (int c = c0; c < 256; c += U * ngroups) {
+            float dot[U];
+            if (dsub == 2) {
+                float2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cu = min(c + u * ngroups, 255);
+                    v[u] = __ldg(reinterpret_cast<const float2*>(codebooks_t + ((size_t)cu * M + j) * 2));
                 }
-            }
-        }
-        for (int i = lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
-        __syncthreads();
-
-        // ---- scan: warp-strided over chunks of CH slots ----
-        const int nchunks = s_pref[a.nprobe];
-        int cnt = 0;
-        uint32_t thr_u = 0xFFFFFFFFu;
-        int p = 0;
-        int ch = warp;
-        ChunkPos cur{0, 0, 0};
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-        if (ch < nchunks) {
-            while (ch >= s_pref[p + 1]) ++p;
-            cur.p = p; cur.within = (ch - s_pref[p]) * S::CH; cur.g0 = ((int64_t)s_start[p] << 5) + cur.within;
-            const uint4* src = pass_ptr<S>(a.slot_codes, cur.g0, R > 0 ? S::NPASS - 1 : 0, lane);
-            c0 = __ldg(src); c1 = __ldg(src + 1);
-        }
-        while (ch < nchunks) {
-            // position of this warp's next chunk (for the prefetch of its first pass)
-            const int chn = ch + kScanWarps;
-            ChunkPos nxt = cur;
-            if (chn < nchunks) {
-                while (chn >= s_pref[p + 1]) ++p;
-                nxt.p = p; nxt.within = (chn - s_pref[p]) * S::CH; nxt.g0 = ((int64_t)s_start[p] << 5) + nxt.within;
-            }
-            float res[S::NG];
-            float rem[S::NG];
-            float acc[32];
-            int ps = 0;
-            // pass order: the R left-overs first (all blocks of the chunk at once), then F passes per block
-            if (R > 0) {
-                // prefetch: the next pass of this chunk, or the first pass of the next chunk
-                uint4 n0 = c0, n1 = c1;
-                if (F > 0) { const uint4* s2 = pass_ptr<S>(a.slot_codes, cur.g0, 0, lane); n0 = __ldg(s2); n1 = __ldg(s2 + 1); }
-                else if (chn < nchunks) { const uint4* s2 = pass_ptr<S>(a.slot_codes, nxt.g0, S::NPASS - 1, lane); n0 = __ldg(s2); n1 = __ldg(s2 + 1); }
 #pragma unroll
-                for (int v = 0; v < 32; ++v) acc[v] = 0.0f;
-                lookup32<slot_imm(32 * F)>(c0, c1, lut_b, laneconst, acc);
-                Butterfly<32, R / 2>::run(acc, lane);
+                for (int u = 0; u < U; ++u) dot[u] = fmaf(qv[1], v[u].y, qv[0] * v[u].x);
+            } else if ((dsub & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < S::NG; ++i) rem[i] = acc[i];
-                c0 = n0; c1 = n1;
-            }
-            if (F > 0) {
+                for (int u = 0; u < U; ++u) dot[u] = 0.0f;
 #pragma unroll
-                for (int blk = 0; blk < S::NG; ++blk) {
+                for (int e = 0; e < 16; e += 4) {
+                    if (e < dsub) {
+                        float4 v[U];
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) acc[v] = 0.0f;
-#pragma unroll
-                    for (int f = 0; f < F; ++f) {
-                        ps = blk * F + f;
-                        uint4 n0 = c0, n1 = c1;
-                        if (ps + 1 < S::NG * F) {
-                            const uint4* s2 = pass_ptr<S>(a.slot_codes, cur.g0, ps + 1, lane);
-                            n0 = __ldg(s2); n1 = __ldg(s2 + 1);
-                        } else if (chn < nchunks) {
-                            const uint4* s2 = pass_ptr<S>(a.slot_codes, nxt.g0, R > 0 ? S::NPASS - 1 : 0, lane);
-                            n0 = __ldg(s2); n1 = __ldg(s2 + 1);
+                        for (int u = 0; u < U; ++u) {
+                            const int cu = min(c + u * ngroups, 255);
+                            v[u] = __ldg(reinterpret_cast<const float4*>(codebooks_t + ((size_t)cu * M + j) * dsub + e));
                         }
-                        // compile-time slot immediate per f
-                        if (f == 0) lookup32<slot_imm(0)>(c0, c1, lut_b, laneconst, acc);
-                        else if (f == 1) lookup32<slot_imm(32)>(c0, c1, lut_b, laneconst, acc);
-                        else if (f == 2) lookup32<slot_imm(64)>(c0, c1, lut_b, laneconst, acc);
-                        else lookup32<slot_imm(96)>(c0, c1, lut_b, laneconst, acc);
-                        c0 = n0; c1 = n1;
-                    }
-                    Butterfly<32, 16>::run(acc, lane);
-                    res[blk] = acc[0];
-                }
-                if (R > 0) {
-                    // left-over sums live in lane blk * R + v / NG, entry v % NG
 #pragma unroll
-                    for (int blk = 0; blk < S::NG; ++blk) {
-                        const int srcl = blk * R + lane / S::NG;
-                        float pick = 0.0f;
-#pragma unroll
-                        for (int i = 0; i < S::NG; ++i) {
-                            const float t = __shfl_sync(0xFFFFFFFFu, rem[i], srcl);
-                            if ((lane % S::NG) == i) pick = t;
-                        }
-                        res[blk] += pick;
+                        for (int u = 0; u < U; ++u)
+                            dot[u] = fmaf(qv[e + 3], v[u].w, fmaf(qv[e + 2], v[u].z, fmaf(qv[e + 1], v[u].y, fmaf(qv[e], v[u].x, dot[u]))));
                     }
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < S::NG; ++i) res[i] = rem[i];
-            }
-
-            // ---- candidates: result i of lane l is  (F > 0) block i, vector l
-            //                                          (F == 0) block l / R, vector NG * (l % R) + i
-            const float bias = s_bias[cur.p];
-            const int len = s_len[cur.p];
-            {
-                const uint32_t t = *cta_thr;
-                if (t < thr_u) thr_u = t;
-            }
+                for (int u = 0; u < U; ++u) dot[u] = 0.0f;
 #pragma unroll
-            for (int i = 0; i < S::NG; ++i) {
-                const int vec = (F > 0) ? (32 * i + lane) : (32 * (lane / (R ? R : 32)) + S::NG * (lane % (R ? R : 32)) + i);
-                const int within = cur.within + vec;
-                const bool valid = within < len;
-                const int64_t g = cur.g0 + vec;
-                const float tx = valid ? __ldg(a.slot_tx + g) : 0.0f;
-                const float sum = (bias + tx) + res[i];
-                if (valid) ++scanned_local;
-                const u64 key = make_key(sum, 0u, order_max);
-                const bool pass = valid && ((uint32_t)(key >> 32) <= thr_u);
-                const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
-                if (ball) {
-                    if (pass) {
-                        const uint32_t id = (uint32_t)a.slot_ids[g];
-                        wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)id;
-                    }
-                    cnt += __popc(ball);
-                    __syncwarp();
-                    if (cnt + 32 > a.Pw - a.k) {
-                        for (int t = a.k + cnt + lane; t < a.Pw; t += 32) wq[t] = kEmptyKey;
-                        __syncwarp();
-                        bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
-                        cnt = 0;
-                        const u64 t = wq[a.k - 1];
-                        if (t != kEmptyKey) {
-                            const uint32_t tu = (uint32_t)(t >> 32);
-                            if (tu < thr_u) thr_u = tu;
-                            if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(s_misc + 1), tu);
+                for (int e = 0; e < 16; ++e) {
+                    if (e < dsub) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int cu = min(c + u * ngroups, 255);
+                            dot[u] = fmaf(qv[e], __ldg(codebooks_t + ((size_t)cu * M + j) * dsub + e), dot[u]);
                         }
                     }
                 }
             }
-            cur = nxt;
-            ch = chn;
-        }
-        // ---- epilogue: flush warp queues, merge, write ----
-        if (cnt > 0) {
-            for (int i = a.k + cnt + lane; i < a.Pw; i += 32) wq[i] = kEmptyKey;
-            __syncwarp();
-            bitonic_sort_keys<true>(wq, a.Pw, lane, 32);
-        }
-        __syncwarp();
-        for (int i = lane; i < a.k; i += 32) s_merge[warp * a.k + i] = wq[i];
-        for (int i = kScanWarps * a.k + tid; i < a.P2; i += kScanThreads) s_merge[i] = kEmptyKey;
-        __syncthreads();
-        bitonic_sort_keys<false>(s_merge, a.P2, tid, kScanThreads);
-        for (int i = tid; i < a.k; i += kScanThreads) {
-            const u64 key = s_merge[i];
-            const size_t o = (size_t)qi * a.k + i;
-            if (key == kEmptyKey) { a.out_dist[o] = __int_as_float(0x7fc00000); a.out_ids[o] = -1; }
-            else {
-                const float sc = key_score(key, order_max);
-                a.out_dist[o] = order_max ? -sc : sc;     // IP: API distance = -score (DistanceUtils.swift:40-46)
-                a.out_ids[o] = (int64_t)key_id(key);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cu = c + u * ngroups;
+                if (cu < 256) { colA[cu * 64] = dot[u]; colB[cu * 64] = dot[u]; }
             }
         }
+    } else {
+        for (int c = c0; c < 256; c += ngroups) {
+            const float* cw = codebooks_t + ((size_t)c * M + j) * dsub;
+            float dot = 0.0f;
+            for (int e = 0; e < dsub; ++e) dot = fmaf(__ldg(q + j * dsub + e), __ldg(cw + e), dot);
+            dot *= lut_scale;
+            colA[c * 64] = dot; colB[c * 64] = dot;
+        }
+    }
+}
+
+// one warp: sort the queue (k best first), refresh the thresholds
+__device__ __noinline__ uint32_t flush_queue(u64* wq, int Pw, int k, int cnt, bool sorted_valid, uint32_t thr_u, int* s_thr) {
+    const int lane = threadIdx.x & 31;
+    if (!sorted_valid) for (int t = lane; t < k; t += 32) wq[t] = kEmptyKey;
+    for (int t = k + cnt + lane; t < Pw; t += 32) wq[t] = kEmptyKey;
+    __syncwarp();
+    bitonic_sort_keys<true>(wq, Pw, lane, 32);
+    const u64 t = wq[k - 1];
+    if (t != kEmptyKey) {
+        const uint32_t tu = (uint32_t)(t >> 32);
+        if (tu < thr_u) thr_u = tu;
+        if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(s_thr), tu);
+    }
+    return thr_u;
+}
+
+// m = 16 G
+template <int G>
+__global__ void __launch_bounds__(kFastThreads, 1)
+ivfpq_scan_kernel(ScanArgs a) {
+    constexpr int m = 16 * G;
+    constexpr int NTAB = (G + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+
+    // ---- shared-memory map: bookkeeping first, then the 64 KB-aligned tables ----
+    float* s_bias = reinterpret_cast<float*>(smem_raw);                   // [nprobe]
+    int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);             // [nprobe]  first slot / 32
+    int* s_len = s_start + a.nprobe;                                      // [nprobe]
+    int* s_pref = s_len + a.nprobe;                                       // [nprobe + 1] chunk prefix
+    int* s_item = s_pref + a.nprobe + 1;                                  // [2] work items (double buffered)
+    int* s_thr = s_item + 2;                                              // [1] CTA acceptance threshold
+    int* s_ncand = s_thr + 1;                                             // [1] candidates published for the merge
+    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_ncand + 1) + 15) & ~(uintptr_t)15);
+    u64* s_cand = s_wq + (size_t)nwarps * a.Pw;                           // [nwarps * Pw] published candidates
+    unsigned char* misc_end = reinterpret_cast<unsigned char*>(s_cand + (size_t)nwarps * a.Pw);
+    const uint32_t dyn_abs = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t tab_abs = (dyn_abs + (uint32_t)(misc_end - smem_raw) + 65535u) & ~65535u;
+    float* s_lut = reinterpret_cast<float*>(smem_raw + (tab_abs - dyn_abs)); // NTAB x [256][64]
+    if (tab_abs - dyn_abs + NTAB * 65536u > (uint32_t)a.smem_bytes) {
+        if (tid == 0 && blockIdx.x == 0 && a.status) *a.status = 1;
+        return;
+    }
+
+    const int order_max = (a.metric == VIX_METRIC_IP);
+    const float lut_scale = order_max ? 1.0f : -2.0f;
+    u64* wq = s_wq + (size_t)warp * a.Pw;
+    unsigned long long scanned_local = 0;
+    volatile uint32_t* cta_thr = reinterpret_cast<volatile uint32_t*>(s_thr);
+
+    // per-lane look-up constants: table address | 4 * (16 * replica + ((b ^ lane) & 15))
+    uint32_t pre[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        pre[b] = tab_abs | (4u * (16u * (lane >> 4) + ((b ^ lane) & 15)));
+        asm volatile("" : "+r"(pre[b]));      // opaque: keep the 16 constants in registers, never recompute them
+    }
+
+    if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); *s_ncand = 0; }
+    __syncthreads();
+    int buf = 0;
+    bool have_prev = false;
+    int64_t prev_qi = 0;
+    for (;;) {
+        const int item = s_item[buf];
+        const bool more = item < a.nq;
+        const int64_t qi = more ? (a.order ? a.order[item] : item) : 0;
+        const float* q = a.queries + qi * (int64_t)a.d;
+        const int32_t* qprobes = a.probes + qi * (int64_t)a.nprobe;
+
+        if (warp == 0) {
+            // ---- select the k best of the candidates the warps published for the PREVIOUS query, while
+            //      the other warps already build this query's table.  Keys are unique, so "the smallest key
+            //      greater than the last one taken" walks them in order without mutating anything.
+            if (have_prev) {
+                select_and_write(s_cand, *s_ncand, a.k, order_max, prev_qi, a.out_dist, a.out_ids);
+                __syncwarp();
+                if (lane == 0) *s_ncand = 0;
+            }
+        } else if (more) {
+            // ---- prologue of this query (warps 1..) ----
+            if (tid == 32) { s_item[buf ^ 1] = atomicAdd(a.work_counter, 1); *cta_thr = 0xFFFFFFFFu; }
+            if (warp == 1)
+                build_probe_table(qprobes, a.bias + qi * (int64_t)a.nprobe, a.nprobe, a.list_off, a.list_len, s_start,
+                                  s_len, s_pref, s_bias);
+            else
+                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid - 64, (int)blockDim.x - 64);
+        }
+        __syncthreads();                                   // (1) table, probe table, bias ready; merge done
+        if (!more) break;
+
+        // ---- scan: warp-strided over 32-slot chunks of the probed lists ----
+        const int nchunks = s_pref[a.nprobe];
+        int cnt = 0;                                       // unsorted candidates behind the k sorted ones
+        bool sorted_valid = false;                         // wq[0, k) holds a sorted best list
+        uint32_t thr_u = 0xFFFFFFFFu;
+        int p = 0;
+        uint4 wA[G], wB[G];
+        int ch = warp;
+        int cp = 0;
+        int64_t cg = 0;
+        bool cvalid = false;
+        float ctx_ = 0.0f;                                 // t_x of the current chunk's vector (prefetched)
+        if (ch < nchunks) {
+            while (ch >= s_pref[p + 1]) ++p;
+            const int within = (ch - s_pref[p]) * 32 + lane;
+            cp = p; cvalid = within < s_len[p];
+            cg = ((int64_t)s_start[p] << 5) + within;
+            load_codes<G>(wA, a.slot_codes, cg, cvalid);
+            ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;
+        }
+        // one chunk: prefetch this warp's next chunk into wn, look the current one (wc) up, select
+        auto do_chunk = [&](uint4 (&wc)[G], uint4 (&wn)[G]) {
+            const float tx = ctx_;
+            const int64_t g = cg;
+            const bool valid = cvalid;
+            const float bias = s_bias[cp];
+#define VIX_ADVANCE()                                                         \
+            ch += nwarps;                                                         \
+            if (ch < nchunks) {                                                   \
+                while (ch >= s_pref[p + 1]) ++p;                                  \
+                const int within = (ch - s_pref[p]) * 32 + lane;                  \
+                cp = p; cvalid = within < s_len[p];                               \
+                cg = ((int64_t)s_start[p] << 5) + within;                         \
+                load_codes<G>(wn, a.slot_codes, cg, cvalid);                      \
+                ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;                     \
+            }
+#ifndef VIX_SCAN_NOPREFETCH
+            VIX_ADVANCE()
+#endif
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            lookup16<0>(wc[0], pre, s0, s1, s2, s3);
+            if (G > 1) lookup16<1>(wc[G > 1 ? 1 : 0], pre, s0, s1, s2, s3);
+            if (G > 2) lookup16<2>(wc[G > 2 ? 2 : 0], pre, s0, s1, s2, s3);
+            if (G > 3) lookup16<3>(wc[G > 3 ? 3 : 0], pre, s0, s1, s2, s3);
+#ifdef VIX_SCAN_NOPREFETCH
+            VIX_ADVANCE()
+#endif
+#undef VIX_ADVANCE
+            const float sum = (bias + tx) + ((s0 + s1) + (s2 + s3));
+            if (valid) ++scanned_local;
+            {
+                const uint32_t t = *cta_thr;
+                if (t < thr_u) thr_u = t;
+            }
+            const u64 key = make_key(sum, 0u, order_max);
+            const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
+            if (thr_u == 0xFFFFFFFFu && a.k <= 32) {
+                // no threshold yet: the k-th smallest of this chunk bounds the final k-th best
+                const uint32_t kth = warp_kth_smallest(ku, a.k - 1, lane);
+                if (kth != 0xFFFFFFFFu) {
+                    thr_u = kth;
+                    if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(s_thr), kth);
+                }
+            }
+            const bool pass = valid && (ku <= thr_u);
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
+            if (ball) {
+                if (cnt + 32 > a.Pw - a.k) {
+                    thr_u = flush_queue(wq, a.Pw, a.k, cnt, sorted_valid, thr_u, s_thr);   // make room: keep the k best
+                    cnt = 0; sorted_valid = true;
+                }
+                if (pass) {
+                    const uint32_t id = (uint32_t)a.slot_ids[g];
+                    wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)id;
+                }
+                cnt += __popc(ball);
+                __syncwarp();
+            }
+        };
+#ifdef VIX_SCAN_NOPREFETCH
+        (void)wB;
+        while (ch < nchunks) do_chunk(wA, wA);
+#else
+        while (ch < nchunks) {
+            do_chunk(wA, wB);
+            if (ch >= nchunks) break;
+            do_chunk(wB, wA);
+        }
+#endif
+        // ---- publish the entries that can still make the top k into the CTA candidate buffer ----
+        {
+            const uint32_t t = *cta_thr;
+            if (t < thr_u) thr_u = t;
+            const int lo = sorted_valid ? 0 : a.k;
+            const int hi = a.k + cnt;
+            for (int base = lo; base < hi; base += 32) {
+                const int i = base + lane;
+                const u64 key = (i < hi) ? wq[i] : kEmptyKey;
+                const bool keep = key != kEmptyKey && (uint32_t)(key >> 32) <= thr_u;
+                const unsigned ball = __ballot_sync(0xFFFFFFFFu, keep);
+                if (ball) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(s_ncand, __popc(ball));
+                    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                    if (keep) s_cand[pos + __popc(ball & ((1u << lane) - 1u))] = key;
+                }
+            }
+        }
+        __syncthreads();                                   // (2) scan finished everywhere, candidates published
+        have_prev = true;
+        prev_qi = qi;
+        buf ^= 1;
     }
     if (a.scanned) {
         for (int o = 16; o > 0; o >>= 1) scanned_local += __shfl_xor_sync(0xFFFFFFFFu, scanned_local, o);
@@ -470,50 +601,49 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
 // ------------------------------------------------------------------------------------------------
 ScanLayout scan_layout(int m) {
     ScanLayout L;
-    const int F = m / 32, R = m % 32;
-    const bool fast = m > 0 && m <= 128 && (R == 0 || R == 16 || (R == 8 && F == 0));
-    L.fast = fast;
-    L.ng = fast ? (R == 0 ? 1 : 32 / R) : 1;
-    L.align = 32 * L.ng;
+    L.fast = m > 0 && m % 16 == 0 && m <= 64;
+    L.align = 32;
     return L;
 }
 
-static size_t scan_smem_bytes(const ScanArgs& a, const ScanLayout& L) {
-    size_t s;
-    if (L.fast) {
-        const int slots = 32 * (a.m / 32 + ((a.m % 32) ? 1 : 0));
-        s = (size_t)((slots + 63) / 64) * 65536;
-    } else {
-        s = (size_t)a.m * 256 * 4;
-    }
-    s += (size_t)a.d * 4 + (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 8 + 16;
+static size_t generic_smem_bytes(const ScanArgs& a) {
+    size_t s = (size_t)a.m * 256 * 4;
+    s += (size_t)a.d * 4 + (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16;
     s += (size_t)kScanWarps * a.Pw * 8 + (size_t)a.P2 * 8;
     return s;
 }
 
-template <int F, int R>
-static int launch_fast(ScanArgs& a, size_t smem) {
-    auto kern = ivfpq_scan_kernel<F, R>;
+template <int G>
+static int launch_fast(ScanArgs& a) {
+    constexpr int NTAB = (G + 1) / 2;
+    // as many warps as the per-warp selection queues leave room for (24 unless k is large)
+    int nwarps = kFastThreads / 32;
+    while (nwarps > 3 && 2 * (size_t)nwarps * a.Pw * 8 > 56 * 1024) --nwarps;
+    size_t misc = (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16 + 16 + 2 * (size_t)nwarps * a.Pw * 8;
+    // the tables start at the next 64 KB boundary of the shared window, wherever the dynamic segment begins
+    size_t smem = misc + 65535 + (size_t)NTAB * 65536;
+    if (smem > 227 * 1024) smem = 227 * 1024;
+    VIX_REQUIRE(misc + 1024 <= 65536 && (size_t)(NTAB + 1) * 65536 <= smem + 1024 + 65535, VIX_ERR_UNSUPPORTED,
+                "ivfpq scan: k = %d, nprobe = %d need %zu bytes of bookkeeping shared memory", a.k, a.nprobe, misc);
+    a.smem_bytes = (int)smem;
+    auto kern = ivfpq_scan_kernel<G>;
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    VIX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, smem));
-    if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)num_sms() * occ;
+    int64_t grid = num_sms();
     if (grid > a.nq) grid = a.nq;
-    kern<<<(unsigned)grid, kScanThreads, smem, ctx().stream>>>(a);
+    kern<<<(unsigned)grid, 32 * nwarps, smem, ctx().stream>>>(a);
     VIX_LAUNCH_CHECK();
     return VIX_OK;
 }
 
 int launch_ivfpq_scan(ScanArgs& a) {
-    a.Pw = next_pow2(a.k + 32);
-    a.P2 = next_pow2(kScanWarps * a.k);
     const ScanLayout L = scan_layout(a.m);
-    const size_t smem = scan_smem_bytes(a, L);
-    VIX_REQUIRE(smem <= 227 * 1024, VIX_ERR_UNSUPPORTED,
-                "ivfpq scan: m = %d, k = %d, nprobe = %d need %zu bytes of shared memory", a.m, a.k, a.nprobe, smem);
-    VIX_REQUIRE(a.nprobe <= kScanThreads, VIX_ERR_INVALID_K, "ivfpq scan: nprobe > %d", kScanThreads);
     if (!L.fast) {
+        a.Pw = next_pow2(a.k + 32);
+        a.P2 = next_pow2(kScanWarps * a.k);
+        const size_t smem = generic_smem_bytes(a);
+        VIX_REQUIRE(smem <= 227 * 1024, VIX_ERR_UNSUPPORTED,
+                    "ivfpq scan: m = %d, k = %d, nprobe = %d need %zu bytes of shared memory", a.m, a.k, a.nprobe, smem);
+        VIX_REQUIRE(a.nprobe <= kScanThreads, VIX_ERR_INVALID_K, "ivfpq scan: nprobe > %d", kScanThreads);
         VIX_CUDA(cudaFuncSetAttribute(ivfpq_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         VIX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ivfpq_scan_generic_kernel, kScanThreads, smem));
@@ -523,18 +653,24 @@ int launch_ivfpq_scan(ScanArgs& a) {
         VIX_LAUNCH_CHECK();
         return VIX_OK;
     }
+    a.Pw = next_pow2(a.k + 64);
+    a.P2 = 0;
+    VIX_REQUIRE(a.nprobe <= 256, VIX_ERR_INVALID_K, "ivfpq scan: nprobe > 256");
     VIX_REQUIRE(a.work_counter != nullptr, VIX_ERR_NULL_PTR, "ivfpq scan: work counter missing");
-    VIX_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), ctx().stream));
+    VIX_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int), ctx().stream));
+    a.status = a.work_counter + 1;
+    Scratch<float> bias;
+    const int64_t npairs = a.nq * (int64_t)a.nprobe;
+    VIX_TRY(bias.alloc((size_t)npairs));
+    probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
+        a.queries, a.probes, a.coarse, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
+    VIX_LAUNCH_CHECK();
+    a.bias = bias.ptr;
     switch (a.m) {
-        case 8:   return launch_fast<0, 8>(a, smem);
-        case 16:  return launch_fast<0, 16>(a, smem);
-        case 32:  return launch_fast<1, 0>(a, smem);
-        case 48:  return launch_fast<1, 16>(a, smem);
-        case 64:  return launch_fast<2, 0>(a, smem);
-        case 80:  return launch_fast<2, 16>(a, smem);
-        case 96:  return launch_fast<3, 0>(a, smem);
-        case 112: return launch_fast<3, 16>(a, smem);
-        case 128: return launch_fast<4, 0>(a, smem);
+        case 16: return launch_fast<1>(a);
+        case 32: return launch_fast<2>(a);
+        case 48: return launch_fast<3>(a);
+        case 64: return launch_fast<4>(a);
     }
     set_error("ivfpq scan: unsupported m = %d", a.m);
     return VIX_ERR_UNSUPPORTED;

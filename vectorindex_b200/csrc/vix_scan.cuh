@@ -10,8 +10,11 @@ struct ScanArgs {
     const float* queries; int64_t nq; int d, m, ks, dsub;
     const int32_t* probes; int nprobe;            // [nq x nprobe], -1 padded
     const int32_t* order;                         // optional [nq]: work item -> query (locality order)
-    int* work_counter;                            // device int, zeroed by the launcher
+    int* work_counter;                            // device int[2], zeroed by the launcher: [0] queue head, [1] status
+    int* status;                                  // set by the launcher (= work_counter + 1)
+    int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
     const float* coarse;                          // [kc x d]
+    const float* bias;                            // [nq x nprobe] per-probe term ||q - c||^2 (L2) / <q, c> (IP)
     const float* codebooks;                       // [m x ks x dsub]
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
     const int64_t* list_off; const int32_t* list_len;
@@ -22,13 +25,12 @@ struct ScanArgs {
 };
 
 // How the inverted lists are laid out for a given m.
-//   fast:  lists start at multiples of `align` slots; inside every 32-slot block the codes are stored
-//          transposed, [sub-quantiser][vector] (32 bytes per sub-quantiser);
-//   else:  plain AoS rows, lists 32-aligned.
+//   fast:  AoS rows with the 16 codes of every group of 16 sub-quantisers "rotated" by the slot index:
+//          byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15);
+//   else:  plain AoS rows.  Lists start at multiples of `align` slots either way.
 struct ScanLayout {
     bool fast;
-    int ng;       // 32-slot blocks a warp works on at once
-    int align;    // list start / padded length granularity in slots (32 * ng)
+    int align;    // list start / padded length granularity in slots
 };
 ScanLayout scan_layout(int m);
 
