@@ -285,6 +285,11 @@ int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k,
 int vix_index_trace(vix_index_t* h, int capacity);
 int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out);
 
+/* Test hook (not part of the reference surface): the raw TF32 tensor-core scores S~ of the shortlist pass
+ * (vix_gemm.cu), out[nq x kc]; device pointers only. */
+int vix_debug_tc_scores_f32(const float* queries, int64_t nq, const float* centroids, int kc, int d, int metric,
+                            const float* centroid_norms, float* out);
+
 /* a16  AccelerableIndex-shaped convenience (AccelerableIndex.swift:15-127): candidates [c x d]
  * contiguous in, (indices into candidates, distances) out, per query. */
 int vix_accel_rank_candidates_f32(const float* queries, int64_t nq, const float* candidates, int64_t c,

@@ -212,6 +212,45 @@ def test_select_and_merge_topk(oracle, vk):
         assert np.array_equal(bits(gs[b, :ms.size]), bits(ms + np.float32(0)))   # keys canonicalise -0 to +0
 
 
+# ------------------------------------------------------------------------------------------------ tensor-core shortlist
+@pytest.mark.parametrize("nq,kc,d,metric", [(300, 2048, 96, 0), (257, 1500, 128, 1), (130, 4096, 100, 0), (64, 1024, 768, 1)])
+def test_tensor_core_scores_within_tf32_bound(vk, nq, kc, d, metric):
+    """raw tcgen05 (kind::tf32) scores of the shortlist pass: |S~ - S| <= the bound the threshold uses."""
+    import ctypes as C
+    import torch
+    from vectorindex_b200 import _lib
+    rng = np.random.default_rng(nq + kc)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    c = rng.standard_normal((kc, d)).astype(np.float32) * 2
+    cn = (c.astype(np.float64) ** 2).sum(1).astype(np.float32)
+    tq, tc_, tn = torch.from_numpy(q).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(cn).cuda()
+    out = torch.empty((nq, kc), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().vix_debug_tc_scores_f32(_lib.ptr(tq), C.c_int64(nq), _lib.ptr(tc_), C.c_int(kc), C.c_int(d),
+                                                  C.c_int(metric), _lib.ptr(tn) if metric == 0 else None, _lib.ptr(out)))
+    got = out.cpu().numpy().astype(np.float64)
+    dot = q.astype(np.float64) @ c.astype(np.float64).T
+    want = cn[None, :].astype(np.float64) - 2 * dot if metric == 0 else -dot
+    rel = (2.0 if metric == 0 else 1.0) * 1.25 * (2.0 / 1024 + d / 4194304.0)
+    bound = rel * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(c, axis=1).max()
+    assert np.all(np.abs(got - want) <= bound), float(np.max(np.abs(got - want) / bound))
+    assert np.max(np.abs(got - want) / bound) > 1e-4          # and it really is the TF32 path, not fp32
+
+
+@pytest.mark.parametrize("nq,kc,d,nprobe,metric", [(500, 4096, 96, 32, 0), (333, 2048, 128, 16, 1), (200, 8192, 64, 64, 0),
+                                                   (150, 3000, 100, 8, 0)])
+def test_tensor_core_probe_selection_is_exact(oracle, vk, nq, kc, d, nprobe, metric):
+    """probe lists through the tensor-core shortlist + exact rescoring == the oracle's, bit for bit (ids and scores),
+    including heavy ties (integer-valued data)."""
+    rng = np.random.default_rng(kc + d)
+    c = np.round(rng.standard_normal((kc, d)) * 3).astype(np.float32)
+    q = np.round(rng.standard_normal((nq, d)) * 3).astype(np.float32)
+    c[kc // 2] = c[kc // 3]                                      # exact duplicate centroids: tie -> lower index
+    oi, os_ = oracle.probe_select_batch(q, c, nprobe, metric)
+    gi, gs = vk.ivf_select_nprobe_batch_f32(q, c, nprobe, metric)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(bits(gs), bits(os_))
+
+
 # ------------------------------------------------------------------------------------------------ coarse probing
 @pytest.mark.parametrize("metric", [0, 1])
 def test_centroid_scores_and_probe_selection(oracle, vk, metric):

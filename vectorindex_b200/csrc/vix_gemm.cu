@@ -1,17 +1,594 @@
-// vix_gemm.cu -- tensor-core (tcgen05) contraction path for the GEMM-shaped stages (coarse probe
-// selection, flat scan).  Round-1 state: the entry point below forwards to the exact CUDA-core
-// kernels of vix_scoring.cu; the tcgen05 + TMA shortlist kernel replaces the body, with the exact
-// kernels kept as the rescoring stage (see DESIGN.md "Tensor-core plan").
+// vix_gemm.cu -- tensor-core shortlist for the GEMM-shaped stages: coarse probe selection (a6-a8), IVF list
+// assignment (a9) and the flat scan (a1-a4).
+//
+// The reference computes these stages as a dense query x centroid (or query x base) contraction followed
+// by a per-row selection (Kernels/CentroidBatchScore.swift:39-88 + IVFIndex.swift:905-927;
+// KMeansMiniBatchKernel.swift:341-359; FlatIndexOptimized.swift:390-477).  Parity is exact (bit-identical
+// ids, tie -> lower index), so the tensor cores cannot produce the final answer -- TF32 drops 13 mantissa
+// bits -- but they can produce a PROVABLY sufficient shortlist:
+//
+//   pass 1  S~ = ||c||^2 - 2 <q, c>  (IP: -<q, c>) on tcgen05 (kind::tf32, operands fed by TMA straight
+//           from the fp32 arrays, accumulators in TMEM).  The epilogue reduces every group of `gcols`
+//           columns of a row to its minimum; nothing else leaves the SM.
+//   select  T_q = (k-th smallest group minimum of row q) + 2 eps_q.  k different groups hold a score
+//           <= that minimum, so the exact k-th best score is <= T_q - eps_q, and every member of the exact
+//           top k has S~ <= T_q  (eps_q bounds |S~ - S| for the row: TF32 truncation + accumulation).
+//   pass 2  the same contraction again (cheaper than keeping 10^9 scores); the epilogue emits the columns
+//           with S~ <= T_q into a per-row candidate list (expected ~1.2 k entries).
+//   exact   the candidates are rescored in the reference's operation order by the exact CUDA-core
+//           kernels and selected by (score, index); rows whose list overflowed fall back to the exact
+//           kernel entirely.
+//
+// Kernel structure (one CTA per SM, persistent over (row tile, column split) work items):
+//   warp 0      TMA producer: A (128 rows x 32 tf32) and B (128 columns x 32 tf32) K-blocks, 128B swizzle,
+//               into a 5-stage shared-memory ring guarded by full/empty mbarriers
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma M128 N128 K8 (4 per K-block); tcgen05.commit
+//               releases ring slots and publishes finished accumulators; two accumulator buffers in TMEM
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns), fused ||c||^2 term, group minima / emission
+// Every mbarrier wait is bounded (a stuck pipeline raises an error flag instead of hanging the GPU).
 #include "vix_common.cuh"
+#include "vix_exact.cuh"
+#include "vix_topk.cuh"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 namespace vix {
 
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                         const float* cnorm, const uint64_t* disabled, int32_t* out_idx, float* out_scores);
+int row_norms_device(const float* x, int64_t n, int d, float* out);
 
+namespace tc {
+
+constexpr int kM = 128, kN = 128, kKB = 32;            // tile rows, tile columns, tf32 elements per K-block
+constexpr int kStages = 5;
+constexpr int kStageBytes = (kM + kN) * kKB * 4;       // 32 KB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;                         // two fp32 accumulators of 128 columns
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+enum Mode { MODE_WRITE = 0, MODE_MIN = 1, MODE_EMIT = 2 };
+
+struct Args {
+    int64_t nA;            // rows (queries / vectors)
+    int nB;                // columns (centroids / base rows)
+    int kblocks;           // ceil(d / 32)
+    int ntiles;            // ceil(nB / 128)
+    int tiles_per_split, nsplit, mtiles;
+    int mode, metric;
+    const float* bnorm;    // [nB] ||c||^2 (L2) or nullptr
+    int gcols, ngroups;    // MODE_MIN: columns per group (32, 64 or a multiple of 128), groups per row
+    float* gmin;           // MODE_MIN: [nA x ngroups]
+    const float* thr;      // MODE_EMIT: [nA]
+    int* cand_cnt;         // MODE_EMIT: [nA]
+    int32_t* cand_idx;     // MODE_EMIT: [nA x cap]
+    int cap;
+    float* out;            // MODE_WRITE: [nA x nB]
+    int* error;            // set to 1 when a barrier wait times out
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: ~2 s at 2 GHz, then raise the error flag and give up
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(error) != 0) {
+            atomicExch(error, 1);
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile [rows][32 tf32] = rows x 128 B, 128B swizzle (8-row atoms of 1024 B): SBO = 1024 B
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024 B alignment for the swizzle atoms
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = base;                                                      // kStages x (A 16 KB | B 16 KB)
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageBytes);   // [kStages]
+    uint64_t* empty = full + kStages;                                                // [kStages]
+    uint64_t* tfull = empty + kStages;                                               // [2]
+    uint64_t* tempty = tfull + 2;                                                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [4 warps][2][128] column norms
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nitems = a.mtiles * a.nsplit;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            bool ok = true;
+            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+                const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+                const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
+                for (int nt = nt0; nt < nt1 && ok; ++nt) {
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        if (!mbar_wait(empty + stage, phase ^ 1, a.error)) { ok = false; break; }
+                        unsigned char* sA = ring + (size_t)stage * kStageBytes;
+                        mbar_expect_tx(full + stage, kStageBytes);
+                        tma_load_2d(sA, &mapA, full + stage, kb * kKB, mt * kM);
+                        tma_load_2d(sA + kM * kKB * 4, &mapB, full + stage, kb * kKB, nt * kN);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t aphase = 0;
+            bool ok = true;
+            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+                const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+                const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
+                (void)mt;
+                for (int nt = nt0; nt < nt1 && ok; ++nt) {
+                    if (!mbar_wait(tempty + acc, aphase ^ 1, a.error)) { ok = false; break; }
+                    fence_after_sync();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)acc * kN;
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        if (!mbar_wait(full + stage, phase, a.error)) { ok = false; break; }
+                        fence_after_sync();
+                        const uint32_t sA = smem_u32(ring + (size_t)stage * kStageBytes);
+                        const uint64_t da = make_desc(sA), db = make_desc(sA + kM * kKB * 4);
+#pragma unroll
+                        for (int k = 0; k < kKB / 8; ++k)      // K = 8 tf32 (32 B) per instruction: +2 in 16 B units
+                            mma_tf32(tmem_d, da + 2 * k, db + 2 * k, (kb | k) ? 1u : 0u);
+                        mma_commit(empty + stage);             // frees the ring slot when these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    if (!ok) break;
+                    mma_commit(tfull + acc);                   // accumulator complete
+                    if (++acc == 2) { acc = 0; aphase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t aphase = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+            const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
+            const int64_t row = (int64_t)mt * kM + quarter * 32 + lane;
+            const bool row_ok = row < a.nA;
+            const float thr = (a.mode == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
+            float gmin = INFINITY;
+            for (int nt = nt0; nt < nt1 && ok; ++nt) {
+                // stage this tile's column norms (one private copy per warp: no CTA-level barrier needed)
+                float* bn = s_bn + ((warp - 2) * 2 + acc) * kN;
+#pragma unroll
+                for (int t = 0; t < kN / 32; ++t) {
+                    const int col = nt * kN + t * 32 + lane;
+                    bn[t * 32 + lane] = (a.bnorm && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
+                }
+                __syncwarp();
+                if (!mbar_wait(tfull + acc, aphase, a.error)) { ok = false; break; }
+                fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN;
+                const int colbase = nt * kN;
+                const bool full_tile = colbase + kN <= a.nB;
+#pragma unroll 1
+                for (int ck = 0; ck < kN / 32; ++ck) {
+                    float v[32];
+                    tmem_ld32(taddr + ck * 32, v);
+                    float cmin = INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = colbase + ck * 32 + i;
+                        float s = (a.metric == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], bn[ck * 32 + i]) : -v[i];
+                        if (!full_tile && col >= a.nB) s = INFINITY;
+                        if (a.mode == MODE_WRITE) {
+                            if (row_ok && col < a.nB) a.out[row * a.nB + col] = s;
+                        } else if (a.mode == MODE_MIN) {
+                            cmin = fminf(cmin, s);
+                        } else {
+                            if (s <= thr) {
+                                const int pos = atomicAdd(a.cand_cnt + row, 1);
+                                if (pos < a.cap) a.cand_idx[row * a.cap + pos] = col;
+                            }
+                        }
+                    }
+                    if (a.mode == MODE_MIN) {
+                        gmin = fminf(gmin, cmin);
+                        // group boundary: gcols is 32, 64 or a multiple of 128 that divides the split
+                        const int colend = colbase + ck * 32 + 32;
+                        if (colend % a.gcols == 0 || (nt == a.ntiles - 1 && ck == kN / 32 - 1)) {
+                            const int g = (colend - 1) / a.gcols;
+                            if (row_ok && g < a.ngroups) a.gmin[row * a.ngroups + g] = gmin;
+                            gmin = INFINITY;
+                        }
+                    }
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + acc);      // 4 arrivals free the accumulator
+                if (++acc == 2) { acc = 0; aphase ^= 1; }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// rows x d fp32 row-major, box = 32 columns (128 B) x 128 rows, 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int d) {
+    EncodeTiledFn fn = encode_fn();
+    VIX_REQUIRE(fn != nullptr, VIX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VIX_REQUIRE(r == CUDA_SUCCESS, VIX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %lld x %d operand", (int)r,
+                (long long)rows, d);
+    return VIX_OK;
+}
+
+bool supported(int64_t nA, int64_t nB, int d, const float* A, const float* B) {
+    if (nA <= 0 || nB <= 0 || d < 4 || (d & 3) != 0) return false;            // TMA: 16-byte row pitch
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+    if (nB >= (1LL << 31) - kN) return false;
+    return encode_fn() != nullptr;
+}
+
+static size_t smem_bytes() { return (size_t)kStages * kStageBytes + 1024 + 256 + 4 * 2 * kN * 4; }
+
+static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Args& a) {
+    CUtensorMap mapA, mapB;
+    VIX_TRY(make_map(&mapA, A, nA, d));
+    VIX_TRY(make_map(&mapB, B, nB, d));
+    a.nA = nA; a.nB = nB;
+    a.kblocks = (d + kKB - 1) / kKB;
+    a.ntiles = (nB + kN - 1) / kN;
+    a.mtiles = (int)((nA + kM - 1) / kM);
+    // column splits: enough work items for ~3 waves of the SMs; in MODE_MIN a split is a whole number of groups
+    int nsplit = (3 * num_sms() + a.mtiles - 1) / a.mtiles;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > a.ntiles) nsplit = a.ntiles;
+    int tps = (a.ntiles + nsplit - 1) / nsplit;
+    if (a.mode == MODE_MIN && a.gcols > kN) {
+        const int tpg = a.gcols / kN;
+        tps = (tps + tpg - 1) / tpg * tpg;
+    }
+    a.tiles_per_split = tps;
+    a.nsplit = (a.ntiles + tps - 1) / tps;
+    const size_t smem = smem_bytes();
+    VIX_CUDA(cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)a.mtiles * a.nsplit;
+    if (grid > num_sms()) grid = num_sms();
+    tc_score_kernel<<<(unsigned)grid, kThreads, smem, ctx().stream>>>(mapA, mapB, a);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- thresholds
+// T_q = (k-th smallest group minimum of the row) + margin_q; one CTA per row, bitonic sort of <= 2048 minima
+__global__ void __launch_bounds__(256)
+threshold_kernel(const float* __restrict__ gmin, int ngroups, int P, int k, const float* __restrict__ anorm,
+                 const float* __restrict__ bnorm_max, float rel, float* __restrict__ thr) {
+    extern __shared__ __align__(16) unsigned char smem_thr[];
+    uint32_t* s = reinterpret_cast<uint32_t*>(smem_thr);
+    const int64_t row = blockIdx.x;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        s[i] = (i < ngroups) ? f32_orderable(gmin[row * ngroups + i]) : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint32_t x = s[lo], y = s[hi];
+                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        const float kth = (k - 1 < ngroups) ? f32_from_orderable(s[k - 1]) : INFINITY;
+        // |S~ - S| <= rel * ||q|| * max||c||  (TF32 operand truncation 2 * 2^-10 + fp32 accumulation, with margin)
+        const float eps = rel * sqrtf(anorm[row]) * bnorm_max[0];
+        thr[row] = kth + 2.0f * eps;
+    }
+}
+
+__global__ void max_sqrt_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    // single CTA: out[0] = sqrt(max x)
+    __shared__ float s[256];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+    s[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] = fmaxf(s[threadIdx.x], s[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = sqrtf(s[0]);
+}
+
+// ---------------------------------------------------------------------------------------------- exact rescoring
+// One CTA per row: exact CentroidBatchScore value of every candidate in the reference's operation order
+// (sequential dot, then -2 s + ||c||^2 / -s; Kernels/CentroidBatchScore.swift:54-64), keys (score, index),
+// bitonic sort, best `k` out.  Rows whose candidate list overflowed are flagged for the exact fallback.
+__global__ void __launch_bounds__(256)
+rescore_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int d, int metric,
+                     const float* __restrict__ bnorm, const int* __restrict__ cand_cnt,
+                     const int32_t* __restrict__ cand_idx, int cap, int P, int k, int32_t* __restrict__ out_idx,
+                     float* __restrict__ out_scores, int* __restrict__ overflow_rows, int* __restrict__ n_overflow) {
+    extern __shared__ __align__(16) unsigned char smem_rs[];
+    u64* keys = reinterpret_cast<u64*>(smem_rs);
+    float* sq = reinterpret_cast<float*>(keys + P);
+    const int64_t row = blockIdx.x;
+    const int n = cand_cnt[row];
+    if (n > cap) {
+        if (threadIdx.x == 0) overflow_rows[atomicAdd(n_overflow, 1)] = (int)row;
+        return;
+    }
+    for (int e = threadIdx.x; e < d; e += blockDim.x) sq[e] = A[row * d + e];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = kEmptyKey;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = cand_idx[row * cap + i];
+        const float dot = exact_pair<SpecSeqDot>(sq, B + (int64_t)c * d, d);
+        const float s = (metric == VIX_METRIC_L2) ? fadd(fmul(-2.0f, dot), bnorm[c]) : fmul(-1.0f, dot);
+        keys[i] = make_key(s, (uint32_t)c, 0);
+    }
+    __syncthreads();
+    bitonic_sort_keys<false>(keys, P, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const u64 key = keys[i];
+        const size_t o = (size_t)row * k + i;
+        if (key == kEmptyKey) { out_idx[o] = -1; if (out_scores) out_scores[o] = __int_as_float(0x7fc00000); }
+        else { out_idx[o] = (int32_t)key_id(key); if (out_scores) out_scores[o] = key_score(key, 0); }
+    }
+}
+
+__global__ void gather_rows_f32_kernel(const float* __restrict__ x, int d, const int* __restrict__ rows, int n,
+                                       float* __restrict__ out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) out[(int64_t)i * d + e] = x[(int64_t)rows[i] * d + e];
+}
+__global__ void scatter_probe_rows_kernel(const int32_t* __restrict__ idx, const float* __restrict__ sc, int k,
+                                          const int* __restrict__ rows, int n, int32_t* __restrict__ out_idx,
+                                          float* __restrict__ out_sc) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int e = threadIdx.x; e < k; e += blockDim.x) {
+        out_idx[(int64_t)rows[i] * k + e] = idx[(int64_t)i * k + e];
+        if (out_sc) out_sc[(int64_t)rows[i] * k + e] = sc[(int64_t)i * k + e];
+    }
+}
+
+// columns per group so that a row has between ~4 k and 2048 group minima
+static int choose_gcols(int nB, int k) {
+    int g = 32;
+    while ((nB + g - 1) / g > 2048) g *= 2;
+    while (g < 128 && (nB + g - 1) / g > 64 * k && (nB + 2 * g - 1) / (2 * g) >= 8 * k) g *= 2;
+    return g;
+}
+
+}  // namespace tc
+
+// Debug / test entry: the raw tensor-core scores S~ (MODE_WRITE)
+int tc_scores_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, const float* cnorm,
+                     float* out) {
+    VIX_REQUIRE(tc::supported(nq, kc, d, q, c), VIX_ERR_UNSUPPORTED, "tensor-core path needs d %% 4 == 0 and 16-byte aligned operands");
+    Scratch<int> err;
+    VIX_TRY(err.alloc(1));
+    VIX_CUDA(cudaMemsetAsync(err.ptr, 0, 4, ctx().stream));
+    tc::Args a{};
+    a.mode = tc::MODE_WRITE; a.metric = metric; a.bnorm = cnorm; a.out = out; a.error = err.ptr;
+    a.gcols = 32; a.ngroups = 0;
+    VIX_TRY(tc::launch(q, nq, c, kc, d, a));
+    int herr = 0;
+    VIX_CUDA(cudaMemcpyAsync(&herr, err.ptr, 4, cudaMemcpyDeviceToHost, ctx().stream));
+    VIX_CUDA(cudaStreamSynchronize(ctx().stream));
+    VIX_REQUIRE(herr == 0, VIX_ERR_CUDA, "tensor-core pipeline timed out");
+    return VIX_OK;
+}
+
+// Probe selection through the tensor-core shortlist; results identical to probe_select_device.
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                              const float* cnorm, int32_t* out_idx, float* out_scores) {
-    return probe_select_device(q, nq, c, kc, d, metric, nprobe, cnorm, nullptr, out_idx, out_scores);
+    const int keff = nprobe < kc ? nprobe : kc;
+    const int gcols = tc::choose_gcols(kc, keff);
+    const int ngroups = (kc + gcols - 1) / gcols;
+    const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && tc::supported(nq, kc, d, q, c) && kc >= 1024 && nq >= 16 &&
+                        ngroups >= 2 * keff && keff <= 256 && d <= 4096 && (metric == VIX_METRIC_IP || cnorm != nullptr);
+    if (!use_tc) return probe_select_device(q, nq, c, kc, d, metric, nprobe, cnorm, nullptr, out_idx, out_scores);
+    cudaStream_t s = ctx().stream;
+    const int cap = keff * 4 + 128;
+    Scratch<float> gmin, thr, qn, cn_tmp, cmax;
+    Scratch<int> cand_cnt, flags, ovf_rows;
+    Scratch<int32_t> cand_idx;
+    VIX_TRY(gmin.alloc((size_t)nq * ngroups));
+    VIX_TRY(thr.alloc((size_t)nq));
+    VIX_TRY(qn.alloc((size_t)nq));
+    VIX_TRY(cmax.alloc(1));
+    VIX_TRY(cand_cnt.alloc((size_t)nq));
+    VIX_TRY(cand_idx.alloc((size_t)nq * cap));
+    VIX_TRY(flags.alloc(2));                           // [0] pipeline error, [1] number of overflow rows
+    VIX_TRY(ovf_rows.alloc((size_t)nq));
+    VIX_CUDA(cudaMemsetAsync(flags.ptr, 0, 8, s));
+    VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
+    VIX_TRY(row_norms_device(q, nq, d, qn.ptr));
+    const float* cn = cnorm;
+    if (!cn) { VIX_TRY(cn_tmp.alloc((size_t)kc)); VIX_TRY(row_norms_device(c, kc, d, cn_tmp.ptr)); cn = cn_tmp.ptr; }
+    tc::max_sqrt_kernel<<<1, 256, 0, s>>>(cn, kc, cmax.ptr);
+    VIX_LAUNCH_CHECK();
+
+    tc::Args a{};
+    a.metric = metric; a.bnorm = (metric == VIX_METRIC_L2) ? cn : nullptr; a.error = flags.ptr;
+    a.mode = tc::MODE_MIN; a.gcols = gcols; a.ngroups = ngroups; a.gmin = gmin.ptr;
+    VIX_TRY(tc::launch(q, nq, c, kc, d, a));
+    // |S~ - S|: dot error (2 * 2^-10 truncation + d * 2^-22 accumulation) * ||q|| ||c||, doubled for the L2 score
+    const float rel = ((metric == VIX_METRIC_L2) ? 2.0f : 1.0f) * 1.25f * (2.0f / 1024.0f + (float)d / 4194304.0f);
+    {
+        int P = next_pow2(ngroups < 2 ? 2 : ngroups);
+        tc::threshold_kernel<<<(unsigned)nq, 256, (size_t)P * 4, s>>>(gmin.ptr, ngroups, P, keff, qn.ptr, cmax.ptr, rel, thr.ptr);
+        VIX_LAUNCH_CHECK();
+    }
+    a.mode = tc::MODE_EMIT; a.thr = thr.ptr; a.cand_cnt = cand_cnt.ptr; a.cand_idx = cand_idx.ptr; a.cap = cap;
+    VIX_TRY(tc::launch(q, nq, c, kc, d, a));
+    {
+        const int P = next_pow2(cap);
+        const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+        VIX_CUDA(cudaFuncSetAttribute(tc::rescore_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::rescore_probe_kernel<<<(unsigned)nq, 256, smem, s>>>(q, c, d, metric, cn, cand_cnt.ptr, cand_idx.ptr, cap, P, nprobe,
+                                                               out_idx, out_scores, ovf_rows.ptr, flags.ptr + 1);
+        VIX_LAUNCH_CHECK();
+    }
+    int hflags[2] = {0, 0};
+    VIX_CUDA(cudaMemcpyAsync(hflags, flags.ptr, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    VIX_REQUIRE(hflags[0] == 0, VIX_ERR_CUDA, "tensor-core pipeline timed out");
+    if (hflags[1] > 0) {
+        // rows whose shortlist overflowed: exact kernel on the gathered rows
+        const int n = hflags[1];
+        Scratch<float> sub, sub_sc;
+        Scratch<int32_t> sub_idx;
+        VIX_TRY(sub.alloc((size_t)n * d));
+        VIX_TRY(sub_idx.alloc((size_t)n * nprobe));
+        VIX_TRY(sub_sc.alloc((size_t)n * nprobe));
+        tc::gather_rows_f32_kernel<<<n, 128, 0, s>>>(q, d, ovf_rows.ptr, n, sub.ptr);
+        VIX_LAUNCH_CHECK();
+        VIX_TRY(probe_select_device(sub.ptr, n, c, kc, d, metric, nprobe, cn, nullptr, sub_idx.ptr, sub_sc.ptr));
+        tc::scatter_probe_rows_kernel<<<n, 128, 0, s>>>(sub_idx.ptr, sub_sc.ptr, nprobe, ovf_rows.ptr, n, out_idx, out_scores);
+        VIX_LAUNCH_CHECK();
+    }
+    return VIX_OK;
 }
 
 }  // namespace vix
+
+using namespace vix;
+
+extern "C" {
+
+/* test hook: raw tensor-core scores of the shortlist pass (not part of the reference surface) */
+int vix_debug_tc_scores_f32(const float* queries, int64_t nq, const float* centroids, int kc, int d, int metric,
+                            const float* centroid_norms, float* out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(queries && centroids && out, VIX_ERR_NULL_PTR, "vix_debug_tc_scores_f32: null pointer");
+    VIX_REQUIRE(is_device_ptr(queries) && is_device_ptr(centroids) && is_device_ptr(out) &&
+                    (centroid_norms == nullptr || is_device_ptr(centroid_norms)),
+                VIX_ERR_INVALID_PARAM, "vix_debug_tc_scores_f32: device pointers only");
+    return tc_scores_device(queries, nq, centroids, kc, d, metric, centroid_norms, out);
+}
+
+}  // extern "C"

@@ -236,6 +236,9 @@ __global__ void merge_keys_kernel(const u64* __restrict__ keys, int nin, int P2,
     }
 }
 
+int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
+                             const float* cnorm, int32_t* out_idx, float* out_scores);
+
 int launch_merge_keys(const u64* keys, int64_t rows, int nin, int k, int order_max, int dist_mode,
                       float* out_score, int64_t* out_id64, int32_t* out_id32, int* out_count,
                       uint32_t id_xor = 0) {
@@ -752,7 +755,9 @@ int vix_ivf_select_nprobe_batch_f32(const float* Q, int64_t b, int d, const floa
         if (centroid_norms) { VIX_TRY(dn.stage(centroid_norms, (size_t)kc)); cnp = dn.dev; }
         else { VIX_TRY(cn.alloc((size_t)kc)); VIX_TRY(row_norms_device(dc.dev, kc, d, cn.ptr)); cnp = cn.ptr; }
     }
-    VIX_TRY(probe_select_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dmask.dev, dids.dev, dsc.dev));
+    // no list mask: tensor-core shortlist + exact rescoring (vix_gemm.cu; identical results); else the exact kernel
+    if (dmask.dev == nullptr) VIX_TRY(probe_select_fast_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dids.dev, dsc.dev));
+    else VIX_TRY(probe_select_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dmask.dev, dids.dev, dsc.dev));
     VIX_TRY(dids.commit());
     VIX_TRY(dsc.commit());
     return finish(true);
