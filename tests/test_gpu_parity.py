@@ -117,6 +117,30 @@ def test_ivf_assign_bit_exact(oracle, vk, n, kc, d):
     assert np.array_equal(bits(gd), bits(od))
 
 
+@pytest.mark.parametrize("n,kc,d,kind", [(6000, 2048, 96, "gauss"), (5000, 1500, 128, "sift"), (3000, 4096, 100, "gauss"),
+                                         (2000, 1024, 768, "gauss")])
+def test_ivf_assign_tensor_core_shortlist_is_exact(oracle, vk, n, kc, d, kind):
+    """kc >= 1024 takes the tcgen05 shortlist + exact rescoring path: same assignment and distance bits as the
+    oracle, including duplicated centroids (tie -> lower index) and integer-valued data."""
+    from vectorindex_b200 import datagen
+    rng = np.random.default_rng(n + kc + d)
+    if kind == "sift":
+        x = datagen.sift_like(n + kc, d, 64, 11)
+        c = np.ascontiguousarray(x[n:])
+        x = np.ascontiguousarray(x[:n])
+    else:
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        c = (x[rng.integers(0, n, kc)] + rng.standard_normal((kc, d)).astype(np.float32) * 0.3).astype(np.float32)
+    c[kc - 1] = c[7]
+    c[kc // 2] = c[7]                                               # three identical centroids
+    x[:5] = c[[7, 8, 9, kc - 1, kc // 2]]                           # points sitting exactly on centroids
+    oa, od = oracle.assign(x, c)
+    ga, gd = vk.ivf_assign_f32(x, c, return_dist=True)
+    assert np.array_equal(ga, oa)
+    assert np.array_equal(bits(gd), bits(od))
+    assert ga[0] == 7 and ga[3] == 7 and ga[4] == 7
+
+
 def test_ivf_assign_ties_go_to_lower_index(oracle, vk):
     """heavy ties: integer-valued SIFT-like data and duplicated centroids (KMeansMiniBatchKernel.swift:352)."""
     from vectorindex_b200 import datagen

@@ -457,6 +457,53 @@ rescore_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, i
     }
 }
 
+// k = 1 (assignment): T = (smallest group minimum) + margin, one thread per row
+__global__ void threshold_min_kernel(const float* __restrict__ gmin, int64_t n, int ngroups, const float* __restrict__ anorm,
+                                     const float* __restrict__ bnorm_max, float rel, float* __restrict__ thr) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    float m = INFINITY;
+    for (int g = 0; g < ngroups; ++g) m = fminf(m, gmin[row * ngroups + g]);
+    thr[row] = m + 2.0f * rel * sqrtf(anorm[row]) * bnorm_max[0];
+}
+
+// IVF list assignment from the shortlist: one thread per vector evaluates the reference's exact distance
+// (_vi_km12_l2sq_aos order, KMeansMiniBatchKernel.swift:198-225) for its few candidates and keeps
+// (distance, then lower index) (:341-359).  Rows without a usable shortlist go to the exact kernel.
+__global__ void __launch_bounds__(128)
+rescore_assign_kernel(const float* __restrict__ X, int64_t n, const float* __restrict__ C, int d,
+                      const int* __restrict__ cand_cnt, const int32_t* __restrict__ cand_idx, int cap,
+                      int32_t* __restrict__ assign, float* __restrict__ dist, int* __restrict__ overflow_rows,
+                      int* __restrict__ n_overflow) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int cnt = cand_cnt[row];
+    if (cnt > cap || cnt == 0) {
+        overflow_rows[atomicAdd(n_overflow, 1)] = (int)row;
+        return;
+    }
+    const float* x = X + row * d;
+    float bd = INFINITY;
+    int bi = 0x7FFFFFFF;
+    for (int i = 0; i < cnt; ++i) {
+        const int c = cand_idx[row * cap + i];
+        const float dd = exact_pair<SpecKm12L2>(x, C + (int64_t)c * d, d);
+        if (dd < bd || (dd == bd && c < bi)) { bd = dd; bi = c; }
+    }
+    if (bi == 0x7FFFFFFF) { overflow_rows[atomicAdd(n_overflow, 1)] = (int)row; return; }
+    assign[row] = bi;
+    if (dist) dist[row] = bd;
+}
+
+__global__ void scatter_assign_rows_kernel(const int32_t* __restrict__ sub_assign, const float* __restrict__ sub_dist,
+                                           const int* __restrict__ rows, int n, int32_t* __restrict__ assign,
+                                           float* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    assign[rows[i]] = sub_assign[i];
+    if (dist) dist[rows[i]] = sub_dist[i];
+}
+
 __global__ void gather_rows_f32_kernel(const float* __restrict__ x, int d, const int* __restrict__ rows, int n,
                                        float* __restrict__ out) {
     const int i = blockIdx.x;
@@ -476,6 +523,7 @@ __global__ void scatter_probe_rows_kernel(const int32_t* __restrict__ idx, const
 
 // columns per group so that a row has between ~4 k and 2048 group minima
 static int choose_gcols(int nB, int k) {
+    if (k <= 1) return nB > 4096 ? 4096 : 128;       // assignment: only the row minimum matters
     int g = 32;
     while ((nB + g - 1) / g > 2048) g *= 2;
     while (g < 128 && (nB + g - 1) / g > 64 * k && (nB + 2 * g - 1) / (2 * g) >= 8 * k) g *= 2;
@@ -569,6 +617,70 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
         VIX_LAUNCH_CHECK();
         VIX_TRY(probe_select_device(sub.ptr, n, c, kc, d, metric, nprobe, cn, nullptr, sub_idx.ptr, sub_sc.ptr));
         tc::scatter_probe_rows_kernel<<<n, 128, 0, s>>>(sub_idx.ptr, sub_sc.ptr, nprobe, ovf_rows.ptr, n, out_idx, out_scores);
+        VIX_LAUNCH_CHECK();
+    }
+    return VIX_OK;
+}
+
+int ivf_assign_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
+
+// IVF list assignment (a9) through the tensor-core shortlist; results identical to ivf_assign_device.
+int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist) {
+    if (n == 0) return VIX_OK;
+    const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && tc::supported(n, kc, d, x, c) && kc >= 1024 && n >= 1024 &&
+                        d <= 4096 && n < (1LL << 31);
+    if (!use_tc) return ivf_assign_device(x, n, d, c, kc, assign, dist);
+    cudaStream_t s = ctx().stream;
+    const int gcols = tc::choose_gcols(kc, 1);
+    const int ngroups = (kc + gcols - 1) / gcols;
+    const int cap = 32;
+    Scratch<float> gmin, thr, xn, cn, cmax;
+    Scratch<int> cand_cnt, flags, ovf_rows;
+    Scratch<int32_t> cand_idx;
+    VIX_TRY(gmin.alloc((size_t)n * ngroups));
+    VIX_TRY(thr.alloc((size_t)n));
+    VIX_TRY(xn.alloc((size_t)n));
+    VIX_TRY(cn.alloc((size_t)kc));
+    VIX_TRY(cmax.alloc(1));
+    VIX_TRY(cand_cnt.alloc((size_t)n));
+    VIX_TRY(cand_idx.alloc((size_t)n * cap));
+    VIX_TRY(flags.alloc(2));
+    VIX_TRY(ovf_rows.alloc((size_t)n));
+    VIX_CUDA(cudaMemsetAsync(flags.ptr, 0, 8, s));
+    VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)n * 4, s));
+    VIX_TRY(row_norms_device(x, n, d, xn.ptr));
+    VIX_TRY(row_norms_device(c, kc, d, cn.ptr));
+    tc::max_sqrt_kernel<<<1, 256, 0, s>>>(cn.ptr, kc, cmax.ptr);
+    VIX_LAUNCH_CHECK();
+    tc::Args a{};
+    a.metric = VIX_METRIC_L2; a.bnorm = cn.ptr; a.error = flags.ptr;
+    a.mode = tc::MODE_MIN; a.gcols = gcols; a.ngroups = ngroups; a.gmin = gmin.ptr;
+    VIX_TRY(tc::launch(x, n, c, kc, d, a));
+    // TF32 shortlist error + the rounding of the exact fp32 evaluation itself
+    const float rel = 2.0f * 1.25f * (2.0f / 1024.0f + (float)d / 2097152.0f);
+    tc::threshold_min_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gmin.ptr, n, ngroups, xn.ptr, cmax.ptr, rel, thr.ptr);
+    VIX_LAUNCH_CHECK();
+    a.mode = tc::MODE_EMIT; a.thr = thr.ptr; a.cand_cnt = cand_cnt.ptr; a.cand_idx = cand_idx.ptr; a.cap = cap;
+    VIX_TRY(tc::launch(x, n, c, kc, d, a));
+    tc::rescore_assign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(x, n, c, d, cand_cnt.ptr, cand_idx.ptr, cap, assign, dist,
+                                                                       ovf_rows.ptr, flags.ptr + 1);
+    VIX_LAUNCH_CHECK();
+    int hflags[2] = {0, 0};
+    VIX_CUDA(cudaMemcpyAsync(hflags, flags.ptr, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    VIX_REQUIRE(hflags[0] == 0, VIX_ERR_CUDA, "tensor-core pipeline timed out");
+    if (hflags[1] > 0) {
+        const int m = hflags[1];
+        Scratch<float> sub, sub_dist;
+        Scratch<int32_t> sub_assign;
+        VIX_TRY(sub.alloc((size_t)m * d));
+        VIX_TRY(sub_assign.alloc((size_t)m));
+        VIX_TRY(sub_dist.alloc((size_t)m));
+        tc::gather_rows_f32_kernel<<<m, 128, 0, s>>>(x, d, ovf_rows.ptr, m, sub.ptr);
+        VIX_LAUNCH_CHECK();
+        VIX_TRY(ivf_assign_device(sub.ptr, m, d, c, kc, sub_assign.ptr, sub_dist.ptr));
+        tc::scatter_assign_rows_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(sub_assign.ptr, sub_dist.ptr, ovf_rows.ptr, m,
+                                                                                assign, dist);
         VIX_LAUNCH_CHECK();
     }
     return VIX_OK;

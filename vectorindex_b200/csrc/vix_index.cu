@@ -33,6 +33,7 @@ int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, i
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                         const float* cnorm, const uint64_t* disabled, int32_t* out_idx, float* out_scores);
 int ivf_assign_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
+int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
 int ivf_assign_metric_device(const float* x, int64_t n, int d, const float* c, int kc, int metric,
                              const float* cnorm, int32_t* assign);
 int row_norms_device(const float* x, int64_t n, int d, float* out);
@@ -453,7 +454,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
             int32_t* ac = h->assign.ptr + n0 + b;
             // list assignment: euclidean => _vi_km12_assignAOS (IVFIndex.swift:362-375);
             // dot product => first-min of the CentroidBatchScore row (IVFIndex.swift:376-435)
-            if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_device(xc, cn, d, h->coarse.ptr, h->kc, ac, nullptr));
+            if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_auto_device(xc, cn, d, h->coarse.ptr, h->kc, ac, nullptr));
             else VIX_TRY(ivf_assign_metric_device(xc, cn, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, ac));
             if (h->p.kind == VIX_INDEX_IVF_PQ) {
                 // pq_encode_residual_u8_f32 with default opts => C ..._with_csq (PQEncode.swift:247-286)
@@ -716,7 +717,7 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
     if (h->p.kind == VIX_INDEX_IVF_PQ) {
         Scratch<int32_t> asg;
         VIX_TRY(asg.alloc((size_t)n));
-        if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_device(dx.dev, n, d, h->coarse.ptr, kc, asg.ptr, nullptr));
+        if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_auto_device(dx.dev, n, d, h->coarse.ptr, kc, asg.ptr, nullptr));
         else VIX_TRY(ivf_assign_metric_device(dx.dev, n, d, h->coarse.ptr, kc, h->p.metric, nullptr, asg.ptr));
         const int m = h->p.m, ks = h->p.ks;
         VIX_TRY(h->codebooks.resize((size_t)ks * d, false));

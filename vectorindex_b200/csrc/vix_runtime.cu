@@ -45,6 +45,14 @@ int ensure_device() {
         set_error("libvindex_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
         return VIX_ERR_NO_DEVICE;
     }
+    // keep freed scratch memory in the stream-ordered pool: with the default release threshold (0) every
+    // stream synchronisation hands it back to the driver and the next call pays for mapping it again
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     ok = 1;
     return VIX_OK;
 }

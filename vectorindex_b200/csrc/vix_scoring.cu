@@ -239,6 +239,8 @@ __global__ void merge_keys_kernel(const u64* __restrict__ keys, int nin, int P2,
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                              const float* cnorm, int32_t* out_idx, float* out_scores);
 
+int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
+
 int launch_merge_keys(const u64* keys, int64_t rows, int nin, int k, int order_max, int dist_mode,
                       float* out_score, int64_t* out_id64, int32_t* out_id32, int* out_count,
                       uint32_t id_xor = 0) {
@@ -777,7 +779,7 @@ int vix_ivf_assign_f32(const float* x, int64_t n, int d, const float* centroids,
     VIX_TRY(dc.stage(centroids, (size_t)kc * d));
     VIX_TRY(da.stage(assign_out, (size_t)n));
     VIX_TRY(dd.stage(dist_out, dist_out ? (size_t)n : 0));
-    VIX_TRY(ivf_assign_device(dx.dev, n, d, dc.dev, kc, da.dev, dd.dev));
+    VIX_TRY(ivf_assign_auto_device(dx.dev, n, d, dc.dev, kc, da.dev, dd.dev));   // tensor-core shortlist + exact rescoring
     VIX_TRY(da.commit());
     VIX_TRY(dd.commit());
     return finish(true);

@@ -23,6 +23,7 @@
 namespace vix {
 
 int ivf_assign_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
+int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
 int pq_encode_device(const float* x, int64_t n, int d, int m, int ks, const float* cb, const float* csq,
                      const float* coarse, const int32_t* assign, uint8_t* codes, int use_dot, int layout,
                      int B, int g, int u4);
@@ -251,7 +252,7 @@ int train_coarse_device(const float* x, int64_t n, int d, int kc, int metric, co
     VIX_TRY(assign.alloc((size_t)ns));
     VIX_TRY(dist.alloc((size_t)ns));
     return lloyd_device(xp, ns, d, d, 0, kc, iters, centroids_out, d, 0, assign.ptr, dist.ptr, [&]() {
-        return ivf_assign_device(xp, ns, d, centroids_out, kc, assign.ptr, dist.ptr);
+        return ivf_assign_auto_device(xp, ns, d, centroids_out, kc, assign.ptr, dist.ptr);
     });
 }
 
@@ -419,7 +420,7 @@ int vix_kmeans_minibatch_f32(const float* x, int64_t n, int d, int kc, const flo
     int rc;
     if (cfg && cfg->mode == 1) {
         rc = train_coarse_device(dx.dev, n, d, kc, VIX_METRIC_L2, cfg, dc.dev);
-        if (rc == VIX_OK && da.dev) rc = ivf_assign_device(dx.dev, n, d, dc.dev, kc, da.dev, nullptr);
+        if (rc == VIX_OK && da.dev) rc = ivf_assign_auto_device(dx.dev, n, d, dc.dev, kc, da.dev, nullptr);
     } else {
         rc = kmeans_parity_device(dx.dev, n, d, kc, dinit.dev, cfg, dc.dev, da.dev);
     }
