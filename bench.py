@@ -152,12 +152,14 @@ def chunks_of(n):
 
 # ------------------------------------------------------------------------------------------------ build
 def build_index(cfg, synth, rank, world, bcast=None):
-    """Train on the first chunks (rank 0, parameters broadcast), then add this rank's chunks.
-    Returns (index, ground-truth ids for the first GT_QUERIES queries over THIS rank's rows)."""
+    """Train on the first chunks (rank 0, parameters broadcast), then build: every rank generates, assigns and
+    encodes ITS chunks of the database; rows travel to the rank owning their inverted list (all-to-all).
+    Returns (per-rank index, sharded view or None, exact ground truth of the first GT_QUERIES queries over the
+    rows this rank generated, timings)."""
     import torch
     from vectorindex_b200 import kernels as vk
     from vectorindex_b200._lib import KMeansCfg, PQTrainCfg
-    from vectorindex_b200.index import IVFPQIndex
+    from vectorindex_b200.index import IVFPQIndex, ShardedIVFPQIndex
 
     n, d, nlist, m = cfg["n"], cfg["d"], cfg["nlist"], cfg["m"]
     idx = IVFPQIndex(d, "euclidean", nlist=nlist, nprobe=cfg["nprobe"], m=m)
@@ -176,12 +178,14 @@ def build_index(cfg, synth, rank, world, bcast=None):
         coarse = torch.empty((nlist, d), dtype=torch.float32, device=synth.dev)
         cb = torch.empty((m, 256, d // m), dtype=torch.float32, device=synth.dev)
         cn = torch.empty((m, 256), dtype=torch.float32, device=synth.dev)
+    sh = None
     if world > 1:
         for t in (coarse, cb, cn):
             bcast(t)
         if rank != 0:
             idx.set_coarse(coarse)
             idx.set_codebooks(cb, cn)
+        sh = ShardedIVFPQIndex.wrap(idx, nlist, cfg["nprobe"])
     torch.cuda.synchronize()
     t_train = time.time() - t0
 
@@ -190,22 +194,30 @@ def build_index(cfg, synth, rank, world, bcast=None):
     k = cfg["k"]
     gt_d = torch.full((GT_QUERIES, k), float("inf"), device=synth.dev)
     gt_i = torch.full((GT_QUERIES, k), -1, dtype=torch.int64, device=synth.dev)
-    for ci, (b, c) in enumerate(chunks_of(n)):
-        if ci % world != rank:
-            continue
-        x = synth.rows(b, c)
-        ids = torch.arange(b, b + c, dtype=torch.int64, device=synth.dev)
-        idx.batch_insert(x, ids)
-        dd, ii = vk.flat_search_f32(qgt, x, k, 0)                  # exact ground truth, chunk by chunk
-        alld = torch.cat([gt_d, dd], 1)
-        alli = torch.cat([gt_i, ii + b], 1)
-        o = torch.argsort(alld, dim=1, stable=True)[:, :k]
-        gt_d, gt_i = torch.gather(alld, 1, o), torch.gather(alli, 1, o)
+    chunks = chunks_of(n)
+    for c0 in range(0, len(chunks), world):                          # one collective round per `world` chunks
+        ci = c0 + rank
+        if ci < len(chunks):
+            b, c = chunks[ci]
+            x = synth.rows(b, c)
+            ids = torch.arange(b, b + c, dtype=torch.int64, device=synth.dev)
+            dd, ii = vk.flat_search_f32(qgt, x, k, 0)                # exact ground truth, chunk by chunk
+            alld = torch.cat([gt_d, dd], 1)
+            alli = torch.cat([gt_i, ii + b], 1)
+            o = torch.argsort(alld, dim=1, stable=True)[:, :k]
+            gt_d, gt_i = torch.gather(alld, 1, o), torch.gather(alli, 1, o)
+        else:
+            x = torch.empty((0, d), dtype=torch.float32, device=synth.dev)
+            ids = torch.empty((0,), dtype=torch.int64, device=synth.dev)
+        if sh is not None:
+            sh.add(x, ids)
+        else:
+            idx.batch_insert(x, ids)
         del x, ids
     idx.list_sizes()                                                 # forces the list build (untimed)
     torch.cuda.synchronize()
     t_add = time.time() - t0
-    return idx, (gt_d, gt_i), dict(train_s=round(t_train, 2), add_s=round(t_add, 2))
+    return idx, sh, (gt_d, gt_i), dict(train_s=round(t_train, 2), add_s=round(t_add, 2))
 
 
 def recall_at_k(found, truth, k):
@@ -283,7 +295,7 @@ def main():
     synth = Synth(cfg, dev)
     eff_world = world if args.impl == "ours" else 1
     bcast = (lambda t: dist.broadcast(t, 0)) if dist else None
-    idx, (gt_d, gt_i), build_t = build_index(cfg, synth, rank if args.impl == "ours" else 0, eff_world, bcast)
+    idx, sh, (gt_d, gt_i), build_t = build_index(cfg, synth, rank if args.impl == "ours" else 0, eff_world, bcast)
     log(f"[bench] rank {rank}: built {idx.count} vectors ({build_t})")
     nq, k, d = cfg["nq"], cfg["k"], cfg["d"]
     q_dev = synth.queries(nq)
@@ -294,7 +306,8 @@ def main():
 
     base_cfg = {"workload": cfg["label"], "n": cfg["n"], "d": d, "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
                 "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": "euclidean",
-                "partition": f"database chunks of {CHUNK} rows dealt round-robin over {eff_world} rank(s); queries replicated",
+                "partition": f"inverted lists in contiguous blocks over {eff_world} rank(s) (coarse scoring sharded the same way); "
+                             "queries replicated; probe lists and top-k merged by all-gather + mergeTopK",
                 "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps",
                 "build": build_t}
 
@@ -321,22 +334,16 @@ def main():
     # ---------------------------------------------------------------- our arm
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    probes = None
-    if world > 1:
-        all_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        all_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
     st = _lib.SearchStats()
     _lib.check(L.vix_set_async(1))
     qp, dp, ip = _lib.ptr(q_dev), _lib.ptr(out_d), _lib.ptr(out_i)
 
     def step_device():
         # asynchronous: nothing here waits for the GPU (stage events are traced inside the library)
-        _lib.check(L.vix_index_search(idx._h, qp, C.c_int64(nq), C.c_int(k), C.c_int(0), dp, ip))
         if world == 1:
+            _lib.check(L.vix_index_search(idx._h, qp, C.c_int64(nq), C.c_int(k), C.c_int(0), dp, ip))
             return out_d, out_i
-        dist.all_gather_into_tensor(all_d, out_d)
-        dist.all_gather_into_tensor(all_i, out_i)
-        return merge_shard_results(all_d, all_i, k)
+        return sh.batch_search(q_dev, k)
 
     def barrier():
         if dist:
@@ -372,9 +379,7 @@ def main():
 
     # ---- end to end through the public API with pinned host buffers
     _lib.check(L.vix_set_async(0))
-    from vectorindex_b200.index import ShardedIVFPQIndex
     if world > 1:
-        sh = ShardedIVFPQIndex.wrap(idx)
         api = lambda: sh.batch_search(q_host, k)                      # noqa: E731
     else:
         api = lambda: idx.batch_search(q_host, k)                     # noqa: E731
@@ -401,12 +406,8 @@ def main():
 
     # recall of the (merged) result against the exact ground truth
     if dist:
-        g_d = torch.empty((world,) + tuple(gt_d.shape), dtype=gt_d.dtype, device=dev)
-        g_i = torch.empty((world,) + tuple(gt_i.shape), dtype=gt_i.dtype, device=dev)
-        dist.all_gather_into_tensor(g_d, gt_d.contiguous())
-        dist.all_gather_into_tensor(g_i, gt_i.contiguous())
         _lib.check(L.vix_set_async(0))
-        gt_d, gt_i = merge_shard_results(g_d, g_i, k)
+        gt_d, gt_i = merge_shard_results(sh._all_gather(gt_d.contiguous()), sh._all_gather(gt_i.contiguous()), k)
     torch.cuda.synchronize()
     recall = recall_at_k(res_i[:GT_QUERIES], gt_i, k)
     assert np.array_equal(np.asarray(h_i), res_i.cpu().numpy()), "host-path ids differ from the device-path ids"

@@ -278,6 +278,20 @@ int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k,
                         float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,
                         vix_search_stats* stats /* nullable */);
 
+/* ---- multi-GPU: inverted lists are partitioned over ranks by contiguous list-id blocks ------------------
+ * Search on rank r of R:  vix_index_probe_range over r's block of centroids (local top-nprobe, GLOBAL list ids)
+ *   -> all-gather + vix_merge_topk_f32 (.min; ids = list ids) = the global probe lists of IVFIndex.swift:905-927
+ *   -> vix_index_search_with_probes (lists this rank does not hold are empty, so only owned lists are scanned)
+ *   -> all-gather + vix_merge_topk_f32 of the per-rank [nq x k] results (TopKMerge.swift:11-61).
+ * Build: any rank assigns + encodes a batch (vix_index_encode); rows are routed to the rank owning their
+ * list and appended there with vix_index_add_encoded. */
+int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int nprobe, int list_begin, int list_count,
+                          int32_t* list_ids_out /* [nq x nprobe] */, float* list_scores_out /* nullable */);
+int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                 int nprobe, float* out_dist, int64_t* out_ids);
+int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_out, uint8_t* codes_out /* [n x m] */);
+int vix_index_add_encoded(vix_index_t* h, const int32_t* assign, const uint8_t* codes, const int64_t* ids, int64_t n);
+
 /* Stage timing without host synchronisation (bench / profiling): after vix_index_trace(h, capacity) the
  * next `capacity` searches WITHOUT a stats struct record their stage events and scanned-code count on
  * the stream and return asynchronously; vix_index_trace_get(h, i, &st) waits for call i and reads them

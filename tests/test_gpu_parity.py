@@ -423,6 +423,45 @@ def test_ivfpq_index_stagewise_parity(oracle, n, d, m, kc, nprobe, metric, kind)
     assert np.array_equal(gi2, gi) and np.array_equal(bits(gd2), bits(gd))
 
 
+def test_sharded_pieces_emulated_on_one_gpu(oracle):
+    """Two list-block shards built and searched in ONE process (the ranks emulated sequentially, the collectives
+    replaced by concatenation): probe_range + merge == the single index's probe lists, search_with_probes + merge
+    == the single index's result, and encode/add_encoded build the same lists as batch_insert."""
+    from vectorindex_b200 import kernels as vk
+    from vectorindex_b200.index import IVFPQIndex, list_block, list_owner
+    n, d, m, kc, nq, k, nprobe, world = 9000, 64, 16, 40, 50, 10, 6, 2
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=99)
+    ids = np.arange(n, dtype=np.int64) * 5 + 3
+    single = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+    single.set_coarse(coarse); single.set_codebooks(cb, norms)
+    single.batch_insert(xb, ids)
+    sd, si, sp = single.batch_search(q, k, return_probes=True)
+    shards = []
+    for r in range(world):
+        ix = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+        ix.set_coarse(coarse); ix.set_codebooks(cb, norms)
+        shards.append(ix)
+    asg, codes = shards[0].encode(xb)                                  # any rank may encode
+    owner = list_owner(asg.astype(np.int64), kc, world)
+    for r in range(world):
+        sel = owner == r
+        shards[r].add_encoded(asg[sel], codes[sel], ids[sel])
+    assert sum(s_.count for s_ in shards) == n
+    # stage 1: local top-nprobe per centroid block -> merged global probe lists
+    pid, psc = zip(*[shards[r].probe_range(q, nprobe, *list_block(kc, r, world)) for r in range(world)])
+    sc = np.ascontiguousarray(np.stack(psc, 1))                         # [nq x world x nprobe]
+    idm = np.ascontiguousarray(np.stack(pid, 1).astype(np.int64))
+    _, gp = vk.mergeTopK(sc, idm, nprobe, 0)
+    assert np.array_equal(gp.astype(np.int32), sp)
+    # stage 2: every shard scans the probed lists it owns -> merged top-k
+    res = [shards[r].search_with_probes(q, k, gp.astype(np.int32)) for r in range(world)]
+    dd = np.ascontiguousarray(np.stack([r_[0] for r_ in res], 1))
+    ii = np.ascontiguousarray(np.stack([r_[1] for r_ in res], 1))
+    md, mi = vk.mergeTopK(dd, ii, k, 0)
+    assert np.array_equal(mi, si)
+    assert np.array_equal(bits(md), bits(sd))
+
+
 def test_ivfpq_edge_cases(oracle):
     from vectorindex_b200.index import IVFPQIndex
     from vectorindex_b200 import VectorIndexError

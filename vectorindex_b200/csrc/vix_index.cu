@@ -469,7 +469,8 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
 }
 
 static int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
-                               int64_t* out_ids, int32_t* out_probes, vix_search_stats* stats) {
+                               int64_t* out_ids, int32_t* out_probes, vix_search_stats* stats,
+                               const int32_t* given_probes = nullptr) {
     const int d = h->p.d;
     cudaStream_t s = ctx().stream;
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -510,8 +511,16 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         Scratch<int32_t> probes;
         int32_t* pp = dp.dev;
         if (!pp) { VIX_TRY(probes.alloc((size_t)nq * nprobe)); pp = probes.ptr; }
-        VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
-                                         h->coarse_norms.ptr, pp, nullptr));
+        In<int32_t> gp;
+        if (given_probes) {
+            // probe lists chosen by the caller (sharded search: the globally merged top-nprobe)
+            VIX_TRY(gp.stage(given_probes, (size_t)nq * nprobe));
+            if (dp.dev) VIX_CUDA(cudaMemcpyAsync(dp.dev, gp.dev, (size_t)nq * nprobe * 4, cudaMemcpyDeviceToDevice, s));
+            pp = const_cast<int32_t*>(gp.dev);
+        } else {
+            VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
+                                             h->coarse_norms.ptr, pp, nullptr));
+        }
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
         if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
         DevBuf<unsigned long long>& scanned = h->scanned;
@@ -819,6 +828,97 @@ int vix_index_clear(vix_index_t* h) {
     h->vecs.size = h->ids.size = h->assign.size = h->codes.size = 0;
     h->dirty = true;
     return VIX_OK;
+}
+
+__global__ void offset_ids_kernel(int32_t* ids, int64_t n, int offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ids[i] >= 0) ids[i] += offset;
+}
+
+int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes, int nprobe,
+                                 float* out_dist, int64_t* out_ids) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && probes, VIX_ERR_NULL_PTR, "vix_index_search_with_probes: null pointer");
+    VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "vix_index_search_with_probes: nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_search_with_probes: IVF index not trained");
+    return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr, probes);
+}
+
+int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int nprobe, int list_begin, int list_count,
+                          int32_t* list_ids_out, float* list_scores_out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && queries && list_ids_out, VIX_ERR_NULL_PTR, "vix_index_probe_range: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_probe_range: not trained");
+    VIX_REQUIRE(nprobe > 0 && nprobe <= VIX_MAX_K, VIX_ERR_INVALID_K, "vix_index_probe_range: nprobe");
+    VIX_REQUIRE(list_begin >= 0 && list_count > 0 && list_begin + list_count <= h->kc, VIX_ERR_INVALID_PARAM,
+                "vix_index_probe_range: list range [%d, %d) outside [0, %d)", list_begin, list_begin + list_count, h->kc);
+    if (nq <= 0) return VIX_OK;
+    const int d = h->p.d;
+    In<float> dq;
+    Out<int32_t> di;
+    Out<float> ds;
+    VIX_TRY(dq.stage(queries, (size_t)nq * d));
+    VIX_TRY(di.stage(list_ids_out, (size_t)nq * nprobe));
+    VIX_TRY(ds.stage(list_scores_out, list_scores_out ? (size_t)nq * nprobe : 0));
+    VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr + (size_t)list_begin * d, list_count, d, h->p.metric, nprobe,
+                                     h->coarse_norms.ptr + list_begin, di.dev, ds.dev));
+    if (list_begin > 0) {
+        const int64_t total = nq * (int64_t)nprobe;
+        offset_ids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(di.dev, total, list_begin);
+        VIX_LAUNCH_CHECK();
+    }
+    VIX_TRY(di.commit());
+    VIX_TRY(ds.commit());
+    return finish(di.is_host() || ds.is_host());
+}
+
+int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_out, uint8_t* codes_out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && x && assign_out, VIX_ERR_NULL_PTR, "vix_index_encode: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_encode: coarse quantiser not trained / set");
+    const bool pq = h->p.kind == VIX_INDEX_IVF_PQ;
+    if (pq) VIX_REQUIRE(h->has_pq && codes_out, VIX_ERR_NOT_TRAINED, "vix_index_encode: PQ codebooks not trained / codes_out missing");
+    if (n <= 0) return VIX_OK;
+    const int d = h->p.d;
+    In<float> dx;
+    Out<int32_t> da;
+    Out<uint8_t> dc;
+    VIX_TRY(dx.stage(x, (size_t)n * d));
+    VIX_TRY(da.stage(assign_out, (size_t)n));
+    VIX_TRY(dc.stage(pq ? codes_out : nullptr, pq ? (size_t)n * h->p.m : 0));
+    if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_auto_device(dx.dev, n, d, h->coarse.ptr, h->kc, da.dev, nullptr));
+    else VIX_TRY(ivf_assign_metric_device(dx.dev, n, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, da.dev));
+    if (pq)
+        VIX_TRY(pq_encode_device(dx.dev, n, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, da.dev, dc.dev, 1,
+                                 PQ_LAYOUT_AOS, 64, 8, 0));
+    VIX_TRY(da.commit());
+    VIX_TRY(dc.commit());
+    return finish(da.is_host() || dc.is_host());
+}
+
+int vix_index_add_encoded(vix_index_t* h, const int32_t* assign, const uint8_t* codes, const int64_t* ids, int64_t n) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && (n == 0 || (assign && codes && ids)), VIX_ERR_NULL_PTR, "vix_index_add_encoded: null pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind == VIX_INDEX_IVF_PQ && h->has_coarse && h->has_pq, VIX_ERR_NOT_TRAINED,
+                "vix_index_add_encoded: needs a trained IVF-PQ index");
+    if (n <= 0) return VIX_OK;
+    VIX_REQUIRE(h->n + n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "index shard limited to 2^31 - 1 rows");
+    if (!is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    cudaStream_t s = ctx().stream;
+    const int64_t n0 = h->n;
+    VIX_TRY(h->ids.resize((size_t)(n0 + n)));
+    VIX_TRY(h->assign.resize((size_t)(n0 + n)));
+    VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->p.m));
+    VIX_CUDA(cudaMemcpyAsync(h->ids.ptr + n0, ids, (size_t)n * 8, cudaMemcpyDefault, s));
+    VIX_CUDA(cudaMemcpyAsync(h->assign.ptr + n0, assign, (size_t)n * 4, cudaMemcpyDefault, s));
+    VIX_CUDA(cudaMemcpyAsync(h->codes.ptr + (size_t)n0 * h->p.m, codes, (size_t)n * h->p.m, cudaMemcpyDefault, s));
+    h->n = n0 + n;
+    h->dirty = true;
+    return finish(true);
 }
 
 int vix_index_trace(vix_index_t* h, int capacity) {

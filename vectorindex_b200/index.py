@@ -15,9 +15,9 @@ smaller id (TopK.swift:8-31).  Ids are integers in [0, 2^32 - 1) (the reference'
 The metadata filter of the reference is a host closure and cannot run on the device; the only filter the
 kernels honour is the list-disable bitmask of ivf_select_nprobe (IVFSelect.swift:366-395).
 
-Multi-GPU: ``ShardedIVFPQIndex`` partitions the database by vector range over the ranks of a
-``torch.distributed`` process group; queries are replicated, every rank scans its shard, and the per-rank
-top-k lists are merged with ONE all-gather + the mergeTopK kernel.
+Multi-GPU: ``ShardedIVFPQIndex`` partitions the inverted lists over the ranks of a ``torch.distributed``
+process group; queries are replicated, every rank scores its block of centroids and scans the probed lists
+it owns, and probe lists / per-rank top-k lists are merged with an all-gather + the mergeTopK kernel.
 """
 from __future__ import annotations
 
@@ -177,6 +177,48 @@ class IVFPQIndex(IVFIndex):
         check(lib().vix_index_get_codebooks(self._h, ptr(cb), ptr(cn)))
         return cb, cn
 
+    # ---- pieces of the sharded pipeline (ShardedIVFPQIndex)
+    def probe_range(self, queries, nprobe, list_begin, list_count):
+        """local top-nprobe over the centroid block [list_begin, list_begin + list_count): (global list ids, scores)"""
+        q = as_input(queries, np.float32)
+        self._check_dim(q, "probe_range")
+        nq = int(q.shape[0])
+        ids = empty_like_input(q, (nq, nprobe), np.int32)
+        sc = empty_like_input(q, (nq, nprobe), np.float32)
+        check(lib().vix_index_probe_range(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(nprobe), C.c_int(list_begin),
+                                          C.c_int(list_count), ptr(ids, np.int32), ptr(sc, np.float32)))
+        return ids, sc
+
+    def search_with_probes(self, queries, k, probes):
+        q = as_input(queries, np.float32)
+        self._check_dim(q, "search_with_probes")
+        pr = as_input(probes, np.int32)
+        nq, nprobe = int(q.shape[0]), int(pr.shape[1])
+        dist = empty_like_input(q, (nq, k), np.float32)
+        ids = empty_like_input(q, (nq, k), np.int64)
+        check(lib().vix_index_search_with_probes(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k), ptr(pr, np.int32),
+                                                 C.c_int(nprobe), ptr(dist, np.float32), ptr(ids, np.int64)))
+        return dist, ids
+
+    def encode(self, vectors):
+        """(list assignment, PQ codes) of a batch without storing it (bit-exact, same kernels as batch_insert)"""
+        x = as_input(vectors, np.float32)
+        self._check_dim(x, "encode")
+        n = int(x.shape[0])
+        asg = empty_like_input(x, (n,), np.int32)
+        codes = empty_like_input(x, (n, self.params.m), np.uint8)
+        if n == 0:
+            return asg, codes
+        check(lib().vix_index_encode(self._h, ptr(x, np.float32), C.c_int64(n), ptr(asg, np.int32), ptr(codes, np.uint8)))
+        return asg, codes
+
+    def add_encoded(self, assign, codes, ids):
+        a, c, i = as_input(assign, np.int32), as_input(codes, np.uint8), as_input(ids, np.int64)
+        if int(a.shape[0]) == 0:
+            return
+        check(lib().vix_index_add_encoded(self._h, ptr(a, np.int32), ptr(c, np.uint8), ptr(i, np.int64),
+                                          C.c_int64(int(a.shape[0]))))
+
     def import_lists(self, list_offsets, codes, ids):
         lo = np.ascontiguousarray(list_offsets, dtype=np.int64)
         codes = as_input(codes, np.uint8)
@@ -199,16 +241,24 @@ class IVFPQIndex(IVFIndex):
 # ------------------------------------------------------------------------------------------------
 # multi-GPU
 # ------------------------------------------------------------------------------------------------
-def shard_range(n: int, rank: int, world: int):
-    """Contiguous vector range of ``rank`` (flat rows / vector ranges shard independently)."""
-    per = (n + world - 1) // world
-    b = min(n, rank * per)
-    return b, min(n, b + per)
+def list_block(kc: int, rank: int, world: int):
+    """Contiguous block of inverted lists owned by ``rank``: (first list, number of lists).  Lists are disjoint
+    (IVFIndex.swift:370-375), so they shard without any data-path dependency between ranks."""
+    per = (kc + world - 1) // world
+    b = min(kc, rank * per)
+    return b, min(kc, b + per) - b
+
+
+def list_owner(assign, kc: int, world: int):
+    """Rank owning each list id in ``assign`` (numpy or torch)."""
+    per = (kc + world - 1) // world
+    return assign // per
 
 
 def merge_shard_results(dist_all, ids_all, k, metric=METRIC_L2):
-    """mergeTopK over per-rank results.  dist_all/ids_all: [world x nq x k] (numpy or torch).  API distances
-    ascend for both metrics, so the merge order is always .min with ties -> smaller id (TopKMerge.swift:66-71)."""
+    """mergeTopK over per-rank results.  dist_all/ids_all: [world x nq x k] (numpy or torch).  API distances and
+    probe scores both ascend ("smaller is better"), so the merge order is always .min with ties -> smaller id
+    (TopKMerge.swift:66-71)."""
     from .kernels import mergeTopK
     if _lib._is_torch(dist_all):
         sc = dist_all.permute(1, 0, 2).contiguous()
@@ -219,82 +269,9 @@ def merge_shard_results(dist_all, ids_all, k, metric=METRIC_L2):
     return mergeTopK(sc, idm, k, 0)
 
 
-class ShardedIVFPQIndex:
-    """One IVFPQIndex per rank holding a vector range; search = local fused scan + all-gather + merge."""
-
-    def __init__(self, dimension, metric="euclidean", nlist=256, nprobe=8, m=16, ks=256, group=None):
-        import torch.distributed as dist
-        self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.local = IVFPQIndex(dimension, metric, nlist, nprobe, m, ks)
-
-    def set_parameters(self, coarse, codebooks, centroid_norms=None):
-        self.local.set_coarse(coarse)
-        self.local.set_codebooks(codebooks, centroid_norms)
-
-    def add_global(self, vectors, ids=None):
-        """Every rank passes the SAME global array; each keeps its own range."""
-        n = int(vectors.shape[0])
-        b, e = shard_range(n, self.rank, self.world)
-        idl = ids[b:e] if ids is not None else np.arange(b, e, dtype=np.int64)
-        if _lib._is_torch(vectors) and not _lib._is_torch(idl):
-            import torch
-            idl = torch.as_tensor(idl, device=vectors.device)
-        self.local.batch_insert(vectors[b:e], idl)
-
-    @classmethod
-    def wrap(cls, local_index, group=None):
-        """Sharded view over an already built per-rank IVFPQIndex."""
-        import torch.distributed as dist
-        self = cls.__new__(cls)
-        self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.local = local_index
-        return self
-
-    def batch_search(self, queries, k, nprobe=0):
-        """Replicated queries -> local fused scan -> ONE all-gather of the packed per-rank (distance, id)
-        lists -> mergeTopK kernel.  Host (numpy) queries are staged to the device once and only the merged
-        [nq x k] result returns to the host."""
-        import torch
-        import torch.distributed as dist
-        if self.world == 1:
-            return self.local.batch_search(queries, k, nprobe)
-        was_numpy = not _lib._is_torch(queries)
-        nccl = dist.get_backend(self.group) == "nccl"
-        if was_numpy and nccl:
-            dev = torch.device("cuda", torch.cuda.current_device())
-            queries = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(dev, non_blocking=True)
-        d_loc, i_loc = self.local.batch_search(queries, k, nprobe)
-        md, mi = self.gather_merge(d_loc, i_loc, k)
-        if was_numpy and _lib._is_torch(md):
-            md, mi = md.cpu().numpy(), mi.cpu().numpy()
-        return md, mi
-
-    def gather_merge(self, d_loc, i_loc, k):
-        """all-gather + merge of per-rank [nq x k] results (torch tensors or numpy arrays)."""
-        import torch
-        import torch.distributed as dist
-        if not _lib._is_torch(d_loc):
-            d_loc, i_loc = torch.from_numpy(d_loc), torch.from_numpy(i_loc)
-            if dist.get_backend(self.group) == "nccl":
-                dev = torch.device("cuda", torch.cuda.current_device())
-                d_loc, i_loc = d_loc.to(dev), i_loc.to(dev)
-        nq = d_loc.shape[0]
-        d_all = torch.empty((self.world, nq, k), dtype=d_loc.dtype, device=d_loc.device)
-        i_all = torch.empty((self.world, nq, k), dtype=i_loc.dtype, device=i_loc.device)
-        dist.all_gather_into_tensor(d_all, d_loc.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(i_all, i_loc.contiguous(), group=self.group)
-        if d_all.is_cuda:
-            return merge_shard_results(d_all, i_all, k)
-        return merge_shard_results_host(d_all.numpy(), i_all.numpy(), k)
-
-
 def merge_shard_results_host(dist_all, ids_all, k):
-    """Host restatement of the shard merge (used on CPU-only ranks and by the gloo tests): k smallest of
-    the union by (distance, id); NaN / id -1 entries are padding."""
+    """Host restatement of the shard merge (CPU-only ranks, gloo tests): k smallest of the union by
+    (distance, id); NaN / id -1 entries are padding."""
     world, nq, kk = dist_all.shape
     d = np.transpose(dist_all, (1, 0, 2)).reshape(nq, world * kk)
     i = np.transpose(ids_all, (1, 0, 2)).reshape(nq, world * kk)
@@ -307,3 +284,136 @@ def merge_shard_results_host(dist_all, ids_all, k):
         out_d[r, :order.size] = dv[order]
         out_i[r, :order.size] = iv[order]
     return out_d, out_i
+
+
+class ShardedIVFPQIndex:
+    """IVF-PQ index partitioned over the ranks of a ``torch.distributed`` group by contiguous blocks of
+    inverted lists.  Every rank holds the coarse centroids and PQ codebooks and the codes of
+    ITS lists only.
+
+    build   any rank assigns + encodes whatever rows it is handed (``add``); rows travel to the rank that
+            owns their list with one all-to-all and are appended there already encoded;
+    search  each rank scores only its block of centroids (local top-nprobe) -> all-gather + mergeTopK give
+            the global probe lists, identical on every rank and identical to the single-GPU order
+            (IVFIndex.swift:593-595) -> each rank scans the probed lists it owns -> all-gather + mergeTopK of
+            the per-rank [nq x k] results (TopKMerge.swift:11-61).
+
+    ``local`` may be any object with probe_range / search_with_probes / encode / add_encoded / set_coarse /
+    set_codebooks (the gloo tests plug in an oracle-backed one, the product path an ``IVFPQIndex``)."""
+
+    def __init__(self, dimension, metric="euclidean", nlist=256, nprobe=8, m=16, ks=256, group=None, local=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = local if local is not None else IVFPQIndex(dimension, metric, nlist, nprobe, m, ks)
+        self.nprobe = int(nprobe)
+        self.kc = int(nlist)
+
+    @classmethod
+    def wrap(cls, local_index, kc, nprobe, group=None):
+        """Sharded view over an already built per-rank index."""
+        self = cls.__new__(cls)
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local, self.kc, self.nprobe = local_index, int(kc), int(nprobe)
+        return self
+
+    # ---- parameters
+    def set_parameters(self, coarse, codebooks, centroid_norms=None):
+        self.kc = int(coarse.shape[0])
+        self.local.set_coarse(coarse)
+        self.local.set_codebooks(codebooks, centroid_norms)
+
+    def _nccl(self):
+        import torch.distributed as dist
+        return dist.get_backend(self.group) == "nccl"
+
+    def _to_comm(self, a):
+        """array -> tensor on the device the process group communicates over"""
+        import torch
+        if not _lib._is_torch(a):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        if self._nccl() and not a.is_cuda:
+            a = a.to(torch.device("cuda", torch.cuda.current_device()))
+        return a.contiguous()
+
+    def _all_gather(self, t):
+        import torch
+        import torch.distributed as dist
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)                  # concatenated along dim 0
+        return out.view((self.world,) + tuple(t.shape))
+
+    # ---- build
+    def add(self, vectors, ids):
+        """Rows handed to THIS rank (any rows; ranks normally pass disjoint slices of the database)."""
+        import torch
+        import torch.distributed as dist
+        assign, codes = self.local.encode(vectors)
+        if self.world == 1:
+            self.local.add_encoded(assign, codes, ids)
+            return
+        assign, codes, ids = self._to_comm(assign), self._to_comm(codes), self._to_comm(ids)
+        owner = list_owner(assign.to(torch.int64), self.kc, self.world)
+        order = torch.argsort(owner, stable=True)
+        send_cnt = torch.bincount(owner, minlength=self.world).to(torch.int64)
+        recv_cnt = torch.empty_like(send_cnt)
+        dist.all_to_all_single(recv_cnt, send_cnt, group=self.group)
+        ssz, rsz = send_cnt.tolist(), recv_cnt.tolist()
+        nrecv = int(sum(rsz))
+
+        def exchange(t):
+            t = t[order].contiguous()
+            out = torch.empty((nrecv,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_to_all_single(out, t, output_split_sizes=rsz, input_split_sizes=ssz, group=self.group)
+            return out
+
+        r_assign, r_codes, r_ids = exchange(assign), exchange(codes), exchange(ids)
+        if nrecv:
+            if not self._nccl():
+                r_assign, r_codes, r_ids = r_assign.numpy(), r_codes.numpy(), r_ids.numpy()
+            self.local.add_encoded(r_assign, r_codes, r_ids)
+
+    # ---- search
+    def global_probes(self, queries, nprobe=0):
+        """The global probe lists [nq x nprobe] (int32), identical on every rank."""
+        import torch
+        nprobe = nprobe if nprobe > 0 else self.nprobe
+        begin, count = list_block(self.kc, self.rank, self.world)
+        ids, sc = self.local.probe_range(queries, nprobe, begin, count)
+        if self.world == 1:
+            return ids
+        ids_all = self._all_gather(self._to_comm(ids).to(torch.int64))
+        sc_all = self._all_gather(self._to_comm(sc))
+        if sc_all.is_cuda:
+            _, mi = merge_shard_results(sc_all, ids_all, nprobe)
+        else:
+            _, mi = merge_shard_results_host(sc_all.numpy(), ids_all.numpy(), nprobe)
+            mi = torch.from_numpy(mi)
+        return mi.to(torch.int32).contiguous()
+
+    def batch_search(self, queries, k, nprobe=0):
+        """Replicated queries in, merged [nq x k] (distances, ids) out on every rank.  Host (numpy) queries are
+        staged to the device once and only the merged result returns to the host."""
+        import torch
+        was_numpy = not _lib._is_torch(queries)
+        if self.world > 1 and was_numpy and self._nccl():
+            queries = self._to_comm(np.ascontiguousarray(queries, dtype=np.float32))
+        nprobe = nprobe if nprobe > 0 else self.nprobe
+        probes = self.global_probes(queries, nprobe)
+        if not self._nccl() and _lib._is_torch(probes):
+            probes = probes.numpy()
+        d_loc, i_loc = self.local.search_with_probes(queries, k, probes)
+        if self.world == 1:
+            return d_loc, i_loc
+        d_all, i_all = self._all_gather(self._to_comm(d_loc)), self._all_gather(self._to_comm(i_loc))
+        if d_all.is_cuda:
+            md, mi = merge_shard_results(d_all, i_all, k)
+        else:
+            md, mi = merge_shard_results_host(d_all.numpy(), i_all.numpy(), k)
+        if was_numpy and _lib._is_torch(md):
+            md, mi = md.cpu().numpy(), mi.cpu().numpy()
+        return md, mi
