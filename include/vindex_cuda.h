@@ -273,6 +273,11 @@ typedef struct {
     float   ms_coarse;            /* CUDA-event time of the probe-selection stage                 */
     float   ms_scan;              /* ... of the LUT + ADC + top-k stage                           */
     float   ms_total;
+    /* fused IVF-PQ scan only: SM cycles one scanning warp per CTA spent building the per-query table and probe
+     * bookkeeping / scanning / waiting for the other warps at the end of a query, summed over CTAs */
+    int64_t cycles_prologue, cycles_scan, cycles_tail;
+    int64_t cycles_select, cycles_probe_table, cycles_lut;   /* the three concurrent pieces of the prologue */
+    int64_t merge_candidates;                                 /* entries handed to the per-query top-k merge */
 } vix_search_stats;
 int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
                         float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,

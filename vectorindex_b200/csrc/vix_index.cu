@@ -524,7 +524,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
         if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
         DevBuf<unsigned long long>& scanned = h->scanned;
-        if (stats) { VIX_TRY(scanned.resize(1, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 8, s)); }
+        if (stats) { VIX_TRY(scanned.resize(8, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 64, s)); }
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
             ScanArgs a{};
             a.queries = dq.dev; a.nq = nq; a.d = d; a.m = h->p.m; a.ks = h->p.ks; a.dsub = d / h->p.m;
@@ -533,6 +533,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.slot_codes = h->slot_codes.ptr; a.slot_tx = h->slot_tx.ptr; a.slot_ids = h->slot_ids.ptr;
             a.metric = h->p.metric; a.k = k; a.out_dist = dd.dev; a.out_ids = di.dev;
             a.scanned = stats ? scanned.ptr : (traced ? h->trace_scanned.ptr + h->trace_n : nullptr);
+            a.phase_cycles = stats ? scanned.ptr + 1 : nullptr;
             a.codebooks_t = h->codebooks_t.ptr;
             VIX_TRY(h->work_counter.resize(2, false));
             a.work_counter = h->work_counter.ptr;
@@ -556,10 +557,14 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         if (traced) VIX_CUDA(cudaEventRecord(tev[2], s));
         if (stats) {
             VIX_CUDA(cudaEventRecord(ev[2], s));
-            unsigned long long sc = 0;
-            VIX_CUDA(cudaMemcpyAsync(&sc, scanned.ptr, 8, cudaMemcpyDeviceToHost, s));
+            unsigned long long sc4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            VIX_CUDA(cudaMemcpyAsync(sc4, scanned.ptr, 64, cudaMemcpyDeviceToHost, s));
             VIX_CUDA(cudaStreamSynchronize(s));
+            const unsigned long long sc = sc4[0];
             stats->codes_scanned = (int64_t)sc;
+            stats->cycles_prologue = (int64_t)sc4[1]; stats->cycles_scan = (int64_t)sc4[2]; stats->cycles_tail = (int64_t)sc4[3];
+            stats->cycles_select = (int64_t)sc4[4]; stats->cycles_probe_table = (int64_t)sc4[5]; stats->cycles_lut = (int64_t)sc4[6];
+            stats->merge_candidates = (int64_t)sc4[7];
             stats->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->p.m : d * 4);
         }
         VIX_TRY(dp.commit());

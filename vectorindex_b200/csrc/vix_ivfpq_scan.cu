@@ -117,11 +117,48 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t v, int kth, int l
 
 // ---- per-query prologue / epilogue pieces, kept out of line so that the scan loop owns the registers ----
 
-// warp 0: the k best of the n published candidates.  Keys are unique, so "the smallest key greater than
-// the last one taken" walks them in order without mutating anything.
+// warp 0: the k best of the n published candidates.  Keys are unique, so "the smallest key greater than the
+// last one taken" walks them in order.  Up to 512 candidates live in registers (16 per lane); each of the k
+// rounds is a lane-local minimum over the registers plus two warp REDUX steps.
+__device__ __forceinline__ void write_result(u64 mn, int order_max, size_t o, float* __restrict__ out_dist,
+                                             int64_t* __restrict__ out_ids) {
+    if (mn == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
+    else {
+        const float sc = key_score(mn, order_max);
+        out_dist[o] = order_max ? -sc : sc;   // IP: API distance = -score (DistanceUtils.swift:40-46)
+        out_ids[o] = (int64_t)key_id(mn);
+    }
+}
+
 __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int n, int k, int order_max, int64_t qi,
-                                              float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+                                             float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
     const int lane = threadIdx.x & 31;
+    if (n <= 512) {
+        constexpr int R = 16;
+        uint32_t kh[R], kl[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int t = lane + 32 * r;
+            const u64 key = (t < n) ? s_cand[t] : kEmptyKey;
+            kh[r] = (uint32_t)(key >> 32); kl[r] = (uint32_t)key;
+        }
+        for (int i = 0; i < k; ++i) {
+            uint32_t mh = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool less = kh[r] < mh || (kh[r] == mh && kl[r] < ml);
+                mh = less ? kh[r] : mh; ml = less ? kl[r] : ml;
+            }
+            const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
+            const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
+            // the owner retires the key it contributed
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (kh[r] == gh && kl[r] == gl) { kh[r] = 0xFFFFFFFFu; kl[r] = 0xFFFFFFFFu; }
+            if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
+        }
+        return;
+    }
     uint32_t last_hi = 0, last_lo = 0;
     bool first = true;
     for (int i = 0; i < k; ++i) {
@@ -134,16 +171,7 @@ __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int
         }
         const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
         const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
-        const u64 mn = ((u64)gh << 32) | gl;
-        if (lane == 0) {
-            const size_t o = (size_t)qi * k + i;
-            if (mn == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
-            else {
-                const float sc = key_score(mn, order_max);
-                out_dist[o] = order_max ? -sc : sc;   // IP: API distance = -score (DistanceUtils.swift:40-46)
-                out_ids[o] = (int64_t)key_id(mn);
-            }
-        }
+        if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
         last_hi = gh; last_lo = gl; first = false;
     }
 }
@@ -202,7 +230,7 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
     float* col = s_lut + (t16 >> 1) * 16384 + (t16 & 1) * 32 + (j & 15);
     float* colA = col + 16 * rep_first;
     float* colB = col + 16 * (rep_first ^ 1);
-    constexpr int U = 4;
+    constexpr int U = 8;
     if (dsub <= 16) {
         float qv[16];
 #pragma unroll
@@ -299,10 +327,11 @@ ivfpq_scan_kernel(ScanArgs a) {
     int* s_pref = s_len + a.nprobe;                                       // [nprobe + 1] chunk prefix
     int* s_item = s_pref + a.nprobe + 1;                                  // [2] work items (double buffered)
     int* s_thr = s_item + 2;                                              // [1] CTA acceptance threshold
-    int* s_ncand = s_thr + 1;                                             // [1] candidates published for the merge
-    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_ncand + 1) + 15) & ~(uintptr_t)15);
-    u64* s_cand = s_wq + (size_t)nwarps * a.Pw;                           // [nwarps * Pw] published candidates
-    unsigned char* misc_end = reinterpret_cast<unsigned char*>(s_cand + (size_t)nwarps * a.Pw);
+    int* s_ncand = s_thr + 1;                                             // [2] candidates published for the merge
+    int* s_next = s_ncand + 2;                                            // [1] next chunk to hand out
+    u64* s_wq = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(s_next + 1) + 15) & ~(uintptr_t)15);
+    u64* s_cand = s_wq + (size_t)nwarps * a.Pw;                           // [2][nwarps * Pw] published candidates
+    unsigned char* misc_end = reinterpret_cast<unsigned char*>(s_cand + 2 * (size_t)nwarps * a.Pw);
     const uint32_t dyn_abs = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t tab_abs = (dyn_abs + (uint32_t)(misc_end - smem_raw) + 65535u) & ~65535u;
     float* s_lut = reinterpret_cast<float*>(smem_raw + (tab_abs - dyn_abs)); // NTAB x [256][64]
@@ -325,11 +354,13 @@ ivfpq_scan_kernel(ScanArgs a) {
         asm volatile("" : "+r"(pre[b]));      // opaque: keep the 16 constants in registers, never recompute them
     }
 
-    if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); *s_ncand = 0; }
+    if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); s_ncand[0] = 0; s_ncand[1] = 0; }
     __syncthreads();
     int buf = 0;
     bool have_prev = false;
     int64_t prev_qi = 0;
+    long long t_mark = clock64();
+    unsigned long long cyc_pro = 0, cyc_scan = 0, cyc_tail = 0;
     for (;;) {
         const int item = s_item[buf];
         const bool more = item < a.nq;
@@ -337,35 +368,51 @@ ivfpq_scan_kernel(ScanArgs a) {
         const float* q = a.queries + qi * (int64_t)a.d;
         const int32_t* qprobes = a.probes + qi * (int64_t)a.nprobe;
 
-        if (warp == 0) {
-            // ---- select the k best of the candidates the warps published for the PREVIOUS query, while
-            //      the other warps already build this query's table.  Keys are unique, so "the smallest key
-            //      greater than the last one taken" walks them in order without mutating anything.
-            if (have_prev) {
-                select_and_write(s_cand, *s_ncand, a.k, order_max, prev_qi, a.out_dist, a.out_ids);
-                __syncwarp();
-                if (lane == 0) *s_ncand = 0;
-            }
-        } else if (more) {
-            // ---- prologue of this query (warps 1..) ----
-            if (tid == 32) { s_item[buf ^ 1] = atomicAdd(a.work_counter, 1); *cta_thr = 0xFFFFFFFFu; }
+        if (more) {
+            // ---- prologue: warp 1 builds the probe table, every other warp the look-up table ----
+            if (tid == 32) { s_item[buf ^ 1] = atomicAdd(a.work_counter, 1); *cta_thr = 0xFFFFFFFFu; *s_next = 0; }
+            const long long t0 = clock64();
             if (warp == 1)
                 build_probe_table(qprobes, a.bias + qi * (int64_t)a.nprobe, a.nprobe, a.list_off, a.list_len, s_start,
                                   s_len, s_pref, s_bias);
             else
-                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid - 64, (int)blockDim.x - 64);
+                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, warp == 0 ? tid : tid - 32, (int)blockDim.x - 32);
+            if (a.phase_cycles && (tid == 32 || tid == 64)) atomicAdd(a.phase_cycles + (tid == 32 ? 4 : 5), (unsigned long long)(clock64() - t0));
         }
-        __syncthreads();                                   // (1) table, probe table, bias ready; merge done
+        __syncthreads();                                   // (1) table, probe table, bias ready
+        // ---- warp 0 first selects the k best of the candidates published for the PREVIOUS query; the other
+        //      warps are already scanning, and chunks are handed out dynamically, so nobody waits for it
+        if (warp == 0 && have_prev) {
+            const long long t0 = clock64();
+            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 6, (unsigned long long)s_ncand[buf ^ 1]);
+            select_and_write(s_cand + (size_t)(buf ^ 1) * nwarps * a.Pw, s_ncand[buf ^ 1], a.k, order_max, prev_qi, a.out_dist,
+                             a.out_ids);
+            __syncwarp();
+            if (lane == 0) s_ncand[buf ^ 1] = 0;
+            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 3, (unsigned long long)(clock64() - t0));
+        }
         if (!more) break;
+        { const long long t = clock64(); cyc_pro += (unsigned long long)(t - t_mark); t_mark = t; }
 
-        // ---- scan: warp-strided over 32-slot chunks of the probed lists ----
+        // ---- scan: 32-slot chunks of the probed lists, handed out dynamically ----
         const int nchunks = s_pref[a.nprobe];
         int cnt = 0;                                       // unsorted candidates behind the k sorted ones
         bool sorted_valid = false;                         // wq[0, k) holds a sorted best list
         uint32_t thr_u = 0xFFFFFFFFu;
         int p = 0;
         uint4 wA[G], wB[G];
-        int ch = warp;
+        // chunks are handed out CTA-wide, kGrab consecutive chunks per shared-memory atomic
+        constexpr int kGrab = 4;
+        int grab_end = 0;
+        auto grab = [&](int prev) {
+            if (prev + 1 < grab_end) return prev + 1;
+            int c = 0;
+            if (lane == 0) c = atomicAdd(s_next, kGrab);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            grab_end = c + kGrab;
+            return c;
+        };
+        int ch = grab(-1);
         int cp = 0;
         int64_t cg = 0;
         bool cvalid = false;
@@ -385,7 +432,7 @@ ivfpq_scan_kernel(ScanArgs a) {
             const bool valid = cvalid;
             const float bias = s_bias[cp];
 #define VIX_ADVANCE()                                                         \
-            ch += nwarps;                                                         \
+            ch = grab(ch);                                                        \
             if (ch < nchunks) {                                                   \
                 while (ch >= s_pref[p + 1]) ++p;                                  \
                 const int within = (ch - s_pref[p]) * 32 + lane;                  \
@@ -460,13 +507,15 @@ ivfpq_scan_kernel(ScanArgs a) {
                 const unsigned ball = __ballot_sync(0xFFFFFFFFu, keep);
                 if (ball) {
                     int pos = 0;
-                    if (lane == 0) pos = atomicAdd(s_ncand, __popc(ball));
+                    if (lane == 0) pos = atomicAdd(s_ncand + buf, __popc(ball));
                     pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-                    if (keep) s_cand[pos + __popc(ball & ((1u << lane) - 1u))] = key;
+                    if (keep) s_cand[(size_t)buf * nwarps * a.Pw + pos + __popc(ball & ((1u << lane) - 1u))] = key;
                 }
             }
         }
+        { const long long t = clock64(); cyc_scan += (unsigned long long)(t - t_mark); t_mark = t; }
         __syncthreads();                                   // (2) scan finished everywhere, candidates published
+        { const long long t = clock64(); cyc_tail += (unsigned long long)(t - t_mark); t_mark = t; }
         have_prev = true;
         prev_qi = qi;
         buf ^= 1;
@@ -474,6 +523,11 @@ ivfpq_scan_kernel(ScanArgs a) {
     if (a.scanned) {
         for (int o = 16; o > 0; o >>= 1) scanned_local += __shfl_xor_sync(0xFFFFFFFFu, scanned_local, o);
         if (lane == 0 && scanned_local) atomicAdd(a.scanned, scanned_local);
+    }
+    if (a.phase_cycles && tid == 64) {                     // one scanning warp per CTA reports its phase split
+        atomicAdd(a.phase_cycles + 0, cyc_pro);
+        atomicAdd(a.phase_cycles + 1, cyc_scan);
+        atomicAdd(a.phase_cycles + 2, cyc_tail);
     }
 }
 
@@ -618,8 +672,8 @@ static int launch_fast(ScanArgs& a) {
     constexpr int NTAB = (G + 1) / 2;
     // as many warps as the per-warp selection queues leave room for (24 unless k is large)
     int nwarps = kFastThreads / 32;
-    while (nwarps > 3 && 2 * (size_t)nwarps * a.Pw * 8 > 56 * 1024) --nwarps;
-    size_t misc = (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16 + 16 + 2 * (size_t)nwarps * a.Pw * 8;
+    while (nwarps > 3 && 3 * (size_t)nwarps * a.Pw * 8 > 56 * 1024) --nwarps;
+    size_t misc = (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 24 + 16 + 3 * (size_t)nwarps * a.Pw * 8;
     // the tables start at the next 64 KB boundary of the shared window, wherever the dynamic segment begins
     size_t smem = misc + 65535 + (size_t)NTAB * 65536;
     if (smem > 227 * 1024) smem = 227 * 1024;

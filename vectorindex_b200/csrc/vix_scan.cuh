@@ -22,6 +22,7 @@ struct ScanArgs {
     int metric, k, Pw, P2;
     float* out_dist; int64_t* out_ids;            // [nq x k]
     unsigned long long* scanned;                  // optional: total list entries visited
+    unsigned long long* phase_cycles;             // optional [3]: SM cycles in prologue / scan / tail wait, summed over CTAs
 };
 
 // How the inverted lists are laid out for a given m.
