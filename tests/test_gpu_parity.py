@@ -526,6 +526,65 @@ def test_device_resident_search_equals_host_path(oracle):
     assert dd.is_cuda and np.array_equal(di.cpu().numpy(), hi) and np.array_equal(bits(dd.cpu().numpy()), bits(hd))
 
 
+# ------------------------------------------------------------------------------------------------ reference-parity trainers
+def test_kmeanspp_seed_parity(oracle, vk):
+    """kmeansPlusPlusSeed (KMeansSeeding.swift:167-409): same LCG stream, same chosen rows, same centroids."""
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((3000, 24)) + 3 * rng.standard_normal((9, 24))[rng.integers(0, 9, 3000)]).astype(np.float32)
+    for seed, stream, k in ((42, 0, 37), (7, 3, 64)):
+        oc, och = oracle.kmeanspp_seed(x, k, seed, stream)
+        gc, gch = vk.kmeansPlusPlusSeed(x, k, seed, stream)
+        assert np.array_equal(gch, och)
+        assert np.array_equal(bits(gc), bits(oc))
+
+
+@pytest.mark.parametrize("n,d,kc,batch,epochs", [(5000, 16, 64, 1024, 5), (1500, 33, 20, 256, 3), (900, 8, 300, 128, 2)])
+def test_kmeans_minibatch_parity(oracle, vk, n, d, kc, batch, epochs):
+    """kmeans_minibatch_f32 in reference-parity mode: batches drawn with replacement from the LCG, batch-mean
+    replacement, the 'empties' repair quirk, reservoir-sampled inertia and the early stop -- centroids and final
+    assignments bit-identical to the oracle (KMeansMiniBatchKernel.swift:401-724)."""
+    rng = np.random.default_rng(n + kc)
+    x = (rng.standard_normal((n, d)) + 2 * rng.standard_normal((11, d))[rng.integers(0, 11, n)]).astype(np.float32)
+    rc, oc, oa, info = oracle.kmeans_minibatch(x, kc, None, batch, epochs, 1e-4, 42, 0, compute_assignments=True)
+    assert rc == 0
+    st, gc, ga = vk.kmeans_minibatch_f32(x, kc, None, vk.kmeans_cfg(batch, epochs, 1e-4, 42, 0, True, 0), compute_assignments=True)
+    assert np.array_equal(bits(gc), bits(oc))
+    assert np.array_equal(ga, oa)
+    # explicit initial centroids take the same path minus the seeding
+    init = np.ascontiguousarray(x[:kc])
+    rc, oc2, _, _ = oracle.kmeans_minibatch(x, kc, init, batch, 2, 1e-4, 5, 1)
+    _, gc2, _ = vk.kmeans_minibatch_f32(x, kc, init, vk.kmeans_cfg(batch, 2, 1e-4, 5, 1, False, 0))
+    assert np.array_equal(bits(gc2), bits(oc2))
+
+
+@pytest.mark.parametrize("n,d,m,ks,algo,policy,residual,sample_n", [
+    (3000, 32, 4, 256, 0, 0, False, 0),      # Lloyd, subset seeding (n > 4 ks), .split
+    (3000, 32, 4, 256, 0, 1, True, 0),       # Lloyd on residuals, .reseed
+    (700, 24, 3, 256, 0, 0, True, 0),        # n <= 4 ks: strided seeding; empty clusters guaranteed -> .split repair
+    (2500, 16, 2, 64, 0, 2, False, 1200),    # sampled training set, .ignore
+    (3000, 32, 4, 256, 1, 0, True, 0),       # mini-batch (forces sample_n = 2000 and .reseed, PQTrain.swift:144-149)
+    (1800, 16, 2, 128, 1, 0, False, 900),    # mini-batch with an explicit sample
+])
+def test_pq_train_parity(oracle, vk, n, d, m, ks, algo, policy, residual, sample_n):
+    """pq_train_f32 in reference-parity mode: Xoroshiro128** streams per sub-space, selection sampling, k-means++
+    seeding, Lloyd / mini-batch with the reference's repair policies -- codebooks and norms bit-identical to the
+    oracle (PQTrain.swift:83-388, 856-1442)."""
+    rng = np.random.default_rng(n + ks + algo)
+    x = (rng.standard_normal((n, d)) + 2 * rng.standard_normal((7, d))[rng.integers(0, 7, n)]).astype(np.float32)
+    coarse = asg = None
+    if residual:
+        coarse = np.ascontiguousarray(x[rng.choice(n, 9, replace=False)])
+        asg, _ = oracle.assign(x, coarse)
+    rc, ocb, onorm, _ = oracle.pq_train(x, m, ks, coarse=coarse, assign_=asg, algorithm=algo, max_iters=4, batch_size=512,
+                                        empty_policy=policy, sample_n=sample_n, seed=42, stream_id=2)
+    assert rc == 0
+    cfg = vk.pq_train_cfg(algorithm=algo, max_iters=4, tol=1e-4, batch_size=512, sample_n=sample_n, seed=42, stream_id=2,
+                          empty_policy=policy, mode=0)
+    gcb, gnorm = vk.pq_train_f32(x, m, ks, coarse, asg, cfg)
+    assert np.array_equal(bits(gcb), bits(ocb))
+    assert np.array_equal(bits(gnorm), bits(onorm))
+
+
 def test_gpu_training_builds_a_working_index(oracle):
     """mode-1 trainers (deterministic Lloyd): the trained IVF-PQ index reaches a sane recall and two
     trainings give bit-identical parameters (rank-to-rank reproducibility for the sharded build)."""

@@ -41,6 +41,10 @@ int train_coarse_device(const float* x, int64_t n, int d, int kc, int metric, co
                         float* centroids_out);
 int train_pq_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
                     const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
+int kmeans_parity_device(const float* x, int64_t n, int d, int kc, const float* init, const vix_kmeans_cfg* cfg,
+                         float* centroids_out, int32_t* assign_out);
+int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
+                           const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                              const float* cnorm, int32_t* out_idx, float* out_scores);
 
@@ -723,7 +727,9 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
     VIX_TRY(dx.stage(x, (size_t)n * d));
     const int kc = (int)(h->p.nlist < n ? h->p.nlist : n);          // nlist clamped to n (IVFIndex.swift:320)
     VIX_TRY(h->coarse.resize((size_t)kc * d, false));
-    VIX_TRY(train_coarse_device(dx.dev, n, d, kc, h->p.metric, kcfg, h->coarse.ptr));
+    // mode 0: the reference's trainer (k-means++ + mini-batch, IVFIndex.swift:337-341, 668-681); mode 1: GPU Lloyd
+    if (kcfg && kcfg->mode == 0) VIX_TRY(kmeans_parity_device(dx.dev, n, d, kc, nullptr, kcfg, h->coarse.ptr, nullptr));
+    else VIX_TRY(train_coarse_device(dx.dev, n, d, kc, h->p.metric, kcfg, h->coarse.ptr));
     h->kc = kc;
     VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
     VIX_TRY(row_norms_device(h->coarse.ptr, kc, d, h->coarse_norms.ptr));
@@ -736,7 +742,8 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
         const int m = h->p.m, ks = h->p.ks;
         VIX_TRY(h->codebooks.resize((size_t)ks * d, false));
         VIX_TRY(h->cb_norms.resize((size_t)m * ks, false));
-        VIX_TRY(train_pq_device(dx.dev, n, d, m, ks, h->coarse.ptr, asg.ptr, pcfg, h->codebooks.ptr, h->cb_norms.ptr));
+        if (pcfg && pcfg->mode == 0) VIX_TRY(pq_train_parity_device(dx.dev, n, d, m, ks, h->coarse.ptr, asg.ptr, pcfg, h->codebooks.ptr, h->cb_norms.ptr));
+        else VIX_TRY(train_pq_device(dx.dev, n, d, m, ks, h->coarse.ptr, asg.ptr, pcfg, h->codebooks.ptr, h->cb_norms.ptr));
         VIX_TRY(update_codebooks_t(h));
         h->has_pq = true;
     }
