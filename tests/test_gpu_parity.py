@@ -186,6 +186,24 @@ def test_flat_search_bench_fixture_and_ties(oracle, vk):
     assert gi[0, 0] == 0 and gi[0, 1] == 3000
 
 
+@pytest.mark.parametrize("n,d,nq,k,metric", [(100000, 128, 200, 10, 0), (20000, 96, 64, 32, 1), (9000, 768, 40, 5, 0),
+                                             (12000, 100, 33, 20, 0)])
+def test_flat_search_tensor_core_shortlist_is_exact(oracle, vk, n, d, nq, k, metric):
+    """n >= 4096 takes the tcgen05 shortlist + exact rescoring path (C1-shaped first case): ids and distance bits equal
+    the oracle's restatement of the reference kernels, including duplicated base rows (tie -> smaller id)."""
+    from vectorindex_b200 import datagen
+    xb = datagen.bench_vectors(n, d, 123) if metric == 0 else np.random.default_rng(n).standard_normal((n, d)).astype(np.float32)
+    q = datagen.bench_vectors(nq, d, 321)
+    xb[n // 2] = xb[17]
+    xb[n - 1] = xb[17]
+    q[0] = xb[17]
+    od, oi, _ = oracle.flat_search(q, xb, k, metric)
+    gd, gi = vk.flat_search_f32(q, xb, k, metric)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(bits(gd), bits(od))
+    assert gi[0, 0] == 17 and set(gi[0, :3]) == {17, n // 2, n - 1}
+
+
 def test_flat_search_edge_cases(vk):
     q = np.zeros((3, 8), dtype=np.float32)
     d, i = vk.flat_search_f32(q, np.zeros((0, 8), np.float32), 4)

@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 
 namespace vix {
@@ -504,6 +505,66 @@ __global__ void scatter_assign_rows_kernel(const int32_t* __restrict__ sub_assig
     if (dist) dist[rows[i]] = sub_dist[i];
 }
 
+// Flat scan from the shortlist: one CTA per query evaluates the reference kernel for every candidate --
+// _l2sqr_single_direct (d < 256, L2SqrKernel.swift:192-238), the fused dot form with clamp (d >= 256, :411-448) or
+// InnerProduct (InnerProduct.swift:115-184) -- then selects by (score, id) and maps to the API distance
+// (FlatIndexOptimized.swift:457-474: sqrt for L2, -dot for IP).
+__global__ void __launch_bounds__(256)
+rescore_flat_kernel(const float* __restrict__ A, const float* __restrict__ B, int d, int metric, int dotfused,
+                    const float* __restrict__ anorm, const float* __restrict__ bnorm, const int* __restrict__ cand_cnt,
+                    const int32_t* __restrict__ cand_idx, int cap, int P, int k, int raw, float* __restrict__ out_dist,
+                    int64_t* __restrict__ out_ids, int* __restrict__ overflow_rows, int* __restrict__ n_overflow) {
+    extern __shared__ __align__(16) unsigned char smem_rf[];
+    u64* keys = reinterpret_cast<u64*>(smem_rf);
+    float* sq = reinterpret_cast<float*>(keys + P);
+    const int64_t row = blockIdx.x;
+    const int n = cand_cnt[row];
+    if (n > cap) {
+        if (threadIdx.x == 0) overflow_rows[atomicAdd(n_overflow, 1)] = (int)row;
+        return;
+    }
+    const int order_max = (metric == VIX_METRIC_IP);
+    for (int e = threadIdx.x; e < d; e += blockDim.x) sq[e] = A[row * d + e];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = kEmptyKey;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = cand_idx[row * cap + i];
+        const float* xr = B + (int64_t)c * d;
+        float s;
+        if (order_max) s = exact_pair<SpecIp4>(sq, xr, d);
+        else if (dotfused) {
+            const float dot = exact_pair<SpecDot16>(sq, xr, d);
+            const float dist = fsub(fadd(anorm[row], bnorm[c]), fmul(2.0f, dot));
+            s = dist < 0.0f ? 0.0f : dist;
+        } else s = exact_pair<SpecDirect16L2>(sq, xr, d);
+        keys[i] = make_key(s, (uint32_t)c, order_max);
+    }
+    __syncthreads();
+    bitonic_sort_keys<false>(keys, P, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const u64 key = keys[i];
+        const size_t o = (size_t)row * k + i;
+        if (key == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
+        else {
+            float sc = key_score(key, order_max);
+            if (!raw) sc = order_max ? -sc : __fsqrt_rn(sc);
+            out_dist[o] = sc;
+            out_ids[o] = (int64_t)key_id(key);
+        }
+    }
+}
+
+__global__ void scatter_flat_rows_kernel(const float* __restrict__ sub_d, const int64_t* __restrict__ sub_i, int k,
+                                         const int* __restrict__ rows, int n, float* __restrict__ out_d,
+                                         int64_t* __restrict__ out_i) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int e = threadIdx.x; e < k; e += blockDim.x) {
+        out_d[(int64_t)rows[i] * k + e] = sub_d[(int64_t)i * k + e];
+        out_i[(int64_t)rows[i] * k + e] = sub_i[(int64_t)i * k + e];
+    }
+}
+
 __global__ void gather_rows_f32_kernel(const float* __restrict__ x, int d, const int* __restrict__ rows, int n,
                                        float* __restrict__ out) {
     const int i = blockIdx.x;
@@ -617,6 +678,82 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
         VIX_LAUNCH_CHECK();
         VIX_TRY(probe_select_device(sub.ptr, n, c, kc, d, metric, nprobe, cn, nullptr, sub_idx.ptr, sub_sc.ptr));
         tc::scatter_probe_rows_kernel<<<n, 128, 0, s>>>(sub_idx.ptr, sub_sc.ptr, nprobe, ovf_rows.ptr, n, out_idx, out_scores);
+        VIX_LAUNCH_CHECK();
+    }
+    return VIX_OK;
+}
+
+int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                       const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
+
+// Exact flat search (a1-a4) through the tensor-core shortlist; results identical to flat_search_device.
+int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                            const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores) {
+    if (nq == 0 || k <= 0) return VIX_OK;
+    const int keff = (int)(k < n ? k : n);
+    const int gcols = n > 0 ? tc::choose_gcols((int)std::min<int64_t>(n, 0x7FFFFF00), keff) : 32;
+    const int64_t ngroups64 = n > 0 ? (n + gcols - 1) / gcols : 0;
+    const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && xb_norm == nullptr && n >= 4096 && n < (1LL << 31) - 256 &&
+                        nq >= 16 && tc::supported(nq, n, d, q, xb) && ngroups64 >= 2 * keff && keff <= 256 && d <= 4096;
+    if (!use_tc) return flat_search_device(q, nq, xb, n, d, metric, k, xb_norm, out_dist, out_ids, raw_scores);
+    cudaStream_t s = ctx().stream;
+    const int ngroups = (int)ngroups64;
+    const int nb = (int)n;
+    const int cap = keff * 4 + 128;
+    Scratch<float> gmin, thr, qn, xn, xmax;
+    Scratch<int> cand_cnt, flags, ovf_rows;
+    Scratch<int32_t> cand_idx;
+    VIX_TRY(gmin.alloc((size_t)nq * ngroups));
+    VIX_TRY(thr.alloc((size_t)nq));
+    VIX_TRY(qn.alloc((size_t)nq));
+    VIX_TRY(xn.alloc((size_t)n));
+    VIX_TRY(xmax.alloc(1));
+    VIX_TRY(cand_cnt.alloc((size_t)nq));
+    VIX_TRY(cand_idx.alloc((size_t)nq * cap));
+    VIX_TRY(flags.alloc(2));
+    VIX_TRY(ovf_rows.alloc((size_t)nq));
+    VIX_CUDA(cudaMemsetAsync(flags.ptr, 0, 8, s));
+    VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
+    VIX_TRY(row_norms_device(q, nq, d, qn.ptr));
+    VIX_TRY(row_norms_device(xb, n, d, xn.ptr));          // Norms.l2NormSquared: also the exact ||x||^2 of the d >= 256 path
+    tc::max_sqrt_kernel<<<1, 256, 0, s>>>(xn.ptr, n, xmax.ptr);
+    VIX_LAUNCH_CHECK();
+    tc::Args a{};
+    a.metric = metric; a.bnorm = (metric == VIX_METRIC_L2) ? xn.ptr : nullptr; a.error = flags.ptr;
+    a.mode = tc::MODE_MIN; a.gcols = gcols; a.ngroups = ngroups; a.gmin = gmin.ptr;
+    VIX_TRY(tc::launch(q, nq, xb, nb, d, a));
+    const float rel = ((metric == VIX_METRIC_L2) ? 2.0f : 1.0f) * 1.25f * (2.0f / 1024.0f + (float)d / 2097152.0f);
+    {
+        const int P = next_pow2(ngroups < 2 ? 2 : ngroups);
+        tc::threshold_kernel<<<(unsigned)nq, 256, (size_t)P * 4, s>>>(gmin.ptr, ngroups, P, keff, qn.ptr, xmax.ptr, rel, thr.ptr);
+        VIX_LAUNCH_CHECK();
+    }
+    a.mode = tc::MODE_EMIT; a.thr = thr.ptr; a.cand_cnt = cand_cnt.ptr; a.cand_idx = cand_idx.ptr; a.cap = cap;
+    VIX_TRY(tc::launch(q, nq, xb, nb, d, a));
+    {
+        const int P = next_pow2(cap);
+        const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+        VIX_CUDA(cudaFuncSetAttribute(tc::rescore_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::rescore_flat_kernel<<<(unsigned)nq, 256, smem, s>>>(q, xb, d, metric, d >= 256 ? 1 : 0, qn.ptr, xn.ptr, cand_cnt.ptr,
+                                                              cand_idx.ptr, cap, P, k, raw_scores ? 1 : 0, out_dist, out_ids,
+                                                              ovf_rows.ptr, flags.ptr + 1);
+        VIX_LAUNCH_CHECK();
+    }
+    int hflags[2] = {0, 0};
+    VIX_CUDA(cudaMemcpyAsync(hflags, flags.ptr, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    VIX_REQUIRE(hflags[0] == 0, VIX_ERR_CUDA, "tensor-core pipeline timed out");
+    if (hflags[1] > 0) {
+        const int m = hflags[1];
+        Scratch<float> sub, sub_d;
+        Scratch<int64_t> sub_i;
+        VIX_TRY(sub.alloc((size_t)m * d));
+        VIX_TRY(sub_d.alloc((size_t)m * k));
+        VIX_TRY(sub_i.alloc((size_t)m * k));
+        tc::gather_rows_f32_kernel<<<m, 128, 0, s>>>(q, d, ovf_rows.ptr, m, sub.ptr);
+        VIX_LAUNCH_CHECK();
+        VIX_TRY(flat_search_device(sub.ptr, m, xb, n, d, metric, k, nullptr, sub_d.ptr, sub_i.ptr, raw_scores));
+        tc::scatter_flat_rows_kernel<<<m, 128, 0, s>>>(sub_d.ptr, sub_i.ptr, k, ovf_rows.ptr, m, out_dist, out_ids);
         VIX_LAUNCH_CHECK();
     }
     return VIX_OK;

@@ -30,6 +30,8 @@ int pq_encode_device(const float* x, int64_t n, int d, int m, int ks, const floa
                      int B, int g, int u4);
 int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
                        const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
+int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                            const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                         const float* cnorm, const uint64_t* disabled, int32_t* out_idx, float* out_scores);
 int ivf_assign_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
@@ -501,7 +503,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         VIX_REQUIRE(h->p.kind != VIX_INDEX_IVF_PQ, VIX_ERR_NOT_TRAINED, "index_search: IVF-PQ index is not trained");
         Scratch<int64_t> rows;
         VIX_TRY(rows.alloc((size_t)nq * k));
-        VIX_TRY(flat_search_device(dq.dev, nq, h->vecs.ptr, h->n, d, h->p.metric, k, nullptr, dd.dev, rows.ptr, false));
+        VIX_TRY(flat_search_auto_device(dq.dev, nq, h->vecs.ptr, h->n, d, h->p.metric, k, nullptr, dd.dev, rows.ptr, false));
         // row index -> user id
         gather_ids_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, s>>>(rows.ptr, h->ids.ptr, di.dev, nq * (int64_t)k);
         VIX_LAUNCH_CHECK();

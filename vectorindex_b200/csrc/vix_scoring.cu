@@ -241,6 +241,9 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
 
 int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
 
+int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                            const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
+
 int launch_merge_keys(const u64* keys, int64_t rows, int nin, int k, int order_max, int dist_mode,
                       float* out_score, int64_t* out_id64, int32_t* out_id32, int* out_count,
                       uint32_t id_xor = 0) {
@@ -623,7 +626,7 @@ int vix_flat_search_f32(const float* queries, int64_t nq, const float* xb, int64
     VIX_TRY(dx.stage(xb, (size_t)n * d));
     VIX_TRY(dd.stage(out_dist, (size_t)nq * k));
     VIX_TRY(di.stage(out_ids, (size_t)nq * k));
-    VIX_TRY(flat_search_device(dq.dev, nq, dx.dev, n, d, metric, k, nullptr, dd.dev, di.dev, false));
+    VIX_TRY(flat_search_auto_device(dq.dev, nq, dx.dev, n, d, metric, k, nullptr, dd.dev, di.dev, false));   // tensor-core shortlist + exact rescoring
     VIX_TRY(dd.commit());
     VIX_TRY(di.commit());
     return finish(dd.is_host() || di.is_host());
@@ -647,7 +650,7 @@ int vix_accel_rank_candidates_f32(const float* queries, int64_t nq, const float*
     VIX_TRY(dd.stage(out_distances, (size_t)nq * k));
     VIX_TRY(di.stage(out_indices, (size_t)nq * k));
     VIX_TRY(id64.alloc((size_t)nq * k));
-    VIX_TRY(flat_search_device(dq.dev, nq, dx.dev, c, d, metric, k, nullptr, dd.dev, id64.ptr, false));
+    VIX_TRY(flat_search_auto_device(dq.dev, nq, dx.dev, c, d, metric, k, nullptr, dd.dev, id64.ptr, false));
     // narrow ids to int32 (AcceleratedResults.indices, AccelerableIndex.swift:60-75)
     {
         int64_t total = nq * (int64_t)k;
