@@ -47,7 +47,8 @@ namespace tc {
 constexpr int kM = 128, kN = 128, kKB = 32;            // tile rows, tile columns, tf32 elements per K-block
 constexpr int kStages = 5;
 constexpr int kStageBytes = (kM + kN) * kKB * 4;       // 32 KB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: each takes 64 of the 128 columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 256;                         // two fp32 accumulators of 128 columns
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
 
@@ -171,12 +172,12 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* tfull = empty + kStages;                                               // [2]
     uint64_t* tempty = tfull + 2;                                                    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [4 warps][2][128] column norms
+    float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [kEpiWarps][2][64] column norms
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -238,8 +239,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+        // ================= epilogue (warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4) =================
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         int acc = 0; uint32_t aphase = 0;
         bool ok = true;
         for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
@@ -250,48 +252,77 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const float thr = (a.mode == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
             float gmin = INFINITY;
             for (int nt = nt0; nt < nt1 && ok; ++nt) {
-                // stage this tile's column norms (one private copy per warp: no CTA-level barrier needed)
-                float* bn = s_bn + ((warp - 2) * 2 + acc) * kN;
+                // stage this warp's 64 column norms (private copy per warp: no CTA-level barrier needed)
+                float* bn = s_bn + ((warp - 2) * 2 + acc) * 64;
 #pragma unroll
-                for (int t = 0; t < kN / 32; ++t) {
-                    const int col = nt * kN + t * 32 + lane;
+                for (int t = 0; t < 2; ++t) {
+                    const int col = nt * kN + half * 64 + t * 32 + lane;
                     bn[t * 32 + lane] = (a.bnorm && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
                 }
                 __syncwarp();
                 if (!mbar_wait(tfull + acc, aphase, a.error)) { ok = false; break; }
                 fence_after_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN;
-                const int colbase = nt * kN;
-                const bool full_tile = colbase + kN <= a.nB;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN + (uint32_t)half * 64;
+                const int colbase = nt * kN + half * 64;
+                const bool full_tile = nt * kN + kN <= a.nB;
 #pragma unroll 1
-                for (int ck = 0; ck < kN / 32; ++ck) {
+                for (int ck = 0; ck < 2; ++ck) {
                     float v[32];
                     tmem_ld32(taddr + ck * 32, v);
-                    float cmin = INFINITY;
+                    const float4* bn4 = reinterpret_cast<const float4*>(bn + ck * 32);
+                    float sc[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = colbase + ck * 32 + i;
-                        float s = (a.metric == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], bn[ck * 32 + i]) : -v[i];
-                        if (!full_tile && col >= a.nB) s = INFINITY;
-                        if (a.mode == MODE_WRITE) {
-                            if (row_ok && col < a.nB) a.out[row * a.nB + col] = s;
-                        } else if (a.mode == MODE_MIN) {
-                            cmin = fminf(cmin, s);
-                        } else {
-                            if (s <= thr) {
-                                const int pos = atomicAdd(a.cand_cnt + row, 1);
-                                if (pos < a.cap) a.cand_idx[row * a.cap + pos] = col;
-                            }
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 nb = (a.metric == VIX_METRIC_L2) ? bn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = 4 * i4 + u;
+                            float s = (a.metric == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], nbv[u]) : -v[i];
+                            if (!full_tile && colbase + ck * 32 + i >= a.nB) s = INFINITY;
+                            sc[i] = s;
                         }
                     }
-                    if (a.mode == MODE_MIN) {
-                        gmin = fminf(gmin, cmin);
-                        // group boundary: gcols is 32, 64 or a multiple of 128 that divides the split
-                        const int colend = colbase + ck * 32 + 32;
-                        if (colend % a.gcols == 0 || (nt == a.ntiles - 1 && ck == kN / 32 - 1)) {
-                            const int g = (colend - 1) / a.gcols;
+                    if (a.mode == MODE_WRITE) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int col = colbase + ck * 32 + i;
+                            if (row_ok && col < a.nB) a.out[row * a.nB + col] = sc[i];
+                        }
+                    } else if (a.mode == MODE_MIN) {
+                        // tree minimum of the 32 columns
+#pragma unroll
+                        for (int w2 = 16; w2 > 0; w2 >>= 1)
+#pragma unroll
+                            for (int i = 0; i < w2; ++i) sc[i] = fminf(sc[i], sc[i + w2]);
+                        gmin = fminf(gmin, sc[0]);
+                        // group boundary.  gcols 32 / 64: groups are whole chunks / half-tile strips of this thread;
+                        // gcols = 128 t: a group is this thread's 64-column strip of t consecutive tiles (the two
+                        // column halves of a tile belong to different groups: any disjoint partition is valid)
+                        bool flush;
+                        int g;
+                        if (a.gcols < kN) {
+                            const int colend = colbase + ck * 32 + 32;
+                            flush = (colend % a.gcols) == 0;
+                            g = (colend - 1) / a.gcols;
+                        } else {
+                            const int tpg = a.gcols / kN;
+                            flush = ck == 1 && (((nt + 1) % tpg) == 0 || nt == a.ntiles - 1);
+                            g = (nt / tpg) * 2 + half;
+                        }
+                        if (flush) {
                             if (row_ok && g < a.ngroups) a.gmin[row * a.ngroups + g] = gmin;
                             gmin = INFINITY;
+                        }
+                    } else {
+                        uint32_t hit = 0;                          // columns of this chunk with S~ <= T
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) hit |= (sc[i] <= thr) ? (1u << i) : 0u;
+                        while (hit) {                              // rare: ~1.2 k hits per row in the whole matrix
+                            const int i = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            const int pos = atomicAdd(a.cand_cnt + row, 1);
+                            if (pos < a.cap) a.cand_idx[row * a.cap + pos] = colbase + ck * 32 + i;
                         }
                     }
                 }
@@ -350,7 +381,7 @@ bool supported(int64_t nA, int64_t nB, int d, const float* A, const float* B) {
     return encode_fn() != nullptr;
 }
 
-static size_t smem_bytes() { return (size_t)kStages * kStageBytes + 1024 + 256 + 4 * 2 * kN * 4; }
+static size_t smem_bytes() { return (size_t)kStages * kStageBytes + 1024 + 256 + (size_t)kEpiWarps * 2 * 64 * 4; }
 
 static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Args& a) {
     CUtensorMap mapA, mapB;
@@ -582,10 +613,18 @@ __global__ void scatter_probe_rows_kernel(const int32_t* __restrict__ idx, const
     }
 }
 
+// number of group minima per row for a given group width (see the MODE_MIN epilogue)
+static int num_groups(int64_t nB, int gcols) {
+    if (gcols < kN) return (int)((nB + gcols - 1) / gcols);
+    const int64_t ntiles = (nB + kN - 1) / kN, tpg = gcols / kN;
+    return (int)(2 * ((ntiles + tpg - 1) / tpg));
+}
+
 // columns per group so that a row has between ~4 k and 2048 group minima
 static int choose_gcols(int nB, int k) {
     if (k <= 1) return nB > 4096 ? 4096 : 128;       // assignment: only the row minimum matters
     int g = 32;
+    while ((nB + g - 1) / g > 1024 && (nB + 2 * g - 1) / (2 * g) >= 8 * k) g *= 2;
     while ((nB + g - 1) / g > 2048) g *= 2;
     while (g < 128 && (nB + g - 1) / g > 64 * k && (nB + 2 * g - 1) / (2 * g) >= 8 * k) g *= 2;
     return g;
@@ -616,7 +655,7 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
                              const float* cnorm, int32_t* out_idx, float* out_scores) {
     const int keff = nprobe < kc ? nprobe : kc;
     const int gcols = tc::choose_gcols(kc, keff);
-    const int ngroups = (kc + gcols - 1) / gcols;
+    const int ngroups = tc::num_groups(kc, gcols);
     const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && tc::supported(nq, kc, d, q, c) && kc >= 1024 && nq >= 16 &&
                         ngroups >= 2 * keff && keff <= 256 && d <= 4096 && (metric == VIX_METRIC_IP || cnorm != nullptr);
     if (!use_tc) return probe_select_device(q, nq, c, kc, d, metric, nprobe, cnorm, nullptr, out_idx, out_scores);
@@ -692,7 +731,7 @@ int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t
     if (nq == 0 || k <= 0) return VIX_OK;
     const int keff = (int)(k < n ? k : n);
     const int gcols = n > 0 ? tc::choose_gcols((int)std::min<int64_t>(n, 0x7FFFFF00), keff) : 32;
-    const int64_t ngroups64 = n > 0 ? (n + gcols - 1) / gcols : 0;
+    const int64_t ngroups64 = n > 0 ? tc::num_groups(n, gcols) : 0;
     const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && xb_norm == nullptr && n >= 4096 && n < (1LL << 31) - 256 &&
                         nq >= 16 && tc::supported(nq, n, d, q, xb) && ngroups64 >= 2 * keff && keff <= 256 && d <= 4096;
     if (!use_tc) return flat_search_device(q, nq, xb, n, d, metric, k, xb_norm, out_dist, out_ids, raw_scores);
@@ -769,7 +808,7 @@ int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int
     if (!use_tc) return ivf_assign_device(x, n, d, c, kc, assign, dist);
     cudaStream_t s = ctx().stream;
     const int gcols = tc::choose_gcols(kc, 1);
-    const int ngroups = (kc + gcols - 1) / gcols;
+    const int ngroups = tc::num_groups(kc, gcols);
     const int cap = 32;
     Scratch<float> gmin, thr, xn, cn, cmax;
     Scratch<int> cand_cnt, flags, ovf_rows;

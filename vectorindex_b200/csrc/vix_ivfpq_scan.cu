@@ -56,17 +56,17 @@ __device__ __forceinline__ float lds_imm(uint32_t addr) {
 
 // one group of 16 sub-quantisers: 16 look-ups of one lane, 4 running sums
 template <int T>
-__device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[16], float& s0, float& s1, float& s2,
+__device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[8], float& s0, float& s1, float& s2,
                                          float& s3) {
     constexpr int IMM = (T & 1) * 128 + (T >> 1) * 65536;
     const uint32_t x[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        // result bytes: [0] = 4 * slot (lane constant), [1] = code, [2..3] = table address >> 16
-        s0 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 0], 0x7604));
-        s1 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 1], 0x7614));
-        s2 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 2], 0x7624));
-        s3 += lds_imm<IMM>(__byte_perm(x[i], pre[4 * i + 3], 0x7634));
+        // result bytes: [0] = 4 * slot (lane constant; two per register), [1] = code, [2..3] = table address >> 16
+        s0 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604));
+        s1 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7615));
+        s2 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624));
+        s3 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7635));
     }
 }
 
@@ -346,12 +346,16 @@ ivfpq_scan_kernel(ScanArgs a) {
     unsigned long long scanned_local = 0;
     volatile uint32_t* cta_thr = reinterpret_cast<volatile uint32_t*>(s_thr);
 
-    // per-lane look-up constants: table address | 4 * (16 * replica + ((b ^ lane) & 15))
-    uint32_t pre[16];
+    // per-lane look-up constants
+    // (byte b of a group: slot byte offset 4 * (16 * replica + ((b ^ lane) & 15)); packed two per register under
+    // the table address, whose low 16 bits are zero)
+    uint32_t pre[8];
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-        pre[b] = tab_abs | (4u * (16u * (lane >> 4) + ((b ^ lane) & 15)));
-        asm volatile("" : "+r"(pre[b]));      // opaque: keep the 16 constants in registers, never recompute them
+    for (int b = 0; b < 16; b += 2) {
+        const uint32_t c0 = 4u * (16u * (lane >> 4) + ((b ^ lane) & 15));
+        const uint32_t c1 = 4u * (16u * (lane >> 4) + (((b + 1) ^ lane) & 15));
+        pre[b >> 1] = tab_abs | c0 | (c1 << 8);
+        asm volatile("" : "+r"(pre[b >> 1]));  // opaque: keep the constants in registers, never recompute them
     }
 
     if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); s_ncand[0] = 0; s_ncand[1] = 0; }
