@@ -178,7 +178,7 @@ __global__ void place_rows_kernel(const int32_t* __restrict__ sorted_rows, const
 }
 
 // Fill one slot: codes in the scan layout (vix_scan.cuh), id, t_x.  One warp per slot (lanes split the
-// sub-quantisers).  rotated != 0: byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15).
+// sub-quantisers).  rotated != 0: byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15), chunk-blocked.
 __global__ void __launch_bounds__(256)
 fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const uint8_t* __restrict__ codes,
                      const int64_t* __restrict__ ids, const int32_t* __restrict__ assign,
@@ -190,9 +190,11 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
     if (g >= nslots) return;
     const int row = slot_row[g];
     const int dsub = d / m;
-    uint8_t* dst = slot_codes + g * (int64_t)m;
+    // rotated (fast) layout is also chunk-blocked: byte b of slot g lives at chunk * 32 m + (b / 16) * 512 + (g % 32) * 16 + b % 16
+    uint8_t* dst = rotated ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) * 16 : slot_codes + g * (int64_t)m;
+    const int cstride = rotated ? 512 - 16 : 0;        // extra offset per 16-byte piece
     if (row < 0) {
-        for (int b = lane; b < m; b += 32) dst[b] = 0;
+        for (int b = lane; b < m; b += 32) dst[b + (b >> 4) * cstride] = 0;
         if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
         return;
     }
@@ -201,7 +203,7 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
     double acc = 0.0;
     for (int b = lane; b < m; b += 32) {
         const int j = rotated ? ((b & ~15) | ((b ^ (int)(g & 15)) & 15)) : b;
-        dst[b] = src[j];
+        dst[b + (b >> 4) * cstride] = src[j];
     }
     if (metric == VIX_METRIC_L2) {
         for (int j = lane; j < m; j += 32) {

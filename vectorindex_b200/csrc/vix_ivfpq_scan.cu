@@ -15,7 +15,7 @@
 // conflict-free LDS, one PRMT and one FADD per code byte and nothing else in the inner loop:
 //
 //   * one stored vector per lane (no cross-lane reduction); a warp streams 32-slot chunks of the probed
-//     lists with 128-bit loads, the next chunk prefetched into registers;
+//     lists with fully coalesced 128-bit loads (chunk-blocked code layout), the next chunk prefetched into registers;
 //   * the table is code-major, T[code][64 slots] (256 B per code, 64 KB per table, one table per 32
 //     sub-quantisers).  A 32-slot half row holds ONE group of 16 sub-quantisers twice (replica 0 | 1);
 //     codes are stored "rotated" -- byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15) -- so
@@ -70,11 +70,13 @@ __device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[8
     }
 }
 
+// codes of slot g: chunk-blocked layout -- inside a 32-slot chunk the 16-byte piece c of every slot is stored
+// contiguously ([c][slot][16]), so each of the G 128-bit loads of a warp reads 512 consecutive bytes (16 full sectors)
 template <int G>
 __device__ __forceinline__ void load_codes(uint4 (&w)[G], const uint8_t* __restrict__ codes, int64_t g, bool valid) {
-    const uint4* src = reinterpret_cast<const uint4*>(codes + g * (int64_t)(16 * G));
+    const uint4* src = reinterpret_cast<const uint4*>(codes + (g >> 5) * (int64_t)(512 * G)) + (g & 31);
 #pragma unroll
-    for (int c = 0; c < G; ++c) w[c] = valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < G; ++c) w[c] = valid ? __ldg(src + 32 * c) : make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
@@ -414,18 +416,29 @@ ivfpq_scan_kernel(ScanArgs a) {
             if (lane == 0) c = atomicAdd(s_next, kGrab);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
             grab_end = c + kGrab;
+            const uint32_t t = *cta_thr;                   // refresh the CTA-wide acceptance threshold
+            if (t < thr_u) thr_u = t;
             return c;
         };
         int ch = grab(-1);
-        int cp = 0;
+        // the probe the warp is in is cached in registers: chunk range [pb, pe), first slot / 32, length, bias
+        int pb = 0, pe = 0, pstart = 0, plen = 0;
+        float pbias = 0.0f;
         int64_t cg = 0;
         bool cvalid = false;
-        float ctx_ = 0.0f;                                 // t_x of the current chunk's vector (prefetched)
+        float ctx_ = 0.0f, cbias = 0.0f;                   // t_x and bias of the current chunk (prefetched)
+        auto locate = [&]() {                              // position of chunk `ch` (chunk indices only grow)
+            if (ch >= pe) {
+                while (ch >= s_pref[p + 1]) ++p;
+                pb = s_pref[p]; pe = s_pref[p + 1]; pstart = s_start[p]; plen = s_len[p]; pbias = s_bias[p];
+            }
+            const int within = (ch - pb) * 32 + lane;
+            cvalid = within < plen;
+            cg = ((int64_t)pstart << 5) + within;
+            cbias = pbias;
+        };
         if (ch < nchunks) {
-            while (ch >= s_pref[p + 1]) ++p;
-            const int within = (ch - s_pref[p]) * 32 + lane;
-            cp = p; cvalid = within < s_len[p];
-            cg = ((int64_t)s_start[p] << 5) + within;
+            locate();
             load_codes<G>(wA, a.slot_codes, cg, cvalid);
             ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;
         }
@@ -434,14 +447,11 @@ ivfpq_scan_kernel(ScanArgs a) {
             const float tx = ctx_;
             const int64_t g = cg;
             const bool valid = cvalid;
-            const float bias = s_bias[cp];
+            const float bias = cbias;
 #define VIX_ADVANCE()                                                         \
             ch = grab(ch);                                                        \
             if (ch < nchunks) {                                                   \
-                while (ch >= s_pref[p + 1]) ++p;                                  \
-                const int within = (ch - s_pref[p]) * 32 + lane;                  \
-                cp = p; cvalid = within < s_len[p];                               \
-                cg = ((int64_t)s_start[p] << 5) + within;                         \
+                locate();                                                         \
                 load_codes<G>(wn, a.slot_codes, cg, cvalid);                      \
                 ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;                     \
             }
@@ -459,10 +469,6 @@ ivfpq_scan_kernel(ScanArgs a) {
 #undef VIX_ADVANCE
             const float sum = (bias + tx) + ((s0 + s1) + (s2 + s3));
             if (valid) ++scanned_local;
-            {
-                const uint32_t t = *cta_thr;
-                if (t < thr_u) thr_u = t;
-            }
             const u64 key = make_key(sum, 0u, order_max);
             const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
             if (thr_u == 0xFFFFFFFFu && a.k <= 32) {

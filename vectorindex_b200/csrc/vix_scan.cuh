@@ -26,8 +26,9 @@ struct ScanArgs {
 };
 
 // How the inverted lists are laid out for a given m.
-//   fast:  AoS rows with the 16 codes of every group of 16 sub-quantisers "rotated" by the slot index:
-//          byte b of slot g holds sub-quantiser (b & ~15) | ((b ^ g) & 15);
+//   fast:  the 16 codes of every group of 16 sub-quantisers "rotated" by the slot index (byte b of slot g holds
+//          sub-quantiser (b & ~15) | ((b ^ g) & 15)) and stored chunk-blocked: inside a 32-slot chunk the 16-byte
+//          piece c of slot s sits at chunk * 32 m + c * 512 + s * 16;
 //   else:  plain AoS rows.  Lists start at multiples of `align` slots either way.
 struct ScanLayout {
     bool fast;
