@@ -40,6 +40,9 @@ PRESETS = {
     # one eighth of c5 (what one GPU holds at N = 8), for kernel work on one GPU
     "c5s": dict(n=12_500_000, d=96, nlist=8192, nprobe=8, m=48, nq=10_000, k=10, shape="deep", clusters=12_500,
                 label="one-eighth shard of configs[4]: IVF-PQ 12.5M x 96, nlist=8192, nprobe=8, M=48, batch 10k, k=10"),
+    # BASELINE.json configs[3]: inner-product, embedding-shaped; nprobe / batch are not specified there (32 / 10k assumed)
+    "c4": dict(n=10_000_000, d=768, nlist=16384, nprobe=32, m=64, nq=10_000, k=10, shape="deep", clusters=16384, metric="dotProduct",
+               label="IVF-PQ inner-product 10M x 768 embedding-shaped, nlist=16384, nprobe=32 (assumed), M=64, batch 10k queries, k=10 (BASELINE configs[3])"),
     "c3": dict(n=1_000_000, d=128, nlist=4096, nprobe=32, m=16, nq=10_000, k=10, shape="sift", clusters=4096,
                label="IVF-PQ 1M x 128 SIFT-shaped, nlist=4096, nprobe=32, M=16, batch 10k queries, k=10 (BASELINE configs[2])"),
     "tiny": dict(n=200_000, d=96, nlist=512, nprobe=8, m=48, nq=1000, k=10, shape="deep", clusters=1000,
@@ -162,7 +165,7 @@ def build_index(cfg, synth, rank, world, bcast=None):
     from vectorindex_b200.index import IVFPQIndex, ShardedIVFPQIndex
 
     n, d, nlist, m = cfg["n"], cfg["d"], cfg["nlist"], cfg["m"]
-    idx = IVFPQIndex(d, "euclidean", nlist=nlist, nprobe=cfg["nprobe"], m=m)
+    idx = IVFPQIndex(d, cfg.get("metric", "euclidean"), nlist=nlist, nprobe=cfg["nprobe"], m=m)
     t0 = time.time()
     ntrain = min(n, max(32 * nlist, 65536))
     if rank == 0:
@@ -201,7 +204,7 @@ def build_index(cfg, synth, rank, world, bcast=None):
             b, c = chunks[ci]
             x = synth.rows(b, c)
             ids = torch.arange(b, b + c, dtype=torch.int64, device=synth.dev)
-            dd, ii = vk.flat_search_f32(qgt, x, k, 0)                # exact ground truth, chunk by chunk
+            dd, ii = vk.flat_search_f32(qgt, x, k, 1 if cfg.get("metric") == "dotProduct" else 0)   # exact ground truth
             alld = torch.cat([gt_d, dd], 1)
             alli = torch.cat([gt_i, ii + b], 1)
             o = torch.argsort(alld, dim=1, stable=True)[:, :k]
@@ -233,7 +236,7 @@ def cpu_search_arm(cfg, idx, q_host, budget_s=12.0, gpu_ids=None):
     cb, norms = idx.get_codebooks()
     off, codes, lids, _ = idx.export_lists()
     cores = os.cpu_count() or 1
-    args = (coarse, cb, norms, off, codes, lids, cfg["m"], 256, cfg["nprobe"], cfg["k"], 0)
+    args = (coarse, cb, norms, off, codes, lids, cfg["m"], 256, cfg["nprobe"], cfg["k"], 1 if cfg.get("metric") == "dotProduct" else 0)
     probe = min(q_host.shape[0], 2 * cores)
     t0 = time.perf_counter()
     oracle.ivfpq_search(q_host[:probe], *args)
@@ -305,7 +308,7 @@ def main():
     q_host = q_pin.numpy()
 
     base_cfg = {"workload": cfg["label"], "n": cfg["n"], "d": d, "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
-                "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": "euclidean",
+                "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": cfg.get("metric", "euclidean"),
                 "partition": f"inverted lists in contiguous blocks over {eff_world} rank(s) (coarse scoring sharded the same way); "
                              "queries replicated; probe lists and top-k merged by all-gather + mergeTopK",
                 "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps",
@@ -425,6 +428,9 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel from the committed `ncu --set full`
+    # captures (profiles/): known only for the configurations that were captured
+    traffic = {("c5", 1): 86.459323e9 + 6.125568e6, ("c5s", 1): 5.486273e9 + 5.3e6}.get((args.workload, world))
     per_launch_bytes = scan_bytes / K                                  # rank 0's scan kernel, one launch per step
     per_launch_ms = scan_ms / K
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
@@ -439,7 +445,8 @@ def main():
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches,
         "roofline": {"kernel": "ivfpq_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/r01_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch)" if traffic else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                      "job_code_bytes_per_step": scan_bytes_all / K},

@@ -30,7 +30,11 @@ except StopIteration:
     sys.exit(0)
 hdr = rows[hi]
 ia, isrc, isamp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hi + 1:]:                      # first kernel of the report only
+    if len(r) != len(hdr) or not r[ia].isdigit():
+        break
+    data.append(r)
 tot = sum(int(r[ia]) for r in data) or 1
 tots = sum(int(r[isamp]) for r in data) or 1
 print(f"-- source page: {tot} warp instructions, {tots} samples; top {top} by samples")

@@ -62,7 +62,8 @@ struct Args {
     int tiles_per_split, nsplit, mtiles;
     int mode, metric;
     const float* bnorm;    // [nB] ||c||^2 (L2) or nullptr
-    int gcols, ngroups;    // MODE_MIN: columns per group (32, 64 or a multiple of 128), groups per row
+    int gcols, ngroups;    // MODE_MIN: columns per group (32, 64 or 128 * 2^t), groups per row
+    int gshift;            // log2(gcols) when gcols < 128, else log2(gcols / 128); set by launch()
     float* gmin;           // MODE_MIN: [nA x ngroups]
     const float* thr;      // MODE_EMIT: [nA]
     int* cand_cnt;         // MODE_EMIT: [nA]
@@ -161,6 +162,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+template <int MODE, int METRIC>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -249,7 +251,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
             const int64_t row = (int64_t)mt * kM + quarter * 32 + lane;
             const bool row_ok = row < a.nA;
-            const float thr = (a.mode == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
+            const float thr = (MODE == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
             float gmin = INFINITY;
             for (int nt = nt0; nt < nt1 && ok; ++nt) {
                 // stage this warp's 64 column norms (private copy per warp: no CTA-level barrier needed)
@@ -273,23 +275,26 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     float sc[32];
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const float4 nb = (a.metric == VIX_METRIC_L2) ? bn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 nb = (METRIC == VIX_METRIC_L2) ? bn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
                         const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int i = 4 * i4 + u;
-                            float s = (a.metric == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], nbv[u]) : -v[i];
-                            if (!full_tile && colbase + ck * 32 + i >= a.nB) s = INFINITY;
-                            sc[i] = s;
+                            sc[i] = (METRIC == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], nbv[u]) : -v[i];
                         }
                     }
-                    if (a.mode == MODE_WRITE) {
+                    if (!full_tile) {                              // last column tile only: mask the columns beyond nB
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (colbase + ck * 32 + i >= a.nB) sc[i] = INFINITY;
+                    }
+                    if (MODE == MODE_WRITE) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int col = colbase + ck * 32 + i;
                             if (row_ok && col < a.nB) a.out[row * a.nB + col] = sc[i];
                         }
-                    } else if (a.mode == MODE_MIN) {
+                    } else if (MODE == MODE_MIN) {
                         // tree minimum of the 32 columns
 #pragma unroll
                         for (int w2 = 16; w2 > 0; w2 >>= 1)
@@ -301,14 +306,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         // column halves of a tile belong to different groups: any disjoint partition is valid)
                         bool flush;
                         int g;
-                        if (a.gcols < kN) {
+                        if (a.gcols < kN) {                       // gcols and tiles-per-group are powers of two
                             const int colend = colbase + ck * 32 + 32;
-                            flush = (colend % a.gcols) == 0;
-                            g = (colend - 1) / a.gcols;
+                            flush = (colend & (a.gcols - 1)) == 0;
+                            g = (colend - 1) >> a.gshift;
                         } else {
-                            const int tpg = a.gcols / kN;
-                            flush = ck == 1 && (((nt + 1) % tpg) == 0 || nt == a.ntiles - 1);
-                            g = (nt / tpg) * 2 + half;
+                            flush = ck == 1 && (((nt + 1) & ((1 << a.gshift) - 1)) == 0 || nt == a.ntiles - 1);
+                            g = (nt >> a.gshift) * 2 + half;
                         }
                         if (flush) {
                             if (row_ok && g < a.ngroups) a.gmin[row * a.ngroups + g] = gmin;
@@ -402,11 +406,26 @@ static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Arg
     }
     a.tiles_per_split = tps;
     a.nsplit = (a.ntiles + tps - 1) / tps;
+    {
+        int v = a.gcols < kN ? a.gcols : a.gcols / kN, sh = 0;
+        while ((1 << sh) < v) ++sh;
+        VIX_REQUIRE((1 << sh) == v, VIX_ERR_INVALID_PARAM, "tensor-core shortlist: group width %d is not a power of two", a.gcols);
+        a.gshift = sh;
+    }
     const size_t smem = smem_bytes();
-    VIX_CUDA(cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = (int64_t)a.mtiles * a.nsplit;
     if (grid > num_sms()) grid = num_sms();
-    tc_score_kernel<<<(unsigned)grid, kThreads, smem, ctx().stream>>>(mapA, mapB, a);
+#define VIX_TC_LAUNCH(MODE_, METRIC_)                                                                                   \
+    do {                                                                                                               \
+        auto kern = tc_score_kernel<MODE_, METRIC_>;                                                                   \
+        VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        kern<<<(unsigned)grid, kThreads, smem, ctx().stream>>>(mapA, mapB, a);                                         \
+    } while (0)
+    const bool l2 = a.metric == VIX_METRIC_L2;
+    if (a.mode == MODE_MIN) { if (l2) VIX_TC_LAUNCH(MODE_MIN, VIX_METRIC_L2); else VIX_TC_LAUNCH(MODE_MIN, VIX_METRIC_IP); }
+    else if (a.mode == MODE_EMIT) { if (l2) VIX_TC_LAUNCH(MODE_EMIT, VIX_METRIC_L2); else VIX_TC_LAUNCH(MODE_EMIT, VIX_METRIC_IP); }
+    else { if (l2) VIX_TC_LAUNCH(MODE_WRITE, VIX_METRIC_L2); else VIX_TC_LAUNCH(MODE_WRITE, VIX_METRIC_IP); }
+#undef VIX_TC_LAUNCH
     VIX_LAUNCH_CHECK();
     return VIX_OK;
 }
