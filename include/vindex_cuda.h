@@ -96,6 +96,14 @@ int vix_flat_search_f32(const float* queries, int64_t nq, const float* xb, int64
 int vix_select_topk_f32(const float* scores, const int32_t* ids, int64_t n, int k, int ordering,
                         float* out_scores, int32_t* out_ids, int* out_count);
 
+/* Kernel #40 rerank_exact_topk_batch (Operations/Rerank/ExactRerank.swift:698-814; spec step 7 of
+ * docs/kernel-specs/DONE_22_adc_scan.md:873-878), DenseArray backend: cand_ids [nq x C] are rows of xb [N x d];
+ * ids outside [0, N) are missing and skipped; scores are the raw kernel values (L2^2 without sqrt / dot);
+ * ordering .min for L2, .max for IP, ties -> smaller candidate id; padded with +-inf / id -1. */
+int vix_rerank_exact_topk_f32(const float* queries, int64_t nq, int d, int metric, const int64_t* cand_ids, int C, int K,
+                              const float* xb, int64_t N, const float* xb_sq_norms /* nullable */, float* top_scores,
+                              int64_t* top_ids);
+
 /* a5  mergeTopK (Operations/Selection/TopKMerge.swift:11-61): nlists best->worst lists stored as
  * rows of [nlists x list_stride] with lens[l] valid entries, for `batch` independent queries
  * (scores/ids are [batch x nlists x list_stride], lens [batch x nlists]); ties: smaller id, then

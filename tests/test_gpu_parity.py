@@ -254,6 +254,41 @@ def test_select_and_merge_topk(oracle, vk):
         assert np.array_equal(bits(gs[b, :ms.size]), bits(ms + np.float32(0)))   # keys canonicalise -0 to +0
 
 
+# ------------------------------------------------------------------------------------------------ exact re-rank (Kernel #40)
+@pytest.mark.parametrize("d,metric,norms", [(96, 0, False), (128, 0, True), (320, 0, False), (64, 1, False)])
+def test_rerank_exact_topk(oracle, vk, d, metric, norms):
+    """rerank_exact_topk with the DenseArray reader: reference kernel scores of the candidate rows (oracle restatement
+    of L2Sqr.run / InnerProduct.run), missing ids skipped, ties -> smaller id, padded with the sentinel."""
+    rng = np.random.default_rng(d + metric)
+    n, nq, c, k = 5000, 20, 200, 12
+    xb = np.round(rng.standard_normal((n, d)) * 2).astype(np.float32)          # integer-valued: ties
+    q = np.round(rng.standard_normal((nq, d)) * 2).astype(np.float32)
+    cand = rng.integers(0, n, (nq, c)).astype(np.int64)
+    cand[:, 5] = -1                                                            # missing
+    cand[:, 9] = n + 3                                                         # out of range -> missing
+    cand[3, 20:] = -1                                                          # fewer than k present
+    cand[3, 12:20] = -1
+    xn = (xb.astype(np.float64) ** 2).sum(1).astype(np.float32) if norms else None     # caller-supplied ||x||^2
+    gs, gi = vk.rerank_exact_topk(q, cand, xb, k, metric, xn)
+    for r in range(nq):
+        ids = np.array([v for v in cand[r] if 0 <= v < n], dtype=np.int64)
+        rows = xb[ids]
+        if metric == 1:
+            sc = oracle.ip_block(q[r], rows)
+        elif norms:
+            qn = np.float32(0)
+            for v in q[r]:
+                qn = np.float32(qn + np.float32(v * v))                        # norm2: sequential sum (ExactRerank.swift:243)
+            sc = oracle.l2sqr_block(q[r], rows, xn[ids], float(qn))
+        else:
+            sc = oracle.l2sqr_block(q[r], rows)
+        order = np.lexsort((ids, -sc if metric == 1 else sc))[:k]
+        want_i = np.full(k, -1, np.int64); want_s = np.full(k, -np.inf if metric == 1 else np.inf, np.float32)
+        want_i[:order.size] = ids[order]; want_s[:order.size] = sc[order]
+        assert np.array_equal(gi[r], want_i), r
+        assert np.array_equal(bits(gs[r]), bits(want_s)), r
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core shortlist
 @pytest.mark.parametrize("nq,kc,d,metric", [(300, 2048, 96, 0), (257, 1500, 128, 1), (130, 4096, 100, 0), (64, 1024, 768, 1)])
 def test_tensor_core_scores_within_tf32_bound(vk, nq, kc, d, metric):

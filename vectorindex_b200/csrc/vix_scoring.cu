@@ -464,6 +464,60 @@ int ivf_assign_metric_device(const float* x, int64_t n, int d, const float* c, i
     return launch_pair<SpecSeqDot, EPI_ARGMIN>(p, 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kernel #40 exact re-rank (Operations/Rerank/ExactRerank.swift:698-814), DenseArray backend: one CTA per
+// query scores its C candidate rows with the reference kernel (L2Sqr.run: direct for d < 256 without norms,
+// fused dot form otherwise; InnerProduct.run), skips missing ids (skipMissing), selects the K best by
+// (score per the metric's ordering, then smaller candidate id) and pads with the sentinel / id -1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float* __restrict__ Q, int d, int metric, const int64_t* __restrict__ cand, int C, int K,
+              const float* __restrict__ xb, int64_t N, const float* __restrict__ xnorm, int dotfused, int P,
+              float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) unsigned char smem_rr[];
+    u64* keys = reinterpret_cast<u64*>(smem_rr);
+    float* sq = reinterpret_cast<float*>(keys + P);
+    __shared__ float s_qn;
+    const int64_t row = blockIdx.x;
+    const int order_max = (metric == VIX_METRIC_IP);
+    for (int e = threadIdx.x; e < d; e += blockDim.x) sq[e] = Q[row * d + e];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = kEmptyKey;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // ||q||^2: with caller-supplied base norms the re-rank passes its own sequential sum (ExactRerank.swift:243, 276);
+        // otherwise L2Sqr.run computes Norms.l2NormSquared itself (L2SqrKernel.swift:95-106)
+        float qn = 0.0f;
+        if (!order_max && dotfused) {
+            if (xnorm) for (int e = 0; e < d; ++e) qn = fadd(qn, fmul(sq[e], sq[e]));
+            else qn = exact_norm_l2sq(sq, d);
+        }
+        s_qn = qn;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const int64_t id = cand[row * C + i];
+        if (id < 0 || id >= N) continue;                                  // missing row
+        const float* xr = xb + id * d;
+        float s;
+        if (order_max) s = exact_pair<SpecIp4>(sq, xr, d);
+        else if (dotfused) {
+            const float dot = exact_pair<SpecDot16>(sq, xr, d);
+            const float xn = xnorm ? xnorm[id] : exact_norm_l2sq(xr, d);
+            const float dist = fsub(fadd(s_qn, xn), fmul(2.0f, dot));
+            s = dist < 0.0f ? 0.0f : dist;
+        } else s = exact_pair<SpecDirect16L2>(sq, xr, d);
+        keys[i] = make_key(s, (uint32_t)id, order_max);
+    }
+    __syncthreads();
+    bitonic_sort_keys<false>(keys, P, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const u64 key = (i < P) ? keys[i] : kEmptyKey;
+        const size_t o = (size_t)row * K + i;
+        if (key == kEmptyKey) { out_scores[o] = order_max ? -INFINITY : INFINITY; out_ids[o] = -1; }
+        else { out_scores[o] = key_score(key, order_max); out_ids[o] = (int64_t)key_id(key); }
+    }
+}
+
 __global__ void narrow_ids_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int32_t)in[i];
@@ -660,6 +714,39 @@ int vix_accel_rank_candidates_f32(const float* queries, int64_t nq, const float*
     VIX_TRY(dd.commit());
     VIX_TRY(di.commit());
     return finish(true);
+}
+
+int vix_rerank_exact_topk_f32(const float* queries, int64_t nq, int d, int metric, const int64_t* cand_ids, int C, int K,
+                              const float* xb, int64_t N, const float* xb_sq_norms, float* top_scores, int64_t* top_ids) {
+    VIX_TRY(ensure_device());
+    if (nq <= 0 || K <= 0) return VIX_OK;
+    VIX_REQUIRE(queries && cand_ids && xb && top_scores && top_ids, VIX_ERR_NULL_PTR, "vix_rerank_exact_topk_f32: null pointer");
+    VIX_REQUIRE(d > 0 && N >= 0, VIX_ERR_INVALID_DIM, "vix_rerank_exact_topk_f32: bad shape");
+    VIX_REQUIRE(metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP, VIX_ERR_INVALID_PARAM, "vix_rerank_exact_topk_f32: metric");
+    VIX_REQUIRE(K <= C, VIX_ERR_INVALID_K, "vix_rerank_exact_topk_f32: K must be <= C (ExactRerank.swift:730)");
+    VIX_REQUIRE(C <= 16384, VIX_ERR_UNSUPPORTED, "vix_rerank_exact_topk_f32: at most 16384 candidates per query");
+    VIX_REQUIRE(N < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM, "vix_rerank_exact_topk_f32: N must be < 2^32 - 1");
+    In<float> dq, dx, dn;
+    In<int64_t> dc;
+    Out<float> ds;
+    Out<int64_t> di;
+    VIX_TRY(dq.stage(queries, (size_t)nq * d));
+    VIX_TRY(dc.stage(cand_ids, (size_t)nq * C));
+    VIX_TRY(dx.stage(xb, (size_t)N * d));
+    VIX_TRY(dn.stage(xb_sq_norms, xb_sq_norms ? (size_t)N : 0));
+    VIX_TRY(ds.stage(top_scores, (size_t)nq * K));
+    VIX_TRY(di.stage(top_ids, (size_t)nq * K));
+    const int P = next_pow2(C < 2 ? 2 : C);
+    const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+    VIX_REQUIRE(smem <= 200 * 1024, VIX_ERR_UNSUPPORTED, "vix_rerank_exact_topk_f32: C = %d, d = %d exceed shared memory", C, d);
+    VIX_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int dotfused = (xb_sq_norms != nullptr || d >= 256) ? 1 : 0;       // L2SqrKernel.swift:95-106
+    rerank_kernel<<<(unsigned)nq, 256, smem, ctx().stream>>>(dq.dev, d, metric, dc.dev, C, K, dx.dev, N, dn.dev, dotfused, P, ds.dev,
+                                                            di.dev);
+    VIX_LAUNCH_CHECK();
+    VIX_TRY(ds.commit());
+    VIX_TRY(di.commit());
+    return finish(ds.is_host() || di.is_host());
 }
 
 int vix_select_topk_f32(const float* scores, const int32_t* ids, int64_t n, int k, int ordering,

@@ -199,6 +199,23 @@ def mergeTopK(scores, ids, k, ordering=ORDER_MIN, lens=None):
     return os_, oi
 
 
+def rerank_exact_topk(queries, cand_ids, xb, k, metric=METRIC_L2, xb_sq_norms=None):
+    """rerank_exact_topk_batch with the DenseArray reader (Operations/Rerank/ExactRerank.swift:698-814):
+    cand_ids [nq x C] rows of xb; returns (raw scores [nq x k], ids [nq x k]) best first, padded with +-inf / -1."""
+    queries, xb = as_input(queries, np.float32), as_input(xb, np.float32)
+    cand = as_input(cand_ids, np.int64)
+    nq, d = _shape2(queries)
+    n, _ = _shape2(xb)
+    c = int(cand.shape[1])
+    sc = empty_like_input(queries, (nq, k), np.float32)
+    ids = empty_like_input(queries, (nq, k), np.int64)
+    nr = as_input(xb_sq_norms, np.float32)
+    check(lib().vix_rerank_exact_topk_f32(ptr(queries, np.float32), C.c_int64(nq), C.c_int(d), C.c_int(metric), ptr(cand, np.int64),
+                                          C.c_int(c), C.c_int(k), ptr(xb, np.float32), C.c_int64(n), ptr(nr), ptr(sc, np.float32),
+                                          ptr(ids, np.int64)))
+    return sc, ids
+
+
 # ------------------------------------------------------------------------------------------------ coarse quantiser
 def centroid_batch_score(queries, centroids, metric=METRIC_L2, centroid_norms=None):
     queries, centroids = as_input(queries, np.float32), as_input(centroids, np.float32)
