@@ -54,19 +54,31 @@ __device__ __forceinline__ float lds_imm(uint32_t addr) {
     return v;
 }
 
-// one group of 16 sub-quantisers: 16 look-ups of one lane, 4 running sums
+// two look-ups whose results land in a 64-bit register pair, added to a pair of running sums with ONE packed
+// add (add.rn.f32x2, sm_100): (lo, hi) += (T[a0], T[a1])
+template <int IMM>
+__device__ __forceinline__ void lookup2(uint32_t a0, uint32_t a1, unsigned long long& acc) {
+    asm volatile(
+        "{\n\t.reg .f32 lo, hi;\n\t.reg .b64 pr;\n\t"
+        "ld.shared.f32 lo, [%1+%3];\n\t"
+        "ld.shared.f32 hi, [%2+%3];\n\t"
+        "mov.b64 pr, {lo, hi};\n\t"
+        "add.rn.f32x2 %0, %0, pr;\n\t}"
+        : "+l"(acc)
+        : "r"(a0), "r"(a1), "n"(IMM));
+}
+
+// one group of 16 sub-quantisers: 16 look-ups of one lane, 4 running sums kept as two f32x2 pairs (s0, s1), (s2, s3)
 template <int T>
-__device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[8], float& s0, float& s1, float& s2,
-                                         float& s3) {
+__device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[8], unsigned long long& s01,
+                                         unsigned long long& s23) {
     constexpr int IMM = (T & 1) * 128 + (T >> 1) * 65536;
     const uint32_t x[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         // result bytes: [0] = 4 * slot (lane constant; two per register), [1] = code, [2..3] = table address >> 16
-        s0 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604));
-        s1 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7615));
-        s2 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624));
-        s3 += lds_imm<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7635));
+        lookup2<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604), __byte_perm(x[i], pre[2 * i + 0], 0x7615), s01);
+        lookup2<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624), __byte_perm(x[i], pre[2 * i + 1], 0x7635), s23);
     }
 }
 
@@ -458,11 +470,13 @@ ivfpq_scan_kernel(ScanArgs a) {
 #ifndef VIX_SCAN_NOPREFETCH
             VIX_ADVANCE()
 #endif
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            lookup16<0>(wc[0], pre, s0, s1, s2, s3);
-            if (G > 1) lookup16<1>(wc[G > 1 ? 1 : 0], pre, s0, s1, s2, s3);
-            if (G > 2) lookup16<2>(wc[G > 2 ? 2 : 0], pre, s0, s1, s2, s3);
-            if (G > 3) lookup16<3>(wc[G > 3 ? 3 : 0], pre, s0, s1, s2, s3);
+            unsigned long long s01 = 0ull, s23 = 0ull;     // (s0, s1), (s2, s3) as f32x2 pairs
+            lookup16<0>(wc[0], pre, s01, s23);
+            if (G > 1) lookup16<1>(wc[G > 1 ? 1 : 0], pre, s01, s23);
+            if (G > 2) lookup16<2>(wc[G > 2 ? 2 : 0], pre, s01, s23);
+            if (G > 3) lookup16<3>(wc[G > 3 ? 3 : 0], pre, s01, s23);
+            const float s0 = __uint_as_float((uint32_t)s01), s1 = __uint_as_float((uint32_t)(s01 >> 32));
+            const float s2 = __uint_as_float((uint32_t)s23), s3 = __uint_as_float((uint32_t)(s23 >> 32));
 #ifdef VIX_SCAN_NOPREFETCH
             VIX_ADVANCE()
 #endif
