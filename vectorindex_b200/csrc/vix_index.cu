@@ -249,6 +249,7 @@ static int build_lists(vix_index* h) {
     int64_t nslots = 0;
     VIX_CUDA(cudaMemcpyAsync(&nslots, h->list_off.ptr + kc, 8, cudaMemcpyDeviceToHost, s));
     VIX_CUDA(cudaStreamSynchronize(s));
+    VIX_REQUIRE(nslots < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "index shard limited to 2^31 - 1 list slots (rows + list padding)");
     h->nslots = nslots;
     VIX_TRY(h->slot_row.resize((size_t)nslots, false));
     VIX_TRY(h->slot_ids.resize((size_t)nslots, false));

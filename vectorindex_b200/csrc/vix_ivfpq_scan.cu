@@ -85,10 +85,12 @@ __device__ __forceinline__ void lookup16(const uint4& w, const uint32_t (&pre)[8
 // codes of slot g: chunk-blocked layout -- inside a 32-slot chunk the 16-byte piece c of every slot is stored
 // contiguously ([c][slot][16]), so each of the G 128-bit loads of a warp reads 512 consecutive bytes (16 full sectors)
 template <int G>
-__device__ __forceinline__ void load_codes(uint4 (&w)[G], const uint8_t* __restrict__ codes, int64_t g, bool valid) {
-    const uint4* src = reinterpret_cast<const uint4*>(codes + (g >> 5) * (int64_t)(512 * G)) + (g & 31);
+__device__ __forceinline__ void load_codes(uint4 (&w)[G], const uint8_t* __restrict__ codes, uint32_t g) {
+    // every slot of a chunk exists in memory (lists are padded to whole chunks; padding holds code 0), so the
+    // loads need no predicate
+    const uint4* src = reinterpret_cast<const uint4*>(codes + (size_t)(g >> 5) * (512u * G)) + (g & 31u);
 #pragma unroll
-    for (int c = 0; c < G; ++c) w[c] = valid ? __ldg(src + 32 * c) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < G; ++c) w[c] = __ldg(src + 32 * c);
 }
 
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
@@ -436,7 +438,7 @@ ivfpq_scan_kernel(ScanArgs a) {
         // the probe the warp is in is cached in registers: chunk range [pb, pe), first slot / 32, length, bias
         int pb = 0, pe = 0, pstart = 0, plen = 0;
         float pbias = 0.0f;
-        int64_t cg = 0;
+        uint32_t cg = 0;                                   // slot of this lane in the current chunk (< 2^31 slots)
         bool cvalid = false;
         float ctx_ = 0.0f, cbias = 0.0f;                   // t_x and bias of the current chunk (prefetched)
         auto locate = [&]() {                              // position of chunk `ch` (chunk indices only grow)
@@ -446,26 +448,26 @@ ivfpq_scan_kernel(ScanArgs a) {
             }
             const int within = (ch - pb) * 32 + lane;
             cvalid = within < plen;
-            cg = ((int64_t)pstart << 5) + within;
+            cg = ((uint32_t)pstart << 5) + (uint32_t)within;
             cbias = pbias;
         };
         if (ch < nchunks) {
             locate();
-            load_codes<G>(wA, a.slot_codes, cg, cvalid);
-            ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;
+            load_codes<G>(wA, a.slot_codes, cg);
+            ctx_ = __ldg(a.slot_tx + cg);                  // padding slots hold t_x = 0
         }
         // one chunk: prefetch this warp's next chunk into wn, look the current one (wc) up, select
         auto do_chunk = [&](uint4 (&wc)[G], uint4 (&wn)[G]) {
             const float tx = ctx_;
-            const int64_t g = cg;
+            const uint32_t g = cg;
             const bool valid = cvalid;
             const float bias = cbias;
 #define VIX_ADVANCE()                                                         \
             ch = grab(ch);                                                        \
             if (ch < nchunks) {                                                   \
                 locate();                                                         \
-                load_codes<G>(wn, a.slot_codes, cg, cvalid);                      \
-                ctx_ = cvalid ? __ldg(a.slot_tx + cg) : 0.0f;                     \
+                load_codes<G>(wn, a.slot_codes, cg);                              \
+                ctx_ = __ldg(a.slot_tx + cg);                                     \
             }
 #ifndef VIX_SCAN_NOPREFETCH
             VIX_ADVANCE()
