@@ -407,6 +407,19 @@ def main():
         e2e_ms = e2e_s * 1e3
         scan_bytes_all = float(scan_bytes)
 
+    # diagnostic (untimed): where a sharded step spends its time on this rank, and the per-rank scan times
+    phase_ms = None
+    if dist:
+        sh.phase_times = {}
+        for _ in range(3):
+            sh.batch_search(q_dev, k)
+        phase_ms = {kk: round(v / 3, 3) for kk, v in sh.phase_times.items()}
+        sh.phase_times = None
+        per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+        per_rank[rank] = scan_ms / K
+        dist.all_reduce(per_rank)
+        phase_ms["scan_ms_per_rank"] = [round(float(v), 3) for v in per_rank]
+
     # recall of the (merged) result against the exact ground truth
     if dist:
         _lib.check(L.vix_set_async(0))
@@ -439,7 +452,8 @@ def main():
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(base_cfg, recall_at_10=recall, recall_queries=GT_QUERIES,
-                       stage_ms_per_step={"probe_select": coarse_ms / K, "lut_adc_scan_topk": scan_ms / K}),
+                       stage_ms_per_step={"probe_select": coarse_ms / K, "lut_adc_scan_topk": scan_ms / K},
+                       sharded_phase_ms=phase_ms),
         "clocks": clk.summary(),
         "e2e": {"value": nq * K / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / K},

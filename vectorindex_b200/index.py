@@ -403,10 +403,21 @@ class ShardedIVFPQIndex:
         if self.world > 1 and was_numpy and self._nccl():
             queries = self._to_comm(np.ascontiguousarray(queries, dtype=np.float32))
         nprobe = nprobe if nprobe > 0 else self.nprobe
+        marks = [] if getattr(self, "phase_times", None) is not None and self._nccl() else None
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         probes = self.global_probes(queries, nprobe)
+        mark("probe_range+gather+merge")
         if not self._nccl() and _lib._is_torch(probes):
             probes = probes.numpy()
         d_loc, i_loc = self.local.search_with_probes(queries, k, probes)
+        mark("scan")
         if self.world == 1:
             return d_loc, i_loc
         d_all, i_all = self._all_gather(self._to_comm(d_loc)), self._all_gather(self._to_comm(i_loc))
@@ -414,6 +425,11 @@ class ShardedIVFPQIndex:
             md, mi = merge_shard_results(d_all, i_all, k)
         else:
             md, mi = merge_shard_results_host(d_all.numpy(), i_all.numpy(), k)
+        mark("gather+merge")
+        if marks:
+            torch.cuda.synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                self.phase_times[name] = self.phase_times.get(name, 0.0) + a.elapsed_time(b)
         if was_numpy and _lib._is_torch(md):
             md, mi = md.cpu().numpy(), mi.cpu().numpy()
         return md, mi
