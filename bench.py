@@ -288,6 +288,7 @@ def main():
     _lib.check(L.vix_set_device(local_rank))
     dist = None
     if world > 1 and args.impl == "ours":
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's banner / logs off stdout (ONE JSON line there)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
