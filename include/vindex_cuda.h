@@ -302,6 +302,9 @@ int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int 
                           int32_t* list_ids_out /* [nq x nprobe] */, float* list_scores_out /* nullable */);
 int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                  int nprobe, float* out_dist, int64_t* out_ids);
+/* same, with the stage timings / scan statistics of vix_index_search_ex (synchronises) */
+int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                    int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats /* nullable */);
 int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_out, uint8_t* codes_out /* [n x m] */);
 int vix_index_add_encoded(vix_index_t* h, const int32_t* assign, const uint8_t* codes, const int64_t* ids, int64_t n);
 

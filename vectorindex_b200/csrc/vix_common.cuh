@@ -135,6 +135,8 @@ struct Scratch {
 
 // synchronise when any output lives on the host or the context is synchronous
 int finish(bool any_host_output);
+int* pipeline_error_flag();    // mapped pinned host int, device-writable (nullptr if it cannot be allocated)
+int check_pipeline_error();    // VIX_ERR_CUDA once after a tensor-core pipeline timed out
 
 // ------------------------------------------------------------------------------------------------
 // Device helpers

@@ -70,7 +70,8 @@ struct Args {
     int32_t* cand_idx;     // MODE_EMIT: [nA x cap]
     int cap;
     float* out;            // MODE_WRITE: [nA x nB]
-    int* error;            // set to 1 when a barrier wait times out
+    int* error;            // device flag, set to 1 when a barrier wait times out (the other waits then give up too)
+    int* error_host;       // optional mapped host copy of the flag (raised once, never polled by the device)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -97,12 +98,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // bounded wait: ~2 s at 2 GHz, then raise the error flag and give up
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error, int* error_host) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(error) != 0) {
             atomicExch(error, 1);
+            if (error_host) { *reinterpret_cast<volatile int*>(error_host) = 1; __threadfence_system(); }
             return false;
         }
     }
@@ -199,7 +201,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
                 for (int nt = nt0; nt < nt1 && ok; ++nt) {
                     for (int kb = 0; kb < a.kblocks; ++kb) {
-                        if (!mbar_wait(empty + stage, phase ^ 1, a.error)) { ok = false; break; }
+                        if (!mbar_wait(empty + stage, phase ^ 1, a.error, a.error_host)) { ok = false; break; }
                         unsigned char* sA = ring + (size_t)stage * kStageBytes;
                         mbar_expect_tx(full + stage, kStageBytes);
                         tma_load_2d(sA, &mapA, full + stage, kb * kKB, mt * kM);
@@ -220,11 +222,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
                 (void)mt;
                 for (int nt = nt0; nt < nt1 && ok; ++nt) {
-                    if (!mbar_wait(tempty + acc, aphase ^ 1, a.error)) { ok = false; break; }
+                    if (!mbar_wait(tempty + acc, aphase ^ 1, a.error, a.error_host)) { ok = false; break; }
                     fence_after_sync();
                     const uint32_t tmem_d = tmem_base + (uint32_t)acc * kN;
                     for (int kb = 0; kb < a.kblocks; ++kb) {
-                        if (!mbar_wait(full + stage, phase, a.error)) { ok = false; break; }
+                        if (!mbar_wait(full + stage, phase, a.error, a.error_host)) { ok = false; break; }
                         fence_after_sync();
                         const uint32_t sA = smem_u32(ring + (size_t)stage * kStageBytes);
                         const uint64_t da = make_desc(sA), db = make_desc(sA + kM * kKB * 4);
@@ -262,7 +264,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     bn[t * 32 + lane] = (a.bnorm && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
                 }
                 __syncwarp();
-                if (!mbar_wait(tfull + acc, aphase, a.error)) { ok = false; break; }
+                if (!mbar_wait(tfull + acc, aphase, a.error, a.error_host)) { ok = false; break; }
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN + (uint32_t)half * 64;
                 const int colbase = nt * kN + half * 64;
@@ -472,39 +474,106 @@ __global__ void max_sqrt_kernel(const float* __restrict__ x, int64_t n, float* _
 }
 
 // ---------------------------------------------------------------------------------------------- exact rescoring
-// One CTA per row: exact CentroidBatchScore value of every candidate in the reference's operation order
+// One WARP per row: exact CentroidBatchScore value of every candidate in the reference's operation order
 // (sequential dot, then -2 s + ||c||^2 / -s; Kernels/CentroidBatchScore.swift:54-64), keys (score, index),
-// bitonic sort, best `k` out.  Rows whose candidate list overflowed are flagged for the exact fallback.
-__global__ void __launch_bounds__(256)
-rescore_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int d, int metric,
+// bitonic sort of the next power of two >= n, best `k` out.  The warp takes 32 candidates at a time: their rows
+// are read 32 floats at a time with coalesced 128-byte loads (all 32 in flight) into a padded shared tile, and
+// lane i then walks row i of the tile -- one sequential chain per candidate, the same operations in the same order
+// as a thread reading its row straight from global memory, at a thirtieth of the L1 traffic.  Nothing in the
+// kernel synchronises more than a warp.  Rows whose candidate list overflowed are flagged for the exact kernel below.
+constexpr int kRescoreWarps = 8;
+__global__ void __launch_bounds__(32 * kRescoreWarps)
+rescore_probe_kernel(const float* __restrict__ A, int64_t nA, const float* __restrict__ B, int d, int metric,
                      const float* __restrict__ bnorm, const int* __restrict__ cand_cnt,
-                     const int32_t* __restrict__ cand_idx, int cap, int P, int k, int32_t* __restrict__ out_idx,
+                     const int32_t* __restrict__ cand_idx, int cap, int Pmax, int k, int32_t* __restrict__ out_idx,
                      float* __restrict__ out_scores, int* __restrict__ overflow_rows, int* __restrict__ n_overflow) {
     extern __shared__ __align__(16) unsigned char smem_rs[];
-    u64* keys = reinterpret_cast<u64*>(smem_rs);
-    float* sq = reinterpret_cast<float*>(keys + P);
-    const int64_t row = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dpad = (d + 31) & ~31;
+    u64* keys = reinterpret_cast<u64*>(smem_rs) + (size_t)warp * Pmax;                       // [warps][Pmax]
+    float* sq = reinterpret_cast<float*>(reinterpret_cast<u64*>(smem_rs) + (size_t)kRescoreWarps * Pmax) + (size_t)warp * dpad;
+    float* tile = reinterpret_cast<float*>(reinterpret_cast<u64*>(smem_rs) + (size_t)kRescoreWarps * Pmax) +
+                  (size_t)kRescoreWarps * dpad + (size_t)warp * (32 * 33);                   // [warps][32][33]
+    const int64_t row = (int64_t)blockIdx.x * kRescoreWarps + warp;
+    if (row >= nA) return;
     const int n = cand_cnt[row];
     if (n > cap) {
-        if (threadIdx.x == 0) overflow_rows[atomicAdd(n_overflow, 1)] = (int)row;
+        if (lane == 0) overflow_rows[atomicAdd(n_overflow, 1)] = (int)row;
         return;
     }
-    for (int e = threadIdx.x; e < d; e += blockDim.x) sq[e] = A[row * d + e];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = kEmptyKey;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = cand_idx[row * cap + i];
-        const float dot = exact_pair<SpecSeqDot>(sq, B + (int64_t)c * d, d);
-        const float s = (metric == VIX_METRIC_L2) ? fadd(fmul(-2.0f, dot), bnorm[c]) : fmul(-1.0f, dot);
-        keys[i] = make_key(s, (uint32_t)c, 0);
+    const int P = next_pow2(n < 2 ? 2 : n);                            // <= Pmax
+    for (int e = lane; e < dpad; e += 32) sq[e] = e < d ? A[row * d + e] : 0.0f;
+    for (int i = n + lane; i < P; i += 32) keys[i] = kEmptyKey;
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int c = cand_idx[row * cap + (i < n ? i : base)];
+        float acc = 0.0f;
+        for (int e0 = 0; e0 < d; e0 += 32) {
+            const int w = min(32, d - e0);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {                             // candidate j of the batch: 128 coalesced bytes
+                const int cj = __shfl_sync(0xFFFFFFFFu, c, j);
+                v[j] = lane < w ? __ldg(B + (int64_t)cj * d + e0 + lane) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[j * 33 + lane] = v[j];
+            __syncwarp();
+            for (int t = 0; t < w; ++t) acc = fadd(acc, fmul(sq[e0 + t], tile[lane * 33 + t]));
+            __syncwarp();
+        }
+        if (i < n) {
+            const float s = (metric == VIX_METRIC_L2) ? fadd(fmul(-2.0f, acc), bnorm[c]) : fmul(-1.0f, acc);
+            keys[i] = make_key(s, (uint32_t)c, 0);
+        }
     }
-    __syncthreads();
-    bitonic_sort_keys<false>(keys, P, threadIdx.x, blockDim.x);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const u64 key = keys[i];
+    __syncwarp();
+    bitonic_sort_keys<true>(keys, P, lane, 32);
+    for (int i = lane; i < k; i += 32) {
+        const u64 key = i < P ? keys[i] : kEmptyKey;
         const size_t o = (size_t)row * k + i;
         if (key == kEmptyKey) { out_idx[o] = -1; if (out_scores) out_scores[o] = __int_as_float(0x7fc00000); }
         else { out_idx[o] = (int32_t)key_id(key); if (out_scores) out_scores[o] = key_score(key, 0); }
+    }
+}
+
+// The rows whose shortlist overflowed (normally none), without a host round trip: a fixed grid walks the list the
+// kernel above left on the device; one CTA per row scores EVERY column in the same operation order and selects by
+// (score, index) with a CTA-wide queue.
+__global__ void __launch_bounds__(256)
+probe_overflow_rows_kernel(const float* __restrict__ A, const float* __restrict__ B, int nB, int d, int metric,
+                           const float* __restrict__ bnorm, const int* __restrict__ overflow_rows,
+                           const int* __restrict__ n_overflow, int P, int k, int32_t* __restrict__ out_idx,
+                           float* __restrict__ out_scores) {
+    extern __shared__ __align__(16) unsigned char smem_po[];
+    u64* keys = reinterpret_cast<u64*>(smem_po);
+    float* sq = reinterpret_cast<float*>(keys + P);
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    const int nrows = *n_overflow;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int64_t row = overflow_rows[r];
+        __syncthreads();
+        for (int e = threadIdx.x; e < d; e += blockDim.x) sq[e] = A[row * d + e];
+        BlockQueue q{keys, &s_cnt, &s_thr, k, P};
+        q.init();
+        for (int base = 0; base < nB; base += blockDim.x) {
+            q.flush_if_needed(blockDim.x);
+            const int c = base + threadIdx.x;
+            if (c < nB) {
+                const float dot = exact_pair<SpecSeqDot>(sq, B + (int64_t)c * d, d);
+                const float s = (metric == VIX_METRIC_L2) ? fadd(fmul(-2.0f, dot), bnorm[c]) : fmul(-1.0f, dot);
+                q.push(make_key(s, (uint32_t)c, 0));
+            }
+        }
+        q.flush();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const u64 key = keys[i];
+            const size_t o = (size_t)row * k + i;
+            if (key == kEmptyKey) { out_idx[o] = -1; if (out_scores) out_scores[o] = __int_as_float(0x7fc00000); }
+            else { out_idx[o] = (int32_t)key_id(key); if (out_scores) out_scores[o] = key_score(key, 0); }
+        }
     }
 }
 
@@ -677,9 +746,14 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     const int ngroups = tc::num_groups(kc, gcols);
     const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && tc::supported(nq, kc, d, q, c) && kc >= 1024 && nq >= 16 &&
                         ngroups >= 2 * keff && keff <= 256 && d <= 4096 && (metric == VIX_METRIC_IP || cnorm != nullptr);
-    if (!use_tc) return probe_select_device(q, nq, c, kc, d, metric, nprobe, cnorm, nullptr, out_idx, out_scores);
-    cudaStream_t s = ctx().stream;
     const int cap = keff * 4 + 128;
+    const size_t rescore_smem = (size_t)tc::kRescoreWarps * ((size_t)next_pow2(cap) * 8 + (size_t)((d + 31) & ~31) * 4 + 32 * 33 * 4);
+    if (!use_tc || rescore_smem > 227 * 1024)
+        return probe_select_device(q, nq, c, kc, d, metric, nprobe, cnorm, nullptr, out_idx, out_scores);
+    cudaStream_t s = ctx().stream;
+    VIX_TRY(check_pipeline_error());                   // a pipeline that gave up in an earlier asynchronous call
+    int* pipe_flag = pipeline_error_flag();
+    VIX_REQUIRE(pipe_flag != nullptr, VIX_ERR_OOM, "cannot allocate the mapped pipeline-error flag");
     Scratch<float> gmin, thr, qn, cn_tmp, cmax;
     Scratch<int> cand_cnt, flags, ovf_rows;
     Scratch<int32_t> cand_idx;
@@ -689,7 +763,7 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     VIX_TRY(cmax.alloc(1));
     VIX_TRY(cand_cnt.alloc((size_t)nq));
     VIX_TRY(cand_idx.alloc((size_t)nq * cap));
-    VIX_TRY(flags.alloc(2));                           // [0] pipeline error, [1] number of overflow rows
+    VIX_TRY(flags.alloc(2));                           // [0] pipeline gave up, [1] number of overflow rows
     VIX_TRY(ovf_rows.alloc((size_t)nq));
     VIX_CUDA(cudaMemsetAsync(flags.ptr, 0, 8, s));
     VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
@@ -700,7 +774,7 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     VIX_LAUNCH_CHECK();
 
     tc::Args a{};
-    a.metric = metric; a.bnorm = (metric == VIX_METRIC_L2) ? cn : nullptr; a.error = flags.ptr;
+    a.metric = metric; a.bnorm = (metric == VIX_METRIC_L2) ? cn : nullptr; a.error = flags.ptr; a.error_host = pipe_flag;
     a.mode = tc::MODE_MIN; a.gcols = gcols; a.ngroups = ngroups; a.gmin = gmin.ptr;
     VIX_TRY(tc::launch(q, nq, c, kc, d, a));
     // |S~ - S|: dot error (2 * 2^-10 truncation + d * 2^-22 accumulation) * ||q|| ||c||, doubled for the L2 score
@@ -714,28 +788,19 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     VIX_TRY(tc::launch(q, nq, c, kc, d, a));
     {
         const int P = next_pow2(cap);
-        const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+        const size_t smem = rescore_smem;
         VIX_CUDA(cudaFuncSetAttribute(tc::rescore_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::rescore_probe_kernel<<<(unsigned)nq, 256, smem, s>>>(q, c, d, metric, cn, cand_cnt.ptr, cand_idx.ptr, cap, P, nprobe,
-                                                               out_idx, out_scores, ovf_rows.ptr, flags.ptr + 1);
+        tc::rescore_probe_kernel<<<(unsigned)((nq + tc::kRescoreWarps - 1) / tc::kRescoreWarps), 32 * tc::kRescoreWarps, smem, s>>>(
+            q, nq, c, d, metric, cn, cand_cnt.ptr, cand_idx.ptr, cap, P, nprobe, out_idx, out_scores, ovf_rows.ptr, flags.ptr + 1);
         VIX_LAUNCH_CHECK();
     }
-    int hflags[2] = {0, 0};
-    VIX_CUDA(cudaMemcpyAsync(hflags, flags.ptr, 8, cudaMemcpyDeviceToHost, s));
-    VIX_CUDA(cudaStreamSynchronize(s));
-    VIX_REQUIRE(hflags[0] == 0, VIX_ERR_CUDA, "tensor-core pipeline timed out");
-    if (hflags[1] > 0) {
-        // rows whose shortlist overflowed: exact kernel on the gathered rows
-        const int n = hflags[1];
-        Scratch<float> sub, sub_sc;
-        Scratch<int32_t> sub_idx;
-        VIX_TRY(sub.alloc((size_t)n * d));
-        VIX_TRY(sub_idx.alloc((size_t)n * nprobe));
-        VIX_TRY(sub_sc.alloc((size_t)n * nprobe));
-        tc::gather_rows_f32_kernel<<<n, 128, 0, s>>>(q, d, ovf_rows.ptr, n, sub.ptr);
-        VIX_LAUNCH_CHECK();
-        VIX_TRY(probe_select_device(sub.ptr, n, c, kc, d, metric, nprobe, cn, nullptr, sub_idx.ptr, sub_sc.ptr));
-        tc::scatter_probe_rows_kernel<<<n, 128, 0, s>>>(sub_idx.ptr, sub_sc.ptr, nprobe, ovf_rows.ptr, n, out_idx, out_scores);
+    {
+        // rows whose shortlist overflowed, if any (no host round trip: the call stays asynchronous)
+        const int P = next_pow2(nprobe + 256);
+        const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+        VIX_CUDA(cudaFuncSetAttribute(tc::probe_overflow_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::probe_overflow_rows_kernel<<<(unsigned)(2 * num_sms()), 256, smem, s>>>(q, c, kc, d, metric, cn, ovf_rows.ptr,
+                                                                                  flags.ptr + 1, P, nprobe, out_idx, out_scores);
         VIX_LAUNCH_CHECK();
     }
     return VIX_OK;

@@ -304,20 +304,34 @@ static int build_lists(vix_index* h) {
 // ------------------------------------------------------------------------------------------------
 // query order for the scan: work item -> query, sorted by first probed list (L2 locality)
 // ------------------------------------------------------------------------------------------------
+// key of a query = the first probed list that holds vectors HERE (on a shard most probes belong to other ranks);
+// one warp per query
 __global__ void first_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe,
-                                   int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq) { const int l = probes[i * nprobe]; keys[i] = l < 0 ? 0x7FFFFFFF : l; vals[i] = (int32_t)i; }
+                                   const int32_t* __restrict__ list_len, int32_t* __restrict__ keys,
+                                   int32_t* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    int key = 0x7FFFFFFF;
+    for (int base = 0; base < nprobe; base += 32) {
+        const int p = base + lane;
+        const int l = p < nprobe ? __ldg(probes + i * nprobe + p) : -1;
+        const bool here = l >= 0 && __ldg(list_len + l) > 0;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
+        if (ball) { key = __shfl_sync(0xFFFFFFFFu, l, __ffs(ball) - 1); break; }
+    }
+    if (lane == 0) { keys[i] = key; vals[i] = (int32_t)i; }
 }
 
-static int query_order(const int32_t* probes, int64_t nq, int nprobe, int kc, Scratch<int32_t>& order) {
+static int query_order(const int32_t* probes, int64_t nq, int nprobe, const int32_t* list_len, int kc,
+                       Scratch<int32_t>& order) {
     cudaStream_t s = ctx().stream;
     Scratch<int32_t> keys, keys_out, vals;
     VIX_TRY(keys.alloc((size_t)nq));
     VIX_TRY(keys_out.alloc((size_t)nq));
     VIX_TRY(vals.alloc((size_t)nq));
     VIX_TRY(order.alloc((size_t)nq));
-    first_probe_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(probes, nq, nprobe, keys.ptr, vals.ptr);
+    first_probe_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(probes, nq, nprobe, list_len, keys.ptr, vals.ptr);
     VIX_LAUNCH_CHECK();
     size_t tmp_bytes = 0;
     VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_out.ptr, vals.ptr, order.ptr, (int)nq, 0, 31, s));
@@ -533,7 +547,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
         if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
         DevBuf<unsigned long long>& scanned = h->scanned;
-        if (stats) { VIX_TRY(scanned.resize(8, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 64, s)); }
+        if (stats) { VIX_TRY(scanned.resize(16, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 128, s)); }
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
             ScanArgs a{};
             a.queries = dq.dev; a.nq = nq; a.d = d; a.m = h->p.m; a.ks = h->p.ks; a.dsub = d / h->p.m;
@@ -548,7 +562,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.work_counter = h->work_counter.ptr;
             Scratch<int32_t> order;
             if (scan_layout(a.m).fast && nq > 2 * num_sms()) {
-                VIX_TRY(query_order(pp, nq, nprobe, h->kc, order));
+                VIX_TRY(query_order(pp, nq, nprobe, h->list_len.ptr, h->kc, order));
                 a.order = order.ptr;
             }
             VIX_TRY(launch_ivfpq_scan(a));
@@ -566,9 +580,12 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         if (traced) VIX_CUDA(cudaEventRecord(tev[2], s));
         if (stats) {
             VIX_CUDA(cudaEventRecord(ev[2], s));
-            unsigned long long sc4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            VIX_CUDA(cudaMemcpyAsync(sc4, scanned.ptr, 64, cudaMemcpyDeviceToHost, s));
+            unsigned long long sc4[16] = {0};
+            VIX_CUDA(cudaMemcpyAsync(sc4, scanned.ptr, 128, cudaMemcpyDeviceToHost, s));
             VIX_CUDA(cudaStreamSynchronize(s));
+#ifdef VIX_SCAN_DIAG
+            fprintf(stderr, "[vix diag] chunks %llu, queue flushes %llu, chunks with a passing entry %llu\n", sc4[9], sc4[10], sc4[11]);
+#endif
             const unsigned long long sc = sc4[0];
             stats->codes_scanned = (int64_t)sc;
             stats->cycles_prologue = (int64_t)sc4[1]; stats->cycles_scan = (int64_t)sc4[2]; stats->cycles_tail = (int64_t)sc4[3];
@@ -860,6 +877,16 @@ int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t n
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_search_with_probes: IVF index not trained");
     return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr, probes);
+}
+
+int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                    int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && probes, VIX_ERR_NULL_PTR, "vix_index_search_with_probes_ex: null pointer");
+    VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "vix_index_search_with_probes_ex: nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_search_with_probes_ex: IVF index not trained");
+    return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, stats, probes);
 }
 
 int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int nprobe, int list_begin, int list_count,

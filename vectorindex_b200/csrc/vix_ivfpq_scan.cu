@@ -43,6 +43,12 @@ namespace vix {
 #ifndef VIX_SCAN_FN
 #define VIX_SCAN_FN __noinline__
 #endif
+#ifndef VIX_SCAN_L2PF
+#define VIX_SCAN_L2PF 0      // L2 prefetch of chunk runs: 0 none, 1 first run of a query only, 2 every run (measured: both slower)
+#endif
+#ifndef VIX_SCAN_GUIDED
+#define VIX_SCAN_GUIDED 1    // runs shrink towards the end of a query
+#endif
 constexpr int kFastThreads = VIX_SCAN_THREADS;   // one CTA per SM
 constexpr int kScanWarps = 8;              // generic kernel
 constexpr int kScanThreads = kScanWarps * 32;
@@ -97,27 +103,8 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
-// per-probe term of the decomposition: ||q - c_l||^2 (L2) or <q, c_l> (IP); one warp per (query, probe)
-__global__ void __launch_bounds__(256)
-probe_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
-                  int64_t npairs, int nprobe, int d, int order_max, float* __restrict__ bias) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= npairs) return;
-    const int l = probes[w];
-    float part = 0.0f;
-    if (l >= 0) {
-        const float* q = queries + (w / nprobe) * (int64_t)d;
-        const float* c = coarse + (int64_t)l * d;
-        if (order_max) for (int e = lane; e < d; e += 32) part = fmaf(__ldg(q + e), __ldg(c + e), part);
-        else for (int e = lane; e < d; e += 32) { const float df = __ldg(q + e) - __ldg(c + e); part = fmaf(df, df, part); }
-    }
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-    if (lane == 0) bias[w] = part;
-}
-
 // k-th smallest (0-based rank kth) of one 32-bit key per lane: bitonic network over the warp
-__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
+__device__ VIX_SCAN_FN uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -192,49 +179,76 @@ __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int
     }
 }
 
-// warp 1: probe table, bias and exclusive prefix of chunk counts, all inside one warp; loads batched
-__device__ VIX_SCAN_FN void build_probe_table(const int32_t* __restrict__ qprobes, const float* __restrict__ qbias,
-                                               int nprobe, const int64_t* __restrict__ list_off,
-                                               const int32_t* __restrict__ list_len, int* s_start, int* s_len,
-                                               int* s_pref, float* s_bias) {
+// one warp, while the other warps scan the previous query: everything a query needs besides its look-up table.
+//   * the query itself, copied to shared memory (the table build reads it from there);
+//   * the probe table -- first slot / 32, length and exclusive prefix of the chunk counts of the probed lists that are
+//     NOT EMPTY here (a shard holds only its block of lists; the other probes are dropped, so the scan never walks
+//     over them);
+//   * the per-probe term of the decomposition, ||q - c_l||^2 (L2) or <q, c_l> (IP), for those lists.
+__device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d, const float* __restrict__ coarse,
+                                               int order_max, const int32_t* __restrict__ qprobes, int nprobe,
+                                               const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
+                                               int* s_start, int* s_len, int* s_pref, float* s_bias, int* s_np,
+                                               float* s_q) {
     const int lane = threadIdx.x & 31;
     int lv[8], lenv[8];
     int64_t offv[8];
-    float bv[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int p = 32 * it + lane;
         lv[it] = (p < nprobe) ? __ldg(qprobes + p) : -1;
-        bv[it] = (p < nprobe) ? __ldg(qbias + p) : 0.0f;
     }
+    for (int e = lane; e < d; e += 32) s_q[e] = __ldg(q + e);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         offv[it] = 0; lenv[it] = 0;
         if (lv[it] >= 0) { offv[it] = __ldg(list_off + lv[it]); lenv[it] = __ldg(list_len + lv[it]); }
     }
-    int carry = 0;
+    int carry = 0, np = 0;
+    int* s_list = reinterpret_cast<int*>(s_bias);          // list ids first, overwritten by the bias below
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         if (32 * it < nprobe) {
-            const int p = 32 * it + lane;
             const int nch = (lenv[it] + 31) >> 5;
             int inc = nch;
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-            if (p < nprobe) {
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, nch > 0);
+            if (nch > 0) {
+                const int p = np + __popc(ball & ((1u << lane) - 1u));
                 s_start[p] = (int)(offv[it] >> 5); s_len[p] = lenv[it]; s_pref[p] = carry + inc - nch;
-                s_bias[p] = bv[it];
+                s_list[p] = lv[it];
             }
+            np += __popc(ball);
             carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
     }
-    if (lane == 0) s_pref[nprobe] = carry;
+    if (lane == 0) { s_pref[np] = carry; *s_np = np; }
+    __syncwarp();
+    // bias: lane-strided partial sums, xor-tree across the warp; four lists in flight
+    for (int p0 = 0; p0 < np; p0 += 4) {
+        float part[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            part[u] = 0.0f;
+            if (p0 + u < np) {
+                const float* c = coarse + (int64_t)s_list[p0 + u] * d;
+                if (order_max) for (int e = lane; e < d; e += 32) part[u] = fmaf(s_q[e], __ldg(c + e), part[u]);
+                else for (int e = lane; e < d; e += 32) { const float df = s_q[e] - __ldg(c + e); part[u] = fmaf(df, df, part[u]); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            for (int o = 16; o > 0; o >>= 1) part[u] += __shfl_xor_sync(0xFFFFFFFFu, part[u], o);
+        if (lane < 4 && p0 + lane < np) s_bias[p0 + lane] = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+    }
 }
 
-// warps 2..: T[c][slot(j)] = scale * <q_j, cb_j[c]>.  Thread t of the `nthr` builders owns ONE sub-quantiser
+// every warp: T[c][slot(j)] = scale * <q_j, cb_j[c]>.  Thread t of the `nthr` builders owns ONE sub-quantiser
 // j = t % M (its query slice stays in registers) and walks the codes c = t / M, t / M + nthr / M, ...;
-// codebooks_t is [256][M][dsub], so the M threads of a code read consecutive memory.  Four codes per thread
-// are in flight.  The two replicas of an entry are written in opposite order by the two half-warps, so a
-// warp-wide store touches 32 different banks.
+// codebooks_t is [256][M][dsub], so the M threads of a code read consecutive memory.  The build is bound by the
+// latency of those (L2-resident) reads, so as many codes as the registers hold are in flight per thread: all of
+// a thread's codes at dsub = 2 (one round trip), eight otherwise.  The two replicas of an entry are written in
+// opposite order by the two half-warps, so a warp-wide store touches 32 different banks.
 template <int M>
 __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __restrict__ q,
                                       const float* __restrict__ codebooks_t, int dsub, float lut_scale, int t, int nthr) {
@@ -247,22 +261,31 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
     float* colA = col + 16 * rep_first;
     float* colB = col + 16 * (rep_first ^ 1);
     constexpr int U = 8;
-    if (dsub <= 16) {
+    if (dsub == 2) {
+        // codes per thread with a full CTA of builders: ceil(256 / (512 / M))
+        constexpr int U2 = (256 + (kFastThreads / M) - 1) / (kFastThreads / M);
+        const float q0 = q[j * 2] * lut_scale, q1 = q[j * 2 + 1] * lut_scale;
+        for (int c = c0; c < 256; c += U2 * ngroups) {
+            float2 v[U2];
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int cu = min(c + u * ngroups, 255);
+                v[u] = __ldg(reinterpret_cast<const float2*>(codebooks_t + ((size_t)cu * M + j) * 2));
+            }
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int cu = c + u * ngroups;
+                const float dot = fmaf(q1, v[u].y, q0 * v[u].x);
+                if (cu < 256) { colA[cu * 64] = dot; colB[cu * 64] = dot; }
+            }
+        }
+    } else if (dsub <= 16) {
         float qv[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) qv[e] = (e < dsub) ? __ldg(q + j * dsub + e) * lut_scale : 0.0f;
+        for (int e = 0; e < 16; ++e) qv[e] = (e < dsub) ? q[j * dsub + e] * lut_scale : 0.0f;
         for (int c = c0; c < 256; c += U * ngroups) {
             float dot[U];
-            if (dsub == 2) {
-                float2 v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int cu = min(c + u * ngroups, 255);
-                    v[u] = __ldg(reinterpret_cast<const float2*>(codebooks_t + ((size_t)cu * M + j) * 2));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) dot[u] = fmaf(qv[1], v[u].y, qv[0] * v[u].x);
-            } else if ((dsub & 3) == 0) {
+            if ((dsub & 3) == 0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) dot[u] = 0.0f;
 #pragma unroll
@@ -303,7 +326,7 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
         for (int c = c0; c < 256; c += ngroups) {
             const float* cw = codebooks_t + ((size_t)c * M + j) * dsub;
             float dot = 0.0f;
-            for (int e = 0; e < dsub; ++e) dot = fmaf(__ldg(q + j * dsub + e), __ldg(cw + e), dot);
+            for (int e = 0; e < dsub; ++e) dot = fmaf(q[j * dsub + e], __ldg(cw + e), dot);
             dot *= lut_scale;
             colA[c * 64] = dot; colB[c * 64] = dot;
         }
@@ -326,22 +349,29 @@ __device__ __noinline__ uint32_t flush_queue(u64* wq, int Pw, int k, int cnt, bo
     return thr_u;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // m = 16 G
 template <int G>
 __global__ void __launch_bounds__(kFastThreads, 1)
 ivfpq_scan_kernel(ScanArgs a) {
     constexpr int m = 16 * G;
     constexpr int NTAB = (G + 1) / 2;
+    constexpr int kGrab = 4;                             // largest run of chunks handed to a warp at once
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
 
     // ---- shared-memory map: bookkeeping first, then the 64 KB-aligned tables ----
-    float* s_bias = reinterpret_cast<float*>(smem_raw);                   // [nprobe]
-    int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);             // [nprobe]  first slot / 32
-    int* s_len = s_start + a.nprobe;                                      // [nprobe]
-    int* s_pref = s_len + a.nprobe;                                       // [nprobe + 1] chunk prefix
-    int* s_item = s_pref + a.nprobe + 1;                                  // [2] work items (double buffered)
+    // probe tables, double buffered (the next query's is built while this one is scanned):
+    // [bias nprobe][first slot / 32 nprobe][length nprobe][chunk prefix nprobe + 1]
+    const int pt_words = 4 * a.nprobe + 1;
+    int* s_pt = reinterpret_cast<int*>(smem_raw);                         // [2][pt_words]
+    float* s_qv = reinterpret_cast<float*>(s_pt + 2 * pt_words);          // [2][d] the queries themselves
+    int* s_np = reinterpret_cast<int*>(s_qv + 2 * a.d);                   // [2] non-empty probes of the query
+    int* s_item = s_np + 2;                                               // [2] work items (double buffered)
     int* s_thr = s_item + 2;                                              // [1] CTA acceptance threshold
     int* s_ncand = s_thr + 1;                                             // [2] candidates published for the merge
     int* s_next = s_ncand + 2;                                            // [1] next chunk to hand out
@@ -360,7 +390,11 @@ ivfpq_scan_kernel(ScanArgs a) {
     const float lut_scale = order_max ? 1.0f : -2.0f;
     u64* wq = s_wq + (size_t)warp * a.Pw;
     unsigned long long scanned_local = 0;
+#ifdef VIX_SCAN_DIAG
+    unsigned long long diag = 0;     // chunks [0, 24) | queue flushes [24, 44) | chunks with a passing entry [44, 64)
+#endif
     volatile uint32_t* cta_thr = reinterpret_cast<volatile uint32_t*>(s_thr);
+    volatile int* v_next = reinterpret_cast<volatile int*>(s_next);
 
     // per-lane look-up constants
     // (byte b of a group: slot byte offset 4 * (16 * replica + ((b ^ lane) & 15)); packed two per register under
@@ -374,7 +408,22 @@ ivfpq_scan_kernel(ScanArgs a) {
         asm volatile("" : "+r"(pre[b >> 1]));  // opaque: keep the constants in registers, never recompute them
     }
 
+    // probe table of work item `item` into buffer b (one warp)
+    auto probe_table = [&](int item, int b) {
+        if (item >= a.nq) return;
+        const int64_t qn = a.order ? a.order[item] : item;
+        int* pt = s_pt + b * pt_words;
+        build_probe_table(a.queries + qn * (int64_t)a.d, a.d, a.coarse, order_max, a.probes + qn * (int64_t)a.nprobe,
+                          a.nprobe, a.list_off, a.list_len, pt + a.nprobe, pt + 2 * a.nprobe, pt + 3 * a.nprobe,
+                          reinterpret_cast<float*>(pt), s_np + b, s_qv + b * a.d);
+    };
+
     if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); s_ncand[0] = 0; s_ncand[1] = 0; }
+    __syncthreads();
+    if (warp == 1) {
+        probe_table(s_item[0], 0);
+        if (lane == 0) s_item[1] = atomicAdd(a.work_counter, 1);
+    }
     __syncthreads();
     int buf = 0;
     bool have_prev = false;
@@ -385,23 +434,44 @@ ivfpq_scan_kernel(ScanArgs a) {
         const int item = s_item[buf];
         const bool more = item < a.nq;
         const int64_t qi = more ? (a.order ? a.order[item] : item) : 0;
-        const float* q = a.queries + qi * (int64_t)a.d;
-        const int32_t* qprobes = a.probes + qi * (int64_t)a.nprobe;
+        const float* q = s_qv + buf * a.d;
+        const int* pt = s_pt + buf * pt_words;
+        const float* p_bias = reinterpret_cast<const float*>(pt);
+        const int* p_start = pt + a.nprobe;
+        const int* p_len = pt + 2 * a.nprobe;
+        const int* p_pref = pt + 3 * a.nprobe;
+        const int nchunks = more ? p_pref[s_np[buf]] : 0;
+
+        // L2 prefetch of the run of chunks [c0, c0 + cnt) of the query's chunk sequence, as far as it stays inside the
+        // list c0 lies in (one uniform walk of the probe table; `hint` = a probe at or before c0's)
+        auto prefetch_group = [&](int c0, int cnt, int hint) {
+            if (c0 >= nchunks) return;
+            int pp = hint;
+            while (c0 >= p_pref[pp + 1]) ++pp;
+            const int cidx = p_start[pp] + (c0 - p_pref[pp]);
+            const int n = min(cnt, p_pref[pp + 1] - c0);
+            const unsigned char* base = a.slot_codes + (size_t)cidx * (512u * G);
+            for (int l = lane; l < n * 4 * G; l += 32) prefetch_l2(base + l * 128);
+            if (lane < n) prefetch_l2(a.slot_tx + (size_t)(cidx + lane) * 32);
+        };
 
         if (more) {
-            // ---- prologue: warp 1 builds the probe table, every other warp the look-up table ----
-            if (tid == 32) { s_item[buf ^ 1] = atomicAdd(a.work_counter, 1); *cta_thr = 0xFFFFFFFFu; *s_next = 0; }
+            // ---- prologue: the first run of chunks of every warp is fixed (warp w: chunks [4 w, 4 w + 4)) and starts
+            //      its way from HBM to L2 now, under the table build ----
+            if (tid == 32) { *cta_thr = 0xFFFFFFFFu; *s_next = nwarps * kGrab; }
             const long long t0 = clock64();
-            if (warp == 1)
-                build_probe_table(qprobes, a.bias + qi * (int64_t)a.nprobe, a.nprobe, a.list_off, a.list_len, s_start,
-                                  s_len, s_pref, s_bias);
-            else
-                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, warp == 0 ? tid : tid - 32, (int)blockDim.x - 32);
-            if (a.phase_cycles && (tid == 32 || tid == 64)) atomicAdd(a.phase_cycles + (tid == 32 ? 4 : 5), (unsigned long long)(clock64() - t0));
+            if (nchunks > 0) {
+#if VIX_SCAN_L2PF >= 1
+                prefetch_group(warp * kGrab, kGrab, 0);
+#endif
+                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, (int)blockDim.x);
+            }
+            if (a.phase_cycles && tid == 64) atomicAdd(a.phase_cycles + 5, (unsigned long long)(clock64() - t0));
         }
-        __syncthreads();                                   // (1) table, probe table, bias ready
-        // ---- warp 0 first selects the k best of the candidates published for the PREVIOUS query; the other
-        //      warps are already scanning, and chunks are handed out dynamically, so nobody waits for it
+        __syncthreads();                                   // (1) table ready; s_item[buf] has been read by everybody
+        // ---- warp 0 first selects the k best of the candidates published for the PREVIOUS query and warp 1 builds
+        //      the NEXT query's probe table; the other warps are already scanning, and chunks are handed out
+        //      dynamically, so nobody waits for either
         if (warp == 0 && have_prev) {
             const long long t0 = clock64();
             if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 6, (unsigned long long)s_ncand[buf ^ 1]);
@@ -412,29 +482,50 @@ ivfpq_scan_kernel(ScanArgs a) {
             if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 3, (unsigned long long)(clock64() - t0));
         }
         if (!more) break;
+        if (warp == 1) {
+            const long long t0 = clock64();
+            probe_table(s_item[buf ^ 1], buf ^ 1);
+            if (lane == 0) s_item[buf] = atomicAdd(a.work_counter, 1);   // the item after the next
+            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 4, (unsigned long long)(clock64() - t0));
+        }
         { const long long t = clock64(); cyc_pro += (unsigned long long)(t - t_mark); t_mark = t; }
 
         // ---- scan: 32-slot chunks of the probed lists, handed out dynamically ----
-        const int nchunks = s_pref[a.nprobe];
         int cnt = 0;                                       // unsorted candidates behind the k sorted ones
         bool sorted_valid = false;                         // wq[0, k) holds a sorted best list
         uint32_t thr_u = 0xFFFFFFFFu;
         int p = 0;
         uint4 wA[G], wB[G];
-        // chunks are handed out CTA-wide, kGrab consecutive chunks per shared-memory atomic
-        constexpr int kGrab = 4;
-        int grab_end = 0;
+        // Chunks are handed out CTA-wide in runs of 4, 2 and, near the end, 1 (so the warps finish together).  A warp
+        // owns its current run [ch, grab_end) and the next one [nx_c, nx_end), which it prefetched into L2 when it
+        // took it: the bytes in flight per SM are what hides the HBM latency, registers hold only one chunk ahead.
+        int grab_end = warp * kGrab + kGrab, nx_c = 0, nx_end = 0;
+        auto take_run = [&]() {
+            int c = 0, g = 0;
+            if (lane == 0) {
+#if VIX_SCAN_GUIDED
+                const int rem = nchunks - *v_next;
+                g = rem >= 8 * nwarps ? kGrab : (rem >= 3 * nwarps ? 2 : 1);
+#else
+                g = kGrab;
+#endif
+                c = atomicAdd(s_next, g);
+            }
+            nx_c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            nx_end = nx_c + __shfl_sync(0xFFFFFFFFu, g, 0);
+#if VIX_SCAN_L2PF >= 2
+            prefetch_group(nx_c, nx_end - nx_c, p);
+#endif
+        };
         auto grab = [&](int prev) {
             if (prev + 1 < grab_end) return prev + 1;
-            int c = 0;
-            if (lane == 0) c = atomicAdd(s_next, kGrab);
-            c = __shfl_sync(0xFFFFFFFFu, c, 0);
-            grab_end = c + kGrab;
-            const uint32_t t = *cta_thr;                   // refresh the CTA-wide acceptance threshold
-            if (t < thr_u) thr_u = t;
+            const int c = nx_c;
+            grab_end = nx_end;
+            take_run();
             return c;
         };
-        int ch = grab(-1);
+        int ch = warp * kGrab;
+        take_run();
         // the probe the warp is in is cached in registers: chunk range [pb, pe), first slot / 32, length, bias
         int pb = 0, pe = 0, pstart = 0, plen = 0;
         float pbias = 0.0f;
@@ -443,8 +534,8 @@ ivfpq_scan_kernel(ScanArgs a) {
         float ctx_ = 0.0f, cbias = 0.0f;                   // t_x and bias of the current chunk (prefetched)
         auto locate = [&]() {                              // position of chunk `ch` (chunk indices only grow)
             if (ch >= pe) {
-                while (ch >= s_pref[p + 1]) ++p;
-                pb = s_pref[p]; pe = s_pref[p + 1]; pstart = s_start[p]; plen = s_len[p]; pbias = s_bias[p];
+                while (ch >= p_pref[p + 1]) ++p;
+                pb = p_pref[p]; pe = p_pref[p + 1]; pstart = p_start[p]; plen = p_len[p]; pbias = p_bias[p];
             }
             const int within = (ch - pb) * 32 + lane;
             cvalid = within < plen;
@@ -462,6 +553,10 @@ ivfpq_scan_kernel(ScanArgs a) {
             const uint32_t g = cg;
             const bool valid = cvalid;
             const float bias = cbias;
+            const uint32_t cta_t = *cta_thr;               // the CTA-wide acceptance threshold, refreshed every chunk
+#ifdef VIX_SCAN_DIAG
+            diag += 1ull;
+#endif
 #define VIX_ADVANCE()                                                         \
             ch = grab(ch);                                                        \
             if (ch < nchunks) {                                                   \
@@ -487,6 +582,7 @@ ivfpq_scan_kernel(ScanArgs a) {
             if (valid) ++scanned_local;
             const u64 key = make_key(sum, 0u, order_max);
             const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
+            thr_u = min(thr_u, cta_t);
             if (thr_u == 0xFFFFFFFFu && a.k <= 32) {
                 // no threshold yet: the k-th smallest of this chunk bounds the final k-th best
                 const uint32_t kth = warp_kth_smallest(ku, a.k - 1, lane);
@@ -501,13 +597,30 @@ ivfpq_scan_kernel(ScanArgs a) {
                 if (cnt + 32 > a.Pw - a.k) {
                     thr_u = flush_queue(wq, a.Pw, a.k, cnt, sorted_valid, thr_u, s_thr);   // make room: keep the k best
                     cnt = 0; sorted_valid = true;
+#ifdef VIX_SCAN_DIAG
+                    diag += 1ull << 24;
+#endif
                 }
+#ifdef VIX_SCAN_DIAG
+                diag += 1ull << 44;
+#endif
                 if (pass) {
                     const uint32_t id = (uint32_t)a.slot_ids[g];
                     wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)id;
                 }
-                cnt += __popc(ball);
+                const int ncnt = cnt + __popc(ball);
                 __syncwarp();
+                if (a.k <= 32 && (ncnt >> 5) != (cnt >> 5)) {
+                    // 32 more entries have been accepted since the last look: each beat the threshold of its time, so
+                    // their k-th smallest is a tighter bound on the final k-th best -- far cheaper than sorting the queue
+                    const u64 e = wq[a.k + (ncnt & ~31) - 32 + lane];
+                    const uint32_t kth = warp_kth_smallest((uint32_t)(e >> 32), a.k - 1, lane);
+                    if (kth < thr_u) {
+                        thr_u = kth;
+                        if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(s_thr), kth);
+                    }
+                }
+                cnt = ncnt;
             }
         };
 #ifdef VIX_SCAN_NOPREFETCH
@@ -550,6 +663,13 @@ ivfpq_scan_kernel(ScanArgs a) {
         for (int o = 16; o > 0; o >>= 1) scanned_local += __shfl_xor_sync(0xFFFFFFFFu, scanned_local, o);
         if (lane == 0 && scanned_local) atomicAdd(a.scanned, scanned_local);
     }
+#ifdef VIX_SCAN_DIAG
+    if (a.phase_cycles && lane == 0) {
+        atomicAdd(a.phase_cycles + 8, diag & 0xFFFFFFull);
+        atomicAdd(a.phase_cycles + 9, (diag >> 24) & 0xFFFFFull);
+        atomicAdd(a.phase_cycles + 10, diag >> 44);
+    }
+#endif
     if (a.phase_cycles && tid == 64) {                     // one scanning warp per CTA reports its phase split
         atomicAdd(a.phase_cycles + 0, cyc_pro);
         atomicAdd(a.phase_cycles + 1, cyc_scan);
@@ -699,7 +819,7 @@ static int launch_fast(ScanArgs& a) {
     // as many warps as the per-warp selection queues leave room for (24 unless k is large)
     int nwarps = kFastThreads / 32;
     while (nwarps > 3 && 3 * (size_t)nwarps * a.Pw * 8 > 56 * 1024) --nwarps;
-    size_t misc = (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 24 + 16 + 3 * (size_t)nwarps * a.Pw * 8;
+    size_t misc = 2 * ((size_t)a.nprobe * 16 + 4) + 2 * (size_t)a.d * 4 + 40 + 16 + 3 * (size_t)nwarps * a.Pw * 8;
     // the tables start at the next 64 KB boundary of the shared window, wherever the dynamic segment begins
     size_t smem = misc + 65535 + (size_t)NTAB * 65536;
     if (smem > 227 * 1024) smem = 227 * 1024;
@@ -739,13 +859,6 @@ int launch_ivfpq_scan(ScanArgs& a) {
     VIX_REQUIRE(a.work_counter != nullptr, VIX_ERR_NULL_PTR, "ivfpq scan: work counter missing");
     VIX_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int), ctx().stream));
     a.status = a.work_counter + 1;
-    Scratch<float> bias;
-    const int64_t npairs = a.nq * (int64_t)a.nprobe;
-    VIX_TRY(bias.alloc((size_t)npairs));
-    probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
-        a.queries, a.probes, a.coarse, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
-    VIX_LAUNCH_CHECK();
-    a.bias = bias.ptr;
     switch (a.m) {
         case 16: return launch_fast<1>(a);
         case 32: return launch_fast<2>(a);

@@ -75,8 +75,35 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// A tensor-core pipeline that gives up on a barrier raises this flag.  It lives in mapped pinned host memory, so the
+// host can look at it without a device-to-host copy (and therefore without synchronising the stream): it is
+// checked when a call that used the pipeline synchronises anyway, and at the start of the next such call.
+static int* g_pipe_flag = nullptr;
+
+int* pipeline_error_flag() {
+    if (!g_pipe_flag) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        memset(p, 0, 64);
+        g_pipe_flag = static_cast<int*>(p);
+    }
+    return g_pipe_flag;
+}
+
+int check_pipeline_error() {
+    if (g_pipe_flag && *reinterpret_cast<volatile int*>(g_pipe_flag) != 0) {
+        *reinterpret_cast<volatile int*>(g_pipe_flag) = 0;
+        set_error("tensor-core pipeline timed out waiting on a barrier; the results of that call are invalid");
+        return VIX_ERR_CUDA;
+    }
+    return VIX_OK;
+}
+
 int finish(bool any_host_output) {
-    if (any_host_output || !ctx().async) VIX_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (any_host_output || !ctx().async) {
+        VIX_CUDA(cudaStreamSynchronize(ctx().stream));
+        return check_pipeline_error();
+    }
     return VIX_OK;
 }
 

@@ -14,7 +14,6 @@ struct ScanArgs {
     int* status;                                  // set by the launcher (= work_counter + 1)
     int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
     const float* coarse;                          // [kc x d]
-    const float* bias;                            // [nq x nprobe] per-probe term ||q - c||^2 (L2) / <q, c> (IP)
     const float* codebooks;                       // [m x ks x dsub]
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
     const int64_t* list_off; const int32_t* list_len;

@@ -189,13 +189,19 @@ class IVFPQIndex(IVFIndex):
                                           C.c_int(list_count), ptr(ids, np.int32), ptr(sc, np.float32)))
         return ids, sc
 
-    def search_with_probes(self, queries, k, probes):
+    def search_with_probes(self, queries, k, probes, stats=False):
         q = as_input(queries, np.float32)
         self._check_dim(q, "search_with_probes")
         pr = as_input(probes, np.int32)
         nq, nprobe = int(q.shape[0]), int(pr.shape[1])
         dist = empty_like_input(q, (nq, k), np.float32)
         ids = empty_like_input(q, (nq, k), np.int64)
+        if stats:
+            st = _lib.SearchStats()
+            check(lib().vix_index_search_with_probes_ex(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
+                                                        ptr(pr, np.int32), C.c_int(nprobe), ptr(dist, np.float32),
+                                                        ptr(ids, np.int64), C.byref(st)))
+            return dist, ids, st
         check(lib().vix_index_search_with_probes(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k), ptr(pr, np.int32),
                                                  C.c_int(nprobe), ptr(dist, np.float32), ptr(ids, np.int64)))
         return dist, ids
