@@ -302,6 +302,20 @@ int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int 
                           int32_t* list_ids_out /* [nq x nprobe] */, float* list_scores_out /* nullable */);
 int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                  int nprobe, float* out_dist, int64_t* out_ids);
+/* Packed records for the two exchange steps: key = orderable(score) << 32 | id (score = probe score, resp. API
+ * distance; both ascend), so ascending key order is mergeTopK's (score, then smaller id) order (TopKMerge.swift:66-71).
+ * ONE all-gather of 8-byte keys per step; the merges read the gathered [world x nq x kk] layout directly.
+ *   vix_index_probe_range_keys  -> all-gather -> vix_merge_probe_keys   = the global probe lists [nq x nprobe]
+ *   vix_index_search_with_probes_keys -> all-gather -> vix_merge_result_keys = the merged [nq x k] result
+ * Unused slots are 0xFFFFFFFFFFFFFFFF (keys) / id -1, NaN (merged outputs). */
+int vix_index_probe_range_keys(vix_index_t* h, const float* queries, int64_t nq, int nprobe, int list_begin, int list_count,
+                               uint64_t* keys_out /* [nq x nprobe] */);
+int vix_merge_probe_keys(const uint64_t* keys_all /* [world x nq x nprobe] */, int world, int64_t nq, int nprobe,
+                         int32_t* probes_out /* [nq x nprobe] */);
+int vix_index_search_with_probes_keys(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                      int nprobe, uint64_t* keys_out /* [nq x k] */);
+int vix_merge_result_keys(const uint64_t* keys_all /* [world x nq x k] */, int world, int64_t nq, int k,
+                          float* out_dist, int64_t* out_ids /* [nq x k] */);
 /* same, with the stage timings / scan statistics of vix_index_search_ex (synchronises) */
 int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                     int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats /* nullable */);

@@ -515,6 +515,47 @@ def test_sharded_pieces_emulated_on_one_gpu(oracle):
     assert np.array_equal(bits(md), bits(sd))
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "dotProduct"])
+def test_sharded_key_exchange_emulated_on_one_gpu(oracle, metric):
+    """The packed-record exchange of the NCCL path (probe_range_keys -> gather -> merge_probe_keys ->
+    search_with_probes_keys -> gather -> merge_result_keys), three list-block shards emulated in one process with the
+    all-gathers replaced by np.stack: probe lists, ids and distance bits equal the single index's."""
+    from vectorindex_b200.index import IVFPQIndex, list_block, list_owner, merge_probe_keys, merge_result_keys
+    n, d, m, kc, nq, k, nprobe, world = 7000, 64, 16, 45, 40, 10, 7, 3
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=17)
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    single = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    single.set_coarse(coarse); single.set_codebooks(cb, norms)
+    single.batch_insert(xb, ids)
+    sd, si, sp = single.batch_search(q, k, return_probes=True)
+    shards = []
+    for r in range(world):
+        ix = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+        ix.set_coarse(coarse); ix.set_codebooks(cb, norms)
+        shards.append(ix)
+    asg, codes = shards[0].encode(xb)
+    owner = list_owner(asg.astype(np.int64), kc, world)
+    for r in range(world):
+        sel = owner == r
+        shards[r].add_encoded(asg[sel], codes[sel], ids[sel])
+    pk = np.stack([shards[r].probe_range_keys(q, nprobe, *list_block(kc, r, world)) for r in range(world)])
+    assert pk.dtype == np.uint64 and pk.shape == (world, nq, nprobe)
+    gp = merge_probe_keys(pk)
+    assert gp.dtype == np.int32 and np.array_equal(gp, sp)
+    rk = np.stack([shards[r].search_with_probes_keys(q, k, gp) for r in range(world)])
+    md, mi = merge_result_keys(rk)
+    assert np.array_equal(mi, si)
+    assert np.array_equal(bits(md), bits(sd))
+    # fewer than k vectors in the probed lists of a shard -> padded keys, merged result unaffected
+    tiny = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    tiny.set_coarse(coarse); tiny.set_codebooks(cb, norms)
+    tiny.add_encoded(asg[:3], codes[:3], ids[:3])
+    tk = tiny.search_with_probes_keys(q, k, gp)
+    assert (tk == np.uint64(0xFFFFFFFFFFFFFFFF)).sum() >= nq * (k - 3)
+    md2, mi2 = merge_result_keys(np.stack([tk, np.full_like(tk, 0xFFFFFFFFFFFFFFFF)]))
+    assert np.array_equal(mi2 >= 0, ~np.isnan(md2))
+
+
 def test_ivfpq_edge_cases(oracle):
     from vectorindex_b200.index import IVFPQIndex
     from vectorindex_b200 import VectorIndexError

@@ -90,7 +90,8 @@ _EXPORTS = [
     "vix_index_set_codebooks", "vix_index_get_coarse", "vix_index_get_codebooks", "vix_index_add",
     "vix_index_import_lists", "vix_index_count", "vix_index_list_sizes", "vix_index_export_lists", "vix_index_clear",
     "vix_index_search", "vix_index_search_ex", "vix_index_trace", "vix_index_trace_get", "vix_index_probe_range", "vix_index_search_with_probes",
-    "vix_index_search_with_probes_ex",
+    "vix_index_search_with_probes_ex", "vix_index_probe_range_keys", "vix_merge_probe_keys",
+    "vix_index_search_with_probes_keys", "vix_merge_result_keys",
     "vix_index_encode", "vix_index_add_encoded", "vix_debug_tc_scores_f32", "vix_accel_rank_candidates_f32",
     "cpq_encode_u8_f32", "cpq_encode_u8_f32_with_csq", "cpq_encode_u4_f32", "cpq_encode_residual_u8_f32",
     "cpq_encode_residual_u8_f32_with_csq", "cpq_encode_residual_u4_f32", "cpq_pack_u4_bulk", "cpq_unpack_u4_bulk",
@@ -180,6 +181,7 @@ def empty_like_input(ref, shape, dtype):
     """Output buffer living where ``ref`` lives (torch CUDA tensor -> CUDA tensor, else numpy)."""
     if _is_torch(ref):
         import torch
-        tdt = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8}[dtype]
+        tdt = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8,
+               np.uint64: torch.int64}[dtype]              # torch carries the 64 key bits in int64 tensors
         return torch.empty(shape, dtype=tdt, device=ref.device)
     return np.empty(shape, dtype=dtype)

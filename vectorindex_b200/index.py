@@ -206,6 +206,28 @@ class IVFPQIndex(IVFIndex):
                                                  C.c_int(nprobe), ptr(dist, np.float32), ptr(ids, np.int64)))
         return dist, ids
 
+    def probe_range_keys(self, queries, nprobe, list_begin, list_count):
+        """probe_range as packed records: key = orderable(score) << 32 | list id, [nq x nprobe] (numpy uint64 / torch
+        int64 carrying the same bits) -- what one all-gather of the sharded search exchanges"""
+        q = as_input(queries, np.float32)
+        self._check_dim(q, "probe_range_keys")
+        nq = int(q.shape[0])
+        keys = empty_like_input(q, (nq, nprobe), np.uint64)
+        check(lib().vix_index_probe_range_keys(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(nprobe), C.c_int(list_begin),
+                                               C.c_int(list_count), ptr(keys, np.uint64)))
+        return keys
+
+    def search_with_probes_keys(self, queries, k, probes):
+        """search_with_probes as packed records: key = orderable(distance) << 32 | id, [nq x k]"""
+        q = as_input(queries, np.float32)
+        self._check_dim(q, "search_with_probes_keys")
+        pr = as_input(probes, np.int32)
+        nq, nprobe = int(q.shape[0]), int(pr.shape[1])
+        keys = empty_like_input(q, (nq, k), np.uint64)
+        check(lib().vix_index_search_with_probes_keys(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k), ptr(pr, np.int32),
+                                                      C.c_int(nprobe), ptr(keys, np.uint64)))
+        return keys
+
     def encode(self, vectors):
         """(list assignment, PQ codes) of a batch without storing it (bit-exact, same kernels as batch_insert)"""
         x = as_input(vectors, np.float32)
@@ -273,6 +295,27 @@ def merge_shard_results(dist_all, ids_all, k, metric=METRIC_L2):
         sc = np.ascontiguousarray(np.transpose(dist_all, (1, 0, 2)))
         idm = np.ascontiguousarray(np.transpose(ids_all, (1, 0, 2)))
     return mergeTopK(sc, idm, k, 0)
+
+
+def merge_probe_keys(keys_all):
+    """[world x nq x nprobe] gathered probe keys -> the global probe lists [nq x nprobe] int32 (mergeTopK order)"""
+    keys_all = as_input(keys_all, np.uint64)
+    world, nq, nprobe = (int(v) for v in keys_all.shape)
+    probes = empty_like_input(keys_all, (nq, nprobe), np.int32)
+    check(lib().vix_merge_probe_keys(ptr(keys_all, np.uint64), C.c_int(world), C.c_int64(nq), C.c_int(nprobe),
+                                     ptr(probes, np.int32)))
+    return probes
+
+
+def merge_result_keys(keys_all):
+    """[world x nq x k] gathered result keys -> merged (distances [nq x k] f32, ids [nq x k] int64)"""
+    keys_all = as_input(keys_all, np.uint64)
+    world, nq, k = (int(v) for v in keys_all.shape)
+    dist = empty_like_input(keys_all, (nq, k), np.float32)
+    ids = empty_like_input(keys_all, (nq, k), np.int64)
+    check(lib().vix_merge_result_keys(ptr(keys_all, np.uint64), C.c_int(world), C.c_int64(nq), C.c_int(k),
+                                      ptr(dist, np.float32), ptr(ids, np.int64)))
+    return dist, ids
 
 
 def merge_shard_results_host(dist_all, ids_all, k):
@@ -418,6 +461,23 @@ class ShardedIVFPQIndex:
                 marks.append((name, e))
 
         mark("start")
+        if self.world > 1 and self._nccl() and hasattr(self.local, "probe_range_keys"):
+            # device path: two all-gathers of packed 8-byte records, merges straight from the gathered layout
+            begin, count = list_block(self.kc, self.rank, self.world)
+            pk = self._all_gather(self.local.probe_range_keys(queries, nprobe, begin, count))
+            probes = merge_probe_keys(pk)
+            mark("probe_range+gather+merge")
+            rk = self.local.search_with_probes_keys(queries, k, probes)
+            mark("scan")
+            md, mi = merge_result_keys(self._all_gather(rk))
+            mark("gather+merge")
+            if marks:
+                torch.cuda.synchronize()
+                for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                    self.phase_times[name] = self.phase_times.get(name, 0.0) + a.elapsed_time(b)
+            if was_numpy:
+                md, mi = md.cpu().numpy(), mi.cpu().numpy()
+            return md, mi
         probes = self.global_probes(queries, nprobe)
         mark("probe_range+gather+merge")
         if not self._nccl() and _lib._is_torch(probes):
