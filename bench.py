@@ -255,7 +255,20 @@ def cpu_search_arm(cfg, idx, q_host, budget_s=12.0, gpu_ids=None):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's real stdout (see main: fd 1 is pointed at stderr while
+    the bench runs, so that banners of libraries -- NCCL's version line -- cannot land on stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -331,7 +344,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": base_cfg, "cpu_baseline": info,
                 "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         clk.stop()
         return 0
 
@@ -469,7 +482,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline and not args.profile:
         info, _, _ = cpu_search_arm(cfg, idx, q_host, gpu_ids=np.asarray(h_i))
         line["cpu_baseline"] = info
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,143 @@
+"""Committed golden vectors (tests/golden/, written by scripts/make_golden.py from the seeded inputs of
+tests/golden_inputs.py).
+
+cpq_encode_reference.npz are outputs of the REFERENCE's own C encoder (pq_encode.c compiled unmodified): the oracle
+restatement (CPU) and the CUDA library (GPU, through the reference's cpq_* symbols) must reproduce them bit for bit.
+oracle_search_small.npz freezes the oracle's output of every stage of the search path (no reference test pins LUT / ADC
+arithmetic); the GPU tests compare the C-ABI entry points with it."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VARIANTS = ["u8", "u8_nodot", "u8_csq", "res", "res_nodot", "res_csq", "u4", "res_u4"]
+
+
+def _enc():
+    return np.load(os.path.join(GOLD, "cpq_encode_reference.npz"))
+
+
+def _srch():
+    return np.load(os.path.join(GOLD, "oracle_search_small.npz"))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------ CPU: oracle vs golden
+@pytest.mark.parametrize("problem", ["parity", "random"])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_oracle_reproduces_reference_encoder_golden(oracle, problem, variant):
+    x, cb8, cb4, coarse, assign, m = gi.encoder_problems()[problem]
+    gold = _enc()
+    csq = gold[f"{problem}.csq"]
+    assert np.array_equal(bits(oracle.pq_centroid_sq(cb8, m, 256, x.shape[1] // m, swift=True)), bits(csq))
+    res = variant.startswith("res")
+    kw = dict(coarse=coarse, assign_=assign) if res else {}
+    if variant.endswith("u4"):
+        got = oracle.pq_encode_u4(x, cb4, m, 16, **kw)
+    elif variant.endswith("csq"):
+        got = oracle.pq_encode_u8(x, cb8, m, 256, centroid_sq=csq, **kw)
+    else:
+        got = oracle.pq_encode_u8(x, cb8, m, 256, use_dot=not variant.endswith("nodot"), **kw)
+    assert np.array_equal(got, gold[f"{problem}.{variant}"])
+
+
+def test_first_row_of_reference_fixture_pin():
+    """first row of the n=16, d=32, m=8 fixture through the reference C path."""
+    assert _enc()["parity.u8"][0].tolist() == [212, 186, 160, 117, 255, 154, 186, 249]
+
+
+def test_oracle_reproduces_search_golden(oracle):
+    P, g = gi.search_problem(), _srch()
+    xb, q, coarse, cb, m, kc, nprobe, k = P["xb"], P["q"], P["coarse"], P["cb"], P["m"], P["kc"], P["nprobe"], P["k"]
+    asg, adist = oracle.assign(xb, coarse)
+    assert np.array_equal(asg, g["assign"]) and np.array_equal(bits(adist), bits(g["assign_dist"]))
+    codes = oracle.pq_encode_u8(xb, cb, m, 256, centroid_sq=g["cb_norms"].reshape(-1), coarse=coarse, assign_=asg)
+    assert np.array_equal(codes, g["codes"])
+    pid, psc = oracle.probe_select_batch(q, coarse, nprobe, 0, oracle.centroid_norms(coarse))
+    assert np.array_equal(pid, g["probe_ids"]) and np.array_equal(bits(psc), bits(g["probe_scores"]))
+    fd, fi, _ = oracle.flat_search(q, xb, k, 0)
+    assert np.array_equal(fi, g["flat_ids"]) and np.array_equal(bits(fd), bits(g["flat_dist"]))
+
+
+# ------------------------------------------------------------------------------------------ GPU: C ABI vs golden
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem", ["parity", "random"])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_cuda_encoder_reproduces_reference_encoder_golden(vk, problem, variant):
+    from vectorindex_b200._lib import PQEncodeOpts
+    x, cb8, cb4, coarse, assign, m = gi.encoder_problems()[problem]
+    gold = _enc()
+    csq = gold[f"{problem}.csq"]
+    nodot = PQEncodeOpts(0, False, False, 8, 0, 0, 0)
+    if variant == "u8":
+        got = vk.pq_encode_u8_f32(x, cb8, m, 256)
+    elif variant == "u8_nodot":
+        got = vk.pq_encode_u8_f32(x, cb8, m, 256, nodot)
+    elif variant == "u8_csq":
+        got = vk.pq_encode_u8_f32_withCSQ(x, cb8, csq, m, 256)
+    elif variant == "res":
+        got = vk.pq_encode_residual_u8_f32(x, cb8, coarse, assign, m, 256)
+    elif variant == "res_nodot":
+        got = vk.pq_encode_residual_u8_f32(x, cb8, coarse, assign, m, 256, nodot)
+    elif variant == "res_csq":
+        got = vk.pq_encode_residual_u8_f32_withCSQ(x, cb8, csq, coarse, assign, m, 256)
+    elif variant == "u4":
+        got = vk.pq_encode_u4_f32(x, cb4, m, 16)
+    else:
+        got = vk.pq_encode_residual_u4_f32(x, cb4, coarse, assign, m, 16)
+    assert np.array_equal(np.asarray(got).reshape(gold[f"{problem}.{variant}"].shape), gold[f"{problem}.{variant}"])
+
+
+@pytest.mark.gpu
+def test_cuda_search_stages_reproduce_golden(vk):
+    from vectorindex_b200.index import IVFPQIndex
+    P, g = gi.search_problem(), _srch()
+    xb, q, coarse, cb, m, kc, nprobe, k = P["xb"], P["q"], P["coarse"], P["cb"], P["m"], P["kc"], P["nprobe"], P["k"]
+    d = xb.shape[1]
+    norms = g["cb_norms"]
+    asg, adist = vk.ivf_assign_f32(xb, coarse, return_dist=True)
+    assert np.array_equal(asg, g["assign"]) and np.array_equal(bits(adist), bits(g["assign_dist"]))
+    codes = vk.pq_encode_residual_u8_f32_withCSQ(xb, cb.reshape(-1), norms.reshape(-1), coarse, asg, m, 256)
+    assert np.array_equal(np.asarray(codes).reshape(-1, m), g["codes"])
+    cn = vk.row_norms_f32(coarse)
+    pid, psc = vk.ivf_select_nprobe_batch_f32(q, coarse, nprobe, 0, None)
+    assert np.array_equal(pid, g["probe_ids"])                      # kernel-level scores use the vDSP form: ids only
+    # residual LUTs of the first probe + ADC over that list: bit-exact (PQLUT.swift:266-386, ADCScan.swift:190-283)
+    luts = vk.pq_lut_residual_l2_f32(q[:8], g["probe_ids"][:8, 0].astype(np.int32), coarse, cb, m, 256, norms)
+    assert np.array_equal(bits(luts), bits(g["lut_first_probe"]))
+    order = np.argsort(g["assign"], kind="stable")
+    off = np.concatenate([[0], np.cumsum(np.bincount(g["assign"], minlength=kc))])
+    pos = 0
+    for r in range(8):
+        l = int(g["probe_ids"][r, 0])
+        rows = order[off[l]:off[l + 1]]
+        n = int(g["adc_first_probe_len"][r])
+        assert rows.size == n
+        if n:
+            out = vk.adc_scan_u8(g["codes"][rows], g["lut_first_probe"][r], m, 256)
+            assert np.array_equal(bits(out), bits(g["adc_first_probe"][pos:pos + n]))
+        pos += n
+    fd, fi = vk.flat_search_f32(q, xb, k, 0)
+    assert np.array_equal(fi, g["flat_ids"]) and np.array_equal(bits(fd), bits(g["flat_dist"]))
+    # the index: same lists, probe lists bit-exact, fused-scan distances within 1e-5 (re-associated sum), id sets equal
+    # except at ties inside that tolerance
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb)
+    gd, gi_, gp = idx.batch_search(q, k, return_probes=True)
+    assert np.array_equal(gp, g["probe_ids"])
+    np.testing.assert_allclose(gd, g["ivfpq_dist"], rtol=1e-5)
+    for r in range(q.shape[0]):
+        extra = set(gi_[r].tolist()) ^ set(g["ivfpq_ids"][r].tolist())
+        if extra:                                                    # only entries tied with the k-th distance may differ
+            kth = g["ivfpq_dist"][r, -1]
+            both = {int(i): float(v) for i, v in zip(g["ivfpq_ids"][r], g["ivfpq_dist"][r])}
+            both.update({int(i): float(v) for i, v in zip(gi_[r], gd[r])})
+            assert all(abs(both[i] - kth) <= 1e-5 * abs(kth) for i in extra)
