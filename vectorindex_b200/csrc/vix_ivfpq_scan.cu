@@ -474,8 +474,9 @@ ivfpq_scan_kernel(ScanArgs a) {
         uint4 wA[G], wB[G];
         // Chunks are handed out CTA-wide in runs of 4, 2 and, near the end, 1 (so the warps finish together).  A warp
         // owns its current run [ch, grab_end) and has already taken the next one [nx_c, nx_end).  (Measured and
-        // dropped: prefetch.global.L2 of the next run -- 7 % slower -- and stepping through a run with pointer
-        // increments instead of re-locating every chunk -- fewer instructions, yet 7 % slower.)
+        // dropped: prefetch.global.L2 of the next run -- 7 % slower; of just the next chunk -- no gain; stepping
+        // through a run with pointer increments instead of re-locating every chunk -- fewer instructions, yet 7 %
+        // slower.)
         int grab_end = warp * kGrab + kGrab, nx_c = 0, nx_end = 0;
         auto take_run = [&]() {
             int c = 0, g = 0;
