@@ -291,6 +291,17 @@ int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k,
                         float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,
                         vix_search_stats* stats /* nullable */);
 
+/* Search with an id filter: IDFilterBitset / idFilterPass of Operations/Filtering/IDFilter.swift:13-135 -- a bitset over
+ * the dense id domain [0, capacity); ids outside the domain never pass; VIX_FILTER_ALLOW keeps ids whose bit is 1,
+ * VIX_FILTER_DENY keeps ids whose bit is 0.  The filter is applied BEFORE selection (the pre-filter of
+ * IVFIndex.search / FlatIndex.search, IVFIndex.swift:813, 1034; FlatIndex.swift:61): the result is the k best of the
+ * vectors that pass, possibly fewer than k (padding id -1 / NaN).  filter_words == NULL => unfiltered search.
+ * Closure filters over metadata are host-side objects in the reference; evaluate them on the host into a bitset. */
+enum { VIX_FILTER_ALLOW = 0, VIX_FILTER_DENY = 1 };
+int vix_index_search_filtered(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
+                              const uint64_t* filter_words /* [ceil(capacity / 64)] */, int64_t filter_capacity,
+                              int filter_mode, float* out_dist, int64_t* out_ids);
+
 /* ---- multi-GPU: inverted lists are partitioned over ranks by contiguous list-id blocks ------------------
  * Search on rank r of R:  vix_index_probe_range over r's block of centroids (local top-nprobe, GLOBAL list ids)
  *   -> all-gather + vix_merge_topk_f32 (.min; ids = list ids) = the global probe lists of IVFIndex.swift:905-927

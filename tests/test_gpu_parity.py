@@ -556,6 +556,63 @@ def test_sharded_key_exchange_emulated_on_one_gpu(oracle, metric):
     assert np.array_equal(mi2 >= 0, ~np.isnan(md2))
 
 
+@pytest.mark.parametrize("mode", ["allow", "deny"])
+@pytest.mark.parametrize("m", [16, 12])          # fused fast kernel / generic kernel
+def test_ivfpq_filtered_search_is_prefilter(oracle, mode, m):
+    """IDFilter semantics (IDFilter.swift:115-135) as a PRE-filter (IVFIndex.swift:813, 1034): the filtered search
+    equals the oracle's search over an index from which the failing vectors were removed; ids outside the bitset's
+    domain never pass."""
+    from vectorindex_b200.index import IDFilter, IVFPQIndex
+    n, d, kc, nq, k, nprobe = 6000, 48, 32, 40, 10, 6
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=5)
+    ids = np.arange(n, dtype=np.int64) * 2 + 1                         # odd ids up to 2n
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse); idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb, ids)
+    rng = np.random.default_rng(3)
+    cap = int(ids.max() * 0.8)                                         # the largest ids lie outside the domain
+    f = IDFilter(cap, mode)
+    f.set(rng.choice(cap, cap // 3, replace=False))
+    keep = f.test(ids)
+    assert 0 < keep.sum() < n and not keep[ids >= cap].any()
+    gd, gi = idx.batch_search(q, k, filter=f)
+    off, codes, lids, asg = idx.export_lists()
+    kept = f.test(lids)
+    lens = np.bincount(np.repeat(np.arange(kc), np.diff(off))[kept], minlength=kc)
+    off2 = np.concatenate([[0], np.cumsum(lens)])
+    od, oi, _ = oracle.ivfpq_search(q, coarse, cb, norms, off2, codes[kept], lids[kept], m, 256, nprobe, k, 0)
+    np.testing.assert_allclose(gd, od, rtol=1e-5, equal_nan=True)
+    same = np.mean([len(set(gi[r]) & set(oi[r])) / k for r in range(nq)])
+    assert same > 0.995
+    assert f.test(gi[gi >= 0]).all()
+    # a filter nothing passes -> empty results (id -1, NaN)
+    none = IDFilter(cap, "allow")
+    ed, ei = idx.batch_search(q, k, filter=none)
+    assert (ei == -1).all() and np.isnan(ed).all()
+
+
+@pytest.mark.parametrize("kind", ["flat", "ivfflat"])
+def test_flat_and_ivfflat_filtered_search(oracle, kind):
+    from vectorindex_b200.index import FlatIndex, IDFilter, IVFIndex
+    rng = np.random.default_rng(11)
+    n, d, nq, k = 5000, 32, 30, 10
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    ids = rng.permutation(3 * n)[:n].astype(np.int64)
+    f = IDFilter(3 * n, "deny").set(rng.choice(3 * n, n, replace=False))
+    keep = f.test(ids)
+    if kind == "flat":
+        idx = FlatIndex(d, "euclidean")
+    else:
+        idx = IVFIndex(d, "euclidean", nlist=8, nprobe=8)              # every list probed: same answer as flat
+        idx.set_coarse(xb[:8].copy())
+    idx.batch_insert(xb, ids)
+    gd, gi = idx.batch_search(q, k, filter=f)
+    od, oi, _ = oracle.flat_search(q, xb[keep], k, 0)
+    assert np.array_equal(gi, ids[keep][oi])
+    assert np.array_equal(bits(gd), bits(od))
+
+
 def test_ivfpq_edge_cases(oracle):
     from vectorindex_b200.index import IVFPQIndex
     from vectorindex_b200 import VectorIndexError

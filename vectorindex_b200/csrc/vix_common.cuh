@@ -179,6 +179,13 @@ __device__ __forceinline__ float key_score(u64 key, int order_max) {
 }
 __device__ __forceinline__ uint32_t key_id(u64 key) { return (uint32_t)(key & 0xFFFFFFFFull); }
 
+// idFilterPass (Operations/Filtering/IDFilter.swift:115-135): out-of-range ids are dropped in either mode
+__device__ __forceinline__ bool id_filter_pass(const uint64_t* __restrict__ words, int64_t cap, int deny, int64_t id) {
+    if (id < 0 || id >= cap) return false;
+    const bool bit = (__ldg(words + (id >> 6)) >> (id & 63)) & 1ull;
+    return deny ? !bit : bit;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace vix

@@ -30,6 +30,8 @@ int pq_encode_device(const float* x, int64_t n, int d, int m, int ks, const floa
                      int B, int g, int u4);
 int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
                        const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
+int flat_search_masked_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                              const uint64_t* disabled_rows, float* out_dist, int64_t* out_ids);
 int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
                             const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores);
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
@@ -349,7 +351,8 @@ __global__ void __launch_bounds__(256)
 ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const int32_t* __restrict__ probes,
                     int nprobe, const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
                     const float* __restrict__ slot_vecs, const int64_t* __restrict__ slot_ids, int metric, int k,
-                    int P, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+                    int P, const uint64_t* __restrict__ filter, int64_t filter_cap, int filter_deny,
+                    float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = reinterpret_cast<u64*>(smem_raw);
     float* s_q = reinterpret_cast<float*>(keys + P);
@@ -368,7 +371,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
             for (int base = 0; base < len; base += blockDim.x) {
                 q.flush_if_needed(blockDim.x);
                 const int i = base + threadIdx.x;
-                if (i < len) {
+                if (i < len && (!filter || id_filter_pass(filter, filter_cap, filter_deny, slot_ids[b + i]))) {
                     const float* v = slot_vecs + (b + i) * (int64_t)d;
                     float dist = (metric == VIX_METRIC_L2) ? __fsqrt_rn(exact_pair<SpecDirect16L2>(s_q, v, d))
                                                            : -exact_pair<SpecIp4>(s_q, v, d);
@@ -389,6 +392,21 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
 // ------------------------------------------------------------------------------------------------
 // host-side index logic
 // ------------------------------------------------------------------------------------------------
+// flat / linear-scan pre-filter: bit r of the mask set <=> row r fails the id filter (64 rows per thread)
+__global__ void filter_row_mask_kernel(const int64_t* __restrict__ ids, int64_t n, const uint64_t* __restrict__ filter,
+                                       int64_t filter_cap, int filter_deny, uint64_t* __restrict__ mask) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 64 >= n) return;
+    uint64_t bits = 0;
+    for (int b = 0; b < 64; ++b) {
+        const int64_t r = w * 64 + b;
+        if (r < n && !id_filter_pass(filter, filter_cap, filter_deny, ids[r])) bits |= 1ull << b;
+    }
+    mask[w] = bits;
+}
+
+struct FilterArgs { const uint64_t* words = nullptr; int64_t cap = 0; int deny = 0; };
+
 __global__ void gather_ids_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ ids,
                                   int64_t* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -493,7 +511,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
 
 static int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
                                int64_t* out_ids, int32_t* out_probes, vix_search_stats* stats,
-                               const int32_t* given_probes = nullptr) {
+                               const int32_t* given_probes = nullptr, const FilterArgs* filter = nullptr) {
     const int d = h->p.d;
     cudaStream_t s = ctx().stream;
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -520,6 +538,15 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         VIX_REQUIRE(h->p.kind != VIX_INDEX_IVF_PQ, VIX_ERR_NOT_TRAINED, "index_search: IVF-PQ index is not trained");
         Scratch<int64_t> rows;
         VIX_TRY(rows.alloc((size_t)nq * k));
+        if (filter && h->n > 0) {
+            Scratch<uint64_t> mask;
+            const int64_t words = (h->n + 63) / 64;
+            VIX_TRY(mask.alloc((size_t)words));
+            filter_row_mask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(h->ids.ptr, h->n, filter->words, filter->cap,
+                                                                                filter->deny, mask.ptr);
+            VIX_LAUNCH_CHECK();
+            VIX_TRY(flat_search_masked_device(dq.dev, nq, h->vecs.ptr, h->n, d, h->p.metric, k, mask.ptr, dd.dev, rows.ptr));
+        } else
         VIX_TRY(flat_search_auto_device(dq.dev, nq, h->vecs.ptr, h->n, d, h->p.metric, k, nullptr, dd.dev, rows.ptr, false));
         // row index -> user id
         gather_ids_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, s>>>(rows.ptr, h->ids.ptr, di.dev, nq * (int64_t)k);
@@ -558,6 +585,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.scanned = stats ? scanned.ptr : (traced ? h->trace_scanned.ptr + h->trace_n : nullptr);
             a.phase_cycles = stats ? scanned.ptr + 1 : nullptr;
             a.codebooks_t = h->codebooks_t.ptr;
+            if (filter) { a.filter = filter->words; a.filter_cap = filter->cap; a.filter_deny = filter->deny; }
             VIX_TRY(h->work_counter.resize(2, false));
             a.work_counter = h->work_counter.ptr;
             Scratch<int32_t> order;
@@ -574,7 +602,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             if (grid > nq) grid = nq;
             ivfflat_scan_kernel<<<(unsigned)grid, 256, smem, s>>>(dq.dev, nq, d, pp, nprobe, h->list_off.ptr,
                                                                  h->list_len.ptr, h->slot_vecs.ptr, h->slot_ids.ptr,
-                                                                 h->p.metric, k, P, dd.dev, di.dev);
+                                                                 h->p.metric, k, P, filter ? filter->words : nullptr,
+                                                                 filter ? filter->cap : 0, filter ? filter->deny : 0, dd.dev, di.dev);
             VIX_LAUNCH_CHECK();
         }
         if (traced) VIX_CUDA(cudaEventRecord(tev[2], s));
@@ -877,6 +906,23 @@ int vix_index_search_with_probes(vix_index_t* h, const float* queries, int64_t n
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_search_with_probes: IVF index not trained");
     return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr, probes);
+}
+
+int vix_index_search_filtered(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
+                              const uint64_t* filter_words, int64_t filter_capacity, int filter_mode,
+                              float* out_dist, int64_t* out_ids) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h != nullptr, VIX_ERR_NULL_PTR, "vix_index_search_filtered: null handle");
+    VIX_REQUIRE(filter_mode == VIX_FILTER_ALLOW || filter_mode == VIX_FILTER_DENY, VIX_ERR_INVALID_PARAM,
+                "vix_index_search_filtered: filter_mode must be VIX_FILTER_ALLOW or VIX_FILTER_DENY");
+    VIX_REQUIRE(filter_capacity >= 0, VIX_ERR_INVALID_PARAM, "vix_index_search_filtered: negative capacity");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!filter_words) return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr);
+    In<uint64_t> fw;
+    VIX_TRY(fw.stage(filter_words, (size_t)((filter_capacity + 63) / 64)));
+    FilterArgs f;
+    f.words = fw.dev; f.cap = filter_capacity; f.deny = filter_mode == VIX_FILTER_DENY;
+    return index_search_locked(h, queries, nq, k, nprobe, out_dist, out_ids, nullptr, nullptr, nullptr, &f);
 }
 
 int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,

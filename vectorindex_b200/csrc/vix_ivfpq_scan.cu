@@ -346,8 +346,8 @@ __device__ __noinline__ uint32_t flush_queue(u64* wq, int Pw, int k, int cnt, bo
     return thr_u;
 }
 
-// m = 16 G
-template <int G>
+// m = 16 G; FILTER: an id filter is active (a separate instantiation, so the unfiltered kernel pays nothing)
+template <int G, bool FILTER>
 __global__ void __launch_bounds__(kFastThreads, 1)
 ivfpq_scan_kernel(ScanArgs a) {
     constexpr int m = 16 * G;
@@ -556,8 +556,20 @@ ivfpq_scan_kernel(ScanArgs a) {
             const float sum = (bias + tx) + ((s0 + s1) + (s2 + s3));
             if (valid) ++scanned_local;
             const u64 key = make_key(sum, 0u, order_max);
-            const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
+            uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
             thr_u = min(thr_u, cta_t);
+            uint32_t fid = 0;
+            bool fchecked = false, fdrop = false;
+            if (FILTER && thr_u == 0xFFFFFFFFu) {
+                // no threshold yet: every entry of the chunk meets the filter now (the bound below must only count
+                // entries that can be returned); afterwards only entries that beat the threshold are looked up
+                if (valid) {
+                    fid = (uint32_t)a.slot_ids[g];
+                    fdrop = !id_filter_pass(a.filter, a.filter_cap, a.filter_deny, (int64_t)fid);
+                    if (fdrop) ku = 0xFFFFFFFFu;
+                }
+                fchecked = true;
+            }
             if (thr_u == 0xFFFFFFFFu && a.k <= 32) {
                 // no threshold yet: the k-th smallest of this chunk bounds the final k-th best
                 const uint32_t kth = warp_kth_smallest(ku, a.k - 1, lane);
@@ -566,7 +578,11 @@ ivfpq_scan_kernel(ScanArgs a) {
                     if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(s_thr), kth);
                 }
             }
-            const bool pass = valid && (ku <= thr_u);
+            bool pass = valid && !fdrop && (ku <= thr_u);
+            if (FILTER && !fchecked && pass) {
+                fid = (uint32_t)a.slot_ids[g];
+                pass = id_filter_pass(a.filter, a.filter_cap, a.filter_deny, (int64_t)fid);
+            }
             const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
             if (ball) {
                 if (cnt + 32 > a.Pw - a.k) {
@@ -580,7 +596,7 @@ ivfpq_scan_kernel(ScanArgs a) {
                 diag += 1ull << 44;
 #endif
                 if (pass) {
-                    const uint32_t id = (uint32_t)a.slot_ids[g];
+                    const uint32_t id = FILTER ? fid : (uint32_t)a.slot_ids[g];
                     wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)id;
                 }
                 const int ncnt = cnt + __popc(ball);
@@ -725,13 +741,15 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
             const float tx = valid ? a.slot_tx[g] : 0.0f;
             const float sum = (s_bias[p] + tx) + s0;
             if (valid) ++scanned_local;
-            const bool pass = valid && (order_max ? !(sum < thr_s) : !(sum > thr_s));
+            bool pass = valid && (order_max ? !(sum < thr_s) : !(sum > thr_s));
+            uint32_t id = 0;
+            if (pass) {
+                id = (uint32_t)a.slot_ids[g];
+                if (a.filter) pass = id_filter_pass(a.filter, a.filter_cap, a.filter_deny, (int64_t)id);
+            }
             const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
             if (ball) {
-                if (pass) {
-                    const uint32_t id = (uint32_t)a.slot_ids[g];
-                    wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = make_key(sum, id, order_max);
-                }
+                if (pass) wq[a.k + cnt + __popc(ball & ((1u << lane) - 1u))] = make_key(sum, id, order_max);
                 cnt += __popc(ball);
                 __syncwarp();
                 if (cnt + 32 > a.Pw - a.k) {
@@ -788,7 +806,7 @@ static size_t generic_smem_bytes(const ScanArgs& a) {
     return s;
 }
 
-template <int G>
+template <int G, bool FILTER>
 static int launch_fast(ScanArgs& a) {
     constexpr int NTAB = (G + 1) / 2;
     // as many warps as the per-warp selection queues leave room for (24 unless k is large)
@@ -801,7 +819,7 @@ static int launch_fast(ScanArgs& a) {
     VIX_REQUIRE(misc + 1024 <= 65536 && (size_t)(NTAB + 1) * 65536 <= smem + 1024 + 65535, VIX_ERR_UNSUPPORTED,
                 "ivfpq scan: k = %d, nprobe = %d need %zu bytes of bookkeeping shared memory", a.k, a.nprobe, misc);
     a.smem_bytes = (int)smem;
-    auto kern = ivfpq_scan_kernel<G>;
+    auto kern = ivfpq_scan_kernel<G, FILTER>;
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = num_sms();
     if (grid > a.nq) grid = a.nq;
@@ -835,10 +853,10 @@ int launch_ivfpq_scan(ScanArgs& a) {
     VIX_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int), ctx().stream));
     a.status = a.work_counter + 1;
     switch (a.m) {
-        case 16: return launch_fast<1>(a);
-        case 32: return launch_fast<2>(a);
-        case 48: return launch_fast<3>(a);
-        case 64: return launch_fast<4>(a);
+        case 16: return a.filter ? launch_fast<1, true>(a) : launch_fast<1, false>(a);
+        case 32: return a.filter ? launch_fast<2, true>(a) : launch_fast<2, false>(a);
+        case 48: return a.filter ? launch_fast<3, true>(a) : launch_fast<3, false>(a);
+        case 64: return a.filter ? launch_fast<4, true>(a) : launch_fast<4, false>(a);
     }
     set_error("ivfpq scan: unsupported m = %d", a.m);
     return VIX_ERR_UNSUPPORTED;

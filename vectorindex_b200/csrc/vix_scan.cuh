@@ -18,6 +18,9 @@ struct ScanArgs {
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
     const int64_t* list_off; const int32_t* list_len;
     const uint8_t* slot_codes; const float* slot_tx; const int64_t* slot_ids;
+    // optional id filter (IDFilter.swift:115-135): ids outside [0, filter_cap) never pass; allowlist keeps set bits,
+    // denylist keeps clear bits.  Applied BEFORE selection (pre-filter, IVFIndex.swift:813, 1034).
+    const uint64_t* filter; int64_t filter_cap; int filter_deny;
     int metric, k, Pw, P2;
     float* out_dist; int64_t* out_ids;            // [nq x k]
     unsigned long long* scanned;                  // optional: total list entries visited

@@ -391,11 +391,27 @@ int row_norms_device(const float* x, int64_t n, int d, float* out) {
 
 // FlatIndexOptimized.fastSearchWithMicrokernels (FlatIndexOptimized.swift:390-477) for nq queries.
 // raw_scores: keep kernel scores (no sqrt / negate) when true.
+static int flat_search_impl(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                            const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores,
+                            const uint64_t* disabled_rows);
+
 int flat_search_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
                        const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores) {
+    return flat_search_impl(q, nq, xb, n, d, metric, k, xb_norm, out_dist, out_ids, raw_scores, nullptr);
+}
+
+// same scan with a row mask (bit b set => base row b is skipped): the pre-filter of FlatIndex.search (FlatIndex.swift:61)
+int flat_search_masked_device(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                              const uint64_t* disabled_rows, float* out_dist, int64_t* out_ids) {
+    return flat_search_impl(q, nq, xb, n, d, metric, k, nullptr, out_dist, out_ids, false, disabled_rows);
+}
+
+static int flat_search_impl(const float* q, int64_t nq, const float* xb, int64_t n, int d, int metric, int k,
+                            const float* xb_norm, float* out_dist, int64_t* out_ids, bool raw_scores,
+                            const uint64_t* disabled_rows) {
     if (nq == 0 || k <= 0) return VIX_OK;
     PairArgs p{};
-    p.A = q; p.nA = nq; p.B = xb; p.nB = n; p.d = d;
+    p.A = q; p.nA = nq; p.B = xb; p.nB = n; p.d = d; p.disabled = disabled_rows;
     if (n == 0) {
         Scratch<u64> keys;
         VIX_TRY(keys.alloc((size_t)nq));

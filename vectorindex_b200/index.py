@@ -39,6 +39,36 @@ def _metric(m):
     return _METRICS[m]
 
 
+class IDFilter:
+    """IDFilterBitset + FilterMode of Operations/Filtering/IDFilter.swift:13-112: ceil(capacity / 64) 64-bit words over
+    the dense id domain [0, capacity).  ``allow``: bit 1 = keep; ``deny``: bit 1 = drop; ids outside the domain never pass."""
+    ALLOW, DENY = 0, 1
+
+    def __init__(self, capacity: int, mode="allow", initial_bit=False):
+        self.capacity = int(capacity)
+        self.mode = {"allow": 0, "allowlist": 0, "deny": 1, "denylist": 1}[mode] if isinstance(mode, str) else int(mode)
+        self.words = np.full((self.capacity + 63) >> 6, np.uint64(0xFFFFFFFFFFFFFFFF) if initial_bit else np.uint64(0),
+                             dtype=np.uint64)
+
+    def set(self, ids, value=True):
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        ids = ids[(ids >= 0) & (ids < self.capacity)]
+        bit = np.uint64(1) << (ids & 63).astype(np.uint64)
+        if value:
+            np.bitwise_or.at(self.words, ids >> 6, bit)
+        else:
+            np.bitwise_and.at(self.words, ids >> 6, ~bit)
+        return self
+
+    def test(self, ids):
+        """idFilterPass for an array of ids"""
+        ids = np.asarray(ids, dtype=np.int64)
+        inside = (ids >= 0) & (ids < self.capacity)
+        safe = np.where(inside, ids, 0)
+        bit = ((self.words[safe >> 6] >> (safe & 63).astype(np.uint64)) & np.uint64(1)).astype(bool)
+        return inside & (bit if self.mode == 0 else ~bit)
+
+
 class _Index:
     kind = INDEX_FLAT
 
@@ -88,7 +118,9 @@ class _Index:
     def clear(self):
         check(lib().vix_index_clear(self._h))
 
-    def batch_search(self, queries, k: int, nprobe: int = 0, return_probes=False, stats=False):
+    def batch_search(self, queries, k: int, nprobe: int = 0, return_probes=False, stats=False, filter=None):
+        """``filter``: an :class:`IDFilter` (allow / deny bitset over dense ids, applied before selection -- the
+        device-expressible form of the reference's ``filter:`` closures, IVFIndex.swift:813, 1034)."""
         q = as_input(queries, np.float32)
         self._check_dim(q, "batch_search")
         nq = int(q.shape[0])
@@ -96,6 +128,13 @@ class _Index:
         dist = empty_like_input(q, (nq, kk), np.float32)
         ids = empty_like_input(q, (nq, kk), np.int64)
         if kk == 0 or nq == 0:
+            return (dist, ids)
+        if filter is not None:
+            if return_probes or stats:
+                raise ValueError("filtered search returns (distances, ids) only")
+            check(lib().vix_index_search_filtered(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k), C.c_int(nprobe),
+                                                  ptr(filter.words, np.uint64), C.c_int64(filter.capacity),
+                                                  C.c_int(filter.mode), ptr(dist, np.float32), ptr(ids, np.int64)))
             return (dist, ids)
         npb = nprobe if nprobe > 0 else self.params.nprobe
         probes = empty_like_input(q, (nq, npb), np.int32) if return_probes else None
