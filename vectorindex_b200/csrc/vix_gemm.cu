@@ -433,33 +433,53 @@ static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Arg
 }
 
 // ---------------------------------------------------------------------------------------------- thresholds
-// T_q = (k-th smallest group minimum of the row) + margin_q; one CTA per row, bitonic sort of <= 2048 minima
+// T_q = (k-th smallest group minimum of the row) + margin_q.  One WARP per row: the <= 32 VPL minima of the row stay in
+// registers as order-preserving 32-bit keys and the k-th smallest is found by a radix select, one bit per step
+// (how many keys share the prefix found so far and have a 0 in this bit?) with warp ballots -- no shared memory, no
+// CTA-wide barrier, a third of the instructions of sorting the row.
+template <int VPL>
 __global__ void __launch_bounds__(256)
-threshold_kernel(const float* __restrict__ gmin, int ngroups, int P, int k, const float* __restrict__ anorm,
+threshold_kernel(const float* __restrict__ gmin, int64_t nrows, int ngroups, int k, const float* __restrict__ anorm,
                  const float* __restrict__ bnorm_max, float rel, float* __restrict__ thr) {
-    extern __shared__ __align__(16) unsigned char smem_thr[];
-    uint32_t* s = reinterpret_cast<uint32_t*>(smem_thr);
-    const int64_t row = blockIdx.x;
-    for (int i = threadIdx.x; i < P; i += blockDim.x)
-        s[i] = (i < ngroups) ? f32_orderable(gmin[row * ngroups + i]) : 0xFFFFFFFFu;
-    __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const uint32_t x = s[lo], y = s[hi];
-                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
-            }
-            __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nrows) return;
+    uint32_t v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int g = lane + 32 * i;
+        v[i] = g < ngroups ? f32_orderable(__ldg(gmin + row * ngroups + g)) : 0xFFFFFFFFu;
+    }
+    float kth = INFINITY;
+    if (k - 1 < ngroups) {
+        uint32_t prefix = 0;
+        int want = k;                                       // rank (1-based) among the keys that match the prefix
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t hi = bit == 31 ? 0u : ~((2u << bit) - 1u);      // the bits above `bit`
+            int zeros = 0;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+                zeros += __popc(__ballot_sync(0xFFFFFFFFu, ((v[i] ^ prefix) & hi) == 0u && !((v[i] >> bit) & 1u)));
+            if (want > zeros) { want -= zeros; prefix |= 1u << bit; }
         }
+        kth = f32_from_orderable(prefix);
     }
-    if (threadIdx.x == 0) {
-        const float kth = (k - 1 < ngroups) ? f32_from_orderable(s[k - 1]) : INFINITY;
-        // |S~ - S| <= rel * ||q|| * max||c||  (TF32 operand truncation 2 * 2^-10 + fp32 accumulation, with margin)
-        const float eps = rel * sqrtf(anorm[row]) * bnorm_max[0];
-        thr[row] = kth + 2.0f * eps;
-    }
+    // |S~ - S| <= rel * ||q|| * max||c||  (TF32 operand truncation 2 * 2^-10 + fp32 accumulation, with margin)
+    if (lane == 0) thr[row] = kth + 2.0f * rel * sqrtf(anorm[row]) * bnorm_max[0];
+}
+
+static int launch_threshold(const float* gmin, int64_t nrows, int ngroups, int k, const float* anorm, const float* bnorm_max,
+                            float rel, float* thr) {
+    const unsigned grid = (unsigned)((nrows * 32 + 255) / 256);
+    cudaStream_t s = ctx().stream;
+    if (ngroups <= 256) threshold_kernel<8><<<grid, 256, 0, s>>>(gmin, nrows, ngroups, k, anorm, bnorm_max, rel, thr);
+    else if (ngroups <= 512) threshold_kernel<16><<<grid, 256, 0, s>>>(gmin, nrows, ngroups, k, anorm, bnorm_max, rel, thr);
+    else if (ngroups <= 1024) threshold_kernel<32><<<grid, 256, 0, s>>>(gmin, nrows, ngroups, k, anorm, bnorm_max, rel, thr);
+    else if (ngroups <= 2048) threshold_kernel<64><<<grid, 256, 0, s>>>(gmin, nrows, ngroups, k, anorm, bnorm_max, rel, thr);
+    else if (ngroups <= 4096) threshold_kernel<128><<<grid, 256, 0, s>>>(gmin, nrows, ngroups, k, anorm, bnorm_max, rel, thr);
+    else { set_error("threshold: %d groups per row (> 4096)", ngroups); return VIX_ERR_UNSUPPORTED; }
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
 }
 
 __global__ void max_sqrt_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
@@ -738,9 +758,16 @@ int tc_scores_device(const float* q, int64_t nq, const float* c, int kc, int d, 
     return VIX_OK;
 }
 
+// out[0] = sqrt(max x[i]) on the device (the index caches it for its coarse-centroid norms)
+int max_sqrt_device(const float* x, int64_t n, float* out) {
+    tc::max_sqrt_kernel<<<1, 256, 0, ctx().stream>>>(x, n, out);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
 // Probe selection through the tensor-core shortlist; results identical to probe_select_device.
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
-                             const float* cnorm, int32_t* out_idx, float* out_scores) {
+                             const float* cnorm, int32_t* out_idx, float* out_scores, const float* cnorm_max_sqrt) {
     const int keff = nprobe < kc ? nprobe : kc;
     const int gcols = tc::choose_gcols(kc, keff);
     const int ngroups = tc::num_groups(kc, gcols);
@@ -770,8 +797,12 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     VIX_TRY(row_norms_device(q, nq, d, qn.ptr));
     const float* cn = cnorm;
     if (!cn) { VIX_TRY(cn_tmp.alloc((size_t)kc)); VIX_TRY(row_norms_device(c, kc, d, cn_tmp.ptr)); cn = cn_tmp.ptr; }
-    tc::max_sqrt_kernel<<<1, 256, 0, s>>>(cn, kc, cmax.ptr);
-    VIX_LAUNCH_CHECK();
+    const float* cmaxp = cnorm_max_sqrt;               // sqrt(max ||c||^2): cached by the index, else computed here
+    if (!cmaxp) {
+        tc::max_sqrt_kernel<<<1, 256, 0, s>>>(cn, kc, cmax.ptr);
+        VIX_LAUNCH_CHECK();
+        cmaxp = cmax.ptr;
+    }
 
     tc::Args a{};
     a.metric = metric; a.bnorm = (metric == VIX_METRIC_L2) ? cn : nullptr; a.error = flags.ptr; a.error_host = pipe_flag;
@@ -779,11 +810,7 @@ int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc,
     VIX_TRY(tc::launch(q, nq, c, kc, d, a));
     // |S~ - S|: dot error (2 * 2^-10 truncation + d * 2^-22 accumulation) * ||q|| ||c||, doubled for the L2 score
     const float rel = ((metric == VIX_METRIC_L2) ? 2.0f : 1.0f) * 1.25f * (2.0f / 1024.0f + (float)d / 4194304.0f);
-    {
-        int P = next_pow2(ngroups < 2 ? 2 : ngroups);
-        tc::threshold_kernel<<<(unsigned)nq, 256, (size_t)P * 4, s>>>(gmin.ptr, ngroups, P, keff, qn.ptr, cmax.ptr, rel, thr.ptr);
-        VIX_LAUNCH_CHECK();
-    }
+    VIX_TRY(tc::launch_threshold(gmin.ptr, nq, ngroups, keff, qn.ptr, cmaxp, rel, thr.ptr));
     a.mode = tc::MODE_EMIT; a.thr = thr.ptr; a.cand_cnt = cand_cnt.ptr; a.cand_idx = cand_idx.ptr; a.cap = cap;
     VIX_TRY(tc::launch(q, nq, c, kc, d, a));
     {
@@ -846,11 +873,7 @@ int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t
     a.mode = tc::MODE_MIN; a.gcols = gcols; a.ngroups = ngroups; a.gmin = gmin.ptr;
     VIX_TRY(tc::launch(q, nq, xb, nb, d, a));
     const float rel = ((metric == VIX_METRIC_L2) ? 2.0f : 1.0f) * 1.25f * (2.0f / 1024.0f + (float)d / 2097152.0f);
-    {
-        const int P = next_pow2(ngroups < 2 ? 2 : ngroups);
-        tc::threshold_kernel<<<(unsigned)nq, 256, (size_t)P * 4, s>>>(gmin.ptr, ngroups, P, keff, qn.ptr, xmax.ptr, rel, thr.ptr);
-        VIX_LAUNCH_CHECK();
-    }
+    VIX_TRY(tc::launch_threshold(gmin.ptr, nq, ngroups, keff, qn.ptr, xmax.ptr, rel, thr.ptr));
     a.mode = tc::MODE_EMIT; a.thr = thr.ptr; a.cand_cnt = cand_cnt.ptr; a.cand_idx = cand_idx.ptr; a.cap = cap;
     VIX_TRY(tc::launch(q, nq, xb, nb, d, a));
     {

@@ -50,7 +50,8 @@ int kmeans_parity_device(const float* x, int64_t n, int d, int kc, const float* 
 int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
                            const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
-                             const float* cnorm, int32_t* out_idx, float* out_scores);
+                             const float* cnorm, int32_t* out_idx, float* out_scores, const float* cnorm_max_sqrt);
+int max_sqrt_device(const float* x, int64_t n, float* out);
 
 // ------------------------------------------------------------------------------------------------
 // growable device buffer
@@ -94,6 +95,7 @@ struct vix_index {
     std::mutex mu;
     int kc = 0;                         // trained coarse centroids (nlist clamped to the training set)
     DevBuf<float> coarse, coarse_norms; // [kc x d], Norms.l2NormSquared per row
+    DevBuf<float> coarse_norm_max;      // [1] sqrt(max coarse_norms): error-bound scale of the tensor-core shortlist
     DevBuf<float> codebooks, cb_norms;  // [m x ks x dsub], [m x ks]
     bool has_coarse = false, has_pq = false;
     // rows in add order
@@ -569,7 +571,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             pp = const_cast<int32_t*>(gp.dev);
         } else {
             VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
-                                             h->coarse_norms.ptr, pp, nullptr));
+                                             h->coarse_norms.ptr, pp, nullptr, h->coarse_norm_max.ptr));
         }
         if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
         if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
@@ -717,6 +719,8 @@ int vix_index_set_coarse(vix_index_t* h, const float* centroids, int kc) {
     VIX_TRY(h->coarse.assign_from(centroids, (size_t)kc * h->p.d));
     VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
     VIX_TRY(row_norms_device(h->coarse.ptr, kc, h->p.d, h->coarse_norms.ptr));   // IVFIndex.swift:470-485
+    VIX_TRY(h->coarse_norm_max.resize(1, false));
+    VIX_TRY(max_sqrt_device(h->coarse_norms.ptr, kc, h->coarse_norm_max.ptr));
     h->has_coarse = true;
     h->dirty = true;
     return finish(true);
@@ -784,6 +788,8 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
     h->kc = kc;
     VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
     VIX_TRY(row_norms_device(h->coarse.ptr, kc, d, h->coarse_norms.ptr));
+    VIX_TRY(h->coarse_norm_max.resize(1, false));
+    VIX_TRY(max_sqrt_device(h->coarse_norms.ptr, kc, h->coarse_norm_max.ptr));
     h->has_coarse = true;
     if (h->p.kind == VIX_INDEX_IVF_PQ) {
         Scratch<int32_t> asg;
@@ -953,7 +959,7 @@ int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int 
     VIX_TRY(di.stage(list_ids_out, (size_t)nq * nprobe));
     VIX_TRY(ds.stage(list_scores_out, list_scores_out ? (size_t)nq * nprobe : 0));
     VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr + (size_t)list_begin * d, list_count, d, h->p.metric, nprobe,
-                                     h->coarse_norms.ptr + list_begin, di.dev, ds.dev));
+                                     h->coarse_norms.ptr + list_begin, di.dev, ds.dev, h->coarse_norm_max.ptr));
     if (list_begin > 0) {
         const int64_t total = nq * (int64_t)nprobe;
         offset_ids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(di.dev, total, list_begin);
@@ -1044,7 +1050,7 @@ int vix_index_probe_range_keys(vix_index_t* h, const float* queries, int64_t nq,
     VIX_TRY(ids.alloc((size_t)total));
     VIX_TRY(sc.alloc((size_t)total));
     VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr + (size_t)list_begin * d, list_count, d, h->p.metric, nprobe,
-                                     h->coarse_norms.ptr + list_begin, ids.ptr, sc.ptr));
+                                     h->coarse_norms.ptr + list_begin, ids.ptr, sc.ptr, h->coarse_norm_max.ptr));
     if (list_begin > 0) {
         offset_ids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(ids.ptr, total, list_begin);
         VIX_LAUNCH_CHECK();

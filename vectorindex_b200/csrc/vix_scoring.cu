@@ -237,7 +237,7 @@ __global__ void merge_keys_kernel(const u64* __restrict__ keys, int nin, int P2,
 }
 
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
-                             const float* cnorm, int32_t* out_idx, float* out_scores);
+                             const float* cnorm, int32_t* out_idx, float* out_scores, const float* cnorm_max_sqrt);
 
 int ivf_assign_auto_device(const float* x, int64_t n, int d, const float* c, int kc, int32_t* assign, float* dist);
 
@@ -864,7 +864,7 @@ int vix_ivf_select_nprobe_batch_f32(const float* Q, int64_t b, int d, const floa
         else { VIX_TRY(cn.alloc((size_t)kc)); VIX_TRY(row_norms_device(dc.dev, kc, d, cn.ptr)); cnp = cn.ptr; }
     }
     // no list mask: tensor-core shortlist + exact rescoring (vix_gemm.cu; identical results); else the exact kernel
-    if (dmask.dev == nullptr) VIX_TRY(probe_select_fast_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dids.dev, dsc.dev));
+    if (dmask.dev == nullptr) VIX_TRY(probe_select_fast_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dids.dev, dsc.dev, nullptr));
     else VIX_TRY(probe_select_device(dq.dev, b, dc.dev, kc, d, metric, nprobe, cnp, dmask.dev, dids.dev, dsc.dev));
     VIX_TRY(dids.commit());
     VIX_TRY(dsc.commit());
