@@ -68,6 +68,7 @@ int         vix_device_count(void);
 int         vix_set_device(int device);      /* cudaSetDevice for the calling thread               */
 int         vix_set_stream(void* cuda_stream);  /* thread-local stream (NULL = legacy default)     */
 int         vix_set_async(int enabled);      /* 1: do not synchronise when all outputs are device ptrs */
+int         vix_get_async(void);             /* the calling thread's current setting (0 / 1)        */
 int         vix_synchronize(void);           /* wait for the calling thread's stream               */
 int64_t     vix_kernel_launches(int reset);  /* kernels launched by this thread (bench bookkeeping) */
 

@@ -80,7 +80,7 @@ _LIB = None
 
 # symbol -> (restype, is_status)
 _EXPORTS = [
-    "vix_version", "vix_last_error", "vix_clear_error", "vix_device_count", "vix_set_device", "vix_set_stream", "vix_set_async",
+    "vix_version", "vix_last_error", "vix_clear_error", "vix_device_count", "vix_set_device", "vix_set_stream", "vix_set_async", "vix_get_async",
     "vix_synchronize", "vix_kernel_launches",
     "vix_l2sqr_f32_block", "vix_ip_f32_block", "vix_row_norms_f32", "vix_flat_search_f32", "vix_select_topk_f32",
     "vix_merge_topk_f32", "vix_rerank_exact_topk_f32", "vix_centroid_batch_score_f32", "vix_ivf_select_nprobe_batch_f32", "vix_ivf_assign_f32",

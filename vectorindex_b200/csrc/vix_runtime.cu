@@ -140,6 +140,8 @@ int vix_set_async(int enabled) {
     return VIX_OK;
 }
 
+int vix_get_async(void) { return ctx().async ? 1 : 0; }
+
 int vix_synchronize(void) {
     VIX_CUDA(cudaStreamSynchronize(ctx().stream));
     return VIX_OK;

@@ -502,14 +502,21 @@ class ShardedIVFPQIndex:
         mark("start")
         if self.world > 1 and self._nccl() and hasattr(self.local, "probe_range_keys"):
             # device path: two all-gathers of packed 8-byte records, merges straight from the gathered layout
-            begin, count = list_block(self.kc, self.rank, self.world)
-            pk = self._all_gather(self.local.probe_range_keys(queries, nprobe, begin, count))
-            probes = merge_probe_keys(pk)
-            mark("probe_range+gather+merge")
-            rk = self.local.search_with_probes_keys(queries, k, probes)
-            mark("scan")
-            md, mi = merge_result_keys(self._all_gather(rk))
-            mark("gather+merge")
+            # every intermediate lives on the device and the stages are ordered by the stream, so the library calls
+            # need not synchronise one by one (the copy of the merged result to the host, below, does it once)
+            was_async = lib().vix_get_async()
+            lib().vix_set_async(1)
+            try:
+                begin, count = list_block(self.kc, self.rank, self.world)
+                pk = self._all_gather(self.local.probe_range_keys(queries, nprobe, begin, count))
+                probes = merge_probe_keys(pk)
+                mark("probe_range+gather+merge")
+                rk = self.local.search_with_probes_keys(queries, k, probes)
+                mark("scan")
+                md, mi = merge_result_keys(self._all_gather(rk))
+                mark("gather+merge")
+            finally:
+                lib().vix_set_async(was_async)
             if marks:
                 torch.cuda.synchronize()
                 for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
