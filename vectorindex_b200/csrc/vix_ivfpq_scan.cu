@@ -100,6 +100,28 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
+// per-probe term of the decomposition, ||q - c_l||^2 (L2) or <q, c_l> (IP), batch-wide: one warp per (query, probe) whose
+// list holds vectors here.  Used when d is large: inside the scan kernel ONE warp per CTA computes these terms for the
+// next query while the others scan, which stops being free once d x nprobe outgrows a query's scan time.
+__global__ void __launch_bounds__(256)
+probe_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
+                  const int32_t* __restrict__ list_len, int64_t npairs, int nprobe, int d, int order_max,
+                  float* __restrict__ bias) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= npairs) return;
+    const int l = probes[w];
+    float part = 0.0f;
+    if (l >= 0 && __ldg(list_len + l) > 0) {
+        const float* q = queries + (w / nprobe) * (int64_t)d;
+        const float* c = coarse + (int64_t)l * d;
+        if (order_max) for (int e = lane; e < d; e += 32) part = fmaf(__ldg(q + e), __ldg(c + e), part);
+        else for (int e = lane; e < d; e += 32) { const float df = __ldg(q + e) - __ldg(c + e); part = fmaf(df, df, part); }
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if (lane == 0) bias[w] = part;
+}
+
 // k-th smallest (0-based rank kth) of one 32-bit key per lane: bitonic network over the warp
 __device__ VIX_SCAN_FN uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
 #pragma unroll
@@ -183,17 +205,20 @@ __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int
 //     over them);
 //   * the per-probe term of the decomposition, ||q - c_l||^2 (L2) or <q, c_l> (IP), for those lists.
 __device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d, const float* __restrict__ coarse,
-                                               int order_max, const int32_t* __restrict__ qprobes, int nprobe,
+                                               int order_max, const int32_t* __restrict__ qprobes,
+                                               const float* __restrict__ qbias, int nprobe,
                                                const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
                                                int* s_start, int* s_len, int* s_pref, float* s_bias, int* s_np,
                                                float* s_q) {
     const int lane = threadIdx.x & 31;
     int lv[8], lenv[8];
     int64_t offv[8];
+    float bv[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int p = 32 * it + lane;
         lv[it] = (p < nprobe) ? __ldg(qprobes + p) : -1;
+        bv[it] = (qbias && p < nprobe) ? __ldg(qbias + p) : 0.0f;
     }
     for (int e = lane; e < d; e += 32) s_q[e] = __ldg(q + e);
 #pragma unroll
@@ -213,7 +238,7 @@ __device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d
             if (nch > 0) {
                 const int p = np + __popc(ball & ((1u << lane) - 1u));
                 s_start[p] = (int)(offv[it] >> 5); s_len[p] = lenv[it]; s_pref[p] = carry + inc - nch;
-                s_list[p] = lv[it];
+                if (qbias) s_bias[p] = bv[it]; else s_list[p] = lv[it];
             }
             np += __popc(ball);
             carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
@@ -221,6 +246,7 @@ __device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d
     }
     if (lane == 0) { s_pref[np] = carry; *s_np = np; }
     __syncwarp();
+    if (qbias) return;                                     // precomputed batch-wide (probe_bias_kernel)
     // bias: lane-strided partial sums, xor-tree across the warp; four lists in flight
     for (int p0 = 0; p0 < np; p0 += 4) {
         float part[4];
@@ -407,8 +433,9 @@ ivfpq_scan_kernel(ScanArgs a) {
         const int64_t qn = a.order ? a.order[item] : item;
         int* pt = s_pt + b * pt_words;
         build_probe_table(a.queries + qn * (int64_t)a.d, a.d, a.coarse, order_max, a.probes + qn * (int64_t)a.nprobe,
-                          a.nprobe, a.list_off, a.list_len, pt + a.nprobe, pt + 2 * a.nprobe, pt + 3 * a.nprobe,
-                          reinterpret_cast<float*>(pt), s_np + b, s_qv + b * a.d);
+                          a.bias ? a.bias + qn * (int64_t)a.nprobe : nullptr, a.nprobe, a.list_off, a.list_len,
+                          pt + a.nprobe, pt + 2 * a.nprobe, pt + 3 * a.nprobe, reinterpret_cast<float*>(pt), s_np + b,
+                          s_qv + b * a.d);
     };
 
     if (tid == 32) { s_item[0] = atomicAdd(a.work_counter, 1); s_ncand[0] = 0; s_ncand[1] = 0; }
@@ -852,6 +879,16 @@ int launch_ivfpq_scan(ScanArgs& a) {
     VIX_REQUIRE(a.work_counter != nullptr, VIX_ERR_NULL_PTR, "ivfpq scan: work counter missing");
     VIX_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int), ctx().stream));
     a.status = a.work_counter + 1;
+    Scratch<float> bias;
+    if ((int64_t)a.d * a.nprobe > 8192) {
+        // one staging warp per CTA cannot hide this much bias arithmetic behind a query's scan: do it batch-wide
+        const int64_t npairs = a.nq * (int64_t)a.nprobe;
+        VIX_TRY(bias.alloc((size_t)npairs));
+        probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
+            a.queries, a.probes, a.coarse, a.list_len, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
+        VIX_LAUNCH_CHECK();
+        a.bias = bias.ptr;
+    }
     switch (a.m) {
         case 16: return a.filter ? launch_fast<1, true>(a) : launch_fast<1, false>(a);
         case 32: return a.filter ? launch_fast<2, true>(a) : launch_fast<2, false>(a);

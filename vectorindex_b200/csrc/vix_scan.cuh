@@ -14,6 +14,7 @@ struct ScanArgs {
     int* status;                                  // set by the launcher (= work_counter + 1)
     int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
     const float* coarse;                          // [kc x d]
+    const float* bias;                            // optional [nq x nprobe]: the per-probe term, precomputed batch-wide (large d)
     const float* codebooks;                       // [m x ks x dsub]
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
     const int64_t* list_off; const int32_t* list_len;
