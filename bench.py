@@ -323,8 +323,8 @@ def main():
 
     base_cfg = {"workload": cfg["label"], "n": cfg["n"], "d": d, "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
                 "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": cfg.get("metric", "euclidean"),
-                "partition": f"inverted lists in contiguous blocks over {eff_world} rank(s) (coarse scoring sharded the same way); "
-                             "queries replicated; probe lists and top-k merged by all-gather + mergeTopK",
+                "partition": f"inverted lists in contiguous blocks over {eff_world} rank(s); queries replicated; probe selection "
+                             "split by query block + all-gather of list ids; per-rank top-k merged by all-gather + mergeTopK",
                 "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps",
                 "build": build_t}
 

@@ -134,6 +134,19 @@ def test_list_block_partition_covers_all_lists():
             assert (owner[b:b + c] == r).all()
 
 
+def test_query_block_partition_covers_the_batch():
+    from vectorindex_b200.index import ShardedIVFPQIndex
+    for nq, world in ((10000, 8), (25, 2), (2, 3), (1, 8), (0, 4), (7, 7)):
+        seen = []
+        for r in range(world):
+            sh = ShardedIVFPQIndex.__new__(ShardedIVFPQIndex)
+            sh.rank, sh.world = r, world
+            lo, cnt, per = sh.query_block(nq)
+            assert 0 <= cnt <= per and per * world >= nq
+            seen += list(range(lo, lo + cnt))
+        assert seen == list(range(nq))
+
+
 def test_sharded_search_equals_single_process_oracle(tmp_path, oracle):
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.npz")

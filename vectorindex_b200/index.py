@@ -381,10 +381,11 @@ class ShardedIVFPQIndex:
 
     build   any rank assigns + encodes whatever rows it is handed (``add``); rows travel to the rank that
             owns their list with one all-to-all and are appended there already encoded;
-    search  each rank scores only its block of centroids (local top-nprobe) -> all-gather + mergeTopK give
-            the global probe lists, identical on every rank and identical to the single-GPU order
-            (IVFIndex.swift:593-595) -> each rank scans the probed lists it owns -> all-gather + mergeTopK of
-            the per-rank [nq x k] results (TopKMerge.swift:11-61).
+    search  each rank selects the probes of ITS block of queries against all centroids (the single-GPU code path:
+            IVFIndex.swift:593-595 order by construction) -> all-gather of list ids = the global probe lists of
+            the whole batch on every rank -> each rank scans the probed lists it owns -> all-gather + mergeTopK of
+            the per-rank [nq x k] results (TopKMerge.swift:11-61).  (probe_range over a centroid BLOCK + merge of
+            per-block candidates remains available for hosts that shard the centroids instead.)
 
     ``local`` may be any object with probe_range / search_with_probes / encode / add_encoded / set_coarse /
     set_codebooks (the gloo tests plug in an oracle-backed one, the product path an ``IVFPQIndex``)."""
@@ -428,6 +429,10 @@ class ShardedIVFPQIndex:
             a = a.to(torch.device("cuda", torch.cuda.current_device()))
         return a.contiguous()
 
+    def _comm_device(self):
+        import torch
+        return torch.device("cuda", torch.cuda.current_device()) if self._nccl() else torch.device("cpu")
+
     def _all_gather(self, t):
         import torch
         import torch.distributed as dist
@@ -466,22 +471,33 @@ class ShardedIVFPQIndex:
             self.local.add_encoded(r_assign, r_codes, r_ids)
 
     # ---- search
+    def query_block(self, nq: int):
+        """Rows of the batch whose probe lists THIS rank computes: (first row, rows, rows per rank)."""
+        per = (nq + self.world - 1) // self.world
+        lo = min(nq, self.rank * per)
+        return lo, min(nq, lo + per) - lo, per
+
     def global_probes(self, queries, nprobe=0):
-        """The global probe lists [nq x nprobe] (int32), identical on every rank."""
+        """The global probe lists [nq x nprobe] (int32), identical on every rank.  Probe selection is partitioned by
+        QUERY: every rank holds all coarse centroids (25 MB at nlist = 65536), selects the probes of its 1/world of
+        the batch against all of them -- the very code path of a single GPU, so the lists are identical to it by
+        construction -- and one all-gather of int32 list ids (nq x nprobe x 4 bytes in total) hands every rank the
+        lists of the whole batch.  No merge step, a sixteenth of the bytes of exchanging per-block candidates."""
         import torch
         nprobe = nprobe if nprobe > 0 else self.nprobe
-        begin, count = list_block(self.kc, self.rank, self.world)
-        ids, sc = self.local.probe_range(queries, nprobe, begin, count)
+        nq = int(queries.shape[0])
         if self.world == 1:
-            return ids
-        ids_all = self._all_gather(self._to_comm(ids).to(torch.int64))
-        sc_all = self._all_gather(self._to_comm(sc))
-        if sc_all.is_cuda:
-            _, mi = merge_shard_results(sc_all, ids_all, nprobe)
+            return self.local.probe_range(queries, nprobe, 0, self.kc)[0]
+        lo, cnt, per = self.query_block(nq)
+        if cnt > 0:
+            ids = self._to_comm(self.local.probe_range(queries[lo:lo + cnt], nprobe, 0, self.kc)[0]).to(torch.int32)
+        if cnt == per:
+            buf = ids
         else:
-            _, mi = merge_shard_results_host(sc_all.numpy(), ids_all.numpy(), nprobe)
-            mi = torch.from_numpy(mi)
-        return mi.to(torch.int32).contiguous()
+            buf = torch.full((per, nprobe), -1, dtype=torch.int32, device=self._comm_device())
+            if cnt > 0:
+                buf[:cnt] = ids
+        return self._all_gather(buf).view(self.world * per, nprobe)[:nq].contiguous()
 
     def batch_search(self, queries, k, nprobe=0):
         """Replicated queries in, merged [nq x k] (distances, ids) out on every rank.  Host (numpy) queries are
@@ -501,16 +517,15 @@ class ShardedIVFPQIndex:
 
         mark("start")
         if self.world > 1 and self._nccl() and hasattr(self.local, "probe_range_keys"):
-            # device path: two all-gathers of packed 8-byte records, merges straight from the gathered layout
+            # device path: probe lists by query block + one all-gather of list ids; local top-k as packed 8-byte records,
+            # one all-gather, merge straight from the gathered layout
             # every intermediate lives on the device and the stages are ordered by the stream, so the library calls
             # need not synchronise one by one (the copy of the merged result to the host, below, does it once)
             was_async = lib().vix_get_async()
             lib().vix_set_async(1)
             try:
-                begin, count = list_block(self.kc, self.rank, self.world)
-                pk = self._all_gather(self.local.probe_range_keys(queries, nprobe, begin, count))
-                probes = merge_probe_keys(pk)
-                mark("probe_range+gather+merge")
+                probes = self.global_probes(queries, nprobe)
+                mark("probe_select+gather")
                 rk = self.local.search_with_probes_keys(queries, k, probes)
                 mark("scan")
                 md, mi = merge_result_keys(self._all_gather(rk))
@@ -525,7 +540,7 @@ class ShardedIVFPQIndex:
                 md, mi = md.cpu().numpy(), mi.cpu().numpy()
             return md, mi
         probes = self.global_probes(queries, nprobe)
-        mark("probe_range+gather+merge")
+        mark("probe_select+gather")
         if not self._nccl() and _lib._is_torch(probes):
             probes = probes.numpy()
         d_loc, i_loc = self.local.search_with_probes(queries, k, probes)
