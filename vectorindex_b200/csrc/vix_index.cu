@@ -615,7 +615,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             VIX_CUDA(cudaMemcpyAsync(sc4, scanned.ptr, 128, cudaMemcpyDeviceToHost, s));
             VIX_CUDA(cudaStreamSynchronize(s));
 #ifdef VIX_SCAN_DIAG
-            fprintf(stderr, "[vix diag] chunks %llu, queue flushes %llu, chunks with a passing entry %llu\n", sc4[9], sc4[10], sc4[11]);
+            fprintf(stderr, "[vix diag] chunks %llu, queue flushes %llu, chunks with a passing entry %llu, barrier wait summed over warps %llu cycles\n",
+                    sc4[9], sc4[10], sc4[11], sc4[12]);
 #endif
             const unsigned long long sc = sc4[0];
             stats->codes_scanned = (int64_t)sc;

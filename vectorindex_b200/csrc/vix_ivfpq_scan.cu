@@ -499,13 +499,13 @@ ivfpq_scan_kernel(ScanArgs a) {
         uint32_t thr_u = 0xFFFFFFFFu;
         int p = 0;
         uint4 wA[G], wB[G];
-        // Chunks are handed out CTA-wide in runs of 4, 2 and, near the end, 1 (so the warps finish together).  A warp
-        // owns its current run [ch, grab_end) and has already taken the next one [nx_c, nx_end).  (Measured and
-        // dropped: prefetch.global.L2 of the next run -- 7 % slower; of just the next chunk -- no gain; stepping
-        // through a run with pointer increments instead of re-locating every chunk -- fewer instructions, yet 7 %
-        // slower.)
-        int grab_end = warp * kGrab + kGrab, nx_c = 0, nx_end = 0;
-        auto take_run = [&]() {
+        // Chunks are handed out CTA-wide in runs of 4, 2 and, near the end, 1 (so the warps finish together); a warp
+        // takes its next run when the current one [ch, grab_end) is used up.  (Measured and dropped: taking a run ahead
+        // and prefetch.global.L2-ing it -- 7 % slower; L2 prefetch of just the next chunk -- no gain; stepping through a
+        // run with pointer increments instead of re-locating every chunk -- fewer instructions, yet 7 % slower.)
+        int grab_end = warp * kGrab + kGrab;
+        auto grab = [&](int prev) {
+            if (prev + 1 < grab_end) return prev + 1;
             int c = 0, g = 0;
             if (lane == 0) {
 #if VIX_SCAN_GUIDED
@@ -516,18 +516,11 @@ ivfpq_scan_kernel(ScanArgs a) {
 #endif
                 c = atomicAdd(s_next, g);
             }
-            nx_c = __shfl_sync(0xFFFFFFFFu, c, 0);
-            nx_end = nx_c + __shfl_sync(0xFFFFFFFFu, g, 0);
-        };
-        auto grab = [&](int prev) {
-            if (prev + 1 < grab_end) return prev + 1;
-            const int c = nx_c;
-            grab_end = nx_end;
-            take_run();
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            grab_end = c + __shfl_sync(0xFFFFFFFFu, g, 0);
             return c;
         };
         int ch = warp * kGrab;
-        take_run();
         // the probe the warp is in is cached in registers: chunk range [pb, pe), first slot / 32, length, bias
         int pb = 0, pe = 0, pstart = 0, plen = 0;
         float pbias = 0.0f;
@@ -687,6 +680,9 @@ ivfpq_scan_kernel(ScanArgs a) {
         atomicAdd(a.phase_cycles + 9, (diag >> 24) & 0xFFFFFull);
         atomicAdd(a.phase_cycles + 10, diag >> 44);
     }
+#endif
+#ifdef VIX_SCAN_DIAG
+    if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 11, cyc_tail);    // barrier wait summed over ALL warps
 #endif
     if (a.phase_cycles && tid == 64) {                     // one scanning warp per CTA reports its phase split
         atomicAdd(a.phase_cycles + 0, cyc_pro);
