@@ -31,6 +31,8 @@
 // the next query's table.  No distance array ever reaches HBM.  Queries are handed out by an atomic
 // counter in an order sorted by first probed list, so CTAs running concurrently scan neighbouring lists
 // and share them through L2.
+#include <stdlib.h>
+
 #include "vix_common.cuh"
 #include "vix_topk.cuh"
 #include "vix_scan.cuh"
@@ -356,6 +358,87 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
     }
 }
 
+// the table was built batch-wide (lut_image_kernel): copy its image with asynchronous 16-byte copies -- every piece of
+// a thread is in flight at once and none of them holds a register
+__device__ VIX_SCAN_FN void copy_lut_image(float* __restrict__ s_lut, const float* __restrict__ image, int n4, int t, int nthr) {
+    const float4* src = reinterpret_cast<const float4*>(image);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lut);
+    for (int i = t; i < n4; i += nthr)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i));
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// The same tables for a whole batch, written to global memory as images of the scan's shared-memory layout
+// ([query][table][code][64 slots], both replicas).  Building a table inside the scan kernel re-reads the codebooks
+// (m x 256 x dsub floats) from L2 once per query and CTA: at dsub = 12, m = 64 that is 786 KB per query against 64 KB of
+// table -- five times the bytes of the scan itself on a one-eighth shard.  Here a CTA takes one group of 16
+// sub-quantisers and kImgQT queries; thread = code.  Codebook vectors come through a shared tile (four sub-quantisers at
+// a time, coalesced reads, odd row pitch) and are used by all kImgQT queries; results are staged in shared memory and
+// leave as full 128-byte lines (16 sub-quantisers x 2 replicas per code).  Same operation order as build_lut (query
+// pre-scaled, ascending fused multiply-adds), so both paths give the same bits.
+constexpr int kImgQT = 4;       // queries per CTA
+constexpr int kImgTJ = 4;       // sub-quantisers per codebook tile
+static size_t lut_image_smem(int dsub) {
+    return ((size_t)256 * (kImgTJ * dsub + 1) + (size_t)kImgQT * 256 * 20 + (size_t)kImgQT * 16 * dsub) * 4;
+}
+template <int M>
+__global__ void __launch_bounds__(256)
+lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const float* __restrict__ codebooks_t, int dsub,
+                 float lut_scale, float* __restrict__ image) {
+    constexpr int NTAB = (M / 16 + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_img[];
+    const int pitch = kImgTJ * dsub + 1;                   // odd: thread c walking row c is conflict-free
+    float* tile = reinterpret_cast<float*>(smem_img);      // [256][pitch]
+    float* outs = tile + 256 * pitch;                      // [kImgQT][256][20]: 16 results + 4 pad (conflict-free 128-bit stores)
+    float* s_q = outs + kImgQT * 256 * 20;                 // [kImgQT][16 * dsub], pre-scaled
+    const int t16 = blockIdx.y;                            // group of 16 sub-quantisers
+    const int64_t q0 = (int64_t)blockIdx.x * kImgQT;
+    const int c = threadIdx.x;                             // code
+    for (int i = threadIdx.x; i < kImgQT * 16 * dsub; i += blockDim.x) {
+        const int qi = i / (16 * dsub), e = i - qi * 16 * dsub;
+        s_q[i] = (q0 + qi < nq) ? __ldg(queries + (q0 + qi) * d + t16 * 16 * dsub + e) * lut_scale : 0.0f;
+    }
+    const int row_f = kImgTJ * dsub;                       // floats of one code in a tile
+    for (int jj = 0; jj < 16 / kImgTJ; ++jj) {
+        __syncthreads();                                   // the previous tile has been used (and s_q is ready)
+        for (int i = threadIdx.x; i < 256 * row_f; i += blockDim.x) {
+            const int r = i / row_f, e = i - r * row_f;
+            tile[r * pitch + e] = __ldg(codebooks_t + ((size_t)r * M + t16 * 16 + jj * kImgTJ) * dsub + e);
+        }
+        __syncthreads();
+        float res[kImgQT][kImgTJ];
+#pragma unroll
+        for (int j4 = 0; j4 < kImgTJ; ++j4) {
+            float dot[kImgQT];
+#pragma unroll
+            for (int qi = 0; qi < kImgQT; ++qi) dot[qi] = 0.0f;
+            for (int e = 0; e < dsub; ++e) {
+                const float v = tile[c * pitch + j4 * dsub + e];
+#pragma unroll
+                for (int qi = 0; qi < kImgQT; ++qi) dot[qi] = fmaf(s_q[qi * 16 * dsub + (jj * kImgTJ + j4) * dsub + e], v, dot[qi]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < kImgQT; ++qi) res[qi][j4] = dot[qi];
+        }
+#pragma unroll
+        for (int qi = 0; qi < kImgQT; ++qi)
+            *reinterpret_cast<float4*>(outs + ((size_t)qi * 256 + c) * 20 + jj * kImgTJ) =
+                make_float4(res[qi][0], res[qi][1], res[qi][2], res[qi][3]);
+    }
+    __syncthreads();
+    // rows of 32 floats (replica A | replica B) per code: eight lanes write one full 128-byte line
+    for (int qi = 0; qi < kImgQT; ++qi) {
+        if (q0 + qi >= nq) break;
+        float* base = image + (size_t)(q0 + qi) * (NTAB * 16384) + (t16 >> 1) * 16384 + (t16 & 1) * 32;
+        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+            const int code = i >> 3, v = i & 7;
+            *reinterpret_cast<float4*>(base + code * 64 + v * 4) =
+                *reinterpret_cast<const float4*>(outs + ((size_t)qi * 256 + code) * 20 + (v & 3) * 4);
+        }
+    }
+}
+
 // one warp: sort the queue (k best first), refresh the thresholds
 __device__ __noinline__ uint32_t flush_queue(u64* wq, int Pw, int k, int cnt, bool sorted_valid, uint32_t thr_u, int* s_thr) {
     const int lane = threadIdx.x & 31;
@@ -467,7 +550,8 @@ ivfpq_scan_kernel(ScanArgs a) {
             if (tid == 32) { *cta_thr = 0xFFFFFFFFu; *s_next = nwarps * kGrab; }
             const long long t0 = clock64();
             if (nchunks > 0) {
-                build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, (int)blockDim.x);
+                if (a.lut_image) copy_lut_image(s_lut, a.lut_image + (size_t)qi * (NTAB * 16384), NTAB * 4096, tid, (int)blockDim.x);
+                else build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, (int)blockDim.x);
             }
             if (a.phase_cycles && tid == 64) atomicAdd(a.phase_cycles + 5, (unsigned long long)(clock64() - t0));
         }
@@ -884,6 +968,28 @@ int launch_ivfpq_scan(ScanArgs& a) {
             a.queries, a.probes, a.coarse, a.list_len, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
         VIX_LAUNCH_CHECK();
         a.bias = bias.ptr;
+    }
+    Scratch<float> image;
+    const size_t cb_bytes = (size_t)a.m * 256 * a.dsub * 4;
+    const size_t img_floats = (size_t)((a.m / 16 + 1) / 2) * 16384;
+    if (cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30) && !getenv("VIX_DISABLE_LUT_IMAGE")) {
+        // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan
+        VIX_TRY(image.alloc((size_t)a.nq * img_floats));
+        const dim3 grid((unsigned)((a.nq + kImgQT - 1) / kImgQT), (unsigned)(a.m / 16));
+        const float scale = a.metric == VIX_METRIC_IP ? 1.0f : -2.0f;
+        const size_t ismem = lut_image_smem(a.dsub);
+#define VIX_IMG(MM)                                                                                                    \
+        VIX_CUDA(cudaFuncSetAttribute(lut_image_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));  \
+        lut_image_kernel<MM><<<grid, 256, ismem, ctx().stream>>>(a.queries, a.nq, a.d, a.codebooks_t, a.dsub, scale, image.ptr)
+        switch (a.m) {
+            case 16: VIX_IMG(16); break;
+            case 32: VIX_IMG(32); break;
+            case 48: VIX_IMG(48); break;
+            case 64: VIX_IMG(64); break;
+        }
+#undef VIX_IMG
+        VIX_LAUNCH_CHECK();
+        a.lut_image = image.ptr;
     }
     switch (a.m) {
         case 16: return a.filter ? launch_fast<1, true>(a) : launch_fast<1, false>(a);
