@@ -374,13 +374,13 @@ __device__ VIX_SCAN_FN void copy_lut_image(float* __restrict__ s_lut, const floa
 // (m x 256 x dsub floats) from L2 once per query and CTA: at dsub = 12, m = 64 that is 786 KB per query against 64 KB of
 // table -- five times the bytes of the scan itself on a one-eighth shard.  Here a CTA takes one group of 16
 // sub-quantisers and kImgQT queries; thread = code.  Codebook vectors come through a shared tile (four sub-quantisers at
-// a time, coalesced reads, odd row pitch) and are used by all kImgQT queries; results are staged in shared memory and
-// leave as full 128-byte lines (16 sub-quantisers x 2 replicas per code).  Same operation order as build_lut (query
-// pre-scaled, ascending fused multiply-adds), so both paths give the same bits.
+// a time, coalesced 128-bit reads, odd row pitch) and are used by all kImgQT queries; a thread writes its code's
+// 16-byte pieces (four sub-quantisers, both replicas) straight to the image.  Same operation order as build_lut
+// (query pre-scaled, ascending fused multiply-adds), so both paths give the same bits.
 constexpr int kImgQT = 4;       // queries per CTA
 constexpr int kImgTJ = 4;       // sub-quantisers per codebook tile
 static size_t lut_image_smem(int dsub) {
-    return ((size_t)256 * (kImgTJ * dsub + 1) + (size_t)kImgQT * 256 * 20 + (size_t)kImgQT * 16 * dsub) * 4;
+    return ((size_t)256 * (kImgTJ * dsub + 1) + (size_t)kImgQT * 16 * dsub) * 4;
 }
 template <int M>
 __global__ void __launch_bounds__(256)
@@ -390,8 +390,7 @@ lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const flo
     extern __shared__ __align__(16) unsigned char smem_img[];
     const int pitch = kImgTJ * dsub + 1;                   // odd: thread c walking row c is conflict-free
     float* tile = reinterpret_cast<float*>(smem_img);      // [256][pitch]
-    float* outs = tile + 256 * pitch;                      // [kImgQT][256][20]: 16 results + 4 pad (conflict-free 128-bit stores)
-    float* s_q = outs + kImgQT * 256 * 20;                 // [kImgQT][16 * dsub], pre-scaled
+    float* s_q = tile + 256 * pitch;                       // [kImgQT][16 * dsub], pre-scaled
     const int t16 = blockIdx.y;                            // group of 16 sub-quantisers
     const int64_t q0 = (int64_t)blockIdx.x * kImgQT;
     const int c = threadIdx.x;                             // code
@@ -400,11 +399,24 @@ lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const flo
         s_q[i] = (q0 + qi < nq) ? __ldg(queries + (q0 + qi) * d + t16 * 16 * dsub + e) * lut_scale : 0.0f;
     }
     const int row_f = kImgTJ * dsub;                       // floats of one code in a tile
+    // this code's row of every query's image: [replica A: 16 sub-quantisers | replica B]
+    float* rowp = image + (size_t)q0 * (NTAB * 16384) + (t16 >> 1) * 16384 + c * 64 + (t16 & 1) * 32;
     for (int jj = 0; jj < 16 / kImgTJ; ++jj) {
         __syncthreads();                                   // the previous tile has been used (and s_q is ready)
-        for (int i = threadIdx.x; i < 256 * row_f; i += blockDim.x) {
-            const int r = i / row_f, e = i - r * row_f;
-            tile[r * pitch + e] = __ldg(codebooks_t + ((size_t)r * M + t16 * 16 + jj * kImgTJ) * dsub + e);
+        const float* src = codebooks_t + ((size_t)t16 * 16 + jj * kImgTJ) * dsub;
+        if ((dsub & 3) == 0) {
+            const int row4 = row_f >> 2;
+            for (int i = threadIdx.x; i < 256 * row4; i += blockDim.x) {
+                const int r = i / row4, p4 = i - r * row4;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * M * dsub) + p4);
+                float* dst = tile + r * pitch + 4 * p4;
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < 256 * row_f; i += blockDim.x) {
+                const int r = i / row_f, e = i - r * row_f;
+                tile[r * pitch + e] = __ldg(src + (size_t)r * M * dsub + e);
+            }
         }
         __syncthreads();
         float res[kImgQT][kImgTJ];
@@ -422,19 +434,13 @@ lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const flo
             for (int qi = 0; qi < kImgQT; ++qi) res[qi][j4] = dot[qi];
         }
 #pragma unroll
-        for (int qi = 0; qi < kImgQT; ++qi)
-            *reinterpret_cast<float4*>(outs + ((size_t)qi * 256 + c) * 20 + jj * kImgTJ) =
-                make_float4(res[qi][0], res[qi][1], res[qi][2], res[qi][3]);
-    }
-    __syncthreads();
-    // rows of 32 floats (replica A | replica B) per code: eight lanes write one full 128-byte line
-    for (int qi = 0; qi < kImgQT; ++qi) {
-        if (q0 + qi >= nq) break;
-        float* base = image + (size_t)(q0 + qi) * (NTAB * 16384) + (t16 >> 1) * 16384 + (t16 & 1) * 32;
-        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-            const int code = i >> 3, v = i & 7;
-            *reinterpret_cast<float4*>(base + code * 64 + v * 4) =
-                *reinterpret_cast<const float4*>(outs + ((size_t)qi * 256 + code) * 20 + (v & 3) * 4);
+        for (int qi = 0; qi < kImgQT; ++qi) {
+            if (q0 + qi < nq) {
+                const float4 v = make_float4(res[qi][0], res[qi][1], res[qi][2], res[qi][3]);
+                float4* dst = reinterpret_cast<float4*>(rowp + (size_t)qi * (NTAB * 16384) + jj * kImgTJ);
+                dst[0] = v;                                // replica A
+                dst[4] = v;                                // replica B (16 floats further on)
+            }
         }
     }
 }
@@ -972,8 +978,11 @@ int launch_ivfpq_scan(ScanArgs& a) {
     Scratch<float> image;
     const size_t cb_bytes = (size_t)a.m * 256 * a.dsub * 4;
     const size_t img_floats = (size_t)((a.m / 16 + 1) / 2) * 16384;
-    if (cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30) && !getenv("VIX_DISABLE_LUT_IMAGE")) {
-        // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan
+    const char* img_env = getenv("VIX_LUT_IMAGE");
+    if (img_env && img_env[0] == '1' && cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30)) {
+        // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan.
+        // OPT-IN (VIX_LUT_IMAGE=1): at C4 it cuts the table's share of a query from 31 k to 2.9 k cycles, but the batch
+        // kernel itself (1.2 ms: scattered 16-byte stores) still costs what that saves (1.1 ms) -- measured, see DESIGN.md
         VIX_TRY(image.alloc((size_t)a.nq * img_floats));
         const dim3 grid((unsigned)((a.nq + kImgQT - 1) / kImgQT), (unsigned)(a.m / 16));
         const float scale = a.metric == VIX_METRIC_IP ? 1.0f : -2.0f;
