@@ -426,8 +426,25 @@ class ShardedIVFPQIndex:
         if not _lib._is_torch(a):
             a = torch.from_numpy(np.ascontiguousarray(a))
         if self._nccl() and not a.is_cuda:
-            a = a.to(torch.device("cuda", torch.cuda.current_device()))
+            # stream-ordered copy: with a pinned source the host does not wait for it (everything that reads the tensor is
+            # enqueued behind it on the same stream); pageable sources are staged by torch and stay safe
+            a = a.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=a.is_pinned())
         return a.contiguous()
+
+    def _to_host(self, t):
+        """device tensor -> numpy array through a pinned staging buffer kept with the index (one D2H at full PCIe rate,
+        one wait), copied out so that the caller owns the result"""
+        import torch
+        pins = self.__dict__.setdefault("_pins", {})
+        key = (t.dtype, tuple(t.shape))
+        buf = pins.get(key)
+        if buf is None:
+            if len(pins) > 8:
+                pins.clear()
+            buf = pins[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return buf.numpy().copy()
 
     def _comm_device(self):
         import torch
@@ -537,7 +554,7 @@ class ShardedIVFPQIndex:
                 for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                     self.phase_times[name] = self.phase_times.get(name, 0.0) + a.elapsed_time(b)
             if was_numpy:
-                md, mi = md.cpu().numpy(), mi.cpu().numpy()
+                md, mi = self._to_host(md), self._to_host(mi)
             return md, mi
         probes = self.global_probes(queries, nprobe)
         mark("probe_select+gather")
