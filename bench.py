@@ -189,6 +189,19 @@ def build_index(cfg, synth, rank, world, bcast=None):
             idx.set_coarse(coarse)
             idx.set_codebooks(cb, cn)
         sh = ShardedIVFPQIndex.wrap(idx, nlist, cfg["nprobe"])
+        # list-block boundaries that equalise the ranks' expected scan work (sum of squared list lengths), from the list
+        # sizes of a sample: rank 0 assigns its training chunk, every rank gets the boundaries
+        from vectorindex_b200.index import balanced_list_bounds
+        bounds = torch.zeros(world + 1, dtype=torch.int64, device=synth.dev)
+        if rank == 0:
+            sample = synth.rows(0, min(n, 2_000_000))
+            asg = vk.ivf_assign_f32(sample, coarse) if cfg.get("metric") != "dotProduct" else \
+                vk.ivf_assign_metric_f32(sample, coarse, 1, None)
+            counts = torch.bincount(asg.to(torch.int64), minlength=nlist).cpu().numpy()
+            bounds.copy_(torch.from_numpy(balanced_list_bounds(counts, world)))
+            del sample, asg
+        bcast(bounds)
+        sh.set_list_bounds(bounds.cpu().numpy())
     torch.cuda.synchronize()
     t_train = time.time() - t0
 

@@ -98,13 +98,15 @@ def _worker(rank, world, port, out_path):
         nprobe, k = 5, 10
         sh = ShardedIVFPQIndex(xb.shape[1], "euclidean", nlist=kc, nprobe=nprobe, m=m, local=OracleLocalIndex(xb.shape[1], m))
         sh.set_parameters(coarse, cb, norms)
+        from vectorindex_b200.index import balanced_list_bounds
+        sh.set_list_bounds(balanced_list_bounds(np.bincount(asg, minlength=kc), world))
         # every rank hands in a different slice of the database, in two batches
         ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
         mine = np.arange(rank, xb.shape[0], world)
         half = mine.size // 2
         sh.add(xb[mine[:half]], ids[mine[:half]])
         sh.add(xb[mine[half:]], ids[mine[half:]])
-        b, c = list_block(kc, rank, world)
+        b, c = list_block(kc, rank, world, sh.bounds)
         held = sh.local.assign
         assert ((held >= b) & (held < b + c)).all()                       # only owned lists arrived here
         assert held.size == int(((asg >= b) & (asg < b + c)).sum())       # and all of their rows did
@@ -132,6 +134,25 @@ def test_list_block_partition_covers_all_lists():
         owner = list_owner(np.arange(kc), kc, world)
         for r, (b, c) in enumerate(blocks):
             assert (owner[b:b + c] == r).all()
+
+
+def test_balanced_list_bounds():
+    import torch
+    from vectorindex_b200.index import balanced_list_bounds, list_block, list_owner
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(0, 3000, 4096)
+    for world in (2, 3, 8):
+        b = balanced_list_bounds(sizes, world)
+        assert b[0] == 0 and b[-1] == sizes.size and (np.diff(b) >= 0).all() and b.size == world + 1
+        work = np.array([float((sizes[b[r]:b[r + 1]].astype(np.float64) ** 2).sum()) for r in range(world)])
+        assert work.max() / work.mean() < 1.01                       # equal-count blocks: several per cent
+        ids = np.arange(sizes.size)
+        own = list_owner(ids, sizes.size, world, b)
+        assert np.array_equal(own, list_owner(torch.from_numpy(ids), sizes.size, world, b).numpy())
+        for r in range(world):
+            lo, cnt = list_block(sizes.size, r, world, b)
+            assert (own[lo:lo + cnt] == r).all() and (own == r).sum() == cnt
+    assert np.array_equal(balanced_list_bounds(np.zeros(10), 4)[[0, -1]], [0, 10])
 
 
 def test_query_block_partition_covers_the_batch():

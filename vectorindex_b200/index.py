@@ -308,18 +308,40 @@ class IVFPQIndex(IVFIndex):
 # ------------------------------------------------------------------------------------------------
 # multi-GPU
 # ------------------------------------------------------------------------------------------------
-def list_block(kc: int, rank: int, world: int):
+def list_block(kc: int, rank: int, world: int, bounds=None):
     """Contiguous block of inverted lists owned by ``rank``: (first list, number of lists).  Lists are disjoint
-    (IVFIndex.swift:370-375), so they shard without any data-path dependency between ranks."""
+    (IVFIndex.swift:370-375), so they shard without any data-path dependency between ranks.  ``bounds`` ([world + 1]
+    ascending list ids, see :func:`balanced_list_bounds`) replaces the default equal-count blocks."""
+    if bounds is not None:
+        return int(bounds[rank]), int(bounds[rank + 1]) - int(bounds[rank])
     per = (kc + world - 1) // world
     b = min(kc, rank * per)
     return b, min(kc, b + per) - b
 
 
-def list_owner(assign, kc: int, world: int):
+def list_owner(assign, kc: int, world: int, bounds=None):
     """Rank owning each list id in ``assign`` (numpy or torch)."""
+    if bounds is not None:
+        if _lib._is_torch(assign):
+            import torch
+            inner = torch.as_tensor(np.asarray(bounds[1:-1], dtype=np.int64), device=assign.device)
+            return torch.bucketize(assign, inner, right=True)
+        return np.searchsorted(np.asarray(bounds[1:-1], dtype=np.int64), assign, side="right")
     per = (kc + world - 1) // world
     return assign // per
+
+
+def balanced_list_bounds(list_sizes, world: int):
+    """Block boundaries [world + 1] that equalise the expected scan work of the ranks.  A list of length L is probed in
+    proportion to the share of queries that fall near it -- for queries drawn like the data, in proportion to L -- and
+    costs L when it is, so its expected work is ~ L^2: boundaries are cut where the prefix sum of L^2 crosses
+    multiples of total / world.  ``list_sizes`` may come from a sample (only ratios matter)."""
+    w = np.asarray(list_sizes, dtype=np.float64) ** 2 + 1e-9
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    targets = cum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cum, targets, side="left")
+    b = np.concatenate([[0], inner, [w.size]]).astype(np.int64)
+    return np.maximum.accumulate(b)
 
 
 def merge_shard_results(dist_all, ids_all, k, metric=METRIC_L2):
@@ -398,6 +420,7 @@ class ShardedIVFPQIndex:
         self.local = local if local is not None else IVFPQIndex(dimension, metric, nlist, nprobe, m, ks)
         self.nprobe = int(nprobe)
         self.kc = int(nlist)
+        self.bounds = None
 
     @classmethod
     def wrap(cls, local_index, kc, nprobe, group=None):
@@ -408,7 +431,16 @@ class ShardedIVFPQIndex:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local, self.kc, self.nprobe = local_index, int(kc), int(nprobe)
+        self.bounds = None
         return self
+
+    def set_list_bounds(self, bounds):
+        """Block boundaries of the list partition ([world + 1], identical on every rank; before the first ``add``).
+        Default: equal-count blocks."""
+        b = np.asarray(bounds, dtype=np.int64)
+        if b.size != self.world + 1 or b[0] != 0 or b[-1] != self.kc or (np.diff(b) < 0).any():
+            raise ValueError("bounds must be [world + 1] ascending list ids from 0 to nlist")
+        self.bounds = b
 
     # ---- parameters
     def set_parameters(self, coarse, codebooks, centroid_norms=None):
@@ -467,7 +499,7 @@ class ShardedIVFPQIndex:
             self.local.add_encoded(assign, codes, ids)
             return
         assign, codes, ids = self._to_comm(assign), self._to_comm(codes), self._to_comm(ids)
-        owner = list_owner(assign.to(torch.int64), self.kc, self.world)
+        owner = list_owner(assign.to(torch.int64), self.kc, self.world, self.bounds)
         order = torch.argsort(owner, stable=True)
         send_cnt = torch.bincount(owner, minlength=self.world).to(torch.int64)
         recv_cnt = torch.empty_like(send_cnt)
