@@ -42,19 +42,23 @@ print(f"rank {rank}/{world}: {idx.count} vectors in lists [{begin}, {begin + cou
 q = synth.queries(nq)
 _, _, probes = idx.batch_search(q, k, return_probes=True)          # global probe lists (full selection)
 probes = probes.contiguous()
-e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+per = (nq + world - 1) // world
+qblk = q[rank * per:(rank + 1) * per].contiguous()                  # the rank's query block of the probe stage
 for it in range(4):
     if it == 3:
         torch.cuda.profiler.start()                               # ncu --profile-from-start off: one full step
+    e[3].record()
+    idx.probe_range(qblk, nprobe, 0, nlist)                         # what the sharded search runs: its queries x all centroids
     e[0].record()
-    pid, psc = idx.probe_range(q, nprobe, begin, count)
+    pid, psc = idx.probe_range(q, nprobe, begin, count)              # (first version: all queries x its centroid block)
     e[1].record()
     dd, ii = idx.search_with_probes(q, k, probes)
     e[2].record()
     torch.cuda.synchronize()
     if it == 3:
         torch.cuda.profiler.stop()
-    print(f"  iter {it}: probe_range {e[0].elapsed_time(e[1]):.3f} ms, search_with_probes {e[1].elapsed_time(e[2]):.3f} ms", flush=True)
+    print(f"  iter {it}: probe by query block {e[3].elapsed_time(e[0]):.3f} ms, by centroid block {e[0].elapsed_time(e[1]):.3f} ms, search_with_probes {e[1].elapsed_time(e[2]):.3f} ms", flush=True)
 dd, ii, st = idx.search_with_probes(q, k, probes, stats=True)
 tot = max(1, st.cycles_prologue + st.cycles_scan + st.cycles_tail)
 gbs = st.code_bytes_scanned / (st.ms_scan * 1e-3) / 1e9

@@ -441,6 +441,7 @@ def _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed, sift=False, unit=False):
     (6000, 512, 64, 24, 5, 0, "gauss"),      # 512 KB of codebooks, dsub=8, batch-wide bias
     (5000, 768, 64, 16, 4, 1, "unit"),       # C4's d / m: dsub=12, inner product, batch-wide bias
     (4000, 640, 64, 16, 4, 0, "gauss"),      # dsub=10: scalar codebook reads
+    (3000, 1664, 64, 12, 4, 0, "gauss"),     # d=1664 (near the exact engine's limit): the staged queries leave room for 15 of 16 warps; dsub=26
 ])
 def test_ivfpq_index_stagewise_parity(oracle, n, d, m, kc, nprobe, metric, kind):
     from vectorindex_b200.index import IVFPQIndex

@@ -923,14 +923,22 @@ template <int G, bool FILTER>
 static int launch_fast(ScanArgs& a) {
     constexpr int NTAB = (G + 1) / 2;
     // as many warps as the per-warp selection queues leave room for (24 unless k is large)
+    // The tables start at a 64 KB boundary of the shared window; the bookkeeping (probe tables, queries, selection queues)
+    // sits in front of them, behind the <= 1 KB the system keeps at the start of the window.  Two tables must start at
+    // 64 KB (they end at 192 of 227 KB); one table may also start at 128 KB.  Large d / nprobe / k are paid for with
+    // fewer warps (smaller queues).
+    const size_t misc_limit = (NTAB == 2) ? 65536 - 1024 : 100 * 1024;
     int nwarps = kFastThreads / 32;
-    while (nwarps > 3 && 3 * (size_t)nwarps * a.Pw * 8 > 56 * 1024) --nwarps;
-    size_t misc = 2 * ((size_t)a.nprobe * 16 + 4) + 2 * (size_t)a.d * 4 + 40 + 16 + 3 * (size_t)nwarps * a.Pw * 8;
-    // the tables start at the next 64 KB boundary of the shared window, wherever the dynamic segment begins
+    auto misc_bytes = [&](int w) {
+        return 2 * ((size_t)a.nprobe * 16 + 4) + 2 * (size_t)a.d * 4 + 40 + 16 + 3 * (size_t)w * a.Pw * 8;
+    };
+    while (nwarps > 3 && (3 * (size_t)nwarps * a.Pw * 8 > 56 * 1024 || misc_bytes(nwarps) > misc_limit)) --nwarps;
+    const size_t misc = misc_bytes(nwarps);
+    VIX_REQUIRE(misc <= misc_limit, VIX_ERR_UNSUPPORTED,
+                "ivfpq scan: d = %d, k = %d, nprobe = %d need %zu bytes of bookkeeping shared memory (limit %zu)", a.d, a.k,
+                a.nprobe, misc, misc_limit);
     size_t smem = misc + 65535 + (size_t)NTAB * 65536;
     if (smem > 227 * 1024) smem = 227 * 1024;
-    VIX_REQUIRE(misc + 1024 <= 65536 && (size_t)(NTAB + 1) * 65536 <= smem + 1024 + 65535, VIX_ERR_UNSUPPORTED,
-                "ivfpq scan: k = %d, nprobe = %d need %zu bytes of bookkeeping shared memory", a.k, a.nprobe, misc);
     a.smem_bytes = (int)smem;
     auto kern = ivfpq_scan_kernel<G, FILTER>;
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
