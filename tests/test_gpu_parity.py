@@ -438,9 +438,9 @@ def _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed, sift=False, unit=False):
     (5000, 256, 128, 16, 4, 0, "gauss"),     # m=128: largest table
     (8000, 128, 32, 40, 40, 0, "gauss"),     # nprobe == kc: exhaustive
     (9000, 128, 64, 32, 6, 1, "unit"),       # C4-shaped inner product, m=64
-    (6000, 512, 64, 24, 5, 0, "gauss"),      # 512 KB of codebooks, dsub=8, batch-wide bias
-    (5000, 768, 64, 16, 4, 1, "unit"),       # C4's d / m: dsub=12, inner product, batch-wide bias
-    (4000, 640, 64, 16, 4, 0, "gauss"),      # dsub=10: scalar codebook reads
+    (6000, 512, 64, 24, 5, 0, "gauss"),      # 512 KB of codebooks: tables built batch-wide (lut_image_kernel), dsub=8
+    (5000, 768, 64, 16, 4, 1, "unit"),       # C4's d / m: dsub=12, inner product, batch-wide tables + batch-wide bias
+    (4000, 640, 64, 16, 4, 0, "gauss"),      # dsub=10: scalar codebook reads in the batch-wide table build
     (3000, 1664, 64, 12, 4, 0, "gauss"),     # d=1664 (near the exact engine's limit): the staged queries leave room for 15 of 16 warps; dsub=26
 ])
 def test_ivfpq_index_stagewise_parity(oracle, n, d, m, kc, nprobe, metric, kind):
@@ -489,8 +489,8 @@ def test_batchwide_tables_equal_in_kernel_tables(oracle, monkeypatch, d, metric)
     idx = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
     idx.set_coarse(coarse); idx.set_codebooks(cb, norms)
     idx.batch_insert(xb)
-    d1, i1 = idx.batch_search(q, k)
-    monkeypatch.setenv("VIX_LUT_IMAGE", "1")                          # the batch-wide path is opt-in
+    d1, i1 = idx.batch_search(q, k)                                   # 512 KB of codebooks or more: batch-wide tables
+    monkeypatch.setenv("VIX_DISABLE_LUT_IMAGE", "1")
     d2, i2 = idx.batch_search(q, k)
     assert np.array_equal(i1, i2) and np.array_equal(bits(d1), bits(d2))
 

@@ -372,74 +372,57 @@ __device__ VIX_SCAN_FN void copy_lut_image(float* __restrict__ s_lut, const floa
 // The same tables for a whole batch, written to global memory as images of the scan's shared-memory layout
 // ([query][table][code][64 slots], both replicas).  Building a table inside the scan kernel re-reads the codebooks
 // (m x 256 x dsub floats) from L2 once per query and CTA: at dsub = 12, m = 64 that is 786 KB per query against 64 KB of
-// table -- five times the bytes of the scan itself on a one-eighth shard.  Here a CTA takes one group of 16
-// sub-quantisers and kImgQT queries; thread = code.  Codebook vectors come through a shared tile (four sub-quantisers at
-// a time, coalesced 128-bit reads, odd row pitch) and are used by all kImgQT queries; a thread writes its code's
-// 16-byte pieces (four sub-quantisers, both replicas) straight to the image.  Same operation order as build_lut
-// (query pre-scaled, ascending fused multiply-adds), so both paths give the same bits.
-constexpr int kImgQT = 4;       // queries per CTA
-constexpr int kImgTJ = 4;       // sub-quantisers per codebook tile
-static size_t lut_image_smem(int dsub) {
-    return ((size_t)256 * (kImgTJ * dsub + 1) + (size_t)kImgQT * 16 * dsub) * 4;
-}
+// table, and the scan kernel sits at the L2 bandwidth for a third of its time.  Here a CTA takes one table (32
+// sub-quantisers) and kImgQT queries; a WARP takes one code at a time and lane = sub-quantiser, so the 32 codebook vectors
+// of a code are one contiguous read (codebooks_t is [code][m][dsub]) shared by the kImgQT queries, and the warp writes the
+// code's whole 256-byte row (2 groups x 2 replicas x 16) of every query.  Same operation order as build_lut (query
+// pre-scaled, ascending fused multiply-adds), so both paths give the same bits.
+constexpr int kImgQT = 8;       // queries per CTA
 template <int M>
 __global__ void __launch_bounds__(256)
 lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const float* __restrict__ codebooks_t, int dsub,
                  float lut_scale, float* __restrict__ image) {
     constexpr int NTAB = (M / 16 + 1) / 2;
-    extern __shared__ __align__(16) unsigned char smem_img[];
-    const int pitch = kImgTJ * dsub + 1;                   // odd: thread c walking row c is conflict-free
-    float* tile = reinterpret_cast<float*>(smem_img);      // [256][pitch]
-    float* s_q = tile + 256 * pitch;                       // [kImgQT][16 * dsub], pre-scaled
-    const int t16 = blockIdx.y;                            // group of 16 sub-quantisers
+    __shared__ float s_q[kImgQT][32 * 17];                 // [query][sub-quantiser][dsub <= 16], pitch 17: conflict-free
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tab = blockIdx.y;                            // table = 32 sub-quantisers
     const int64_t q0 = (int64_t)blockIdx.x * kImgQT;
-    const int c = threadIdx.x;                             // code
-    for (int i = threadIdx.x; i < kImgQT * 16 * dsub; i += blockDim.x) {
-        const int qi = i / (16 * dsub), e = i - qi * 16 * dsub;
-        s_q[i] = (q0 + qi < nq) ? __ldg(queries + (q0 + qi) * d + t16 * 16 * dsub + e) * lut_scale : 0.0f;
+    const int j = tab * 32 + lane;                         // this lane's sub-quantiser
+    const bool live = j < M;
+    for (int i = threadIdx.x; i < kImgQT * 32 * dsub; i += blockDim.x) {
+        const int qi = i / (32 * dsub), r = i - qi * 32 * dsub, jj = r / dsub, e = r - jj * dsub;
+        const bool ok = q0 + qi < nq && tab * 32 + jj < M;
+        s_q[qi][jj * 17 + e] = ok ? __ldg(queries + (q0 + qi) * d + (tab * 32 + jj) * dsub + e) * lut_scale : 0.0f;
     }
-    const int row_f = kImgTJ * dsub;                       // floats of one code in a tile
-    // this code's row of every query's image: [replica A: 16 sub-quantisers | replica B]
-    float* rowp = image + (size_t)q0 * (NTAB * 16384) + (t16 >> 1) * 16384 + c * 64 + (t16 & 1) * 32;
-    for (int jj = 0; jj < 16 / kImgTJ; ++jj) {
-        __syncthreads();                                   // the previous tile has been used (and s_q is ready)
-        const float* src = codebooks_t + ((size_t)t16 * 16 + jj * kImgTJ) * dsub;
-        if ((dsub & 3) == 0) {
-            const int row4 = row_f >> 2;
-            for (int i = threadIdx.x; i < 256 * row4; i += blockDim.x) {
-                const int r = i / row4, p4 = i - r * row4;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * M * dsub) + p4);
-                float* dst = tile + r * pitch + 4 * p4;
-                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    __syncthreads();
+    // slot of sub-quantiser j inside a 64-slot row: group (j / 16) & 1 takes slots [32 g, 32 g + 32): replica A | replica B
+    const int slot = ((lane >> 4) & 1) * 32 + (lane & 15);
+    float* rowbase = image + (size_t)q0 * (NTAB * 16384) + (size_t)tab * 16384 + slot;
+    for (int c = warp; c < 256; c += 8) {
+        float cv[16];
+        if (live) {
+            const float* src = codebooks_t + ((size_t)c * M + j) * dsub;
+            if ((dsub & 3) == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    if (e < dsub) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+                        cv[e] = v.x; cv[e + 1] = v.y; cv[e + 2] = v.z; cv[e + 3] = v.w;
+                    }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) if (e < dsub) cv[e] = __ldg(src + e);
             }
-        } else {
-            for (int i = threadIdx.x; i < 256 * row_f; i += blockDim.x) {
-                const int r = i / row_f, e = i - r * row_f;
-                tile[r * pitch + e] = __ldg(src + (size_t)r * M * dsub + e);
-            }
-        }
-        __syncthreads();
-        float res[kImgQT][kImgTJ];
-#pragma unroll
-        for (int j4 = 0; j4 < kImgTJ; ++j4) {
-            float dot[kImgQT];
-#pragma unroll
-            for (int qi = 0; qi < kImgQT; ++qi) dot[qi] = 0.0f;
-            for (int e = 0; e < dsub; ++e) {
-                const float v = tile[c * pitch + j4 * dsub + e];
-#pragma unroll
-                for (int qi = 0; qi < kImgQT; ++qi) dot[qi] = fmaf(s_q[qi * 16 * dsub + (jj * kImgTJ + j4) * dsub + e], v, dot[qi]);
-            }
-#pragma unroll
-            for (int qi = 0; qi < kImgQT; ++qi) res[qi][j4] = dot[qi];
         }
 #pragma unroll
         for (int qi = 0; qi < kImgQT; ++qi) {
-            if (q0 + qi < nq) {
-                const float4 v = make_float4(res[qi][0], res[qi][1], res[qi][2], res[qi][3]);
-                float4* dst = reinterpret_cast<float4*>(rowp + (size_t)qi * (NTAB * 16384) + jj * kImgTJ);
-                dst[0] = v;                                // replica A
-                dst[4] = v;                                // replica B (16 floats further on)
+            float dot = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) if (e < dsub) dot = fmaf(s_q[qi][lane * 17 + e], cv[e], dot);
+            if (live && q0 + qi < nq) {
+                float* row = rowbase + (size_t)qi * (NTAB * 16384) + c * 64;
+                row[0] = dot;                              // replica A
+                row[16] = dot;                             // replica B
             }
         }
     }
@@ -986,18 +969,13 @@ int launch_ivfpq_scan(ScanArgs& a) {
     Scratch<float> image;
     const size_t cb_bytes = (size_t)a.m * 256 * a.dsub * 4;
     const size_t img_floats = (size_t)((a.m / 16 + 1) / 2) * 16384;
-    const char* img_env = getenv("VIX_LUT_IMAGE");
-    if (img_env && img_env[0] == '1' && cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30)) {
-        // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan.
-        // OPT-IN (VIX_LUT_IMAGE=1): at C4 it cuts the table's share of a query from 31 k to 2.9 k cycles, but the batch
-        // kernel itself (1.2 ms: scattered 16-byte stores) still costs what that saves (1.1 ms) -- measured, see DESIGN.md
+    if (cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30) && !getenv("VIX_DISABLE_LUT_IMAGE")) {
+        // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan
+        // (C4: the table's share of a query 31 k -> 2.9 k cycles for a 0.46 ms batch kernel; scan stage 3.36 -> 2.86 ms)
         VIX_TRY(image.alloc((size_t)a.nq * img_floats));
-        const dim3 grid((unsigned)((a.nq + kImgQT - 1) / kImgQT), (unsigned)(a.m / 16));
+        const dim3 grid((unsigned)((a.nq + kImgQT - 1) / kImgQT), (unsigned)((a.m + 31) / 32));
         const float scale = a.metric == VIX_METRIC_IP ? 1.0f : -2.0f;
-        const size_t ismem = lut_image_smem(a.dsub);
-#define VIX_IMG(MM)                                                                                                    \
-        VIX_CUDA(cudaFuncSetAttribute(lut_image_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));  \
-        lut_image_kernel<MM><<<grid, 256, ismem, ctx().stream>>>(a.queries, a.nq, a.d, a.codebooks_t, a.dsub, scale, image.ptr)
+#define VIX_IMG(MM) lut_image_kernel<MM><<<grid, 256, 0, ctx().stream>>>(a.queries, a.nq, a.d, a.codebooks_t, a.dsub, scale, image.ptr)
         switch (a.m) {
             case 16: VIX_IMG(16); break;
             case 32: VIX_IMG(32); break;
