@@ -470,7 +470,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel from the committed `ncu --set full`
     # captures (profiles/): known only for the configurations that were captured
-    traffic = {("c5", 1): 87.144009e9 + 7.955712e6, ("c5s", 1): 5.486273e9 + 5.3e6}.get((args.workload, world))
+    traffic = {("c5", 1): 87.105206e9 + 7.9e6, ("c5s", 1): 5.486273e9 + 5.3e6}.get((args.workload, world))
     per_launch_bytes = scan_bytes / K                                  # rank 0's scan kernel, one launch per step
     per_launch_ms = scan_ms / K
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
