@@ -795,6 +795,12 @@ void vo_adc_scan_u4(const uint8_t* codes, int64_t n, int m, int ks, const float*
 /* FlatIndexOptimized.swift:390-477 (fastSearchWithMicrokernels): ScoreBlock.run -> selectTopK with
  * ids 0..n-1 (.min for L2, .max for IP) -> extractSorted -> API distance (L2: sqrt, IP: -dot).
  * out_raw (optional) receives the raw kernel scores of the winners.  Unused slots: id -1, NaN. */
+/* computeQueryInvNorm_impl / the on-the-fly row norm of Cosine.run (Cosine.swift:113-114, 186-190), epsilon = 1e-12 */
+float vo_cosine_inv_norm(const float* x, int d) {
+    if (d == 0) return 1.0f / 1e-12f;
+    return 1.0f / (sqrtf(vo_norm_l2sq(x, d)) + 1e-12f);
+}
+
 void vo_flat_search(const float* queries, int64_t nq, const float* xb, int64_t n, int d,
                     int metric, int k, float* out_dist, int64_t* out_ids, float* out_raw) {
     if (k <= 0) return;
@@ -812,6 +818,16 @@ void vo_flat_search(const float* queries, int64_t nq, const float* xb, int64_t n
             } else {
                 for (int64_t i = 0; i < n; ++i) scores[i] = vo_l2sqr_direct(q, xb + i * (int64_t)d, d);
             }
+        } else if (metric == VO_METRIC_COSINE) {
+            /* Cosine.run without cached norms (Operations/Scoring/Cosine.swift:38-131, the branch ScoreBlock.run takes
+             * for a FlatIndexOptimized without a cosineNormsHandle, ScoreBlock.swift:42-58): InnerProduct.run, then per
+             * row v = (dot * qInv) * inv with inv = 1 / (sqrt(l2NormSquared(row)) + 1e-12), clamped to [-1, 1] */
+            const float qinv = vo_cosine_inv_norm(q, d);
+            for (int64_t i = 0; i < n; ++i) {
+                const float* row = xb + i * (int64_t)d;
+                const float v = (vo_ip(q, row, d) * qinv) * vo_cosine_inv_norm(row, d);
+                scores[i] = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+            }
         } else {
             for (int64_t i = 0; i < n; ++i) scores[i] = vo_ip(q, xb + i * (int64_t)d, d);
         }
@@ -821,7 +837,8 @@ void vo_flat_search(const float* queries, int64_t nq, const float* xb, int64_t n
             int64_t o = qi * (int64_t)k + t;
             if (t < got) {
                 out_ids[o] = ti[t];
-                out_dist[o] = (metric == VO_METRIC_L2) ? sqrtf(ts[t]) : -ts[t];
+                /* FlatIndexOptimized.swift:457-474: L2 => sqrt, dot => -dot, cosine => 1 - similarity */
+                out_dist[o] = (metric == VO_METRIC_L2) ? sqrtf(ts[t]) : (metric == VO_METRIC_COSINE ? 1.0f - ts[t] : -ts[t]);
                 if (out_raw) out_raw[o] = ts[t];
             } else {
                 out_ids[o] = -1;

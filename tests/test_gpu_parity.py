@@ -204,6 +204,36 @@ def test_flat_search_tensor_core_shortlist_is_exact(oracle, vk, n, d, nq, k, met
     assert gi[0, 0] == 17 and set(gi[0, :3]) == {17, n // 2, n - 1}
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(3000, 48, 40, 10), (9000, 768, 24, 7), (500, 130, 9, 500)])
+def test_flat_cosine_matches_reference_two_pass(oracle, vk, n, d, nq, k):
+    """Cosine.run without cached norms (Cosine.swift:94-119): InnerProduct.run, (dot * qInv) * inv, clamp, .max selection,
+    API distance 1 - similarity (FlatIndexOptimized.swift:468-470) -- ids and distance bits equal the oracle's, through
+    the kernel-level entry point and through a FLAT index with external ids; a zero row scores 0 (distance 1)."""
+    from vectorindex_b200.index import FlatIndex
+    rng = np.random.default_rng(n + d)
+    xb = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.1, 5.0, (n, 1)).astype(np.float32)
+    xb[7] = 0.0
+    xb[11] = xb[3] * np.float32(2.0)                                  # same direction as row 3: ties broken by the id
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q[0] = xb[3]
+    od, oi, _ = oracle.flat_search(q, xb, k, 2)
+    gd, gi = vk.flat_search_f32(q, xb, k, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    assert gd.min() >= 0.0 and gd.max() <= 2.0
+    ids = np.arange(n, dtype=np.int64) * 3 + 2
+    idx = FlatIndex(d, "cosine")
+    idx.batch_insert(xb, ids)
+    fd, fi = idx.batch_search(q, k)
+    assert np.array_equal(fi, ids[oi]) and np.array_equal(bits(fd), bits(od))
+
+
+def test_cosine_is_flat_only():
+    from vectorindex_b200 import VectorIndexError
+    from vectorindex_b200.index import IVFPQIndex
+    with pytest.raises(VectorIndexError):
+        IVFPQIndex(32, "cosine", nlist=4, nprobe=2, m=4)
+
+
 def test_flat_search_edge_cases(vk):
     q = np.zeros((3, 8), dtype=np.float32)
     d, i = vk.flat_search_f32(q, np.zeros((0, 8), np.float32), 4)

@@ -843,8 +843,10 @@ int flat_search_auto_device(const float* q, int64_t nq, const float* xb, int64_t
     const int keff = (int)(k < n ? k : n);
     const int gcols = n > 0 ? tc::choose_gcols((int)std::min<int64_t>(n, 0x7FFFFF00), keff) : 32;
     const int64_t ngroups64 = n > 0 ? tc::num_groups(n, gcols) : 0;
+    // (cosine: exact CUDA-core scan only -- the shortlist's error bound is for the unnormalised scores)
     const bool use_tc = getenv("VIX_DISABLE_TC") == nullptr && xb_norm == nullptr && n >= 4096 && n < (1LL << 31) - 256 &&
-                        nq >= 16 && tc::supported(nq, n, d, q, xb) && ngroups64 >= 2 * keff && keff <= 256 && d <= 4096;
+                        nq >= 16 && tc::supported(nq, n, d, q, xb) && ngroups64 >= 2 * keff && keff <= 256 && d <= 4096 &&
+                        (metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP);
     if (!use_tc) return flat_search_device(q, nq, xb, n, d, metric, k, xb_norm, out_dist, out_ids, raw_scores);
     cudaStream_t s = ctx().stream;
     const int ngroups = (int)ngroups64;

@@ -688,8 +688,9 @@ int vix_index_create(const vix_index_params* p, vix_index_t** out) {
     VIX_REQUIRE(p && out, VIX_ERR_NULL_PTR, "vix_index_create: null pointer");
     VIX_REQUIRE(p->d > 0, VIX_ERR_INVALID_DIM, "vix_index_create: d must be > 0");
     VIX_REQUIRE(p->kind >= VIX_INDEX_FLAT && p->kind <= VIX_INDEX_IVF_PQ, VIX_ERR_INVALID_PARAM, "vix_index_create: kind");
-    VIX_REQUIRE(p->metric == VIX_METRIC_L2 || p->metric == VIX_METRIC_IP, VIX_ERR_INVALID_PARAM,
-                "vix_index_create: metric must be L2 or IP");
+    VIX_REQUIRE(p->metric == VIX_METRIC_L2 || p->metric == VIX_METRIC_IP ||
+                    (p->metric == VIX_METRIC_COSINE && p->kind == VIX_INDEX_FLAT),
+                VIX_ERR_INVALID_PARAM, "vix_index_create: metric must be L2 or IP (cosine: FLAT index only)");
     if (p->kind != VIX_INDEX_FLAT) VIX_REQUIRE(p->nlist > 0, VIX_ERR_INVALID_K, "vix_index_create: nlist must be > 0");
     if (p->kind == VIX_INDEX_IVF_PQ) {
         VIX_REQUIRE(p->m > 0 && p->d % p->m == 0, VIX_ERR_INVALID_DIM, "vix_index_create: d %% m != 0");

@@ -25,7 +25,8 @@ enum Transform {
     TR_NONE = 0,      // raw score
     TR_CBS_L2 = 1,    // -2 * s + bnorm[b]        CentroidBatchScore L2 (CentroidBatchScore.swift:54-64)
     TR_NEG = 2,       // -s                       CentroidBatchScore IP (alpha = -1)
-    TR_DOTFUSED = 3   // max(0, (anorm[a] + bnorm[b]) - 2 * s)   L2SqrKernel.swift:436-446
+    TR_DOTFUSED = 3,  // max(0, (anorm[a] + bnorm[b]) - 2 * s)   L2SqrKernel.swift:436-446
+    TR_COSINE = 4     // clamp((s * anorm[a]) * bnorm[b], -1, 1) with inverse norms   Cosine.swift:96-119
 };
 
 struct PairArgs {
@@ -50,6 +51,10 @@ __device__ __forceinline__ float apply_transform(int tr, float s, const PairArgs
     if (tr == TR_DOTFUSED) {
         float dist = fsub(fadd(p.anorm[a], p.bnorm[b]), fmul(2.0f, s));
         return dist < 0.0f ? 0.0f : dist;
+    }
+    if (tr == TR_COSINE) {
+        const float v = fmul(fmul(s, p.anorm[a]), p.bnorm[b]);
+        return fminf(1.0f, fmaxf(-1.0f, v));               // clampUnit (Cosine.swift:177)
     }
     return s;
 }
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs p) {
 // ------------------------------------------------------------------------------------------------
 // Merge of per-split key lists: one CTA per row, bitonic sort of P2 keys in shared memory.
 // Output mapping: dist_mode 0 raw score, 1 sqrt(score) (flat L2 API distance), 2 -score (IP API
-// distance, DistanceUtils.swift:40-46); unused slots id -1 / NaN.
+// distance, DistanceUtils.swift:40-46), 3 1 - score (cosine, FlatIndexOptimized.swift:468-470); unused slots id -1 / NaN.
 // ------------------------------------------------------------------------------------------------
 __global__ void merge_keys_kernel(const u64* __restrict__ keys, int nin, int P2, int k, int order_max,
                                   int dist_mode, uint32_t id_xor, float* __restrict__ out_score,
@@ -218,6 +223,7 @@ __global__ void merge_keys_kernel(const u64* __restrict__ keys, int nin, int P2,
             float sc = key_score(key, order_max);
             if (dist_mode == 1) sc = __fsqrt_rn(sc);
             else if (dist_mode == 2) sc = -sc;
+            else if (dist_mode == 3) sc = fsub(1.0f, sc);
             if (out_score) out_score[o] = sc;
             const uint32_t id = key_id(key) ^ id_xor;
             if (out_id64) out_id64[o] = id_xor ? (int64_t)(int32_t)id : (int64_t)id;
@@ -351,6 +357,13 @@ __global__ void row_norms_kernel(const float* __restrict__ x, int64_t n, int d, 
     if (i < n) out[i] = exact_norm_l2sq(x + i * (int64_t)d, d);
 }
 
+// 1 / (sqrt(||x||^2) + 1e-12) per row: computeQueryInvNorm_impl and the on-the-fly row norm of Cosine.run
+// (Cosine.swift:113-114, 186-190; Norms.l2NormSquared order)
+__global__ void row_inv_norms_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn(1.0f, fadd(__fsqrt_rn(exact_norm_l2sq(x + i * (int64_t)d, d)), 1e-12f));
+}
+
 // l2sqr_f32_block / ip_f32_block for ONE query: the query sits in shared memory, each thread owns
 // a base row.  mode 0: direct L2^2 (Direct16), 1: dot-trick L2^2 (Dot16 + norms), 2: inner product.
 __global__ void block_score_kernel(const float* __restrict__ q, const float* __restrict__ xb, int64_t n, int d,
@@ -421,6 +434,19 @@ static int flat_search_impl(const float* q, int64_t nq, const float* xb, int64_t
     if (metric == VIX_METRIC_IP) {
         p.transform = TR_NONE;
         return pair_topk<SpecIp4>(p, k, 1, raw_scores ? 0 : 2, out_dist, out_ids, nullptr);
+    }
+    if (metric == VIX_METRIC_COSINE) {
+        // ScoreBlock.run without cached norms => Cosine.run two-pass (Cosine.swift:94-119): InnerProduct.run, then
+        // (dot * qInv) * inv per row, clamped; selection .max on the similarity; API distance 1 - similarity
+        Scratch<float> qi, xi;
+        VIX_TRY(qi.alloc((size_t)nq));
+        VIX_TRY(xi.alloc((size_t)n));
+        row_inv_norms_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, ctx().stream>>>(q, nq, d, qi.ptr);
+        VIX_LAUNCH_CHECK();
+        row_inv_norms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx().stream>>>(xb, n, d, xi.ptr);
+        VIX_LAUNCH_CHECK();
+        p.transform = TR_COSINE; p.anorm = qi.ptr; p.bnorm = xi.ptr;
+        return pair_topk<SpecIp4>(p, k, 1, raw_scores ? 0 : 3, out_dist, out_ids, nullptr);
     }
     if (d >= 256 || xb_norm) {
         // dot-trick path (L2SqrKernel.swift:95-106): norms by Norms.l2NormSquared
@@ -686,7 +712,8 @@ int vix_flat_search_f32(const float* queries, int64_t nq, const float* xb, int64
     if (k <= 0 || nq == 0) return VIX_OK;   // k <= 0 => [] (IVFIndex.swift:787; FlatIndex.swift:57)
     VIX_REQUIRE(queries && out_dist && out_ids && (xb || n == 0), VIX_ERR_NULL_PTR, "vix_flat_search_f32: null pointer");
     VIX_REQUIRE(d > 0 && n >= 0 && nq >= 0, VIX_ERR_INVALID_DIM, "vix_flat_search_f32: bad shape");
-    VIX_REQUIRE(metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP, VIX_ERR_INVALID_PARAM, "vix_flat_search_f32: metric");
+    VIX_REQUIRE(metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP || metric == VIX_METRIC_COSINE, VIX_ERR_INVALID_PARAM,
+                "vix_flat_search_f32: metric");
     VIX_REQUIRE(k <= VIX_MAX_K, VIX_ERR_INVALID_K, "vix_flat_search_f32: k > %d", VIX_MAX_K);
     VIX_REQUIRE(n < (1LL << 32) - 1, VIX_ERR_INVALID_PARAM, "vix_flat_search_f32: n must be < 2^32 - 1");
     In<float> dq, dx;

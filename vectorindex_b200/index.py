@@ -30,7 +30,8 @@ from ._lib import (INDEX_FLAT, INDEX_IVF_FLAT, INDEX_IVF_PQ, IndexParams, KMeans
                    SearchStats, VectorIndexError, as_input, check, empty_like_input, lib, ptr)
 
 _METRICS = {"euclidean": METRIC_L2, "l2": METRIC_L2, METRIC_L2: METRIC_L2,
-            "dotProduct": METRIC_IP, "dot": METRIC_IP, "ip": METRIC_IP, METRIC_IP: METRIC_IP}
+            "dotProduct": METRIC_IP, "dot": METRIC_IP, "ip": METRIC_IP, METRIC_IP: METRIC_IP,
+            "cosine": 2, 2: 2}                                       # cosine: FlatIndex only
 
 
 def _metric(m):
