@@ -269,6 +269,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN + (uint32_t)half * 64;
                 const int colbase = nt * kN + half * 64;
                 const bool full_tile = nt * kN + kN <= a.nB;
+                unsigned long long hits = 0;                   // MODE_EMIT: this thread's 64 columns with S~ <= T
 #pragma unroll 1
                 for (int ck = 0; ck < 2; ++ck) {
                     float v[32];
@@ -324,18 +325,25 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         uint32_t hit = 0;                          // columns of this chunk with S~ <= T
 #pragma unroll
                         for (int i = 0; i < 32; ++i) hit |= (sc[i] <= thr) ? (1u << i) : 0u;
-                        while (hit) {                              // rare: ~1.2 k hits per row in the whole matrix
-                            const int i = __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            const int pos = atomicAdd(a.cand_cnt + row, 1);
-                            if (pos < a.cap) a.cand_idx[row * a.cap + pos] = colbase + ck * 32 + i;
-                        }
+                        hits |= (unsigned long long)hit << (32 * ck);
                     }
                 }
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty + acc);      // 4 arrivals free the accumulator
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
+                if (MODE == MODE_EMIT && hits) {
+                    // emission AFTER the accumulator has been handed back, one counter update per thread and tile: the
+                    // round trip of the global atomic (rare hits: ~1.2 k per row in the whole matrix) used to sit
+                    // between the TMEM read and the release, once per hit
+                    int pos = atomicAdd(a.cand_cnt + row, __popcll(hits));
+                    while (hits) {
+                        const int i = __ffsll((long long)hits) - 1;
+                        hits &= hits - 1;
+                        if (pos < a.cap) a.cand_idx[row * a.cap + pos] = colbase + i;
+                        ++pos;
+                    }
+                }
             }
         }
     }
