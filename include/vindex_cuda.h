@@ -329,6 +329,16 @@ int vix_index_search_with_probes_keys(vix_index_t* h, const float* queries, int6
                                       int nprobe, uint64_t* keys_out /* [nq x k] */);
 int vix_merge_result_keys(const uint64_t* keys_all /* [world x nq x k] */, int world, int64_t nq, int k,
                           float* out_dist, int64_t* out_ids /* [nq x k] */);
+/* The same two exchanges over PEER MEMORY (NVLink / NVSwitch) instead of NCCL: every rank owns a buffer of `world` slots
+ * that is mapped into all peers (symmetric memory); peer_bufs_dev is a DEVICE array of the `world` buffer addresses.  A
+ * rank's kernels store its block straight into slot `rank` of every peer's buffer; the caller then runs ONE barrier across
+ * the ranks on the stream and merges from its own buffer (vix_merge_result_keys / the gathered probe ids).
+ *   vix_peer_scatter_block                   any device block of a multiple of 16 bytes (the probe-list ids of the rank's query block)
+ *   vix_index_search_with_probes_keys_peers  the fused scan, its local top-k packed and stored by the same call */
+int vix_peer_scatter_block(const void* src, size_t bytes, void* const* peer_bufs_dev, int world, int rank);
+int vix_index_search_with_probes_keys_peers(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                            int nprobe, void* const* peer_bufs_dev, int world, int rank);
+
 /* same, with the stage timings / scan statistics of vix_index_search_ex (synchronises) */
 int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                     int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats /* nullable */);

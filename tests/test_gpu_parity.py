@@ -605,6 +605,41 @@ def test_sharded_key_exchange_emulated_on_one_gpu(oracle, metric):
     assert np.array_equal(mi2 >= 0, ~np.isnan(md2))
 
 
+def test_peer_memory_exchange_entry_points_on_one_gpu(oracle):
+    """vix_peer_scatter_block / vix_index_search_with_probes_keys_peers with two "peers" that are two buffers of the same
+    GPU (on a multi-GPU box they are symmetric-memory mappings of the other ranks): every peer's slot `rank` receives the
+    block, and the packed keys equal those of vix_index_search_with_probes_keys."""
+    import ctypes as C
+    import torch
+    from vectorindex_b200._lib import check, lib, ptr
+    from vectorindex_b200.index import IVFPQIndex
+    dev = torch.device("cuda", 0)
+    world, rank = 2, 1
+    block = torch.arange(4 * 1024, dtype=torch.int32, device=dev)
+    bufs = [torch.full((world, block.numel()), -7, dtype=torch.int32, device=dev) for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    check(lib().vix_peer_scatter_block(ptr(block), C.c_size_t(block.numel() * 4), C.c_void_p(table.data_ptr()), C.c_int(world),
+                                       C.c_int(rank)))
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[rank], block) and (b[0] == -7).all()
+    n, d, m, kc, nq, k, nprobe = 5000, 64, 16, 24, 40, 10, 5
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=8)
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse); idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb)
+    _, _, probes = idx.batch_search(q, k, return_probes=True)
+    want = torch.from_numpy(idx.search_with_probes_keys(q, k, probes).view(np.int64)).to(dev)
+    kb = [torch.zeros((world, nq, k), dtype=torch.int64, device=dev) for _ in range(world)]
+    ktab = torch.tensor([b.data_ptr() for b in kb], dtype=torch.int64, device=dev)
+    qd, pd = torch.from_numpy(q).to(dev), torch.from_numpy(probes).to(dev)
+    check(lib().vix_index_search_with_probes_keys_peers(idx._h, ptr(qd), C.c_int64(nq), C.c_int(k), ptr(pd), C.c_int(nprobe),
+                                                        C.c_void_p(ktab.data_ptr()), C.c_int(world), C.c_int(rank)))
+    torch.cuda.synchronize()
+    for b in kb:
+        assert torch.equal(b[rank], want) and (b[0] == 0).all()
+
+
 @pytest.mark.parametrize("mode", ["allow", "deny"])
 @pytest.mark.parametrize("m", [16, 12])          # fused fast kernel / generic kernel
 def test_ivfpq_filtered_search_is_prefilter(oracle, mode, m):

@@ -91,7 +91,8 @@ _EXPORTS = [
     "vix_index_import_lists", "vix_index_count", "vix_index_list_sizes", "vix_index_export_lists", "vix_index_clear",
     "vix_index_search", "vix_index_search_ex", "vix_index_trace", "vix_index_trace_get", "vix_index_probe_range", "vix_index_search_with_probes",
     "vix_index_search_with_probes_ex", "vix_index_search_filtered", "vix_index_probe_range_keys", "vix_merge_probe_keys",
-    "vix_index_search_with_probes_keys", "vix_merge_result_keys",
+    "vix_index_search_with_probes_keys", "vix_merge_result_keys", "vix_peer_scatter_block",
+    "vix_index_search_with_probes_keys_peers",
     "vix_index_encode", "vix_index_add_encoded", "vix_debug_tc_scores_f32", "vix_accel_rank_candidates_f32",
     "cpq_encode_u8_f32", "cpq_encode_u8_f32_with_csq", "cpq_encode_u4_f32", "cpq_encode_residual_u8_f32",
     "cpq_encode_residual_u8_f32_with_csq", "cpq_encode_residual_u4_f32", "cpq_pack_u4_bulk", "cpq_unpack_u4_bulk",

@@ -1105,6 +1105,71 @@ int vix_index_search_with_probes_keys(vix_index_t* h, const float* queries, int6
     return finish(dk.is_host());
 }
 
+// ---- the exchange steps over PEER MEMORY (NVLink / NVSwitch) instead of NCCL ------------------------------------
+// Every rank owns a buffer of `world` slots mapped into all peers (symmetric memory: torch's _SymmetricMemory in this
+// repo, cuMemMap'ed / IPC allocations from another host); `peer_bufs` is a DEVICE array of the `world` buffer addresses.
+// A rank stores its block straight into slot `rank` of every peer's buffer -- the all-gather IS the producing kernel's
+// store pattern -- and the caller then runs one barrier across the ranks on the stream.
+__global__ void peer_scatter_kernel(const uint4* __restrict__ src, int64_t n16, void* const* __restrict__ peer_bufs,
+                                    int world, int64_t slot16) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int p = 0; p < world; ++p) reinterpret_cast<uint4*>(peer_bufs[p])[slot16 + i] = v;
+    }
+}
+
+// the local top-k of a sharded search packed into keys and stored into slot `rank` of every peer's [world x nq x k] buffer
+__global__ void pack_keys_to_peers_kernel(const float* __restrict__ score, const int64_t* __restrict__ id64, int64_t total,
+                                          void* const* __restrict__ peer_bufs, int world, int64_t slot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t id = id64[i];
+    const u64 key = id < 0 ? kEmptyKey : make_key(score[i], (uint32_t)id, 0);
+    for (int p = 0; p < world; ++p) reinterpret_cast<u64*>(peer_bufs[p])[slot + i] = key;
+}
+
+int vix_peer_scatter_block(const void* src, size_t bytes, void* const* peer_bufs_dev, int world, int rank) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(src && peer_bufs_dev, VIX_ERR_NULL_PTR, "vix_peer_scatter_block: null pointer");
+    VIX_REQUIRE(world > 0 && rank >= 0 && rank < world, VIX_ERR_INVALID_PARAM, "vix_peer_scatter_block: rank / world");
+    VIX_REQUIRE(bytes % 16 == 0 && is_device_ptr(src), VIX_ERR_INVALID_PARAM,
+                "vix_peer_scatter_block: the block must be a device buffer of a multiple of 16 bytes");
+    if (bytes == 0) return VIX_OK;
+    const int64_t n16 = (int64_t)(bytes / 16);
+    const int64_t want = (n16 + 255) / 256;
+    const unsigned grid = (unsigned)(want < 4 * num_sms() ? want : 4 * num_sms());
+    peer_scatter_kernel<<<grid, 256, 0, ctx().stream>>>(static_cast<const uint4*>(src), n16, peer_bufs_dev, world,
+                                                        (int64_t)rank * n16);
+    VIX_LAUNCH_CHECK();
+    return finish(false);
+}
+
+int vix_index_search_with_probes_keys_peers(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
+                                            int nprobe, void* const* peer_bufs_dev, int world, int rank) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h && probes && peer_bufs_dev, VIX_ERR_NULL_PTR, "vix_index_search_with_probes_keys_peers: null pointer");
+    VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "vix_index_search_with_probes_keys_peers: nprobe must be > 0");
+    VIX_REQUIRE(world > 0 && rank >= 0 && rank < world, VIX_ERR_INVALID_PARAM, "vix_index_search_with_probes_keys_peers: rank / world");
+    std::lock_guard<std::mutex> lk(h->mu);
+    VIX_REQUIRE(h->p.kind != VIX_INDEX_FLAT && h->has_coarse, VIX_ERR_NOT_TRAINED,
+                "vix_index_search_with_probes_keys_peers: IVF index not trained");
+    if (nq <= 0 || k <= 0) return VIX_OK;
+    const int64_t total = nq * (int64_t)k;
+    Scratch<float> dist;
+    Scratch<int64_t> ids;
+    VIX_TRY(dist.alloc((size_t)total));
+    VIX_TRY(ids.alloc((size_t)total));
+    In<float> dq;
+    VIX_TRY(dq.stage(queries, (size_t)nq * h->p.d));
+    In<int32_t> dpr;
+    VIX_TRY(dpr.stage(probes, (size_t)nq * nprobe));
+    VIX_TRY(index_search_locked(h, dq.dev, nq, k, nprobe, dist.ptr, ids.ptr, nullptr, nullptr, dpr.dev));
+    pack_keys_to_peers_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(dist.ptr, ids.ptr, total, peer_bufs_dev,
+                                                                                       world, (int64_t)rank * total);
+    VIX_LAUNCH_CHECK();
+    return finish(false);
+}
+
 int vix_merge_result_keys(const uint64_t* keys_all, int world, int64_t nq, int k, float* out_dist, int64_t* out_ids) {
     VIX_TRY(ensure_device());
     VIX_REQUIRE(keys_all && out_dist && out_ids, VIX_ERR_NULL_PTR, "vix_merge_result_keys: null pointer");

@@ -464,6 +464,74 @@ class ShardedIVFPQIndex:
             a = a.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=a.is_pinned())
         return a.contiguous()
 
+    # ---- exchanges over peer memory (NVLink / NVSwitch) -------------------------------------------------------
+    def _p2p(self):
+        """Symmetric-memory state, or None (then NCCL all-gathers carry the exchanges): torch's _SymmetricMemory maps a
+        buffer of every rank into all peers; the library's kernels store into the peers directly."""
+        import os
+        st = self.__dict__.get("_p2p_state", "unset")
+        if st != "unset":
+            return st
+        st = None
+        if self.world > 1 and self._nccl() and not os.environ.get("VIX_NO_P2P") and hasattr(self.local, "_h"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                st = {"symm": symm, "bufs": {}}
+            except Exception:  # noqa: BLE001
+                st = None
+        self._p2p_state = st
+        return st
+
+    def _symm_buffer(self, tag, shape, dtype):
+        """(tensor, handle) of a symmetric buffer, double buffered: consecutive uses of a tag alternate between two
+        allocations, and between two uses of the same one lies the barrier of the other exchange, so a fast rank never
+        overwrites what a slow peer is still merging."""
+        import torch.distributed as dist
+        st = self._p2p_state
+        ent = st["bufs"].get((tag, shape, dtype))
+        if ent is None:
+            pairs = []
+            for _ in range(2):
+                t = st["symm"].empty(shape, dtype=dtype, device=self._comm_device())
+                pairs.append((t, st["symm"].rendezvous(t, self.group if self.group is not None else dist.group.WORLD)))
+            ent = st["bufs"][(tag, shape, dtype)] = {"pairs": pairs, "i": 0}
+        ent["i"] ^= 1
+        return ent["pairs"][ent["i"]]
+
+    def _search_over_peer_memory(self, queries, k, nprobe, mark):
+        """One sharded search step whose two exchanges are stores into peer memory by the producing kernels + one
+        barrier each (vix_peer_scatter_block, vix_index_search_with_probes_keys_peers)."""
+        import torch
+        nq = int(queries.shape[0])
+        lo, cnt, per = self.query_block(nq)
+        if (per * nprobe) % 4:
+            raise ValueError("probe block is not a multiple of 16 bytes")
+        q = as_input(queries, np.float32)
+        # probe lists of this rank's query block -> slot `rank` of every peer's [world * per x nprobe] buffer
+        pbuf, ph = self._symm_buffer("probes", (self.world * per, nprobe), torch.int32)
+        if cnt == per:
+            block = self.local.probe_range(q[lo:lo + cnt], nprobe, 0, self.kc)[0]
+        else:
+            block = torch.full((per, nprobe), -1, dtype=torch.int32, device=pbuf.device)
+            if cnt > 0:
+                block[:cnt] = self.local.probe_range(q[lo:lo + cnt], nprobe, 0, self.kc)[0]
+        check(lib().vix_peer_scatter_block(ptr(block, np.int32), C.c_size_t(per * nprobe * 4), C.c_void_p(int(ph.buffer_ptrs_dev)),
+                                           C.c_int(self.world), C.c_int(self.rank)))
+        ph.barrier()
+        probes = pbuf[:nq]
+        mark("probe_select+gather")
+        # fused scan; its local top-k leaves as packed keys for slot `rank` of every peer's [world x nq x k] buffer
+        kbuf, kh = self._symm_buffer("results", (self.world, nq, k), torch.int64)
+        check(lib().vix_index_search_with_probes_keys_peers(self.local._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
+                                                            ptr(probes, np.int32), C.c_int(nprobe),
+                                                            C.c_void_p(int(kh.buffer_ptrs_dev)), C.c_int(self.world),
+                                                            C.c_int(self.rank)))
+        mark("scan")
+        kh.barrier()
+        out = merge_result_keys(kbuf)
+        mark("gather+merge")
+        return out
+
     def _to_host(self, t):
         """device tensor -> numpy array through a pinned staging buffer kept with the index (one D2H at full PCIe rate,
         one wait), copied out so that the caller owns the result"""
@@ -574,12 +642,22 @@ class ShardedIVFPQIndex:
             was_async = lib().vix_get_async()
             lib().vix_set_async(1)
             try:
-                probes = self.global_probes(queries, nprobe)
-                mark("probe_select+gather")
-                rk = self.local.search_with_probes_keys(queries, k, probes)
-                mark("scan")
-                md, mi = merge_result_keys(self._all_gather(rk))
-                mark("gather+merge")
+                md = None
+                if self._p2p() is not None:
+                    try:
+                        md, mi = self._search_over_peer_memory(queries, k, nprobe, mark)
+                    except Exception as e:  # noqa: BLE001  (no symmetric memory on this system: NCCL carries the exchanges)
+                        import warnings
+                        warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-gathers")
+                        self._p2p_state = None
+                        md = None
+                if md is None:
+                    probes = self.global_probes(queries, nprobe)
+                    mark("probe_select+gather")
+                    rk = self.local.search_with_probes_keys(queries, k, probes)
+                    mark("scan")
+                    md, mi = merge_result_keys(self._all_gather(rk))
+                    mark("gather+merge")
             finally:
                 lib().vix_set_async(was_async)
             if marks:
