@@ -444,8 +444,9 @@ __device__ __noinline__ uint32_t flush_queue(u64* wq, int Pw, int k, int cnt, bo
     return thr_u;
 }
 
-// m = 16 G; FILTER: an id filter is active (a separate instantiation, so the unfiltered kernel pays nothing)
-template <int G, bool FILTER>
+// m = 16 G; FILTER: an id filter is active; STATS: the phase counters of vix_search_stats are kept (separate
+// instantiations, so the production kernel pays neither in instructions nor in registers)
+template <int G, bool FILTER, bool STATS>
 __global__ void __launch_bounds__(kFastThreads, 1)
 ivfpq_scan_kernel(ScanArgs a) {
     constexpr int m = 16 * G;
@@ -520,7 +521,7 @@ ivfpq_scan_kernel(ScanArgs a) {
     int buf = 0;
     bool have_prev = false;
     int64_t prev_qi = 0;
-    long long t_mark = clock64();
+    long long t_mark = STATS ? clock64() : 0;
     unsigned long long cyc_pro = 0, cyc_scan = 0, cyc_tail = 0;
     for (;;) {
         const int item = s_item[buf];
@@ -537,34 +538,34 @@ ivfpq_scan_kernel(ScanArgs a) {
         if (more) {
             // ---- prologue: the table; the first run of chunks of every warp is fixed (warp w: chunks [4 w, 4 w + 4)) ----
             if (tid == 32) { *cta_thr = 0xFFFFFFFFu; *s_next = nwarps * kGrab; }
-            const long long t0 = clock64();
+            const long long t0 = STATS ? clock64() : 0;
             if (nchunks > 0) {
                 if (a.lut_image) copy_lut_image(s_lut, a.lut_image + (size_t)qi * (NTAB * 16384), NTAB * 4096, tid, (int)blockDim.x);
                 else build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, (int)blockDim.x);
             }
-            if (a.phase_cycles && tid == 64) atomicAdd(a.phase_cycles + 5, (unsigned long long)(clock64() - t0));
+            if (STATS && a.phase_cycles && tid == 64) atomicAdd(a.phase_cycles + 5, (unsigned long long)(clock64() - t0));
         }
         __syncthreads();                                   // (1) table ready; s_item[buf] has been read by everybody
         // ---- warp 0 first selects the k best of the candidates published for the PREVIOUS query and warp 1 builds
         //      the NEXT query's probe table; the other warps are already scanning, and chunks are handed out
         //      dynamically, so nobody waits for either
         if (warp == 0 && have_prev) {
-            const long long t0 = clock64();
-            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 6, (unsigned long long)s_ncand[buf ^ 1]);
+            const long long t0 = STATS ? clock64() : 0;
+            if (STATS && a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 6, (unsigned long long)s_ncand[buf ^ 1]);
             select_and_write(s_cand + (size_t)(buf ^ 1) * nwarps * a.Pw, s_ncand[buf ^ 1], a.k, order_max, prev_qi, a.out_dist,
                              a.out_ids);
             __syncwarp();
             if (lane == 0) s_ncand[buf ^ 1] = 0;
-            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 3, (unsigned long long)(clock64() - t0));
+            if (STATS && a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 3, (unsigned long long)(clock64() - t0));
         }
         if (!more) break;
         if (warp == 1) {
-            const long long t0 = clock64();
+            const long long t0 = STATS ? clock64() : 0;
             probe_table(s_item[buf ^ 1], buf ^ 1);
             if (lane == 0) s_item[buf] = atomicAdd(a.work_counter, 1);   // the item after the next
-            if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 4, (unsigned long long)(clock64() - t0));
+            if (STATS && a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 4, (unsigned long long)(clock64() - t0));
         }
-        { const long long t = clock64(); cyc_pro += (unsigned long long)(t - t_mark); t_mark = t; }
+        if (STATS) { const long long t = clock64(); cyc_pro += (unsigned long long)(t - t_mark); t_mark = t; }
 
         // ---- scan: 32-slot chunks of the probed lists, handed out dynamically ----
         int cnt = 0;                                       // unsorted candidates behind the k sorted ones
@@ -736,9 +737,9 @@ ivfpq_scan_kernel(ScanArgs a) {
                 }
             }
         }
-        { const long long t = clock64(); cyc_scan += (unsigned long long)(t - t_mark); t_mark = t; }
+        if (STATS) { const long long t = clock64(); cyc_scan += (unsigned long long)(t - t_mark); t_mark = t; }
         __syncthreads();                                   // (2) scan finished everywhere, candidates published
-        { const long long t = clock64(); cyc_tail += (unsigned long long)(t - t_mark); t_mark = t; }
+        if (STATS) { const long long t = clock64(); cyc_tail += (unsigned long long)(t - t_mark); t_mark = t; }
         have_prev = true;
         prev_qi = qi;
         buf ^= 1;
@@ -757,7 +758,7 @@ ivfpq_scan_kernel(ScanArgs a) {
 #ifdef VIX_SCAN_DIAG
     if (a.phase_cycles && lane == 0) atomicAdd(a.phase_cycles + 11, cyc_tail);    // barrier wait summed over ALL warps
 #endif
-    if (a.phase_cycles && tid == 64) {                     // one scanning warp per CTA reports its phase split
+    if (STATS && a.phase_cycles && tid == 64) {            // one scanning warp per CTA reports its phase split
         atomicAdd(a.phase_cycles + 0, cyc_pro);
         atomicAdd(a.phase_cycles + 1, cyc_scan);
         atomicAdd(a.phase_cycles + 2, cyc_tail);
@@ -904,6 +905,7 @@ static size_t generic_smem_bytes(const ScanArgs& a) {
 
 template <int G, bool FILTER>
 static int launch_fast(ScanArgs& a) {
+    const bool stats = a.phase_cycles != nullptr;
     constexpr int NTAB = (G + 1) / 2;
     // as many warps as the per-warp selection queues leave room for (24 unless k is large)
     // The tables start at a 64 KB boundary of the shared window; the bookkeeping (probe tables, queries, selection queues)
@@ -923,7 +925,7 @@ static int launch_fast(ScanArgs& a) {
     size_t smem = misc + 65535 + (size_t)NTAB * 65536;
     if (smem > 227 * 1024) smem = 227 * 1024;
     a.smem_bytes = (int)smem;
-    auto kern = ivfpq_scan_kernel<G, FILTER>;
+    auto kern = stats ? ivfpq_scan_kernel<G, FILTER, true> : ivfpq_scan_kernel<G, FILTER, false>;
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = num_sms();
     if (grid > a.nq) grid = a.nq;
