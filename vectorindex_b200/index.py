@@ -65,6 +65,8 @@ class IDFilter:
         """idFilterPass for an array of ids"""
         ids = np.asarray(ids, dtype=np.int64)
         inside = (ids >= 0) & (ids < self.capacity)
+        if self.words.size == 0:
+            return np.zeros(ids.shape, dtype=bool)
         safe = np.where(inside, ids, 0)
         bit = ((self.words[safe >> 6] >> (safe & 63).astype(np.uint64)) & np.uint64(1)).astype(bool)
         return inside & (bit if self.mode == 0 else ~bit)
