@@ -81,6 +81,8 @@ def search_golden():
     out["adc_first_probe_len"] = np.array([a.size for a in adcs], dtype=np.int64)
     fd, fi, _ = oracle.flat_search(q, xb, k, 0)
     out["flat_dist"], out["flat_ids"] = fd, fi
+    cd, ci, _ = oracle.flat_search(q, xb, k, 2)                        # cosine (Cosine.run two-pass), distance 1 - sim
+    out["cosine_dist"], out["cosine_ids"] = cd, ci
     ids = np.arange(xb.shape[0], dtype=np.int64)
     od, oi, op = oracle.ivfpq_search(q, coarse, cb, norms, off, codes[order], ids[order], m, 256, nprobe, k, 0)
     out["ivfpq_dist"], out["ivfpq_ids"] = od, oi

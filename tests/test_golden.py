@@ -63,6 +63,26 @@ def test_oracle_reproduces_search_golden(oracle):
     assert np.array_equal(pid, g["probe_ids"]) and np.array_equal(bits(psc), bits(g["probe_scores"]))
     fd, fi, _ = oracle.flat_search(q, xb, k, 0)
     assert np.array_equal(fi, g["flat_ids"]) and np.array_equal(bits(fd), bits(g["flat_dist"]))
+    cd, ci, _ = oracle.flat_search(q, xb, k, 2)
+    assert np.array_equal(ci, g["cosine_ids"]) and np.array_equal(bits(cd), bits(g["cosine_dist"]))
+
+
+def test_oracle_cosine_against_float64(oracle):
+    """Cosine.run two-pass restatement vs a float64 evaluation of 1 - <q, x> / (|q| |x|): same ranking away from
+    near-ties, distances within fp32 rounding; a zero row has similarity 0 (distance 1)."""
+    rng = np.random.default_rng(12)
+    xb = (rng.standard_normal((700, 40)) * rng.uniform(0.2, 4.0, (700, 1))).astype(np.float32)
+    xb[5] = 0.0
+    q = rng.standard_normal((9, 40)).astype(np.float32)
+    d, i, _ = oracle.flat_search(q, xb, 700, 2)
+    x64, q64 = xb.astype(np.float64), q.astype(np.float64)
+    nx = np.linalg.norm(x64, axis=1)
+    sim = (q64 @ x64.T) / np.linalg.norm(q64, axis=1)[:, None] / np.where(nx > 0, nx, 1.0)[None]
+    ref = 1.0 - sim
+    for r in range(q.shape[0]):
+        assert np.allclose(d[r], ref[r][i[r]], atol=3e-6)
+        assert (np.diff(d[r]) >= 0).all()
+        assert d[r][np.where(i[r] == 5)[0][0]] == np.float32(1.0)
 
 
 # ------------------------------------------------------------------------------------------ GPU: C ABI vs golden
@@ -125,6 +145,8 @@ def test_cuda_search_stages_reproduce_golden(vk):
         pos += n
     fd, fi = vk.flat_search_f32(q, xb, k, 0)
     assert np.array_equal(fi, g["flat_ids"]) and np.array_equal(bits(fd), bits(g["flat_dist"]))
+    cd, ci = vk.flat_search_f32(q, xb, k, 2)
+    assert np.array_equal(ci, g["cosine_ids"]) and np.array_equal(bits(cd), bits(g["cosine_dist"]))
     # the index: same lists, probe lists bit-exact, fused-scan distances within 1e-5 (re-associated sum), id sets equal
     # except at ties inside that tolerance
     idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
