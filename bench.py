@@ -60,7 +60,7 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region.  The K timed steps are enqueued asynchronously;
-    while the GPU works through them the host polls NVML from the main thread (a few samples, 10 ms apart).
+    while the GPU works through them the host polls NVML from the main thread (samples 2 ms apart).
     NVML queries take the driver lock that CUDA API calls need, so polling from a second thread (or an
     `nvidia-smi -lms` child) while the host is still launching stalls the launches -- measured: a 6 ms step
     became 60 ms.  Polling only after everything is enqueued perturbs nothing."""
@@ -102,7 +102,7 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             log(f"[bench] NVML sample failed: {e}")
 
-    def poll_until(self, done, period_s=0.01, max_samples=64):
+    def poll_until(self, done, period_s=0.002, max_samples=64):
         """Sample while `done()` is false (at least once)."""
         self.sample()
         while not done() and len(self.clocks) < max_samples:
