@@ -26,11 +26,19 @@
 //     (table | code << 8 | 4 * slot) is ONE byte-permute of the packed code word with a per-lane
 //     constant; the group / table select is the LDS immediate.
 //
-// Top-k: per-warp shared-memory queues keyed (score, id) with a CTA-wide acceptance threshold; at the end
-// of a query every warp publishes its k best and warp 0 merges them while the other warps already build
-// the next query's table.  No distance array ever reaches HBM.  Queries are handed out by an atomic
-// counter in an order sorted by first probed list, so CTAs running concurrently scan neighbouring lists
-// and share them through L2.
+// Top-k: per-warp shared-memory queues keyed (score, id) under a CTA-wide acceptance threshold that every warp re-reads
+// each chunk; the k-th smallest of a warp's first chunk seeds it, and the k-th smallest of every 32 accepted entries
+// lowers it (one shuffle network) -- a queue is sorted only when it overflows.  At the end of a query every warp
+// publishes the entries that can still make the top k.  No distance array ever reaches HBM.
+//
+// Pipeline across queries (one CTA per SM, 16 warps): while the CTA scans query i, warp 1 first stages what query i + 1
+// needs besides its table -- the query (to shared memory), the probe table of the lists that are not empty on this GPU
+// and their bias terms -- and warp 0 first selects the k best of what query i - 1 published; chunks are handed out
+// dynamically (runs of 4, 2, 1), so nobody waits for either.  The per-query serial part is the table build (all warps)
+// between two CTA barriers.  Queries are handed out by an atomic counter in an order sorted by the first probed list that
+// holds vectors here, so CTAs running concurrently scan neighbouring lists and share them through L2.
+// Large d / large codebooks: the bias terms and the tables are built batch-wide instead (probe_bias_kernel,
+// lut_image_kernel) and the scan copies a query's table image with cp.async.
 #include <stdlib.h>
 
 #include "vix_common.cuh"
