@@ -500,6 +500,9 @@ class ShardedIVFPQIndex:
         ent["i"] ^= 1
         return ent["pairs"][ent["i"]]
 
+    # a peer that never arrives makes the barrier kernel trap after this long (an error instead of a hung box)
+    _BARRIER_TIMEOUT_MS = 120_000
+
     def _search_over_peer_memory(self, queries, k, nprobe, mark):
         """One sharded search step whose two exchanges are stores into peer memory by the producing kernels + one
         barrier each (vix_peer_scatter_block, vix_index_search_with_probes_keys_peers)."""
@@ -519,7 +522,7 @@ class ShardedIVFPQIndex:
                 block[:cnt] = self.local.probe_range(q[lo:lo + cnt], nprobe, 0, self.kc)[0]
         check(lib().vix_peer_scatter_block(ptr(block, np.int32), C.c_size_t(per * nprobe * 4), C.c_void_p(int(ph.buffer_ptrs_dev)),
                                            C.c_int(self.world), C.c_int(self.rank)))
-        ph.barrier()
+        ph.barrier(0, self._BARRIER_TIMEOUT_MS)
         probes = pbuf[:nq]
         mark("probe_select+gather")
         # fused scan; its local top-k leaves as packed keys for slot `rank` of every peer's [world x nq x k] buffer
@@ -529,7 +532,7 @@ class ShardedIVFPQIndex:
                                                             C.c_void_p(int(kh.buffer_ptrs_dev)), C.c_int(self.world),
                                                             C.c_int(self.rank)))
         mark("scan")
-        kh.barrier()
+        kh.barrier(0, self._BARRIER_TIMEOUT_MS)
         out = merge_result_keys(kbuf)
         mark("gather+merge")
         return out
