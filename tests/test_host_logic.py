@@ -3,7 +3,7 @@ Operations/Filtering/IDFilter.swift:13-135) and the metric / argument mapping of
 import numpy as np
 import pytest
 
-from vectorindex_b200.index import IDFilter
+from vectorindex_b200.index import IDFilter, compose_id_filters
 
 
 def _pass_reference(words, capacity, deny, i):
@@ -44,3 +44,28 @@ def test_metric_names_map_to_the_abi_values():
     assert (_metric("euclidean"), _metric("dotProduct"), _metric("cosine")) == (0, 1, 2)
     with pytest.raises(Exception):
         _metric("manhattan")
+
+
+def test_compose_id_filters_matches_idfilterpassn():
+    """keep = (allow0 AND ... AND allow3) AND NOT deny, out-of-range ids never pass (IDFilter.swift:140-176)."""
+    rng = np.random.default_rng(9)
+    cap = 777
+    allows = [IDFilter(cap, "allow").set(rng.choice(cap, 500, replace=False)) for _ in range(3)]
+    deny = IDFilter(cap, "deny").set(rng.choice(cap, 200, replace=False))
+    f = compose_id_filters(allows, deny)
+    assert f.mode == IDFilter.ALLOW and f.capacity == cap
+    ids = np.arange(-2, cap + 100)
+    want = np.ones(ids.size, dtype=bool)
+    for a in allows:
+        want &= a.test(ids)
+    want &= deny.test(ids)                                           # a denylist passes ids whose bit is clear
+    assert np.array_equal(f.test(ids), want)
+    assert not (int(f.words[-1]) >> (cap & 63))                      # nothing set past the domain
+    # no allowlist: everything in range starts allowed; nil filters are skipped
+    only_deny = compose_id_filters([None], deny)
+    assert np.array_equal(only_deny.test(ids), deny.test(ids))
+    assert compose_id_filters(capacity=10).test(np.arange(12)).tolist() == [True] * 10 + [False] * 2
+    with pytest.raises(ValueError):
+        compose_id_filters([allows[0]] * 5)
+    with pytest.raises(ValueError):
+        compose_id_filters([IDFilter(cap + 1, "allow")], deny)

@@ -72,6 +72,33 @@ class IDFilter:
         return inside & (bit if self.mode == 0 else ~bit)
 
 
+def compose_id_filters(allows=(), deny=None, capacity=None):
+    """idFilterPassN (Operations/Filtering/IDFilter.swift:140-176): keep = allow0 AND allow1 AND ... AND NOT deny, ids
+    outside [0, capacity) never pass -- folded on the host into ONE allowlist bitset, which is what the device takes.
+    ``allows``: up to four allowlist IDFilters (the reference's limit), ``deny``: one denylist IDFilter; all over the same
+    capacity (or pass ``capacity``).  With no allowlist every in-range id starts allowed."""
+    allows = [a for a in allows if a is not None]
+    if len(allows) > 4:
+        raise ValueError("up to 4 allowlists + 1 denylist (IDFilter.swift:219)")
+    parts = allows + ([deny] if deny is not None else [])
+    if capacity is None:
+        if not parts:
+            raise ValueError("capacity is needed when no filter is given")
+        capacity = parts[0].capacity
+    if any(f.capacity != capacity for f in parts):
+        raise ValueError("composed filters must cover the same id domain")
+    if any(a.mode != IDFilter.ALLOW for a in allows) or (deny is not None and deny.mode != IDFilter.DENY):
+        raise ValueError("allows must be allowlists and deny a denylist")
+    out = IDFilter(capacity, "allow", initial_bit=True)
+    for a in allows:
+        out.words &= a.words
+    if deny is not None:
+        out.words &= ~deny.words
+    if capacity & 63 and out.words.size:                             # bits past the domain stay clear
+        out.words[-1] &= np.uint64((1 << (capacity & 63)) - 1)
+    return out
+
+
 class _Index:
     kind = INDEX_FLAT
 
