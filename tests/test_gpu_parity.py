@@ -3,6 +3,8 @@ on the same seeded inputs.  Bars (BASELINE.json north_star): PQ codes and IVF li
 distances within 1e-5 relative; top-k id sets equal except at ties inside that tolerance.  Where the GPU
 kernel restates the reference's summation order (flat scan, probe scores, LUT, materialising ADC) the
 comparison is bit-exact as well."""
+import os
+
 import numpy as np
 import pytest
 
@@ -522,6 +524,36 @@ def test_batchwide_tables_equal_in_kernel_tables(oracle, monkeypatch, d, metric)
     d1, i1 = idx.batch_search(q, k)                                   # 512 KB of codebooks or more: batch-wide tables
     monkeypatch.setenv("VIX_DISABLE_LUT_IMAGE", "1")
     d2, i2 = idx.batch_search(q, k)
+    assert np.array_equal(i1, i2) and np.array_equal(bits(d1), bits(d2))
+
+
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="two-pipeline scan (VIX_SCAN_DUAL=1): written after this round's GPU budget was spent -- opt-in and "
+                           "not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs the comparison")
+@pytest.mark.parametrize("d,m,metric,nq,k,filtered", [
+    (96, 48, "euclidean", 700, 10, False),     # C5-shaped: three shared 64 KB tables
+    (128, 16, "euclidean", 333, 10, False),    # one table, both pipelines in its two half rows
+    (128, 32, "dotProduct", 301, 32, False),   # k = 32: the queues hold k + 32 entries, a flush per accepted chunk
+    (96, 48, "euclidean", 1, 5, False),        # one query: the second pipeline finds no work
+    (128, 32, "euclidean", 257, 10, True),     # id filter
+])
+def test_two_pipeline_scan_equals_one_pipeline(oracle, monkeypatch, d, m, metric, nq, k, filtered):
+    """ivfpq_scan_kernel<G, FILTER, false, 2> (two query pipelines of 8 warps per CTA) looks up the same tables in the same
+    order as the one-pipeline kernel and selects by the same total order: identical ids and distance bits."""
+    from vectorindex_b200.index import IDFilter, IVFPQIndex
+    n, kc, nprobe = 30000, 48, 12
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=d + m + k)
+    idx = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse); idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb)
+    flt = None
+    if filtered:
+        flt = IDFilter(n, "allow")
+        flt.set(np.arange(0, n, 3))
+    monkeypatch.delenv("VIX_SCAN_DUAL", raising=False)
+    d1, i1 = idx.batch_search(q, k, filter=flt)
+    monkeypatch.setenv("VIX_SCAN_DUAL", "2")                         # 2: a launch that cannot take two pipelines is an error
+    d2, i2 = idx.batch_search(q, k, filter=flt)
     assert np.array_equal(i1, i2) and np.array_equal(bits(d1), bits(d2))
 
 

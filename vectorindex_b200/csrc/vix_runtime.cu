@@ -93,7 +93,8 @@ int* pipeline_error_flag() {
 int check_pipeline_error() {
     if (g_pipe_flag && *reinterpret_cast<volatile int*>(g_pipe_flag) != 0) {
         *reinterpret_cast<volatile int*>(g_pipe_flag) = 0;
-        set_error("tensor-core pipeline timed out waiting on a barrier; the results of that call are invalid");
+        set_error("a device pipeline gave up (tensor-core barrier time-out, or a scan launch whose shared-memory layout did "
+                  "not fit); the results of that call are invalid");
         return VIX_ERR_CUDA;
     }
     return VIX_OK;
