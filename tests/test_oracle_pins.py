@@ -5,7 +5,9 @@
   E2  the bit-level golden vector of Tests/VectorIndexTests/PQTrainTests.swift:724-817
   E3  the published IVF recall 0.9565000000000008 (.bench/post-phase3/ivf_search.json:54)
   +   tie-break pins: TelemetryRecorderTests.swift:229-241, IVFSelectTests.swift:305-347,
-      IVFListVecsReaderRerankTests.swift:66-126 (tie -> smaller id)
+      IVFListVecsReaderRerankTests.swift:5-126 (tie -> smaller id)
+  +   tolerance fixtures, at the reference tests' own accuracies: ScoreBlockTests.swift:24-131 (LCG block, L2^2 / dot /
+      cosine, 1e-4), IVFBatchGEMMParityTests.swift:160-190 (CentroidBatchScore, 1e-3)
 """
 import numpy as np
 import pytest
@@ -150,3 +152,84 @@ def test_topk_min_tie_smaller_id(oracle):
     ms, mi = oracle.merge_topk([(np.array([0.0, 1.0], np.float32), np.array([7, 1], np.int32)),
                                 (np.array([0.0, 0.5], np.float32), np.array([3, 9], np.int32))], 3)
     assert mi.tolist() == [3, 7, 9]
+
+
+# ------------------------------------------------------------------------------------------ tolerance fixtures
+_M64 = (1 << 64) - 1
+
+
+def _lcg_stream(seed):
+    """The LCG every reference fixture uses: s = 2862933555777941757 s + 3037000493 (mod 2^64)."""
+    s = seed & _M64
+    while True:
+        s = (2862933555777941757 * s + 3037000493) & _M64
+        yield s
+
+
+def _seq(fn, a, b):
+    """Scalar float32 loop of the reference's test-side references (`expected += ...` in row order)."""
+    acc = np.float32(0)
+    for x, y in zip(a, b):
+        acc = np.float32(acc + fn(np.float32(x), np.float32(y)))
+    return acc
+
+
+def test_scoreblock_lcg_fixture(oracle):
+    """ScoreBlockTests.swift:24-131: n = 32, d = 16 blocks from the LCG (u = Float(s >> 40) / 2^24, value 2u - 1; seeds
+    0x9E3779B97F4A7C15 / 0xD1B54A32D192ED03); L2^2, dot and cosine of ScoreBlock.run against the scalar loops of the test,
+    at the test's own accuracy 1e-4."""
+    def seeded(count, seed):
+        g = _lcg_stream(seed)
+        return np.array([np.float32(np.float32(next(g) >> 40) / np.float32(1 << 24)) * np.float32(2) - np.float32(1)
+                         for _ in range(count)], dtype=np.float32)
+    n, d = 32, 16
+    q = seeded(d, 0x9E3779B97F4A7C15)
+    xb = seeded(n * d, 0xD1B54A32D192ED03).reshape(n, d)
+    assert q.min() >= -1 and q.max() < 1 and abs(float(xb.mean())) < 0.2
+    l2 = oracle.l2sqr_block(q, xb)
+    ip = oracle.ip_block(q, xb)
+    cd, ci, _ = oracle.flat_search(q[None, :], xb, n, 2)                     # cosine: API distance 1 - similarity
+    cos = np.empty(n, np.float32)
+    cos[ci[0]] = np.float32(1) - cd[0]
+    eps = np.float32(1e-12)
+    q_inv = np.float32(1) / (np.sqrt(_seq(lambda a, b: a * b, q, q)) + eps)
+    for i in range(n):
+        assert abs(l2[i] - _seq(lambda a, b: (a - b) * (a - b), q, xb[i])) <= 1e-4, i
+        dot = _seq(lambda a, b: a * b, q, xb[i])
+        assert abs(ip[i] - dot) <= 1e-4, i
+        x_inv = np.float32(1) / (np.sqrt(_seq(lambda a, b: a * b, xb[i], xb[i])) + eps)
+        want = max(np.float32(-1), min(np.float32(1), np.float32(np.float32(dot * q_inv) * x_inv)))
+        assert abs(cos[i] - want) <= 1e-4, i
+
+
+@pytest.mark.parametrize("metric,seed", [(0, 99), (1, 123)])
+def test_centroid_batch_score_lcg_fixture(oracle, metric, seed):
+    """IVFBatchGEMMParityTests.swift:160-190: d = 12, kc = 7, nq = 5 from LCG(state) with nextInRange(-1...1) =
+    -1 + 2 * Float(s >> 11) / 2^53; CentroidBatchScore against `cNormSq - 2 dot` / `-dot` at the test's accuracy 1e-3."""
+    g = _lcg_stream(seed)
+
+    def nxt():
+        return np.float32(-1) + np.float32(2) * np.float32(np.float32(next(g) >> 11) / np.float32(1 << 53))
+    d, kc, nq = 12, 7, 5
+    queries = np.array([[nxt() for _ in range(d)] for _ in range(nq)], dtype=np.float32)
+    cents = np.array([[nxt() for _ in range(d)] for _ in range(kc)], dtype=np.float32)
+    got = oracle.centroid_batch_score(queries, cents, metric)
+    for qi in range(nq):
+        for c in range(kc):
+            dot = _seq(lambda a, b: a * b, queries[qi], cents[c])
+            want = (_seq(lambda a, b: a * b, cents[c], cents[c]) - np.float32(2) * dot) if metric == 0 else -dot
+            assert abs(got[qi, c] - want) <= 1e-3, (qi, c)
+
+
+def test_rerank_reader_fixtures(oracle):
+    """IVFListVecsReaderRerankTests.swift:5-126: rows (0,0) (1,0) (0,1) (1,1); the nearest two of q = (0.95, 0.06) are ids
+    1, 3; for q = (0.95, 0.05) ids 0 and 3 tie for second place and the smaller id wins (L2Sqr.run scores + the
+    (score, id) order of the selection)."""
+    rows = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float32)
+    s = oracle.l2sqr_block(np.array([0.95, 0.06], np.float32), rows)
+    _, ids = oracle.select_topk(s, 2, oracle.ORDER_MIN)
+    assert ids.tolist() == [1, 3]
+    s = oracle.l2sqr_block(np.array([0.95, 0.05], np.float32), rows)
+    assert s[0] == s[3]
+    _, ids = oracle.select_topk(s, 2, oracle.ORDER_MIN)
+    assert ids.tolist() == [1, 0]
