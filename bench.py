@@ -8,7 +8,8 @@ top-k [-> all-gather + mergeTopK at N > 1]) over ONE batch of nq synthetic queri
 IVF-PQ index.  The default workload is BASELINE.json's headline configuration (configs[4], "c5"):
 IVF-PQ 100M x 96 Deep-shaped, nlist=65536, nprobe=64, M=48, 10k queries, k=10.  The database is FIXED as N
 grows (strong scaling): it is partitioned over the ranks, queries are replicated, each rank scans its
-partition and the per-rank top-k lists are merged after one all-gather.
+partition and the per-rank top-k lists are merged after one all-gather.  (`--partition replicate`: every rank keeps a
+full replica and the batch is split by query instead -- for indexes that fit one GPU; not the default.)
 
 Printed JSON line (rank 0): `value` = queries/s with queries and results resident in HBM; `e2e` = the same
 through the public API with pinned HOST query/result buffers (H2D + D2H inside the timed region);
@@ -154,7 +155,7 @@ def chunks_of(n):
 
 
 # ------------------------------------------------------------------------------------------------ build
-def build_index(cfg, synth, rank, world, bcast=None):
+def build_index(cfg, synth, rank, world, bcast=None, partition="lists"):
     """Train on the first chunks (rank 0, parameters broadcast), then build: every rank generates, assigns and
     encodes ITS chunks of the database; rows travel to the rank owning their inverted list (all-to-all).
     Returns (per-rank index, sharded view or None, exact ground truth of the first GT_QUERIES queries over the
@@ -162,7 +163,7 @@ def build_index(cfg, synth, rank, world, bcast=None):
     import torch
     from vectorindex_b200 import kernels as vk
     from vectorindex_b200._lib import KMeansCfg, PQTrainCfg
-    from vectorindex_b200.index import IVFPQIndex, ShardedIVFPQIndex
+    from vectorindex_b200.index import IVFPQIndex, ReplicatedIVFPQIndex, ShardedIVFPQIndex
 
     n, d, nlist, m = cfg["n"], cfg["d"], cfg["nlist"], cfg["m"]
     idx = IVFPQIndex(d, cfg.get("metric", "euclidean"), nlist=nlist, nprobe=cfg["nprobe"], m=m)
@@ -188,7 +189,8 @@ def build_index(cfg, synth, rank, world, bcast=None):
         if rank != 0:
             idx.set_coarse(coarse)
             idx.set_codebooks(cb, cn)
-        sh = ShardedIVFPQIndex.wrap(idx, nlist, cfg["nprobe"])
+        sh = (ReplicatedIVFPQIndex if partition == "replicate" else ShardedIVFPQIndex).wrap(idx, nlist, cfg["nprobe"])
+    if world > 1 and partition != "replicate":
         # list-block boundaries that equalise the ranks' expected scan work (sum of squared list lengths), from the list
         # sizes of a sample: rank 0 assigns its training chunk, every rank gets the boundaries
         from vectorindex_b200.index import balanced_list_bounds
@@ -288,6 +290,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("VIX_BENCH_WORKLOAD", "c5"), choices=sorted(PRESETS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--partition", default=os.environ.get("VIX_BENCH_PARTITION", "lists"), choices=["lists", "replicate"],
+                    help="N > 1: inverted lists sharded over the ranks (default, what north_star names) or every rank a full "
+                         "replica with the batch split by query (indexes that fit one GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off) "
@@ -325,7 +330,8 @@ def main():
     synth = Synth(cfg, dev)
     eff_world = world if args.impl == "ours" else 1
     bcast = (lambda t: dist.broadcast(t, 0)) if dist else None
-    idx, sh, (gt_d, gt_i), build_t = build_index(cfg, synth, rank if args.impl == "ours" else 0, eff_world, bcast)
+    idx, sh, (gt_d, gt_i), build_t = build_index(cfg, synth, rank if args.impl == "ours" else 0, eff_world, bcast,
+                                                 args.partition)
     log(f"[bench] rank {rank}: built {idx.count} vectors ({build_t})")
     nq, k, d = cfg["nq"], cfg["k"], cfg["d"]
     q_dev = synth.queries(nq)
@@ -336,8 +342,11 @@ def main():
 
     base_cfg = {"workload": cfg["label"], "n": cfg["n"], "d": d, "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
                 "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": cfg.get("metric", "euclidean"),
-                "partition": f"inverted lists in contiguous blocks over {eff_world} rank(s); queries replicated; probe selection "
-                             "split by query block + all-gather of list ids; per-rank top-k merged by all-gather + mergeTopK",
+                "partition": (f"inverted lists in contiguous blocks over {eff_world} rank(s); queries replicated; probe selection "
+                              "split by query block + all-gather of list ids; per-rank top-k merged by all-gather + mergeTopK")
+                if args.partition == "lists" or eff_world == 1 else
+                             f"full replica on each of {eff_world} rank(s); batch split by query block; all-gather of the "
+                             "finished [nq/world x k] blocks",
                 "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps",
                 "build": build_t}
 

@@ -118,6 +118,35 @@ def _worker(rank, world, port, out_path):
         dist.destroy_process_group()
 
 
+def _replica_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vectorindex_b200.index import ReplicatedIVFPQIndex
+        xb, q, coarse, cb, norms, asg, m, kc = _problem()
+        nprobe, k = 5, 10
+        rp = ReplicatedIVFPQIndex(xb.shape[1], "euclidean", nlist=kc, nprobe=nprobe, m=m, local=OracleLocalIndex(xb.shape[1], m))
+        rp.set_parameters(coarse, cb, norms)
+        ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
+        cut = 1100                                                         # ragged contributions: 1100 rows / 1900 rows
+        mine = np.arange(0, cut) if rank == 0 else np.arange(cut, xb.shape[0])
+        half = mine.size // 3
+        rp.add(xb[mine[:half]], ids[mine[:half]])
+        rp.add(xb[mine[half:]], ids[mine[half:]])
+        rp.add(xb[:0], ids[:0])                                           # nothing from anybody
+        assert rp.local.ids.size == xb.shape[0]                           # every replica holds every row ...
+        assert np.array_equal(np.sort(rp.local.ids), ids)                 # ... exactly once
+        md, mi = rp.batch_search(q, k)                                    # 25 queries over 2 ranks: ragged blocks (13 + 12)
+        bd, bi = rp.batch_search(q, k, gather=False)
+        lo, cnt, _ = rp.query_block(q.shape[0])
+        assert np.array_equal(np.asarray(bi), np.asarray(mi)[lo:lo + cnt])
+        np.savez(out_path + f".{rank}.npz", md=np.asarray(md), mi=np.asarray(mi), order=rp.local.ids)
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -181,6 +210,24 @@ def test_sharded_search_equals_single_process_oracle(tmp_path, oracle):
     assert np.array_equal(res["probes"], op)                              # merged probe lists == single-GPU order
     assert np.array_equal(res["mi"], oi)
     assert np.array_equal(res["md"].view(np.uint32), od.view(np.uint32))
+
+
+def test_replicated_search_equals_single_process_oracle(tmp_path, oracle):
+    """ReplicatedIVFPQIndex at world size 2: ragged build contributions and ragged query blocks; every rank ends with the
+    whole answer, bit-identical to the single-process oracle search, and the replicas hold their rows in the same order."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "rep")
+    mp.spawn(_replica_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    xb, q, coarse, cb, norms, asg, m, kc = _problem()
+    ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
+    off, order = oracle.build_lists(asg, kc)
+    codes = oracle.pq_encode_u8(xb, cb, m, 256, centroid_sq=norms.reshape(-1), coarse=coarse, assign_=asg)
+    od, oi, _ = oracle.ivfpq_search(q, coarse, cb, norms, off, codes[order], ids[order], m, 256, 5, 10, 0)
+    res = [np.load(out + f".{r}.npz") for r in range(2)]
+    for r in res:
+        assert np.array_equal(r["mi"], oi)
+        assert np.array_equal(r["md"].view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(res[0]["order"], res[1]["order"])
 
 
 def test_host_merge_matches_definition():

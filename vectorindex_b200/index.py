@@ -720,3 +720,84 @@ class ShardedIVFPQIndex:
         if was_numpy and _lib._is_torch(md):
             md, mi = md.cpu().numpy(), mi.cpu().numpy()
         return md, mi
+
+
+class ReplicatedIVFPQIndex(ShardedIVFPQIndex):
+    """The other way to use several GPUs, for an index that fits ONE of them (BASELINE configs[4] is 12.5 GB of 180 GB):
+    every rank holds ALL inverted lists and a batch is partitioned by QUERY.  Queries are independent units, so the data
+    path has no exchange step at all -- a rank runs the single-GPU search (probe selection + fused scan + top-k, at the
+    single-GPU efficiency: whole probe sets per query, the global k-th best as the threshold) on its 1/world of the batch;
+    one all-gather of the finished [nq/world x k] blocks hands every rank the whole answer (callers that consume their
+    own block skip it: ``gather=False``).  The list-sharded ``ShardedIVFPQIndex`` remains the layout for indexes larger
+    than one GPU's memory (and the one `north_star` names).
+
+    build   a rank assigns + encodes the rows it is handed (1/world of the encoding work); the encoded rows
+            (assignment, codes, ids: m + 12 bytes each) are all-gathered and appended everywhere, rank by rank in
+            the same order, so every replica holds identical lists;
+    search  identical to ``IVFPQIndex.batch_search`` on the rank's query block: results are the single-GPU results by
+            construction."""
+
+    def set_list_bounds(self, bounds):
+        raise ValueError("a replicated index has no list partition")
+
+    def add(self, vectors, ids):
+        import torch
+        import torch.distributed as dist
+        assign, codes = self.local.encode(vectors)
+        if self.world == 1:
+            self.local.add_encoded(assign, codes, ids)
+            return
+        assign, codes, ids = self._to_comm(assign), self._to_comm(codes), self._to_comm(ids)
+        n = int(assign.shape[0])
+        cnt = torch.tensor([n], dtype=torch.int64, device=assign.device)
+        counts = [int(v) for v in self._all_gather(cnt).view(-1).tolist()]
+        cap = max(counts)
+        if cap == 0:
+            return
+
+        def gathered(t):
+            if n < cap:                                                   # ragged: pad to the largest contribution
+                pad = torch.zeros((cap - n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                t = torch.cat([t, pad])
+            return self._all_gather(t.contiguous())                       # [world][cap, ...]
+
+        g_assign, g_codes, g_ids = gathered(assign.to(torch.int32)), gathered(codes), gathered(ids.to(torch.int64))
+        for r in range(self.world):
+            c = counts[r]
+            if c == 0:
+                continue
+            a, co, i = g_assign[r, :c].contiguous(), g_codes[r, :c].contiguous(), g_ids[r, :c].contiguous()
+            if not self._nccl():
+                a, co, i = a.numpy(), co.numpy(), i.numpy()
+            self.local.add_encoded(a, co, i)
+
+    def batch_search(self, queries, k, nprobe=0, gather=True):
+        """[nq x k] (distances, ids) of the whole batch on every rank (``gather=False``: this rank's block only, rows
+        ``query_block(nq)``)."""
+        import torch
+        was_numpy = not _lib._is_torch(queries)
+        nprobe = nprobe if nprobe > 0 else self.nprobe
+        nq = int(queries.shape[0])
+        lo, cnt, per = self.query_block(nq)
+        qb = queries[lo:lo + cnt]
+        if was_numpy and self.world > 1 and self._nccl():
+            qb = self._to_comm(np.ascontiguousarray(qb, dtype=np.float32))      # only this rank's block crosses PCIe
+        if hasattr(self.local, "batch_search"):
+            d_loc, i_loc = self.local.batch_search(qb, k, nprobe)
+        else:                                                                  # oracle-backed stand-in of the gloo tests
+            probes = self.local.probe_range(qb, nprobe, 0, self.kc)[0]
+            d_loc, i_loc = self.local.search_with_probes(qb, k, probes)
+        if self.world == 1 or not gather:
+            return d_loc, i_loc
+        d_loc, i_loc = self._to_comm(d_loc), self._to_comm(i_loc)
+        if cnt < per:                                                          # ragged last block: pad, gather, trim
+            pad_d = torch.full((per - cnt, k), float("nan"), dtype=d_loc.dtype, device=d_loc.device)
+            pad_i = torch.full((per - cnt, k), -1, dtype=i_loc.dtype, device=i_loc.device)
+            d_loc, i_loc = torch.cat([d_loc, pad_d]), torch.cat([i_loc, pad_i])
+        md = self._all_gather(d_loc.contiguous()).view(self.world * per, k)[:nq]
+        mi = self._all_gather(i_loc.contiguous()).view(self.world * per, k)[:nq]
+        if was_numpy:
+            if md.is_cuda:
+                return self._to_host(md.contiguous()), self._to_host(mi.contiguous())
+            return md.numpy().copy(), mi.numpy().copy()
+        return md.contiguous(), mi.contiguous()
