@@ -119,7 +119,9 @@ int vix_merge_topk_f32(const float* scores, const int64_t* ids, const int32_t* l
 /* a6-a9  Coarse quantiser                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
 /* CentroidBatchScore.run (Kernels/CentroidBatchScore.swift:39-88): out[q x kc], smaller is better:
- * L2 => ||c||^2 - 2<q,c> (||q||^2 omitted), IP => -<q,c>.  centroid_norms may be NULL (computed). */
+ * L2 => ||c||^2 - 2<q,c> (||q||^2 omitted), IP => -<q,c>, cosine => 1 - <q,c> qInv cInv with the near-zero-norm
+ * guard (sqrt(||q||^2 ||c||^2) <= ulpOfOne => 1; :70-84).  centroid_norms = ||c||^2 (Norms.l2NormSquared,
+ * IVFIndex.swift:470-485), may be NULL (computed). */
 int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* centroids, int kc,
                                  int d, int metric, const float* centroid_norms, float* out);
 

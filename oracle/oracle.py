@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF = {}
 
-METRIC_L2, METRIC_IP = 0, 1
+METRIC_L2, METRIC_IP, METRIC_COSINE = 0, 1, 2
 ORDER_MIN, ORDER_MAX = 0, 1
 
 f32p = C.POINTER(C.c_float)
@@ -159,7 +159,7 @@ def centroid_batch_score(queries, centroids, metric=METRIC_L2, cnorms=None):
     queries, centroids = _f32(queries), _f32(centroids)
     q, d = queries.shape
     kc = centroids.shape[0]
-    if cnorms is None and metric == METRIC_L2:
+    if cnorms is None and metric in (METRIC_L2, METRIC_COSINE):
         cnorms = centroid_norms(centroids)
     cn = _f32(cnorms) if cnorms is not None else None
     out = np.empty((q, kc), dtype=np.float32)
@@ -172,7 +172,7 @@ def probe_select_batch(queries, centroids, nprobe, metric=METRIC_L2, cnorms=None
     queries, centroids = _f32(queries), _f32(centroids)
     q, d = queries.shape
     kc = centroids.shape[0]
-    if cnorms is None and metric == METRIC_L2:
+    if cnorms is None and metric in (METRIC_L2, METRIC_COSINE):
         cnorms = centroid_norms(centroids)
     cn = _f32(cnorms) if cnorms is not None else None
     idx = np.empty((q, nprobe), dtype=np.int32)
@@ -196,7 +196,7 @@ def assign(x, centroids):
 def assign_metric(x, centroids, metric, cnorms=None):
     x, centroids = _f32(x), _f32(centroids)
     n, d = x.shape
-    if cnorms is None and metric == METRIC_L2:
+    if cnorms is None and metric in (METRIC_L2, METRIC_COSINE):
         cnorms = centroid_norms(centroids)
     cn = _f32(cnorms) if cnorms is not None else None
     a = np.empty(n, dtype=np.int32)

@@ -367,6 +367,19 @@ void vo_centroid_batch_score(const float* queries, int64_t q, const float* centr
             if (metric == VO_METRIC_L2) v = v + centroid_norms[ci];
             row[ci] = v;
         }
+        if (metric == VO_METRIC_COSINE) {
+            /* CentroidBatchScore.swift:70-84 (queriesAreNormalized == false): the row holds -<q, c>;
+             * 1 - dot qInv cInv = 1 + row qInv cInv, except where the near-zero-norm guard of the single-query path
+             * (IVFIndex.swift:558-561) forces the largest distance, 1.  centroid_norms = ||c||^2 by
+             * Norms.l2NormSquared, cInv = 1 / (sqrt(||c||^2) + 1e-12) (rebuildCentroidCache, IVFIndex.swift:470-485). */
+            const float qn = vo_norm_l2sq(qp, d);
+            const float qinv = 1.0f / (sqrtf(qn) + 1e-12f);
+            for (int ci = 0; ci < kc; ++ci) {
+                const float cinv = 1.0f / (sqrtf(centroid_norms[ci]) + 1e-12f);
+                const float denom = sqrtf(qn * centroid_norms[ci]);
+                row[ci] = denom > 1.1920929e-07f ? (1.0f + (row[ci] * qinv) * cinv) : 1.0f;
+            }
+        }
     }
 }
 

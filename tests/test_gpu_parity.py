@@ -373,6 +373,27 @@ def test_centroid_scores_and_probe_selection(oracle, vk, metric):
     assert np.array_equal(gi, oi) and np.array_equal(bits(gs), bits(os_))
 
 
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="cosine CentroidBatchScore epilogue: written after this round's GPU budget was spent, not yet run on a "
+                           "B200; VIX_TEST_EXPERIMENTAL=1 runs it")
+def test_centroid_scores_cosine_guarded(oracle, vk):
+    """CentroidBatchScore.swift:70-84: 1 - <q, c> qInv cInv with the near-zero-norm guard, bit for bit (zero centroid, zero
+    query and a tiny-norm centroid under the guard => exactly 1)."""
+    rng = np.random.default_rng(21)
+    q = rng.standard_normal((70, 96)).astype(np.float32)
+    c = (rng.standard_normal((300, 96)) * rng.uniform(0.1, 3.0, (300, 1))).astype(np.float32)
+    c[7] = 0.0
+    c[9] = 1e-6 * c[9]
+    c[11] = 1e-9
+    q[3] = 0.0
+    got = vk.centroid_batch_score(q, c, 2)
+    want = oracle.centroid_batch_score(q, c, 2)
+    assert np.array_equal(bits(got), bits(want))
+    assert (got[:, 7] == 1.0).all() and (got[3] == 1.0).all()
+    cn = oracle.centroid_norms(c)
+    assert np.array_equal(bits(vk.centroid_batch_score(q, c, 2, cn)), bits(want))
+
+
 def test_probe_selection_pins_and_padding(oracle, vk):
     cents = np.ones((50, 8), dtype=np.float32)                              # IVFSelectTests.swift:305-347
     gi, _ = vk.ivf_select_nprobe_batch_f32(np.zeros((2, 8), np.float32), cents, 20)

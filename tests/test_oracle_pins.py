@@ -233,3 +233,35 @@ def test_rerank_reader_fixtures(oracle):
     assert s[0] == s[3]
     _, ids = oracle.select_topk(s, 2, oracle.ORDER_MIN)
     assert ids.tolist() == [1, 0]
+
+
+def test_centroid_batch_score_cosine_degenerate_centroid_fixture(oracle):
+    """IVFBatchGEMMParityTests.swift:192-214: LCG(456), d = 12, kc = 6, nq = 5, centroid 2 all zero; cosine scores
+    1 - dot qInv cInv at the test's accuracy 1e-3, and the degenerate centroid forced to exactly 1."""
+    g = _lcg_stream(456)
+
+    def nxt():
+        return np.float32(-1) + np.float32(2) * np.float32(np.float32(next(g) >> 11) / np.float32(1 << 53))
+    d, kc, nq = 12, 6, 5
+    queries = np.array([[nxt() for _ in range(d)] for _ in range(nq)], dtype=np.float32)
+    cents = np.array([[nxt() for _ in range(d)] for _ in range(kc)], dtype=np.float32)
+    cents[2] = 0.0
+    got = oracle.centroid_batch_score(queries, cents, 2)
+    eps = np.float32(1e-12)
+    for qi in range(nq):
+        qn = _seq(lambda a, b: a * b, queries[qi], queries[qi])
+        for c in range(kc):
+            cn = _seq(lambda a, b: a * b, cents[c], cents[c])
+            dot = _seq(lambda a, b: a * b, queries[qi], cents[c])
+            if np.sqrt(np.float32(qn * cn)) > np.finfo(np.float32).eps:
+                want = np.float32(1) - dot * (np.float32(1) / (np.sqrt(qn) + eps)) * (np.float32(1) / (np.sqrt(cn) + eps))
+            else:
+                want = np.float32(1)
+            assert abs(got[qi, c] - want) <= 1e-3, (qi, c)
+        assert got[qi, 2] == np.float32(1)
+    # probe order and list assignment under cosine follow the same scores (IVFIndex.swift:376-435, 905-927)
+    pid, psc = oracle.probe_select_batch(queries, cents, 3, 2)
+    for qi in range(nq):
+        order = np.lexsort((np.arange(kc), got[qi]))[:3]
+        assert pid[qi].tolist() == order.tolist() and np.array_equal(psc[qi], got[qi][order])
+    assert np.array_equal(oracle.assign_metric(queries, cents, 2), np.argmin(got, axis=1))

@@ -466,6 +466,21 @@ static int flat_search_impl(const float* q, int64_t nq, const float* xb, int64_t
     return pair_topk<SpecDirect16L2>(p, k, 0, raw_scores ? 0 : 1, out_dist, out_ids, nullptr);
 }
 
+// CentroidBatchScore.swift:70-84, cosine: the block holds -<q, c>; 1 - dot qInv cInv = 1 + row qInv cInv, except where the
+// near-zero-norm guard of the single-query path (IVFIndex.swift:558-561) forces the largest distance, 1.
+// qn / cn = ||.||^2 by Norms.l2NormSquared; the inverse norms are 1 / (sqrt(.) + 1e-12) (IVFIndex.swift:470-485).
+__global__ void cbs_cosine_epilogue_kernel(float* __restrict__ out, int64_t nq, int kc, const float* __restrict__ qn,
+                                           const float* __restrict__ cn) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * (int64_t)kc) return;
+    const int64_t qi = i / kc;
+    const float qn2 = qn[qi], cn2 = cn[i - qi * kc];
+    const float qinv = __fdiv_rn(1.0f, fadd(__fsqrt_rn(qn2), 1e-12f));
+    const float cinv = __fdiv_rn(1.0f, fadd(__fsqrt_rn(cn2), 1e-12f));
+    const float denom = __fsqrt_rn(fmul(qn2, cn2));
+    out[i] = denom > 1.1920929e-07f ? fadd(1.0f, fmul(fmul(out[i], qinv), cinv)) : 1.0f;
+}
+
 int centroid_batch_score_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric,
                                 const float* cnorm, float* out) {
     if (nq == 0 || kc == 0) return VIX_OK;
@@ -848,20 +863,32 @@ int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* c
     VIX_TRY(ensure_device());
     VIX_REQUIRE(queries && centroids && out, VIX_ERR_NULL_PTR, "vix_centroid_batch_score_f32: null pointer");
     VIX_REQUIRE(d > 0 && kc > 0 && q >= 0, VIX_ERR_INVALID_DIM, "vix_centroid_batch_score_f32: bad shape");
-    VIX_REQUIRE(metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP, VIX_ERR_INVALID_PARAM, "metric");
+    VIX_REQUIRE(metric == VIX_METRIC_L2 || metric == VIX_METRIC_IP || metric == VIX_METRIC_COSINE, VIX_ERR_INVALID_PARAM,
+                "vix_centroid_batch_score_f32: metric");
     if (q == 0) return VIX_OK;
     In<float> dq, dc, dn;
     Out<float> dout;
-    Scratch<float> cn;
+    Scratch<float> cn, qn;
     VIX_TRY(dq.stage(queries, (size_t)q * d));
     VIX_TRY(dc.stage(centroids, (size_t)kc * d));
     VIX_TRY(dout.stage(out, (size_t)q * kc));
     const float* cnp = nullptr;
-    if (metric == VIX_METRIC_L2) {
+    if (metric != VIX_METRIC_IP) {
         if (centroid_norms) { VIX_TRY(dn.stage(centroid_norms, (size_t)kc)); cnp = dn.dev; }
         else { VIX_TRY(cn.alloc((size_t)kc)); VIX_TRY(row_norms_device(dc.dev, kc, d, cn.ptr)); cnp = cn.ptr; }
     }
-    VIX_TRY(centroid_batch_score_device(dq.dev, q, dc.dev, kc, d, metric, cnp, dout.dev));
+    if (metric == VIX_METRIC_COSINE) {
+        // -<q, c> in the contraction's order, then the guarded cosine epilogue over the block
+        VIX_REQUIRE((int64_t)q * kc < (1LL << 38), VIX_ERR_UNSUPPORTED, "vix_centroid_batch_score_f32: cosine block too large");
+        VIX_TRY(centroid_batch_score_device(dq.dev, q, dc.dev, kc, d, VIX_METRIC_IP, nullptr, dout.dev));
+        VIX_TRY(qn.alloc((size_t)q));
+        VIX_TRY(row_norms_device(dq.dev, q, d, qn.ptr));
+        const int64_t total = q * (int64_t)kc;
+        cbs_cosine_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(dout.dev, q, kc, qn.ptr, cnp);
+        VIX_LAUNCH_CHECK();
+    } else {
+        VIX_TRY(centroid_batch_score_device(dq.dev, q, dc.dev, kc, d, metric, cnp, dout.dev));
+    }
     VIX_TRY(dout.commit());
     return finish(dout.is_host());
 }
