@@ -265,3 +265,22 @@ def test_centroid_batch_score_cosine_degenerate_centroid_fixture(oracle):
         order = np.lexsort((np.arange(kc), got[qi]))[:3]
         assert pid[qi].tolist() == order.tolist() and np.array_equal(psc[qi], got[qi][order])
     assert np.array_equal(oracle.assign_metric(queries, cents, 2), np.argmin(got, axis=1))
+
+
+def test_fused_residual_encode_equals_materialised(oracle):
+    """ResidualKernelTests.swift:126-200 (n = 2000, d = 1024, m = 8, ks = 256, kc = 100, uniform [-1, 1)): the fused
+    residual encoder and the plain encoder on materialised residuals give the same codes -- for the restatement and for
+    the reference's own compiled C encoder, which also agree with each other."""
+    rng = np.random.default_rng(1)
+    n, d, m, ks, kc = 2000, 1024, 8, 256, 100
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    cent = rng.uniform(-1, 1, (kc, d)).astype(np.float32)
+    asg = rng.integers(0, kc, n).astype(np.int32)
+    cb = rng.uniform(-1, 1, (m * ks, d // m)).astype(np.float32)
+    r = (x - cent[asg]).astype(np.float32)
+    plain = oracle.pq_encode_u8(r, cb, m, ks)
+    fused = oracle.pq_encode_u8(x, cb, m, ks, coarse=cent, assign_=asg)
+    assert np.array_equal(plain, fused)
+    if oracle.ref_lib() is not None:
+        assert np.array_equal(oracle.ref_encode("cpq_encode_u8_f32", r, cb, m, ks), plain)
+        assert np.array_equal(oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=cent, assign_=asg), fused)

@@ -103,8 +103,10 @@ __device__ __forceinline__ void encode_chunk(XF xf, GF gf, const float* __restri
 constexpr int kEncThreads = 256;
 
 // MODE: arithmetic variant; DSUB > 0: sub-vector in registers, DSUB == 0: generic (shared memory).
-template <int MODE, int DSUB>
-__global__ void __launch_bounds__(kEncThreads)
+// THREADS = rows per CTA: 256, or 64 when the generic path stages long sub-vectors (d / m = 128 with residuals, the shape
+// of the reference's ResidualKernelTests.swift:126-200, needs 2 x 128 x THREADS floats).
+template <int MODE, int DSUB, int THREADS = kEncThreads>
+__global__ void __launch_bounds__(THREADS)
 pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, int dsub_rt,
                  const float* __restrict__ codebooks, const float* __restrict__ centroid_sq,
                  const float* __restrict__ coarse, const int32_t* __restrict__ assign,
@@ -115,15 +117,15 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
     constexpr bool kCsq = (MODE == ENC_CSQ || MODE == ENC_CSQ_RES);
 
     uint8_t* s_codes = smem_raw;                                     // [T x m] bytes (AoS staging)
-    const size_t codes_bytes = ((size_t)kEncThreads * m + 15) & ~(size_t)15;
+    const size_t codes_bytes = ((size_t)THREADS * m + 15) & ~(size_t)15;
     float* s_cb = reinterpret_cast<float*>(smem_raw + codes_bytes);  // [kchunk x dsub]
     float* s_csq = s_cb + (size_t)kchunk * dsub;                     // [kchunk]
     float* s_x = s_csq + kchunk;                                     // generic: [dsub x T] (transposed)
-    float* s_g = s_x + (DSUB > 0 ? 0 : (size_t)dsub * kEncThreads);  // generic residual: [dsub x T]
+    float* s_g = s_x + (DSUB > 0 ? 0 : (size_t)dsub * THREADS);  // generic residual: [dsub x T]
     (void)s_g;
 
     const int t = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * kEncThreads;
+    const int64_t i0 = (int64_t)blockIdx.x * THREADS;
     const int64_t i = i0 + t;
     const bool live = i < n;
     const float* xi = x + (live ? i : 0) * (int64_t)d;
@@ -141,12 +143,12 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
                 for (int e = 0; e < DSUB; ++e) gr[e] = live ? gi[(size_t)j * DSUB + e] : 0.0f;
             }
         } else {
-            for (int e = 0; e < dsub; ++e) s_x[(size_t)e * kEncThreads + t] = live ? xi[(size_t)j * dsub + e] : 0.0f;
+            for (int e = 0; e < dsub; ++e) s_x[(size_t)e * THREADS + t] = live ? xi[(size_t)j * dsub + e] : 0.0f;
             if (kRes)
-                for (int e = 0; e < dsub; ++e) s_g[(size_t)e * kEncThreads + t] = live ? gi[(size_t)j * dsub + e] : 0.0f;
+                for (int e = 0; e < dsub; ++e) s_g[(size_t)e * THREADS + t] = live ? gi[(size_t)j * dsub + e] : 0.0f;
         }
-        auto xf = [&](int e) -> float { return DSUB > 0 ? xr[e] : s_x[(size_t)e * kEncThreads + t]; };
-        auto gf = [&](int e) -> float { return DSUB > 0 ? gr[e] : s_g[(size_t)e * kEncThreads + t]; };
+        auto xf = [&](int e) -> float { return DSUB > 0 ? xr[e] : s_x[(size_t)e * THREADS + t]; };
+        auto gf = [&](int e) -> float { return DSUB > 0 ? gr[e] : s_g[(size_t)e * THREADS + t]; };
 
         // base2: x2 (or r2), sequential sum, computed once per (vector, subspace)
         float base2 = 0.0f;
@@ -168,9 +170,9 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
             int k1 = min(ks, k0 + kchunk);
             __syncthreads();   // previous chunk fully consumed
             const int cnt = (k1 - k0) * dsub;
-            for (int e = t; e < cnt; e += kEncThreads) s_cb[e] = cbj[(size_t)k0 * dsub + e];
+            for (int e = t; e < cnt; e += THREADS) s_cb[e] = cbj[(size_t)k0 * dsub + e];
             if (kCsq)
-                for (int e = t; e < k1 - k0; e += kEncThreads) s_csq[e] = centroid_sq[(size_t)j * ks + k0 + e];
+                for (int e = t; e < k1 - k0; e += THREADS) s_csq[e] = centroid_sq[(size_t)j * ks + k0 + e];
             __syncthreads();
             encode_chunk<MODE, DSUB>(xf, gf, s_cb, s_csq, k0, k1, dsub, base2, bd, bk);
         }
@@ -183,7 +185,7 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
 
     if (layout != PQ_LAYOUT_AOS) return;
     __syncthreads();
-    const int64_t rows = (n - i0 < kEncThreads) ? (n - i0) : (int64_t)kEncThreads;
+    const int64_t rows = (n - i0 < THREADS) ? (n - i0) : (int64_t)THREADS;
     if (!u4) {
         // contiguous [rows x m] byte slab
         uint8_t* dst = codes + i0 * (int64_t)m;
@@ -193,17 +195,17 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
             const int64_t nv = total >> 4;
             const uint4* src4 = reinterpret_cast<const uint4*>(s_codes);
             uint4* dst4 = reinterpret_cast<uint4*>(dst);
-            for (int64_t e = t; e < nv; e += kEncThreads) dst4[e] = src4[e];
-            for (int64_t e = (nv << 4) + t; e < total; e += kEncThreads) dst[e] = s_codes[e];
+            for (int64_t e = t; e < nv; e += THREADS) dst4[e] = src4[e];
+            for (int64_t e = (nv << 4) + t; e < total; e += THREADS) dst[e] = s_codes[e];
         } else {
-            for (int64_t e = t; e < total; e += kEncThreads) dst[e] = s_codes[e];
+            for (int64_t e = t; e < total; e += THREADS) dst[e] = s_codes[e];
         }
     } else {
         // u4: two codes per byte, low nibble = even subspace (pq_encode.c:594-596)
         const int mb = m >> 1;
         uint8_t* dst = codes + i0 * (int64_t)mb;
         const int64_t total = rows * mb;
-        for (int64_t e = t; e < total; e += kEncThreads) {
+        for (int64_t e = t; e < total; e += THREADS) {
             int64_t r = e / mb;
             int b = (int)(e - r * mb);
             uint8_t c0 = s_codes[(size_t)r * m + 2 * b];
@@ -213,29 +215,45 @@ pq_encode_kernel(const float* __restrict__ x, int64_t n, int d, int m, int ks, i
     }
 }
 
-template <int MODE, int DSUB>
-static int launch_encode(const float* x, int64_t n, int d, int m, int ks, int dsub, const float* cb,
-                         const float* csq, const float* coarse, const int32_t* assign, uint8_t* codes,
-                         int layout, int B, int g, int u4) {
+template <int MODE, int DSUB, int THREADS>
+static int launch_encode_rows(const float* x, int64_t n, int d, int m, int ks, int dsub, const float* cb,
+                              const float* csq, const float* coarse, const int32_t* assign, uint8_t* codes,
+                              int layout, int B, int g, int u4, bool& fits) {
     constexpr bool kRes = (MODE == ENC_CSQ_RES || MODE == ENC_DOT_RES || MODE == ENC_DIRECT_RES);
-    const size_t fixed = (((size_t)kEncThreads * m + 15) & ~(size_t)15)            // code staging
-                       + (DSUB > 0 ? 0 : (size_t)dsub * kEncThreads * 4 * (kRes ? 2 : 1));
+    const size_t fixed = (((size_t)THREADS * m + 15) & ~(size_t)15)                // code staging
+                       + (DSUB > 0 ? 0 : (size_t)dsub * THREADS * 4 * (kRes ? 2 : 1));
     const size_t budget = 200 * 1024;
-    if (fixed + (size_t)(dsub + 1) * 4 > budget) {
-        set_error("pq_encode: d/m = %d with m = %d does not fit the shared-memory staging", dsub, m);
-        return VIX_ERR_UNSUPPORTED;
-    }
+    fits = fixed + (size_t)(dsub + 1) * 4 <= budget;
+    if (!fits) return VIX_OK;
     size_t kfit = (budget - fixed) / ((size_t)(dsub + 1) * 4);
     int kchunk = (int)(kfit < (size_t)ks ? kfit : (size_t)ks);
     if (kchunk < 1) kchunk = 1;
     size_t smem = (size_t)kchunk * (dsub + 1) * 4 + fixed + 16;
-    auto kern = pq_encode_kernel<MODE, DSUB>;
+    auto kern = pq_encode_kernel<MODE, DSUB, THREADS>;
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (n + kEncThreads - 1) / kEncThreads;
-    kern<<<(unsigned)grid, kEncThreads, smem, ctx().stream>>>(x, n, d, m, ks, dsub, cb, csq, coarse, assign, codes,
-                                                              layout, B, g, u4, kchunk);
+    int64_t grid = (n + THREADS - 1) / THREADS;
+    kern<<<(unsigned)grid, THREADS, smem, ctx().stream>>>(x, n, d, m, ks, dsub, cb, csq, coarse, assign, codes,
+                                                          layout, B, g, u4, kchunk);
     VIX_LAUNCH_CHECK();
     return VIX_OK;
+}
+
+template <int MODE, int DSUB>
+static int launch_encode(const float* x, int64_t n, int d, int m, int ks, int dsub, const float* cb,
+                         const float* csq, const float* coarse, const int32_t* assign, uint8_t* codes,
+                         int layout, int B, int g, int u4) {
+    bool fits = false;
+    VIX_TRY((launch_encode_rows<MODE, DSUB, kEncThreads>(x, n, d, m, ks, dsub, cb, csq, coarse, assign, codes, layout, B, g,
+                                                         u4, fits)));
+    if (fits) return VIX_OK;
+    if constexpr (DSUB == 0) {
+        // long sub-vectors: a quarter of the rows per CTA (the staged [dsub x rows] tiles are what does not fit)
+        VIX_TRY((launch_encode_rows<MODE, 0, 64>(x, n, d, m, ks, dsub, cb, csq, coarse, assign, codes, layout, B, g, u4,
+                                                 fits)));
+        if (fits) return VIX_OK;
+    }
+    set_error("pq_encode: d/m = %d with m = %d does not fit the shared-memory staging", dsub, m);
+    return VIX_ERR_UNSUPPORTED;
 }
 
 template <int MODE>
