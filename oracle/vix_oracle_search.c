@@ -970,7 +970,22 @@ void vo_ivfflat_search(const float* queries, int64_t nq, int d, const float* coa
             int l = probes[p];
             for (int64_t r = list_offsets[l]; r < list_offsets[l + 1]; ++r) {
                 const float* v = vecs + r * (int64_t)d;
-                float dist = (metric == VO_METRIC_L2) ? sqrtf(vo_l2sqr_direct(q, v, d)) : -vo_ip(q, v, d);
+                float dist;
+                if (metric == VO_METRIC_L2) dist = sqrtf(vo_l2sqr_direct(q, v, d));
+                else if (metric == VO_METRIC_IP) dist = -vo_ip(q, v, d);
+                else {
+                    /* DistanceUtils.swift:22-38: 1 - clamp(dot / sqrt(|a|^2 |b|^2)), 1 under the near-zero guard.
+                     * dot / sumOfSquares are VectorCore's (not in the tree): stand-ins, tolerance parity only. */
+                    float a2 = 0.0f, b2 = 0.0f;
+                    for (int t = 0; t < d; ++t) { a2 = a2 + q[t] * q[t]; b2 = b2 + v[t] * v[t]; }
+                    const float denom = sqrtf(a2 * b2);
+                    if (!(denom > 1.1920929e-07f)) dist = 1.0f;
+                    else {
+                        float sim = vo_ip(q, v, d) / denom;
+                        sim = sim > 1.0f ? 1.0f : (sim < -1.0f ? -1.0f : sim);
+                        dist = 1.0f - sim;
+                    }
+                }
                 pr[c].s = dist; pr[c].id = (int32_t)ids[r]; pr[c].ord = VO_ORDER_MIN;
                 ++c;
             }

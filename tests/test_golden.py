@@ -85,6 +85,28 @@ def test_oracle_cosine_against_float64(oracle):
         assert d[r][np.where(i[r] == 5)[0][0]] == np.float32(1.0)
 
 
+def test_oracle_ivfflat_cosine_against_float64(oracle):
+    """IVF-Flat under cosine (IVFIndex.swift:376-435, 905-927; DistanceUtils.swift:22-38): the candidates of the probed
+    lists ranked by a float64 evaluation of 1 - <q, x> / (|q| |x|) give the same ids and distances within fp32 rounding."""
+    rng = np.random.default_rng(5)
+    n, d, kc, nq, k, nprobe = 3000, 48, 24, 20, 10, 6
+    x = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3, (n, 1))).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    coarse = x[rng.choice(n, kc, replace=False)].copy()
+    asg = oracle.assign_metric(x, coarse, 2)
+    off, order = oracle.build_lists(asg, kc)
+    ids = np.arange(n, dtype=np.int64)
+    dd, ii = oracle.ivfflat_search(q, coarse, off, x[order], ids[order], nprobe, k, 2)
+    pid, _ = oracle.probe_select_batch(q, coarse, nprobe, 2)
+    for r in range(nq):
+        cand = np.concatenate([order[off[l]:off[l + 1]] for l in pid[r]])
+        x64, q64 = x[cand].astype(np.float64), q[r].astype(np.float64)
+        dist = 1 - (x64 @ q64) / np.linalg.norm(x64, axis=1) / np.linalg.norm(q64)
+        o = np.argsort(dist, kind="stable")[:k]
+        assert set(cand[o].tolist()) == set(ii[r].tolist())
+        assert np.allclose(dist[o], dd[r], atol=3e-6)
+
+
 # ------------------------------------------------------------------------------------------ GPU: C ABI vs golden
 @pytest.mark.gpu
 @pytest.mark.parametrize("problem", ["parity", "random"])

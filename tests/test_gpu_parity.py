@@ -822,6 +822,36 @@ def test_ivfflat_and_flat_index(oracle, metric):
     assert np.array_equal(fi, oi + 100) and np.array_equal(bits(fd), bits(od))
 
 
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="cosine for the IVF-Flat index: written after this round's GPU budget was spent, not yet run on a "
+                           "B200; VIX_TEST_EXPERIMENTAL=1 runs it")
+def test_ivfflat_cosine_index(oracle):
+    """IVFIndex with the cosine metric: lists by the first minimum of the guarded CentroidBatchScore row
+    (IVFIndex.swift:376-435), probes by (score, list id) (:905-927), candidate distances 1 - clamp(dot / sqrt(|q|^2 |x|^2))
+    (DistanceUtils.swift:22-38); a zero vector sits at distance exactly 1."""
+    from vectorindex_b200.index import IVFIndex
+    rng = np.random.default_rng(18)
+    n, d, kc, nq, k, nprobe = 6000, 48, 40, 30, 10, 6
+    xb = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+    xb[17] = 0.0
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    coarse = np.ascontiguousarray(xb[rng.choice(n, kc, replace=False)])
+    coarse[3] = 0.0                                                     # degenerate centroid: score exactly 1
+    ids = np.arange(n, dtype=np.int64) + 100
+    ivf = IVFIndex(d, "cosine", nlist=kc, nprobe=nprobe)
+    ivf.set_coarse(coarse)
+    ivf.batch_insert(xb, ids)
+    asg = oracle.assign_metric(xb, coarse, 2)
+    assert np.array_equal(ivf.list_sizes(), np.bincount(asg, minlength=kc))
+    off, order = oracle.build_lists(asg, kc)
+    od, oi = oracle.ivfflat_search(q, coarse, off, xb[order], ids[order], nprobe, k, 2)
+    gd, gi, gp = ivf.batch_search(q, k, return_probes=True)
+    assert np.array_equal(gp, oracle.probe_select_batch(q, coarse, nprobe, 2)[0])
+    assert_topk_close(gd, gi, od, oi, rtol=RTOL, atol=1e-6)
+    with pytest.raises(Exception):
+        ivf.probe_range(q, nprobe, 0, kc)                               # sharding pieces: L2 / IP only
+
+
 def test_device_resident_search_equals_host_path(oracle):
     import torch
     from vectorindex_b200.index import IVFPQIndex

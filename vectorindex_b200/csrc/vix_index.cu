@@ -49,6 +49,8 @@ int kmeans_parity_device(const float* x, int64_t n, int d, int kc, const float* 
                          float* centroids_out, int32_t* assign_out);
 int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
                            const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
+int centroid_batch_score_cosine_device(const float* q, int64_t nq, const float* c, int kc, int d, const float* cnorm,
+                                       float* out);
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                              const float* cnorm, int32_t* out_idx, float* out_scores, const float* cnorm_max_sqrt);
 int max_sqrt_device(const float* x, int64_t n, float* out);
@@ -347,6 +349,120 @@ static int query_order(const int32_t* probes, int64_t nq, int nprobe, const int3
     return VIX_OK;
 }
 
+// Cosine candidate distance of the IVF-Flat scan (DistanceUtils.swift:22-38): 1 - clamp(dot / sqrt(|a|^2 |b|^2)), and 1
+// when the denominator is not above ulpOfOne.  The dot product and the sums of squares are VectorCore's there (source not
+// in the reference tree): tolerance parity (1e-5), like the other candidate distances.
+__device__ __forceinline__ float seq_sumsq(const float* v, int d) {
+    float s = 0.0f;
+    for (int e = 0; e < d; ++e) s = fadd(s, fmul(v[e], v[e]));
+    return s;
+}
+__device__ __forceinline__ float cosine_distance(float dot, float amag2, float bmag2) {
+    const float denom = __fsqrt_rn(fmul(amag2, bmag2));
+    if (!(denom > 1.1920929e-07f)) return 1.0f;
+    const float sim = fmaxf(-1.0f, fminf(1.0f, __fdiv_rn(dot, denom)));
+    return fsub(1.0f, sim);
+}
+
+// Cosine list assignment and probe selection (IVFIndex.swift:376-435, 905-927): the guarded CentroidBatchScore block of a
+// tile of rows, then per row the first minimum (strict <, ascending list id) / the nprobe best by (score, list id).
+__global__ void __launch_bounds__(256)
+row_argmin_kernel(const float* __restrict__ scores, int64_t rows, int kc, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const float* row = scores + r * (int64_t)kc;
+    float bs = INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < kc; c += 32) {
+        const float v = row[c];
+        if (v < bs) { bs = v; bi = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (lane == 0) out[r] = bi == 0x7fffffff ? -1 : bi;
+}
+
+__global__ void __launch_bounds__(256)
+row_select_lists_kernel(const float* __restrict__ scores, int64_t rows, int kc, int nprobe, int P,
+                        int32_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        __syncthreads();
+        BlockQueue q{keys, &s_cnt, &s_thr, nprobe, P};
+        q.init();
+        for (int base = 0; base < kc; base += blockDim.x) {
+            q.flush_if_needed(blockDim.x);
+            const int c = base + threadIdx.x;
+            if (c < kc) q.push(make_key(scores[r * (int64_t)kc + c], (uint32_t)c, 0));
+        }
+        q.flush();
+        for (int i = threadIdx.x; i < nprobe; i += blockDim.x) {
+            const u64 key = keys[i];
+            out_idx[r * (int64_t)nprobe + i] = key == kEmptyKey ? -1 : (int32_t)key_id(key);
+        }
+    }
+}
+
+// rows per tile of the materialised score block: at most 64 M scores (256 MB)
+static int64_t cosine_tile_rows(int64_t n, int kc) {
+    int64_t t = (64LL << 20) / (kc > 0 ? kc : 1);
+    if (t < 1) t = 1;
+    if (t > 4096) t = 4096;                                     // the reference's tile (IVFIndex.swift:380)
+    return t < n ? t : n;
+}
+
+static int assign_cosine_device(const float* x, int64_t n, int d, const float* coarse, int kc, const float* cnorm,
+                                int32_t* assign) {
+    if (n == 0) return VIX_OK;
+    const int64_t tile = cosine_tile_rows(n, kc);
+    Scratch<float> scores;
+    VIX_TRY(scores.alloc((size_t)tile * kc));
+    for (int64_t b = 0; b < n; b += tile) {
+        const int64_t cnt = n - b < tile ? n - b : tile;
+        VIX_TRY(centroid_batch_score_cosine_device(x + (size_t)b * d, cnt, coarse, kc, d, cnorm, scores.ptr));
+        row_argmin_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, ctx().stream>>>(scores.ptr, cnt, kc, assign + b);
+        VIX_LAUNCH_CHECK();
+    }
+    return VIX_OK;
+}
+
+static int probe_select_cosine_device(const float* q, int64_t nq, const float* coarse, int kc, int d, const float* cnorm,
+                                      int nprobe, int32_t* out_idx) {
+    if (nq == 0) return VIX_OK;
+    const int64_t tile = cosine_tile_rows(nq, kc);
+    Scratch<float> scores;
+    VIX_TRY(scores.alloc((size_t)tile * kc));
+    const int P = next_pow2(nprobe + 256);
+    const size_t smem = (size_t)P * 8;
+    VIX_CUDA(cudaFuncSetAttribute(row_select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t b = 0; b < nq; b += tile) {
+        const int64_t cnt = nq - b < tile ? nq - b : tile;
+        VIX_TRY(centroid_batch_score_cosine_device(q + (size_t)b * d, cnt, coarse, kc, d, cnorm, scores.ptr));
+        int64_t grid = (int64_t)num_sms() * 4;
+        if (grid > cnt) grid = cnt;
+        row_select_lists_kernel<<<(unsigned)grid, 256, smem, ctx().stream>>>(scores.ptr, cnt, kc, nprobe, P,
+                                                                            out_idx + (size_t)b * nprobe);
+        VIX_LAUNCH_CHECK();
+    }
+    return VIX_OK;
+}
+
+// list assignment under the index's metric (the three callers below): euclidean => _vi_km12_assignAOS
+// (IVFIndex.swift:362-375); dot product / cosine => first minimum of the CentroidBatchScore row (:376-435)
+static int assign_lists_device(vix_index_t* h, const float* x, int64_t n, int32_t* assign) {
+    const int d = h->p.d;
+    if (h->p.metric == VIX_METRIC_L2) return ivf_assign_auto_device(x, n, d, h->coarse.ptr, h->kc, assign, nullptr);
+    if (h->p.metric == VIX_METRIC_COSINE) return assign_cosine_device(x, n, d, h->coarse.ptr, h->kc, h->coarse_norms.ptr, assign);
+    return ivf_assign_metric_device(x, n, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, assign);
+}
+
 // IVF-Flat candidate scan (IVFIndex.swift:1023-1039): exact distance per candidate of the probed
 // lists in the reference's order (Direct16 / Ip4), API distance (sqrt / negate), (distance, id) order.
 __global__ void __launch_bounds__(256)
@@ -375,8 +491,10 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
                 const int i = base + threadIdx.x;
                 if (i < len && (!filter || id_filter_pass(filter, filter_cap, filter_deny, slot_ids[b + i]))) {
                     const float* v = slot_vecs + (b + i) * (int64_t)d;
-                    float dist = (metric == VIX_METRIC_L2) ? __fsqrt_rn(exact_pair<SpecDirect16L2>(s_q, v, d))
-                                                           : -exact_pair<SpecIp4>(s_q, v, d);
+                    float dist;
+                    if (metric == VIX_METRIC_L2) dist = __fsqrt_rn(exact_pair<SpecDirect16L2>(s_q, v, d));
+                    else if (metric == VIX_METRIC_IP) dist = -exact_pair<SpecIp4>(s_q, v, d);
+                    else dist = cosine_distance(exact_pair<SpecIp4>(s_q, v, d), seq_sumsq(s_q, d), seq_sumsq(v, d));
                     q.push(make_key(dist, (uint32_t)slot_ids[b + i], 0));
                 }
             }
@@ -497,8 +615,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
             int32_t* ac = h->assign.ptr + n0 + b;
             // list assignment: euclidean => _vi_km12_assignAOS (IVFIndex.swift:362-375);
             // dot product => first-min of the CentroidBatchScore row (IVFIndex.swift:376-435)
-            if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_auto_device(xc, cn, d, h->coarse.ptr, h->kc, ac, nullptr));
-            else VIX_TRY(ivf_assign_metric_device(xc, cn, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, ac));
+            VIX_TRY(assign_lists_device(h, xc, cn, ac));
             if (h->p.kind == VIX_INDEX_IVF_PQ) {
                 // pq_encode_residual_u8_f32 with default opts => C ..._with_csq (PQEncode.swift:247-286)
                 VIX_TRY(pq_encode_device(xc, cn, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr,
@@ -569,6 +686,8 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             VIX_TRY(gp.stage(given_probes, (size_t)nq * nprobe));
             if (dp.dev) VIX_CUDA(cudaMemcpyAsync(dp.dev, gp.dev, (size_t)nq * nprobe * 4, cudaMemcpyDeviceToDevice, s));
             pp = const_cast<int32_t*>(gp.dev);
+        } else if (h->p.metric == VIX_METRIC_COSINE) {
+            VIX_TRY(probe_select_cosine_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->coarse_norms.ptr, nprobe, pp));
         } else {
             VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
                                              h->coarse_norms.ptr, pp, nullptr, h->coarse_norm_max.ptr));
@@ -689,8 +808,8 @@ int vix_index_create(const vix_index_params* p, vix_index_t** out) {
     VIX_REQUIRE(p->d > 0, VIX_ERR_INVALID_DIM, "vix_index_create: d must be > 0");
     VIX_REQUIRE(p->kind >= VIX_INDEX_FLAT && p->kind <= VIX_INDEX_IVF_PQ, VIX_ERR_INVALID_PARAM, "vix_index_create: kind");
     VIX_REQUIRE(p->metric == VIX_METRIC_L2 || p->metric == VIX_METRIC_IP ||
-                    (p->metric == VIX_METRIC_COSINE && p->kind == VIX_INDEX_FLAT),
-                VIX_ERR_INVALID_PARAM, "vix_index_create: metric must be L2 or IP (cosine: FLAT index only)");
+                    (p->metric == VIX_METRIC_COSINE && p->kind != VIX_INDEX_IVF_PQ),
+                VIX_ERR_INVALID_PARAM, "vix_index_create: metric must be L2 or IP (cosine: FLAT and IVF_FLAT indexes only)");
     if (p->kind != VIX_INDEX_FLAT) VIX_REQUIRE(p->nlist > 0, VIX_ERR_INVALID_K, "vix_index_create: nlist must be > 0");
     if (p->kind == VIX_INDEX_IVF_PQ) {
         VIX_REQUIRE(p->m > 0 && p->d % p->m == 0, VIX_ERR_INVALID_DIM, "vix_index_create: d %% m != 0");
@@ -949,6 +1068,7 @@ int vix_index_probe_range(vix_index_t* h, const float* queries, int64_t nq, int 
     VIX_REQUIRE(h && queries && list_ids_out, VIX_ERR_NULL_PTR, "vix_index_probe_range: null pointer");
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_probe_range: not trained");
+    VIX_REQUIRE(h->p.metric != VIX_METRIC_COSINE, VIX_ERR_UNSUPPORTED, "vix_index_probe_range: cosine indexes are not sharded");
     VIX_REQUIRE(nprobe > 0 && nprobe <= VIX_MAX_K, VIX_ERR_INVALID_K, "vix_index_probe_range: nprobe");
     VIX_REQUIRE(list_begin >= 0 && list_count > 0 && list_begin + list_count <= h->kc, VIX_ERR_INVALID_PARAM,
                 "vix_index_probe_range: list range [%d, %d) outside [0, %d)", list_begin, list_begin + list_count, h->kc);
@@ -1037,6 +1157,7 @@ int vix_index_probe_range_keys(vix_index_t* h, const float* queries, int64_t nq,
     VIX_REQUIRE(h && queries && keys_out, VIX_ERR_NULL_PTR, "vix_index_probe_range_keys: null pointer");
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_probe_range_keys: not trained");
+    VIX_REQUIRE(h->p.metric != VIX_METRIC_COSINE, VIX_ERR_UNSUPPORTED, "vix_index_probe_range_keys: cosine indexes are not sharded");
     VIX_REQUIRE(nprobe > 0 && nprobe <= VIX_MAX_K, VIX_ERR_INVALID_K, "vix_index_probe_range_keys: nprobe");
     VIX_REQUIRE(list_begin >= 0 && list_count > 0 && list_begin + list_count <= h->kc, VIX_ERR_INVALID_PARAM,
                 "vix_index_probe_range_keys: list range [%d, %d) outside [0, %d)", list_begin, list_begin + list_count, h->kc);
@@ -1202,8 +1323,7 @@ int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_
     VIX_TRY(dx.stage(x, (size_t)n * d));
     VIX_TRY(da.stage(assign_out, (size_t)n));
     VIX_TRY(dc.stage(pq ? codes_out : nullptr, pq ? (size_t)n * h->p.m : 0));
-    if (h->p.metric == VIX_METRIC_L2) VIX_TRY(ivf_assign_auto_device(dx.dev, n, d, h->coarse.ptr, h->kc, da.dev, nullptr));
-    else VIX_TRY(ivf_assign_metric_device(dx.dev, n, d, h->coarse.ptr, h->kc, h->p.metric, nullptr, da.dev));
+    VIX_TRY(assign_lists_device(h, dx.dev, n, da.dev));
     if (pq)
         VIX_TRY(pq_encode_device(dx.dev, n, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, da.dev, dc.dev, 1,
                                  PQ_LAYOUT_AOS, 64, 8, 0));

@@ -491,6 +491,21 @@ int centroid_batch_score_device(const float* q, int64_t nq, const float* c, int 
     return launch_pair<SpecSeqDot, EPI_WRITE>(p, 0);
 }
 
+// the cosine block: -<q, c> in the contraction's order, then the guarded epilogue (cnorm = ||c||^2, required)
+int centroid_batch_score_cosine_device(const float* q, int64_t nq, const float* c, int kc, int d, const float* cnorm,
+                                       float* out) {
+    if (nq == 0 || kc == 0) return VIX_OK;
+    VIX_REQUIRE(nq * (int64_t)kc < (1LL << 38), VIX_ERR_UNSUPPORTED, "cosine centroid scores: block too large");
+    VIX_TRY(centroid_batch_score_device(q, nq, c, kc, d, VIX_METRIC_IP, nullptr, out));
+    Scratch<float> qn;
+    VIX_TRY(qn.alloc((size_t)nq));
+    VIX_TRY(row_norms_device(q, nq, d, qn.ptr));
+    const int64_t total = nq * (int64_t)kc;
+    cbs_cosine_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(out, nq, kc, qn.ptr, cnorm);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
 // batchSearch probe stage (IVFIndex.swift:905-927): CentroidBatchScore row + ordered prefix.
 // Outputs [nq x nprobe] padded with -1 / NaN beyond min(nprobe, kc).
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
@@ -868,7 +883,7 @@ int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* c
     if (q == 0) return VIX_OK;
     In<float> dq, dc, dn;
     Out<float> dout;
-    Scratch<float> cn, qn;
+    Scratch<float> cn;
     VIX_TRY(dq.stage(queries, (size_t)q * d));
     VIX_TRY(dc.stage(centroids, (size_t)kc * d));
     VIX_TRY(dout.stage(out, (size_t)q * kc));
@@ -878,14 +893,7 @@ int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* c
         else { VIX_TRY(cn.alloc((size_t)kc)); VIX_TRY(row_norms_device(dc.dev, kc, d, cn.ptr)); cnp = cn.ptr; }
     }
     if (metric == VIX_METRIC_COSINE) {
-        // -<q, c> in the contraction's order, then the guarded cosine epilogue over the block
-        VIX_REQUIRE((int64_t)q * kc < (1LL << 38), VIX_ERR_UNSUPPORTED, "vix_centroid_batch_score_f32: cosine block too large");
-        VIX_TRY(centroid_batch_score_device(dq.dev, q, dc.dev, kc, d, VIX_METRIC_IP, nullptr, dout.dev));
-        VIX_TRY(qn.alloc((size_t)q));
-        VIX_TRY(row_norms_device(dq.dev, q, d, qn.ptr));
-        const int64_t total = q * (int64_t)kc;
-        cbs_cosine_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(dout.dev, q, kc, qn.ptr, cnp);
-        VIX_LAUNCH_CHECK();
+        VIX_TRY(centroid_batch_score_cosine_device(dq.dev, q, dc.dev, kc, d, cnp, dout.dev));
     } else {
         VIX_TRY(centroid_batch_score_device(dq.dev, q, dc.dev, kc, d, metric, cnp, dout.dev));
     }

@@ -31,7 +31,7 @@ from ._lib import (INDEX_FLAT, INDEX_IVF_FLAT, INDEX_IVF_PQ, IndexParams, KMeans
 
 _METRICS = {"euclidean": METRIC_L2, "l2": METRIC_L2, METRIC_L2: METRIC_L2,
             "dotProduct": METRIC_IP, "dot": METRIC_IP, "ip": METRIC_IP, METRIC_IP: METRIC_IP,
-            "cosine": 2, 2: 2}                                       # cosine: FlatIndex only
+            "cosine": 2, 2: 2}                                       # cosine: FlatIndex and IVFIndex (not IVF-PQ)
 
 
 def _metric(m):
