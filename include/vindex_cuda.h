@@ -51,7 +51,8 @@ typedef enum {
 } vix_status;
 
 /* SupportedDistanceMetric subset on the hot path: euclidean, dotProduct (ScoreBlock.swift:24-70) */
-/* cosine: flat search / FLAT index only (Cosine.run two-pass, distance = 1 - similarity); the IVF kinds take L2 / IP */
+/* cosine: flat search / FLAT index (Cosine.run two-pass, distance = 1 - similarity), vix_centroid_batch_score_f32 and the
+ * IVF_FLAT index (guarded CentroidBatchScore rows, DistanceUtils.swift:22-38 candidate distances); IVF_PQ takes L2 / IP */
 typedef enum { VIX_METRIC_L2 = 0, VIX_METRIC_IP = 1, VIX_METRIC_COSINE = 2 } vix_metric;
 
 /* HeapOrdering (Operations/Selection/TopK.swift:8-31): ties always go to the smaller id */
