@@ -481,6 +481,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
         for (int e = threadIdx.x; e < d; e += blockDim.x) s_q[e] = queries[qi * (int64_t)d + e];
         BlockQueue q{keys, &s_cnt, &s_thr, k, P};
         q.init();
+        const float qmag2 = (metric == VIX_METRIC_COSINE) ? seq_sumsq(s_q, d) : 0.0f;
         for (int p = 0; p < nprobe; ++p) {
             const int l = probes[qi * (int64_t)nprobe + p];
             if (l < 0) continue;
@@ -494,7 +495,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
                     float dist;
                     if (metric == VIX_METRIC_L2) dist = __fsqrt_rn(exact_pair<SpecDirect16L2>(s_q, v, d));
                     else if (metric == VIX_METRIC_IP) dist = -exact_pair<SpecIp4>(s_q, v, d);
-                    else dist = cosine_distance(exact_pair<SpecIp4>(s_q, v, d), seq_sumsq(s_q, d), seq_sumsq(v, d));
+                    else dist = cosine_distance(exact_pair<SpecIp4>(s_q, v, d), qmag2, seq_sumsq(v, d));
                     q.push(make_key(dist, (uint32_t)slot_ids[b + i], 0));
                 }
             }
