@@ -51,6 +51,8 @@ int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, cons
                            const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
 int centroid_batch_score_cosine_device(const float* q, int64_t nq, const float* c, int kc, int d, const float* cnorm,
                                        float* out);
+int row_select_device(const float* scores, int64_t rows, int n, int k, const uint64_t* disabled, int32_t* out_idx,
+                      float* out_scores);
 int probe_select_fast_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                              const float* cnorm, int32_t* out_idx, float* out_scores, const float* cnorm_max_sqrt);
 int max_sqrt_device(const float* x, int64_t n, float* out);
@@ -386,30 +388,6 @@ row_argmin_kernel(const float* __restrict__ scores, int64_t rows, int kc, int32_
     if (lane == 0) out[r] = bi == 0x7fffffff ? -1 : bi;
 }
 
-__global__ void __launch_bounds__(256)
-row_select_lists_kernel(const float* __restrict__ scores, int64_t rows, int kc, int nprobe, int P,
-                        int32_t* __restrict__ out_idx) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* keys = reinterpret_cast<u64*>(smem_raw);
-    __shared__ int s_cnt;
-    __shared__ u64 s_thr;
-    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-        __syncthreads();
-        BlockQueue q{keys, &s_cnt, &s_thr, nprobe, P};
-        q.init();
-        for (int base = 0; base < kc; base += blockDim.x) {
-            q.flush_if_needed(blockDim.x);
-            const int c = base + threadIdx.x;
-            if (c < kc) q.push(make_key(scores[r * (int64_t)kc + c], (uint32_t)c, 0));
-        }
-        q.flush();
-        for (int i = threadIdx.x; i < nprobe; i += blockDim.x) {
-            const u64 key = keys[i];
-            out_idx[r * (int64_t)nprobe + i] = key == kEmptyKey ? -1 : (int32_t)key_id(key);
-        }
-    }
-}
-
 // rows per tile of the materialised score block: at most 64 M scores (256 MB)
 static int64_t cosine_tile_rows(int64_t n, int kc) {
     int64_t t = (64LL << 20) / (kc > 0 ? kc : 1);
@@ -439,17 +417,10 @@ static int probe_select_cosine_device(const float* q, int64_t nq, const float* c
     const int64_t tile = cosine_tile_rows(nq, kc);
     Scratch<float> scores;
     VIX_TRY(scores.alloc((size_t)tile * kc));
-    const int P = next_pow2(nprobe + 256);
-    const size_t smem = (size_t)P * 8;
-    VIX_CUDA(cudaFuncSetAttribute(row_select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t b = 0; b < nq; b += tile) {
         const int64_t cnt = nq - b < tile ? nq - b : tile;
         VIX_TRY(centroid_batch_score_cosine_device(q + (size_t)b * d, cnt, coarse, kc, d, cnorm, scores.ptr));
-        int64_t grid = (int64_t)num_sms() * 4;
-        if (grid > cnt) grid = cnt;
-        row_select_lists_kernel<<<(unsigned)grid, 256, smem, ctx().stream>>>(scores.ptr, cnt, kc, nprobe, P,
-                                                                            out_idx + (size_t)b * nprobe);
-        VIX_LAUNCH_CHECK();
+        VIX_TRY(row_select_device(scores.ptr, cnt, kc, nprobe, nullptr, out_idx + (size_t)b * nprobe, nullptr));
     }
     return VIX_OK;
 }

@@ -280,6 +280,61 @@ static size_t tile_smem(int tv, int d, int epi, int P) {
     return s;
 }
 
+// Rows too long for the tiled engine (two 16-row tiles of whole rows no longer fit shared memory, d > ~1700; the
+// reference's tests go to d = 2048, IVFSelectTests.swift:578-609): one thread per pair straight from global memory --
+// the same chain, slowly.  WRITE epilogue only; selections then run on the materialised block (row_select_device).
+template <typename Spec>
+__global__ void __launch_bounds__(256)
+pair_direct_kernel(PairArgs p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nA * p.nB) return;
+    const int64_t a = i / p.nB, b = i - a * p.nB;
+    const float s = exact_pair<Spec>(p.A + a * p.d, p.B + b * p.d, p.d);
+    p.out[a * p.ldo + b] = apply_transform(p.transform, s, p, a, b);
+}
+
+// per row of a materialised [rows x n] score block: the k best columns by (score ascending, column ascending), columns
+// whose bit is set in `disabled` skipped; padded with -1 / NaN.  One CTA per row at a time.
+__global__ void __launch_bounds__(256)
+row_select_kernel(const float* __restrict__ scores, int64_t rows, int n, int k, int P, const uint64_t* __restrict__ disabled,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_scores) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = reinterpret_cast<u64*>(smem_raw);
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        __syncthreads();
+        BlockQueue q{keys, &s_cnt, &s_thr, k, P};
+        q.init();
+        for (int base = 0; base < n; base += blockDim.x) {
+            q.flush_if_needed(blockDim.x);
+            const int c = base + threadIdx.x;
+            if (c < n && !(disabled && ((disabled[c >> 6] >> (c & 63)) & 1ull)))
+                q.push(make_key(scores[r * (int64_t)n + c], (uint32_t)c, 0));
+        }
+        q.flush();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const u64 key = keys[i];
+            out_idx[r * (int64_t)k + i] = key == kEmptyKey ? -1 : (int32_t)key_id(key);
+            if (out_scores) out_scores[r * (int64_t)k + i] = key == kEmptyKey ? __int_as_float(0x7fc00000) : key_score(key, 0);
+        }
+    }
+}
+
+int row_select_device(const float* scores, int64_t rows, int n, int k, const uint64_t* disabled, int32_t* out_idx,
+                      float* out_scores) {
+    if (rows == 0 || k <= 0) return VIX_OK;
+    const int P = next_pow2(k + 256);
+    const size_t smem = (size_t)P * 8;
+    VIX_REQUIRE(smem <= 200 * 1024, VIX_ERR_UNSUPPORTED, "row selection: k = %d exceeds shared memory", k);
+    VIX_CUDA(cudaFuncSetAttribute(row_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)num_sms() * 4;
+    if (grid > rows) grid = rows;
+    row_select_kernel<<<(unsigned)grid, 256, smem, ctx().stream>>>(scores, rows, n, k, P, disabled, out_idx, out_scores);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
 static bool plan_tile(int d, int epi, int k, TilePlan* plan) {
     const size_t budget = 220 * 1024;
     for (int tv = 4; tv >= 1; tv >>= 1) {
@@ -294,6 +349,14 @@ template <typename Spec, int EPI>
 static int launch_pair(PairArgs& p, int k_for_plan, int64_t* nsplit_out = nullptr) {
     TilePlan plan;
     if (!plan_tile(p.d, EPI, k_for_plan, &plan)) {
+        if constexpr (EPI == EPI_WRITE) {
+            const int64_t total = p.nA * p.nB;
+            VIX_REQUIRE(total < (1LL << 38), VIX_ERR_UNSUPPORTED, "exact scoring: %lld pairs at d = %d", (long long)total, p.d);
+            if (total == 0) return VIX_OK;
+            pair_direct_kernel<Spec><<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(p);
+            VIX_LAUNCH_CHECK();
+            return VIX_OK;
+        }
         set_error("exact scoring: d = %d (k = %d) does not fit the shared-memory tile", p.d, k_for_plan);
         return VIX_ERR_UNSUPPORTED;
     }
@@ -511,6 +574,21 @@ int centroid_batch_score_cosine_device(const float* q, int64_t nq, const float* 
 int probe_select_device(const float* q, int64_t nq, const float* c, int kc, int d, int metric, int nprobe,
                         const float* cnorm, const uint64_t* disabled, int32_t* out_idx, float* out_scores) {
     if (nq == 0 || nprobe <= 0) return VIX_OK;
+    TilePlan plan;
+    if (!plan_tile(d, EPI_TOPK, nprobe, &plan)) {
+        // rows too long for the tiled engine: the CentroidBatchScore block of a tile of queries, then the ordered prefix
+        int64_t tile = (64LL << 20) / kc;
+        tile = tile < 1 ? 1 : (tile > nq ? nq : tile);
+        Scratch<float> scores;
+        VIX_TRY(scores.alloc((size_t)tile * kc));
+        for (int64_t b = 0; b < nq; b += tile) {
+            const int64_t cnt = nq - b < tile ? nq - b : tile;
+            VIX_TRY(centroid_batch_score_device(q + (size_t)b * d, cnt, c, kc, d, metric, cnorm, scores.ptr));
+            VIX_TRY(row_select_device(scores.ptr, cnt, kc, nprobe, disabled, out_idx + (size_t)b * nprobe,
+                                      out_scores ? out_scores + (size_t)b * nprobe : nullptr));
+        }
+        return VIX_OK;
+    }
     PairArgs p{};
     p.A = q; p.nA = nq; p.B = c; p.nB = kc; p.d = d;
     p.transform = (metric == VIX_METRIC_L2) ? TR_CBS_L2 : TR_NEG;
