@@ -69,3 +69,47 @@ def test_compose_id_filters_matches_idfilterpassn():
         compose_id_filters([allows[0]] * 5)
     with pytest.raises(ValueError):
         compose_id_filters([IDFilter(cap + 1, "allow")], deny)
+
+
+@pytest.mark.parametrize("pipes", [1, 2])
+def test_scan_table_address_algebra(pipes):
+    """The index arithmetic of the fused scan's look-up tables (vix_ivfpq_scan.cu: build_lut's column formula, the per-lane
+    constants and LDS immediates of lookup16, the rotated code layout), restated on integers for both table layouts: every
+    look-up reads the entry that was written for its (sub-quantiser, code), a warp-wide look-up touches 32 different
+    banks whatever the codes are, and the two pipelines of the two-pipeline layout never share an entry."""
+    k_dual_tab = 36 * 1024
+    tab_abs = 128 * 1024 if pipes == 1 else k_dual_tab               # one pipeline: any 64 KB-aligned shared address
+    G = 3                                                            # m = 48
+    rng = np.random.default_rng(0)
+
+    def written(pipe, j, c, rep):                                    # build_lut: byte address of T[j][c], replica rep
+        t16, jj = j >> 4, j & 15
+        col = ((t16 >> 1) * 16384 + (t16 & 1) * 32) if pipes == 1 else (t16 * 16384 + pipe * 32)
+        return tab_abs + 4 * (col + jj + 16 * rep + c * 64)
+
+    def looked_up(pipe, lane, T, b, code):                           # lookup16<T>: PRMT(code word, lane constant) + immediate
+        const = 4 * (16 * (lane >> 4) + ((b ^ lane) & 15)) + (128 * pipe if pipes == 2 else 0)
+        assert const < 256
+        base = tab_abs if pipes == 1 else 0                          # bytes 2..3 of the lane constant
+        imm = ((T & 1) * 128 + (T >> 1) * 65536) if pipes == 1 else (k_dual_tab + T * 65536)
+        return (base | (code << 8) | const) + imm
+
+    owners = {}
+    for pipe in range(pipes):
+        for j in range(16 * G):
+            for c in (0, 1, 77, 255):
+                for rep in (0, 1):
+                    a = written(pipe, j, c, rep)
+                    assert owners.setdefault(a, (pipe, j, c, rep)) == (pipe, j, c, rep)   # no two entries share an address
+        for T in range(G):
+            for b in range(16):
+                codes = rng.integers(0, 256, 32)
+                addrs = []
+                for lane in range(32):
+                    j = 16 * T + ((b ^ lane) & 15)                   # byte b of slot `lane` holds this sub-quantiser (rotation)
+                    a = looked_up(pipe, lane, T, b, int(codes[lane]))
+                    assert a == written(pipe, j, int(codes[lane]), lane >> 4)
+                    addrs.append(a)
+                assert len({(a >> 2) & 31 for a in addrs}) == 32     # 32 lanes, 32 banks
+    top = max(owners) + 4
+    assert top <= (228 * 1024 if pipes == 2 else tab_abs + 2 * 65536)
