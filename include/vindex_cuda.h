@@ -129,6 +129,10 @@ int vix_centroid_batch_score_f32(const float* queries, int64_t q, const float* c
 /* ivf_select_nprobe_batch_f32 (Kernels/IVFSelect.swift:242-315) with the batchSearch ordering
  * (IVFIndex.swift:593-595, 905-927): per query the nprobe best lists by (score asc, index asc);
  * list_ids_out[b x nprobe] int32, padded with -1 (scores NaN) beyond min(nprobe, kc);
+ * list_scores_out (optional) in the CentroidBatchScore convention, "smaller is better": L2 => ||c||^2 - 2<q,c>,
+ * IP => -<q,c>.  IVFSelect's own listScoresOut (||q||^2 + ||c||^2 - 2<q,c> / <q,c>, IVFSelect.swift:436-479) differ by
+ * a per-query constant / the sign, which leaves the selected lists and their order unchanged; the Swift shim of
+ * INTEGRATION.md restores them;
  * disabled_lists: optional bitmask, bit i set => list i skipped (IVFSelect.swift:366-395). */
 int vix_ivf_select_nprobe_batch_f32(const float* Q, int64_t b, int d, const float* centroids, int kc,
                                     int metric, int nprobe, const float* centroid_norms,

@@ -31,6 +31,16 @@ public func ivf_select_nprobe_batch_f32_cuda(Q: UnsafePointer<Float>, b: Int, d:
     try _vixCheck(vix_ivf_select_nprobe_batch_f32(Q, Int64(b), Int32(d), centroids, Int32(kc),
                                                   metric == .l2 ? 0 : 1, Int32(nprobe), centroidNorms, disabledLists,
                                                   listIDsOut, listScoresOut), "ivf_select_nprobe_batch_f32")
+    // The library orders and reports in the batchSearch convention ("smaller is better": ||c||^2 - 2<q,c>, -<q,c>;
+    // CentroidBatchScore.swift:54-64).  The lists are IVFSelect's (same order, same tie rule); its listScoresOut are
+    // ||q||^2 + ||c||^2 - 2<q,c> and <q,c> (IVFSelect.swift:436-479): restore them here.
+    guard let scores = listScoresOut else { return }
+    for qi in 0..<b {
+        let qn: Float = metric == .l2 ? IndexOps.Support.Norms.l2NormSquared(vector: Q + qi * d, dimension: d) : 0
+        for p in 0..<nprobe where listIDsOut[qi * nprobe + p] >= 0 {
+            scores[qi * nprobe + p] = metric == .l2 ? qn + scores[qi * nprobe + p] : -scores[qi * nprobe + p]
+        }
+    }
 }
 
 // adc_scan_u8 (Operations/Quantization/ADCScan.swift:99-121)
