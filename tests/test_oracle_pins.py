@@ -284,3 +284,17 @@ def test_fused_residual_encode_equals_materialised(oracle):
     if oracle.ref_lib() is not None:
         assert np.array_equal(oracle.ref_encode("cpq_encode_u8_f32", r, cb, m, ks), plain)
         assert np.array_equal(oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=cent, assign_=asg), fused)
+
+
+def test_cosine_zero_norm_and_clamp_pins(oracle):
+    """CosineKernelTests.swift:124-160: an all-zero row has similarity 0 (API distance 1), and two identical vectors of
+    1000s give a similarity that the clamp keeps at <= 1 (distance >= 0)."""
+    rng = np.random.default_rng(4)
+    q = rng.uniform(-1, 1, (1, 16)).astype(np.float32)
+    xb = rng.uniform(-1, 1, (4, 16)).astype(np.float32)
+    xb[0] = 0.0
+    d, i, _ = oracle.flat_search(q, xb, 4, 2)
+    assert abs(float(d[0][i[0] == 0][0]) - 1.0) <= 1e-6
+    big = np.full((1, 8), 1000.0, np.float32)
+    d, _, _ = oracle.flat_search(big, big, 1, 2)
+    assert 0.0 <= float(d[0, 0]) <= 1e-6
