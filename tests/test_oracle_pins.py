@@ -298,3 +298,21 @@ def test_cosine_zero_norm_and_clamp_pins(oracle):
     big = np.full((1, 8), 1000.0, np.float32)
     d, _, _ = oracle.flat_search(big, big, 1, 2)
     assert 0.0 <= float(d[0, 0]) <= 1e-6
+
+
+def _kmeanspp_edge_cases():
+    """KMeansPPSeedingTests.swift:182-296: (data, k, seed) of testKEqualsOne / testKEqualsN / testDuplicateData."""
+    return [
+        (np.arange(60, dtype=np.float32).reshape(20, 3), 1, 999),
+        (np.arange(20, dtype=np.float32).reshape(10, 2), 10, 42),
+        (np.array([[0, 0, 0]] * 5 + [[1, 1, 1]] * 5, dtype=np.float32), 3, 555),
+    ]
+
+
+def test_kmeanspp_edge_case_pins(oracle):
+    """k = 1: one valid index; k = n: every point chosen once; duplicated points: still k distinct indices (the zero-total
+    fallback of the D^2 sampler, KMeansSeeding.swift:368-409)."""
+    for data, k, seed in _kmeanspp_edge_cases():
+        cents, chosen = oracle.kmeanspp_seed(data, k, seed, 0)
+        assert len(set(chosen.tolist())) == k and chosen.min() >= 0 and chosen.max() < data.shape[0]
+        assert np.array_equal(cents, data[chosen])
