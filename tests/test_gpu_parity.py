@@ -918,6 +918,20 @@ def test_kmeanspp_seed_edge_cases(oracle, vk):
         assert np.array_equal(gch, och) and np.array_equal(bits(gc), bits(oc))
 
 
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="edge-case shapes of the reference's mini-batch tests: added after this round's GPU budget was "
+                           "spent, not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs them")
+def test_kmeans_minibatch_edge_cases(oracle, vk):
+    """KMeansMiniBatchTests.swift:405-487, 616-646 (one centroid, batch larger than n, identical points): bit-identical
+    to the oracle in reference-parity mode."""
+    from test_oracle_pins import _kmeans_minibatch_edge_cases
+    for x, kc, init, batch, epochs in _kmeans_minibatch_edge_cases():
+        rc, oc, _, _ = oracle.kmeans_minibatch(x, kc, init, batch, epochs, 1e-4, 0, 0)
+        assert rc == 0
+        st, gc, _ = vk.kmeans_minibatch_f32(x, kc, init, vk.kmeans_cfg(batch, epochs, 1e-4, 0, 0, False, 0))
+        assert np.array_equal(bits(gc), bits(oc))
+
+
 @pytest.mark.parametrize("n,d,kc,batch,epochs", [(5000, 16, 64, 1024, 5), (1500, 33, 20, 256, 3), (900, 8, 300, 128, 2)])
 def test_kmeans_minibatch_parity(oracle, vk, n, d, kc, batch, epochs):
     """kmeans_minibatch_f32 in reference-parity mode: batches drawn with replacement from the LCG, batch-mean

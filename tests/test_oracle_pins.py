@@ -316,3 +316,27 @@ def test_kmeanspp_edge_case_pins(oracle):
         cents, chosen = oracle.kmeanspp_seed(data, k, seed, 0)
         assert len(set(chosen.tolist())) == k and chosen.min() >= 0 and chosen.max() < data.shape[0]
         assert np.array_equal(cents, data[chosen])
+
+
+def _kmeans_minibatch_edge_cases():
+    """KMeansMiniBatchTests.swift:405-487, 616-646: (x, kc, init, batch, epochs) of testSingleCentroid (seeded stand-in for
+    its random data), testBatchSizeLargerThanN (its own deterministic fixture) and testIdenticalData."""
+    rng = np.random.default_rng(0)
+    n, d, k = 30, 4, 3
+    data = (np.arange(n * d) % 20 / 5.0).astype(np.float32).reshape(n, d)
+    init = (np.arange(k * d) % 15 / 5.0).astype(np.float32).reshape(k, d)
+    return [
+        (rng.uniform(-5, 5, (50, 3)).astype(np.float32), 1, None, 10, 5),
+        (data, k, init, 100, 10),
+        (np.ones((50, 4), np.float32), 3, None, 10, 5),
+    ]
+
+
+def test_kmeans_minibatch_edge_case_pins(oracle):
+    (x1, k1, i1, b1, e1), (x2, k2, i2, b2, e2), (x3, k3, i3, b3, e3) = _kmeans_minibatch_edge_cases()
+    rc, c, _, _ = oracle.kmeans_minibatch(x1, k1, i1, b1, e1, 1e-4, 0, 0)
+    assert rc == 0 and np.linalg.norm(c[0] - x1.mean(0)) < 3.0            # "single centroid should be near data mean"
+    rc, c, _, _ = oracle.kmeans_minibatch(x2, k2, i2, b2, e2, 1e-4, 0, 0)
+    assert rc == 0 and np.isfinite(c).all()                                # batchSize > n is handled
+    rc, c, _, _ = oracle.kmeans_minibatch(x3, k3, i3, b3, e3, 1e-4, 0, 0)
+    assert rc == 0 and np.abs(c - 1.0).max() <= 0.1                        # identical data: every centroid on the point
