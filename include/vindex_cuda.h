@@ -255,7 +255,10 @@ void vix_index_params_default(vix_index_params* p);
 int  vix_index_create(const vix_index_params* p, vix_index_t** out);
 void vix_index_destroy(vix_index_t* h);
 
-/* optimize(): coarse k-means (+ PQ codebooks on residuals) from a training sample */
+/* optimize(): coarse k-means (+ PQ codebooks on residuals) from a training sample.  An IVF_FLAT index may already hold
+ * vectors (the reference's insert -> optimize() -> search; until it has centroids its searches are linear scans,
+ * IVFIndex.swift:820-832): they are filed into their lists, and x == NULL trains on them (IVFIndex.swift:279-341).
+ * An IVF_PQ index keeps codes, not vectors: train / set_* first. */
 int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_cfg* kcfg,
                     const vix_pq_train_cfg* pcfg);
 /* stage-wise parity / import: install externally trained parameters */

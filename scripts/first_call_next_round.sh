@@ -10,7 +10,7 @@
 #     --partition $P > gpurun_out/bench_c5_n8_$P.json 2> gpurun_out/bench_c5_n8_$P.err; done'
 set -x
 VIX_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_parity.py -q \
-    -k "two_pipeline or cosine_guarded or long_subvectors or ivfflat_cosine or long_rows or seed_edge_cases or minibatch_edge_cases" 2>&1 | tail -8
+    -k "two_pipeline or cosine_guarded or long_subvectors or ivfflat_cosine or long_rows or seed_edge_cases or minibatch_edge_cases or insert_then_optimize" 2>&1 | tail -8
 timeout 400 python scripts/shard_emul.py 8 0 2>&1 | tail -4
 for D in 0 1; do
   VIX_SCAN_DUAL=$D timeout 300 python bench.py --steps 10 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('VIX_SCAN_DUAL=$D', 'ms/step', round(d['ms_per_step'],3), d['config']['stage_ms_per_step'], 'frac', round(d['roofline']['frac'],3), 'recall', d['config']['recall_at_10'])"

@@ -880,6 +880,41 @@ def test_ivfflat_cosine_index(oracle):
         ivf.probe_range(q, nprobe, 0, kc)                               # sharding pieces: L2 / IP only
 
 
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="IVF-Flat insert -> optimize() -> search: written after this round's GPU budget was spent, not yet run "
+                           "on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
+def test_ivfflat_insert_then_optimize(oracle):
+    """IVFMoreTests.swift:5-15 (linear scan before optimize) and the reference's build order: vectors first, then
+    optimize() over the stored vectors, which files them into their lists; set_coarse on a filled index does the same."""
+    from vectorindex_b200.index import IVFIndex
+    rng = np.random.default_rng(28)
+    n, d, kc, nq, k, nprobe = 5000, 32, 24, 25, 10, 5
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    ids = np.arange(n, dtype=np.int64) + 7
+    ivf = IVFIndex(d, "euclidean", nlist=kc, nprobe=nprobe)
+    ivf.batch_insert(xb[:3000], ids[:3000])
+    ivf.batch_insert(xb[3000:], ids[3000:])
+    fd, fi, _ = oracle.flat_search(q, xb, k, 0)
+    gd, gi = ivf.batch_search(q, k)                                     # not optimised yet: exact linear scan
+    assert np.array_equal(gi, fi + 7) and np.array_equal(bits(gd), bits(fd))
+    ivf.optimize()                                                      # k-means over the stored vectors
+    coarse = ivf.get_coarse()
+    asg = oracle.assign(xb, coarse)[0]
+    assert np.array_equal(ivf.list_sizes(), np.bincount(asg, minlength=coarse.shape[0]))
+    off, order = oracle.build_lists(asg, coarse.shape[0])
+    od, oi = oracle.ivfflat_search(q, coarse, off, xb[order], ids[order], nprobe, k, 0)
+    gd, gi = ivf.batch_search(q, k)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    # the same through set_coarse on an index that already holds its vectors, then more vectors
+    ivf2 = IVFIndex(d, "euclidean", nlist=kc, nprobe=nprobe)
+    ivf2.batch_insert(xb[:4000], ids[:4000])
+    ivf2.set_coarse(coarse)
+    ivf2.batch_insert(xb[4000:], ids[4000:])
+    gd2, gi2 = ivf2.batch_search(q, k)
+    assert np.array_equal(gi2, oi) and np.array_equal(bits(gd2), bits(od))
+
+
 def test_device_resident_search_equals_host_path(oracle):
     import torch
     from vectorindex_b200.index import IVFPQIndex

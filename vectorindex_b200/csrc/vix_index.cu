@@ -547,15 +547,30 @@ __global__ void iota64_kernel(int64_t* a, int64_t n, int64_t start) {
     if (i < n) a[i] = start + i;
 }
 
+// An IVF-Flat index may hold vectors before it has a coarse quantiser (the reference's insert -> optimize() -> search,
+// IVFIndex.swift:279-451; until then searches are linear scans, :820-832): once centroids exist, every stored row gets
+// its list.
+static int assign_stored_rows(vix_index* h) {
+    if (h->p.kind != VIX_INDEX_IVF_FLAT || h->n == 0) return VIX_OK;
+    VIX_TRY(h->assign.resize((size_t)h->n));
+    const int64_t chunk = 1 << 20;
+    for (int64_t b = 0; b < h->n; b += chunk) {
+        const int64_t cn = (h->n - b < chunk) ? (h->n - b) : chunk;
+        VIX_TRY(assign_lists_device(h, h->vecs.ptr + (size_t)b * h->p.d, cn, h->assign.ptr + b));
+    }
+    h->dirty = true;
+    return VIX_OK;
+}
+
 static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, int64_t n) {
     const int d = h->p.d;
     cudaStream_t s = ctx().stream;
     if (n == 0) return VIX_OK;
     VIX_REQUIRE(h->n + n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "index shard limited to 2^31 - 1 rows");
-    if (h->p.kind != VIX_INDEX_FLAT)
+    if (h->p.kind == VIX_INDEX_IVF_PQ) {
         VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "index_add: coarse quantiser not trained / set");
-    if (h->p.kind == VIX_INDEX_IVF_PQ)
         VIX_REQUIRE(h->has_pq, VIX_ERR_NOT_TRAINED, "index_add: PQ codebooks not trained / set");
+    }
     if (ids && !is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
     if (!ids) VIX_REQUIRE(h->n + n < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM, "automatic ids exceed 2^32 - 1");
 
@@ -568,7 +583,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
         VIX_TRY(h->vecs.resize((size_t)(n0 + n) * d));
         VIX_CUDA(cudaMemcpyAsync(h->vecs.ptr + (size_t)n0 * d, x, (size_t)n * d * 4, cudaMemcpyDefault, s));
     }
-    if (h->p.kind != VIX_INDEX_FLAT) {
+    if (h->p.kind != VIX_INDEX_FLAT && h->has_coarse) {          // (IVF-Flat without centroids: rows wait for optimize())
         VIX_TRY(h->assign.resize((size_t)(n0 + n)));
         if (h->p.kind == VIX_INDEX_IVF_PQ) VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->p.m));
         // chunked so that host inputs of any size stage through a bounded device buffer
@@ -807,7 +822,7 @@ int vix_index_set_coarse(vix_index_t* h, const float* centroids, int kc) {
     VIX_REQUIRE(h && centroids, VIX_ERR_NULL_PTR, "vix_index_set_coarse: null pointer");
     VIX_REQUIRE(kc > 0, VIX_ERR_INVALID_K, "vix_index_set_coarse: kc must be > 0");
     std::lock_guard<std::mutex> lk(h->mu);
-    VIX_REQUIRE(h->n == 0, VIX_ERR_CONTRACT, "vix_index_set_coarse: index already holds vectors");
+    VIX_REQUIRE(h->n == 0 || h->p.kind == VIX_INDEX_IVF_FLAT, VIX_ERR_CONTRACT, "vix_index_set_coarse: index already holds vectors");
     h->kc = kc;
     VIX_TRY(h->coarse.assign_from(centroids, (size_t)kc * h->p.d));
     VIX_TRY(h->coarse_norms.resize((size_t)kc, false));
@@ -816,6 +831,7 @@ int vix_index_set_coarse(vix_index_t* h, const float* centroids, int kc) {
     VIX_TRY(max_sqrt_device(h->coarse_norms.ptr, kc, h->coarse_norm_max.ptr));
     h->has_coarse = true;
     h->dirty = true;
+    VIX_TRY(assign_stored_rows(h));
     return finish(true);
 }
 
@@ -865,11 +881,14 @@ int vix_index_get_codebooks(vix_index_t* h, float* codebooks_out, float* centroi
 
 int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_cfg* kcfg, const vix_pq_train_cfg* pcfg) {
     VIX_TRY(ensure_device());
-    VIX_REQUIRE(h && x, VIX_ERR_NULL_PTR, "vix_index_train: null pointer");
-    VIX_REQUIRE(n > 0, VIX_ERR_EMPTY_INPUT, "vix_index_train: empty training set");
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_train: null pointer");
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->p.kind == VIX_INDEX_FLAT) return VIX_OK;
-    VIX_REQUIRE(h->n == 0, VIX_ERR_CONTRACT, "vix_index_train: index already holds vectors");
+    // x == NULL on an IVF-Flat index that holds vectors: optimize() over the stored vectors (IVFIndex.swift:279-341)
+    if (!x && h->p.kind == VIX_INDEX_IVF_FLAT && h->n > 0) { x = h->vecs.ptr; n = h->n; }
+    VIX_REQUIRE(x, VIX_ERR_NULL_PTR, "vix_index_train: null pointer");
+    VIX_REQUIRE(n > 0, VIX_ERR_EMPTY_INPUT, "vix_index_train: empty training set");
+    VIX_REQUIRE(h->n == 0 || h->p.kind == VIX_INDEX_IVF_FLAT, VIX_ERR_CONTRACT, "vix_index_train: index already holds vectors");
     const int d = h->p.d;
     In<float> dx;
     VIX_TRY(dx.stage(x, (size_t)n * d));
@@ -898,6 +917,7 @@ int vix_index_train(vix_index_t* h, const float* x, int64_t n, const vix_kmeans_
         h->has_pq = true;
     }
     h->dirty = true;
+    VIX_TRY(assign_stored_rows(h));
     return finish(true);
 }
 

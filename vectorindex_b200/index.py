@@ -194,18 +194,22 @@ class FlatIndex(_Index):
 
 
 class IVFIndex(_Index):
-    """IVF-Flat.  ``optimize(training_vectors)`` trains the coarse quantiser (k-means) -- unlike the
-    reference actor, vectors are added AFTER training (``batch_insert``), faiss-style, because the
-    device index keeps lists, not a dictionary."""
+    """IVF-Flat.  ``optimize(training_vectors)`` trains the coarse quantiser (k-means).  Like the reference actor
+    (insert -> optimize() -> search, IVFIndex.swift:279-451) the IVF-Flat kind also takes vectors BEFORE it is trained:
+    searches are linear scans until then (:820-832) and ``optimize()`` without arguments trains on the stored vectors
+    and files them into their lists.  The IVF-PQ kind keeps codes, not vectors: it is trained first (faiss-style)."""
     kind = INDEX_IVF_FLAT
 
-    def optimize(self, training_vectors, kmeans_cfg: KMeansCfg | None = None, pq_cfg: PQTrainCfg | None = None):
-        x = as_input(training_vectors, np.float32)
-        self._check_dim(x, "optimize")
+    def optimize(self, training_vectors=None, kmeans_cfg: KMeansCfg | None = None, pq_cfg: PQTrainCfg | None = None):
         if kmeans_cfg is None:
             kmeans_cfg = KMeansCfg(1024, 10, 1e-4, 42, 0, False, 1)
         if pq_cfg is None:
             pq_cfg = PQTrainCfg(0, 25, 1e-4, 1024, 0, 42, 0, 0, 1)
+        if training_vectors is None:                                  # the stored vectors (IVF-Flat only)
+            check(lib().vix_index_train(self._h, None, C.c_int64(0), C.byref(kmeans_cfg), C.byref(pq_cfg)))
+            return
+        x = as_input(training_vectors, np.float32)
+        self._check_dim(x, "optimize")
         check(lib().vix_index_train(self._h, ptr(x, np.float32), C.c_int64(int(x.shape[0])), C.byref(kmeans_cfg),
                                     C.byref(pq_cfg)))
 
