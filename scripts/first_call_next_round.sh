@@ -8,7 +8,7 @@
 #   gpurun --gpus 8 --timeout 900 -- 'for P in lists replicate; do python -m torch.distributed.run --nnodes=1 \
 #     --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 \
 #     --partition $P > gpurun_out/bench_c5_n8_$P.json 2> gpurun_out/bench_c5_n8_$P.err; done'
-set -x
+set -x -o pipefail
 # the whole GPU suite, opt-in tests included; the two-pipeline kernel (named barriers: a mistake there is a hang, not a
 # wrong answer) runs on its own afterwards under a short timeout
 VIX_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -rs -k "not two_pipeline" 2>&1 | tail -25
