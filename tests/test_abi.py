@@ -74,3 +74,9 @@ def test_argument_validation_mirrors_reference_preconditions():
     with pytest.raises(VectorIndexError) as e:                      # PQTrain.swift:96-135 .emptyInput
         kernels.pq_train_f32(np.zeros((0, 8), dtype=np.float32), 2)
     assert e.value.kind == "emptyInput"
+    with pytest.raises(VectorIndexError) as e:                      # PQTrainTests.swift:600-625: n < ks
+        kernels.pq_train_f32(np.zeros((50, 128), dtype=np.float32), 4, ks=100)
+    assert e.value.kind == "emptyInput" and "Insufficient training data" in str(e.value)
+    with pytest.raises(VectorIndexError) as e:                      # PQTrainTests.swift:627-652: d % m != 0
+        kernels.pq_train_f32(np.zeros((1000, 100), dtype=np.float32), 7, ks=64)
+    assert e.value.kind == "invalidDim" and "divisible" in str(e.value)

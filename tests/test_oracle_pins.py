@@ -340,3 +340,11 @@ def test_kmeans_minibatch_edge_case_pins(oracle):
     assert rc == 0 and np.isfinite(c).all()                                # batchSize > n is handled
     rc, c, _, _ = oracle.kmeans_minibatch(x3, k3, i3, b3, e3, 1e-4, 0, 0)
     assert rc == 0 and np.abs(c - 1.0).max() <= 0.1                        # identical data: every centroid on the point
+
+
+def test_pq_train_data_requirements(oracle):
+    """PQTrainTests.swift:574-625: n == ks is the minimum viable training set; n < ks is .emptyInput (status -4)."""
+    rng = np.random.default_rng(0)
+    rc, cb, _, _ = oracle.pq_train(rng.uniform(-1, 1, (64, 128)).astype(np.float32), 4, 64)
+    assert rc == 0 and cb.shape == (4, 64, 32) and np.isfinite(cb).all()
+    assert oracle.pq_train(np.zeros((50, 128), np.float32), 4, 100)[0] == -4

@@ -441,6 +441,12 @@ int vix_pq_train_f32(const float* x, int64_t n, int d, int m, int ks, const floa
     VIX_REQUIRE(ks > 0 && ks <= 256, VIX_ERR_INVALID_K, "vix_pq_train_f32: ks must be in 1..256");
     VIX_REQUIRE((coarse_centroids == nullptr) == (assignments == nullptr), VIX_ERR_CONTRACT,
                 "vix_pq_train_f32: coarse_centroids and assignments must be given together");
+    {   // PQTrain.swift:127-135: fewer training vectors (after sampling) than centroids => .emptyInput
+        const int64_t need_n = (cfg && cfg->sample_n > 0) ? cfg->sample_n : n;
+        VIX_REQUIRE(need_n >= ks, VIX_ERR_EMPTY_INPUT,
+                    "vix_pq_train_f32: Insufficient training data: need at least ks vectors (%lld available, ks = %d)",
+                    (long long)need_n, ks);
+    }
     In<float> dx, dco;
     In<int32_t> das;
     Out<float> dcb, dn;

@@ -360,6 +360,9 @@ def pq_train_f32(x, m, ks=256, coarse_centroids=None, assignments=None, cfg: PQT
         raise VectorIndexError(-7, "pq_train_f32: empty input")
     if m <= 0 or d % m != 0:
         raise VectorIndexError(-1, "pq_train_f32: d must be divisible by m")
+    need_n = cfg.sample_n if cfg is not None and cfg.sample_n > 0 else n
+    if need_n < ks:                                                   # PQTrain.swift:127-135
+        raise VectorIndexError(-7, "pq_train_f32: Insufficient training data: need at least ks vectors")
     dsub = d // m
     cb = empty_like_input(x, (m, ks, dsub), np.float32)
     norms = empty_like_input(x, (m, ks), np.float32)
