@@ -348,3 +348,28 @@ def test_pq_train_data_requirements(oracle):
     rc, cb, _, _ = oracle.pq_train(rng.uniform(-1, 1, (64, 128)).astype(np.float32), 4, 64)
     assert rc == 0 and cb.shape == (4, 64, 32) and np.isfinite(cb).all()
     assert oracle.pq_train(np.zeros((50, 128), np.float32), 4, 100)[0] == -4
+
+
+def test_encode_with_csq_equals_default_fixture(oracle):
+    """PQEncodeParity_SwiftOnly_Tests.swift:41-106 (n = 12, d = 24, m = 6, ks = 256 on the sin / cos fixture, sequential
+    centroid norms): the with-CSQ encoders give the codes of the default ones, plain and residual -- for the restatement and
+    for the reference's compiled C encoder."""
+    n, d, m, ks, kc = 12, 24, 6, 256, 4
+    dsub = d // m
+    i = np.arange(n * d, dtype=np.int64)
+    x = (np.sin((i * 131 % 1024).astype(np.float64)) * 0.25 + np.cos((i * 17 % 997).astype(np.float64)) * 0.125).astype(np.float32).reshape(n, d)
+    j = np.arange(m * ks * dsub, dtype=np.int64)
+    cb = (np.sin((j * 313 % 2048).astype(np.float64)) * 0.2 + np.cos((j * 23 % 1237).astype(np.float64)) * 0.15).astype(np.float32)
+    g = np.arange(kc * d, dtype=np.int64)
+    coarse = (np.cos((g * 19 % 4096).astype(np.float64)) * 0.33).astype(np.float32).reshape(kc, d)
+    asg = (np.arange(n) % kc).astype(np.int32)
+    csq = oracle.pq_centroid_sq(cb, m, ks, dsub, swift=True)             # s += v * v, in order
+    assert np.array_equal(oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq), oracle.pq_encode_u8(x, cb, m, ks))
+    assert np.array_equal(oracle.pq_encode_u8(x, cb, m, ks, centroid_sq=csq, coarse=coarse, assign_=asg),
+                          oracle.pq_encode_u8(x, cb, m, ks, coarse=coarse, assign_=asg))
+    if oracle.ref_lib() is not None:
+        assert np.array_equal(oracle.ref_encode("cpq_encode_u8_f32_with_csq", x, cb, m, ks, centroid_sq=csq),
+                              oracle.ref_encode("cpq_encode_u8_f32", x, cb, m, ks))
+        assert np.array_equal(oracle.ref_encode("cpq_encode_residual_u8_f32_with_csq", x, cb, m, ks, centroid_sq=csq,
+                                                coarse=coarse, assign_=asg),
+                              oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=coarse, assign_=asg))
