@@ -130,8 +130,8 @@ def _replica_worker(rank, world, port, out_path):
         rp = ReplicatedIVFPQIndex(xb.shape[1], "euclidean", nlist=kc, nprobe=nprobe, m=m, local=OracleLocalIndex(xb.shape[1], m))
         rp.set_parameters(coarse, cb, norms)
         ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
-        cut = 1100                                                         # ragged contributions: 1100 rows / 1900 rows
-        mine = np.arange(0, cut) if rank == 0 else np.arange(cut, xb.shape[0])
+        cuts = [0, 1100, xb.shape[0]] if world == 2 else [0, 1100, 2200, xb.shape[0]]   # ragged contributions
+        mine = np.arange(cuts[rank], cuts[rank + 1])
         half = mine.size // 3
         rp.add(xb[mine[:half]], ids[mine[:half]])
         rp.add(xb[mine[half:]], ids[mine[half:]])
@@ -142,6 +142,9 @@ def _replica_worker(rank, world, port, out_path):
         bd, bi = rp.batch_search(q, k, gather=False)
         lo, cnt, _ = rp.query_block(q.shape[0])
         assert np.array_equal(np.asarray(bi), np.asarray(mi)[lo:lo + cnt])
+        sd, si = rp.batch_search(q[:2], k)                                # fewer queries than ranks at world 3: an empty block
+        assert np.array_equal(np.asarray(si), np.asarray(mi)[:2])
+        assert np.array_equal(np.asarray(sd).view(np.uint32), np.asarray(md)[:2].view(np.uint32))
         np.savez(out_path + f".{rank}.npz", md=np.asarray(md), mi=np.asarray(mi), order=rp.local.ids)
     finally:
         dist.destroy_process_group()
@@ -212,22 +215,24 @@ def test_sharded_search_equals_single_process_oracle(tmp_path, oracle):
     assert np.array_equal(res["md"].view(np.uint32), od.view(np.uint32))
 
 
-def test_replicated_search_equals_single_process_oracle(tmp_path, oracle):
-    """ReplicatedIVFPQIndex at world size 2: ragged build contributions and ragged query blocks; every rank ends with the
-    whole answer, bit-identical to the single-process oracle search, and the replicas hold their rows in the same order."""
+@pytest.mark.parametrize("world", [2, 3])
+def test_replicated_search_equals_single_process_oracle(tmp_path, oracle, world):
+    """ReplicatedIVFPQIndex at world size 2 and 3: ragged build contributions, ragged and empty query blocks; every rank ends
+    with the whole answer, bit-identical to the single-process oracle search, and the replicas hold their rows in the same
+    order."""
     import torch.multiprocessing as mp
     out = str(tmp_path / "rep")
-    mp.spawn(_replica_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_replica_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     xb, q, coarse, cb, norms, asg, m, kc = _problem()
     ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
     off, order = oracle.build_lists(asg, kc)
     codes = oracle.pq_encode_u8(xb, cb, m, 256, centroid_sq=norms.reshape(-1), coarse=coarse, assign_=asg)
     od, oi, _ = oracle.ivfpq_search(q, coarse, cb, norms, off, codes[order], ids[order], m, 256, 5, 10, 0)
-    res = [np.load(out + f".{r}.npz") for r in range(2)]
+    res = [np.load(out + f".{r}.npz") for r in range(world)]
     for r in res:
         assert np.array_equal(r["mi"], oi)
         assert np.array_equal(r["md"].view(np.uint32), od.view(np.uint32))
-    assert np.array_equal(res[0]["order"], res[1]["order"])
+        assert np.array_equal(res[0]["order"], r["order"])
 
 
 def test_host_merge_matches_definition():
