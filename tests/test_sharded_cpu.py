@@ -200,10 +200,11 @@ def test_query_block_partition_covers_the_batch():
         assert seen == list(range(nq))
 
 
-def test_sharded_search_equals_single_process_oracle(tmp_path, oracle):
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_equals_single_process_oracle(tmp_path, oracle, world):
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     res = np.load(out)
     xb, q, coarse, cb, norms, asg, m, kc = _problem()
     ids = np.arange(xb.shape[0], dtype=np.int64) * 2 + 1
