@@ -87,6 +87,16 @@ def search_golden():
     od, oi, op = oracle.ivfpq_search(q, coarse, cb, norms, off, codes[order], ids[order], m, 256, nprobe, k, 0)
     out["ivfpq_dist"], out["ivfpq_ids"] = od, oi
     assert np.array_equal(op, pid)
+    # cosine rows of the coarse quantiser and the IVF-Flat index (CentroidBatchScore.swift:70-84; IVFIndex.swift:376-435,
+    # 905-927; DistanceUtils.swift:22-38), one centroid degenerate
+    cz = coarse.copy()
+    cz[5] = 0.0
+    out["cbs_cosine"] = oracle.centroid_batch_score(q, cz, 2)
+    out["probe_ids_cosine"] = oracle.probe_select_batch(q, cz, nprobe, 2)[0]
+    casg = oracle.assign_metric(xb, cz, 2)
+    out["assign_cosine"] = casg
+    coff, corder = oracle.build_lists(casg, kc)
+    out["ivfflat_cosine_dist"], out["ivfflat_cosine_ids"] = oracle.ivfflat_search(q, cz, coff, xb[corder], ids[corder], nprobe, k, 2)
     np.savez_compressed(os.path.join(OUT, "oracle_search_small.npz"), **out)
     print("oracle_search_small.npz:", {k_: v.shape for k_, v in out.items()})
 

@@ -67,6 +67,29 @@ def test_oracle_reproduces_search_golden(oracle):
     assert np.array_equal(ci, g["cosine_ids"]) and np.array_equal(bits(cd), bits(g["cosine_dist"]))
 
 
+def _cosine_coarse(P):
+    cz = P["coarse"].copy()
+    cz[5] = 0.0                                                        # the degenerate centroid of the golden rows
+    return cz
+
+
+def test_oracle_reproduces_cosine_golden(oracle):
+    """the cosine rows of the golden file: guarded CentroidBatchScore block, probe lists, list assignment and IVF-Flat
+    results under the cosine metric (one centroid degenerate: score exactly 1)."""
+    P, g = gi.search_problem(), _srch()
+    xb, q, kc, nprobe, k = P["xb"], P["q"], P["kc"], P["nprobe"], P["k"]
+    cz = _cosine_coarse(P)
+    sc = oracle.centroid_batch_score(q, cz, 2)
+    assert np.array_equal(bits(sc), bits(g["cbs_cosine"])) and (sc[:, 5] == 1.0).all()
+    assert np.array_equal(oracle.probe_select_batch(q, cz, nprobe, 2)[0], g["probe_ids_cosine"])
+    asg = oracle.assign_metric(xb, cz, 2)
+    assert np.array_equal(asg, g["assign_cosine"])
+    off, order = oracle.build_lists(asg, kc)
+    ids = np.arange(xb.shape[0], dtype=np.int64)
+    dd, ii = oracle.ivfflat_search(q, cz, off, xb[order], ids[order], nprobe, k, 2)
+    assert np.array_equal(ii, g["ivfflat_cosine_ids"]) and np.array_equal(bits(dd), bits(g["ivfflat_cosine_dist"]))
+
+
 def test_oracle_cosine_against_float64(oracle):
     """Cosine.run two-pass restatement vs a float64 evaluation of 1 - <q, x> / (|q| |x|): same ranking away from
     near-ties, distances within fp32 rounding; a zero row has similarity 0 (distance 1)."""
@@ -185,3 +208,23 @@ def test_cuda_search_stages_reproduce_golden(vk):
             both = {int(i): float(v) for i, v in zip(g["ivfpq_ids"][r], g["ivfpq_dist"][r])}
             both.update({int(i): float(v) for i, v in zip(gi_[r], gd[r])})
             assert all(abs(both[i] - kth) <= 1e-5 * abs(kth) for i in extra)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
+                    reason="cosine rows of the coarse quantiser / IVF-Flat index: written after this round's GPU budget was "
+                           "spent, not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
+def test_cuda_cosine_rows_reproduce_golden(vk):
+    from vectorindex_b200.index import IVFIndex
+    P, g = gi.search_problem(), _srch()
+    xb, q, kc, nprobe, k = P["xb"], P["q"], P["kc"], P["nprobe"], P["k"]
+    cz = _cosine_coarse(P)
+    assert np.array_equal(bits(vk.centroid_batch_score(q, cz, 2)), bits(g["cbs_cosine"]))
+    ivf = IVFIndex(xb.shape[1], "cosine", nlist=kc, nprobe=nprobe)
+    ivf.set_coarse(cz)
+    ivf.batch_insert(xb)
+    assert np.array_equal(ivf.list_sizes(), np.bincount(g["assign_cosine"], minlength=kc))
+    gd, gi_, gp = ivf.batch_search(q, k, return_probes=True)
+    assert np.array_equal(gp, g["probe_ids_cosine"])
+    assert np.array_equal(gi_, g["ivfflat_cosine_ids"])
+    np.testing.assert_allclose(gd, g["ivfflat_cosine_dist"], rtol=1e-5, atol=1e-6)
