@@ -479,7 +479,12 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel from the committed `ncu --set full`
     # captures (profiles/): known only for the configurations that were captured
-    traffic = {("c5", 1): 87.105206e9 + 7.9e6, ("c5s", 1): 5.486273e9 + 5.3e6}.get((args.workload, world))
+    captures = {("c5", 1, "lists"): (87.105206e9 + 7.9e6, "profiles/r01_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch)"),
+                ("c5s", 1, "lists"): (5.486273e9 + 5.3e6, "profiles/r01_scan_c5s_ncu_summary.txt (ncu --set full, one launch)"),
+                # rank 0's share of the 8-way list-sharded C5, captured on ONE GPU holding exactly that share
+                ("c5", 8, "lists"): (6.422206e9 + 6.883328e6, "profiles/r01_scan_shard8_ncu_summary.txt (ncu --set full, one launch "
+                                                               "of rank 0's one-eighth share, scripts/shard_emul.py 8 0)")}
+    traffic, traffic_src = captures.get((args.workload, world, args.partition if world > 1 else "lists"), (None, None))
     per_launch_bytes = scan_bytes / K                                  # rank 0's scan kernel, one launch per step
     per_launch_ms = scan_ms / K
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
@@ -496,7 +501,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"kernel": "ivfpq_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "profiles/r01_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch)" if traffic else None,
+                     "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                      "job_code_bytes_per_step": scan_bytes_all / K},
