@@ -481,9 +481,10 @@ def main():
     # captures (profiles/): known only for the configurations that were captured
     captures = {("c5", 1, "lists"): (87.105206e9 + 7.9e6, "profiles/r01_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch)"),
                 ("c5s", 1, "lists"): (5.486273e9 + 5.3e6, "profiles/r01_scan_c5s_ncu_summary.txt (ncu --set full, one launch)"),
-                # rank 0's share of the 8-way list-sharded C5, captured on ONE GPU holding exactly that share
+                # one rank's share of an 8-way list-sharded C5, captured on ONE GPU holding the first equal-count eighth of the
+                # lists (the bench's work-balanced boundaries move the block edges by a few lists: approximate for this run)
                 ("c5", 8, "lists"): (6.422206e9 + 6.883328e6, "profiles/r01_scan_shard8_ncu_summary.txt (ncu --set full, one launch "
-                                                               "of rank 0's one-eighth share, scripts/shard_emul.py 8 0)")}
+                                                               "of an equal-count one-eighth share, scripts/shard_emul.py 8 0; approximate)")}
     traffic, traffic_src = captures.get((args.workload, world, args.partition if world > 1 else "lists"), (None, None))
     per_launch_bytes = scan_bytes / K                                  # rank 0's scan kernel, one launch per step
     per_launch_ms = scan_ms / K
