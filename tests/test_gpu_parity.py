@@ -414,6 +414,13 @@ def test_centroid_scores_cosine_guarded(oracle, vk):
     assert (got[:, 7] == 1.0).all() and (got[3] == 1.0).all()
     cn = oracle.centroid_norms(c)
     assert np.array_equal(bits(vk.centroid_batch_score(q, c, 2, cn)), bits(want))
+    # IVFCosineCentroidEdgeCaseTests.swift:27-62: the tiny-norm centroid scores exactly 1, the identical direction ~0
+    c3 = np.zeros((3, 8), np.float32)
+    c3[0, :2] = 1.0; c3[1, 0] = 1.0; c3[2, 0] = 1e-8
+    q3 = np.zeros((1, 8), np.float32)
+    q3[0, :2] = 1.0
+    s3 = vk.centroid_batch_score(q3, c3, 2)[0]
+    assert s3[2] == np.float32(1.0) and abs(float(s3[0])) <= 1e-6 and s3[1] < s3[2]
 
 
 @pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",

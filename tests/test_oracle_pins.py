@@ -373,3 +373,29 @@ def test_encode_with_csq_equals_default_fixture(oracle):
         assert np.array_equal(oracle.ref_encode("cpq_encode_residual_u8_f32_with_csq", x, cb, m, ks, centroid_sq=csq,
                                                 coarse=coarse, assign_=asg),
                               oracle.ref_encode("cpq_encode_residual_u8_f32", x, cb, m, ks, coarse=coarse, assign_=asg))
+
+
+def test_cosine_degenerate_centroid_fixtures(oracle):
+    """IVFCosineCentroidEdgeCaseTests.swift:27-134: centroids (1,1,0..), (1,0,0..), (1e-8,0,..) and the query (1,1,0..):
+    the tiny-norm centroid scores EXACTLY 1 (the guard, not an approximation), the identical direction ~0, both
+    well-formed centroids sort before it, so nprobe = 2 of 3 never probes its list while nprobe = 3 reaches it; all-NaN
+    centroid scores assign nothing (-1)."""
+    c = np.zeros((3, 8), np.float32)
+    c[0, :2] = 1.0
+    c[1, 0] = 1.0
+    c[2, 0] = 1e-8
+    q = np.zeros((1, 8), np.float32)
+    q[0, :2] = 1.0
+    s = oracle.centroid_batch_score(q, c, 2)[0]
+    assert s[2] == np.float32(1.0) and s[0] < s[2] and s[1] < s[2] and abs(float(s[0])) <= 1e-6
+    assert oracle.probe_select_batch(q, c, 2, 2)[0][0].tolist() == [0, 1]
+    assert oracle.probe_select_batch(q, c, 3, 2)[0][0].tolist() == [0, 1, 2]
+    # one vector in list 0, one that only a probe of the degenerate centroid's list can surface
+    vecs = np.stack([q[0], q[0]])
+    off = np.array([0, 1, 1, 2], dtype=np.int64)
+    ids = np.array([10, 20], dtype=np.int64)
+    _, i2 = oracle.ivfflat_search(q, c, off, vecs, ids, 2, 5, 2)
+    _, i3 = oracle.ivfflat_search(q, c, off, vecs, ids, 3, 5, 2)
+    assert set(i2[0][i2[0] >= 0].tolist()) == {10} and set(i3[0][i3[0] >= 0].tolist()) == {10, 20}
+    nan_c = np.array([[np.nan, 0, 0, 0], [np.nan, 1, 1, 1]], dtype=np.float32)
+    assert oracle.assign_metric(np.zeros((1, 4), np.float32), nan_c, 0).tolist() == [-1]
