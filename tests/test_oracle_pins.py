@@ -399,3 +399,26 @@ def test_cosine_degenerate_centroid_fixtures(oracle):
     assert set(i2[0][i2[0] >= 0].tolist()) == {10} and set(i3[0][i3[0] >= 0].tolist()) == {10, 20}
     nan_c = np.array([[np.nan, 0, 0, 0], [np.nan, 1, 1, 1]], dtype=np.float32)
     assert oracle.assign_metric(np.zeros((1, 4), np.float32), nan_c, 0).tolist() == [-1]
+
+
+def test_recall_improves_with_nprobe_fixture(oracle):
+    """IVFProbeMonotonicTests.swift:18-44: n = 300, d = 32, nlist = 32, 20 queries, k = 5, LCG seeds 17 / 19, the actor's
+    optimize() (sorted String ids, k-means++ seed 42, mini-batch min(1024, n) x 20 epochs): recall with nprobe = 8 is at
+    least the recall with nprobe = 1."""
+    n, d, nq, k, nlist = 300, 32, 20, 5, 32
+    base = datagen.bench_vectors(n, d, 17)
+    qs = datagen.bench_vectors(nq, d, 19)
+    order = sorted(range(n), key=lambda i: "id%d" % i)          # IVFIndex.swift:325
+    xs = base[order]
+    cents, _ = oracle.kmeanspp_seed(xs, nlist, seed=42)
+    rc, cents, asg, _ = oracle.kmeans_minibatch(xs, nlist, init=cents, batch_size=min(1024, n), epochs=20, tol=1e-4,
+                                                seed=42, compute_assignments=True)
+    assert rc == 0
+    off, lorder = oracle.build_lists(asg, nlist)
+    ids = np.arange(n, dtype=np.int64)
+    truth = oracle.flat_search(qs, xs, k, 0)[1]
+    avg = []
+    for nprobe in (1, 8):
+        _, got = oracle.ivfflat_search(qs, cents, off, xs[lorder], ids[lorder], nprobe, k, 0)
+        avg.append(np.mean([len(set(truth[r].tolist()) & set(got[r][got[r] >= 0].tolist())) / k for r in range(nq)]))
+    assert avg[1] >= avg[0] and avg[1] > 0.5
