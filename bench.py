@@ -250,7 +250,9 @@ def cpu_search_arm(cfg, idx, q_host, budget_s=12.0, gpu_ids=None):
     coarse = idx.get_coarse()
     cb, norms = idx.get_codebooks()
     off, codes, lids, _ = idx.export_lists()
-    cores = os.cpu_count() or 1
+    # every host core this process may run on, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = oracle.set_threads(want)                                 # = omp_get_max_threads() after the call
     args = (coarse, cb, norms, off, codes, lids, cfg["m"], 256, cfg["nprobe"], cfg["k"], 1 if cfg.get("metric") == "dotProduct" else 0)
     probe = min(q_host.shape[0], 2 * cores)
     t0 = time.perf_counter()
@@ -262,7 +264,7 @@ def cpu_search_arm(cfg, idx, q_host, budget_s=12.0, gpu_ids=None):
     dt = time.perf_counter() - t0
     out = {"value": s / dt, "unit": "queries/s", "cores": cores, "kind": "port",
            "sample": f"first {s} of the {q_host.shape[0]} queries, full index, oracle/ C restatement with OpenMP over queries "
-                     f"({dt:.1f} s)"}
+                     f"({dt:.1f} s, {cores} OpenMP threads)"}
     if gpu_ids is not None:
         g = gpu_ids[:s]
         out["topk_overlap_with_gpu"] = float(np.mean([len(set(g[r]) & set(oi[r])) / cfg["k"] for r in range(s)]))
@@ -342,13 +344,14 @@ def main():
 
     base_cfg = {"workload": cfg["label"], "n": cfg["n"], "d": d, "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
                 "M": cfg["m"], "ks": 256, "batch_queries": nq, "k": k, "metric": cfg.get("metric", "euclidean"),
-                "partition": (f"inverted lists in contiguous blocks over {eff_world} rank(s); queries replicated; probe selection "
-                              "split by query block + all-gather of list ids; per-rank top-k merged by all-gather + mergeTopK")
-                if args.partition == "lists" or eff_world == 1 else
-                             f"full replica on each of {eff_world} rank(s); batch split by query block; all-gather of the "
-                             "finished [nq/world x k] blocks",
-                "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps",
-                "build": build_t}
+                "l2_policy": "inputs larger than L2 (code arrays >> 126 MB); no flush between steps"}
+    # run-dependent facts live OUTSIDE `config`, so that both arms print the same `config` object
+    detail = {"partition": (f"inverted lists in contiguous blocks over {eff_world} rank(s); queries replicated; probe selection "
+                            "split by query block + exchange of list ids; per-rank top-k exchanged + mergeTopK")
+              if args.partition == "lists" or eff_world == 1 else
+              f"full replica on each of {eff_world} rank(s); batch split by query block; all-gather of the "
+              "finished [nq/world x k] blocks",
+              "build": build_t}
 
     # ---------------------------------------------------------------- reference arm (CPU only)
     if args.impl == "reference":
@@ -364,7 +367,7 @@ def main():
         line = {"impl": "reference", "metric": "queries/sec at matched recall@10 (IVF-PQ)", "value": val,
                 "unit": "queries/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_t / K,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": base_cfg, "cpu_baseline": info,
+                "config": base_cfg, "detail": detail, "cpu_baseline": info,
                 "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         clk.stop()
@@ -493,7 +496,8 @@ def main():
         "metric": "queries/sec at matched recall@10 (IVF-PQ)", "value": nq * K / (ms_total * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(base_cfg, recall_at_10=recall, recall_queries=GT_QUERIES,
+        "config": base_cfg,
+        "detail": dict(detail, recall_at_10=recall, recall_queries=GT_QUERIES,
                        stage_ms_per_step={"probe_select": coarse_ms / K, "lut_adc_scan_topk": scan_ms / K},
                        sharded_phase_ms=phase_ms),
         "clocks": clk.summary(),

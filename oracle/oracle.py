@@ -56,6 +56,11 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def set_threads(n: int = 0) -> int:
+    """Host threads of the oracle's OpenMP loops (n > 0 sets them); returns the count in effect."""
+    return int(lib().vo_set_threads(C.c_int(int(n))))
+
+
 def ref_lib(omp: bool = False):
     key = "omp" if omp else "st"
     if key not in _REF:

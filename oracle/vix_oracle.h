@@ -45,6 +45,9 @@ float vo_lut_dot(const float* a, const float* b, int len);
 float vo_pq_sqnorm(const float* a, int d);
 
 /* ---- block scoring ---- */
+/* OpenMP threads of the oracle's row / query loops: n > 0 sets, returns the count in effect */
+int vo_set_threads(int n);
+
 void vo_l2sqr_block(const float* q, const float* xb, int64_t n, int d, float* out,
                     const float* xb_norm, float q_norm);
 void vo_ip_block(const float* q, const float* xb, int64_t n, int d, float* out);

@@ -12,6 +12,22 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Host threads of the OpenMP loops below (over independent rows / queries only).  n > 0 sets the count (the
+ * launcher of a multi-process job exports OMP_NUM_THREADS=1, which would otherwise silently serialise the
+ * CPU baseline); returns the count the next parallel region will use. */
+int vo_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static inline float hsum4(const float* v) { return ((v[0] + v[1]) + v[2]) + v[3]; }
 

@@ -211,9 +211,6 @@ def test_cuda_search_stages_reproduce_golden(vk):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="cosine rows of the coarse quantiser / IVF-Flat index: written after this round's GPU budget was "
-                           "spent, not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 def test_cuda_cosine_rows_reproduce_golden(vk):
     from vectorindex_b200.index import IVFIndex
     P, g = gi.search_problem(), _srch()

@@ -69,9 +69,6 @@ def test_pq_encode_bit_exact_all_entry_points(oracle, vk, n, d, m):
                               oracle.pq_encode_u4(x, cb4, m, 16, coarse=coarse, assign_=assign))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="64-row encode CTAs for long sub-vectors: written after this round's GPU budget was spent, not yet "
-                           "run on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 @pytest.mark.parametrize("n,d,m", [(700, 1024, 8), (300, 1536, 8), (130, 600, 4)])
 def test_pq_encode_long_subvectors(oracle, vk, n, d, m):
     """d / m = 128 (ResidualKernelTests.swift:126-200: fused residual codes == codes of the materialised residuals), 192
@@ -395,9 +392,6 @@ def test_centroid_scores_and_probe_selection(oracle, vk, metric):
     assert np.array_equal(gi, oi) and np.array_equal(bits(gs), bits(os_))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="cosine CentroidBatchScore epilogue: written after this round's GPU budget was spent, not yet run on a "
-                           "B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 def test_centroid_scores_cosine_guarded(oracle, vk):
     """CentroidBatchScore.swift:70-84: 1 - <q, c> qInv cInv with the near-zero-norm guard, bit for bit (zero centroid, zero
     query and a tiny-norm centroid under the guard => exactly 1)."""
@@ -423,9 +417,6 @@ def test_centroid_scores_cosine_guarded(oracle, vk):
     assert s3[2] == np.float32(1.0) and abs(float(s3[0])) <= 1e-6 and s3[1] < s3[2]
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="rows too long for the tiled engine (d > ~1700): written after this round's GPU budget was spent, not "
-                           "yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 @pytest.mark.parametrize("metric", [0, 1])
 def test_probe_selection_long_rows(oracle, vk, metric):
     """IVFSelectTests.swift:578-609: d = 2048, 100 centroids, nprobe = 10 -- one thread per pair + selection on the
@@ -462,7 +453,63 @@ def test_probe_selection_pins_and_padding(oracle, vk):
     assert gi[0].tolist() == [0, 3, 5]
 
 
+# ------------------------------------------------------------------------------------------------ a16 seam
+def test_accel_rank_candidates_reference_fixture(vk):
+    """AccelerableIndexTests.swift:14-66: three stored vectors, query [2, 3, 4], euclidean: the two nearest candidates are
+    rows 0 and 1 at sqrt(3) = 1.732 and sqrt(27) = 5.196 (the distances the reference test feeds back as AcceleratedResults)."""
+    cand = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.float32)
+    idx, dist = vk.accel_rank_candidates(np.array([[2, 3, 4]], dtype=np.float32), cand, 2)
+    assert idx.tolist() == [[0, 1]]
+    np.testing.assert_allclose(dist[0], [1.732, 5.196], atol=1e-3)
+    assert dist.dtype == np.float32 and idx.dtype == np.int32
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2])
+@pytest.mark.parametrize("c,d,nq,k", [(700, 64, 9, 10), (5000, 128, 40, 10), (3, 16, 2, 10), (257, 96, 1, 1)])
+def test_accel_rank_candidates_equals_flat_search(oracle, vk, metric, c, d, nq, k):
+    """The AccelerableIndex seam (AccelerableIndex.swift:15-127, 130-194): candidates [c x d] row-major in, per query the
+    best-first (indices into the candidate block, API distances) out == the reference's flat scoring + selectTopK over that
+    block (FlatIndexOptimized.swift:390-477), bit for bit, incl. duplicate candidates (tie -> smaller index) and c < k."""
+    rng = np.random.default_rng(1000 * metric + c)
+    cand = rng.standard_normal((c, d)).astype(np.float32)
+    if c > 20:
+        cand[c // 2:c // 2 + 6] = cand[3:9]                                # exact ties
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q[0] = cand[min(5, c - 1)]
+    od, oi, _ = oracle.flat_search(q, cand, k, metric)
+    gi, gd = vk.accel_rank_candidates(q, cand, k, metric)
+    assert np.array_equal(gi.astype(np.int64), oi.astype(np.int64))
+    valid = oi >= 0
+    assert np.array_equal(bits(gd)[valid], bits(od)[valid])
+    assert np.isnan(gd[~valid]).all()
+    # nothing to rank: k <= 0 and an empty candidate block
+    assert vk.accel_rank_candidates(q, cand, 0, metric)[0].shape == (nq, 0)
+    ei, ed = vk.accel_rank_candidates(q, np.zeros((0, d), np.float32), 3, metric)
+    assert (ei == -1).all() and np.isnan(ed).all()
+
+
 # ------------------------------------------------------------------------------------------------ LUT + ADC
+def test_fused_residual_lut_equals_lut_of_materialised_residual(oracle, vk):
+    """ResidualKernelTests.swift:208-270: pq_lut_residual_l2_f32(q, c) == pq_lut_l2_f32(q - c) -- on the CUDA library, and
+    both equal to the oracle's tables bit for bit (reference shape d 512, m 8, ks 256, plus a batch of residual shapes)."""
+    rng = np.random.default_rng(208)
+    for d, m in ((512, 8), (96, 48), (128, 16)):
+        ks, nq, kc = 256, 6, 4
+        q = rng.uniform(-1, 1, (nq, d)).astype(np.float32)
+        coarse = rng.uniform(-1, 1, (kc, d)).astype(np.float32)
+        cids = rng.integers(0, kc, nq).astype(np.int32)
+        cb = rng.uniform(-1, 1, m * ks * (d // m)).astype(np.float32)
+        fused = vk.pq_lut_residual_l2_f32(q, cids, coarse, cb, m, ks)
+        plain = vk.pq_lut_batch_l2_f32((q - coarse[cids]).astype(np.float32), cb, m, ks)
+        assert np.array_equal(bits(fused), bits(plain))
+        for i in range(nq):
+            assert np.array_equal(bits(fused[i]), bits(oracle.pq_lut_residual_l2(q[i], coarse[cids[i]], cb, m, ks)))
+        cn = oracle.pq_centroid_sq(cb, m, ks, d // m, swift=False)
+        fn = vk.pq_lut_residual_l2_f32(q, cids, coarse, cb, m, ks, cn)
+        pn = vk.pq_lut_batch_l2_f32((q - coarse[cids]).astype(np.float32), cb, m, ks, cn)
+        assert np.max(np.abs(fn - pn)) < 1e-4                              # the reference test's own accuracy
+
+
 @pytest.mark.parametrize("d,m", [(128, 16), (96, 48), (768, 64), (40, 4)])
 def test_pq_lut_bit_exact(oracle, vk, d, m):
     rng = np.random.default_rng(d)
@@ -605,9 +652,6 @@ def test_batchwide_tables_equal_in_kernel_tables(oracle, monkeypatch, d, metric)
     assert np.array_equal(i1, i2) and np.array_equal(bits(d1), bits(d2))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="two-pipeline scan (VIX_SCAN_DUAL=1): written after this round's GPU budget was spent -- opt-in and "
-                           "not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs the comparison")
 @pytest.mark.parametrize("d,m,metric,nq,k,filtered", [
     (96, 48, "euclidean", 700, 10, False),     # C5-shaped: three shared 64 KB tables
     (128, 16, "euclidean", 333, 10, False),    # one table, both pipelines in its two half rows
@@ -857,9 +901,6 @@ def test_ivfflat_and_flat_index(oracle, metric):
     assert np.array_equal(fi, oi + 100) and np.array_equal(bits(fd), bits(od))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="cosine for the IVF-Flat index: written after this round's GPU budget was spent, not yet run on a "
-                           "B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 def test_ivfflat_cosine_index(oracle):
     """IVFIndex with the cosine metric: lists by the first minimum of the guarded CentroidBatchScore row
     (IVFIndex.swift:376-435), probes by (score, list id) (:905-927), candidate distances 1 - clamp(dot / sqrt(|q|^2 |x|^2))
@@ -885,9 +926,6 @@ def test_ivfflat_cosine_index(oracle):
     assert_topk_close(gd, gi, od, oi, rtol=RTOL, atol=1e-6)
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="IVF-Flat insert -> optimize() -> search: written after this round's GPU budget was spent, not yet run "
-                           "on a B200; VIX_TEST_EXPERIMENTAL=1 runs it")
 def test_ivfflat_insert_then_optimize(oracle):
     """IVFMoreTests.swift:5-15 (linear scan before optimize) and the reference's build order: vectors first, then
     optimize() over the stored vectors, which files them into their lists; set_coarse on a filled index does the same."""
@@ -946,9 +984,6 @@ def test_kmeanspp_seed_parity(oracle, vk):
         assert np.array_equal(bits(gc), bits(oc))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="edge-case shapes of the reference's seeding tests: added after this round's GPU budget was spent, "
-                           "not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs them")
 def test_kmeanspp_seed_edge_cases(oracle, vk):
     """KMeansPPSeedingTests.swift:182-296 (k = 1, k = n, duplicated points): the same chosen rows as the oracle."""
     from test_oracle_pins import _kmeanspp_edge_cases
@@ -958,9 +993,6 @@ def test_kmeanspp_seed_edge_cases(oracle, vk):
         assert np.array_equal(gch, och) and np.array_equal(bits(gc), bits(oc))
 
 
-@pytest.mark.skipif(os.environ.get("VIX_TEST_EXPERIMENTAL") != "1",
-                    reason="edge-case shapes of the reference's mini-batch tests: added after this round's GPU budget was "
-                           "spent, not yet run on a B200; VIX_TEST_EXPERIMENTAL=1 runs them")
 def test_kmeans_minibatch_edge_cases(oracle, vk):
     """KMeansMiniBatchTests.swift:405-487, 616-646 (one centroid, batch larger than n, identical points): bit-identical
     to the oracle in reference-parity mode."""

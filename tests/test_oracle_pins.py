@@ -422,3 +422,23 @@ def test_recall_improves_with_nprobe_fixture(oracle):
         _, got = oracle.ivfflat_search(qs, cents, off, xs[lorder], ids[lorder], nprobe, k, 0)
         avg.append(np.mean([len(set(truth[r].tolist()) & set(got[r][got[r] >= 0].tolist())) / k for r in range(nq)]))
     assert avg[1] >= avg[0] and avg[1] > 0.5
+
+
+def test_fused_residual_lut_equals_lut_of_materialised_residual(oracle):
+    """ResidualKernelTests.swift:208-270 (disabled there over an alignment precondition of the LUT kernel, the property
+    itself is the contract of pq_lut_residual_l2_f32, PQLUT.swift:266-386): the fused residual LUT equals the plain LUT of
+    the materialised residual q - c.  Both restatements subtract first and walk the same accumulators (PQLUT.swift:293-341
+    against :197-240), so with the reference test's shape (d 512, m 8, ks 256) and without centroid norms the two tables are
+    bit-identical -- far inside the reference's own 1e-4; with norms + dot trick the reference's tolerance applies."""
+    rng = np.random.default_rng(208)
+    d, m, ks = 512, 8, 256
+    q = rng.uniform(-1, 1, d).astype(np.float32)
+    c = rng.uniform(-1, 1, d).astype(np.float32)
+    cb = rng.uniform(-1, 1, m * ks * (d // m)).astype(np.float32)
+    fused = oracle.pq_lut_residual_l2(q, c, cb, m, ks)
+    plain = oracle.pq_lut_l2((q - c).astype(np.float32), cb, m, ks)
+    assert np.array_equal(fused.view(np.uint32), plain.view(np.uint32))
+    cn = oracle.pq_centroid_sq(cb, m, ks, d // m, swift=False)
+    fused_n = oracle.pq_lut_residual_l2(q, c, cb, m, ks, cn)
+    plain_n = oracle.pq_lut_l2((q - c).astype(np.float32), cb, m, ks, cn)
+    assert np.max(np.abs(fused_n - plain_n)) < 1e-4 and np.max(np.abs(fused_n - plain)) < 1e-3
