@@ -12,7 +12,19 @@
  *     nothing aborts; vix_last_error() describes the failure;
  *   - there is NO CPU fallback: without a usable CUDA device every entry point returns
  *     VIX_ERR_NO_DEVICE;
- *   - thread-safe: stateless entry points are re-entrant; index handles serialise internally.
+ *   - thread-safe: stateless entry points are re-entrant; an index handle serialises the HOST side of its calls
+ *     (a mutex per handle: one add / search enqueues at a time, the reference's actor isolation, IVFIndex.swift:13).
+ *     Device work of calls issued from different threads is ordered only by their streams: every search owns its
+ *     work queue and scratch (stream-ordered allocations), so concurrent asynchronous searches of one handle on
+ *     different streams are independent; a call that CHANGES the handle (add, train, set_*, clear, the lazy list
+ *     rebuild of the first search after an add) must not overlap other calls still running on another stream --
+ *     synchronise (vix_synchronize) before it;
+ *   - ids live in [0, 2^32 - 1) (the reference's top-k id type is Int32, TopK.swift:59), checked for host AND device
+ *     id arrays; adding an id that is already stored APPENDS a second row (the reference's Dictionary store replaces,
+ *     IVFIndex.swift:42): callers that need replacement delete / rebuild; duplicates are returned as separate results;
+ *   - list ids (assignments handed to vix_index_add_encoded, probe lists handed to *_with_probes*) outside [0, kc) are
+ *     rejected (assignments) or skipped like the -1 padding (probes); rows whose scores are all NaN get no list:
+ *     IVF_FLAT keeps them unreachable as the reference does (IVFIndex.swift:376-435 "guard best >= 0"), IVF_PQ add fails.
  *
  * Each declaration cites the reference interface it replaces (paths relative to
  * /root/reference/Sources/VectorIndex unless another root is given).

@@ -877,6 +877,68 @@ def test_ivfpq_edge_cases(oracle):
     assert idx.search(q[0], 2)[0][0] >= 0
 
 
+def test_invalid_list_ids_device_ids_and_duplicates(oracle):
+    """Contract edges of the handles (include/vindex_cuda.h conventions): list assignments outside [0, kc) are rejected,
+    probe ids outside [0, kc) are skipped like the -1 padding, DEVICE-resident ids are range-checked like host ids, an id
+    stored twice comes back twice (append, not replace), and a NaN row is refused by an IVF-PQ add / left without a list
+    by an IVF-Flat one (IVFIndex.swift:376-435: "guard best >= 0 else continue")."""
+    import torch
+    from vectorindex_b200.index import IVFIndex, IVFPQIndex
+    from vectorindex_b200 import VectorIndexError
+    d, m, kc = 32, 16, 8
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, 2000, d, m, kc, 6, seed=5)
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=3, m=m)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    asg, codes = idx.encode(xb)
+    ids = np.arange(2000, dtype=np.int64)
+    bad = asg.copy()
+    bad[17] = kc
+    with pytest.raises(VectorIndexError):
+        idx.add_encoded(bad, codes, ids)
+    bad[17] = -1
+    with pytest.raises(VectorIndexError):
+        idx.add_encoded(torch.from_numpy(bad).cuda(), torch.from_numpy(codes).cuda(), torch.from_numpy(ids).cuda())
+    dev_ids = torch.from_numpy(ids).cuda()
+    dev_ids[3] = -7
+    with pytest.raises(VectorIndexError):
+        idx.add_encoded(torch.from_numpy(asg).cuda(), torch.from_numpy(codes).cuda(), dev_ids)
+    dev_ids[3] = 0xFFFFFFFF
+    with pytest.raises(VectorIndexError):
+        idx.batch_insert(torch.from_numpy(xb).cuda(), dev_ids)
+    assert idx.count == 0
+    nanrow = xb[:4].copy()
+    nanrow[2] = np.nan
+    with pytest.raises(VectorIndexError):
+        idx.batch_insert(nanrow)
+    assert idx.count == 0
+    idx.add_encoded(torch.from_numpy(asg).cuda(), torch.from_numpy(codes).cuda(),
+                    torch.from_numpy(ids).to(torch.int32).cuda())          # a tensor of another width is cast, not reinterpreted
+    # probes: ids >= kc / < -1 behave like the -1 padding
+    gd, gi, probes = idx.batch_search(q, 5, return_probes=True)
+    wide = np.concatenate([probes, np.full((6, 1), -1, np.int32)], axis=1)
+    junk = wide.copy()
+    junk[:, -1] = [kc, kc + 100, -5, 2 ** 30, -1, kc]
+    d1, i1 = idx.search_with_probes(q, 5, wide)
+    d2, i2 = idx.search_with_probes(q, 5, junk)
+    assert np.array_equal(i1, gi) and np.array_equal(i2, gi) and np.array_equal(bits(d2), bits(gd))
+    # the same id stored twice: both rows are results of their own (identical code => identical distance)
+    row = int(gi[0, 0])
+    idx.add_encoded(asg[row:row + 1], codes[row:row + 1], np.array([row], dtype=np.int64))
+    d3, i3 = idx.batch_search(q[:1], 5)
+    assert i3[0, 0] == row and i3[0, 1] == row and bits(d3)[0, 0] == bits(d3)[0, 1]
+    assert np.array_equal(i3[0, 2:], gi[0, 1:4])
+    # IVF-Flat, cosine: an all-NaN row gets no list and is never returned; the other rows are unaffected
+    flat = IVFIndex(d, "cosine", nlist=kc, nprobe=kc)
+    flat.set_coarse(coarse)
+    xs = xb[:300].copy()
+    xs[5] = np.nan
+    flat.batch_insert(xs)
+    fd, fi = flat.batch_search(q, 10)
+    assert 5 not in fi and (fi >= 0).all() and flat.count == 300
+    assert flat.list_sizes().sum() == 299
+
+
 @pytest.mark.parametrize("metric", [0, 1])
 def test_ivfflat_and_flat_index(oracle, metric):
     from vectorindex_b200.index import FlatIndex, IVFIndex

@@ -170,10 +170,15 @@ def ptr(a, dtype=None):
 
 
 def as_input(a, dtype):
-    """Contiguous array of ``dtype`` (numpy input is converted; torch tensors are passed through)."""
+    """Contiguous array / tensor of ``dtype`` (converted when it is not; stays on its device)."""
     if a is None:
         return None
     if _is_torch(a):
+        import torch
+        want = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8,
+                np.uint64: torch.int64}.get(dtype)
+        if want is not None and a.dtype != want:       # e.g. int32 ids: the C side reads int64
+            a = a.to(want)
         return a.contiguous()
     return np.ascontiguousarray(a, dtype=dtype)
 

@@ -70,9 +70,13 @@ struct DevBuf {
         while (ncap < n) ncap = ncap + ncap / 2 + 1024;
         T* np = nullptr;
         VIX_CUDA(cudaMalloc(reinterpret_cast<void**>(&np), ncap * sizeof(T)));
-        if (keep && ptr && size)
-            VIX_CUDA(cudaMemcpyAsync(np, ptr, size * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
-        if (ptr) { VIX_CUDA(cudaStreamSynchronize(ctx().stream)); cudaFree(ptr); }
+        if (ptr) {
+            cudaError_t e = cudaSuccess;
+            if (keep && size) e = cudaMemcpyAsync(np, ptr, size * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+            if (e != cudaSuccess) { cudaFree(np); VIX_CUDA(e); }          // keep the old buffer, drop the new one
+            cudaFree(ptr);
+        }
         ptr = np; cap = ncap;
         return VIX_OK;
     }
@@ -119,7 +123,6 @@ struct vix_index {
     DevBuf<int64_t> slot_ids;           // [nslots]
     DevBuf<float> slot_vecs;            // IVF_FLAT: [nslots x d]
     DevBuf<float> codebooks_t;          // [ks x m x dsub] code-major copy of the codebooks
-    DevBuf<int> work_counter;           // scan work queue head
     int align = 32;                     // list granularity in slots (ScanLayout::align)
     // search_ex(stats): events and counter are created once per handle
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -176,13 +179,53 @@ __global__ void offsets_kernel(const int32_t* __restrict__ len, int kc, int alig
 }
 
 // slot_row[off[l] + r] = sorted_rows[off_raw[l] + r]
+// Rows without a list (assignment outside [0, kc): the -1 of an all-NaN / all-+inf score row, IVFIndex.swift:376-435
+// "guard best >= 0 else continue") carry the sort key kc, so they sort behind every list and are not placed.
 __global__ void place_rows_kernel(const int32_t* __restrict__ sorted_rows, const int32_t* __restrict__ sorted_lists,
-                                  int64_t n, const int64_t* __restrict__ off, const int64_t* __restrict__ off_raw,
+                                  int64_t n, int kc, const int64_t* __restrict__ off, const int64_t* __restrict__ off_raw,
                                   int32_t* __restrict__ slot_row) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int l = sorted_lists[i];
+    if ((unsigned)l >= (unsigned)kc) return;
     slot_row[off[l] + (i - off_raw[l])] = sorted_rows[i];
+}
+
+// flag[0] += number of assignments outside [0, kc)
+__global__ void count_invalid_assign_kernel(const int32_t* __restrict__ assign, int64_t n, int kc,
+                                            unsigned long long* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && (unsigned)assign[i] >= (unsigned)kc;
+    const unsigned ball = __ballot_sync(0xFFFFFFFFu, bad);
+    if (ball && (threadIdx.x & 31) == 0) atomicAdd(flag, (unsigned long long)__popc(ball));
+}
+
+__global__ void sanitise_assign_kernel(const int32_t* __restrict__ assign, int64_t n, int kc, int32_t* __restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int a = assign[i]; keys[i] = (unsigned)a < (unsigned)kc ? a : kc; }
+}
+
+// flag[0] += ids outside [0, 2^32 - 1) (the id half of a selection key; 0xFFFFFFFF is the empty key)
+__global__ void count_invalid_ids_kernel(const int64_t* __restrict__ ids, int64_t n, unsigned long long* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && (ids[i] < 0 || ids[i] >= 0xFFFFFFFFLL);
+    const unsigned ball = __ballot_sync(0xFFFFFFFFu, bad);
+    if (ball && (threadIdx.x & 31) == 0) atomicAdd(flag, (unsigned long long)__popc(ball));
+}
+
+// number of assignments outside [0, kc) in a device array (synchronises the stream)
+static int count_invalid_assign(const int32_t* assign, int64_t n, int kc, unsigned long long* out) {
+    *out = 0;
+    if (n <= 0) return VIX_OK;
+    Scratch<unsigned long long> flag;
+    VIX_TRY(flag.alloc(1));
+    cudaStream_t s = ctx().stream;
+    VIX_CUDA(cudaMemsetAsync(flag.ptr, 0, 8, s));
+    count_invalid_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(assign, n, kc, flag.ptr);
+    VIX_LAUNCH_CHECK();
+    VIX_CUDA(cudaMemcpyAsync(out, flag.ptr, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    return VIX_OK;
 }
 
 // Fill one slot: codes in the scan layout (vix_scan.cuh), id, t_x.  One warp per slot (lanes split the
@@ -263,7 +306,18 @@ static int build_lists(vix_index* h) {
     VIX_TRY(h->slot_ids.resize((size_t)nslots, false));
     if (nslots > 0) VIX_CUDA(cudaMemsetAsync(h->slot_row.ptr, 0xFF, (size_t)nslots * 4, s));
     if (n > 0) {
-        // stable sort of rows by list: radix sort over the list-id bits
+        // stable sort of rows by list: radix sort over the list-id bits.  Rows without a list (assignment outside
+        // [0, kc)) get the key kc in a sanitised copy of the keys, made only when such rows exist.
+        unsigned long long invalid = 0;
+        VIX_TRY(count_invalid_assign(h->assign.ptr, n, kc, &invalid));
+        Scratch<int32_t> keys;
+        const int32_t* sort_keys = h->assign.ptr;
+        if (invalid) {
+            VIX_TRY(keys.alloc((size_t)n));
+            sanitise_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->assign.ptr, n, kc, keys.ptr);
+            VIX_LAUNCH_CHECK();
+            sort_keys = keys.ptr;
+        }
         Scratch<int32_t> rows_in, rows_out, lists_out;
         VIX_TRY(rows_in.alloc((size_t)n));
         VIX_TRY(rows_out.alloc((size_t)n));
@@ -271,16 +325,16 @@ static int build_lists(vix_index* h) {
         iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows_in.ptr, n);
         VIX_LAUNCH_CHECK();
         int bits = 1;
-        while ((1LL << bits) < kc) ++bits;
+        while ((1LL << bits) < (int64_t)kc + 1) ++bits;               // keys 0 .. kc
         size_t tmp_bytes = 0;
-        VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->assign.ptr, lists_out.ptr, rows_in.ptr,
+        VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sort_keys, lists_out.ptr, rows_in.ptr,
                                                  rows_out.ptr, (int)n, 0, bits, s));
         Scratch<unsigned char> tmp;
         VIX_TRY(tmp.alloc(tmp_bytes + 16));
-        VIX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, h->assign.ptr, lists_out.ptr, rows_in.ptr,
+        VIX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, sort_keys, lists_out.ptr, rows_in.ptr,
                                                  rows_out.ptr, (int)n, 0, bits, s));
         ctx().launches += 1;
-        place_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows_out.ptr, lists_out.ptr, n, h->list_off.ptr,
+        place_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows_out.ptr, lists_out.ptr, n, kc, h->list_off.ptr,
                                                                      off_raw.ptr, h->slot_row.ptr);
         VIX_LAUNCH_CHECK();
     }
@@ -312,42 +366,67 @@ static int build_lists(vix_index* h) {
 // ------------------------------------------------------------------------------------------------
 // query order for the scan: work item -> query, sorted by first probed list (L2 locality)
 // ------------------------------------------------------------------------------------------------
-// key of a query = the first probed list that holds vectors HERE (on a shard most probes belong to other ranks);
-// one warp per query
+// key of a query = the first probed list that holds vectors HERE (on a shard most probes belong to other ranks), kc if
+// none does; one warp per query.  The keys are list ids, so the order is a COUNTING sort written here (histogram over
+// the kc + 1 keys -> exclusive scan -> scatter), three small kernels, no library call on the search path.
 __global__ void first_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe,
-                                   const int32_t* __restrict__ list_len, int32_t* __restrict__ keys,
-                                   int32_t* __restrict__ vals) {
+                                   const int32_t* __restrict__ list_len, int kc, int32_t* __restrict__ keys,
+                                   int32_t* __restrict__ hist) {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq) return;
-    int key = 0x7FFFFFFF;
+    int key = kc;
     for (int base = 0; base < nprobe; base += 32) {
         const int p = base + lane;
         const int l = p < nprobe ? __ldg(probes + i * nprobe + p) : -1;
-        const bool here = l >= 0 && __ldg(list_len + l) > 0;
+        const bool here = (unsigned)l < (unsigned)kc && __ldg(list_len + l) > 0;
         const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
         if (ball) { key = __shfl_sync(0xFFFFFFFFu, l, __ffs(ball) - 1); break; }
     }
-    if (lane == 0) { keys[i] = key; vals[i] = (int32_t)i; }
+    if (lane == 0) { keys[i] = key; atomicAdd(hist + key, 1); }
+}
+
+// single CTA: hist[0, n) -> exclusive prefix sums in place (each thread owns a contiguous run of bins)
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(int32_t* __restrict__ hist, int n) {
+    __shared__ int s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += hist[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_part[threadIdx.x] - sum;
+    for (int i = b; i < e; ++i) { const int v = hist[i]; hist[i] = run; run += v; }
+}
+
+// order[cursor[key]++] = query (queries with the same key land next to each other; their mutual order is free)
+__global__ void scatter_order_kernel(const int32_t* __restrict__ keys, int64_t nq, int32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) order[atomicAdd(cursor + keys[i], 1)] = (int32_t)i;
 }
 
 static int query_order(const int32_t* probes, int64_t nq, int nprobe, const int32_t* list_len, int kc,
                        Scratch<int32_t>& order) {
     cudaStream_t s = ctx().stream;
-    Scratch<int32_t> keys, keys_out, vals;
+    Scratch<int32_t> keys, hist;
     VIX_TRY(keys.alloc((size_t)nq));
-    VIX_TRY(keys_out.alloc((size_t)nq));
-    VIX_TRY(vals.alloc((size_t)nq));
+    VIX_TRY(hist.alloc((size_t)kc + 1));
     VIX_TRY(order.alloc((size_t)nq));
-    first_probe_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(probes, nq, nprobe, list_len, keys.ptr, vals.ptr);
+    VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)kc + 1) * 4, s));
+    first_probe_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(probes, nq, nprobe, list_len, kc, keys.ptr, hist.ptr);
     VIX_LAUNCH_CHECK();
-    size_t tmp_bytes = 0;
-    VIX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_out.ptr, vals.ptr, order.ptr, (int)nq, 0, 31, s));
-    Scratch<unsigned char> tmp;
-    VIX_TRY(tmp.alloc(tmp_bytes + 16));
-    VIX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_out.ptr, vals.ptr, order.ptr, (int)nq, 0, 31, s));
-    ctx().launches += 1;
-    (void)kc;
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(hist.ptr, kc + 1);
+    VIX_LAUNCH_CHECK();
+    scatter_order_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(keys.ptr, nq, hist.ptr, order.ptr);
+    VIX_LAUNCH_CHECK();
     return VIX_OK;
 }
 
@@ -438,7 +517,7 @@ static int assign_lists_device(vix_index_t* h, const float* x, int64_t n, int32_
 // lists in the reference's order (Direct16 / Ip4), API distance (sqrt / negate), (distance, id) order.
 __global__ void __launch_bounds__(256)
 ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const int32_t* __restrict__ probes,
-                    int nprobe, const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
+                    int nprobe, const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len, int kc,
                     const float* __restrict__ slot_vecs, const int64_t* __restrict__ slot_ids, int metric, int k,
                     int P, const uint64_t* __restrict__ filter, int64_t filter_cap, int filter_deny,
                     float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
@@ -455,7 +534,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int64_t nq, int d, const 
         const float qmag2 = (metric == VIX_METRIC_COSINE) ? seq_sumsq(s_q, d) : 0.0f;
         for (int p = 0; p < nprobe; ++p) {
             const int l = probes[qi * (int64_t)nprobe + p];
-            if (l < 0) continue;
+            if ((unsigned)l >= (unsigned)kc) continue;           // -1 padding, or an id no list has
             const int64_t b = list_off[l];
             const int len = list_len[l];
             for (int base = 0; base < len; base += blockDim.x) {
@@ -534,6 +613,24 @@ static int update_codebooks_t(vix_index* h) {
     return VIX_OK;
 }
 
+// device-resident ids (the multi-GPU build hands over what the exchange delivered): same contract, checked by a kernel
+static int check_ids_device(const int64_t* ids, int64_t n) {
+    if (n <= 0) return VIX_OK;
+    Scratch<unsigned long long> flag;
+    VIX_TRY(flag.alloc(1));
+    cudaStream_t s = ctx().stream;
+    VIX_CUDA(cudaMemsetAsync(flag.ptr, 0, 8, s));
+    count_invalid_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, flag.ptr);
+    VIX_LAUNCH_CHECK();
+    unsigned long long bad = 0;
+    VIX_CUDA(cudaMemcpyAsync(&bad, flag.ptr, 8, cudaMemcpyDeviceToHost, s));
+    VIX_CUDA(cudaStreamSynchronize(s));
+    VIX_REQUIRE(bad == 0, VIX_ERR_INVALID_PARAM,
+                "ids must lie in [0, 2^32 - 1) (the reference's TopK id type is Int32, TopK.swift:59); %llu of %lld device-resident "
+                "ids do not", bad, (long long)n);
+    return VIX_OK;
+}
+
 static int check_ids_host(const int64_t* ids, int64_t n) {
     for (int64_t i = 0; i < n; ++i)
         VIX_REQUIRE(ids[i] >= 0 && ids[i] < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM,
@@ -571,7 +668,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
         VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "index_add: coarse quantiser not trained / set");
         VIX_REQUIRE(h->has_pq, VIX_ERR_NOT_TRAINED, "index_add: PQ codebooks not trained / set");
     }
-    if (ids && !is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    if (ids) VIX_TRY(is_device_ptr(ids) ? check_ids_device(ids, n) : check_ids_host(ids, n));
     if (!ids) VIX_REQUIRE(h->n + n < 0xFFFFFFFFLL, VIX_ERR_INVALID_PARAM, "automatic ids exceed 2^32 - 1");
 
     const int64_t n0 = h->n;
@@ -604,6 +701,12 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
             // dot product => first-min of the CentroidBatchScore row (IVFIndex.swift:376-435)
             VIX_TRY(assign_lists_device(h, xc, cn, ac));
             if (h->p.kind == VIX_INDEX_IVF_PQ) {
+                // a row whose scores are all NaN has no list (-1): the residual encoder must not read coarse[-1]
+                unsigned long long invalid = 0;
+                VIX_TRY(count_invalid_assign(ac, cn, h->kc, &invalid));
+                if (invalid) { h->ids.size = (size_t)n0; h->assign.size = (size_t)n0; h->codes.size = (size_t)n0 * h->p.m; }
+                VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM,
+                            "index_add: %llu rows have no nearest list (NaN components?); nothing was added", invalid);
                 // pq_encode_residual_u8_f32 with default opts => C ..._with_csq (PQEncode.swift:247-286)
                 VIX_TRY(pq_encode_device(xc, cn, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr,
                                          ac, h->codes.ptr + (size_t)(n0 + b) * h->p.m, 1, PQ_LAYOUT_AOS, 64, 8, 0));
@@ -686,7 +789,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
             ScanArgs a{};
             a.queries = dq.dev; a.nq = nq; a.d = d; a.m = h->p.m; a.ks = h->p.ks; a.dsub = d / h->p.m;
-            a.probes = pp; a.nprobe = nprobe; a.coarse = h->coarse.ptr; a.codebooks = h->codebooks.ptr;
+            a.probes = pp; a.nprobe = nprobe; a.coarse = h->coarse.ptr; a.kc = h->kc; a.codebooks = h->codebooks.ptr;
             a.list_off = h->list_off.ptr; a.list_len = h->list_len.ptr;
             a.slot_codes = h->slot_codes.ptr; a.slot_tx = h->slot_tx.ptr; a.slot_ids = h->slot_ids.ptr;
             a.metric = h->p.metric; a.k = k; a.out_dist = dd.dev; a.out_ids = di.dev;
@@ -694,8 +797,11 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             a.phase_cycles = stats ? scanned.ptr + 1 : nullptr;
             a.codebooks_t = h->codebooks_t.ptr;
             if (filter) { a.filter = filter->words; a.filter_cap = filter->cap; a.filter_deny = filter->deny; }
-            VIX_TRY(h->work_counter.resize(2, false));
-            a.work_counter = h->work_counter.ptr;
+            // the work queue head belongs to THIS call (stream-ordered scratch): two threads searching the same handle on
+            // different streams in asynchronous mode do not share it
+            Scratch<int> work_counter;
+            VIX_TRY(work_counter.alloc(2));
+            a.work_counter = work_counter.ptr;
             Scratch<int32_t> order;
             if (scan_layout(a.m).fast && nq > 2 * num_sms()) {
                 VIX_TRY(query_order(pp, nq, nprobe, h->list_len.ptr, h->kc, order));
@@ -709,7 +815,7 @@ static int index_search_locked(vix_index* h, const float* queries, int64_t nq, i
             int64_t grid = (int64_t)num_sms() * 4;
             if (grid > nq) grid = nq;
             ivfflat_scan_kernel<<<(unsigned)grid, 256, smem, s>>>(dq.dev, nq, d, pp, nprobe, h->list_off.ptr,
-                                                                 h->list_len.ptr, h->slot_vecs.ptr, h->slot_ids.ptr,
+                                                                 h->list_len.ptr, h->kc, h->slot_vecs.ptr, h->slot_ids.ptr,
                                                                  h->p.metric, k, P, filter ? filter->words : nullptr,
                                                                  filter ? filter->cap : 0, filter ? filter->deny : 0, dd.dev, di.dev);
             VIX_LAUNCH_CHECK();
@@ -941,7 +1047,7 @@ int vix_index_import_lists(vix_index_t* h, const int64_t* list_offsets, const ui
     VIX_REQUIRE(list_offsets[0] == 0 && n >= 0 && n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "vix_index_import_lists: bad offsets");
     for (int l = 0; l < kc; ++l)
         VIX_REQUIRE(list_offsets[l + 1] >= list_offsets[l], VIX_ERR_INVALID_PARAM, "vix_index_import_lists: offsets not monotone");
-    if (!is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    VIX_TRY(is_device_ptr(ids) ? check_ids_device(ids, n) : check_ids_host(ids, n));
     VIX_TRY(h->codes.assign_from(codes, (size_t)n * h->p.m));
     VIX_TRY(h->ids.assign_from(ids, (size_t)n));
     VIX_TRY(h->assign.resize((size_t)n, false));
@@ -1316,6 +1422,11 @@ int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_
     VIX_TRY(da.stage(assign_out, (size_t)n));
     VIX_TRY(dc.stage(pq ? codes_out : nullptr, pq ? (size_t)n * h->p.m : 0));
     VIX_TRY(assign_lists_device(h, dx.dev, n, da.dev));
+    if (pq) {
+        unsigned long long invalid = 0;                 // rows without a list: the residual encoder would read coarse[-1]
+        VIX_TRY(count_invalid_assign(da.dev, n, h->kc, &invalid));
+        VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM, "vix_index_encode: %llu rows have no nearest list (NaN components?)", invalid);
+    }
     if (pq)
         VIX_TRY(pq_encode_device(dx.dev, n, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, da.dev, dc.dev, 1,
                                  PQ_LAYOUT_AOS, 64, 8, 0));
@@ -1332,8 +1443,16 @@ int vix_index_add_encoded(vix_index_t* h, const int32_t* assign, const uint8_t* 
                 "vix_index_add_encoded: needs a trained IVF-PQ index");
     if (n <= 0) return VIX_OK;
     VIX_REQUIRE(h->n + n < 0x7FFFFFFFLL, VIX_ERR_INVALID_PARAM, "index shard limited to 2^31 - 1 rows");
-    if (!is_device_ptr(ids)) VIX_TRY(check_ids_host(ids, n));
+    VIX_TRY(is_device_ptr(ids) ? check_ids_device(ids, n) : check_ids_host(ids, n));
     cudaStream_t s = ctx().stream;
+    {   // every row must name one of this index's lists: the scan layout is built from these ids
+        In<int32_t> da;
+        VIX_TRY(da.stage(assign, (size_t)n));
+        unsigned long long invalid = 0;
+        VIX_TRY(count_invalid_assign(da.dev, n, h->kc, &invalid));
+        VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM, "vix_index_add_encoded: %llu of %lld list assignments lie outside [0, %d)",
+                    invalid, (long long)n, h->kc);
+    }
     const int64_t n0 = h->n;
     VIX_TRY(h->ids.resize((size_t)(n0 + n)));
     VIX_TRY(h->assign.resize((size_t)(n0 + n)));

@@ -122,14 +122,14 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int o) {
 // next query while the others scan, which stops being free once d x nprobe outgrows a query's scan time.
 __global__ void __launch_bounds__(256)
 probe_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
-                  const int32_t* __restrict__ list_len, int64_t npairs, int nprobe, int d, int order_max,
+                  const int32_t* __restrict__ list_len, int kc, int64_t npairs, int nprobe, int d, int order_max,
                   float* __restrict__ bias) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= npairs) return;
     const int l = probes[w];
     float part = 0.0f;
-    if (l >= 0 && __ldg(list_len + l) > 0) {
+    if ((unsigned)l < (unsigned)kc && __ldg(list_len + l) > 0) {
         const float* q = queries + (w / nprobe) * (int64_t)d;
         const float* c = coarse + (int64_t)l * d;
         if (order_max) for (int e = lane; e < d; e += 32) part = fmaf(__ldg(q + e), __ldg(c + e), part);
@@ -190,28 +190,45 @@ __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int
             }
             const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
             const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
-            // the owner retires the key it contributed
+            // ONE owner retires ONE copy of the key: the same (score, id) pair may have been stored more than once
+            // (an id added twice), and every copy is a result of its own
+            int mine = -1;
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (kh[r] == gh && kl[r] == gl) { kh[r] = 0xFFFFFFFFu; kl[r] = 0xFFFFFFFFu; }
+            for (int r = R - 1; r >= 0; --r)
+                if (kh[r] == gh && kl[r] == gl) mine = r;
+            const unsigned owners = __ballot_sync(0xFFFFFFFFu, mine >= 0 && (gh & gl) != 0xFFFFFFFFu);
+            if (owners && lane == __ffs(owners) - 1) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r == mine) { kh[r] = 0xFFFFFFFFu; kl[r] = 0xFFFFFFFFu; }
+            }
             if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
         }
         return;
     }
+    // more candidates than the registers hold (rare): "the smallest key greater than the last one taken" walks the
+    // keys in order; a key stored several times (an id added twice) is taken once per copy
     uint32_t last_hi = 0, last_lo = 0;
-    bool first = true;
+    int taken = 0;                                          // copies of `last` written so far (0: nothing taken yet)
     for (int i = 0; i < k; ++i) {
         uint32_t mh = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
+        int same = 0;
         for (int t = lane; t < n; t += 32) {
             const u64 key = s_cand[t];
             const uint32_t kh = (uint32_t)(key >> 32), kl = (uint32_t)key;
-            const bool after = first || kh > last_hi || (kh == last_hi && kl > last_lo);
+            same += (taken > 0 && kh == last_hi && kl == last_lo) ? 1 : 0;
+            const bool after = taken == 0 || kh > last_hi || (kh == last_hi && kl > last_lo);
             if (after && (kh < mh || (kh == mh && kl < ml))) { mh = kh; ml = kl; }
         }
-        const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
-        const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
+        same = __reduce_add_sync(0xFFFFFFFFu, same);
+        uint32_t gh, gl;
+        if (same > taken) { gh = last_hi; gl = last_lo; taken += 1; }
+        else {
+            gh = __reduce_min_sync(0xFFFFFFFFu, mh);
+            gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
+            last_hi = gh; last_lo = gl; taken = 1;
+        }
         if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
-        last_hi = gh; last_lo = gl; first = false;
     }
 }
 
@@ -224,7 +241,7 @@ __device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int
 __device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d, const float* __restrict__ coarse,
                                                int order_max, const int32_t* __restrict__ qprobes,
                                                const float* __restrict__ qbias, int nprobe,
-                                               const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len,
+                                               const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len, int kc,
                                                int* s_start, int* s_len, int* s_pref, float* s_bias, int* s_np,
                                                float* s_q) {
     const int lane = threadIdx.x & 31;
@@ -241,7 +258,7 @@ __device__ VIX_SCAN_FN void build_probe_table(const float* __restrict__ q, int d
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         offv[it] = 0; lenv[it] = 0;
-        if (lv[it] >= 0) { offv[it] = __ldg(list_off + lv[it]); lenv[it] = __ldg(list_len + lv[it]); }
+        if ((unsigned)lv[it] < (unsigned)kc) { offv[it] = __ldg(list_off + lv[it]); lenv[it] = __ldg(list_len + lv[it]); }
     }
     int carry = 0, np = 0;
     int* s_list = reinterpret_cast<int*>(s_bias);          // list ids first, overwritten by the bias below
@@ -547,7 +564,7 @@ ivfpq_scan_kernel(ScanArgs a) {
         const int64_t qn = a.order ? a.order[item] : item;
         int* pt = s_pt + b * pt_words;
         build_probe_table(a.queries + qn * (int64_t)a.d, a.d, a.coarse, order_max, a.probes + qn * (int64_t)a.nprobe,
-                          a.bias ? a.bias + qn * (int64_t)a.nprobe : nullptr, a.nprobe, a.list_off, a.list_len,
+                          a.bias ? a.bias + qn * (int64_t)a.nprobe : nullptr, a.nprobe, a.list_off, a.list_len, a.kc,
                           pt + a.nprobe, pt + 2 * a.nprobe, pt + 3 * a.nprobe, reinterpret_cast<float*>(pt), s_np + b,
                           s_qv + b * a.d);
     };
@@ -838,8 +855,9 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
         for (int e = tid; e < a.d; e += kScanThreads) s_q[e] = a.queries[qi * (int64_t)a.d + e];
         if (tid < a.nprobe) {
             const int l = a.probes[qi * (int64_t)a.nprobe + tid];
-            s_start[tid] = l >= 0 ? (int)(a.list_off[l] >> 5) : 0;
-            s_len[tid] = l >= 0 ? a.list_len[l] : 0;
+            const bool ok = (unsigned)l < (unsigned)a.kc;
+            s_start[tid] = ok ? (int)(a.list_off[l] >> 5) : 0;
+            s_len[tid] = ok ? a.list_len[l] : 0;
         }
         __syncthreads();
         if (tid == 0) {
@@ -850,7 +868,7 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
         for (int p = warp; p < a.nprobe; p += kScanWarps) {
             const int l = a.probes[qi * (int64_t)a.nprobe + p];
             float part = 0.0f;
-            if (l >= 0) {
+            if ((unsigned)l < (unsigned)a.kc) {
                 const float* c = a.coarse + (int64_t)l * a.d;
                 if (order_max) for (int e = lane; e < a.d; e += 32) part = fmaf(s_q[e], c[e], part);
                 else for (int e = lane; e < a.d; e += 32) { float df = s_q[e] - c[e]; part = fmaf(df, df, part); }
@@ -1049,7 +1067,7 @@ int launch_ivfpq_scan(ScanArgs& a) {
         const int64_t npairs = a.nq * (int64_t)a.nprobe;
         VIX_TRY(bias.alloc((size_t)npairs));
         probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
-            a.queries, a.probes, a.coarse, a.list_len, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
+            a.queries, a.probes, a.coarse, a.list_len, a.kc, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
         VIX_LAUNCH_CHECK();
         a.bias = bias.ptr;
     }

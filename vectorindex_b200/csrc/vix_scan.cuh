@@ -13,7 +13,7 @@ struct ScanArgs {
     int* work_counter;                            // device int[2], zeroed by the launcher: [0] queue head, [1] status
     int* status;                                  // set by the launcher (= work_counter + 1)
     int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
-    const float* coarse;                          // [kc x d]
+    const float* coarse; int kc;                  // [kc x d]; probe ids outside [0, kc) are treated like the -1 padding
     const float* bias;                            // optional [nq x nprobe]: the per-probe term, precomputed batch-wide (large d)
     const float* lut_image;                       // optional [nq][tables x 64 KB]: the look-up tables of every query, already in
                                                   // the scan's shared-memory layout (built batch-wide when the codebooks are large)

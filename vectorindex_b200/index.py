@@ -506,12 +506,24 @@ class ShardedIVFPQIndex:
         if st != "unset":
             return st
         st = None
-        if self.world > 1 and self._nccl() and not os.environ.get("VIX_NO_P2P") and hasattr(self.local, "_h"):
-            try:
-                import torch.distributed._symmetric_memory as symm
+        if self.world > 1 and self._nccl() and hasattr(self.local, "_h"):
+            # decided ONCE and by ALL ranks together (all-reduce MIN of a local capability flag): a rank that cannot map
+            # peer memory must not leave the others waiting in a barrier; a failure inside a step is an error, not a
+            # reason to change the exchange on one rank only
+            import torch
+            import torch.distributed as dist
+            symm, ok = None, 0
+            if not os.environ.get("VIX_NO_P2P"):
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    t = symm.empty((16,), dtype=torch.int32, device=self._comm_device())
+                    ok = 1 if t is not None else 0
+                except Exception:  # noqa: BLE001
+                    symm, ok = None, 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self._comm_device())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
                 st = {"symm": symm, "bufs": {}}
-            except Exception:  # noqa: BLE001
-                st = None
         self._p2p_state = st
         return st
 
@@ -642,6 +654,8 @@ class ShardedIVFPQIndex:
         nq = int(queries.shape[0])
         if self.world == 1:
             return self.local.probe_range(queries, nprobe, 0, self.kc)[0]
+        if nq == 0:                                                            # nothing to exchange (every rank sees nq)
+            return torch.empty((0, nprobe), dtype=torch.int32, device=self._comm_device())
         lo, cnt, per = self.query_block(nq)
         if cnt > 0:
             ids = self._to_comm(self.local.probe_range(queries[lo:lo + cnt], nprobe, 0, self.kc)[0]).to(torch.int32)
@@ -658,6 +672,13 @@ class ShardedIVFPQIndex:
         staged to the device once and only the merged result returns to the host."""
         import torch
         was_numpy = not _lib._is_torch(queries)
+        if int(queries.shape[0]) == 0 or int(k) <= 0:                          # IVFIndex.swift:866: nothing to do
+            kk = max(int(k), 0)
+            if was_numpy:
+                return np.empty((0 if int(queries.shape[0]) == 0 else int(queries.shape[0]), kk), np.float32), \
+                    np.empty((int(queries.shape[0]), kk), np.int64)
+            return (torch.empty((int(queries.shape[0]), kk), dtype=torch.float32, device=queries.device),
+                    torch.empty((int(queries.shape[0]), kk), dtype=torch.int64, device=queries.device))
         if self.world > 1 and was_numpy and self._nccl():
             queries = self._to_comm(np.ascontiguousarray(queries, dtype=np.float32))
         nprobe = nprobe if nprobe > 0 else self.nprobe
@@ -680,13 +701,7 @@ class ShardedIVFPQIndex:
             try:
                 md = None
                 if self._p2p() is not None:
-                    try:
-                        md, mi = self._search_over_peer_memory(queries, k, nprobe, mark)
-                    except Exception as e:  # noqa: BLE001  (no symmetric memory on this system: NCCL carries the exchanges)
-                        import warnings
-                        warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-gathers")
-                        self._p2p_state = None
-                        md = None
+                    md, mi = self._search_over_peer_memory(queries, k, nprobe, mark)
                 if md is None:
                     probes = self.global_probes(queries, nprobe)
                     mark("probe_select+gather")
