@@ -455,12 +455,14 @@ def test_probe_selection_pins_and_padding(oracle, vk):
 
 # ------------------------------------------------------------------------------------------------ a16 seam
 def test_accel_rank_candidates_reference_fixture(vk):
-    """AccelerableIndexTests.swift:14-66: three stored vectors, query [2, 3, 4], euclidean: the two nearest candidates are
-    rows 0 and 1 at sqrt(3) = 1.732 and sqrt(27) = 5.196 (the distances the reference test feeds back as AcceleratedResults)."""
+    """AccelerableIndexTests.swift:14-66: the reference test's three stored vectors and query [2, 3, 4], euclidean, k = 2:
+    getCandidates hands over all three rows; the accelerated side answers with indices INTO that block, best first, and
+    API distances (the shape of AcceleratedResults; the test itself feeds example numbers to finalizeResults).  Rows 0 and 1
+    are the nearest, at sqrt(3) and sqrt(12)."""
     cand = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.float32)
     idx, dist = vk.accel_rank_candidates(np.array([[2, 3, 4]], dtype=np.float32), cand, 2)
     assert idx.tolist() == [[0, 1]]
-    np.testing.assert_allclose(dist[0], [1.732, 5.196], atol=1e-3)
+    np.testing.assert_allclose(dist[0], [3 ** 0.5, 12 ** 0.5], rtol=1e-6)
     assert dist.dtype == np.float32 and idx.dtype == np.int32
 
 
@@ -909,9 +911,18 @@ def test_invalid_list_ids_device_ids_and_duplicates(oracle):
     assert idx.count == 0
     nanrow = xb[:4].copy()
     nanrow[2] = np.nan
+    # euclidean: no distance of a NaN row is "< best", so _vi_km12_assignAOS leaves it in list 0
+    # (KMeansMiniBatchKernel.swift:341-359); dot product: the row has no minimum and no list -- the add is refused
+    assert idx.encode(nanrow)[0].tolist() == oracle.assign(nanrow, coarse)[0].tolist() and idx.encode(nanrow)[0][2] == 0
+    ipx = IVFPQIndex(d, "dotProduct", nlist=kc, nprobe=3, m=m)
+    ipx.set_coarse(coarse)
+    ipx.set_codebooks(cb, norms)
+    assert oracle.assign_metric(nanrow, coarse, 1)[2] == -1
     with pytest.raises(VectorIndexError):
-        idx.batch_insert(nanrow)
-    assert idx.count == 0
+        ipx.batch_insert(nanrow)
+    with pytest.raises(VectorIndexError):
+        ipx.encode(nanrow)
+    assert ipx.count == 0 and idx.count == 0
     idx.add_encoded(torch.from_numpy(asg).cuda(), torch.from_numpy(codes).cuda(),
                     torch.from_numpy(ids).to(torch.int32).cuda())          # a tensor of another width is cast, not reinterpreted
     # probes: ids >= kc / < -1 behave like the -1 padding
@@ -928,7 +939,8 @@ def test_invalid_list_ids_device_ids_and_duplicates(oracle):
     d3, i3 = idx.batch_search(q[:1], 5)
     assert i3[0, 0] == row and i3[0, 1] == row and bits(d3)[0, 0] == bits(d3)[0, 1]
     assert np.array_equal(i3[0, 2:], gi[0, 1:4])
-    # IVF-Flat, cosine: an all-NaN row gets no list and is never returned; the other rows are unaffected
+    # IVF-Flat, cosine: the guarded CentroidBatchScore row of a NaN vector is all 1 (CentroidBatchScore.swift:70-84), so
+    # it lands in list 0 as in the reference; its candidate distance is NaN and it is never returned
     flat = IVFIndex(d, "cosine", nlist=kc, nprobe=kc)
     flat.set_coarse(coarse)
     xs = xb[:300].copy()
@@ -936,7 +948,8 @@ def test_invalid_list_ids_device_ids_and_duplicates(oracle):
     flat.batch_insert(xs)
     fd, fi = flat.batch_search(q, 10)
     assert 5 not in fi and (fi >= 0).all() and flat.count == 300
-    assert flat.list_sizes().sum() == 299
+    want = oracle.assign_metric(xs, coarse, 2, oracle.centroid_norms(coarse))
+    assert want[5] == 0 and flat.list_sizes().tolist() == np.bincount(want[want >= 0], minlength=kc).tolist()
 
 
 @pytest.mark.parametrize("metric", [0, 1])

@@ -40,6 +40,7 @@ struct PairArgs {
     float* out; int64_t ldo;
     // ARGMIN
     int32_t* arg_out; float* min_out;
+    int first_min;                 // 1: plain first minimum, -1 when the row has none (IVFIndex.swift:376-435); 0: km12
     // TOPK
     int k, P, order_max, nsplit; int64_t btiles_per_split;
     u64* keys_out;                 // [nA x nsplit x k]
@@ -175,7 +176,10 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs p) {
             }
             // reference semantics with NaN (KMeansMiniBatchKernel.swift:341-359): the running best
             // starts at centroid 0 and a NaN there is never replaced
-            if (rn[r] || bi == INT64_MAX) { bi = 0; if (rn[r]) bd = __int_as_float(0x7fc00000); }
+            // the first minimum of a CentroidBatchScore row instead (IVFIndex.swift:376-435: best starts at -1,
+            // strict <): a row without any comparable score -- all NaN / +inf -- has no list
+            if (p.first_min) { if (bi == INT64_MAX) bi = -1; }
+            else if (rn[r] || bi == INT64_MAX) { bi = 0; if (rn[r]) bd = __int_as_float(0x7fc00000); }
             if (p.arg_out) p.arg_out[a] = (int32_t)bi;
             if (p.min_out) p.min_out[a] = bd;
         }
@@ -610,7 +614,7 @@ int ivf_assign_metric_device(const float* x, int64_t n, int d, const float* c, i
     PairArgs p{};
     p.A = x; p.nA = n; p.B = c; p.nB = kc; p.d = d;
     p.transform = (metric == VIX_METRIC_L2) ? TR_CBS_L2 : TR_NEG;
-    p.bnorm = cnorm; p.arg_out = assign;
+    p.bnorm = cnorm; p.arg_out = assign; p.first_min = 1;
     return launch_pair<SpecSeqDot, EPI_ARGMIN>(p, 0);
 }
 
