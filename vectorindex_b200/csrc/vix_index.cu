@@ -242,10 +242,11 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
     const int row = slot_row[g];
     const int dsub = d / m;
     // rotated (fast) layout is also chunk-blocked: byte b of slot g lives at chunk * 32 m + (b / 16) * 512 + (g % 32) * 16 + b % 16
-    uint8_t* dst = rotated ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) * 16 : slot_codes + g * (int64_t)m;
-    const int cstride = rotated ? 512 - 16 : 0;        // extra offset per 16-byte piece
+    constexpr int PS = 16;                             // bytes of a slot stored contiguously: one 128-bit load per group
+    uint8_t* dst = rotated ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) * PS : slot_codes + g * (int64_t)m;
+    const int cstride = rotated ? 32 * PS - PS : 0;    // extra offset per piece
     if (row < 0) {
-        for (int b = lane; b < m; b += 32) dst[b + (b >> 4) * cstride] = 0;
+        for (int b = lane; b < m; b += 32) dst[b + (b / PS) * cstride] = 0;
         if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
         return;
     }
@@ -254,7 +255,7 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
     double acc = 0.0;
     for (int b = lane; b < m; b += 32) {
         const int j = rotated ? ((b & ~15) | ((b ^ (int)(g & 15)) & 15)) : b;
-        dst[b + (b >> 4) * cstride] = src[j];
+        dst[b + (b / PS) * cstride] = src[j];
     }
     if (metric == VIX_METRIC_L2) {
         for (int j = lane; j < m; j += 32) {
