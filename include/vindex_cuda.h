@@ -361,6 +361,37 @@ int vix_peer_scatter_block(const void* src, size_t bytes, void* const* peer_bufs
 int vix_index_search_with_probes_keys_peers(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                             int nprobe, void* const* peer_bufs_dev, int world, int rank);
 
+/* ---- the whole sharded step behind the C ABI: one process per GPU, one communicator per process ------------------
+ * north_star: "the database shards by inverted list across the GPUs of one box; queries are broadcast, each GPU produces
+ * a local top-k, and the per-GPU results are merged" -- here without any host-language glue: a non-Python host (the Swift
+ * shim of INTEGRATION.md) calls these four entry points and nothing else.  NCCL is bound at run time (libnccl.so.2,
+ * VIX_NCCL_PATH overrides); the exchanges of a search run over peer-mapped memory (cudaIpc: every rank stores its block
+ * into all peers over NVLink + one barrier kernel) and fall back to ncclAllGather when the ranks cannot map each other
+ * (decided once, collectively; VIX_NO_P2P=1 forces the fallback).
+ *   vix_comm_unique_id   rank 0: the NCCL id (128 bytes) the host hands to every rank by its own means
+ *   vix_comm_create      collective; binds the calling thread's CUDA device
+ *   vix_sharded_add      collective; x / ids: the rows THIS rank contributes (any rows; n may be 0).  Rows are assigned +
+ *                        encoded here and appended on the rank owning their list: list l belongs to rank r iff
+ *                        list_bounds[r] <= l < list_bounds[r + 1] (host array [world + 1], NULL = equal-count blocks)
+ *   vix_sharded_search   collective; every rank passes the SAME batch (host or device pointer; from a host pointer only
+ *                        the rank's own 1/world block crosses PCIe) and receives the merged [nq x k] result.  Results
+ *                        equal vix_index_search on one GPU holding all lists (same probe lists by construction; same
+ *                        (distance, id) order: mergeTopK, TopKMerge.swift:11-61).  Asynchronous mode: no host
+ *                        synchronisation at all when the outputs are device pointers. */
+typedef struct vix_comm vix_comm_t;
+int vix_comm_unique_id(void* id_out, size_t capacity /* >= 128 */);
+int vix_comm_create(const void* id, size_t id_bytes, int rank, int world, vix_comm_t** out);
+int vix_comm_destroy(vix_comm_t* c);
+int vix_comm_rank(const vix_comm_t* c);
+int vix_comm_world(const vix_comm_t* c);
+int vix_comm_uses_peer_memory(const vix_comm_t* c);        /* 1 peer memory, 0 NCCL all-gathers, -1 not decided yet */
+/* rows [first, first + count) of a batch of nq queries are the block whose probe lists `rank` computes */
+int vix_sharded_query_block(int64_t nq, int rank, int world, int64_t* first, int64_t* count);
+int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds /* nullable */, const float* x,
+                    const int64_t* ids, int64_t n);
+int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int64_t nq, int k, int nprobe,
+                       float* out_dist, int64_t* out_ids);
+
 /* same, with the stage timings / scan statistics of vix_index_search_ex (synchronises) */
 int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                     int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats /* nullable */);

@@ -1,0 +1,83 @@
+"""One rank of the multi-GPU parity check (launched by tests/test_sharded_gpu.py under torch.distributed.run, one process
+per GPU): the native sharded step (vix_sharded_add / vix_sharded_search behind ShardedIVFPQIndex) against a single-GPU
+index holding all rows, against the oracle, and against the Python exchange path (VIX_PY_SHARDED=1)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle
+    from vectorindex_b200 import _lib
+    from vectorindex_b200.index import IVFPQIndex, ShardedIVFPQIndex, balanced_list_bounds
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    _lib.check(_lib.lib().vix_set_device(int(os.environ["LOCAL_RANK"])))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    for metric in ("euclidean", "dotProduct"):
+        n, d, m, kc, nq, k, nprobe = 20000, 96, 48, 64, 333, 10, 9
+        rng = np.random.default_rng(7)
+        centres = rng.standard_normal((kc, d)).astype(np.float32)
+        xb = (centres[rng.integers(0, kc, n)] + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
+        q = (centres[rng.integers(0, kc, nq)] + 0.3 * rng.standard_normal((nq, d))).astype(np.float32)
+        cb = (0.3 * rng.standard_normal((m, 256, d // m))).astype(np.float32)
+        ids = (np.arange(n, dtype=np.int64) * 3 + 11)
+        full = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+        full.set_coarse(centres)
+        full.set_codebooks(cb)
+        full.batch_insert(xb, ids)
+        fd, fi = full.batch_search(q, k)
+        local = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+        local.set_coarse(centres)
+        local.set_codebooks(cb)
+        sh = ShardedIVFPQIndex.wrap(local, kc, nprobe)
+        counts = np.bincount(full.export_lists()[3], minlength=kc)
+        sh.set_list_bounds(balanced_list_bounds(counts, world))
+        mine = np.arange(rank, n, world)                                   # ragged, interleaved contributions
+        sh.add(torch.from_numpy(xb[mine]).cuda(), torch.from_numpy(ids[mine]).cuda())
+        sizes = torch.tensor([local.count], device="cuda")
+        dist.all_reduce(sizes)
+        assert int(sizes.item()) == n, (int(sizes.item()), n)
+        # host queries in, host results out
+        sd, si = sh.batch_search(q, k)
+        assert np.array_equal(si, fi) and np.array_equal(sd.view(np.uint32), fd.view(np.uint32)), f"{metric}: sharded != single GPU"
+        # device queries, asynchronous mode
+        _lib.lib().vix_set_async(1)
+        qd = torch.from_numpy(q).cuda()
+        dd, di = sh.batch_search(qd, k)
+        dd2, di2 = sh.batch_search(qd[:50].contiguous(), 3, nprobe=4)     # another shape through the same regions
+        torch.cuda.synchronize()
+        _lib.lib().vix_set_async(0)
+        assert np.array_equal(di.cpu().numpy(), fi) and np.array_equal(dd.cpu().numpy().view(np.uint32), fd.view(np.uint32))
+        f2d, f2i = full.batch_search(q[:50], 3, nprobe=4)
+        assert np.array_equal(di2.cpu().numpy(), f2i) and np.array_equal(dd2.cpu().numpy().view(np.uint32), f2d.view(np.uint32))
+        # the oracle on the same lists (stage-wise parity of the merged result)
+        off, codes, lids, _ = full.export_lists()
+        _, norms = full.get_codebooks()
+        od, oi, _ = oracle.ivfpq_search(q, centres, cb, norms, off, codes, lids, m, 256, nprobe, k, 1 if metric == "dotProduct" else 0)
+        np.testing.assert_allclose(sd, od, rtol=1e-5, atol=1e-6)
+        same = np.mean([len(set(si[r]) & set(oi[r])) / k for r in range(nq)])
+        assert same > 0.999, same
+        peer = sh.comm.uses_peer_memory
+        want_peer = 0 if os.environ.get("VIX_NO_P2P") else 1
+        assert peer == want_peer, f"peer memory state {peer}, expected {want_peer}"
+        # empty batch on every rank
+        ed, ei = sh.batch_search(np.zeros((0, d), np.float32), k)
+        assert ed.shape == (0, k)
+        if rank == 0:
+            print(f"ok {metric}: world {world}, peer memory {peer}, {n} rows, top-k overlap with the oracle {same:.4f}", flush=True)
+        sh.comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

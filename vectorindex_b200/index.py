@@ -430,6 +430,53 @@ def merge_shard_results_host(dist_all, ids_all, k):
     return out_d, out_i
 
 
+class Comm:
+    """``vix_comm_t``: the library's own communicator of one process per GPU (NCCL, bound at run time, + peer-mapped
+    exchange memory).  The 128-byte id of rank 0 reaches the other ranks by the host's own means -- here a
+    ``torch.distributed`` broadcast, in a Swift host whatever it already uses to start its workers."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes):
+        self._c = C.c_void_p(0)
+        buf = (C.c_char * len(unique_id)).from_buffer_copy(unique_id)
+        check(lib().vix_comm_create(buf, C.c_size_t(len(unique_id)), C.c_int(rank), C.c_int(world), C.byref(self._c)))
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        check(lib().vix_comm_unique_id(buf, C.c_size_t(128)))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, group=None):
+        """One communicator per process of an initialised ``torch.distributed`` NCCL group (the id travels by broadcast)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0, group=group)
+        torch.cuda.synchronize()
+        return cls(rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+    @property
+    def uses_peer_memory(self) -> int:
+        return int(lib().vix_comm_uses_peer_memory(self._c))
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c:
+            lib().vix_comm_destroy(self._c)
+            self._c = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class ShardedIVFPQIndex:
     """IVF-PQ index partitioned over the ranks of a ``torch.distributed`` group by contiguous blocks of
     inverted lists.  Every rank holds the coarse centroids and PQ codebooks and the codes of
@@ -485,6 +532,27 @@ class ShardedIVFPQIndex:
     def _nccl(self):
         import torch.distributed as dist
         return dist.get_backend(self.group) == "nccl"
+
+    def _native(self):
+        """The product path: the whole sharded step inside the library (vix_sharded_search / vix_sharded_add over a
+        ``vix_comm_t``).  The Python exchange below remains for CPU ranks (gloo tests with an oracle-backed local index)."""
+        import os
+        if self.world <= 1 or not self._nccl() or not hasattr(self.local, "_h") or os.environ.get("VIX_PY_SHARDED"):
+            return None
+        if self.__dict__.get("comm") is None:
+            self.comm = Comm.from_torch(self.group)
+        return self.comm
+
+    def _pinned(self, tag, shape, dtype):
+        import torch
+        pins = self.__dict__.setdefault("_pins", {})
+        key = (tag, dtype, tuple(shape))
+        buf = pins.get(key)
+        if buf is None:
+            if len(pins) > 8:
+                pins.clear()
+            buf = pins[key] = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return buf
 
     def _to_comm(self, a):
         """array -> tensor on the device the process group communicates over"""
@@ -611,6 +679,14 @@ class ShardedIVFPQIndex:
         """Rows handed to THIS rank (any rows; ranks normally pass disjoint slices of the database)."""
         import torch
         import torch.distributed as dist
+        comm = self._native()
+        if comm is not None:
+            x = as_input(vectors, np.float32)
+            i = as_input(ids, np.int64)
+            b = None if self.bounds is None else np.ascontiguousarray(self.bounds, dtype=np.int64)
+            check(lib().vix_sharded_add(self.local._h, comm._c, ptr(b), ptr(x, np.float32), ptr(i, np.int64),
+                                        C.c_int64(int(x.shape[0]))))
+            return
         assign, codes = self.local.encode(vectors)
         if self.world == 1:
             self.local.add_encoded(assign, codes, ids)
@@ -679,9 +755,25 @@ class ShardedIVFPQIndex:
                     np.empty((int(queries.shape[0]), kk), np.int64)
             return (torch.empty((int(queries.shape[0]), kk), dtype=torch.float32, device=queries.device),
                     torch.empty((int(queries.shape[0]), kk), dtype=torch.int64, device=queries.device))
+        nprobe = nprobe if nprobe > 0 else self.nprobe
+        comm = self._native()
+        if comm is not None:
+            # one library call: probe selection of this rank's block, both exchanges over peer memory, fused scan, merge.
+            # Host queries: the library moves only this rank's block across PCIe; results land in pinned memory.
+            q = as_input(queries, np.float32)
+            nq = int(q.shape[0])
+            if was_numpy:
+                pd, pi = self._pinned("d", (nq, k), torch.float32), self._pinned("i", (nq, k), torch.int64)
+                check(lib().vix_sharded_search(self.local._h, comm._c, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
+                                               C.c_int(nprobe), C.c_void_p(pd.data_ptr()), C.c_void_p(pi.data_ptr())))
+                return pd.numpy().copy(), pi.numpy().copy()
+            md = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            mi = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            check(lib().vix_sharded_search(self.local._h, comm._c, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
+                                           C.c_int(nprobe), ptr(md, np.float32), ptr(mi, np.int64)))
+            return md, mi
         if self.world > 1 and was_numpy and self._nccl():
             queries = self._to_comm(np.ascontiguousarray(queries, dtype=np.float32))
-        nprobe = nprobe if nprobe > 0 else self.nprobe
         marks = [] if getattr(self, "phase_times", None) is not None and self._nccl() else None
 
         def mark(name):
