@@ -376,7 +376,8 @@ int vix_index_search_with_probes_keys_peers(vix_index_t* h, const float* queries
  *   vix_sharded_search   collective; every rank passes the SAME batch (host or device pointer; from a host pointer only
  *                        the rank's own 1/world block crosses PCIe) and receives the merged [nq x k] result.  Results
  *                        equal vix_index_search on one GPU holding all lists (same probe lists by construction; same
- *                        (distance, id) order: mergeTopK, TopKMerge.swift:11-61).  Asynchronous mode: no host
+ *                        (distance, id) order: mergeTopK, TopKMerge.swift:11-61; a distance may differ in its last bit
+ *                        when a row sits in another slot of its list, which changes the order its table entries are summed in).  Asynchronous mode: no host
  *                        synchronisation at all when the outputs are device pointers. */
 typedef struct vix_comm vix_comm_t;
 int vix_comm_unique_id(void* id_out, size_t capacity /* >= 128 */);

@@ -2,9 +2,11 @@
  * NCCL id of rank 0 to the others through pipes (a Swift host would use whatever starts its workers), and every rank runs
  *   vix_comm_create -> vix_index_set_coarse / set_codebooks -> vix_sharded_add -> vix_sharded_search
  * on synthetic data.  Rank 0 also holds a single-GPU index with ALL rows and requires the sharded result to equal its
- * result bit for bit (ids and distances).  Usage: sharded_smoke [world]  (needs `world` GPUs; built and run by
+ * result: same ids, distances to fp32 rounding (the order in which a vector's table entries are summed follows its slot in
+ * its list, and a shard receives its rows in another order than the single index).  Usage: sharded_smoke [world]  (needs `world` GPUs; built and run by
  * tests/test_sharded_gpu.py).  VIX_NO_P2P=1 exercises the NCCL all-gather fallback. */
 #define _POSIX_C_SOURCE 200809L
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,7 +85,7 @@ static int run_rank(int rank, int world, const unsigned char* id) {
         int64_t* fi = malloc(sizeof(int64_t) * NQ * K);
         CHECK(vix_index_search(full, q, NQ, K, 0, fd, fi));
         for (int i = 0; i < NQ * K; ++i)
-            if (fi[i] != si[i] || memcmp(&fd[i], &sd[i], 4) != 0) {
+            if (fi[i] != si[i] || fabsf(fd[i] - sd[i]) > 2e-6f * fabsf(fd[i])) {
                 if (bad < 5) fprintf(stderr, "mismatch at %d: sharded (%lld, %g) single (%lld, %g)\n", i, (long long)si[i], sd[i], (long long)fi[i], fd[i]);
                 ++bad;
             }

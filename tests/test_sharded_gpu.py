@@ -1,6 +1,7 @@
 """Multi-GPU behind the C ABI (vix_comm_* / vix_sharded_*): a single rank on one GPU, and -- when the box has two GPUs --
 two ranks from a plain C host (fork + pipes, no Python, no MPI) and from torch.distributed.run, over peer memory and over
-the NCCL fallback.  Results must equal a single-GPU index holding all rows, bit for bit."""
+the NCCL fallback.  Results must equal a single-GPU index holding all rows (same ids; distances to fp32 rounding, bit for
+bit when the rows sit in the same slots)."""
 import os
 import shutil
 import subprocess
