@@ -393,6 +393,16 @@ int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds /*
 int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int64_t nq, int k, int nprobe,
                        float* out_dist, int64_t* out_ids);
 
+/* f-1  The IVF-PQ query with its optional last step (docs/kernel-specs/DONE_22_adc_scan.md:873-878, "7. Optional: exact
+ * rerank (kernel #40)"; IVFIndex.swift:1380-1439): ADC search for the rerank_r best candidates per query (k <= rerank_r <=
+ * VIX_MAX_K), then rerank_exact_topk over the ORIGINAL vectors with the DenseArray reader: id -> row of xb [N x d] (ids
+ * outside [0, N) are missing and skipped).  Outputs as vix_rerank_exact_topk_f32: raw exact scores (L2^2 / dot), best
+ * first by (score under the metric's ordering, smaller id), padded with +-inf / id -1.  xb may live on the device (it is
+ * staged per call otherwise). */
+int vix_index_search_rerank(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe, int rerank_r,
+                            const float* xb, int64_t N, const float* xb_sq_norms /* nullable */, float* out_scores,
+                            int64_t* out_ids);
+
 /* same, with the stage timings / scan statistics of vix_index_search_ex (synchronises) */
 int vix_index_search_with_probes_ex(vix_index_t* h, const float* queries, int64_t nq, int k, const int32_t* probes,
                                     int nprobe, float* out_dist, int64_t* out_ids, vix_search_stats* stats /* nullable */);

@@ -931,7 +931,9 @@ void vo_ivfpq_search(const float* queries, int64_t nq, int d, const float* coars
                 for (int t = 0; t < d; ++t) bias = bias + q[t] * cl[t];
             }
             float* dist = (float*)malloc(sizeof(float) * (size_t)len);
-            vo_adc_scan_u8(codes + b * (int64_t)m, len, m, ks, lut, dist, 0, bias, 0);
+            /* ks = 16: packed nibbles, m / 2 bytes per row (adc_scan_u4, ADCScan.swift:384-456) */
+            if (ks == 16) vo_adc_scan_u4(codes + b * (int64_t)(m / 2), len, m, ks, lut, dist, 0, bias, 0);
+            else vo_adc_scan_u8(codes + b * (int64_t)m, len, m, ks, lut, dist, 0, bias, 0);
             float* ts = ls + (size_t)p * k;
             int32_t* ti = li + (size_t)p * k;
             int got = vo_select_topk(dist, NULL, len, k, ord, ts, ti);

@@ -853,6 +853,94 @@ def test_flat_and_ivfflat_filtered_search(oracle, kind):
     assert np.array_equal(bits(gd), bits(od))
 
 
+@pytest.mark.parametrize("metric,d,m", [("euclidean", 64, 16), ("dotProduct", 96, 48), ("euclidean", 40, 10)])
+def test_ivfpq_index_with_u4_codes(oracle, vk, metric, d, m):
+    """ks = 16 inside the index handles (the reference's 4-bit API: cpq_encode_residual_u4_f32, pq_encode.c:692-739;
+    adc_scan_u4 with packed nibbles, ADCScan.swift:384-456): list assignment and packed codes bit-exact with the oracle's
+    restatement of the C encoder, the fused search within 1e-5 of pq_lut_residual_l2 -> adc_scan_u4 -> selectTopK ->
+    mergeTopK, lists exported / imported in the packed format, and a GPU-trained ks = 16 index answers queries."""
+    from vectorindex_b200.index import IVFPQIndex
+    n, kc, nq, k, nprobe, ks = 7000, 20, 41, 10, 5, 16
+    mi = 1 if metric == "dotProduct" else 0
+    rng = np.random.default_rng(d + m)
+    centres = 3 * rng.standard_normal((kc // 2, d))
+    x = (rng.standard_normal((n + nq, d)) + centres[rng.integers(0, kc // 2, n + nq)]).astype(np.float32)
+    xb, q = np.ascontiguousarray(x[:n]), np.ascontiguousarray(x[n:])
+    coarse = np.ascontiguousarray(xb[rng.choice(n, kc, replace=False)])
+    cb = (0.8 * rng.standard_normal((m, ks, d // m))).astype(np.float32)
+    idx = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m, ks=ks)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb)
+    ids = np.arange(n, dtype=np.int64) * 2 + 1
+    idx.batch_insert(xb, ids)
+    off, codes, lids, asg = idx.export_lists()
+    assert codes.shape == (n, m // 2)
+    oasg = oracle.assign(xb, coarse)[0] if mi == 0 else oracle.assign_metric(xb, coarse, 1)
+    assert np.array_equal(asg, oasg)
+    ocodes = oracle.pq_encode_u4(xb, cb, m, ks, coarse=coarse, assign_=oasg)
+    _, order = oracle.build_lists(oasg, kc)
+    assert np.array_equal(codes, ocodes[order]) and np.array_equal(lids, ids[order])
+    _, norms = idx.get_codebooks()
+    gd, gi = idx.batch_search(q, k)
+    od, oi, _ = oracle.ivfpq_search(q, coarse, cb, norms, off, codes, lids, m, ks, nprobe, k, mi)
+    assert_topk_close(gd, gi, od, oi, atol=1e-5)
+    # the packed lists travel: import into a fresh handle == same answers; encode() returns the packed codes
+    other = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m, ks=ks)
+    other.set_coarse(coarse)
+    other.set_codebooks(cb, norms)
+    other.import_lists(off, codes, lids)
+    d2, i2 = other.batch_search(q, k)
+    assert np.array_equal(i2, gi) and np.array_equal(bits(d2), bits(gd))
+    a3, c3 = idx.encode(xb[:100])
+    assert np.array_equal(a3, oasg[:100]) and np.array_equal(c3, ocodes[:100])
+    # trained on the GPU
+    tr = IVFPQIndex(d, metric, nlist=kc, nprobe=kc, m=m, ks=ks)
+    tr.optimize(xb)
+    tr.batch_insert(xb)
+    td, ti = tr.batch_search(xb[:20], 5)
+    assert (ti >= 0).all() and tr.get_codebooks()[0].shape == (m, ks, d // m)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "dotProduct"])
+def test_ivfpq_search_with_exact_rerank(oracle, vk, metric):
+    """Step 7 of the IVF-PQ query (DONE_22_adc_scan.md:873-878): ADC top-R, then Kernel #40 over the original vectors.
+    Equal to the composition the oracle runs -- ivfpq_search(k = R) -> rerank_exact_topk (ExactRerank.swift:698-814): ids and
+    exact score bits (the candidate SETS agree unless an ADC tie inside the 1e-5 tolerance straddles rank R; such rows are
+    compared on the candidates both sides hold).  The re-rank recovers recall the codes lost."""
+    from vectorindex_b200.index import IVFPQIndex
+    n, d, m, kc, nq, k, R, nprobe = 6000, 64, 16, 24, 60, 10, 50, 6
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=77)
+    mi = 1 if metric == "dotProduct" else 0
+    idx = IVFPQIndex(d, metric, nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse)
+    idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb)                                                    # ids = rows
+    gs, gi = idx.batch_search_rerank(q, k, xb, R)
+    off, codes, lids, _ = idx.export_lists()
+    od, oi, _ = oracle.ivfpq_search(q, coarse, cb, norms, off, codes, lids, m, 256, nprobe, R, mi)
+    ad, ai = idx.batch_search(q, R)
+    exact_d, exact_i, _ = oracle.flat_search(q, xb, k, mi)
+    hit_adc = hit_rr = 0
+    for r in range(nq):
+        cand = oi[r][oi[r] >= 0]
+        rows = xb[cand]
+        sc = oracle.ip_block(q[r], rows) if mi else oracle.l2sqr_block(q[r], rows)
+        order = np.lexsort((cand, -sc if mi else sc))[:k]
+        if set(ai[r].tolist()) == set(oi[r].tolist()):                      # same candidate set: bit-exact outcome
+            assert np.array_equal(gi[r], cand[order]), r
+            assert np.array_equal(bits(gs[r]), bits(sc[order])), r
+        else:                                                               # boundary tie of the ADC stage
+            assert len(set(gi[r].tolist()) & set(cand[order].tolist())) >= k - 1
+        hit_adc += len(set(ai[r][:k].tolist()) & set(exact_i[r].tolist()))
+        hit_rr += len(set(gi[r].tolist()) & set(exact_i[r].tolist()))
+    assert hit_rr >= hit_adc and hit_rr > 0
+    from vectorindex_b200 import VectorIndexError
+    with pytest.raises(VectorIndexError):
+        idx.batch_search_rerank(q, 10, xb, 5)                               # K <= C (ExactRerank.swift:730)
+    s2, i2 = idx.batch_search_rerank(q[:3], 4, xb[:100], 40)                # candidates beyond the reader's rows are missing
+    assert ((i2 < 100) & (i2 >= -1)).all()
+
+
 def test_ivfpq_edge_cases(oracle):
     from vectorindex_b200.index import IVFPQIndex
     from vectorindex_b200 import VectorIndexError

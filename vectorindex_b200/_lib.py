@@ -89,7 +89,7 @@ _EXPORTS = [
     "vix_index_params_default", "vix_index_create", "vix_index_destroy", "vix_index_train", "vix_index_set_coarse",
     "vix_index_set_codebooks", "vix_index_get_coarse", "vix_index_get_codebooks", "vix_index_add",
     "vix_index_import_lists", "vix_index_count", "vix_index_list_sizes", "vix_index_export_lists", "vix_index_clear",
-    "vix_index_search", "vix_index_search_ex", "vix_index_trace", "vix_index_trace_get", "vix_index_probe_range", "vix_index_search_with_probes",
+    "vix_index_search", "vix_index_search_ex", "vix_index_search_rerank", "vix_index_trace", "vix_index_trace_get", "vix_index_probe_range", "vix_index_search_with_probes",
     "vix_index_search_with_probes_ex", "vix_index_search_filtered", "vix_index_probe_range_keys", "vix_merge_probe_keys",
     "vix_index_search_with_probes_keys", "vix_merge_result_keys", "vix_peer_scatter_block",
     "vix_index_search_with_probes_keys_peers",

@@ -126,6 +126,8 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
                      const float* __restrict__ coarse, const float* __restrict__ codebooks, int d, int m, int ks,
                      int rotated, int metric, uint8_t* __restrict__ slot_codes, int64_t* __restrict__ slot_ids,
                      float* __restrict__ slot_tx) {
+    // ks = 16: packed nibbles (m / 2 bytes per row, plain AoS slots; never rotated)
+    const int cb_ = ks == 16 ? m / 2 : m;
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= nslots) return;
@@ -133,23 +135,24 @@ fill_slots_pq_kernel(const int32_t* __restrict__ slot_row, int64_t nslots, const
     const int dsub = d / m;
     // rotated (fast) layout is also chunk-blocked: byte b of slot g lives at chunk * 32 m + (b / 16) * 512 + (g % 32) * 16 + b % 16
     constexpr int PS = 16;                             // bytes of a slot stored contiguously: one 128-bit load per group
-    uint8_t* dst = rotated ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) * PS : slot_codes + g * (int64_t)m;
+    uint8_t* dst = rotated ? slot_codes + (g >> 5) * (int64_t)(32 * m) + (g & 31) * PS : slot_codes + g * (int64_t)cb_;
     const int cstride = rotated ? 32 * PS - PS : 0;    // extra offset per piece
     if (row < 0) {
-        for (int b = lane; b < m; b += 32) dst[b + (b / PS) * cstride] = 0;
+        for (int b = lane; b < cb_; b += 32) dst[b + (b / PS) * cstride] = 0;
         if (lane == 0) { slot_ids[g] = -1; slot_tx[g] = 0.0f; }
         return;
     }
-    const uint8_t* src = codes + (int64_t)row * m;
+    const uint8_t* src = codes + (int64_t)row * cb_;
     const float* c = coarse + (int64_t)assign[row] * d;
     double acc = 0.0;
-    for (int b = lane; b < m; b += 32) {
+    for (int b = lane; b < cb_; b += 32) {
         const int j = rotated ? ((b & ~15) | ((b ^ (int)(g & 15)) & 15)) : b;
         dst[b + (b / PS) * cstride] = src[j];
     }
     if (metric == VIX_METRIC_L2) {
         for (int j = lane; j < m; j += 32) {
-            const float* cw = codebooks + ((size_t)j * ks + src[j]) * dsub;
+            const int code = ks == 16 ? ((j & 1) ? (src[j >> 1] >> 4) : (src[j >> 1] & 15)) : src[j];
+            const float* cw = codebooks + ((size_t)j * ks + code) * dsub;
             const float* cj = c + (size_t)j * dsub;
             for (int e = 0; e < dsub; ++e) {
                 double r = (double)cw[e];
@@ -231,8 +234,8 @@ int build_lists(vix_index* h) {
     }
     if (h->p.kind == VIX_INDEX_IVF_PQ) {
         const int m = h->p.m;
-        const int rotated = scan_layout(m).fast ? 1 : 0;
-        VIX_TRY(h->slot_codes.resize((size_t)nslots * m + 16, false));
+        const int rotated = (scan_layout(m).fast && h->p.ks == 256) ? 1 : 0;
+        VIX_TRY(h->slot_codes.resize((size_t)nslots * h->code_bytes() + 16, false));
         VIX_TRY(h->slot_tx.resize((size_t)nslots, false));
         if (nslots > 0) {
             int64_t threads = nslots * 32;
@@ -548,6 +551,17 @@ static int assign_stored_rows(vix_index* h) {
     return VIX_OK;
 }
 
+// residual PQ codes of rows whose lists are known: ks = 256 => pq_encode_residual_u8_f32 with default opts => the C
+// ..._with_csq entry (PQEncode.swift:247-286); ks = 16 => cpq_encode_residual_u4_f32 (direct L2, packed nibbles,
+// pq_encode.c:692-739)
+int encode_rows_device(vix_index* h, const float* x, int64_t n, const int32_t* assign, uint8_t* codes) {
+    if (h->p.ks == 16)
+        return pq_encode_device(x, n, h->p.d, h->p.m, 16, h->codebooks.ptr, nullptr, h->coarse.ptr, assign, codes, 0, PQ_LAYOUT_AOS,
+                                64, 8, 1);
+    return pq_encode_device(x, n, h->p.d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, assign, codes, 1,
+                            PQ_LAYOUT_AOS, 64, 8, 0);
+}
+
 static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, int64_t n) {
     const int d = h->p.d;
     cudaStream_t s = ctx().stream;
@@ -571,7 +585,7 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
     }
     if (h->p.kind != VIX_INDEX_FLAT && h->has_coarse) {          // (IVF-Flat without centroids: rows wait for optimize())
         VIX_TRY(h->assign.resize((size_t)(n0 + n)));
-        if (h->p.kind == VIX_INDEX_IVF_PQ) VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->p.m));
+        if (h->p.kind == VIX_INDEX_IVF_PQ) VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->code_bytes()));
         // chunked so that host inputs of any size stage through a bounded device buffer
         const int64_t chunk = 1 << 20;
         Scratch<float> stage;
@@ -593,12 +607,11 @@ static int index_add_locked(vix_index* h, const float* x, const int64_t* ids, in
                 // a row whose scores are all NaN has no list (-1): the residual encoder must not read coarse[-1]
                 unsigned long long invalid = 0;
                 VIX_TRY(count_invalid_assign(ac, cn, h->kc, &invalid));
-                if (invalid) { h->ids.size = (size_t)n0; h->assign.size = (size_t)n0; h->codes.size = (size_t)n0 * h->p.m; }
+                if (invalid) { h->ids.size = (size_t)n0; h->assign.size = (size_t)n0; h->codes.size = (size_t)n0 * h->code_bytes(); }
                 VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM,
                             "index_add: %llu rows have no nearest list (NaN components?); nothing was added", invalid);
                 // pq_encode_residual_u8_f32 with default opts => C ..._with_csq (PQEncode.swift:247-286)
-                VIX_TRY(pq_encode_device(xc, cn, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr,
-                                         ac, h->codes.ptr + (size_t)(n0 + b) * h->p.m, 1, PQ_LAYOUT_AOS, 64, 8, 0));
+                VIX_TRY(encode_rows_device(h, xc, cn, ac, h->codes.ptr + (size_t)(n0 + b) * h->code_bytes()));
             }
         }
     }
@@ -692,7 +705,7 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             VIX_TRY(work_counter.alloc(2));
             a.work_counter = work_counter.ptr;
             Scratch<int32_t> order;
-            if (scan_layout(a.m).fast && nq > 2 * num_sms()) {
+            if (scan_layout(a.m).fast && a.ks == 256 && nq > 2 * num_sms()) {
                 VIX_TRY(query_order(pp, nq, nprobe, h->list_len.ptr, h->kc, order));
                 a.order = order.ptr;
             }
@@ -724,7 +737,7 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             stats->cycles_prologue = (int64_t)sc4[1]; stats->cycles_scan = (int64_t)sc4[2]; stats->cycles_tail = (int64_t)sc4[3];
             stats->cycles_select = (int64_t)sc4[4]; stats->cycles_probe_table = (int64_t)sc4[5]; stats->cycles_lut = (int64_t)sc4[6];
             stats->merge_candidates = (int64_t)sc4[7];
-            stats->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->p.m : d * 4);
+            stats->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->code_bytes() : d * 4);
         }
         VIX_TRY(dp.commit());
     }
@@ -795,7 +808,8 @@ int vix_index_create(const vix_index_params* p, vix_index_t** out) {
     if (p->kind != VIX_INDEX_FLAT) VIX_REQUIRE(p->nlist > 0, VIX_ERR_INVALID_K, "vix_index_create: nlist must be > 0");
     if (p->kind == VIX_INDEX_IVF_PQ) {
         VIX_REQUIRE(p->m > 0 && p->d % p->m == 0, VIX_ERR_INVALID_DIM, "vix_index_create: d %% m != 0");
-        VIX_REQUIRE(p->ks == 256, VIX_ERR_INVALID_K, "vix_index_create: ks must be 256");
+        VIX_REQUIRE(p->ks == 256 || (p->ks == 16 && p->m % 2 == 0), VIX_ERR_INVALID_K,
+                    "vix_index_create: ks must be 256 (u8 codes) or 16 with an even m (u4 codes, two per byte)");
     }
     vix_index* h = new (std::nothrow) vix_index();
     VIX_REQUIRE(h, VIX_ERR_OOM, "vix_index_create: out of host memory");
@@ -937,7 +951,7 @@ int vix_index_import_lists(vix_index_t* h, const int64_t* list_offsets, const ui
     for (int l = 0; l < kc; ++l)
         VIX_REQUIRE(list_offsets[l + 1] >= list_offsets[l], VIX_ERR_INVALID_PARAM, "vix_index_import_lists: offsets not monotone");
     VIX_TRY(is_device_ptr(ids) ? check_ids_device(ids, n) : check_ids_host(ids, n));
-    VIX_TRY(h->codes.assign_from(codes, (size_t)n * h->p.m));
+    VIX_TRY(h->codes.assign_from(codes, (size_t)n * h->code_bytes()));
     VIX_TRY(h->ids.assign_from(ids, (size_t)n));
     VIX_TRY(h->assign.resize((size_t)n, false));
     Scratch<int64_t> doff;
@@ -974,7 +988,7 @@ int vix_index_export_lists(vix_index_t* h, int64_t* list_offsets, uint8_t* codes
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->has_coarse, VIX_ERR_NOT_TRAINED, "vix_index_export_lists: not trained");
     if (h->dirty) VIX_TRY(build_lists(h));
-    const int kc = h->kc, m = h->p.m;
+    const int kc = h->kc, m = h->code_bytes();                        // bytes per stored code
     const int64_t n = h->n;
     Scratch<int64_t> off_raw;
     VIX_TRY(off_raw.alloc((size_t)kc + 1));
@@ -1313,16 +1327,14 @@ int vix_index_encode(vix_index_t* h, const float* x, int64_t n, int32_t* assign_
     Out<uint8_t> dc;
     VIX_TRY(dx.stage(x, (size_t)n * d));
     VIX_TRY(da.stage(assign_out, (size_t)n));
-    VIX_TRY(dc.stage(pq ? codes_out : nullptr, pq ? (size_t)n * h->p.m : 0));
+    VIX_TRY(dc.stage(pq ? codes_out : nullptr, pq ? (size_t)n * h->code_bytes() : 0));
     VIX_TRY(assign_lists_device(h, dx.dev, n, da.dev));
     if (pq) {
         unsigned long long invalid = 0;                 // rows without a list: the residual encoder would read coarse[-1]
         VIX_TRY(count_invalid_assign(da.dev, n, h->kc, &invalid));
         VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM, "vix_index_encode: %llu rows have no nearest list (NaN components?)", invalid);
     }
-    if (pq)
-        VIX_TRY(pq_encode_device(dx.dev, n, d, h->p.m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, da.dev, dc.dev, 1,
-                                 PQ_LAYOUT_AOS, 64, 8, 0));
+    if (pq) VIX_TRY(encode_rows_device(h, dx.dev, n, da.dev, dc.dev));
     VIX_TRY(da.commit());
     VIX_TRY(dc.commit());
     return finish(da.is_host() || dc.is_host());
@@ -1348,10 +1360,10 @@ int index_add_encoded_locked(vix_index* h, const int32_t* assign, const uint8_t*
     const int64_t n0 = h->n;
     VIX_TRY(h->ids.resize((size_t)(n0 + n)));
     VIX_TRY(h->assign.resize((size_t)(n0 + n)));
-    VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->p.m));
+    VIX_TRY(h->codes.resize((size_t)(n0 + n) * h->code_bytes()));
     VIX_CUDA(cudaMemcpyAsync(h->ids.ptr + n0, ids, (size_t)n * 8, cudaMemcpyDefault, s));
     VIX_CUDA(cudaMemcpyAsync(h->assign.ptr + n0, assign, (size_t)n * 4, cudaMemcpyDefault, s));
-    VIX_CUDA(cudaMemcpyAsync(h->codes.ptr + (size_t)n0 * h->p.m, codes, (size_t)n * h->p.m, cudaMemcpyDefault, s));
+    VIX_CUDA(cudaMemcpyAsync(h->codes.ptr + (size_t)n0 * h->code_bytes(), codes, (size_t)n * h->code_bytes(), cudaMemcpyDefault, s));
     h->n = n0 + n;
     h->dirty = true;
     return finish(true);
@@ -1395,11 +1407,41 @@ int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out) {
     unsigned long long sc = 0;
     VIX_CUDA(cudaMemcpy(&sc, h->trace_scanned.ptr + i, 8, cudaMemcpyDeviceToHost));
     out->codes_scanned = (int64_t)sc;
-    out->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->p.m : h->p.d * 4);
+    out->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->code_bytes() : h->p.d * 4);
     cudaEventElapsedTime(&out->ms_coarse, ev[0], ev[1]);
     cudaEventElapsedTime(&out->ms_scan, ev[1], ev[2]);
     cudaEventElapsedTime(&out->ms_total, ev[0], ev[2]);
     return VIX_OK;
+}
+
+// Step 7 of the IVF-PQ query (docs/kernel-specs/DONE_22_adc_scan.md:873-878; IVFIndex.swift:1380-1439 does the same for
+// its Kernel#30 lists): the ADC search keeps the R best candidates of a query, Kernel #40 re-scores them exactly against the
+// original vectors and returns the k best by (exact score, smaller id).
+int vix_index_search_rerank(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe, int rerank_r,
+                            const float* xb, int64_t N, const float* xb_sq_norms, float* out_scores, int64_t* out_ids) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_search_rerank: null handle");
+    if (k <= 0 || nq <= 0) return VIX_OK;
+    VIX_REQUIRE(queries && xb && out_scores && out_ids, VIX_ERR_NULL_PTR, "vix_index_search_rerank: null pointer");
+    VIX_REQUIRE(rerank_r >= k, VIX_ERR_INVALID_K, "vix_index_search_rerank: rerank_r (%d) must be >= k (%d) (ExactRerank.swift:730)", rerank_r, k);
+    VIX_REQUIRE(rerank_r <= VIX_MAX_K, VIX_ERR_INVALID_K, "vix_index_search_rerank: rerank_r > %d", VIX_MAX_K);
+    VIX_REQUIRE(h->p.metric != VIX_METRIC_COSINE, VIX_ERR_UNSUPPORTED, "vix_index_search_rerank: L2 / IP (Kernel #40's metrics on this path)");
+    In<float> dq;
+    VIX_TRY(dq.stage(queries, (size_t)nq * h->p.d));
+    Scratch<float> cdist;
+    Scratch<int64_t> cids;
+    VIX_TRY(cdist.alloc((size_t)nq * rerank_r));
+    VIX_TRY(cids.alloc((size_t)nq * rerank_r));
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        // candidates: approximate top-R (ids -1 pad short rows; the re-rank skips them as missing)
+        const bool was_async = ctx().async;
+        ctx().async = true;                                   // device outputs: no need to wait between the two stages
+        const int rc = index_search_locked(h, dq.dev, nq, rerank_r, nprobe, cdist.ptr, cids.ptr, nullptr, nullptr);
+        ctx().async = was_async;
+        VIX_TRY(rc);
+    }
+    return vix_rerank_exact_topk_f32(dq.dev, nq, h->p.d, h->p.metric, cids.ptr, rerank_r, k, xb, N, xb_sq_norms, out_scores, out_ids);
 }
 
 int vix_index_search(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,

@@ -86,6 +86,9 @@ struct vix_index {
     template <typename T> using DevBuf = vix::DevBuf<T>;
     vix_index_params p;
     std::mutex mu;
+    // bytes of one stored PQ code: m (ks = 256) or m / 2 (ks = 16: two codes per byte, low nibble = even sub-quantiser,
+    // pq_encode.c:594-596)
+    int code_bytes() const { return p.ks == 16 ? p.m / 2 : p.m; }
     int kc = 0;                         // trained coarse centroids (nlist clamped to the training set)
     DevBuf<float> coarse, coarse_norms; // [kc x d], Norms.l2NormSquared per row
     DevBuf<float> coarse_norm_max;      // [1] sqrt(max coarse_norms): error-bound scale of the tensor-core shortlist
@@ -137,5 +140,7 @@ int merge_shard_keys(const u64* keys_all, int world, int64_t nq, int kk, int ord
 // append already encoded rows (device or host pointers) to an IVF-PQ index whose mutex the caller holds
 int index_add_encoded_locked(vix_index* h, const int32_t* assign, const uint8_t* codes, const int64_t* ids, int64_t n);
 int build_lists(vix_index* h);
+// residual PQ codes (u8, or packed u4 when ks = 16) of rows whose list assignments are known (device pointers)
+int encode_rows_device(vix_index* h, const float* x, int64_t n, const int32_t* assign, uint8_t* codes);
 
 }  // namespace vix

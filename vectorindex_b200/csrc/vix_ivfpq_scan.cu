@@ -835,8 +835,10 @@ __global__ void __launch_bounds__(kScanThreads)
 ivfpq_scan_generic_kernel(ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.m;
-    float* s_lut = reinterpret_cast<float*>(smem_raw);          // [m][256]
-    float* s_q = s_lut + (size_t)m * 256;
+    const int ks = a.ks;                                        // 256, or 16 (packed nibbles, low nibble = even sub-quantiser)
+    const int cbytes = ks == 16 ? m / 2 : m;
+    float* s_lut = reinterpret_cast<float*>(smem_raw);          // [m][ks]
+    float* s_q = s_lut + (size_t)m * ks;
     float* s_bias = s_q + a.d;
     int* s_start = reinterpret_cast<int*>(s_bias + a.nprobe);
     int* s_len = s_start + a.nprobe;
@@ -876,8 +878,8 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
             if (lane == 0) s_bias[p] = part;
         }
-        for (int e = tid; e < m * 256; e += kScanThreads) {
-            const int j = e >> 8;
+        for (int e = tid; e < m * ks; e += kScanThreads) {
+            const int j = e / ks;
             const float* cw = a.codebooks + (size_t)e * a.dsub;
             const float* qj = s_q + j * a.dsub;
             float dot = 0.0f;
@@ -896,9 +898,17 @@ ivfpq_scan_generic_kernel(ScanArgs a) {
             const int within = (ch - s_pref[p]) * 32 + lane;
             const bool valid = within < s_len[p];
             const int64_t g = ((int64_t)s_start[p] << 5) + within;
-            const uint8_t* src = a.slot_codes + g * (int64_t)m;
+            const uint8_t* src = a.slot_codes + g * (int64_t)cbytes;
             float s0 = 0.f;
-            if (valid) for (int j = 0; j < m; ++j) s0 += s_lut[(size_t)j * 256 + src[j]];
+            if (valid) {
+                if (ks == 16) {
+                    for (int j = 0; j < m; j += 2) {
+                        const int byte = src[j >> 1];
+                        s0 += s_lut[(size_t)j * 16 + (byte & 15)];
+                        s0 += s_lut[(size_t)(j + 1) * 16 + (byte >> 4)];
+                    }
+                } else for (int j = 0; j < m; ++j) s0 += s_lut[(size_t)j * ks + src[j]];
+            }
             const float tx = valid ? a.slot_tx[g] : 0.0f;
             const float sum = (s_bias[p] + tx) + s0;
             if (valid) ++scanned_local;
@@ -961,7 +971,7 @@ ScanLayout scan_layout(int m) {
 }
 
 static size_t generic_smem_bytes(const ScanArgs& a) {
-    size_t s = (size_t)a.m * 256 * 4;
+    size_t s = (size_t)a.m * a.ks * 4;
     s += (size_t)a.d * 4 + (size_t)a.nprobe * 12 + (size_t)(a.nprobe + 1) * 4 + 16;
     s += (size_t)kScanWarps * a.Pw * 8 + (size_t)a.P2 * 8;
     return s;
@@ -1036,7 +1046,7 @@ static int launch_fast(ScanArgs& a) {
 
 int launch_ivfpq_scan(ScanArgs& a) {
     const ScanLayout L = scan_layout(a.m);
-    if (!L.fast) {
+    if (!L.fast || a.ks != 256) {
         a.Pw = next_pow2(a.k + 32);
         a.P2 = next_pow2(kScanWarps * a.k);
         const size_t smem = generic_smem_bytes(a);

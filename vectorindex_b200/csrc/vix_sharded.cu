@@ -480,7 +480,7 @@ int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds, c
     std::lock_guard<std::mutex> lc(c->mu);
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(h->p.kind == VIX_INDEX_IVF_PQ && h->has_coarse && h->has_pq, VIX_ERR_NOT_TRAINED, "vix_sharded_add: needs a trained IVF-PQ index");
-    const int world = c->world, rank = c->rank, d = h->p.d, m = h->p.m;
+    const int world = c->world, rank = c->rank, d = h->p.d, m = h->code_bytes();   // m: bytes per stored code
     cudaStream_t s = ctx().stream;
     // block boundaries of the list partition: given, or equal-count blocks
     std::vector<int64_t> bounds((size_t)world + 1);
@@ -511,8 +511,7 @@ int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds, c
         unsigned long long invalid = 0;
         VIX_TRY(count_invalid_assign(asg.ptr, n, h->kc, &invalid));
         VIX_REQUIRE(invalid == 0, VIX_ERR_INVALID_PARAM, "vix_sharded_add: %llu rows have no nearest list (NaN components?)", invalid);
-        VIX_TRY(pq_encode_device(dx.dev, n, d, m, h->p.ks, h->codebooks.ptr, h->cb_norms.ptr, h->coarse.ptr, asg.ptr, codes.ptr, 1,
-                                 PQ_LAYOUT_AOS, 64, 8, 0));
+        VIX_TRY(encode_rows_device(h, dx.dev, n, asg.ptr, codes.ptr));
         // 2. rows ordered by owning rank (stable: rows keep their order inside a block)
         VIX_TRY(owner.alloc((size_t)n));
         VIX_TRY(row.alloc((size_t)n));

@@ -238,6 +238,11 @@ class IVFIndex(_Index):
 class IVFPQIndex(IVFIndex):
     kind = INDEX_IVF_PQ
 
+    @property
+    def code_bytes(self) -> int:
+        """bytes of one stored code: m (ks = 256), m / 2 (ks = 16: two codes per byte, ADCScan.swift:384-456)"""
+        return self.params.m // 2 if self.params.ks == 16 else self.params.m
+
     def set_codebooks(self, codebooks, centroid_norms=None):
         cb = as_input(codebooks, np.float32)
         cn = as_input(centroid_norms, np.float32)
@@ -261,6 +266,23 @@ class IVFPQIndex(IVFIndex):
         check(lib().vix_index_probe_range(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(nprobe), C.c_int(list_begin),
                                           C.c_int(list_count), ptr(ids, np.int32), ptr(sc, np.float32)))
         return ids, sc
+
+    def batch_search_rerank(self, queries, k: int, vectors, rerank_r: int, nprobe: int = 0, sq_norms=None):
+        """The IVF-PQ query with the spec's optional step 7 (DONE_22_adc_scan.md:873-878): ADC top-``rerank_r`` candidates,
+        then Kernel #40 exact re-rank against the original ``vectors`` (row = id).  Returns (raw exact scores, ids)."""
+        q = as_input(queries, np.float32)
+        self._check_dim(q, "batch_search_rerank")
+        xb = as_input(vectors, np.float32)
+        nq, kk = int(q.shape[0]), max(int(k), 0)
+        sc = empty_like_input(q, (nq, kk), np.float32)
+        ids = empty_like_input(q, (nq, kk), np.int64)
+        if nq == 0 or kk == 0:
+            return sc, ids
+        nr = as_input(sq_norms, np.float32)
+        check(lib().vix_index_search_rerank(self._h, ptr(q, np.float32), C.c_int64(nq), C.c_int(k), C.c_int(nprobe),
+                                            C.c_int(int(rerank_r)), ptr(xb, np.float32), C.c_int64(int(xb.shape[0])), ptr(nr),
+                                            ptr(sc, np.float32), ptr(ids, np.int64)))
+        return sc, ids
 
     def search_with_probes(self, queries, k, probes, stats=False):
         q = as_input(queries, np.float32)
@@ -307,7 +329,7 @@ class IVFPQIndex(IVFIndex):
         self._check_dim(x, "encode")
         n = int(x.shape[0])
         asg = empty_like_input(x, (n,), np.int32)
-        codes = empty_like_input(x, (n, self.params.m), np.uint8)
+        codes = empty_like_input(x, (n, self.code_bytes), np.uint8)
         if n == 0:
             return asg, codes
         check(lib().vix_index_encode(self._h, ptr(x, np.float32), C.c_int64(n), ptr(asg, np.int32), ptr(codes, np.uint8)))
@@ -332,7 +354,7 @@ class IVFPQIndex(IVFIndex):
         kc = C.c_int(0)
         check(lib().vix_index_get_coarse(self._h, None, C.byref(kc)))
         off = np.empty(kc.value + 1, dtype=np.int64)
-        codes = np.empty((n, self.params.m), dtype=np.uint8)
+        codes = np.empty((n, self.code_bytes), dtype=np.uint8)
         ids = np.empty(n, dtype=np.int64)
         asg = np.empty(n, dtype=np.int32)
         check(lib().vix_index_export_lists(self._h, ptr(off), ptr(codes), ptr(ids), ptr(asg)))
