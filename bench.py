@@ -449,11 +449,24 @@ def main():
     # diagnostic (untimed): where a sharded step spends its time on this rank, and the per-rank scan times
     phase_ms = None
     if dist:
-        sh.phase_times = {}
-        for _ in range(3):
-            sh.batch_search(q_dev, k)
-        phase_ms = {kk: round(v / 3, 3) for kk, v in sh.phase_times.items()}
-        sh.phase_times = None
+        comm = getattr(sh, "comm", None)
+        if comm is not None and args.partition == "lists":         # the library's own phase events (vix_comm_trace)
+            _lib.check(L.vix_comm_trace(comm._c, 1))
+            acc = np.zeros(3)
+            ph = (C.c_float * 3)()
+            for _ in range(3):
+                sh.batch_search(q_dev, k)
+                _lib.check(L.vix_comm_trace_get(comm._c, ph))
+                acc += np.array(list(ph))
+            _lib.check(L.vix_comm_trace(comm._c, 0))
+            phase_ms = dict(zip(("probe_select+exchange", "scan", "exchange+merge"), (round(float(v) / 3, 3) for v in acc)))
+            phase_ms["peer_memory"] = comm.uses_peer_memory
+        else:
+            sh.phase_times = {}
+            for _ in range(3):
+                sh.batch_search(q_dev, k)
+            phase_ms = {kk: round(v / 3, 3) for kk, v in sh.phase_times.items()}
+            sh.phase_times = None
         per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
         per_rank[rank] = scan_ms / K
         dist.all_reduce(per_rank)

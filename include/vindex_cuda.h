@@ -386,6 +386,10 @@ int vix_comm_destroy(vix_comm_t* c);
 int vix_comm_rank(const vix_comm_t* c);
 int vix_comm_world(const vix_comm_t* c);
 int vix_comm_uses_peer_memory(const vix_comm_t* c);        /* 1 peer memory, 0 NCCL all-gathers, -1 not decided yet */
+/* measurement aid: CUDA events around the three phases of the LAST vix_sharded_search on this communicator --
+ * probe selection + exchange | fused scan | result exchange + merge (ms; waits for that search to finish) */
+int vix_comm_trace(vix_comm_t* c, int enabled);
+int vix_comm_trace_get(vix_comm_t* c, float* phase_ms /* [3] */);
 /* rows [first, first + count) of a batch of nq queries are the block whose probe lists `rank` computes */
 int vix_sharded_query_block(int64_t nq, int rank, int world, int64_t* first, int64_t* count);
 int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds /* nullable */, const float* x,

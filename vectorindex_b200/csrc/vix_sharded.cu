@@ -114,6 +114,9 @@ struct vix_comm {
     // NCCL path: plain local buffers with the same roles
     void* gather_probes = nullptr; size_t gather_probes_bytes = 0;
     void* gather_keys = nullptr; size_t gather_keys_bytes = 0;
+    // optional phase events of the last search (vix_comm_trace): start | probes exchanged | scanned | merged
+    bool trace = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace vix {
@@ -343,6 +346,7 @@ int vix_comm_destroy(vix_comm_t* c) {
     close_peers(c);
     if (c->gather_probes) cudaFree(c->gather_probes);
     if (c->gather_keys) cudaFree(c->gather_keys);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     delete c;
     return VIX_OK;
@@ -392,6 +396,8 @@ int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int6
     Scratch<int64_t> lids;
     VIX_TRY(ldist.alloc((size_t)total));
     VIX_TRY(lids.alloc((size_t)total));
+    auto mark = [&](int i) { if (c->trace) cudaEventRecord(c->ev[i], s); };
+    mark(0);
 
     if (c->peer_state == 1) {
         char* base = static_cast<char*>(c->local);
@@ -425,9 +431,11 @@ int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int6
             VIX_LAUNCH_CHECK();
             VIX_TRY(peer_barrier(c));
         }
+        mark(1);
         // 4. fused scan over the probed lists this rank owns
         const float* qall = host_q ? qbuf : queries;
         VIX_TRY(index_search_locked(h, qall, nq, k, nprobe, ldist.ptr, lids.ptr, nullptr, nullptr, pbuf));
+        mark(2);
         // 5. its top-k leaves as packed keys for slot `rank` of every rank's result buffer; barrier; merge
         pack_result_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ldist.ptr, lids.ptr, total, c->peer_dev, world,
                                                                               c->off_results + (size_t)rank * total * 8, nullptr);
@@ -460,7 +468,9 @@ int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int6
             VIX_LAUNCH_CHECK();
         }
         VIX_NCCL(g_nccl.AllGather(pblock, pall, (size_t)per * nprobe, ncclInt32, c->comm, s));   // in place
+        mark(1);
         VIX_TRY(index_search_locked(h, dq.dev, nq, k, nprobe, ldist.ptr, lids.ptr, nullptr, nullptr, pall));
+        mark(2);
         u64* kall = static_cast<u64*>(c->gather_keys);
         pack_result_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ldist.ptr, lids.ptr, total, nullptr, world, 0,
                                                                               kall + (size_t)rank * total);
@@ -468,9 +478,29 @@ int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int6
         VIX_NCCL(g_nccl.AllGather(kall + (size_t)rank * total, kall, (size_t)total, ncclUint64, c->comm, s));
         VIX_TRY(merge_shard_keys(kall, world, nq, k, 0, 0, nullptr, dd.dev, di.dev));
     }
+    mark(3);
     VIX_TRY(dd.commit());
     VIX_TRY(di.commit());
     return finish(dd.is_host() || di.is_host());
+}
+
+int vix_comm_trace(vix_comm_t* c, int enabled) {
+    VIX_REQUIRE(c, VIX_ERR_NULL_PTR, "vix_comm_trace: null handle");
+    std::lock_guard<std::mutex> lc(c->mu);
+    if (enabled)
+        for (auto& e : c->ev)
+            if (!e) VIX_CUDA(cudaEventCreate(&e));
+    c->trace = enabled != 0;
+    return VIX_OK;
+}
+
+int vix_comm_trace_get(vix_comm_t* c, float* phase_ms /* [3] */) {
+    VIX_REQUIRE(c && phase_ms, VIX_ERR_NULL_PTR, "vix_comm_trace_get: null pointer");
+    std::lock_guard<std::mutex> lc(c->mu);
+    VIX_REQUIRE(c->trace && c->ev[3], VIX_ERR_CONTRACT, "vix_comm_trace_get: tracing is off");
+    VIX_CUDA(cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; ++i) VIX_CUDA(cudaEventElapsedTime(phase_ms + i, c->ev[i], c->ev[i + 1]));
+    return VIX_OK;
 }
 
 int vix_sharded_add(vix_index_t* h, vix_comm_t* c, const int64_t* list_bounds, const float* x, const int64_t* ids, int64_t n) {
