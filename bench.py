@@ -421,7 +421,12 @@ def main():
 
     # ---- end to end through the public API with pinned host buffers
     _lib.check(L.vix_set_async(0))
-    if world > 1:
+    if world > 1 and args.partition == "lists":
+        # pinned host result buffers, as a host that cares about the copy back would pass them
+        o_pin = (torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy(),
+                 torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy())
+        api = lambda: sh.batch_search(q_host, k, out=o_pin)           # noqa: E731
+    elif world > 1:
         api = lambda: sh.batch_search(q_host, k)                      # noqa: E731
     else:
         api = lambda: idx.batch_search(q_host, k)                     # noqa: E731

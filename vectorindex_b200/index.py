@@ -765,9 +765,10 @@ class ShardedIVFPQIndex:
                 buf[:cnt] = ids
         return self._all_gather(buf).view(self.world * per, nprobe)[:nq].contiguous()
 
-    def batch_search(self, queries, k, nprobe=0):
+    def batch_search(self, queries, k, nprobe=0, out=None):
         """Replicated queries in, merged [nq x k] (distances, ids) out on every rank.  Host (numpy) queries are
-        staged to the device once and only the merged result returns to the host."""
+        staged to the device once and only the merged result returns to the host.  ``out``: optional (distances f32,
+        ids int64) host arrays the result is written into (pinned ones make the copy back asynchronous)."""
         import torch
         was_numpy = not _lib._is_torch(queries)
         if int(queries.shape[0]) == 0 or int(k) <= 0:                          # IVFIndex.swift:866: nothing to do
@@ -785,6 +786,11 @@ class ShardedIVFPQIndex:
             q = as_input(queries, np.float32)
             nq = int(q.shape[0])
             if was_numpy:
+                if out is not None:
+                    od, oi = out
+                    check(lib().vix_sharded_search(self.local._h, comm._c, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
+                                                   C.c_int(nprobe), ptr(od, np.float32), ptr(oi, np.int64)))
+                    return od, oi
                 pd, pi = self._pinned("d", (nq, k), torch.float32), self._pinned("i", (nq, k), torch.int64)
                 check(lib().vix_sharded_search(self.local._h, comm._c, ptr(q, np.float32), C.c_int64(nq), C.c_int(k),
                                                C.c_int(nprobe), C.c_void_p(pd.data_ptr()), C.c_void_p(pi.data_ptr())))
