@@ -42,7 +42,10 @@ PRESETS = {
     "c5s": dict(n=12_500_000, d=96, nlist=8192, nprobe=8, m=48, nq=10_000, k=10, shape="deep", clusters=12_500,
                 label="one-eighth shard of configs[4]: IVF-PQ 12.5M x 96, nlist=8192, nprobe=8, M=48, batch 10k, k=10"),
     # BASELINE.json configs[3]: inner-product, embedding-shaped; nprobe / batch are not specified there (32 / 10k assumed)
-    "c4": dict(n=10_000_000, d=768, nlist=16384, nprobe=32, m=64, nq=10_000, k=10, shape="deep", clusters=16384, metric="dotProduct",
+    # data: "embed" = the deep recipe plus near-duplicate structure (groups of 8 rows share a seed vector, queries are
+    # perturbed base rows): with isotropic 768-d noise alone every cluster-mate is equidistant from a query and recall@10 of
+    # ANY 64-byte code is ~0.05 (round 1), which measures nothing
+    "c4": dict(n=10_000_000, d=768, nlist=16384, nprobe=32, m=64, nq=10_000, k=10, shape="embed", clusters=16384, metric="dotProduct",
                label="IVF-PQ inner-product 10M x 768 embedding-shaped, nlist=16384, nprobe=32 (assumed), M=64, batch 10k queries, k=10 (BASELINE configs[3])"),
     "c3": dict(n=1_000_000, d=128, nlist=4096, nprobe=32, m=16, nq=10_000, k=10, shape="sift", clusters=4096,
                label="IVF-PQ 1M x 128 SIFT-shaped, nlist=4096, nprobe=32, M=16, batch 10k queries, k=10 (BASELINE configs[2])"),
@@ -129,7 +132,7 @@ class Synth:
         g = torch.Generator(device=dev)
         g.manual_seed(SEED)
         c = torch.randn((cfg["clusters"], cfg["d"]), generator=g, device=dev)
-        if cfg["shape"] == "deep":
+        if cfg["shape"] in ("deep", "embed"):
             self.centres = c / c.norm(dim=1, keepdim=True)
         else:  # SIFT-shaped: non-negative integer-valued components in [0, 218] with heavy ties
             self.centres = (c.abs() * 40).floor().clamp_(0, 218)
@@ -144,9 +147,27 @@ class Synth:
             v = self.centres[which] + (0.3 / cfg["d"] ** 0.5) * noise
             v /= v.norm(dim=1, keepdim=True)
             return v.contiguous()
+        if cfg["shape"] == "embed":
+            # groups of 8 consecutive rows: one cluster, one seed vector (centre + 0.3-norm noise), 0.06-norm noise per row
+            grp = torch.arange(count, device=self.dev) // 8
+            first = grp * 8                                               # the row whose draws define the group
+            v = self.centres[which[first]] + (0.3 / cfg["d"] ** 0.5) * noise[first]
+            v += (0.06 / cfg["d"] ** 0.5) * torch.randn((count, cfg["d"]), generator=g, device=self.dev)
+            v /= v.norm(dim=1, keepdim=True)
+            return v.contiguous()
         return (self.centres[which] + 12.0 * noise).abs_().floor_().clamp_(0, 218).contiguous()
 
     def queries(self, nq: int):
+        if self.cfg["shape"] == "embed":                                   # perturbed base rows (every 7th row of the first chunk)
+            torch = self.t
+            n0 = min(self.cfg["n"], CHUNK)
+            base = self.rows(0, n0)
+            pick = (torch.arange(nq, device=self.dev) * 7) % n0
+            g = torch.Generator(device=self.dev)
+            g.manual_seed(321)
+            v = base[pick] + (0.06 / self.cfg["d"] ** 0.5) * torch.randn((nq, self.cfg["d"]), generator=g, device=self.dev)
+            v /= v.norm(dim=1, keepdim=True)
+            return v.contiguous()
         return self.rows(0, nq, seed=321)
 
 
@@ -429,7 +450,9 @@ def main():
     elif world > 1:
         api = lambda: sh.batch_search(q_host, k)                      # noqa: E731
     else:
-        api = lambda: idx.batch_search(q_host, k)                     # noqa: E731
+        o_pin = (torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy(),
+                 torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy())
+        api = lambda: idx.batch_search(q_host, k, out=o_pin)          # noqa: E731
     for _ in range(1 if args.profile else W):
         api()
     barrier()

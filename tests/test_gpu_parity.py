@@ -88,6 +88,41 @@ def test_pq_encode_long_subvectors(oracle, vk, n, d, m):
     assert np.array_equal(fused, vk.pq_encode_u8_f32((x - coarse[assign]).astype(np.float32), cb, m))
 
 
+@pytest.mark.parametrize("n,d,m", [(20000, 128, 16), (9000, 64, 4), (12345, 48, 6), (5000, 512, 64)])
+def test_pq_encode_tensor_core_shortlist_is_exact(oracle, vk, n, d, m, monkeypatch):
+    """n >= 4096 with d / m in {8, 16} takes the tcgen05 shortlist (vix_pq_tc.cu): one TF32 MMA per (row tile, sub-space),
+    finalists re-evaluated in the reference's arithmetic.  The codes must equal the oracle's restatement of pq_encode.c and
+    the CUDA-core kernel's (VIX_DISABLE_PQ_TC=1) bit for bit -- with and without centroid norms, plain and residual --
+    including duplicated codewords (tie -> smaller k), rows that ARE codewords, zero rows, rows of large magnitude (the
+    error bound scales with ||x_j||) and near-ties (codewords 1 ulp apart)."""
+    rng = np.random.default_rng(n + d)
+    ks, dsub, kc = 256, d // m, 7
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    cb = rng.uniform(-1, 1, (m, ks, dsub)).astype(np.float32)
+    cb[:, 200] = cb[:, 17]                                                  # exact duplicates: the smaller index must win
+    cb[:, 201] = np.nextafter(cb[:, 18], np.float32(2))                     # near-ties, one ulp apart
+    x[:m * 8:8] = np.concatenate([cb[j, 17] for j in range(m)])            # rows that are codeword 17 in every sub-space
+    x[1] = 0.0
+    x[2] *= 1000.0
+    x[3] *= 1e-4
+    cbf = cb.reshape(-1)
+    csq = oracle.pq_centroid_sq(cbf, m, ks, dsub, swift=False)
+    coarse = rng.uniform(-1, 1, (kc, d)).astype(np.float32)
+    assign = rng.integers(0, kc, n).astype(np.int32)
+    want = oracle.pq_encode_u8(x, cbf, m, ks)
+    want_csq = oracle.pq_encode_u8(x, cbf, m, ks, centroid_sq=csq)
+    want_res = oracle.pq_encode_u8(x, cbf, m, ks, centroid_sq=csq, coarse=coarse, assign_=assign)
+    want_res_dot = oracle.pq_encode_u8(x, cbf, m, ks, coarse=coarse, assign_=assign)
+    for disable in (None, "1"):                                             # tensor-core path, then the CUDA-core kernel
+        if disable:
+            monkeypatch.setenv("VIX_DISABLE_PQ_TC", disable)
+        assert np.array_equal(vk.pq_encode_u8_f32(x, cbf, m), want)
+        assert np.array_equal(vk.pq_encode_u8_f32_withCSQ(x, cbf, csq, m), want_csq)
+        assert np.array_equal(vk.pq_encode_residual_u8_f32_withCSQ(x, cbf, csq, coarse, assign, m), want_res)
+        assert np.array_equal(vk.pq_encode_residual_u8_f32(x, cbf, coarse, assign, m), want_res_dot)
+    assert (want[:m * 8:8] == 17).all()
+
+
 def test_pq_encode_reference_fixture_and_layouts(oracle, vk):
     """fixture of PQEncodeParity_AoS_C_vs_Swift_Tests.swift:5-31 against the compiled reference encoder,
     including the SoA-blocked and interleaved output layouts (pq_encode.c:260-276)."""

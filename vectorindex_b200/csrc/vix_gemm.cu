@@ -372,13 +372,13 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// rows x d fp32 row-major, box = 32 columns (128 B) x 128 rows, 128B swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int d) {
+// rows x d fp32 row-major, box = 32 columns (128 B) x box_rows rows, 128B swizzle, zero fill out of bounds
+int make_map_rows(CUtensorMap* map, const float* ptr, int64_t rows, int d, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     VIX_REQUIRE(fn != nullptr, VIX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kM};
+    cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -387,6 +387,8 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int d) {
                 (long long)rows, d);
     return VIX_OK;
 }
+
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int d) { return make_map_rows(map, ptr, rows, d, kM); }
 
 bool supported(int64_t nA, int64_t nB, int d, const float* A, const float* B) {
     if (nA <= 0 || nB <= 0 || d < 4 || (d & 3) != 0) return false;            // TMA: 16-byte row pitch

@@ -395,12 +395,19 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
 }
 
 // the table was built batch-wide (lut_image_kernel): copy its image with asynchronous 16-byte copies -- every piece of
-// a thread is in flight at once and none of them holds a register
-__device__ VIX_SCAN_FN void copy_lut_image(float* __restrict__ s_lut, const float* __restrict__ image, int n4, int t, int nthr) {
+// a thread is in flight at once and none of them holds a register.  The image is COMPACT ([table][code][32 slots]: one
+// copy of every entry, half the bytes to write and to read back); the two replicas of a shared-memory row are made here,
+// each 16-byte source piece going to both.
+__device__ VIX_SCAN_FN void copy_lut_image(float* __restrict__ s_lut, const float* __restrict__ image, int npieces, int t, int nthr) {
     const float4* src = reinterpret_cast<const float4*>(image);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lut);
-    for (int i = t; i < n4; i += nthr)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i));
+    for (int i = t; i < npieces; i += nthr) {
+        // piece i: table i / 2048, code (i / 8) % 256, group parity (i / 4) % 2, four entries 4 (i % 4) .. of the group
+        const uint32_t row = (uint32_t)(i >> 3), w = (uint32_t)i & 7u;
+        const uint32_t d0 = dst + row * 256u + (w >> 2) * 128u + (w & 3u) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src + i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 64u), "l"(src + i));
+    }
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -431,9 +438,8 @@ lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const flo
         s_q[qi][jj * 17 + e] = ok ? __ldg(queries + (q0 + qi) * d + (tab * 32 + jj) * dsub + e) * lut_scale : 0.0f;
     }
     __syncthreads();
-    // slot of sub-quantiser j inside a 64-slot row: group (j / 16) & 1 takes slots [32 g, 32 g + 32): replica A | replica B
-    const int slot = ((lane >> 4) & 1) * 32 + (lane & 15);
-    float* rowbase = image + (size_t)q0 * (NTAB * 16384) + (size_t)tab * 16384 + slot;
+    // compact image: [table][code][32 slots], slot = 16 * ((j / 16) & 1) + j % 16 = the lane (copy_lut_image makes the replicas)
+    float* rowbase = image + (size_t)q0 * (NTAB * 8192) + (size_t)tab * 8192 + lane;
     for (int c = warp; c < 256; c += 8) {
         float cv[16];
         if (live) {
@@ -456,9 +462,7 @@ lut_image_kernel(const float* __restrict__ queries, int64_t nq, int d, const flo
 #pragma unroll
             for (int e = 0; e < 16; ++e) if (e < dsub) dot = fmaf(s_q[qi][lane * 17 + e], cv[e], dot);
             if (live && q0 + qi < nq) {
-                float* row = rowbase + (size_t)qi * (NTAB * 16384) + c * 64;
-                row[0] = dot;                              // replica A
-                row[16] = dot;                             // replica B
+                rowbase[(size_t)qi * (NTAB * 8192) + c * 32] = dot;      // one coalesced 128-byte row per warp
             }
         }
     }
@@ -599,7 +603,7 @@ ivfpq_scan_kernel(ScanArgs a) {
             const long long t0 = STATS ? clock64() : 0;
             if (nchunks > 0) {
                 if constexpr (PIPES == 1) {
-                    if (a.lut_image) copy_lut_image(s_lut, a.lut_image + (size_t)qi * (NTAB * 16384), NTAB * 4096, tid, (int)blockDim.x);
+                    if (a.lut_image) copy_lut_image(s_lut, a.lut_image + (size_t)qi * (NTAB * 8192), NTAB * 2048, tid, (int)blockDim.x);
                     else build_lut<m>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, (int)blockDim.x);
                 } else {                                   // (the launcher never combines table images with two pipelines)
                     if (pipe == 0) build_lut<m, 0>(s_lut, q, a.codebooks_t, a.dsub, lut_scale, tid, nthreads);
@@ -1083,7 +1087,7 @@ int launch_ivfpq_scan(ScanArgs& a) {
     }
     Scratch<float> image;
     const size_t cb_bytes = (size_t)a.m * 256 * a.dsub * 4;
-    const size_t img_floats = (size_t)((a.m / 16 + 1) / 2) * 16384;
+    const size_t img_floats = (size_t)((a.m / 16 + 1) / 2) * 8192;      // compact: [table][256 codes][32 slots]
     if (cb_bytes >= 512 * 1024 && a.dsub <= 16 && (size_t)a.nq * img_floats * 4 <= (4ull << 30) && !getenv("VIX_DISABLE_LUT_IMAGE")) {
         // large codebooks: build every query's table once, batch-wide, instead of once per query inside the scan
         // (C4: the table's share of a query 31 k -> 2.9 k cycles for a 0.46 ms batch kernel; scan stage 3.36 -> 2.86 ms)

@@ -15,8 +15,9 @@ struct ScanArgs {
     int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
     const float* coarse; int kc;                  // [kc x d]; probe ids outside [0, kc) are treated like the -1 padding
     const float* bias;                            // optional [nq x nprobe]: the per-probe term, precomputed batch-wide (large d)
-    const float* lut_image;                       // optional [nq][tables x 64 KB]: the look-up tables of every query, already in
-                                                  // the scan's shared-memory layout (built batch-wide when the codebooks are large)
+    const float* lut_image;                       // optional [nq][tables][256 codes][32 slots]: the look-up tables of every query,
+                                                  // compact (the scan makes the two replicas of a shared-memory row while
+                                                  // copying); built batch-wide when the codebooks are large
     const float* codebooks;                       // [m x ks x dsub]
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
     const int64_t* list_off; const int32_t* list_len;

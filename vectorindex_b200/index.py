@@ -148,15 +148,21 @@ class _Index:
     def clear(self):
         check(lib().vix_index_clear(self._h))
 
-    def batch_search(self, queries, k: int, nprobe: int = 0, return_probes=False, stats=False, filter=None):
+    def batch_search(self, queries, k: int, nprobe: int = 0, return_probes=False, stats=False, filter=None, out=None):
         """``filter``: an :class:`IDFilter` (allow / deny bitset over dense ids, applied before selection -- the
-        device-expressible form of the reference's ``filter:`` closures, IVFIndex.swift:813, 1034)."""
+        device-expressible form of the reference's ``filter:`` closures, IVFIndex.swift:813, 1034).
+        ``out``: optional (distances f32 [nq x k], ids int64 [nq x k]) buffers to write into (e.g. pinned host arrays)."""
         q = as_input(queries, np.float32)
         self._check_dim(q, "batch_search")
         nq = int(q.shape[0])
         kk = max(int(k), 0)
-        dist = empty_like_input(q, (nq, kk), np.float32)
-        ids = empty_like_input(q, (nq, kk), np.int64)
+        if out is not None:
+            dist, ids = out
+            if tuple(dist.shape) != (nq, kk) or tuple(ids.shape) != (nq, kk):
+                raise ValueError("out buffers must be [nq x k]")
+        else:
+            dist = empty_like_input(q, (nq, kk), np.float32)
+            ids = empty_like_input(q, (nq, kk), np.int64)
         if kk == 0 or nq == 0:
             return (dist, ids)
         if filter is not None:
