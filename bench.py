@@ -51,6 +51,12 @@ PRESETS = {
                label="IVF-PQ 1M x 128 SIFT-shaped, nlist=4096, nprobe=32, M=16, batch 10k queries, k=10 (BASELINE configs[2])"),
     "tiny": dict(n=200_000, d=96, nlist=512, nprobe=8, m=48, nq=1000, k=10, shape="deep", clusters=1000,
                  label="tiny self-test"),
+    # BASELINE.json configs[0] / configs[1]: the parity-test configurations, measurable through the same contract
+    # (one GPU; `python bench.py --workload c1|c2`); data = the reference benchmark's LCG vectors (main.swift:535-548)
+    "c1": dict(kind="flat", n=100_000, d=128, nq=1000, k=10,
+               label="Flat exact L2 search, 100k x 128 fp32 synthetic base, 1k queries, k=10 (BASELINE configs[0])"),
+    "c2": dict(kind="pq_encode", n=1_000_000, d=128, m=16, ks=256,
+               label="PQ train+encode 1M x 128 fp32, M=16 subquantizers x 256 centroids (BASELINE configs[1])"),
 }
 CHUNK = 1_000_000
 GT_QUERIES = 256
@@ -292,6 +298,154 @@ def cpu_search_arm(cfg, idx, q_host, budget_s=12.0, gpu_ids=None):
     return out, dt, s
 
 
+# ------------------------------------------------------------------------------------------------ configs[0..1]
+def run_side_workload(args, cfg, K, W):
+    """BASELINE configs[0] (flat exact search) and configs[1] (PQ train + encode) on ONE GPU through the same contract:
+    value = device-resident throughput (CUDA events), e2e = host buffers in and out, roofline, cpu_baseline (the oracle /
+    the reference's own compiled encoder on a bounded sample).  Parity of both is covered by tests/test_gpu_fullsize.py."""
+    import torch
+    from oracle import oracle
+    from vectorindex_b200 import _lib, datagen, kernels as vk
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    _lib.check(L.vix_set_device(0))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    _lib.check(L.vix_set_stream(C.c_void_p(stream.cuda_stream)))
+    clk = ClockSampler(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    cores = oracle.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    n, d = cfg["n"], cfg["d"]
+    detail = {}
+    if cfg["kind"] == "flat":
+        nq, k = cfg["nq"], cfg["k"]
+        xb_h = datagen.bench_vectors(n, d, 123)
+        q_pin = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
+        q_pin.copy_(torch.from_numpy(datagen.bench_vectors(nq, d, 321)))
+        xb, q = torch.from_numpy(xb_h).to(dev), q_pin.to(dev)
+        o_pin = (torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy(),
+                 torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy())
+        od, oi = torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev)
+
+        def step():
+            _lib.check(L.vix_flat_search_f32(_lib.ptr(q), C.c_int64(nq), _lib.ptr(xb), C.c_int64(n), C.c_int(d), C.c_int(0),
+                                             C.c_int(k), _lib.ptr(od), _lib.ptr(oi)))
+
+        def api():      # host queries in, host results out (the base stays resident: it is the index)
+            _lib.check(L.vix_flat_search_f32(_lib.ptr(q_pin.numpy()), C.c_int64(nq), _lib.ptr(xb), C.c_int64(n), C.c_int(d),
+                                             C.c_int(0), C.c_int(k), _lib.ptr(o_pin[0]), _lib.ptr(o_pin[1])))
+        units, unit, metric = nq, "queries/s", "queries/sec (flat exact L2, k=10)"
+        h2d, d2h = nq * d * 4, nq * k * 12
+        work = 2.0 * nq * n * d                                       # SURVEY 8d: 2 Q N d flop
+        t0 = time.perf_counter()
+        cd, ci, _ = oracle.flat_search(q_pin.numpy(), xb_h, k, 0)
+        cpu_dt = time.perf_counter() - t0
+        cpu = {"value": nq / cpu_dt, "unit": unit, "cores": cores, "kind": "port",
+               "sample": f"all {nq} queries against the full base, oracle/ C restatement of L2Sqr + selectTopK ({cpu_dt:.1f} s)"}
+        check = lambda: bool(np.array_equal(o_pin[1], ci) and np.array_equal(o_pin[0].view(np.uint32), cd.view(np.uint32)))   # noqa: E731
+        detail["parity_with_cpu_baseline"] = "ids and distance bits equal"
+        # two TF32 tensor-core passes dominate the step; TF32 runs at half the bf16 rate
+        peak = float(peaks.get("bf16_tflops_sustained", 1385.9)) / 2.0
+        roof = {"kernel": "tc_score_kernel (two passes: group minima, emission) + exact rescoring", "bound": "tensor",
+                "unit": "TFLOP/s", "peak": peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32)" if peaks else "fallback"}
+    else:
+        m, ks = cfg["m"], cfg["ks"]
+        x_h = datagen.bench_vectors(n, d, 123, normalize=False)
+        x = torch.from_numpy(x_h).to(dev)
+        x_pin = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
+        x_pin.copy_(torch.from_numpy(x_h))
+        t0 = time.perf_counter()
+        tcfg = vk.pq_train_cfg(algorithm=0, max_iters=25, sample_n=65536, mode=1)   # GPU Lloyd, 25 iterations (DESIGN.md 7)
+        cb, norms = vk.pq_train_f32(x, m, ks, cfg=tcfg)
+        torch.cuda.synchronize()
+        detail["train_s"] = round(time.perf_counter() - t0, 3)
+        cbf, nf = cb.reshape(-1).contiguous(), norms.reshape(-1).contiguous()
+        codes = torch.empty((n, m), dtype=torch.uint8, device=dev)
+        c_pin = torch.empty((n, m), dtype=torch.uint8, pin_memory=True).numpy()
+
+        def step():
+            L.cpq_encode_u8_f32_with_csq(_lib.ptr(x), C.c_int64(n), C.c_int(d), C.c_int(m), C.c_int(ks), _lib.ptr(cbf), _lib.ptr(nf),
+                                         _lib.ptr(codes), None)
+
+        def api():      # the reference's own entry point with HOST pointers, as the Swift wrapper calls it
+            L.cpq_encode_u8_f32_with_csq(_lib.ptr(x_pin.numpy()), C.c_int64(n), C.c_int(d), C.c_int(m), C.c_int(ks), _lib.ptr(cbf),
+                                         _lib.ptr(nf), _lib.ptr(c_pin), None)
+        units, unit, metric = n, "vectors/s", "vectors/sec (PQ encode, M=16 x 256, bit-exact codes)"
+        h2d, d2h = n * d * 4, n * m
+        work = 4.0 * n * d + n * m                                    # SURVEY 8d: bytes in + out
+        ns = n                                                        # the CPU arm: the reference's C encoder on the whole input (~1.3 s)
+        cbh, nh = cbf.cpu().numpy(), nf.cpu().numpy()
+        t0 = time.perf_counter()
+        try:
+            ref = oracle.ref_encode("cpq_encode_u8_f32_with_csq", x_h[:ns], cbh, m, ks, centroid_sq=nh, omp=True)
+            kind = "reference"
+            what = "the reference's pq_encode.c compiled unmodified with OpenMP (oracle/_ref)"
+        except Exception:  # noqa: BLE001  (oracle/_ref not built on this box)
+            ref = oracle.pq_encode_u8(x_h[:ns], cbh, m, ks, centroid_sq=nh)
+            kind, what = "port", "oracle/ C restatement of pq_encode.c"
+        cpu_dt = time.perf_counter() - t0
+        cpu = {"value": ns / cpu_dt, "unit": unit, "cores": cores, "kind": kind,
+               "sample": f"all {ns} vectors, {what} ({cpu_dt:.1f} s)"}
+        check = lambda: bool(np.array_equal(c_pin[:ns], ref))        # noqa: E731
+        detail["parity_with_cpu_baseline"] = "codes bit-identical on all vectors"
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof = {"kernel": "pq_tc_encode_kernel (tcgen05 shortlist + exact finalists)", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "note": "compute-bound by the per-codeword epilogue, far from the HBM floor: see DESIGN.md 4.4"}
+    _lib.check(L.vix_set_async(1))
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    L.vix_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    clk.poll_until(e1.query)
+    torch.cuda.synchronize()
+    launches = int(L.vix_kernel_launches(0))
+    ms = e0.elapsed_time(e1) / K
+    _lib.check(L.vix_set_async(0))
+    for _ in range(W):
+        api()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        api()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    _lib.check(L.vix_synchronize())
+    assert check(), "GPU result differs from the CPU baseline on the same inputs"
+    achieved = work / (ms * 1e-3) / (1e12 if roof["bound"] == "tensor" else 1e9)
+    roof.update({"achieved": achieved, "frac": achieved / roof["peak"], "algorithmic_per_launch": work, "ms_per_launch": ms,
+                 "timing": "algorithmic work / the whole step (the named kernels dominate it)"})
+    shape = {k2: v for k2, v in cfg.items() if k2 not in ("kind", "label")}
+    line = {"metric": metric, "value": units / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (tf32 shortlist, exact fp32 finalists)", "data": "synthetic",
+            "config": dict({"workload": cfg["label"]}, **shape,
+                           l2_policy="flat: the 51 MB base is L2-resident by design (it is read once per batch); "
+                                     "pq_encode: 512 MB input > L2, no flush between steps"),
+            "detail": detail, "clocks": clk.summary(),
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+    if args.impl == "reference":
+        line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": unit, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": line["config"], "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    emit(line)
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ main
 def emit(line: dict):
     """The ONE JSON line of the contract, on the process's real stdout (see main: fd 1 is pointed at stderr while
@@ -336,6 +490,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if cfg.get("kind") in ("flat", "pq_encode"):
+        if rank != 0:
+            return 0                                                 # single-GPU workloads: the other ranks have nothing to do
+        return run_side_workload(args, cfg, K, W)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     L = _lib.lib()
@@ -523,7 +681,9 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel from the committed `ncu --set full`
     # captures (profiles/): known only for the configurations that were captured
-    captures = {("c5", 1, "lists"): (87.105206e9 + 7.9e6, "profiles/r01_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch)"),
+    # (a CONSTANT from that capture, not a per-run measurement: the traffic of a launch depends only on the index and the batch)
+    captures = {("c5", 1, "lists"): (87.148642e9 + 7.127e6, "profiles/r02_scan_c5_n1_ncu_summary.txt (ncu --set full, one launch; a "
+                                                              "constant from that capture, not measured in this run)"),
                 ("c5s", 1, "lists"): (5.486273e9 + 5.3e6, "profiles/r01_scan_c5s_ncu_summary.txt (ncu --set full, one launch)"),
                 # one rank's share of an 8-way list-sharded C5, captured on ONE GPU holding the first equal-count eighth of the
                 # lists (the bench's work-balanced boundaries move the block edges by a few lists: approximate for this run)
