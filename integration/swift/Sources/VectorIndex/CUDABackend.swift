@@ -83,5 +83,30 @@ public final class CUDAIVFPQIndex {
                                                 Int32(VIX_FILTER_ALLOW.rawValue), &dist, &ids), "vix_index_search_filtered")
         return (dist, ids)
     }
+    // step 7 of the IVF-PQ query (docs/kernel-specs/DONE_22_adc_scan.md:873-878): ADC top-R, then Kernel #40 over the
+    // original vectors (DenseArray reader: id = row of `vectors`); raw exact scores out (L2^2 / dot), best first
+    public func batchSearchReranked(_ q: [Float], nq: Int, k: Int, rerankR: Int, vectors: UnsafePointer<Float>, count: Int)
+        throws -> ([Float], [Int64]) {
+        var sc = [Float](repeating: .infinity, count: nq * k); var ids = [Int64](repeating: -1, count: nq * k)
+        try _vixCheck(vix_index_search_rerank(h, q, Int64(nq), Int32(k), 0, Int32(rerankR), vectors, Int64(count), nil, &sc, &ids),
+                      "search_rerank")
+        return (sc, ids)
+    }
+
+    // ---- one process per GPU: the inverted lists sharded over the ranks of a vix_comm_t (csrc/vix_sharded.cu) ----
+    // `id`: the 128 bytes rank 0 obtained from vix_comm_unique_id and handed to every worker by the host's own means
+    public static func makeComm(id: [UInt8], rank: Int, world: Int) throws -> OpaquePointer? {
+        var c: OpaquePointer?
+        try _vixCheck(vix_comm_create(id, id.count, Int32(rank), Int32(world), &c), "comm_create")
+        return c
+    }
+    public func shardedInsert(_ comm: OpaquePointer?, _ x: [Float], ids: [Int64]) throws {      // collective
+        try _vixCheck(vix_sharded_add(h, comm, nil, x, ids, Int64(ids.count)), "sharded_add")
+    }
+    public func shardedSearch(_ comm: OpaquePointer?, _ q: [Float], nq: Int, k: Int) throws -> ([Float], [Int64]) {   // collective
+        var dist = [Float](repeating: .nan, count: nq * k); var ids = [Int64](repeating: -1, count: nq * k)
+        try _vixCheck(vix_sharded_search(h, comm, q, Int64(nq), Int32(k), 0, &dist, &ids), "sharded_search")
+        return (dist, ids)
+    }
 }
 #endif

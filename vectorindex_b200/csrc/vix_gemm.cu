@@ -45,7 +45,8 @@ int row_norms_device(const float* x, int64_t n, int d, float* out);
 namespace tc {
 
 constexpr int kM = 128, kN = 128, kKB = 32;            // tile rows, tile columns, tf32 elements per K-block
-constexpr int kStages = 5;
+constexpr int kStages = 5;                            // ring stages when A and B share a stage (32 KB each)
+constexpr int kStagesMax = 8;                         // ... when only B streams (16 KB each): as many as fit, up to this
 constexpr int kStageBytes = (kM + kN) * kKB * 4;       // 32 KB
 constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: each takes 64 of the 128 columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -60,6 +61,7 @@ struct Args {
     int kblocks;           // ceil(d / 32)
     int ntiles;            // ceil(nB / 128)
     int tiles_per_split, nsplit, mtiles;
+    int nstages;           // ring stages of this launch (set by launch())
     int mode, metric;
     const float* bnorm;    // [nB] ||c||^2 (L2) or nullptr
     int gcols, ngroups;    // MODE_MIN: columns per group (32, 64 or 128 * 2^t), groups per row
@@ -152,6 +154,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load in two halves: `issue` starts it, `wait` makes the registers readable (it names them as in/out operands,
+// so no use can be scheduled in front of it).  Both 32-column loads of a tile are issued before the first wait.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32], uint32_t (&q)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+    asm volatile(""
+                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]),
+                   "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]), "+r"(q[16]),
+                   "+r"(q[17]), "+r"(q[18]), "+r"(q[19]), "+r"(q[20]), "+r"(q[21]), "+r"(q[22]), "+r"(q[23]), "+r"(q[24]),
+                   "+r"(q[25]), "+r"(q[26]), "+r"(q[27]), "+r"(q[28]), "+r"(q[29]), "+r"(q[30]), "+r"(q[31])
+                 :: "memory");
+}
+
 // K-major operand tile [rows][32 tf32] = rows x 128 B, 128B swizzle (8-row atoms of 1024 B): SBO = 1024 B
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -164,24 +194,35 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int MODE, int METRIC>
+// ARES: the row tile of A (kblocks x 16 KB, d <= 128) stays RESIDENT in shared memory for all the column tiles of a work
+// item (two buffers: the next item's rows load while this item finishes) and only B streams through the ring.  Without
+// it every column tile re-reads its A tile, and at d = 96 the kernel runs at the L2 -> SM bandwidth (96 KB per 128 x 128
+// tile, 77 % of the chip's L2 read rate, tensor pipe 38 % busy); resident rows halve that traffic.
+template <int MODE, int METRIC, bool ARES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024 B alignment for the swizzle atoms
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* ring = base;                                                      // kStages x (A 16 KB | B 16 KB)
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageBytes);   // [kStages]
-    uint64_t* empty = full + kStages;                                                // [kStages]
-    uint64_t* tfull = empty + kStages;                                               // [2]
+    constexpr int kTileBytes = kM * kKB * 4;                                         // one K-block of a tile: 16 KB
+    constexpr int kRingStage = ARES ? kTileBytes : kStageBytes;                      // B only | A + B
+    const size_t a_bytes = ARES ? (size_t)a.kblocks * kTileBytes : 0;                // one resident A buffer
+    unsigned char* a_res = base;                                                     // ARES: 2 x [kblocks] x 16 KB
+    unsigned char* ring = base + 2 * a_bytes;                                        // kStages x (A 16 KB | B 16 KB), or x B
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.nstages * kRingStage);  // [kStagesMax]
+    uint64_t* empty = full + kStagesMax;                                             // [kStagesMax]
+    uint64_t* tfull = empty + kStagesMax;                                            // [2]
     uint64_t* tempty = tfull + 2;                                                    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* afull = tempty + 2;                                                    // [2] resident A buffer loaded
+    uint64_t* aempty = afull + 2;                                                    // [2] ... no longer read by any MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
     float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [kEpiWarps][2][64] column norms
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kStagesMax; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
+        for (int b = 0; b < 2; ++b) { mbar_init(afull + b, 1); mbar_init(aempty + b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -196,17 +237,30 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             bool ok = true;
-            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+            int nitem = 0;                                             // items of this CTA so far: A buffer nitem & 1
+            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x, ++nitem) {
                 const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
                 const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
+                if (ARES) {
+                    // the item's rows, once: all K-blocks on one barrier
+                    const int ab = nitem & 1;
+                    if (!mbar_wait(aempty + ab, ((uint32_t)(nitem >> 1) & 1u) ^ 1u, a.error, a.error_host)) { ok = false; break; }
+                    mbar_expect_tx(afull + ab, (uint32_t)a_bytes);
+                    for (int kb = 0; kb < a.kblocks; ++kb)
+                        tma_load_2d(a_res + (size_t)ab * a_bytes + (size_t)kb * kTileBytes, &mapA, afull + ab, kb * kKB, mt * kM);
+                }
                 for (int nt = nt0; nt < nt1 && ok; ++nt) {
                     for (int kb = 0; kb < a.kblocks; ++kb) {
                         if (!mbar_wait(empty + stage, phase ^ 1, a.error, a.error_host)) { ok = false; break; }
-                        unsigned char* sA = ring + (size_t)stage * kStageBytes;
-                        mbar_expect_tx(full + stage, kStageBytes);
-                        tma_load_2d(sA, &mapA, full + stage, kb * kKB, mt * kM);
-                        tma_load_2d(sA + kM * kKB * 4, &mapB, full + stage, kb * kKB, nt * kN);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        unsigned char* sS = ring + (size_t)stage * kRingStage;
+                        mbar_expect_tx(full + stage, kRingStage);
+                        if (ARES) {
+                            tma_load_2d(sS, &mapB, full + stage, kb * kKB, nt * kN);
+                        } else {
+                            tma_load_2d(sS, &mapA, full + stage, kb * kKB, mt * kM);
+                            tma_load_2d(sS + kTileBytes, &mapB, full + stage, kb * kKB, nt * kN);
+                        }
+                        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -217,10 +271,16 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t aphase = 0;
             bool ok = true;
-            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+            int nitem = 0;
+            for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x, ++nitem) {
                 const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
                 const int nt0 = sp * a.tiles_per_split, nt1 = min(a.ntiles, nt0 + a.tiles_per_split);
                 (void)mt;
+                const int ab = nitem & 1;
+                if (ARES) {
+                    if (!mbar_wait(afull + ab, (uint32_t)(nitem >> 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                    fence_after_sync();
+                }
                 for (int nt = nt0; nt < nt1 && ok; ++nt) {
                     if (!mbar_wait(tempty + acc, aphase ^ 1, a.error, a.error_host)) { ok = false; break; }
                     fence_after_sync();
@@ -228,18 +288,20 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int kb = 0; kb < a.kblocks; ++kb) {
                         if (!mbar_wait(full + stage, phase, a.error, a.error_host)) { ok = false; break; }
                         fence_after_sync();
-                        const uint32_t sA = smem_u32(ring + (size_t)stage * kStageBytes);
-                        const uint64_t da = make_desc(sA), db = make_desc(sA + kM * kKB * 4);
+                        const uint32_t sS = smem_u32(ring + (size_t)stage * kRingStage);
+                        const uint32_t sA = ARES ? smem_u32(a_res + (size_t)ab * a_bytes + (size_t)kb * kTileBytes) : sS;
+                        const uint64_t da = make_desc(sA), db = make_desc(ARES ? sS : sS + kTileBytes);
 #pragma unroll
                         for (int k = 0; k < kKB / 8; ++k)      // K = 8 tf32 (32 B) per instruction: +2 in 16 B units
                             mma_tf32(tmem_d, da + 2 * k, db + 2 * k, (kb | k) ? 1u : 0u);
                         mma_commit(empty + stage);             // frees the ring slot when these MMAs retire
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                     }
                     if (!ok) break;
                     mma_commit(tfull + acc);                   // accumulator complete
                     if (++acc == 2) { acc = 0; aphase ^= 1; }
                 }
+                if (ARES && ok) mma_commit(aempty + ab);       // the resident rows are free when this item's MMAs retire
             }
         }
     } else {
@@ -255,14 +317,24 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const bool row_ok = row < a.nA;
             const float thr = (MODE == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
             float gmin = INFINITY;
-            for (int nt = nt0; nt < nt1 && ok; ++nt) {
-                // stage this warp's 64 column norms (private copy per warp: no CTA-level barrier needed)
-                float* bn = s_bn + ((warp - 2) * 2 + acc) * 64;
+            // this warp's 64 column norms of a tile travel one tile ahead in registers: the L2 round trip of the load used
+            // to sit in front of every tile's accumulator wait (the top stall of the kernel: the eight epilogue warps take
+            // the tiles one after the other, so whatever a tile waits for is paid per tile)
+            float nb_next[2];
+            auto load_norms = [&](int nt) {
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int col = nt * kN + half * 64 + t * 32 + lane;
-                    bn[t * 32 + lane] = (a.bnorm && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
+                    nb_next[t] = (a.bnorm && nt < nt1 && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
                 }
+            };
+            load_norms(nt0);
+            for (int nt = nt0; nt < nt1 && ok; ++nt) {
+                // stage the norms (private copy per warp: no CTA-level barrier needed), start the next tile's loads
+                float* bn = s_bn + ((warp - 2) * 2 + acc) * 64;
+                bn[lane] = nb_next[0];
+                bn[32 + lane] = nb_next[1];
+                load_norms(nt + 1);
                 __syncwarp();
                 if (!mbar_wait(tfull + acc, aphase, a.error, a.error_host)) { ok = false; break; }
                 fence_after_sync();
@@ -270,10 +342,16 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int colbase = nt * kN + half * 64;
                 const bool full_tile = nt * kN + kN <= a.nB;
                 unsigned long long hits = 0;                   // MODE_EMIT: this thread's 64 columns with S~ <= T
-#pragma unroll 1
+                // both 32-column loads of this thread's strip are in flight together (one TMEM round trip per tile, not two)
+                uint32_t vraw[2][32];
+                tmem_ld32_issue(taddr, vraw[0]);
+                tmem_ld32_issue(taddr + 32, vraw[1]);
+                tmem_ld32_wait(vraw[0], vraw[1]);
+#pragma unroll
                 for (int ck = 0; ck < 2; ++ck) {
                     float v[32];
-                    tmem_ld32(taddr + ck * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vraw[ck][i]);
                     const float4* bn4 = reinterpret_cast<const float4*>(bn + ck * 32);
                     float sc[32];
 #pragma unroll
@@ -397,7 +475,19 @@ bool supported(int64_t nA, int64_t nB, int d, const float* A, const float* B) {
     return encode_fn() != nullptr;
 }
 
-static size_t smem_bytes() { return (size_t)kStages * kStageBytes + 1024 + 256 + (size_t)kEpiWarps * 2 * 64 * 4; }
+// rows resident (ARES) when both A buffers and the B ring fit: d <= 128
+static bool a_resident(int kblocks) { return kblocks <= 4 && getenv("VIX_TC_NO_ARES") == nullptr; }
+static int ring_stages(int kblocks) {
+    if (!a_resident(kblocks)) return kStages;
+    const size_t left = 227 * 1024 - 8 * 1024 - (size_t)2 * kblocks * kM * kKB * 4;
+    const int n = (int)(left / ((size_t)kM * kKB * 4));
+    return n > kStagesMax ? kStagesMax : n;
+}
+static size_t smem_bytes(int kblocks) {
+    const size_t ring = a_resident(kblocks) ? (size_t)2 * kblocks * kM * kKB * 4 + (size_t)ring_stages(kblocks) * kM * kKB * 4
+                                            : (size_t)kStages * kStageBytes;
+    return ring + 1024 + 512 + (size_t)kEpiWarps * 2 * 64 * 4;
+}
 
 static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Args& a) {
     CUtensorMap mapA, mapB;
@@ -408,7 +498,10 @@ static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Arg
     a.ntiles = (nB + kN - 1) / kN;
     a.mtiles = (int)((nA + kM - 1) / kM);
     // column splits: enough work items for ~3 waves of the SMs; in MODE_MIN a split is a whole number of groups
-    int nsplit = (3 * num_sms() + a.mtiles - 1) / a.mtiles;
+    // (eight waves: with three, the last wave of C5's probe stage ran a fifth of the SMs)
+    const char* wv = getenv("VIX_TC_WAVES");
+    const int waves = wv ? atoi(wv) : 8;
+    int nsplit = (waves * num_sms() + a.mtiles - 1) / a.mtiles;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > a.ntiles) nsplit = a.ntiles;
     int tps = (a.ntiles + nsplit - 1) / nsplit;
@@ -424,12 +517,14 @@ static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Arg
         VIX_REQUIRE((1 << sh) == v, VIX_ERR_INVALID_PARAM, "tensor-core shortlist: group width %d is not a power of two", a.gcols);
         a.gshift = sh;
     }
-    const size_t smem = smem_bytes();
+    const size_t smem = smem_bytes(a.kblocks);
+    const bool ares = a_resident(a.kblocks);
+    a.nstages = ring_stages(a.kblocks);
     int64_t grid = (int64_t)a.mtiles * a.nsplit;
     if (grid > num_sms()) grid = num_sms();
 #define VIX_TC_LAUNCH(MODE_, METRIC_)                                                                                   \
     do {                                                                                                               \
-        auto kern = tc_score_kernel<MODE_, METRIC_>;                                                                   \
+        auto kern = ares ? tc_score_kernel<MODE_, METRIC_, true> : tc_score_kernel<MODE_, METRIC_, false>;             \
         VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kern<<<(unsigned)grid, kThreads, smem, ctx().stream>>>(mapA, mapB, a);                                         \
     } while (0)
