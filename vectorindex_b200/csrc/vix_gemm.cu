@@ -44,13 +44,15 @@ int row_norms_device(const float* x, int64_t n, int d, float* out);
 
 namespace tc {
 
-constexpr int kM = 128, kN = 128, kKB = 32;            // tile rows, tile columns, tf32 elements per K-block
-constexpr int kStages = 5;                            // ring stages when A and B share a stage (32 KB each)
-constexpr int kStagesMax = 8;                         // ... when only B streams (16 KB each): as many as fit, up to this
-constexpr int kStageBytes = (kM + kN) * kKB * 4;       // 32 KB
-constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: each takes 64 of the 128 columns
+constexpr int kM = 128, kN = 256, kKB = 32;            // tile rows, tile columns, tf32 elements per K-block
+// (N = 256: one tcgen05.mma M128 N256 K8 is 128 clocks of tensor work.  With N = 128 the single MMA-issuing lane -- four
+//  MMAs, a commit and two mbarrier round trips per K-block, ~60 instructions -- could not keep the pipe busy: 38 % active)
+constexpr int kStages = 4;                            // ring stages when A and B share a stage (16 + 32 KB each)
+constexpr int kStagesMax = 8;                         // ... when only B streams (32 KB each): as many as fit, up to this
+constexpr int kStageBytes = (kM + kN) * kKB * 4;       // 48 KB
+constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: each takes 128 of the 256 columns, 64 at a time
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kTmemCols = 256;                         // two fp32 accumulators of 128 columns
+constexpr int kTmemCols = 512;                         // two fp32 accumulators of 256 columns
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
 
 enum Mode { MODE_WRITE = 0, MODE_MIN = 1, MODE_EMIT = 2 };
@@ -204,8 +206,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024 B alignment for the swizzle atoms
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int kTileBytes = kM * kKB * 4;                                         // one K-block of a tile: 16 KB
-    constexpr int kRingStage = ARES ? kTileBytes : kStageBytes;                      // B only | A + B
+    constexpr int kTileBytes = kM * kKB * 4;                                         // one K-block of the A tile: 16 KB
+    constexpr int kBTileBytes = kN * kKB * 4;                                        // ... of the B tile: 32 KB
+    constexpr int kRingStage = ARES ? kBTileBytes : kStageBytes;                     // B only | A + B
     const size_t a_bytes = ARES ? (size_t)a.kblocks * kTileBytes : 0;                // one resident A buffer
     unsigned char* a_res = base;                                                     // ARES: 2 x [kblocks] x 16 KB
     unsigned char* ring = base + 2 * a_bytes;                                        // kStages x (A 16 KB | B 16 KB), or x B
@@ -216,7 +219,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* afull = tempty + 2;                                                    // [2] resident A buffer loaded
     uint64_t* aempty = afull + 2;                                                    // [2] ... no longer read by any MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
-    float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [kEpiWarps][2][64] column norms
+    float* s_bn = reinterpret_cast<float*>(tmem_slot + 4);                           // [kEpiWarps][2][128] column norms
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -258,7 +261,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             tma_load_2d(sS, &mapB, full + stage, kb * kKB, nt * kN);
                         } else {
                             tma_load_2d(sS, &mapA, full + stage, kb * kKB, mt * kM);
-                            tma_load_2d(sS + kTileBytes, &mapB, full + stage, kb * kKB, nt * kN);
+                            tma_load_2d(sS + kTileBytes, &mapB, full + stage, kb * kKB, nt * kN);      // 256 rows: 32 KB
                         }
                         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                     }
@@ -306,6 +309,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else {
         // ================= epilogue (warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4) =================
+        // a thread owns one row and 128 of the tile's 256 columns, taken in two rounds of 64 (two 32-column TMEM loads in
+        // flight per round)
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         int acc = 0; uint32_t aphase = 0;
@@ -317,109 +322,116 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const bool row_ok = row < a.nA;
             const float thr = (MODE == MODE_EMIT && row_ok) ? a.thr[row] : -INFINITY;
             float gmin = INFINITY;
-            // this warp's 64 column norms of a tile travel one tile ahead in registers: the L2 round trip of the load used
-            // to sit in front of every tile's accumulator wait (the top stall of the kernel: the eight epilogue warps take
-            // the tiles one after the other, so whatever a tile waits for is paid per tile)
-            float nb_next[2];
+            // this warp's 128 column norms of a tile travel one tile ahead in registers (their L2 round trip used to sit in
+            // front of every tile's accumulator wait)
+            float nb_next[4];
             auto load_norms = [&](int nt) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int col = nt * kN + half * 64 + t * 32 + lane;
+                for (int t = 0; t < 4; ++t) {
+                    const int col = nt * kN + half * 128 + t * 32 + lane;
                     nb_next[t] = (a.bnorm && nt < nt1 && col < a.nB) ? __ldg(a.bnorm + col) : 0.0f;
                 }
             };
             load_norms(nt0);
             for (int nt = nt0; nt < nt1 && ok; ++nt) {
                 // stage the norms (private copy per warp: no CTA-level barrier needed), start the next tile's loads
-                float* bn = s_bn + ((warp - 2) * 2 + acc) * 64;
-                bn[lane] = nb_next[0];
-                bn[32 + lane] = nb_next[1];
+                float* bn = s_bn + ((warp - 2) * 2 + acc) * 128;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) bn[t * 32 + lane] = nb_next[t];
                 load_norms(nt + 1);
                 __syncwarp();
                 if (!mbar_wait(tfull + acc, aphase, a.error, a.error_host)) { ok = false; break; }
                 fence_after_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN + (uint32_t)half * 64;
-                const int colbase = nt * kN + half * 64;
                 const bool full_tile = nt * kN + kN <= a.nB;
-                unsigned long long hits = 0;                   // MODE_EMIT: this thread's 64 columns with S~ <= T
-                // both 32-column loads of this thread's strip are in flight together (one TMEM round trip per tile, not two)
-                uint32_t vraw[2][32];
-                tmem_ld32_issue(taddr, vraw[0]);
-                tmem_ld32_issue(taddr + 32, vraw[1]);
-                tmem_ld32_wait(vraw[0], vraw[1]);
+                unsigned long long hits[2] = {0ull, 0ull};     // MODE_EMIT: this thread's columns with S~ <= T, per round
+#pragma unroll 1
+                for (int rd = 0; rd < 2; ++rd) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kN + (uint32_t)half * 128 +
+                                           (uint32_t)rd * 64;
+                    const int colbase = nt * kN + half * 128 + rd * 64;
+                    uint32_t vraw[2][32];
+                    tmem_ld32_issue(taddr, vraw[0]);
+                    tmem_ld32_issue(taddr + 32, vraw[1]);
+                    tmem_ld32_wait(vraw[0], vraw[1]);
 #pragma unroll
-                for (int ck = 0; ck < 2; ++ck) {
-                    float v[32];
+                    for (int ck = 0; ck < 2; ++ck) {
+                        float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vraw[ck][i]);
-                    const float4* bn4 = reinterpret_cast<const float4*>(bn + ck * 32);
-                    float sc[32];
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vraw[ck][i]);
+                        const float4* bn4 = reinterpret_cast<const float4*>(bn + rd * 64 + ck * 32);
+                        float sc[32];
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const float4 nb = (METRIC == VIX_METRIC_L2) ? bn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 nb = (METRIC == VIX_METRIC_L2) ? bn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = 4 * i4 + u;
-                            sc[i] = (METRIC == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], nbv[u]) : -v[i];
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = 4 * i4 + u;
+                                sc[i] = (METRIC == VIX_METRIC_L2) ? fmaf(-2.0f, v[i], nbv[u]) : -v[i];
+                            }
                         }
-                    }
-                    if (!full_tile) {                              // last column tile only: mask the columns beyond nB
+                        if (!full_tile) {                          // last column tile only: mask the columns beyond nB
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (colbase + ck * 32 + i >= a.nB) sc[i] = INFINITY;
-                    }
-                    if (MODE == MODE_WRITE) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int col = colbase + ck * 32 + i;
-                            if (row_ok && col < a.nB) a.out[row * a.nB + col] = sc[i];
+                            for (int i = 0; i < 32; ++i)
+                                if (colbase + ck * 32 + i >= a.nB) sc[i] = INFINITY;
                         }
-                    } else if (MODE == MODE_MIN) {
-                        // tree minimum of the 32 columns
+                        if (MODE == MODE_WRITE) {
 #pragma unroll
-                        for (int w2 = 16; w2 > 0; w2 >>= 1)
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = colbase + ck * 32 + i;
+                                if (row_ok && col < a.nB) a.out[row * a.nB + col] = sc[i];
+                            }
+                        } else if (MODE == MODE_MIN) {
+                            // tree minimum of the 32 columns
 #pragma unroll
-                            for (int i = 0; i < w2; ++i) sc[i] = fminf(sc[i], sc[i + w2]);
-                        gmin = fminf(gmin, sc[0]);
-                        // group boundary.  gcols 32 / 64: groups are whole chunks / half-tile strips of this thread;
-                        // gcols = 128 t: a group is this thread's 64-column strip of t consecutive tiles (the two
-                        // column halves of a tile belong to different groups: any disjoint partition is valid)
-                        bool flush;
-                        int g;
-                        if (a.gcols < kN) {                       // gcols and tiles-per-group are powers of two
-                            const int colend = colbase + ck * 32 + 32;
-                            flush = (colend & (a.gcols - 1)) == 0;
-                            g = (colend - 1) >> a.gshift;
+                            for (int w2 = 16; w2 > 0; w2 >>= 1)
+#pragma unroll
+                                for (int i = 0; i < w2; ++i) sc[i] = fminf(sc[i], sc[i + w2]);
+                            gmin = fminf(gmin, sc[0]);
+                            // group boundary.  gcols 32 / 64 / 128: groups are whole chunks / rounds / the 128-column strip of
+                            // this thread; gcols = 256 t: a group is this thread's strip of t consecutive tiles (the two
+                            // column halves of a tile belong to different groups: any disjoint partition is valid)
+                            bool flush;
+                            int g;
+                            if (a.gcols < kN) {                   // gcols and tiles-per-group are powers of two
+                                const int colend = colbase + ck * 32 + 32;
+                                flush = (colend & (a.gcols - 1)) == 0;
+                                g = (colend - 1) >> a.gshift;
+                            } else {
+                                flush = rd == 1 && ck == 1 && (((nt + 1) & ((1 << a.gshift) - 1)) == 0 || nt == a.ntiles - 1);
+                                g = (nt >> a.gshift) * 2 + half;
+                            }
+                            if (flush) {
+                                if (row_ok && g < a.ngroups) a.gmin[row * a.ngroups + g] = gmin;
+                                gmin = INFINITY;
+                            }
                         } else {
-                            flush = ck == 1 && (((nt + 1) & ((1 << a.gshift) - 1)) == 0 || nt == a.ntiles - 1);
-                            g = (nt >> a.gshift) * 2 + half;
-                        }
-                        if (flush) {
-                            if (row_ok && g < a.ngroups) a.gmin[row * a.ngroups + g] = gmin;
-                            gmin = INFINITY;
-                        }
-                    } else {
-                        uint32_t hit = 0;                          // columns of this chunk with S~ <= T
+                            uint32_t hit = 0;                      // columns of this chunk with S~ <= T
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) hit |= (sc[i] <= thr) ? (1u << i) : 0u;
-                        hits |= (unsigned long long)hit << (32 * ck);
+                            for (int i = 0; i < 32; ++i) hit |= (sc[i] <= thr) ? (1u << i) : 0u;
+                            hits[rd] |= (unsigned long long)hit << (32 * ck);
+                        }
                     }
                 }
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty + acc);      // 4 arrivals free the accumulator
+                if (lane == 0) mbar_arrive(tempty + acc);      // 8 arrivals free the accumulator
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
-                if (MODE == MODE_EMIT && hits) {
+                if (MODE == MODE_EMIT && (hits[0] | hits[1])) {
                     // emission AFTER the accumulator has been handed back, one counter update per thread and tile: the
-                    // round trip of the global atomic (rare hits: ~1.2 k per row in the whole matrix) used to sit
+                    // round trip of the global atomic (rare hits: a few hundred per row in the whole matrix) used to sit
                     // between the TMEM read and the release, once per hit
-                    int pos = atomicAdd(a.cand_cnt + row, __popcll(hits));
-                    while (hits) {
-                        const int i = __ffsll((long long)hits) - 1;
-                        hits &= hits - 1;
-                        if (pos < a.cap) a.cand_idx[row * a.cap + pos] = colbase + i;
-                        ++pos;
+                    int pos = atomicAdd(a.cand_cnt + row, __popcll(hits[0]) + __popcll(hits[1]));
+#pragma unroll
+                    for (int rd = 0; rd < 2; ++rd) {
+                        unsigned long long h = hits[rd];
+                        const int colbase = nt * kN + half * 128 + rd * 64;
+                        while (h) {
+                            const int i = __ffsll((long long)h) - 1;
+                            h &= h - 1;
+                            if (pos < a.cap) a.cand_idx[row * a.cap + pos] = colbase + i;
+                            ++pos;
+                        }
                     }
                 }
             }
@@ -476,23 +488,24 @@ bool supported(int64_t nA, int64_t nB, int d, const float* A, const float* B) {
 }
 
 // rows resident (ARES) when both A buffers and the B ring fit: d <= 128
-static bool a_resident(int kblocks) { return kblocks <= 4 && getenv("VIX_TC_NO_ARES") == nullptr; }
+// (d <= 96: both A buffers + three 32 KB B stages; at d = 128 only two B stages would be left, so A streams there)
+static bool a_resident(int kblocks) { return kblocks <= 3 && getenv("VIX_TC_NO_ARES") == nullptr; }
 static int ring_stages(int kblocks) {
     if (!a_resident(kblocks)) return kStages;
-    const size_t left = 227 * 1024 - 8 * 1024 - (size_t)2 * kblocks * kM * kKB * 4;
-    const int n = (int)(left / ((size_t)kM * kKB * 4));
+    const size_t left = 227 * 1024 - 12 * 1024 - (size_t)2 * kblocks * kM * kKB * 4;
+    const int n = (int)(left / ((size_t)kN * kKB * 4));
     return n > kStagesMax ? kStagesMax : n;
 }
 static size_t smem_bytes(int kblocks) {
-    const size_t ring = a_resident(kblocks) ? (size_t)2 * kblocks * kM * kKB * 4 + (size_t)ring_stages(kblocks) * kM * kKB * 4
+    const size_t ring = a_resident(kblocks) ? (size_t)2 * kblocks * kM * kKB * 4 + (size_t)ring_stages(kblocks) * kN * kKB * 4
                                             : (size_t)kStages * kStageBytes;
-    return ring + 1024 + 512 + (size_t)kEpiWarps * 2 * 64 * 4;
+    return ring + 1024 + 512 + (size_t)kEpiWarps * 2 * 128 * 4;
 }
 
 static int launch(const float* A, int64_t nA, const float* B, int nB, int d, Args& a) {
     CUtensorMap mapA, mapB;
     VIX_TRY(make_map(&mapA, A, nA, d));
-    VIX_TRY(make_map(&mapB, B, nB, d));
+    VIX_TRY(make_map_rows(&mapB, B, nB, d, kN));
     a.nA = nA; a.nB = nB;
     a.kblocks = (d + kKB - 1) / kKB;
     a.ntiles = (nB + kN - 1) / kN;
