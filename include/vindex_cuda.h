@@ -171,6 +171,10 @@ typedef struct {
     bool strict_fp;         /* scalar sequential sums instead of the 8-lane order (strictFP)             */
 } vix_pq_lut_opts;
 
+/* pq_query_subnorms_f32 (PQLUT.swift:174-187): out[q][j] = ||q_j||^2 in the LUT kernels' own reduction order (_simd_dot),
+ * for nq queries at once; computed once and reused across the LUTs of a query's probed lists. */
+int vix_pq_query_subnorms_f32(const float* queries, int64_t nq, int d, int m, float* out /* [nq x m] */);
+
 /* pq_lut_batch_l2_f32 (PQLUT.swift:392-465) / pq_lut_l2_f32 (:191-261) for nq queries:
  * luts[nq x m x ks]. */
 int vix_pq_lut_batch_l2_f32(const float* queries, int64_t nq, int d, int m, int ks,

@@ -526,6 +526,24 @@ def test_accel_rank_candidates_equals_flat_search(oracle, vk, metric, c, d, nq, 
 
 
 # ------------------------------------------------------------------------------------------------ LUT + ADC
+def test_pq_query_subnorms(oracle, vk):
+    """pq_query_subnorms_f32 (PQLUT.swift:174-187): ||q_j||^2 in the LUT kernels' reduction order, bit for bit; feeding them
+    to the oracle's pq_lut_l2 (its qSubNorms argument) reproduces the table the CUDA library builds on its own."""
+    rng = np.random.default_rng(174)
+    for d, m in ((128, 16), (96, 48), (768, 64), (40, 4)):
+        q = rng.standard_normal((7, d)).astype(np.float32)
+        got = vk.pq_query_subnorms_f32(q, m)
+        dsub = d // m
+        want = np.array([[oracle.lut_dot(q[i, j * dsub:(j + 1) * dsub], q[i, j * dsub:(j + 1) * dsub]) for j in range(m)]
+                         for i in range(q.shape[0])], dtype=np.float32)
+        assert np.array_equal(bits(got), bits(want))
+        cb = rng.standard_normal(m * 256 * dsub).astype(np.float32)
+        cn = oracle.pq_centroid_sq(cb, m, 256, dsub, swift=False)
+        lut = vk.pq_lut_batch_l2_f32(q, cb, m, 256, cn)
+        for i in range(q.shape[0]):
+            assert np.array_equal(bits(lut[i]), bits(oracle.pq_lut_l2(q[i], cb, m, 256, cn, q_sub_norms=got[i])))
+
+
 def test_fused_residual_lut_equals_lut_of_materialised_residual(oracle, vk):
     """ResidualKernelTests.swift:208-270: pq_lut_residual_l2_f32(q, c) == pq_lut_l2_f32(q - c) -- on the CUDA library, and
     both equal to the oracle's tables bit for bit (reference shape d 512, m 8, ks 256, plus a batch of residual shapes)."""

@@ -252,7 +252,34 @@ static int lut_entry(const char* fn, const float* queries, const int32_t* coarse
 
 using namespace vix;
 
+namespace vix {
+// pq_query_subnorms_f32 (PQLUT.swift:174-187): out[q][j] = _simd_dot(q_j, q_j, dsub), the LUT kernels' own reduction
+__global__ void query_subnorms_kernel(const float* __restrict__ q, int64_t total, int m, int dsub, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (query, sub-space)
+    if (i >= total) return;
+    const float* qj = q + i * dsub;                                        // rows are contiguous: q[(query * m + j) * dsub]
+    out[i] = exact_pair<SpecLut8Dot>(qj, qj, dsub);
+    (void)m;
+}
+}  // namespace vix
+
 extern "C" {
+
+int vix_pq_query_subnorms_f32(const float* queries, int64_t nq, int d, int m, float* out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(queries && out, VIX_ERR_NULL_PTR, "vix_pq_query_subnorms_f32: null pointer");
+    VIX_REQUIRE(d > 0 && m > 0 && d % m == 0, VIX_ERR_INVALID_DIM, "vix_pq_query_subnorms_f32: d must be divisible by m");
+    if (nq <= 0) return VIX_OK;
+    In<float> dq;
+    Out<float> dout;
+    VIX_TRY(dq.stage(queries, (size_t)nq * d));
+    VIX_TRY(dout.stage(out, (size_t)nq * m));
+    const int64_t total = nq * (int64_t)m;
+    query_subnorms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(dq.dev, total, m, d / m, dout.dev);
+    VIX_LAUNCH_CHECK();
+    VIX_TRY(dout.commit());
+    return finish(dout.is_host());
+}
 
 int vix_pq_lut_batch_l2_f32(const float* queries, int64_t nq, int d, int m, int ks, const float* codebooks,
                             float* luts, const float* centroid_norms, const vix_pq_lut_opts* opts) {

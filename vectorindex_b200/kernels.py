@@ -271,6 +271,15 @@ def ivf_assign_metric_f32(x, centroids, metric, centroid_norms=None):
 
 
 # ------------------------------------------------------------------------------------------------ LUT / ADC
+def pq_query_subnorms_f32(queries, m):
+    """``pq_query_subnorms_f32`` (PQLUT.swift:174-187) for a batch: [nq x m] squared norms of the query sub-vectors."""
+    queries = as_input(queries, np.float32)
+    nq, d = _shape2(queries)
+    out = empty_like_input(queries, (nq, m), np.float32)
+    check(lib().vix_pq_query_subnorms_f32(ptr(queries, np.float32), C.c_int64(nq), C.c_int(d), C.c_int(m), ptr(out, np.float32)))
+    return out
+
+
 def pq_lut_batch_l2_f32(queries, codebooks, m, ks=256, centroid_norms=None, opts: PQLutOpts | None = None):
     queries, codebooks = as_input(queries, np.float32), as_input(codebooks, np.float32)
     nq, d = _shape2(queries)
