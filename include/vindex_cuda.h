@@ -246,6 +246,15 @@ int vix_pq_train_f32(const float* x, int64_t n, int d, int m, int ks, const floa
                      const int32_t* assignments, const vix_pq_train_cfg* cfg, float* codebooks_out,
                      float* centroid_norms_out);
 
+/* pq_train_streaming_f32 (Kernels/PQTrain.swift:391-706): the mini-batch trainer over `nchunks` row blocks that the host
+ * hands over one pointer each (host or device, valid for the call; no residual form).  Reference parity only (the
+ * reference's RNG streams, per-chunk permutations, Bernoulli row sampling, running-mean blend and pass-level repair are
+ * replayed; distances and argmins run on the GPU): bit-identical codebooks, incl. the reference's own golden vector
+ * (Tests/VectorIndexTests/PQTrainTests.swift:724-817).  Defaults as the reference: max_iters 15, batch_size 8192,
+ * sample_n 2000 when more rows are given. */
+int vix_pq_train_streaming_f32(const float* const* chunks, const int64_t* chunk_n, int nchunks, int d, int m, int ks,
+                               const vix_pq_train_cfg* cfg, float* codebooks_out, float* centroid_norms_out /* nullable */);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* a15  Index handles: build / train / add / search with device-resident state.                     */
 /* Mirrors VectorIndexProtocol (IndexProtocols.swift:50-103) for FlatIndex(Optimized), IVFIndex     */

@@ -1267,6 +1267,50 @@ def test_pq_train_parity(oracle, vk, n, d, m, ks, algo, policy, residual, sample
     assert np.array_equal(bits(gnorm), bits(onorm))
 
 
+def test_pq_train_streaming_reference_golden_bits(oracle, vk):
+    """pq_train_streaming_f32 on the GPU reproduces the reference's OWN golden vector (PQTrainTests.swift:724-817: ks 16,
+    d 16, m 2, 40 LCG rows in two chunks, seed 42, mini-batch, 10 passes, batch 512 => the bit patterns of codebooks[0..3])
+    and the oracle's codebooks bit for bit -- from host chunks and from device chunks."""
+    import torch
+    from vectorindex_b200 import datagen
+    ks, d, m, n = 16, 16, 2, 40
+    full = datagen.lcg24_floats(0x5773_7EA1_1234_5678, n * d)[0].reshape(n, d)
+    chunks = [np.ascontiguousarray(full[:20]), np.ascontiguousarray(full[20:])]
+    cfg = vk.pq_train_cfg(algorithm=1, max_iters=10, batch_size=512, seed=42, mode=0)
+    cb, norms = vk.pq_train_streaming_f32(chunks, m, ks, cfg)
+    want = np.array([0.7648039, -0.5310464, -0.7147653, 0.30723625], dtype=np.float32)
+    assert bits(cb.reshape(-1)[:4]).tolist() == bits(want).tolist()
+    rc, ocb = oracle.pq_train_streaming(chunks, d, m, ks, seed=42, algorithm=1, max_iters=10, batch_size=512)
+    assert rc == 0 and np.array_equal(bits(cb), bits(ocb))
+    cb2, _ = vk.pq_train_streaming_f32([torch.from_numpy(c).cuda() for c in chunks], m, ks, cfg)
+    assert np.array_equal(bits(cb2), bits(cb))
+    seq = np.zeros((m, ks), dtype=np.float32)                              # centroid norms: sequential sum of squares (PQTrain.swift:299-307)
+    for u in range(d // m):
+        seq = (seq + cb[:, :, u] * cb[:, :, u]).astype(np.float32)
+    assert np.array_equal(bits(norms), bits(seq))
+
+
+@pytest.mark.parametrize("sizes,d,m,ks,iters,batch,sample_n", [
+    ((700, 0, 1300, 450), 32, 4, 64, 3, 256, 0),       # more rows than 2000: Bernoulli sampling (sample_n forced to 2000), subset seeding
+    ((300, 260), 24, 3, 256, 3, 128, 0),               # fewer rows than 4 ks: streaming seeding; empty clusters -> pass-level repair
+    ((900, 900, 900), 16, 2, 32, 2, 8192, 1000),       # explicit sample, default batch (one batch per chunk)
+])
+def test_pq_train_streaming_parity(oracle, vk, sizes, d, m, ks, iters, batch, sample_n):
+    """Streaming trainer against the oracle on ragged chunk lists (one of them empty): per-chunk permutations, row sampling,
+    blend, repair -- codebooks bit-identical (PQTrain.swift:391-706, 1444-1575)."""
+    rng = np.random.default_rng(sum(sizes) + ks)
+    chunks = [(rng.standard_normal((n, d)) + 2 * rng.standard_normal((5, d))[rng.integers(0, 5, n)]).astype(np.float32) for n in sizes]
+    rc, ocb = oracle.pq_train_streaming(chunks, d, m, ks, seed=7, stream_id=3, algorithm=1, max_iters=iters, batch_size=batch,
+                                        sample_n=sample_n)
+    assert rc == 0
+    cfg = vk.pq_train_cfg(algorithm=1, max_iters=iters, batch_size=batch, sample_n=sample_n, seed=7, stream_id=3, mode=0)
+    gcb, gnorm = vk.pq_train_streaming_f32(chunks, m, ks, cfg)
+    assert np.array_equal(bits(gcb), bits(ocb))
+    from vectorindex_b200 import VectorIndexError
+    with pytest.raises(VectorIndexError):
+        vk.pq_train_streaming_f32([chunks[0][:ks - 1]], m, ks, cfg)      # fewer rows than centroids (PQTrain.swift:127-135)
+
+
 def test_gpu_training_builds_a_working_index(oracle):
     """mode-1 trainers (deterministic Lloyd): the trained IVF-PQ index reaches a sane recall and two
     trainings give bit-identical parameters (rank-to-rank reproducibility for the sharded build)."""

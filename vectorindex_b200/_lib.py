@@ -85,7 +85,7 @@ _EXPORTS = [
     "vix_l2sqr_f32_block", "vix_ip_f32_block", "vix_row_norms_f32", "vix_flat_search_f32", "vix_select_topk_f32",
     "vix_merge_topk_f32", "vix_rerank_exact_topk_f32", "vix_centroid_batch_score_f32", "vix_ivf_select_nprobe_batch_f32", "vix_ivf_assign_f32",
     "vix_ivf_assign_metric_f32", "vix_pq_query_subnorms_f32", "vix_pq_lut_batch_l2_f32", "vix_pq_lut_residual_l2_f32", "vix_adc_scan_u8",
-    "vix_adc_scan_u4", "vix_kmeanspp_seed_f32", "vix_kmeans_minibatch_f32", "vix_pq_train_f32",
+    "vix_adc_scan_u4", "vix_kmeanspp_seed_f32", "vix_kmeans_minibatch_f32", "vix_pq_train_f32", "vix_pq_train_streaming_f32",
     "vix_index_params_default", "vix_index_create", "vix_index_destroy", "vix_index_train", "vix_index_set_coarse",
     "vix_index_set_codebooks", "vix_index_get_coarse", "vix_index_get_codebooks", "vix_index_add",
     "vix_index_import_lists", "vix_index_count", "vix_index_list_sizes", "vix_index_export_lists", "vix_index_clear",

@@ -379,6 +379,8 @@ int kmeans_parity_device(const float* x, int64_t n, int d, int kc, const float* 
                          float* centroids_out, int32_t* assign_out);
 int kmeanspp_parity_device(const float* x, int64_t n, int d, int k, uint64_t seed, uint64_t stream, float* centroids_out,
                            int64_t* chosen_out);
+int pq_train_streaming_parity_device(const float* X, const std::vector<int64_t>& chunk_n, int d, int m, int ks,
+                                     const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
 int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, const float* coarse, const int32_t* assign,
                            const vix_pq_train_cfg* cfg, float* codebooks_out, float* norms_out);
 
@@ -476,6 +478,41 @@ int vix_pq_train_f32(const float* x, int64_t n, int d, int m, int ks, const floa
     VIX_TRY(dn.commit());
     VIX_TRY(finish(true));
     return rc;
+}
+
+int vix_pq_train_streaming_f32(const float* const* chunks, const int64_t* chunk_n, int nchunks, int d, int m, int ks,
+                               const vix_pq_train_cfg* cfg, float* codebooks_out, float* centroid_norms_out) {
+    VIX_TRY(ensure_device());
+    VIX_REQUIRE(chunks && chunk_n && codebooks_out, VIX_ERR_NULL_PTR, "vix_pq_train_streaming_f32: null pointer");
+    VIX_REQUIRE(nchunks > 0, VIX_ERR_EMPTY_INPUT, "vix_pq_train_streaming_f32: no chunks");
+    VIX_REQUIRE(d > 0 && m > 0 && d % m == 0, VIX_ERR_INVALID_DIM, "vix_pq_train_streaming_f32: need d %% m == 0");
+    VIX_REQUIRE(ks >= 1 && ks <= 256, VIX_ERR_INVALID_K, "vix_pq_train_streaming_f32: ks must be in 1..256");
+    std::vector<int64_t> cn((size_t)nchunks);
+    int64_t total = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        VIX_REQUIRE(chunk_n[c] >= 0 && (chunk_n[c] == 0 || chunks[c]), VIX_ERR_NULL_PTR, "vix_pq_train_streaming_f32: chunk %d", c);
+        cn[(size_t)c] = chunk_n[c];
+        total += chunk_n[c];
+    }
+    VIX_REQUIRE(total >= ks, VIX_ERR_EMPTY_INPUT,
+                "vix_pq_train_streaming_f32: Insufficient training data: need at least ks vectors (%lld available, ks = %d)",
+                (long long)total, ks);
+    // the chunks (host or device, each valid for the call) laid end to end on the device
+    Scratch<float> X;
+    VIX_TRY(X.alloc((size_t)total * d));
+    int64_t at = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        if (cn[(size_t)c] == 0) continue;
+        VIX_CUDA(cudaMemcpyAsync(X.ptr + (size_t)at * d, chunks[c], (size_t)cn[(size_t)c] * d * 4, cudaMemcpyDefault, ctx().stream));
+        at += cn[(size_t)c];
+    }
+    Out<float> dcb, dn;
+    VIX_TRY(dcb.stage(codebooks_out, (size_t)ks * d));
+    VIX_TRY(dn.stage(centroid_norms_out, centroid_norms_out ? (size_t)m * ks : 0));
+    VIX_TRY(pq_train_streaming_parity_device(X.ptr, cn, d, m, ks, cfg, dcb.dev, dn.dev));
+    VIX_TRY(dcb.commit());
+    VIX_TRY(dn.commit());
+    return finish(true);
 }
 
 }  // extern "C"

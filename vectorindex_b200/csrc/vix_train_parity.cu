@@ -416,7 +416,10 @@ int launch_sub_assign(const SubSrc& src, int64_t n, const float* C, int ks, int 
 
 // k-means++ over `npts` sub-vectors of `src` (PQTrain.swift:856-1019): i0 = clamp(Int(uniform * n)); then
 // r = uniform * sum(dmin); first i with (r -= dmin[i]) <= 0; dmin updated with strict <
-int seed_subspace(const SubSrc& src, int64_t npts, int ks, int use_residual, Xoro& rng, float* C /* device [ks x dsub] */) {
+// streaming != 0: streamingKMeansppSeed (PQTrain.swift:391-706): the same draws over the chunks laid end to end, except that a
+// degenerate sum falls back to row 0 WITHOUT a draw and an exhausted walk to centroid 0
+int seed_subspace(const SubSrc& src, int64_t npts, int ks, int use_residual, Xoro& rng, float* C /* device [ks x dsub] */,
+                  int streaming = 0) {
     cudaStream_t s = ctx().stream;
     const int dsub = src.dsub;
     Scratch<float> dmin;
@@ -453,16 +456,23 @@ int seed_subspace(const SubSrc& src, int64_t npts, int ks, int use_residual, Xor
         double sum = 0.0;
         for (int64_t i = 0; i < npts; ++i) sum += (double)h[(size_t)i];
         int64_t pick;
+        bool copy_first_centroid = false;
         if (!(sum > 0)) {
-            pick = (int64_t)(rng.f64() * (double)npts);
-            if (pick < 0) pick = 0;
-            if (pick > npts - 1) pick = npts - 1;
+            if (streaming) pick = 0;
+            else {
+                pick = (int64_t)(rng.f64() * (double)npts);
+                if (pick < 0) pick = 0;
+                if (pick > npts - 1) pick = npts - 1;
+            }
         } else {
             double r = rng.f64() * sum;
             pick = npts - 1;
-            for (int64_t i = 0; i < npts; ++i) { r -= (double)h[(size_t)i]; if (r <= 0) { pick = i; break; } }
+            bool chosen = false;
+            for (int64_t i = 0; i < npts; ++i) { r -= (double)h[(size_t)i]; if (r <= 0) { pick = i; chosen = true; break; } }
+            copy_first_centroid = streaming && !chosen;
         }
-        VIX_TRY(pick_into(pick, k));
+        if (copy_first_centroid) VIX_CUDA(cudaMemcpyAsync(C + (size_t)k * dsub, C, (size_t)dsub * 4, cudaMemcpyDeviceToDevice, s));
+        else VIX_TRY(pick_into(pick, k));
         sub_dist_point_kernel<<<blocks_for(npts), 256, 0, s>>>(src, npts, C + (size_t)k * dsub, use_residual, 1, dmin.ptr);
         VIX_LAUNCH_CHECK();
     }
@@ -730,6 +740,159 @@ int pq_train_parity_device(const float* x, int64_t n, int d, int m, int ks, cons
         else VIX_TRY(lloyd_subspace(all, n, j, ks, cfg, Cj));
     }
     if (norms_out) {                                                 // :299-307 sequential sum of squares
+        std::vector<float> cb;
+        VIX_TRY(to_host(cb, codebooks_out, (size_t)m * ks * dsub));
+        std::vector<float> nr((size_t)m * ks);
+        for (size_t r = 0; r < nr.size(); ++r) {
+            float acc = 0.0f;
+            for (int u = 0; u < dsub; ++u) { const float v = cb[r * dsub + u]; acc = acc + v * v; }
+            nr[r] = acc;
+        }
+        VIX_TRY(to_device(norms_out, nr));
+    }
+    return VIX_OK;
+}
+
+// pq_train_streaming_f32 (Kernels/PQTrain.swift:391-706), no residual: X holds the chunks laid end to end on the device
+// (row (c, i) = prefix[c] + i); the chunk structure lives on in the control flow -- one permutation per chunk and pass,
+// Bernoulli sampling of the rows of a batch, the running-mean blend per batch, the pass-level repair from 512 random rows.
+int pq_train_streaming_parity_device(const float* X, const std::vector<int64_t>& chunk_n, int d, int m, int ks,
+                                     const vix_pq_train_cfg* in_cfg, float* codebooks_out, float* norms_out) {
+    cudaStream_t s = ctx().stream;
+    vix_pq_train_cfg cfg{};
+    if (in_cfg) cfg = *in_cfg;
+    else { cfg.seed = 42; }
+    cfg.algorithm = 1;
+    if (cfg.max_iters <= 0) cfg.max_iters = 15;
+    if (cfg.batch_size <= 0) cfg.batch_size = 8192;
+    const int nchunks = (int)chunk_n.size();
+    std::vector<int64_t> prefix((size_t)nchunks + 1, 0);
+    for (int c = 0; c < nchunks; ++c) prefix[(size_t)c + 1] = prefix[(size_t)c] + chunk_n[(size_t)c];
+    const int64_t total = prefix[(size_t)nchunks];
+    VIX_REQUIRE(total > 0 && total < (1LL << 31), VIX_ERR_EMPTY_INPUT, "pq_train_streaming: %lld rows", (long long)total);
+    if (cfg.sample_n <= 0 && total > 2000) cfg.sample_n = 2000;
+    const int dsub = d / m;
+    const int64_t repair_eval_n = 512;
+    const int B = cfg.batch_size > 1 ? cfg.batch_size : 1;
+    Scratch<uint32_t> d_idx;
+    Scratch<int32_t> d_bk;
+    Scratch<float> d_sub, d_md;
+    const int64_t cap_rows = std::max<int64_t>(std::max<int64_t>(B, repair_eval_n), 4LL * ks);
+    VIX_TRY(d_idx.alloc((size_t)cap_rows));
+    VIX_TRY(d_bk.alloc((size_t)cap_rows));
+    VIX_TRY(d_sub.alloc((size_t)cap_rows * dsub));
+    VIX_TRY(d_md.alloc((size_t)cap_rows));
+    std::vector<float> Ch((size_t)ks * dsub), sub_h;
+    std::vector<int32_t> bk_h;
+    for (int j = 0; j < m; ++j) {
+        Xoro rng(cfg.seed, (uint64_t)cfg.stream_id, (uint64_t)j);
+        SubSrc all{X, d, j * dsub, dsub, nullptr, nullptr, nullptr, d};
+        float* Cj = codebooks_out + (size_t)j * ks * dsub;
+        VIX_CUDA(cudaMemsetAsync(Cj, 0, (size_t)ks * dsub * 4, s));
+        const int64_t cap = 4LL * ks;
+        if (total > cap) {                                           // seed on a sample of 4 ks rows (dense copy)
+            std::vector<uint32_t> picks;
+            const int64_t got = sample_wo_repl((uint32_t)total, (uint32_t)cap, rng, picks);
+            (void)got;
+            VIX_TRY(to_device(d_idx.ptr, picks));
+            SubSrc sub = all;
+            sub.idx = d_idx.ptr;
+            sub_gather_kernel<<<blocks_for(cap * dsub), 256, 0, s>>>(sub, cap, 0, d_sub.ptr);
+            VIX_LAUNCH_CHECK();
+            SubSrc dn{d_sub.ptr, dsub, 0, dsub, nullptr, nullptr, nullptr, 0};
+            VIX_TRY(seed_subspace(dn, cap, ks, 0, rng, Cj));         // kmeansppSeedSubspaceDense
+        } else {
+            VIX_TRY(seed_subspace(all, total, ks, 0, rng, Cj, 1));   // streamingKMeansppSeed
+        }
+        std::vector<int64_t> gcounts((size_t)ks, 0), counts((size_t)ks);
+        std::vector<double> sums((size_t)ks * dsub);
+        for (int pass = 0; pass < cfg.max_iters; ++pass) {
+            const int64_t limit = cfg.sample_n > 0 ? std::min<int64_t>(total, cfg.sample_n) : total;
+            double prob = (double)limit / (double)(total > 1 ? total : 1);
+            if (prob < 0.0) prob = 0.0;
+            if (prob > 1.0) prob = 1.0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int64_t nc = chunk_n[(size_t)c];
+                if (nc <= 0) continue;
+                std::vector<uint32_t> idx((size_t)nc);               // minibatchKMeansSubspaceChunk (:1444-1575)
+                for (int64_t i = 0; i < nc; ++i) idx[(size_t)i] = (uint32_t)i;
+                randperm(idx, rng);
+                for (int64_t sb = 0; sb < nc;) {
+                    const int64_t e = std::min<int64_t>(sb + B, nc);
+                    std::vector<uint32_t> rows;
+                    for (int64_t t = sb; t < e; ++t) {
+                        if (prob < 1.0) { const double u = rng.f64(); if (u > prob) continue; }
+                        rows.push_back((uint32_t)(prefix[(size_t)c] + idx[(size_t)t]));
+                    }
+                    sb = e;
+                    const int64_t bc = (int64_t)rows.size();
+                    if (bc == 0) continue;                           // (a batch without rows blends nothing)
+                    VIX_TRY(to_device(d_idx.ptr, rows));
+                    SubSrc sub = all;
+                    sub.idx = d_idx.ptr;
+                    VIX_TRY(launch_sub_assign(sub, bc, Cj, ks, 0, d_bk.ptr, nullptr));
+                    sub_gather_kernel<<<blocks_for(bc * dsub), 256, 0, s>>>(sub, bc, 0, d_sub.ptr);
+                    VIX_LAUNCH_CHECK();
+                    VIX_TRY(to_host(bk_h, d_bk.ptr, (size_t)bc));
+                    VIX_TRY(to_host(sub_h, d_sub.ptr, (size_t)bc * dsub));
+                    VIX_TRY(to_host(Ch, Cj, (size_t)ks * dsub));
+                    std::fill(sums.begin(), sums.end(), 0.0);
+                    std::fill(counts.begin(), counts.end(), 0);
+                    for (int64_t t = 0; t < bc; ++t) {
+                        double* sk = sums.data() + (size_t)bk_h[(size_t)t] * dsub;
+                        for (int u = 0; u < dsub; ++u) sk[u] += (double)sub_h[(size_t)t * dsub + u];
+                        counts[(size_t)bk_h[(size_t)t]] += 1;
+                    }
+                    for (int k = 0; k < ks; ++k) {                  // running-mean blend
+                        const int64_t ck = counts[(size_t)k];
+                        if (ck <= 0) continue;
+                        const int64_t old_n = gcounts[(size_t)k], new_n = old_n + ck;
+                        gcounts[(size_t)k] = new_n;
+                        const double old_w = (double)old_n / (double)new_n, new_w = (double)ck / (double)new_n;
+                        for (int u = 0; u < dsub; ++u) {
+                            const double old_val = (double)Ch[(size_t)k * dsub + u];
+                            const double batch_mean = sums[(size_t)k * dsub + u] / (double)ck;
+                            const float v = (float)(old_w * old_val + new_w * batch_mean);
+                            Ch[(size_t)k * dsub + u] = std::isfinite(v) ? v : 0.0f;
+                        }
+                    }
+                    VIX_TRY(to_device(Cj, Ch));
+                }
+            }
+            // pass-level repair (:543-640): clusters that never received anything take the farthest of 512 random rows
+            std::vector<int> empties;
+            for (int k = 0; k < ks; ++k) if (gcounts[(size_t)k] == 0) empties.push_back(k);
+            if (!empties.empty()) {
+                const int64_t eval_n = std::min<int64_t>(total, repair_eval_n);
+                std::vector<uint32_t> rows((size_t)eval_n);
+                for (int64_t t = 0; t < eval_n; ++t) {
+                    int64_t g = (int64_t)(rng.f64() * (double)total);
+                    // the reference walks the chunks with the last one open-ended: a draw of exactly `total` lands past its end
+                    if (g > total - 1) g = total - 1;
+                    rows[(size_t)t] = (uint32_t)g;
+                }
+                VIX_TRY(to_device(d_idx.ptr, rows));
+                SubSrc sub = all;
+                sub.idx = d_idx.ptr;
+                VIX_TRY(launch_sub_assign(sub, eval_n, Cj, ks, 0, nullptr, d_md.ptr));
+                std::vector<float> md_h;
+                VIX_TRY(to_host(md_h, d_md.ptr, (size_t)eval_n));
+                std::vector<OrdT> o((size_t)eval_n);
+                for (int64_t t = 0; t < eval_n; ++t) o[(size_t)t] = OrdT{md_h[(size_t)t], t};
+                std::stable_sort(o.begin(), o.end(), ord_less);
+                std::vector<int64_t> src_rows;
+                std::vector<int> ksl;
+                for (size_t r = 0; r < empties.size() && (int64_t)r < eval_n; ++r) {
+                    src_rows.push_back((int64_t)rows[(size_t)o[r].i]);
+                    ksl.push_back(empties[r]);
+                    gcounts[(size_t)empties[r]] = 1;
+                }
+                VIX_TRY(copy_raw_rows(X, d, j * dsub, dsub, src_rows, ksl, Cj));
+            }
+        }
+    }
+    VIX_CUDA(cudaStreamSynchronize(s));
+    if (norms_out) {
         std::vector<float> cb;
         VIX_TRY(to_host(cb, codebooks_out, (size_t)m * ks * dsub));
         std::vector<float> nr((size_t)m * ks);

@@ -383,6 +383,24 @@ def pq_train_f32(x, m, ks=256, coarse_centroids=None, assignments=None, cfg: PQT
     return cb, norms
 
 
+def pq_train_streaming_f32(chunks, m, ks=256, cfg=None):
+    """``pq_train_streaming_f32`` (Kernels/PQTrain.swift:391-706): mini-batch PQ training over row blocks handed over one
+    by one (numpy arrays or CUDA tensors, [n_c x d] each); reference parity.  Returns (codebooks [m x ks x dsub], norms)."""
+    chunks = [as_input(c, np.float32) for c in chunks]
+    if not chunks:
+        raise VectorIndexError(-7, "pq_train_streaming_f32: empty input")
+    d = int(chunks[0].shape[1])
+    if m <= 0 or d % m != 0:
+        raise VectorIndexError(-1, "pq_train_streaming_f32: d must be divisible by m")
+    ptrs = (C.c_void_p * len(chunks))(*[ptr(c, np.float32).value or 0 for c in chunks])
+    cn = (C.c_int64 * len(chunks))(*[int(c.shape[0]) for c in chunks])
+    cb = np.empty((m, ks, d // m), dtype=np.float32)
+    norms = np.empty((m, ks), dtype=np.float32)
+    check(lib().vix_pq_train_streaming_f32(ptrs, cn, C.c_int(len(chunks)), C.c_int(d), C.c_int(m), C.c_int(ks), _opts_ptr(cfg),
+                                           ptr(cb, np.float32), ptr(norms, np.float32)))
+    return cb, norms
+
+
 def accel_rank_candidates(queries, candidates, k, metric=METRIC_L2):
     """AccelerableIndex-shaped hand-off (AccelerableIndex.swift:15-127): candidates [c x d] in,
     (indices into candidates, distances) out, per query."""
