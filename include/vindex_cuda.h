@@ -85,6 +85,8 @@ int         vix_set_async(int enabled);      /* 1: do not synchronise when all o
 int         vix_get_async(void);             /* the calling thread's current setting (0 / 1)        */
 int         vix_synchronize(void);           /* wait for the calling thread's stream               */
 int64_t     vix_kernel_launches(int reset);  /* kernels launched by this thread (bench bookkeeping) */
+int64_t     vix_scan_tc_launches(void);      /* IVF-PQ searches of this process that took the list-major tensor-core
+                                                scan (csrc/vix_ivfpq_tc.cu) rather than the query-major one (tests, bench) */
 
 /* ------------------------------------------------------------------------------------------------ */
 /* a1-a3  Flat scoring.  Replaces @_cdecl l2sqr_f32_block / ip_f32_block                            */

@@ -734,6 +734,39 @@ def test_two_pipeline_scan_equals_one_pipeline(oracle, monkeypatch, d, m, metric
     assert np.array_equal(i1, i2) and np.array_equal(bits(d1), bits(d2))
 
 
+@pytest.mark.parametrize("d,m,n,kc,nq,nprobe,k,kind", [
+    (96, 48, 60000, 64, 600, 12, 10, "unit"),      # C5-shaped: three groups of 16 sub-quantisers (the last one read through its replica)
+    (32, 16, 30000, 40, 300, 8, 10, "gauss"),      # one group
+    (64, 32, 30000, 48, 257, 10, 5, "gauss"),      # two groups
+    (128, 64, 30000, 32, 300, 6, 32, "gauss"),     # four groups, two K-atoms, k = 32
+    (96, 48, 3000, 200, 300, 40, 10, "gauss"),     # tiny lists (many below k vectors: their queries are handed back), 15 per list
+    (96, 48, 40000, 24, 1500, 24, 10, "unit"),     # nprobe == kc and > 64 queries per list: several column groups per list
+    (96, 48, 20000, 32, 200, 8, 1, "sift"),        # k = 1, integer-valued data with heavy ties
+])
+def test_list_major_tensor_core_scan_equals_query_major_scan(oracle, monkeypatch, d, m, n, kc, nq, nprobe, k, kind):
+    """vix_ivfpq_tc.cu (decode once per list, fp16 tensor-core shortlist, finalists in the look-up-table scan's arithmetic)
+    returns the ids AND the distance bits of vix_ivfpq_scan.cu, which the other tests pin to the oracle at 1e-5."""
+    from vectorindex_b200 import _lib
+    from vectorindex_b200.index import IVFPQIndex
+    xb, q, coarse, cb, norms = _make_ivfpq_problem(oracle, n, d, m, kc, nq, seed=d + m + k + n, sift=kind == "sift", unit=kind == "unit")
+    idx = IVFPQIndex(d, "euclidean", nlist=kc, nprobe=nprobe, m=m)
+    idx.set_coarse(coarse); idx.set_codebooks(cb, norms)
+    idx.batch_insert(xb)
+    monkeypatch.setenv("VIX_TC_SCAN", "0")
+    before = _lib.lib().vix_scan_tc_launches()
+    d1, i1 = idx.batch_search(q, k)
+    assert _lib.lib().vix_scan_tc_launches() == before
+    monkeypatch.setenv("VIX_TC_SCAN", "1")
+    d2, i2 = idx.batch_search(q, k)
+    assert _lib.lib().vix_scan_tc_launches() == before + 1
+    assert np.array_equal(i1, i2)
+    assert np.array_equal(bits(d1), bits(d2))
+    # and the oracle (the reference's composition) on the first queries, as for the query-major scan
+    off, codes, lids, _ = idx.export_lists()
+    od, oi, _ = oracle.ivfpq_search(q[:48], coarse, cb, norms, off, codes, lids, m, 256, nprobe, k, 0)
+    assert_topk_close(d2[:48], i2[:48], od, oi, rtol=RTOL, atol=0.0)
+
+
 def test_sharded_pieces_emulated_on_one_gpu(oracle):
     """Two list-block shards built and searched in ONE process (the ranks emulated sequentially, the collectives
     replaced by concatenation): probe_range + merge == the single index's probe lists, search_with_probes + merge

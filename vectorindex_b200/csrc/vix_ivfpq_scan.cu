@@ -44,6 +44,7 @@
 #include "vix_common.cuh"
 #include "vix_topk.cuh"
 #include "vix_scan.cuh"
+#include "vix_scan_select.cuh"
 
 namespace vix {
 
@@ -154,84 +155,6 @@ __device__ VIX_SCAN_FN uint32_t warp_kth_smallest(uint32_t v, int kth, int lane)
     return __shfl_sync(0xFFFFFFFFu, v, kth);
 }
 
-// ---- per-query prologue / epilogue pieces, kept out of line so that the scan loop owns the registers ----
-
-// warp 0: the k best of the n published candidates.  Keys are unique, so "the smallest key greater than the
-// last one taken" walks them in order.  Up to 512 candidates live in registers (16 per lane); each of the k
-// rounds is a lane-local minimum over the registers plus two warp REDUX steps.
-__device__ __forceinline__ void write_result(u64 mn, int order_max, size_t o, float* __restrict__ out_dist,
-                                             int64_t* __restrict__ out_ids) {
-    if (mn == kEmptyKey) { out_dist[o] = __int_as_float(0x7fc00000); out_ids[o] = -1; }
-    else {
-        const float sc = key_score(mn, order_max);
-        out_dist[o] = order_max ? -sc : sc;   // IP: API distance = -score (DistanceUtils.swift:40-46)
-        out_ids[o] = (int64_t)key_id(mn);
-    }
-}
-
-__device__ VIX_SCAN_FN void select_and_write(const u64* __restrict__ s_cand, int n, int k, int order_max, int64_t qi,
-                                             float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
-    const int lane = threadIdx.x & 31;
-    if (n <= 512) {
-        constexpr int R = 16;
-        uint32_t kh[R], kl[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int t = lane + 32 * r;
-            const u64 key = (t < n) ? s_cand[t] : kEmptyKey;
-            kh[r] = (uint32_t)(key >> 32); kl[r] = (uint32_t)key;
-        }
-        for (int i = 0; i < k; ++i) {
-            uint32_t mh = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const bool less = kh[r] < mh || (kh[r] == mh && kl[r] < ml);
-                mh = less ? kh[r] : mh; ml = less ? kl[r] : ml;
-            }
-            const uint32_t gh = __reduce_min_sync(0xFFFFFFFFu, mh);
-            const uint32_t gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
-            // ONE owner retires ONE copy of the key: the same (score, id) pair may have been stored more than once
-            // (an id added twice), and every copy is a result of its own
-            int mine = -1;
-#pragma unroll
-            for (int r = R - 1; r >= 0; --r)
-                if (kh[r] == gh && kl[r] == gl) mine = r;
-            const unsigned owners = __ballot_sync(0xFFFFFFFFu, mine >= 0 && (gh & gl) != 0xFFFFFFFFu);
-            if (owners && lane == __ffs(owners) - 1) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r == mine) { kh[r] = 0xFFFFFFFFu; kl[r] = 0xFFFFFFFFu; }
-            }
-            if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
-        }
-        return;
-    }
-    // more candidates than the registers hold (rare): "the smallest key greater than the last one taken" walks the
-    // keys in order; a key stored several times (an id added twice) is taken once per copy
-    uint32_t last_hi = 0, last_lo = 0;
-    int taken = 0;                                          // copies of `last` written so far (0: nothing taken yet)
-    for (int i = 0; i < k; ++i) {
-        uint32_t mh = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
-        int same = 0;
-        for (int t = lane; t < n; t += 32) {
-            const u64 key = s_cand[t];
-            const uint32_t kh = (uint32_t)(key >> 32), kl = (uint32_t)key;
-            same += (taken > 0 && kh == last_hi && kl == last_lo) ? 1 : 0;
-            const bool after = taken == 0 || kh > last_hi || (kh == last_hi && kl > last_lo);
-            if (after && (kh < mh || (kh == mh && kl < ml))) { mh = kh; ml = kl; }
-        }
-        same = __reduce_add_sync(0xFFFFFFFFu, same);
-        uint32_t gh, gl;
-        if (same > taken) { gh = last_hi; gl = last_lo; taken += 1; }
-        else {
-            gh = __reduce_min_sync(0xFFFFFFFFu, mh);
-            gl = __reduce_min_sync(0xFFFFFFFFu, mh == gh ? ml : 0xFFFFFFFFu);
-            last_hi = gh; last_lo = gl; taken = 1;
-        }
-        if (lane == 0) write_result(((u64)gh << 32) | gl, order_max, (size_t)qi * k + i, out_dist, out_ids);
-    }
-}
-
 // one warp, while the other warps scan the previous query: everything a query needs besides its look-up table.
 //   * the query itself, copied to shared memory (the table build reads it from there);
 //   * the probe table -- first slot / 32, length and exclusive prefix of the chunk counts of the probed lists that are
@@ -336,7 +259,7 @@ __device__ VIX_SCAN_FN void build_lut(float* __restrict__ s_lut, const float* __
 #pragma unroll
             for (int u = 0; u < U2; ++u) {
                 const int cu = c + u * ngroups;
-                const float dot = fmaf(q1, v[u].y, q0 * v[u].x);
+                const float dot = lut_entry2(q0, q1, v[u]);
                 if (cu < 256) { colA[cu * 64] = dot; colB[cu * 64] = dot; }
             }
         }
@@ -563,8 +486,10 @@ ivfpq_scan_kernel(ScanArgs a) {
     }
 
     // probe table of work item `item` into buffer b (one warp)
+    // work items: every query, or (tensor-core path: the queries it hands back) the first *nq_dev entries of `order`
+    const int nq_items = a.nq_dev ? *a.nq_dev : (int)a.nq;
     auto probe_table = [&](int item, int b) {
-        if (item >= a.nq) return;
+        if (item >= nq_items) return;
         const int64_t qn = a.order ? a.order[item] : item;
         int* pt = s_pt + b * pt_words;
         build_probe_table(a.queries + qn * (int64_t)a.d, a.d, a.coarse, order_max, a.probes + qn * (int64_t)a.nprobe,
@@ -587,7 +512,7 @@ ivfpq_scan_kernel(ScanArgs a) {
     unsigned long long cyc_pro = 0, cyc_scan = 0, cyc_tail = 0;
     for (;;) {
         const int item = s_item[buf];
-        const bool more = item < a.nq;
+        const bool more = item < nq_items;
         const int64_t qi = more ? (a.order ? a.order[item] : item) : 0;
         const float* q = s_qv + buf * a.d;
         const int* pt = s_pt + buf * pt_words;
@@ -1048,7 +973,25 @@ static int launch_fast(ScanArgs& a) {
     return VIX_OK;
 }
 
+int launch_probe_bias(const ScanArgs& a, float* bias) {
+    const int64_t npairs = a.nq * (int64_t)a.nprobe;
+    probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
+        a.queries, a.probes, a.coarse, a.list_len, a.kc, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
+bool tc_scan_supported(const ScanArgs& a);
+int launch_ivfpq_scan_tc(ScanArgs& a);
+
 int launch_ivfpq_scan(ScanArgs& a) {
+    const ScanLayout L = scan_layout(a.m);
+    if (L.fast && tc_scan_supported(a)) return launch_ivfpq_scan_tc(a);      // list-major, tensor cores (vix_ivfpq_tc.cu)
+    return launch_ivfpq_scan_classic(a);
+}
+
+// query-major: one look-up table per query
+int launch_ivfpq_scan_classic(ScanArgs& a) {
     const ScanLayout L = scan_layout(a.m);
     if (!L.fast || a.ks != 256) {
         a.Pw = next_pow2(a.k + 32);
@@ -1076,13 +1019,10 @@ int launch_ivfpq_scan(ScanArgs& a) {
     int* const loud = pipeline_error_flag();
     a.status = loud ? loud : a.work_counter + 1;
     Scratch<float> bias;
-    if ((int64_t)a.d * a.nprobe > 8192) {
+    if (!a.bias && (int64_t)a.d * a.nprobe > 8192) {
         // one staging warp per CTA cannot hide this much bias arithmetic behind a query's scan: do it batch-wide
-        const int64_t npairs = a.nq * (int64_t)a.nprobe;
-        VIX_TRY(bias.alloc((size_t)npairs));
-        probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
-            a.queries, a.probes, a.coarse, a.list_len, a.kc, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias.ptr);
-        VIX_LAUNCH_CHECK();
+        VIX_TRY(bias.alloc((size_t)(a.nq * (int64_t)a.nprobe)));
+        VIX_TRY(launch_probe_bias(a, bias.ptr));
         a.bias = bias.ptr;
     }
     Scratch<float> image;

@@ -1,0 +1,893 @@
+// vix_ivfpq_tc.cu -- list-major IVF-PQ scan: decode once per list, score every query that probes it on the tensor cores,
+// re-evaluate the finalists in the arithmetic of the look-up-table scan (vix_ivfpq_scan.cu).
+//
+// Reference composition: pq_lut_residual_l2_f32 -> adc_scan_u8 -> selectTopK -> mergeTopK
+// (/root/reference/docs/kernel-specs/DONE_22_adc_scan.md:831-881; PQLUT.swift:266-386; ADCScan.swift:190-283).
+//
+// Why: the query-major scan spends one shared-memory look-up per (query, code byte) and sits on the look-up pipe
+// (61 wavefronts per 32 vectors and query).  A batch probes every list several times (C5: 10 k queries x 64
+// probes over 65 536 lists = 9.8 queries per list), and with the decomposition the scan already uses,
+//
+//   ||q - x^||^2 = ||q - c_l||^2 + t_x - 2 <q, r^>          (bias per (query, list), t_x per stored vector)
+//
+// the only (query, vector) term is a dot product with the DECODED residual r^ = (cb_j[code_j])_j.  So per list:
+//
+//   decode   32 vectors per warp, one vector per lane: 16 G look-ups into ONE query-independent table (the codebooks as
+//            fp16 pairs, T[code][64 slots], 64 KB) and 16 G 4-byte stores build a 128 x d fp16 operand tile in the
+//            tensor cores' K-major 128B-swizzled layout.  Look-ups and stores are bank-conflict free by construction
+//            (rotated codes + a lane -> row permutation); ~100 wavefronts per 32 vectors, paid once per LIST VISIT.
+//   MMA      tcgen05.mma kind::f16 M128 N16..64 K16: D[vector][query] = <r^, q> for the queries probing the list (their
+//            fp16 rows gathered into the B tile), fp32 accumulators in TMEM.
+//   filter   one thread per vector row: D >= tau_q + h_v  <=>  bias + t_x - 2 <q, r^> <= thr_q + eps_q, where thr_q is an
+//            EXACT upper bound of the query's k-th best distance (the look-up-table scan over the query's first probed
+//            list) and eps_q bounds |fp16 tensor-core score - the look-up-table scan's fp32 sum|.  Survivors (tens per
+//            query) go to a per-query candidate list.
+//   exact    the candidates are re-evaluated with the very arithmetic of the look-up-table scan (same table entries, same
+//            summation order) and selected by (score, id) together with the seed results: the output is bit-identical
+//            to vix_ivfpq_scan.cu's.  Queries whose seed holds fewer than k vectors, or whose list overflows, are handed
+//            to that kernel entirely.
+//
+// Kernel structure (one persistent CTA per SM, 18 warps):
+//   warps 0-11   decoders, three groups of four warps; group g owns operand stage g (128 rows)
+//   warps 12-15  filter: tcgen05.ld of the accumulators (one TMEM lane quarter each), emission
+//   warp 16      MMA issuer (one lane)
+//   warp 17      work: takes the next list from a global counter, publishes the item, gathers the B tile + tau
+// Every mbarrier wait is bounded (a stuck pipeline raises the error flag instead of hanging the GPU).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <stdio.h>
+
+#include "vix_common.cuh"
+#include "vix_scan.cuh"
+#include "vix_scan_select.cuh"
+
+namespace vix {
+
+int launch_ivfpq_scan_classic(ScanArgs& a);
+static std::atomic<long long> g_tc_launches{0};
+
+namespace tcs {
+
+constexpr int kNQ = 64;                                  // query columns per item
+constexpr int kStagesA = 3;                              // = decoder groups
+constexpr int kItemRing = 4;
+constexpr int kDBufs = 4;                                // accumulator buffers in TMEM (kDBufs x kNQ columns)
+constexpr int kDecWarps = 4 * kStagesA, kEpiWarp0 = kDecWarps, kMmaWarp = kEpiWarp0 + 4, kLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = 32 * (kLoadWarp + 1);           // 576
+constexpr uint32_t kTabAbs = 4096;                       // ABSOLUTE shared addresses: the table's travels in the LDS immediate
+constexpr uint32_t kABase = kTabAbs + 65536;
+constexpr uint32_t kAAtom = 128 * 128;                   // one K-atom (64 halves) of 128 rows
+constexpr uint32_t kAStage = 2 * kAAtom;                 // d <= 128
+constexpr uint32_t kBBase = kABase + kStagesA * kAStage;
+constexpr uint32_t kBAtom = kNQ * 128;
+constexpr uint32_t kBBuf = 2 * kBAtom;
+constexpr uint32_t kEndAbs = kBBase + 2 * kBBuf;
+constexpr int kTmemCols = kDBufs * kNQ;                  // 256
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);   // A, B fp16 (format 0), D fp32, K-major both
+
+struct Item { int first_chunk, nchunks, len, n, pair_begin, pad0, pad1, pad2; };
+
+struct Small {                                           // the bookkeeping in front of the table
+    uint64_t item_full[kItemRing], item_empty[kItemRing];
+    uint64_t a_full[kStagesA], a_empty[kStagesA];
+    uint64_t b_full[2], b_empty[2];
+    uint64_t d_full[kDBufs], d_empty[kDBufs];
+    Item items[kItemRing];
+    float tau[2][kNQ];
+    uint32_t pair[2][kNQ];
+    uint32_t tmem_slot;
+};
+
+struct Args {
+    const uint8_t* slot_codes; const float* slot_tx;
+    const int64_t* list_off; const int32_t* list_len; int kc;
+    const int32_t* pair_off;       // [kc + 1]
+    const uint32_t* pairs;         // [npairs] query * nprobe + probe position, grouped by list
+    const float* bias;             // [nq x nprobe]
+    const __half* qh;              // [nq x d] scaled fp16 queries
+    const float* uq;               // [nq]  -thr / 2 - eps
+    const uint32_t* table;         // [256][64] half2: the codebooks, scaled (slot = sub-quantiser; odd G: last group twice)
+    const float* scales;           // [0] s_q, [1] s_c
+    int nprobe, d, m;
+    int* list_counter;
+    int* cand_cnt; u64* cand; int cap;
+    int smem_bytes;
+    int* status;                   // layout refusal (loud)
+    int* error; int* error_host;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error, int* error_host) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(error) != 0) {
+            atomicExch(error, 1);
+            if (error_host) { *reinterpret_cast<volatile int*>(error_host) = 1; __threadfence_system(); }
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major operand tile, rows of 128 B, 128B swizzle (8-row atoms of 1024 B): SBO = 1024 B
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_tab(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// lane (= slot of a 32-slot chunk) -> row of the warp's 32-row block of the operand tile, chosen so that the 32 stores of a
+// warp (rows x rotated sub-quantisers under the 128B swizzle) hit 32 different banks at every step
+__device__ __forceinline__ uint32_t row_of_lane(uint32_t l) {
+    const uint32_t l0 = l & 1u, l1 = (l >> 1) & 1u, l2 = (l >> 2) & 1u, l3 = (l >> 3) & 1u, l4 = (l >> 4) & 1u;
+    return 8u * (2u * l3 + l1) + 4u * l2 + 2u * l0 + (l2 ^ l4);
+}
+__device__ __forceinline__ uint32_t lane_of_row(uint32_t r) {
+    const uint32_t b0 = r & 1u, b1 = (r >> 1) & 1u, b2 = (r >> 2) & 1u, b3 = (r >> 3) & 1u, b4 = (r >> 4) & 1u;
+    return b1 | (b3 << 1) | (b2 << 2) | (b4 << 3) | ((b0 ^ b2) << 4);
+}
+
+// one group of 16 sub-quantisers of one vector: 16 look-ups, 16 stores.  KIND 0 / 1: the even / odd step of a pair of groups
+// (the half-warps take the two groups in opposite order, so their look-ups use different banks); KIND 2: the last group of
+// an odd G (the second half-warp reads the group's replica).
+template <int IMM>
+__device__ __forceinline__ void decode16(const uint4& w, const uint32_t (&pre)[8], uint32_t sbase) {
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t v0 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604));
+        const uint32_t v1 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7615));
+        const uint32_t v2 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624));
+        const uint32_t v3 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7635));
+        sts32(sbase ^ (uint32_t)((4 * i + 0) << 2), v0);
+        sts32(sbase ^ (uint32_t)((4 * i + 1) << 2), v1);
+        sts32(sbase ^ (uint32_t)((4 * i + 2) << 2), v2);
+        sts32(sbase ^ (uint32_t)((4 * i + 3) << 2), v3);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_scan_kernel(Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t dyn_abs = smem_u32(smem_raw);
+    if (dyn_abs + (uint32_t)sizeof(Small) > kTabAbs || kEndAbs > dyn_abs + (uint32_t)a.smem_bytes) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && a.status) *a.status = 1;
+        return;
+    }
+    Small& S = *reinterpret_cast<Small*>(smem_raw);
+    unsigned char* const abs0 = smem_raw - dyn_abs;          // generic pointer of absolute shared address 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kItemRing; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kDecWarps + 4 + 1); }
+        for (int i = 0; i < kStagesA; ++i) { mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.b_full[i], 32); mbar_init(&S.b_empty[i], 4); }
+        for (int i = 0; i < kDBufs; ++i) { mbar_init(&S.d_full[i], 1); mbar_init(&S.d_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(&S.tmem_slot, kTmemCols);
+    {   // the decode table: 64 KB, once per CTA
+        const uint4* src = reinterpret_cast<const uint4*>(a.table);
+        uint4* dst = reinterpret_cast<uint4*>(abs0 + kTabAbs);
+        for (int i = threadIdx.x; i < 4096; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = S.tmem_slot;
+    const float sc = __ldg(a.scales) * __ldg(a.scales + 1);
+    constexpr int m = 16 * G;
+    constexpr int kKSteps = m / 8;                           // K = 16 halves per MMA, d = 2 m
+
+    if (warp < kDecWarps) {
+        // ------------------------------------------------------------------------------------------ decoders
+        const int grp = warp >> 2, wi = warp & 3;
+        const uint32_t h = (uint32_t)lane >> 4;
+        const uint32_t row = 32u * wi + row_of_lane((uint32_t)lane), r7 = row & 7u;
+        const uint32_t rowoff = (row >> 3) * 1024u + r7 * 128u;
+        const uint32_t lo0 = ((((4u * h) ^ r7 ^ (((uint32_t)lane >> 2) & 3u)) & 7u) << 4) | (((uint32_t)lane & 3u) << 2);
+        const uint32_t stage_base = kABase + (uint32_t)grp * kAStage + rowoff;
+        uint32_t pre0[8], pre1[8];
+#pragma unroll
+        for (int b = 0; b < 16; b += 2) {
+            const uint32_t c0 = 64u * h + 4u * ((uint32_t)(b ^ lane) & 15u);
+            const uint32_t c1 = 64u * h + 4u * ((uint32_t)((b + 1) ^ lane) & 15u);
+            pre0[b >> 1] = c0 | (c1 << 8);
+            pre1[b >> 1] = pre0[b >> 1] ^ 0x4040u;
+            asm volatile("" : "+r"(pre0[b >> 1]), "+r"(pre1[b >> 1]));
+        }
+        int it = 0;
+        long long u0 = 0;
+        for (;;) {
+            const int slot = it % kItemRing;
+            if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
+            const int fc = S.items[slot].first_chunk, nch = S.items[slot].nchunks;
+            if (nch < 0) break;
+            const int nt = (nch + 3) >> 2;
+            int t = (int)(((long long)grp - u0 % kStagesA + kStagesA) % kStagesA);
+            bool ok = true;
+            for (; t < nt; t += kStagesA) {
+                const long long use = (u0 + t) / kStagesA;
+                const int ch = 4 * t + wi;
+                uint4 w[G];
+                if (ch < nch) {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + (size_t)(fc + ch) * (512u * G)) + lane;
+#pragma unroll
+                    for (int s = 0; s < G; ++s) {
+                        const int pi = s >> 1;
+                        const bool last_odd = (G & 1) && s == G - 1;
+                        const int piece = last_odd ? G - 1 : 2 * pi + ((s & 1) ? 1 - (int)h : (int)h);
+                        w[s] = __ldg(src + 32 * piece);
+                    }
+                }
+                if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                if (ch < nch) {
+#pragma unroll
+                    for (int s = 0; s < G; ++s) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int pi = s >> 1;
+                        const bool last_odd = (G & 1) && s == G - 1;
+                        const uint32_t sb = stage_base + (uint32_t)pi * kAAtom;
+                        // (the immediates are compile-time: the loop is fully unrolled over s)
+                        if (last_odd) {
+                            if (s == 0) decode16<(int)kTabAbs + 64 * 0>(w[s], pre0, sb + (lo0 ^ (h << 6)));
+                            if (s == 2) decode16<(int)kTabAbs + 64 * 2>(w[s], pre0, sb + (lo0 ^ (h << 6)));
+                        } else if ((s & 1) == 0) {
+                            if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre0, sb + lo0);
+                            if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre0, sb + lo0);
+                        } else {
+                            if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre1, sb + (lo0 ^ 0x40u));
+                            if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre1, sb + (lo0 ^ 0x40u));
+                        }
+                    }
+                }
+                fence_async_proxy();
+                mbar_arrive(&S.a_full[grp]);
+            }
+            if (!ok) break;
+            u0 += nt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.item_empty[slot]);
+            ++it;
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int it = 0;
+            long long u = 0;
+            for (;;) {
+                const int slot = it % kItemRing;
+                if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
+                const int nch = S.items[slot].nchunks, n = S.items[slot].n;
+                if (nch < 0) break;
+                const int nt = (nch + 3) >> 2;
+                const uint32_t idesc = kIdescF16 | ((uint32_t)(((n + 15) & ~15) >> 3) << 17);
+                const int buf = it & 1;
+                if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host)) break;
+                bool ok = true;
+                for (int t = 0; t < nt; ++t, ++u) {
+                    const int st = (int)(u % kStagesA), db = (int)(u % kDBufs);
+                    if (!mbar_wait(&S.a_full[st], (uint32_t)(u / kStagesA) & 1u, a.error, a.error_host)) { ok = false; break; }
+                    if (u >= kDBufs && !mbar_wait(&S.d_empty[db], (uint32_t)(u / kDBufs - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                    fence_after_sync();
+                    const uint32_t dcol = tmem_base + (uint32_t)(db * kNQ);
+#pragma unroll
+                    for (int ks = 0; ks < kKSteps; ++ks) {
+                        const uint64_t ad = make_desc(kABase + (uint32_t)st * kAStage + (uint32_t)(ks >> 2) * kAAtom) + (uint64_t)(2 * (ks & 3));
+                        const uint64_t bd = make_desc(kBBase + (uint32_t)buf * kBBuf + (uint32_t)(ks >> 2) * kBAtom) + (uint64_t)(2 * (ks & 3));
+                        mma_f16(dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    mma_commit(&S.a_empty[st]);
+                    mma_commit(&S.d_full[db]);
+                }
+                if (!ok) break;
+                mbar_arrive(&S.item_empty[slot]);
+                ++it;
+            }
+        }
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+        // ------------------------------------------------------------------------------------------ filter
+        const int wq = warp - kEpiWarp0;                     // = warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t sl = lane_of_row((uint32_t)lane);     // TMEM lane = tile row -> slot of the chunk
+        int it = 0;
+        long long u = 0;
+        for (;;) {
+            const int slot = it % kItemRing;
+            if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
+            const int fc = S.items[slot].first_chunk, nch = S.items[slot].nchunks, len = S.items[slot].len, n = S.items[slot].n;
+            if (nch < 0) break;
+            const int nt = (nch + 3) >> 2;
+            const int buf = it & 1;
+            if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host)) break;
+            const float* tau = S.tau[buf];
+            bool ok = true;
+            for (int t = 0; t < nt; ++t, ++u) {
+                const int db = (int)(u % kDBufs);
+                const int ch = 4 * t + wq;
+                const int within = ch * 32 + (int)sl;
+                const bool valid = ch < nch && within < len;
+                const uint32_t g = ((uint32_t)(fc + ch) << 5) + sl;
+                const float tx = valid ? __ldg(a.slot_tx + g) : 0.0f;
+                const float hv = sc * (0.5f * tx - 1.5e-6f * fabsf(tx));
+                if (!mbar_wait(&S.d_full[db], (uint32_t)(u / kDBufs) & 1u, a.error, a.error_host)) { ok = false; break; }
+                fence_after_sync();
+                for (int cb = 0; cb < n; cb += 16) {
+                    float dv[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(db * kNQ + cb), dv);
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) any |= dv[c] >= tau[cb + c] + hv;       // tau = NaN behind the last query
+                    if (any && valid) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            if (dv[c] >= tau[cb + c] + hv) {
+                                const uint32_t pr = S.pair[buf][cb + c];
+                                const uint32_t q = pr / (uint32_t)a.nprobe;
+                                const int pos = atomicAdd(a.cand_cnt + q, 1);
+                                if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = ((u64)pr << 32) | (u64)g;
+                            }
+                        }
+                    }
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.d_empty[db]);
+            }
+            if (!ok) break;
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&S.b_empty[buf]); mbar_arrive(&S.item_empty[slot]); }
+            ++it;
+        }
+    } else if (warp == kLoadWarp) {
+        // ------------------------------------------------------------------------------------------ work + B tiles
+        constexpr int CH = m / 4;                             // 16-byte pieces of a query row (d = 2 m halves)
+        int it = 0;
+        bool ok = true;
+        auto publish = [&](int fc, int nch, int len, int n, int pb) {
+            const int slot = it % kItemRing;
+            if (it >= kItemRing && !mbar_wait(&S.item_empty[slot], (uint32_t)(it / kItemRing - 1) & 1u, a.error, a.error_host)) return false;
+            if (lane == 0) {
+                Item& I = S.items[slot];
+                I.first_chunk = fc; I.nchunks = nch; I.len = len; I.n = n; I.pair_begin = pb;
+                __threadfence_block();
+                mbar_arrive(&S.item_full[slot]);
+            }
+            __syncwarp();
+            return true;
+        };
+        while (ok) {
+            int l = 0;
+            if (lane == 0) l = atomicAdd(a.list_counter, 1);
+            l = __shfl_sync(0xFFFFFFFFu, l, 0);
+            if (l >= a.kc) break;
+            const int pb = __ldg(a.pair_off + l), pe = __ldg(a.pair_off + l + 1);
+            if (pe == pb) continue;
+            const int len = __ldg(a.list_len + l);
+            const int fc = (int)(__ldg(a.list_off + l) >> 5), nch = (len + 31) >> 5;
+            for (int g0 = pb; g0 < pe && ok; g0 += kNQ) {
+                const int n = min(kNQ, pe - g0);
+                if (!publish(fc, nch, len, n, g0)) { ok = false; break; }
+                const int buf = it & 1;
+                if (it >= 2 && !mbar_wait(&S.b_empty[buf], (uint32_t)((it >> 1) - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                const uint32_t bbase = kBBase + (uint32_t)buf * kBBuf;
+                for (int idx = lane; idx < n * CH; idx += 32) {
+                    const int c = idx / CH, chn = idx - c * CH;
+                    const uint32_t q = __ldg(a.pairs + g0 + c) / (uint32_t)a.nprobe;
+                    const uint32_t dst = bbase + (uint32_t)(chn >> 3) * kBAtom + (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u +
+                                         (uint32_t)(((chn & 7) ^ (c & 7)) << 4);
+                    const char* src = reinterpret_cast<const char*>(a.qh) + (size_t)q * (size_t)(4 * m) + (size_t)chn * 16;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+                }
+                asm volatile("cp.async.commit_group;");
+                for (int c = lane; c < kNQ; c += 32) {
+                    float tv = __int_as_float(0x7fc00000);                  // NaN behind the last query: no column value passes
+                    uint32_t pr = 0;
+                    if (c < n) {
+                        pr = __ldg(a.pairs + g0 + c);
+                        const float b = __ldg(a.bias + pr);
+                        tv = sc * ((0.5f * b - 1.5e-6f * fabsf(b)) + __ldg(a.uq + pr / (uint32_t)a.nprobe));
+                    }
+                    S.tau[buf][c] = tv;
+                    S.pair[buf][c] = pr;
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fence_async_proxy();
+                mbar_arrive(&S.b_full[buf]);
+                ++it;
+            }
+        }
+        if (ok) publish(0, -1, 0, 0, 0);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------- the small kernels
+// decode table + its scale + the residual norm bound: one CTA.  table[code][slot] = half2(s_c cb_j[code]); the last group of
+// an odd number of groups is stored twice (the second half-warp reads the replica).  meta: [1] = s_c, [2] = R_max =
+// sqrt(sum_j max_c ||cb_j[c]||^2) >= ||r^|| of every stored vector.
+__global__ void __launch_bounds__(1024)
+table_kernel(const float* __restrict__ codebooks, int m, uint32_t* __restrict__ table, float* __restrict__ meta) {
+    __shared__ float s_max[32], s_r2[64];
+    __shared__ float s_scale;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = 0.0f;
+    for (int i = tid; i < m * 256 * 2; i += 1024) mx = fmaxf(mx, fabsf(codebooks[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if (lane == 0) s_max[warp] = mx;
+    // max_c ||cb_j[c]||^2: one warp per sub-quantiser
+    for (int j = warp; j < m; j += 32) {
+        float r2 = 0.0f;
+        for (int c = lane; c < 256; c += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(codebooks + ((size_t)j * 256 + c) * 2);
+            r2 = fmaxf(r2, v.x * v.x + v.y * v.y);
+        }
+        for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, o));
+        if (lane == 0) s_r2[j] = r2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float g = 0.0f;
+        for (int w = 0; w < 32; ++w) g = fmaxf(g, s_max[w]);
+        int e = 0;
+        float s = 1.0f;
+        if (g > 0.0f && g < __int_as_float(0x7f800000)) { frexpf(g, &e); s = ldexpf(1.0f, 10 - e); }
+        float r2 = 0.0f;
+        for (int j = 0; j < m; ++j) r2 += s_r2[j];
+        s_scale = s;
+        meta[1] = s;
+        meta[2] = sqrtf(r2) * 1.0001f;
+    }
+    __syncthreads();
+    const float s = s_scale;
+    const int G = m / 16;
+    for (int i = tid; i < 256 * 64; i += 1024) {
+        const int c = i >> 6, slot = i & 63;
+        int j = slot;
+        if ((G & 1) && slot >= m && slot < m + 16) j = slot - 16;          // replica of the last group
+        uint32_t v = 0;
+        if (j < m) {
+            const float2 f = *reinterpret_cast<const float2*>(codebooks + ((size_t)j * 256 + c) * 2);
+            const __half2 hh = __floats2half2_rn(f.x * s, f.y * s);
+            v = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        table[i] = v;
+    }
+}
+
+// per query (one warp): ||q||, and the batch maximum of |q_e| (the fp16 scale)
+__global__ void __launch_bounds__(256)
+query_norm_kernel(const float* __restrict__ queries, int64_t nq, int d, float* __restrict__ qnorm, unsigned int* __restrict__ maxabs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    float s = 0.0f, mx = 0.0f;
+    for (int e = lane; e < d; e += 32) { const float v = __ldg(queries + q * d + e); s = fmaf(v, v, s); mx = fmaxf(mx, fabsf(v)); }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xFFFFFFFFu, s, o); mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o)); }
+    if (lane == 0) {
+        qnorm[q] = sqrtf(s);
+        if (mx == mx && mx < __int_as_float(0x7f800000)) atomicMax(maxabs, __float_as_uint(mx));
+    }
+}
+
+// first probe position whose list holds vectors here: the seed of the query (one warp per query)
+__global__ void __launch_bounds__(256)
+seed_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, const int32_t* __restrict__ list_len, int kc,
+                  int32_t* __restrict__ seed_list, int32_t* __restrict__ seed_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    int l0 = -1, p0 = -1;
+    for (int base = 0; base < nprobe; base += 32) {
+        const int p = base + lane;
+        const int l = p < nprobe ? __ldg(probes + i * nprobe + p) : -1;
+        const bool here = (unsigned)l < (unsigned)kc && __ldg(list_len + l) > 0;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
+        if (ball) { const int src = __ffs(ball) - 1; l0 = __shfl_sync(0xFFFFFFFFu, l, src); p0 = base + src; break; }
+    }
+    if (lane == 0) { seed_list[i] = l0; seed_pos[i] = p0; }
+}
+
+// per query (one warp), after the seed scan: the fp16 row, u_q = -thr / 2 - eps_q, and whether the query can take this path
+// (a finite k-th seed distance and a finite error bound)
+__global__ void __launch_bounds__(256)
+query_prep_kernel(const float* __restrict__ queries, int64_t nq, int d, const float* __restrict__ qnorm,
+                  const unsigned int* __restrict__ maxabs, float* __restrict__ meta, const float* __restrict__ seed_dist, int k,
+                  __half* __restrict__ qh, float* __restrict__ uq, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const float g = __uint_as_float(*maxabs);
+    float sq = 1.0f;
+    if (g > 0.0f) { int e = 0; frexpf(g, &e); sq = ldexpf(1.0f, 10 - e); }
+    if (q == 0 && lane == 0) meta[0] = sq;
+    const float s_c = meta[1], rmax = meta[2];
+    for (int e = lane; e < d; e += 32) qh[q * d + e] = __float2half_rn(__ldg(queries + q * d + e) * sq);
+    if (lane == 0) {
+        const float qn = qnorm[q];
+        const float thr = seed_dist[q * k + (k - 1)];
+        // |fp16 tensor-core <q, r^> - exact| <= eta ||q|| ||r^|| + the subnormal floor of the two conversions, and the
+        // look-up-table scan's own fp32 sum is within 2e-6 of (|bias| + |t_x| + 2 ||q|| ||r^||) of the exact value
+        // (the |bias| and |t_x| shares ride in tau and h_v)
+        const float eta = 1.05f * 0.0009765625f + (float)d * 4.8e-7f;
+        const float eps = eta * qn * rmax + 6e-8f * sqrtf((float)d) * (rmax / sq + qn / s_c) + 2e-6f * qn * rmax;
+        const float u = -0.5f * thr - eps - 2e-6f * fabsf(thr);
+        const bool fine = thr == thr && fabsf(thr) < __int_as_float(0x7f800000) && u == u && fabsf(u) < __int_as_float(0x7f800000) &&
+                          qn * sq < 60000.0f;
+        uq[q] = fine ? u : 0.0f;
+        flag[q] = fine ? 0 : 1;
+    }
+}
+
+// (query, probe position) pairs of this path, counted per list; also the entries every valid pair visits (statistics)
+__global__ void __launch_bounds__(256)
+pair_count_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe, const int32_t* __restrict__ list_len, int kc,
+                  const int32_t* __restrict__ seed_pos, const int* __restrict__ flag, int32_t* __restrict__ hist,
+                  unsigned long long* __restrict__ scanned) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long vis = 0;
+    if (i < npairs) {
+        const int l = __ldg(probes + i);
+        if ((unsigned)l < (unsigned)kc) {
+            const int len = __ldg(list_len + l);
+            vis = (unsigned long long)len;
+            const int64_t q = i / nprobe;
+            if (len > 0 && !flag[q] && (int)(i - q * nprobe) != seed_pos[q]) atomicAdd(hist + l, 1);
+        }
+    }
+    if (scanned) {
+        for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xFFFFFFFFu, vis, o);
+        if ((threadIdx.x & 31) == 0 && vis) atomicAdd(scanned, vis);
+    }
+}
+__global__ void __launch_bounds__(256)
+pair_scatter_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe, const int32_t* __restrict__ list_len, int kc,
+                    const int32_t* __restrict__ seed_pos, const int* __restrict__ flag, int32_t* __restrict__ cursor,
+                    uint32_t* __restrict__ pairs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int l = __ldg(probes + i);
+    if ((unsigned)l >= (unsigned)kc || __ldg(list_len + l) <= 0) return;
+    const int64_t q = i / nprobe;
+    if (flag[q] || (int)(i - q * nprobe) == seed_pos[q]) return;
+    pairs[atomicAdd(cursor + l, 1)] = (uint32_t)i;
+}
+
+// exclusive prefix sums of hist[0, n) -> off[0, n], cursor[0, n) (a copy the scatter advances); two small kernels
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(256)
+block_sum_kernel(const int32_t* __restrict__ hist, int n, int32_t* __restrict__ bsum) {
+    __shared__ int s_w[8];
+    const int base = blockIdx.x * kScanBlock;
+    int s = 0;
+    for (int i = threadIdx.x; i < kScanBlock; i += 256) s += base + i < n ? hist[base + i] : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; bsum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256)
+block_scan_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __restrict__ bsum, int32_t* __restrict__ off,
+                  int32_t* __restrict__ cursor) {
+    __shared__ int s_w[8];
+    __shared__ int s_base;
+    const int base = blockIdx.x * kScanBlock;
+    if (threadIdx.x < 32) {
+        int s = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += 32) s += bsum[b];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (threadIdx.x == 0) s_base = s;
+    }
+    // thread t owns the 4 consecutive bins base + 4 t ..
+    int v[4], s = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const int i = base + 4 * threadIdx.x + e; v[e] = i < n ? hist[i] : 0; s += v[e]; }
+    int inc = s;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)(threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int run = s_base + inc - s;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_w[w];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = base + 4 * threadIdx.x + e;
+        if (i < n) { off[i] = run; cursor[i] = run; }
+        run += v[e];
+        if (i == n - 1) off[n] = run;
+    }
+}
+
+// one warp per query: the candidates in the look-up-table scan's arithmetic, selected with the seed results
+template <int G>
+__global__ void __launch_bounds__(128)
+finalist_kernel(const float* __restrict__ queries, int64_t nq, int nprobe, const float* __restrict__ bias,
+                const float* __restrict__ codebooks_t, const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx,
+                const int64_t* __restrict__ slot_ids, const int* __restrict__ cand_cnt, const u64* __restrict__ cand, int cap,
+                const float* __restrict__ seed_dist, const int64_t* __restrict__ seed_ids, int k, const int* __restrict__ flag,
+                int32_t* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    constexpr int m = 16 * G;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    u64* keys = reinterpret_cast<u64*>(fsm) + (size_t)warp * (cap + 64);
+    float* sq = reinterpret_cast<float*>(reinterpret_cast<u64*>(fsm) + (size_t)4 * (cap + 64)) + (size_t)warp * (2 * m);
+    const int cnt = cand_cnt[q];
+    if (flag[q] || cnt > cap) {
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)q;
+        return;
+    }
+    for (int e = lane; e < 2 * m; e += 32) sq[e] = __ldg(queries + q * (2 * m) + e) * -2.0f;   // the table build's pre-scaled query
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+        const u64 c = cand[(size_t)q * cap + i];
+        const uint32_t pr = (uint32_t)(c >> 32), g = (uint32_t)c;
+        const uint32_t sl = g & 31u;
+        const uint4* src = reinterpret_cast<const uint4*>(slot_codes + (size_t)(g >> 5) * (512u * G)) + sl;
+        float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) {
+            const uint4 w = __ldg(src + 32 * grp);
+            const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t b = 4 * i4 + t;
+                    const uint32_t code = (x[i4] >> (8 * t)) & 255u;
+                    const uint32_t j = 16u * grp + ((b ^ sl) & 15u);
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(codebooks_t + ((size_t)code * m + j) * 2));
+                    s[t] = fadd(s[t], lut_entry2(sq[2 * j], sq[2 * j + 1], v));
+                }
+            }
+        }
+        const float sum = fadd(fadd(__ldg(bias + pr), __ldg(slot_tx + g)), fadd(fadd(s[0], s[1]), fadd(s[2], s[3])));
+        keys[i] = make_key(sum, 0u, 0) | (u64)(uint32_t)slot_ids[g];
+    }
+    int n = cnt;
+    for (int i = lane; i < k; i += 32) {                       // the seed's results (its list is not among the pairs)
+        const int64_t id = seed_ids[q * k + i];
+        keys[cnt + i] = id >= 0 ? (make_key(seed_dist[q * k + i], 0u, 0) | (u64)(uint32_t)id) : kEmptyKey;
+    }
+    n += k;
+    __syncwarp();
+    select_and_write(keys, n, k, 0, q, out_dist, out_ids);
+}
+
+__global__ void smem_base_kernel(uint32_t* out) {
+    extern __shared__ __align__(1024) unsigned char probe_raw[];
+    if (threadIdx.x == 0) *out = smem_u32(probe_raw);
+}
+
+// the absolute shared address at which this device starts a kernel's dynamic shared memory (1024 on sm_100: the system's
+// reserve), asked once; -1 when the layout above does not fit behind it
+static int smem_base() {
+    static std::once_flag once;
+    static int base = -1;
+    std::call_once(once, [] {
+        uint32_t* d = nullptr;
+        uint32_t h = 0xFFFFFFFFu;
+        if (cudaMalloc(&d, 4) != cudaSuccess) return;
+        smem_base_kernel<<<1, 32, 1024>>>(d);
+        if (cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) == cudaSuccess && h + sizeof(Small) <= kTabAbs &&
+            kEndAbs - h <= 227u * 1024u)
+            base = (int)h;
+        cudaFree(d);
+        (void)cudaGetLastError();
+    });
+    return base;
+}
+
+}  // namespace tcs
+
+// L2, dsub = 2, rotated lists, no filter, no phase statistics; batches large enough that lists are shared.
+// VIX_TC_SCAN=0 disables the path, =1 takes it whenever the shape allows.
+bool tc_scan_supported(const ScanArgs& a) {
+    const char* env = getenv("VIX_TC_SCAN");
+    if (env && env[0] == '0') return false;
+    if (a.metric != VIX_METRIC_L2 || a.dsub != 2 || a.ks != 256 || !(a.m == 16 || a.m == 32 || a.m == 48 || a.m == 64)) return false;
+    if (a.filter || a.phase_cycles || a.nq_dev || a.k > 64) return false;
+    if (a.nq * (int64_t)a.nprobe >= (1LL << 32) || a.nq < 1) return false;
+    if (!(env && env[0] == '1') && a.nq * (int64_t)a.nprobe < 32768) return false;
+    return tcs::smem_base() >= 0;
+}
+
+int launch_ivfpq_scan_tc(ScanArgs& a) {
+    using namespace tcs;
+    cudaStream_t s = ctx().stream;
+    const int64_t nq = a.nq, npairs = a.nq * (int64_t)a.nprobe;
+    const int k = a.k, m = a.m, d = a.d, G = m / 16;
+    int cap = 1024;
+    while (cap > 128 && (size_t)nq * cap * 8 > (1ull << 30)) cap >>= 1;
+
+    Scratch<uint32_t> table, pairs;
+    Scratch<float> meta, qnorm, uq, seed_dist, bias;
+    Scratch<unsigned int> maxabs;
+    Scratch<int32_t> seed_list, seed_pos, hist, off, cursor, bsum, fb_list;
+    Scratch<int64_t> seed_ids;
+    Scratch<int> flag, counters, cand_cnt, wc_seed, wc_fb;
+    Scratch<__half> qh;
+    Scratch<u64> cand;
+    VIX_TRY(table.alloc(256 * 64));
+    VIX_TRY(meta.alloc(4));
+    VIX_TRY(qnorm.alloc((size_t)nq));
+    VIX_TRY(uq.alloc((size_t)nq));
+    VIX_TRY(maxabs.alloc(1));
+    VIX_TRY(seed_list.alloc((size_t)nq));
+    VIX_TRY(seed_pos.alloc((size_t)nq));
+    VIX_TRY(seed_dist.alloc((size_t)nq * k));
+    VIX_TRY(seed_ids.alloc((size_t)nq * k));
+    VIX_TRY(flag.alloc((size_t)nq));
+    VIX_TRY(qh.alloc((size_t)nq * d));
+    VIX_TRY(hist.alloc((size_t)a.kc + 1));
+    VIX_TRY(off.alloc((size_t)a.kc + 1));
+    VIX_TRY(cursor.alloc((size_t)a.kc + 1));
+    const int nblk = (a.kc + kScanBlock - 1) / kScanBlock;
+    VIX_TRY(bsum.alloc((size_t)nblk));
+    VIX_TRY(pairs.alloc((size_t)npairs));
+    VIX_TRY(bias.alloc((size_t)npairs));
+    VIX_TRY(counters.alloc(4));                    // [0] list counter, [1] error, [2] fall-back count
+    VIX_TRY(cand_cnt.alloc((size_t)nq));
+    VIX_TRY(cand.alloc((size_t)nq * cap));
+    VIX_TRY(fb_list.alloc((size_t)nq));
+    VIX_TRY(wc_seed.alloc(2));
+    VIX_TRY(wc_fb.alloc(2));
+    VIX_CUDA(cudaMemsetAsync(maxabs.ptr, 0, 4, s));
+    VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)a.kc + 1) * 4, s));
+    VIX_CUDA(cudaMemsetAsync(counters.ptr, 0, 16, s));
+    VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
+
+    table_kernel<<<1, 1024, 0, s>>>(a.codebooks, m, table.ptr, meta.ptr);
+    VIX_LAUNCH_CHECK();
+    const unsigned qwarps = (unsigned)((nq * 32 + 255) / 256);
+    query_norm_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr);
+    VIX_LAUNCH_CHECK();
+    seed_probe_kernel<<<qwarps, 256, 0, s>>>(a.probes, nq, a.nprobe, a.list_len, a.kc, seed_list.ptr, seed_pos.ptr);
+    VIX_LAUNCH_CHECK();
+    {   // seed: the look-up-table scan over the first probed list that holds vectors here
+        ScanArgs sd = a;
+        sd.probes = seed_list.ptr; sd.nprobe = 1;
+        sd.out_dist = seed_dist.ptr; sd.out_ids = seed_ids.ptr;
+        sd.scanned = nullptr; sd.bias = nullptr; sd.lut_image = nullptr;
+        sd.work_counter = wc_seed.ptr;
+        VIX_TRY(launch_ivfpq_scan_classic(sd));
+    }
+    query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, seed_dist.ptr, k, qh.ptr, uq.ptr,
+                                            flag.ptr);
+    VIX_LAUNCH_CHECK();
+    const unsigned pblocks = (unsigned)((npairs + 255) / 256);
+    pair_count_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, seed_pos.ptr, flag.ptr, hist.ptr, a.scanned);
+    VIX_LAUNCH_CHECK();
+    block_sum_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.kc, bsum.ptr);
+    VIX_LAUNCH_CHECK();
+    block_scan_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.kc, bsum.ptr, off.ptr, cursor.ptr);
+    VIX_LAUNCH_CHECK();
+    pair_scatter_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, seed_pos.ptr, flag.ptr, cursor.ptr,
+                                               pairs.ptr);
+    VIX_LAUNCH_CHECK();
+    VIX_TRY(launch_probe_bias(a, bias.ptr));
+
+    Args t{};
+    t.slot_codes = a.slot_codes; t.slot_tx = a.slot_tx; t.list_off = a.list_off; t.list_len = a.list_len; t.kc = a.kc;
+    t.pair_off = off.ptr; t.pairs = pairs.ptr; t.bias = bias.ptr; t.qh = qh.ptr; t.uq = uq.ptr; t.table = table.ptr;
+    t.scales = meta.ptr; t.nprobe = a.nprobe; t.d = d; t.m = m;
+    t.list_counter = counters.ptr; t.cand_cnt = cand_cnt.ptr; t.cand = cand.ptr; t.cap = cap;
+    t.error = counters.ptr + 1; t.error_host = pipeline_error_flag();
+    t.status = t.error_host ? t.error_host : counters.ptr + 3;
+    const int smem = (int)kEndAbs - smem_base();
+    t.smem_bytes = smem;
+    int grid = num_sms();
+    if (grid > a.kc) grid = a.kc;
+#define VIX_TCS(GG)                                                                                                        \
+    do {                                                                                                                   \
+        VIX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
+        tc_scan_kernel<GG><<<grid, kThreads, smem, s>>>(t);                                                                \
+        VIX_LAUNCH_CHECK();                                                                                                \
+        const size_t fsm = (size_t)4 * (cap + 64) * 8 + (size_t)4 * 2 * m * 4;                                             \
+        VIX_CUDA(cudaFuncSetAttribute(finalist_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));         \
+        finalist_kernel<GG><<<(unsigned)((nq + 3) / 4), 128, fsm, s>>>(a.queries, nq, a.nprobe, bias.ptr, a.codebooks_t,    \
+            a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, cand.ptr, cap, seed_dist.ptr, seed_ids.ptr, k, flag.ptr,    \
+            fb_list.ptr, counters.ptr + 2, a.out_dist, a.out_ids);                                                         \
+        VIX_LAUNCH_CHECK();                                                                                                \
+    } while (0)
+    switch (G) {
+        case 1: VIX_TCS(1); break;
+        case 2: VIX_TCS(2); break;
+        case 3: VIX_TCS(3); break;
+        case 4: VIX_TCS(4); break;
+    }
+#undef VIX_TCS
+    {   // the queries handed back: all their probes through the look-up-table scan
+        ScanArgs fb = a;
+        fb.order = fb_list.ptr; fb.nq_dev = counters.ptr + 2;
+        fb.scanned = nullptr; fb.bias = bias.ptr; fb.lut_image = nullptr;
+        fb.work_counter = wc_fb.ptr;
+        VIX_TRY(launch_ivfpq_scan_classic(fb));
+    }
+    g_tc_launches.fetch_add(1);
+    if (getenv("VIX_TC_SCAN_DEBUG")) {
+        // diagnostics (synchronises): queries handed back, candidates per query
+        int hc[4] = {0, 0, 0, 0};
+        std::vector<int> cc((size_t)nq);
+        VIX_CUDA(cudaMemcpyAsync(hc, counters.ptr, 16, cudaMemcpyDeviceToHost, s));
+        VIX_CUDA(cudaMemcpyAsync(cc.data(), cand_cnt.ptr, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        VIX_CUDA(cudaStreamSynchronize(s));
+        long long tot = 0;
+        int mx = 0;
+        for (int64_t i = 0; i < nq; ++i) { tot += cc[(size_t)i]; mx = cc[(size_t)i] > mx ? cc[(size_t)i] : mx; }
+        fprintf(stderr, "[vix tc scan] nq %lld, handed back %d, candidates %lld (max %d per query, cap %d), error %d\n", (long long)nq,
+                hc[2], tot, mx, cap, hc[1]);
+    }
+    return VIX_OK;
+}
+
+long long tc_scan_launches() { return g_tc_launches.load(); }
+
+}  // namespace vix

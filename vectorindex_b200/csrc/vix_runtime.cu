@@ -112,6 +112,8 @@ int finish(bool any_host_output) {
 
 using namespace vix;
 
+namespace vix { long long tc_scan_launches(); }
+
 extern "C" {
 
 int vix_version(void) { return 100; }   // 0.1.0
@@ -153,5 +155,7 @@ int64_t vix_kernel_launches(int reset) {
     if (reset) ctx().launches = 0;
     return v;
 }
+
+int64_t vix_scan_tc_launches(void) { return (int64_t)vix::tc_scan_launches(); }
 
 }  // extern "C"

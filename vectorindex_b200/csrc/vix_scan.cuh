@@ -10,6 +10,8 @@ struct ScanArgs {
     const float* queries; int64_t nq; int d, m, ks, dsub;
     const int32_t* probes; int nprobe;            // [nq x nprobe], -1 padded
     const int32_t* order;                         // optional [nq]: work item -> query (locality order)
+    const int* nq_dev;                            // optional (device): number of work items, when only the host does not know it
+                                                  // (then `order` lists them and nq bounds the launch)
     int* work_counter;                            // device int[2], zeroed by the launcher: [0] queue head, [1] status
     int* status;                                  // set by the launcher (= work_counter + 1)
     int smem_bytes;                               // dynamic shared memory of the launch (set by the launcher)
@@ -42,6 +44,8 @@ struct ScanLayout {
 };
 ScanLayout scan_layout(int m);
 
-int launch_ivfpq_scan(ScanArgs& a);
+int launch_ivfpq_scan(ScanArgs& a);            // picks the path
+int launch_ivfpq_scan_classic(ScanArgs& a);    // query-major look-up-table scan (vix_ivfpq_scan.cu)
+int launch_probe_bias(const ScanArgs& a, float* bias);   // bias[q x nprobe]: the per-probe term, batch-wide
 
 }  // namespace vix
