@@ -736,7 +736,8 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             VIX_TRY(work_counter.alloc(2));
             a.work_counter = work_counter.ptr;
             Scratch<int32_t> order;
-            if (scan_layout(a.m).fast && a.ks == 256 && nq > 2 * num_sms()) {
+            // (the list-major path does not go query by query: no order to compute)
+            if (scan_layout(a.m).fast && a.ks == 256 && nq > 2 * num_sms() && !tc_scan_supported(a)) {
                 VIX_TRY(query_order(pp, nq, nprobe, h->list_len.ptr, h->kc, order));
                 a.order = order.ptr;
             }

@@ -140,21 +140,6 @@ probe_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__
     if (lane == 0) bias[w] = part;
 }
 
-// k-th smallest (0-based rank kth) of one 32-bit key per lane: bitonic network over the warp
-__device__ VIX_SCAN_FN uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
-            const bool up = (lane & size) == 0 || size == 32;
-            const bool lower = (lane & stride) == 0;
-            v = (lower == up) ? min(v, other) : max(v, other);
-        }
-    }
-    return __shfl_sync(0xFFFFFFFFu, v, kth);
-}
-
 // one warp, while the other warps scan the previous query: everything a query needs besides its look-up table.
 //   * the query itself, copied to shared memory (the table build reads it from there);
 //   * the probe table -- first slot / 32, length and exclusive prefix of the chunk counts of the probed lists that are

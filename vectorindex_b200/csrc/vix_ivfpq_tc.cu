@@ -262,59 +262,92 @@ tc_scan_kernel(Args a) {
             pre1[b >> 1] = pre0[b >> 1] ^ 0x4040u;
             asm volatile("" : "+r"(pre0[b >> 1]), "+r"(pre1[b >> 1]));
         }
-        int it = 0;
+        // The warp walks its units (tile t of item it with (units before the item + t) % 3 == grp) with the NEXT unit's codes
+        // already in flight while it decodes the current one (two register buffers, loop unrolled by two).  Moving on may
+        // cross into the next item: the descriptor of an item is copied to registers, so its ring slot is released at once.
+        int it = 0, slot = 0, fc = 0, nch = 0, nt = 0, t = 0;
         long long u0 = 0;
-        for (;;) {
-            const int slot = it % kItemRing;
-            if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
-            const int fc = S.items[slot].first_chunk, nch = S.items[slot].nchunks;
-            if (nch < 0) break;
-            const int nt = (nch + 3) >> 2;
-            int t = (int)(((long long)grp - u0 % kStagesA + kStagesA) % kStagesA);
-            bool ok = true;
-            for (; t < nt; t += kStagesA) {
-                const long long use = (u0 + t) / kStagesA;
-                const int ch = 4 * t + wi;
-                uint4 w[G];
-                if (ch < nch) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + (size_t)(fc + ch) * (512u * G)) + lane;
-#pragma unroll
-                    for (int s = 0; s < G; ++s) {
-                        const int pi = s >> 1;
-                        const bool last_odd = (G & 1) && s == G - 1;
-                        const int piece = last_odd ? G - 1 : 2 * pi + ((s & 1) ? 1 - (int)h : (int)h);
-                        w[s] = __ldg(src + 32 * piece);
-                    }
+        bool opened = false;
+        // (it, t) -> this group's next unit at or behind it.  1: found; 0: the sentinel (or a time-out); 2 (only when not
+        // `blocking`): the next item is not published yet.  Looking ahead must not block: the loader publishes item i + 2 only
+        // after item i is finished, which may need the very unit this warp still holds.
+        auto seek = [&](bool blocking) -> int {
+            for (;;) {
+                if (opened) {
+                    if (t < nt) return 1;
+                    u0 += nt;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.item_empty[slot]);
+                    ++it;
+                    opened = false;
                 }
-                if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
-                if (ch < nch) {
-#pragma unroll
-                    for (int s = 0; s < G; ++s) {
-                        constexpr int dummy = 0; (void)dummy;
-                        const int pi = s >> 1;
-                        const bool last_odd = (G & 1) && s == G - 1;
-                        const uint32_t sb = stage_base + (uint32_t)pi * kAAtom;
-                        // (the immediates are compile-time: the loop is fully unrolled over s)
-                        if (last_odd) {
-                            if (s == 0) decode16<(int)kTabAbs + 64 * 0>(w[s], pre0, sb + (lo0 ^ (h << 6)));
-                            if (s == 2) decode16<(int)kTabAbs + 64 * 2>(w[s], pre0, sb + (lo0 ^ (h << 6)));
-                        } else if ((s & 1) == 0) {
-                            if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre0, sb + lo0);
-                            if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre0, sb + lo0);
-                        } else {
-                            if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre1, sb + (lo0 ^ 0x40u));
-                            if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre1, sb + (lo0 ^ 0x40u));
-                        }
-                    }
-                }
-                fence_async_proxy();
-                mbar_arrive(&S.a_full[grp]);
+                slot = it % kItemRing;
+                const uint32_t par = (uint32_t)(it / kItemRing) & 1u;
+                if (blocking) { if (!mbar_wait(&S.item_full[slot], par, a.error, a.error_host)) return 0; }
+                else if (!__all_sync(0xFFFFFFFFu, mbar_try_wait(&S.item_full[slot], par))) return 2;
+                fc = S.items[slot].first_chunk; nch = S.items[slot].nchunks;
+                if (nch < 0) return 0;
+                nt = (nch + 3) >> 2;
+                t = (int)(((long long)grp - u0 % kStagesA + kStagesA) % kStagesA);
+                opened = true;
             }
-            if (!ok) break;
-            u0 += nt;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.item_empty[slot]);
-            ++it;
+        };
+        auto load = [&](uint4 (&w)[G], int ch) {
+            if (ch < nch) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + (size_t)(fc + ch) * (512u * G)) + lane;
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int pi = s >> 1;
+                    const bool last_odd = (G & 1) && s == G - 1;
+                    const int piece = last_odd ? G - 1 : 2 * pi + ((s & 1) ? 1 - (int)h : (int)h);
+                    w[s] = __ldg(src + 32 * piece);
+                }
+            }
+        };
+        auto process = [&](const uint4 (&w)[G], bool live, long long use) -> bool {
+            if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host)) return false;
+            if (live) {
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int pi = s >> 1;
+                    const bool last_odd = (G & 1) && s == G - 1;
+                    const uint32_t sb = stage_base + (uint32_t)pi * kAAtom;
+                    // (the immediates are compile-time: the loop is fully unrolled over s)
+                    if (last_odd) {
+                        if (s == 0) decode16<(int)kTabAbs + 64 * 0>(w[s], pre0, sb + (lo0 ^ (h << 6)));
+                        if (s == 2) decode16<(int)kTabAbs + 64 * 2>(w[s], pre0, sb + (lo0 ^ (h << 6)));
+                    } else if ((s & 1) == 0) {
+                        if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre0, sb + lo0);
+                        if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre0, sb + lo0);
+                    } else {
+                        if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre1, sb + (lo0 ^ 0x40u));
+                        if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre1, sb + (lo0 ^ 0x40u));
+                    }
+                }
+            }
+            fence_async_proxy();
+            mbar_arrive(&S.a_full[grp]);
+            return true;
+        };
+        uint4 wA[G], wB[G];
+        if (seek(true) == 1) {
+            load(wA, 4 * t + wi);
+            for (;;) {
+                bool live = 4 * t + wi < nch;
+                long long use = (u0 + t) / kStagesA;
+                t += kStagesA;
+                int r = seek(false);
+                if (r == 1) load(wB, 4 * t + wi);
+                if (!process(wA, live, use) || r == 0) break;
+                if (r == 2) { if (seek(true) != 1) break; load(wB, 4 * t + wi); }
+                live = 4 * t + wi < nch;
+                use = (u0 + t) / kStagesA;
+                t += kStagesA;
+                r = seek(false);
+                if (r == 1) load(wA, 4 * t + wi);
+                if (!process(wB, live, use) || r == 0) break;
+                if (r == 2) { if (seek(true) != 1) break; load(wA, 4 * t + wi); }
+            }
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------------------------------ MMA issuer
@@ -364,6 +397,12 @@ tc_scan_kernel(Args a) {
             if (nch < 0) break;
             const int nt = (nch + 3) >> 2;
             const int buf = it & 1;
+            // t_x of this thread's row of tile t; the NEXT tile's is in flight while this one is filtered
+            auto load_tx = [&](int t) {
+                const int ch = 4 * t + wq;
+                return (ch < nch && ch * 32 + (int)sl < len) ? __ldg(a.slot_tx + (((uint32_t)(fc + ch) << 5) + sl)) : 0.0f;
+            };
+            float tx_next = load_tx(0);
             if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host)) break;
             const float* tau = S.tau[buf];
             bool ok = true;
@@ -373,10 +412,11 @@ tc_scan_kernel(Args a) {
                 const int within = ch * 32 + (int)sl;
                 const bool valid = ch < nch && within < len;
                 const uint32_t g = ((uint32_t)(fc + ch) << 5) + sl;
-                const float tx = valid ? __ldg(a.slot_tx + g) : 0.0f;
-                const float hv = sc * (0.5f * tx - 1.5e-6f * fabsf(tx));
+                const float tx = tx_next;
+                tx_next = t + 1 < nt ? load_tx(t + 1) : 0.0f;
                 if (!mbar_wait(&S.d_full[db], (uint32_t)(u / kDBufs) & 1u, a.error, a.error_host)) { ok = false; break; }
                 fence_after_sync();
+                const float hv = sc * (0.5f * tx - 1.5e-6f * fabsf(tx));
                 for (int cb = 0; cb < n; cb += 16) {
                     float dv[16];
                     tmem_ld16(tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(db * kNQ + cb), dv);
@@ -553,6 +593,96 @@ seed_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, co
         if (ball) { const int src = __ffs(ball) - 1; l0 = __shfl_sync(0xFFFFFFFFu, l, src); p0 = base + src; break; }
     }
     if (lane == 0) { seed_list[i] = l0; seed_pos[i] = p0; }
+}
+
+// The seed: one WARP per query scans the first probed list that holds vectors here and keeps its k best -- exact keys, the
+// same table entries (lut_entry2 from the code-major codebooks, L1-resident) in the same summation order as the
+// look-up-table scan, but without building a 128 KB table for one list.  The k-th distance is the threshold of the filter.
+template <int G>
+__global__ void __launch_bounds__(256)
+seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* __restrict__ seed_list,
+                 const float* __restrict__ coarse, const float* __restrict__ codebooks_t, const int64_t* __restrict__ list_off,
+                 const int32_t* __restrict__ list_len, const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx,
+                 const int64_t* __restrict__ slot_ids, int k, int Pw, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    constexpr int m = 16 * G, d = 2 * m;
+    extern __shared__ __align__(16) unsigned char ssm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
+    if (q >= nq) return;
+    u64* wq = reinterpret_cast<u64*>(ssm) + (size_t)warp * Pw;
+    float2* sq = reinterpret_cast<float2*>(reinterpret_cast<u64*>(ssm) + (size_t)8 * Pw) + (size_t)warp * m;
+    const int l = seed_list[q];
+    if (l < 0) {
+        for (int i = lane; i < k; i += 32) write_result(kEmptyKey, 0, (size_t)q * k + i, out_dist, out_ids);
+        return;
+    }
+    const float* qv = queries + q * d;
+    // bias ||q - c_l||^2 in the order of probe_bias_kernel / build_probe_table (lane-strided partial sums, xor tree)
+    float bias = 0.0f;
+    {
+        const float* c = coarse + (int64_t)l * d;
+        for (int e = lane; e < d; e += 32) { const float df = __ldg(qv + e) - __ldg(c + e); bias = fmaf(df, df, bias); }
+        for (int o = 16; o > 0; o >>= 1) bias += __shfl_xor_sync(0xFFFFFFFFu, bias, o);
+    }
+    for (int j = lane; j < m; j += 32) sq[j] = make_float2(__ldg(qv + 2 * j) * -2.0f, __ldg(qv + 2 * j + 1) * -2.0f);
+    for (int i = lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+    __syncwarp();
+    const int len = __ldg(list_len + l);
+    const uint32_t first = (uint32_t)(__ldg(list_off + l) >> 5);
+    const int nch = (len + 31) >> 5;
+    const float2* cbt = reinterpret_cast<const float2*>(codebooks_t);
+    int cnt = 0;
+    uint32_t thr_u = 0xFFFFFFFFu;
+    const uint32_t rot = (uint32_t)lane & 15u;
+    for (int ch = 0; ch < nch; ++ch) {
+        const uint32_t g = ((first + (uint32_t)ch) << 5) + (uint32_t)lane;
+        const bool valid = ch * 32 + lane < len;
+        const uint4* src = reinterpret_cast<const uint4*>(slot_codes + (size_t)(first + ch) * (512u * G)) + lane;
+        float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) {
+            const uint4 w = __ldg(src + 32 * grp);
+            const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t b = 4 * i4 + t;
+                    const uint32_t code = (x[i4] >> (8 * t)) & 255u;
+                    const uint32_t j = 16u * grp + (b ^ rot);
+                    const float2 v = __ldg(cbt + code * m + j);
+                    const float2 qq = sq[j];
+                    s[t] = fadd(s[t], lut_entry2(qq.x, qq.y, v));
+                }
+            }
+        }
+        const float sum = fadd(fadd(bias, __ldg(slot_tx + g)), fadd(fadd(s[0], s[1]), fadd(s[2], s[3])));
+        const u64 key = make_key(sum, 0u, 0);
+        const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
+        if (thr_u == 0xFFFFFFFFu && k <= 32) {
+            const uint32_t kth = warp_kth_smallest(ku, k - 1, lane);       // k entries of this chunk are at least this good
+            if (kth != 0xFFFFFFFFu) thr_u = kth;
+        }
+        const bool pass = valid && ku <= thr_u;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
+        if (ball) {
+            if (cnt + 32 > Pw - k) {                                       // make room: keep the k best
+                for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+                __syncwarp();
+                bitonic_sort_keys<true>(wq, Pw, lane, 32);
+                const u64 t = wq[k - 1];
+                if (t != kEmptyKey) thr_u = min(thr_u, (uint32_t)(t >> 32));
+                cnt = 0;
+            }
+            if (pass) wq[k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)(uint32_t)slot_ids[g];
+            cnt += __popc(ball);
+            __syncwarp();
+        }
+    }
+    for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+    __syncwarp();
+    bitonic_sort_keys<true>(wq, Pw, lane, 32);
+    for (int i = lane; i < k; i += 32) write_result(wq[i], 0, (size_t)q * k + i, out_dist, out_ids);
 }
 
 // per query (one warp), after the seed scan: the fp16 row, u_q = -thr / 2 - eps_q, and whether the query can take this path
@@ -772,7 +902,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     Scratch<unsigned int> maxabs;
     Scratch<int32_t> seed_list, seed_pos, hist, off, cursor, bsum, fb_list;
     Scratch<int64_t> seed_ids;
-    Scratch<int> flag, counters, cand_cnt, wc_seed, wc_fb;
+    Scratch<int> flag, counters, cand_cnt, wc_fb;
     Scratch<__half> qh;
     Scratch<u64> cand;
     VIX_TRY(table.alloc(256 * 64));
@@ -797,7 +927,6 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_TRY(cand_cnt.alloc((size_t)nq));
     VIX_TRY(cand.alloc((size_t)nq * cap));
     VIX_TRY(fb_list.alloc((size_t)nq));
-    VIX_TRY(wc_seed.alloc(2));
     VIX_TRY(wc_fb.alloc(2));
     VIX_CUDA(cudaMemsetAsync(maxabs.ptr, 0, 4, s));
     VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)a.kc + 1) * 4, s));
@@ -811,13 +940,24 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_LAUNCH_CHECK();
     seed_probe_kernel<<<qwarps, 256, 0, s>>>(a.probes, nq, a.nprobe, a.list_len, a.kc, seed_list.ptr, seed_pos.ptr);
     VIX_LAUNCH_CHECK();
-    {   // seed: the look-up-table scan over the first probed list that holds vectors here
-        ScanArgs sd = a;
-        sd.probes = seed_list.ptr; sd.nprobe = 1;
-        sd.out_dist = seed_dist.ptr; sd.out_ids = seed_ids.ptr;
-        sd.scanned = nullptr; sd.bias = nullptr; sd.lut_image = nullptr;
-        sd.work_counter = wc_seed.ptr;
-        VIX_TRY(launch_ivfpq_scan_classic(sd));
+    {   // seed: the first probed list that holds vectors here, one warp per query
+        const int Pw = next_pow2(k + 64);
+        const size_t ssm = (size_t)8 * Pw * 8 + (size_t)8 * m * 8;
+        const unsigned sblocks = (unsigned)((nq + 7) / 8);
+#define VIX_SEED(GG)                                                                                                       \
+        do {                                                                                                               \
+            VIX_CUDA(cudaFuncSetAttribute(seed_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));    \
+            seed_scan_kernel<GG><<<sblocks, 256, ssm, s>>>(a.queries, nq, seed_list.ptr, a.coarse, a.codebooks_t, a.list_off, \
+                a.list_len, a.slot_codes, a.slot_tx, a.slot_ids, k, Pw, seed_dist.ptr, seed_ids.ptr);                      \
+            VIX_LAUNCH_CHECK();                                                                                            \
+        } while (0)
+        switch (G) {
+            case 1: VIX_SEED(1); break;
+            case 2: VIX_SEED(2); break;
+            case 3: VIX_SEED(3); break;
+            case 4: VIX_SEED(4); break;
+        }
+#undef VIX_SEED
     }
     query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, seed_dist.ptr, k, qh.ptr, uq.ptr,
                                             flag.ptr);

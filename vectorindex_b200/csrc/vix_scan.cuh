@@ -45,6 +45,7 @@ struct ScanLayout {
 ScanLayout scan_layout(int m);
 
 int launch_ivfpq_scan(ScanArgs& a);            // picks the path
+bool tc_scan_supported(const ScanArgs& a);     // would launch_ivfpq_scan take the list-major tensor-core path (vix_ivfpq_tc.cu)?
 int launch_ivfpq_scan_classic(ScanArgs& a);    // query-major look-up-table scan (vix_ivfpq_scan.cu)
 int launch_probe_bias(const ScanArgs& a, float* bias);   // bias[q x nprobe]: the per-probe term, batch-wide
 

@@ -16,6 +16,21 @@ namespace vix {
 // two paths produce the same bits.
 __device__ __forceinline__ float lut_entry2(float q0s, float q1s, float2 v) { return fmaf(q1s, v.y, q0s * v.x); }
 
+// k-th smallest (0-based rank kth) of one 32-bit key per lane: bitonic network over the warp
+static __device__ VIX_SCAN_FN uint32_t warp_kth_smallest(uint32_t v, int kth, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
+            const bool up = (lane & size) == 0 || size == 32;
+            const bool lower = (lane & stride) == 0;
+            v = (lower == up) ? min(v, other) : max(v, other);
+        }
+    }
+    return __shfl_sync(0xFFFFFFFFu, v, kth);
+}
+
 // ---- per-query prologue / epilogue pieces, kept out of line so that the scan loop owns the registers ----
 
 // warp 0: the k best of the n published candidates.  Keys are unique, so "the smallest key greater than the
