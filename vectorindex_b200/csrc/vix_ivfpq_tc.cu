@@ -67,6 +67,7 @@ constexpr uint32_t kBAtom = kNQ * 128;
 constexpr uint32_t kBBuf = 2 * kBAtom;
 constexpr uint32_t kEndAbs = kBBase + 2 * kBBuf;
 constexpr int kTmemCols = kDBufs * kNQ;                  // 256
+constexpr int kSeedChunks = 8;                           // the seed looks at the first 256 vectors of a query's first list
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);   // A, B fp16 (format 0), D fp32, K-major both
 
 struct Item { int first_chunk, nchunks, len, n, pair_begin, pad0, pad1, pad2; };
@@ -94,7 +95,8 @@ struct Args {
     const float* scales;           // [0] s_q, [1] s_c
     int nprobe, d, m;
     int* list_counter;
-    int* cand_cnt; u64* cand; int cap;
+    u64* log; int* log_cnt; int log_cap;   // survivors: one private log per filter warp [grid x 4][log_cap] (no atomics, no
+                                           // round trips on the filter's critical path); log_cnt[w] may exceed log_cap
     int smem_bytes;
     int* status;                   // layout refusal (loud)
     int* error; int* error_host;
@@ -388,6 +390,8 @@ tc_scan_kernel(Args a) {
         // ------------------------------------------------------------------------------------------ filter
         const int wq = warp - kEpiWarp0;                     // = warp % 4: the TMEM lane quarter this warp may read
         const uint32_t sl = lane_of_row((uint32_t)lane);     // TMEM lane = tile row -> slot of the chunk
+        u64* const mylog = a.log + (size_t)(blockIdx.x * 4 + wq) * (size_t)a.log_cap;
+        int nlog = 0;
         int it = 0;
         long long u = 0;
         for (;;) {
@@ -423,14 +427,16 @@ tc_scan_kernel(Args a) {
                     bool any = false;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) any |= dv[c] >= tau[cb + c] + hv;       // tau = NaN behind the last query
-                    if (any && valid) {
+                    if (__any_sync(0xFFFFFFFFu, any && valid)) {
+                        // rare: append (pair, slot) records to this warp's log -- positions from a ballot, plain stores
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            if (dv[c] >= tau[cb + c] + hv) {
-                                const uint32_t pr = S.pair[buf][cb + c];
-                                const uint32_t q = pr / (uint32_t)a.nprobe;
-                                const int pos = atomicAdd(a.cand_cnt + q, 1);
-                                if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = ((u64)pr << 32) | (u64)g;
+                            const bool hit = valid && dv[c] >= tau[cb + c] + hv;
+                            const unsigned ball = __ballot_sync(0xFFFFFFFFu, hit);
+                            if (ball) {
+                                const int pos = nlog + __popc(ball & ((1u << lane) - 1u));
+                                if (hit && pos < a.log_cap) mylog[pos] = ((u64)S.pair[buf][cb + c] << 32) | (u64)g;
+                                nlog += __popc(ball);
                             }
                         }
                     }
@@ -444,6 +450,7 @@ tc_scan_kernel(Args a) {
             if (lane == 0) { mbar_arrive(&S.b_empty[buf]); mbar_arrive(&S.item_empty[slot]); }
             ++it;
         }
+        if (lane == 0) a.log_cnt[blockIdx.x * 4 + wq] = nlog;
     } else if (warp == kLoadWarp) {
         // ------------------------------------------------------------------------------------------ work + B tiles
         constexpr int CH = m / 4;                             // 16-byte pieces of a query row (d = 2 m halves)
@@ -595,15 +602,18 @@ seed_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, co
     if (lane == 0) { seed_list[i] = l0; seed_pos[i] = p0; }
 }
 
-// The seed: one WARP per query scans the first probed list that holds vectors here and keeps its k best -- exact keys, the
-// same table entries (lut_entry2 from the code-major codebooks, L1-resident) in the same summation order as the
-// look-up-table scan, but without building a 128 KB table for one list.  The k-th distance is the threshold of the filter.
+// The seed: one WARP per query evaluates the first kSeedChunks x 32 vectors of the first probed list that holds vectors here
+// and keeps their k best -- exact keys, the same table entries (lut_entry2 from the code-major codebooks, L1-resident) in
+// the same summation order as the look-up-table scan, but without building a 128 KB table.  The k-th of ANY k stored
+// vectors is an upper bound of the query's k-th best distance: that is the threshold of the filter.  (The whole list would
+// give a tighter threshold and fewer finalists, but costs more than the finalists it saves: C5 1.77 ms against 0.3 ms.)
 template <int G>
 __global__ void __launch_bounds__(256)
 seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* __restrict__ seed_list,
                  const float* __restrict__ coarse, const float* __restrict__ codebooks_t, const int64_t* __restrict__ list_off,
                  const int32_t* __restrict__ list_len, const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx,
-                 const int64_t* __restrict__ slot_ids, int k, int Pw, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+                 const int64_t* __restrict__ slot_ids, int k, int Pw, int max_chunks, float* __restrict__ out_dist,
+                 int64_t* __restrict__ out_ids) {
     constexpr int m = 16 * G, d = 2 * m;
     extern __shared__ __align__(16) unsigned char ssm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -629,7 +639,7 @@ seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
     __syncwarp();
     const int len = __ldg(list_len + l);
     const uint32_t first = (uint32_t)(__ldg(list_off + l) >> 5);
-    const int nch = (len + 31) >> 5;
+    const int nch = min((len + 31) >> 5, max_chunks);               // a SAMPLE of the list: any k vectors bound the k-th best
     const float2* cbt = reinterpret_cast<const float2*>(codebooks_t);
     int cnt = 0;
     uint32_t thr_u = 0xFFFFFFFFu;
@@ -719,7 +729,7 @@ query_prep_kernel(const float* __restrict__ queries, int64_t nq, int d, const fl
 // (query, probe position) pairs of this path, counted per list; also the entries every valid pair visits (statistics)
 __global__ void __launch_bounds__(256)
 pair_count_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe, const int32_t* __restrict__ list_len, int kc,
-                  const int32_t* __restrict__ seed_pos, const int* __restrict__ flag, int32_t* __restrict__ hist,
+                  const int* __restrict__ flag, int32_t* __restrict__ hist,
                   unsigned long long* __restrict__ scanned) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long vis = 0;
@@ -728,8 +738,7 @@ pair_count_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe
         if ((unsigned)l < (unsigned)kc) {
             const int len = __ldg(list_len + l);
             vis = (unsigned long long)len;
-            const int64_t q = i / nprobe;
-            if (len > 0 && !flag[q] && (int)(i - q * nprobe) != seed_pos[q]) atomicAdd(hist + l, 1);
+            if (len > 0 && !flag[i / nprobe]) atomicAdd(hist + l, 1);
         }
     }
     if (scanned) {
@@ -739,14 +748,13 @@ pair_count_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe
 }
 __global__ void __launch_bounds__(256)
 pair_scatter_kernel(const int32_t* __restrict__ probes, int64_t npairs, int nprobe, const int32_t* __restrict__ list_len, int kc,
-                    const int32_t* __restrict__ seed_pos, const int* __restrict__ flag, int32_t* __restrict__ cursor,
+                    const int* __restrict__ flag, int32_t* __restrict__ cursor,
                     uint32_t* __restrict__ pairs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     const int l = __ldg(probes + i);
     if ((unsigned)l >= (unsigned)kc || __ldg(list_len + l) <= 0) return;
-    const int64_t q = i / nprobe;
-    if (flag[q] || (int)(i - q * nprobe) == seed_pos[q]) return;
+    if (flag[i / nprobe]) return;
     pairs[atomicAdd(cursor + l, 1)] = (uint32_t)i;
 }
 
@@ -794,38 +802,36 @@ block_scan_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __rest
     }
 }
 
-// one warp per query: the candidates in the look-up-table scan's arithmetic, selected with the seed results
+// The finalists.  One CTA per log, one thread per (pair, slot) record: the record is replaced by its exact key -- the
+// look-up-table scan's arithmetic: the same table entries (lut_entry2), the same four partial sums in the same order -- and
+// the query it belongs to is counted.  (Per record, not per query: a few queries have thousands of survivors.)
+// A log that overflowed hands every query back (flagged through *overflow).
 template <int G>
-__global__ void __launch_bounds__(128)
-finalist_kernel(const float* __restrict__ queries, int64_t nq, int nprobe, const float* __restrict__ bias,
-                const float* __restrict__ codebooks_t, const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx,
-                const int64_t* __restrict__ slot_ids, const int* __restrict__ cand_cnt, const u64* __restrict__ cand, int cap,
-                const float* __restrict__ seed_dist, const int64_t* __restrict__ seed_ids, int k, const int* __restrict__ flag,
-                int32_t* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+__global__ void __launch_bounds__(256)
+log_key_kernel(u64* __restrict__ log, const int* __restrict__ log_cnt, int log_cap, uint32_t* __restrict__ log_q,
+               const float* __restrict__ queries, int nprobe, const float* __restrict__ bias, const float* __restrict__ codebooks_t,
+               const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx, const int64_t* __restrict__ slot_ids,
+               int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
     constexpr int m = 16 * G;
-    extern __shared__ __align__(16) unsigned char fsm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
-    if (q >= nq) return;
-    u64* keys = reinterpret_cast<u64*>(fsm) + (size_t)warp * (cap + 64);
-    float* sq = reinterpret_cast<float*>(reinterpret_cast<u64*>(fsm) + (size_t)4 * (cap + 64)) + (size_t)warp * (2 * m);
-    const int cnt = cand_cnt[q];
-    if (flag[q] || cnt > cap) {
-        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)q;
-        return;
-    }
-    for (int e = lane; e < 2 * m; e += 32) sq[e] = __ldg(queries + q * (2 * m) + e) * -2.0f;   // the table build's pre-scaled query
-    __syncwarp();
-    for (int i = lane; i < cnt; i += 32) {
-        const u64 c = cand[(size_t)q * cap + i];
+    const int w = blockIdx.x;
+    int n = log_cnt[w];
+    if (n > log_cap) { if (threadIdx.x == 0) *overflow = 1; n = log_cap; }
+    u64* recs = log + (size_t)w * log_cap;
+    const float2* cbt = reinterpret_cast<const float2*>(codebooks_t);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const u64 c = recs[i];
         const uint32_t pr = (uint32_t)(c >> 32), g = (uint32_t)c;
+        const uint32_t q = pr / (uint32_t)nprobe;
         const uint32_t sl = g & 31u;
         const uint4* src = reinterpret_cast<const uint4*>(slot_codes + (size_t)(g >> 5) * (512u * G)) + sl;
+        const float2* qv = reinterpret_cast<const float2*>(queries + (size_t)q * (2 * m));
+        uint4 w4[G];
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) w4[grp] = __ldg(src + 32 * grp);
         float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int grp = 0; grp < G; ++grp) {
-            const uint4 w = __ldg(src + 32 * grp);
-            const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+            const uint32_t x[4] = {w4[grp].x, w4[grp].y, w4[grp].z, w4[grp].w};
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
 #pragma unroll
@@ -833,22 +839,45 @@ finalist_kernel(const float* __restrict__ queries, int64_t nq, int nprobe, const
                     const uint32_t b = 4 * i4 + t;
                     const uint32_t code = (x[i4] >> (8 * t)) & 255u;
                     const uint32_t j = 16u * grp + ((b ^ sl) & 15u);
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(codebooks_t + ((size_t)code * m + j) * 2));
-                    s[t] = fadd(s[t], lut_entry2(sq[2 * j], sq[2 * j + 1], v));
+                    const float2 v = __ldg(cbt + code * m + j);
+                    const float2 qq = __ldg(qv + j);
+                    s[t] = fadd(s[t], lut_entry2(qq.x * -2.0f, qq.y * -2.0f, v));     // the table build's pre-scaled query
                 }
             }
         }
         const float sum = fadd(fadd(__ldg(bias + pr), __ldg(slot_tx + g)), fadd(fadd(s[0], s[1]), fadd(s[2], s[3])));
-        keys[i] = make_key(sum, 0u, 0) | (u64)(uint32_t)slot_ids[g];
+        recs[i] = make_key(sum, 0u, 0) | (u64)(uint32_t)slot_ids[g];
+        log_q[(size_t)w * log_cap + i] = q;
+        atomicAdd(cand_cnt + q, 1);
     }
-    int n = cnt;
-    for (int i = lane; i < k; i += 32) {                       // the seed's results (its list is not among the pairs)
-        const int64_t id = seed_ids[q * k + i];
-        keys[cnt + i] = id >= 0 ? (make_key(seed_dist[q * k + i], 0u, 0) | (u64)(uint32_t)id) : kEmptyKey;
+}
+
+// keys -> one contiguous run per query (cursor = the exclusive prefix sums of the counts)
+__global__ void __launch_bounds__(256)
+key_scatter_kernel(const u64* __restrict__ log, const int* __restrict__ log_cnt, int log_cap, const uint32_t* __restrict__ log_q,
+                   int32_t* __restrict__ cursor, u64* __restrict__ keys) {
+    const int w = blockIdx.x;
+    const int n = min(log_cnt[w], log_cap);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const size_t at = (size_t)w * log_cap + i;
+        keys[atomicAdd(cursor + log_q[at], 1)] = log[at];
     }
-    n += k;
-    __syncwarp();
-    select_and_write(keys, n, k, 0, q, out_dist, out_ids);
+}
+
+// one warp per query: the k best of its keys by (score, id) -- or the query is handed back
+__global__ void __launch_bounds__(128)
+select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict__ keys, int k, const int* __restrict__ flag,
+              const int* __restrict__ overflow, int32_t* __restrict__ fb_list, int* __restrict__ fb_count,
+              float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    if (flag[q] || *overflow) {
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)q;
+        return;
+    }
+    // (the seed's k vectors passed the filter: at least k keys)
+    select_and_write(keys + off[q], off[q + 1] - off[q], k, 0, q, out_dist, out_ids);
 }
 
 __global__ void smem_base_kernel(uint32_t* out) {
@@ -894,15 +923,15 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     cudaStream_t s = ctx().stream;
     const int64_t nq = a.nq, npairs = a.nq * (int64_t)a.nprobe;
     const int k = a.k, m = a.m, d = a.d, G = m / 16;
-    int cap = 1024;
-    while (cap > 128 && (size_t)nq * cap * 8 > (1ull << 30)) cap >>= 1;
 
     Scratch<uint32_t> table, pairs;
     Scratch<float> meta, qnorm, uq, seed_dist, bias;
     Scratch<unsigned int> maxabs;
     Scratch<int32_t> seed_list, seed_pos, hist, off, cursor, bsum, fb_list;
     Scratch<int64_t> seed_ids;
-    Scratch<int> flag, counters, cand_cnt, wc_fb;
+    Scratch<int> flag, counters, wc_fb;
+    Scratch<int32_t> cand_cnt, cand_off, cand_cur;
+    Scratch<uint32_t> log_q;
     Scratch<__half> qh;
     Scratch<u64> cand;
     VIX_TRY(table.alloc(256 * 64));
@@ -923,14 +952,15 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_TRY(bsum.alloc((size_t)nblk));
     VIX_TRY(pairs.alloc((size_t)npairs));
     VIX_TRY(bias.alloc((size_t)npairs));
-    VIX_TRY(counters.alloc(4));                    // [0] list counter, [1] error, [2] fall-back count
-    VIX_TRY(cand_cnt.alloc((size_t)nq));
-    VIX_TRY(cand.alloc((size_t)nq * cap));
+    VIX_TRY(counters.alloc(8));                    // [0] list counter, [1] error, [2] fall-back count, [3] status, [4] log overflow
+    VIX_TRY(cand_cnt.alloc((size_t)nq + 1));
+    VIX_TRY(cand_off.alloc((size_t)nq + 1));
+    VIX_TRY(cand_cur.alloc((size_t)nq + 1));
     VIX_TRY(fb_list.alloc((size_t)nq));
     VIX_TRY(wc_fb.alloc(2));
     VIX_CUDA(cudaMemsetAsync(maxabs.ptr, 0, 4, s));
     VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)a.kc + 1) * 4, s));
-    VIX_CUDA(cudaMemsetAsync(counters.ptr, 0, 16, s));
+    VIX_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, s));
     VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
 
     table_kernel<<<1, 1024, 0, s>>>(a.codebooks, m, table.ptr, meta.ptr);
@@ -948,7 +978,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         do {                                                                                                               \
             VIX_CUDA(cudaFuncSetAttribute(seed_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));    \
             seed_scan_kernel<GG><<<sblocks, 256, ssm, s>>>(a.queries, nq, seed_list.ptr, a.coarse, a.codebooks_t, a.list_off, \
-                a.list_len, a.slot_codes, a.slot_tx, a.slot_ids, k, Pw, seed_dist.ptr, seed_ids.ptr);                      \
+                a.list_len, a.slot_codes, a.slot_tx, a.slot_ids, k, Pw, kSeedChunks, seed_dist.ptr, seed_ids.ptr);                      \
             VIX_LAUNCH_CHECK();                                                                                            \
         } while (0)
         switch (G) {
@@ -963,38 +993,45 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
                                             flag.ptr);
     VIX_LAUNCH_CHECK();
     const unsigned pblocks = (unsigned)((npairs + 255) / 256);
-    pair_count_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, seed_pos.ptr, flag.ptr, hist.ptr, a.scanned);
+    pair_count_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, flag.ptr, hist.ptr, a.scanned);
     VIX_LAUNCH_CHECK();
     block_sum_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.kc, bsum.ptr);
     VIX_LAUNCH_CHECK();
     block_scan_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.kc, bsum.ptr, off.ptr, cursor.ptr);
     VIX_LAUNCH_CHECK();
-    pair_scatter_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, seed_pos.ptr, flag.ptr, cursor.ptr,
+    pair_scatter_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, flag.ptr, cursor.ptr,
                                                pairs.ptr);
     VIX_LAUNCH_CHECK();
     VIX_TRY(launch_probe_bias(a, bias.ptr));
 
+    int grid = num_sms();
+    if (grid > a.kc) grid = a.kc;
+    // room for 256 survivors per query over all logs (C5: ~100 per query with the sampled seed), at least 4096 per log
+    const int64_t want = (nq * 256 + grid * 4 - 1) / (grid * 4);
+    const int log_cap = (int)(want < 4096 ? 4096 : want);
+    Scratch<u64> log;
+    Scratch<int> log_cnt;
+    VIX_TRY(log.alloc((size_t)grid * 4 * log_cap));
+    VIX_TRY(log_cnt.alloc((size_t)grid * 4));
+    VIX_TRY(log_q.alloc((size_t)grid * 4 * log_cap));
+    VIX_TRY(cand.alloc((size_t)grid * 4 * log_cap));
+    VIX_CUDA(cudaMemsetAsync(log_cnt.ptr, 0, (size_t)grid * 4 * sizeof(int), s));
     Args t{};
     t.slot_codes = a.slot_codes; t.slot_tx = a.slot_tx; t.list_off = a.list_off; t.list_len = a.list_len; t.kc = a.kc;
     t.pair_off = off.ptr; t.pairs = pairs.ptr; t.bias = bias.ptr; t.qh = qh.ptr; t.uq = uq.ptr; t.table = table.ptr;
     t.scales = meta.ptr; t.nprobe = a.nprobe; t.d = d; t.m = m;
-    t.list_counter = counters.ptr; t.cand_cnt = cand_cnt.ptr; t.cand = cand.ptr; t.cap = cap;
+    t.list_counter = counters.ptr; t.log = log.ptr; t.log_cnt = log_cnt.ptr; t.log_cap = log_cap;
     t.error = counters.ptr + 1; t.error_host = pipeline_error_flag();
     t.status = t.error_host ? t.error_host : counters.ptr + 3;
     const int smem = (int)kEndAbs - smem_base();
     t.smem_bytes = smem;
-    int grid = num_sms();
-    if (grid > a.kc) grid = a.kc;
 #define VIX_TCS(GG)                                                                                                        \
     do {                                                                                                                   \
         VIX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
         tc_scan_kernel<GG><<<grid, kThreads, smem, s>>>(t);                                                                \
         VIX_LAUNCH_CHECK();                                                                                                \
-        const size_t fsm = (size_t)4 * (cap + 64) * 8 + (size_t)4 * 2 * m * 4;                                             \
-        VIX_CUDA(cudaFuncSetAttribute(finalist_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));         \
-        finalist_kernel<GG><<<(unsigned)((nq + 3) / 4), 128, fsm, s>>>(a.queries, nq, a.nprobe, bias.ptr, a.codebooks_t,    \
-            a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, cand.ptr, cap, seed_dist.ptr, seed_ids.ptr, k, flag.ptr,    \
-            fb_list.ptr, counters.ptr + 2, a.out_dist, a.out_ids);                                                         \
+        log_key_kernel<GG><<<grid * 4, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
+            a.codebooks_t, a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, counters.ptr + 4);                           \
         VIX_LAUNCH_CHECK();                                                                                                \
     } while (0)
     switch (G) {
@@ -1004,6 +1041,19 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         case 4: VIX_TCS(4); break;
     }
 #undef VIX_TCS
+    {   // per-query runs of keys, then the selection
+        const int qblk = (int)((nq + kScanBlock - 1) / kScanBlock);
+        VIX_TRY(bsum.alloc((size_t)qblk));
+        block_sum_kernel<<<qblk, 256, 0, s>>>(cand_cnt.ptr, (int)nq, bsum.ptr);
+        VIX_LAUNCH_CHECK();
+        block_scan_kernel<<<qblk, 256, 0, s>>>(cand_cnt.ptr, (int)nq, bsum.ptr, cand_off.ptr, cand_cur.ptr);
+        VIX_LAUNCH_CHECK();
+        key_scatter_kernel<<<grid * 4, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, cand_cur.ptr, cand.ptr);
+        VIX_LAUNCH_CHECK();
+        select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(nq, cand_off.ptr, cand.ptr, k, flag.ptr, counters.ptr + 4, fb_list.ptr,
+                                                              counters.ptr + 2, a.out_dist, a.out_ids);
+        VIX_LAUNCH_CHECK();
+    }
     {   // the queries handed back: all their probes through the look-up-table scan
         ScanArgs fb = a;
         fb.order = fb_list.ptr; fb.nq_dev = counters.ptr + 2;
@@ -1022,8 +1072,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         long long tot = 0;
         int mx = 0;
         for (int64_t i = 0; i < nq; ++i) { tot += cc[(size_t)i]; mx = cc[(size_t)i] > mx ? cc[(size_t)i] : mx; }
-        fprintf(stderr, "[vix tc scan] nq %lld, handed back %d, candidates %lld (max %d per query, cap %d), error %d\n", (long long)nq,
-                hc[2], tot, mx, cap, hc[1]);
+        fprintf(stderr, "[vix tc scan] nq %lld, handed back %d, candidates %lld (max %d per query; %d per log), error %d\n", (long long)nq,
+                hc[2], tot, mx, log_cap, hc[1]);
     }
     return VIX_OK;
 }
