@@ -56,8 +56,11 @@ constexpr int kNQ = 64;                                  // query columns per it
 constexpr int kStagesA = 3;                              // = decoder groups
 constexpr int kItemRing = 4;
 constexpr int kDBufs = 4;                                // accumulator buffers in TMEM (kDBufs x kNQ columns)
-constexpr int kDecWarps = 4 * kStagesA, kEpiWarp0 = kDecWarps, kMmaWarp = kEpiWarp0 + 4, kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = 32 * (kLoadWarp + 1);           // 576
+constexpr int kEpiSets = 2;                              // filter warp sets: set e takes the units u % kEpiSets == e
+constexpr int kEpiWarps = 4 * kEpiSets;
+constexpr int kDecWarps = 4 * kStagesA, kEpiWarp0 = kDecWarps, kMmaWarp = kEpiWarp0 + kEpiWarps, kLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = 32 * (kLoadWarp + 1);           // 704
+static_assert(kEpiWarp0 % 4 == 0 && kDBufs % kEpiSets == 0, "a filter warp reads the TMEM lane quarter warp % 4");
 constexpr uint32_t kTabAbs = 4096;                       // ABSOLUTE shared addresses: the table's travels in the LDS immediate
 constexpr uint32_t kABase = kTabAbs + 65536;
 constexpr uint32_t kAAtom = 128 * 128;                   // one K-atom (64 halves) of 128 rows
@@ -100,6 +103,7 @@ struct Args {
     int smem_bytes;
     int* status;                   // layout refusal (loud)
     int* error; int* error_host;
+    unsigned long long* diag;      // VIX_TCS_DIAG builds: waiting cycles per role and barrier kind
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -119,7 +123,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error, int* error_host) {
+#ifdef VIX_TCS_DIAG
+#define VIX_DG(i) dg[i]
+#else
+#define VIX_DG(i) dg_none
+#endif
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error, int* error_host, unsigned long long& waited) {
+#ifdef VIX_TCS_DIAG
+    const long long w0 = clock64();
+    struct Acc { unsigned long long& w; long long t; __device__ ~Acc() { w += (unsigned long long)(clock64() - t); } } acc{waited, w0};
+#endif
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
@@ -225,11 +238,14 @@ tc_scan_kernel(Args a) {
     Small& S = *reinterpret_cast<Small*>(smem_raw);
     unsigned char* const abs0 = smem_raw - dyn_abs;          // generic pointer of absolute shared address 0
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long dg[4] = {0, 0, 0, 0}, dg_none = 0;      // VIX_TCS_DIAG: cycles this thread waited, per barrier kind
+    (void)dg; (void)dg_none;
+    const long long dg_t0 = clock64();
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kItemRing; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kDecWarps + 4 + 1); }
+        for (int i = 0; i < kItemRing; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kDecWarps + kEpiWarps + 1); }
         for (int i = 0; i < kStagesA; ++i) { mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.b_full[i], 32); mbar_init(&S.b_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.b_full[i], 32); mbar_init(&S.b_empty[i], kEpiWarps); }
         for (int i = 0; i < kDBufs; ++i) { mbar_init(&S.d_full[i], 1); mbar_init(&S.d_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -285,7 +301,7 @@ tc_scan_kernel(Args a) {
                 }
                 slot = it % kItemRing;
                 const uint32_t par = (uint32_t)(it / kItemRing) & 1u;
-                if (blocking) { if (!mbar_wait(&S.item_full[slot], par, a.error, a.error_host)) return 0; }
+                if (blocking) { if (!mbar_wait(&S.item_full[slot], par, a.error, a.error_host, VIX_DG(0))) return 0; }
                 else if (!__all_sync(0xFFFFFFFFu, mbar_try_wait(&S.item_full[slot], par))) return 2;
                 fc = S.items[slot].first_chunk; nch = S.items[slot].nchunks;
                 if (nch < 0) return 0;
@@ -307,7 +323,7 @@ tc_scan_kernel(Args a) {
             }
         };
         auto process = [&](const uint4 (&w)[G], bool live, long long use) -> bool {
-            if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host)) return false;
+            if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host, VIX_DG(1))) return false;
             if (live) {
 #pragma unroll
                 for (int s = 0; s < G; ++s) {
@@ -358,18 +374,18 @@ tc_scan_kernel(Args a) {
             long long u = 0;
             for (;;) {
                 const int slot = it % kItemRing;
-                if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
+                if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host, VIX_DG(0))) break;
                 const int nch = S.items[slot].nchunks, n = S.items[slot].n;
                 if (nch < 0) break;
                 const int nt = (nch + 3) >> 2;
                 const uint32_t idesc = kIdescF16 | ((uint32_t)(((n + 15) & ~15) >> 3) << 17);
                 const int buf = it & 1;
-                if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host)) break;
+                if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host, VIX_DG(1))) break;
                 bool ok = true;
                 for (int t = 0; t < nt; ++t, ++u) {
                     const int st = (int)(u % kStagesA), db = (int)(u % kDBufs);
-                    if (!mbar_wait(&S.a_full[st], (uint32_t)(u / kStagesA) & 1u, a.error, a.error_host)) { ok = false; break; }
-                    if (u >= kDBufs && !mbar_wait(&S.d_empty[db], (uint32_t)(u / kDBufs - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                    if (!mbar_wait(&S.a_full[st], (uint32_t)(u / kStagesA) & 1u, a.error, a.error_host, VIX_DG(2))) { ok = false; break; }
+                    if (u >= kDBufs && !mbar_wait(&S.d_empty[db], (uint32_t)(u / kDBufs - 1) & 1u, a.error, a.error_host, VIX_DG(3))) { ok = false; break; }
                     fence_after_sync();
                     const uint32_t dcol = tmem_base + (uint32_t)(db * kNQ);
 #pragma unroll
@@ -386,17 +402,18 @@ tc_scan_kernel(Args a) {
                 ++it;
             }
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
         // ------------------------------------------------------------------------------------------ filter
-        const int wq = warp - kEpiWarp0;                     // = warp % 4: the TMEM lane quarter this warp may read
+        const int wq = (warp - kEpiWarp0) & 3;               // = warp % 4: the TMEM lane quarter this warp may read
+        const int eset = (warp - kEpiWarp0) >> 2;            // this warp's set filters the units u % kEpiSets == eset
         const uint32_t sl = lane_of_row((uint32_t)lane);     // TMEM lane = tile row -> slot of the chunk
-        u64* const mylog = a.log + (size_t)(blockIdx.x * 4 + wq) * (size_t)a.log_cap;
+        u64* const mylog = a.log + (size_t)(blockIdx.x * kEpiWarps + (warp - kEpiWarp0)) * (size_t)a.log_cap;
         int nlog = 0;
         int it = 0;
         long long u = 0;
         for (;;) {
             const int slot = it % kItemRing;
-            if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host)) break;
+            if (!mbar_wait(&S.item_full[slot], (uint32_t)(it / kItemRing) & 1u, a.error, a.error_host, VIX_DG(0))) break;
             const int fc = S.items[slot].first_chunk, nch = S.items[slot].nchunks, len = S.items[slot].len, n = S.items[slot].n;
             if (nch < 0) break;
             const int nt = (nch + 3) >> 2;
@@ -406,19 +423,22 @@ tc_scan_kernel(Args a) {
                 const int ch = 4 * t + wq;
                 return (ch < nch && ch * 32 + (int)sl < len) ? __ldg(a.slot_tx + (((uint32_t)(fc + ch) << 5) + sl)) : 0.0f;
             };
-            float tx_next = load_tx(0);
-            if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host)) break;
+            // this set's tiles of the item: t0, t0 + kEpiSets, ... ((u + t) % kEpiSets == eset)
+            const int t0 = (int)(((long long)eset - u % kEpiSets + kEpiSets) % kEpiSets);
+            float tx_next = load_tx(t0);
+            if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host, VIX_DG(1))) break;
             const float* tau = S.tau[buf];
             bool ok = true;
-            for (int t = 0; t < nt; ++t, ++u) {
-                const int db = (int)(u % kDBufs);
+            for (int t = t0; t < nt; t += kEpiSets) {
+                const long long uu = u + t;
+                const int db = (int)(uu % kDBufs);
                 const int ch = 4 * t + wq;
                 const int within = ch * 32 + (int)sl;
                 const bool valid = ch < nch && within < len;
                 const uint32_t g = ((uint32_t)(fc + ch) << 5) + sl;
                 const float tx = tx_next;
-                tx_next = t + 1 < nt ? load_tx(t + 1) : 0.0f;
-                if (!mbar_wait(&S.d_full[db], (uint32_t)(u / kDBufs) & 1u, a.error, a.error_host)) { ok = false; break; }
+                tx_next = t + kEpiSets < nt ? load_tx(t + kEpiSets) : 0.0f;
+                if (!mbar_wait(&S.d_full[db], (uint32_t)(uu / kDBufs) & 1u, a.error, a.error_host, VIX_DG(2))) { ok = false; break; }
                 fence_after_sync();
                 const float hv = sc * (0.5f * tx - 1.5e-6f * fabsf(tx));
                 for (int cb = 0; cb < n; cb += 16) {
@@ -446,11 +466,12 @@ tc_scan_kernel(Args a) {
                 if (lane == 0) mbar_arrive(&S.d_empty[db]);
             }
             if (!ok) break;
+            u += nt;
             __syncwarp();
             if (lane == 0) { mbar_arrive(&S.b_empty[buf]); mbar_arrive(&S.item_empty[slot]); }
             ++it;
         }
-        if (lane == 0) a.log_cnt[blockIdx.x * 4 + wq] = nlog;
+        if (lane == 0) a.log_cnt[blockIdx.x * kEpiWarps + (warp - kEpiWarp0)] = nlog;
     } else if (warp == kLoadWarp) {
         // ------------------------------------------------------------------------------------------ work + B tiles
         constexpr int CH = m / 4;                             // 16-byte pieces of a query row (d = 2 m halves)
@@ -458,7 +479,7 @@ tc_scan_kernel(Args a) {
         bool ok = true;
         auto publish = [&](int fc, int nch, int len, int n, int pb) {
             const int slot = it % kItemRing;
-            if (it >= kItemRing && !mbar_wait(&S.item_empty[slot], (uint32_t)(it / kItemRing - 1) & 1u, a.error, a.error_host)) return false;
+            if (it >= kItemRing && !mbar_wait(&S.item_empty[slot], (uint32_t)(it / kItemRing - 1) & 1u, a.error, a.error_host, VIX_DG(0))) return false;
             if (lane == 0) {
                 Item& I = S.items[slot];
                 I.first_chunk = fc; I.nchunks = nch; I.len = len; I.n = n; I.pair_begin = pb;
@@ -481,7 +502,7 @@ tc_scan_kernel(Args a) {
                 const int n = min(kNQ, pe - g0);
                 if (!publish(fc, nch, len, n, g0)) { ok = false; break; }
                 const int buf = it & 1;
-                if (it >= 2 && !mbar_wait(&S.b_empty[buf], (uint32_t)((it >> 1) - 1) & 1u, a.error, a.error_host)) { ok = false; break; }
+                if (it >= 2 && !mbar_wait(&S.b_empty[buf], (uint32_t)((it >> 1) - 1) & 1u, a.error, a.error_host, VIX_DG(1))) { ok = false; break; }
                 const uint32_t bbase = kBBase + (uint32_t)buf * kBBuf;
                 for (int idx = lane; idx < n * CH; idx += 32) {
                     const int c = idx / CH, chn = idx - c * CH;
@@ -511,6 +532,14 @@ tc_scan_kernel(Args a) {
         }
         if (ok) publish(0, -1, 0, 0, 0);
     }
+#ifdef VIX_TCS_DIAG
+    if (a.diag && lane == 0) {
+        // roles: 0 decoders (12 warps), 1 filter (4 warps), 2 MMA, 3 loader; [role][4 waits] + [role] total cycles at 16 + role
+        const int role = warp < kDecWarps ? 0 : warp < kMmaWarp ? 1 : warp == kMmaWarp ? 2 : 3;
+        for (int i = 0; i < 4; ++i) atomicAdd(a.diag + role * 4 + i, dg[i]);
+        atomicAdd(a.diag + 16 + role, (unsigned long long)(clock64() - dg_t0));
+    }
+#endif
     fence_before_sync();
     __syncthreads();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
@@ -1007,15 +1036,15 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     int grid = num_sms();
     if (grid > a.kc) grid = a.kc;
     // room for 256 survivors per query over all logs (C5: ~100 per query with the sampled seed), at least 4096 per log
-    const int64_t want = (nq * 256 + grid * 4 - 1) / (grid * 4);
+    const int64_t want = (nq * 256 + grid * kEpiWarps - 1) / (grid * kEpiWarps);
     const int log_cap = (int)(want < 4096 ? 4096 : want);
     Scratch<u64> log;
     Scratch<int> log_cnt;
-    VIX_TRY(log.alloc((size_t)grid * 4 * log_cap));
-    VIX_TRY(log_cnt.alloc((size_t)grid * 4));
-    VIX_TRY(log_q.alloc((size_t)grid * 4 * log_cap));
-    VIX_TRY(cand.alloc((size_t)grid * 4 * log_cap));
-    VIX_CUDA(cudaMemsetAsync(log_cnt.ptr, 0, (size_t)grid * 4 * sizeof(int), s));
+    VIX_TRY(log.alloc((size_t)grid * kEpiWarps * log_cap));
+    VIX_TRY(log_cnt.alloc((size_t)grid * kEpiWarps));
+    VIX_TRY(log_q.alloc((size_t)grid * kEpiWarps * log_cap));
+    VIX_TRY(cand.alloc((size_t)grid * kEpiWarps * log_cap));
+    VIX_CUDA(cudaMemsetAsync(log_cnt.ptr, 0, (size_t)grid * kEpiWarps * sizeof(int), s));
     Args t{};
     t.slot_codes = a.slot_codes; t.slot_tx = a.slot_tx; t.list_off = a.list_off; t.list_len = a.list_len; t.kc = a.kc;
     t.pair_off = off.ptr; t.pairs = pairs.ptr; t.bias = bias.ptr; t.qh = qh.ptr; t.uq = uq.ptr; t.table = table.ptr;
@@ -1023,6 +1052,12 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     t.list_counter = counters.ptr; t.log = log.ptr; t.log_cnt = log_cnt.ptr; t.log_cap = log_cap;
     t.error = counters.ptr + 1; t.error_host = pipeline_error_flag();
     t.status = t.error_host ? t.error_host : counters.ptr + 3;
+#ifdef VIX_TCS_DIAG
+    Scratch<unsigned long long> diag;
+    VIX_TRY(diag.alloc(32));
+    VIX_CUDA(cudaMemsetAsync(diag.ptr, 0, 256, s));
+    t.diag = diag.ptr;
+#endif
     const int smem = (int)kEndAbs - smem_base();
     t.smem_bytes = smem;
 #define VIX_TCS(GG)                                                                                                        \
@@ -1030,7 +1065,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         VIX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
         tc_scan_kernel<GG><<<grid, kThreads, smem, s>>>(t);                                                                \
         VIX_LAUNCH_CHECK();                                                                                                \
-        log_key_kernel<GG><<<grid * 4, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
+        log_key_kernel<GG><<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
             a.codebooks_t, a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, counters.ptr + 4);                           \
         VIX_LAUNCH_CHECK();                                                                                                \
     } while (0)
@@ -1048,7 +1083,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         VIX_LAUNCH_CHECK();
         block_scan_kernel<<<qblk, 256, 0, s>>>(cand_cnt.ptr, (int)nq, bsum.ptr, cand_off.ptr, cand_cur.ptr);
         VIX_LAUNCH_CHECK();
-        key_scatter_kernel<<<grid * 4, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, cand_cur.ptr, cand.ptr);
+        key_scatter_kernel<<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, cand_cur.ptr, cand.ptr);
         VIX_LAUNCH_CHECK();
         select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(nq, cand_off.ptr, cand.ptr, k, flag.ptr, counters.ptr + 4, fb_list.ptr,
                                                               counters.ptr + 2, a.out_dist, a.out_ids);
@@ -1072,6 +1107,19 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         long long tot = 0;
         int mx = 0;
         for (int64_t i = 0; i < nq; ++i) { tot += cc[(size_t)i]; mx = cc[(size_t)i] > mx ? cc[(size_t)i] : mx; }
+#ifdef VIX_TCS_DIAG
+        unsigned long long hd[32];
+        VIX_CUDA(cudaMemcpy(hd, diag.ptr, 256, cudaMemcpyDeviceToHost));
+        const char* names[4][4] = {{"item_full", "a_empty", "-", "-"}, {"item_full", "b_full", "d_full", "-"},
+                                   {"item_full", "b_full", "a_full", "d_empty"}, {"item_empty", "b_empty", "-", "-"}};
+        const char* roles[4] = {"decoder", "filter", "mma", "loader"};
+        const double nw[4] = {12.0 * grid, 1.0 * kEpiWarps * grid, 1.0 * grid, 1.0 * grid};
+        for (int r = 0; r < 4; ++r) {
+            fprintf(stderr, "[vix tc diag] %-8s total %10.0f cycles per warp; waits:", roles[r], (double)hd[16 + r] / nw[r]);
+            for (int i = 0; i < 4; ++i) if (names[r][i][0] != '-') fprintf(stderr, " %s %.0f", names[r][i], (double)hd[r * 4 + i] / nw[r]);
+            fprintf(stderr, "\n");
+        }
+#endif
         fprintf(stderr, "[vix tc scan] nq %lld, handed back %d, candidates %lld (max %d per query; %d per log), error %d\n", (long long)nq,
                 hc[2], tot, mx, log_cap, hc[1]);
     }
