@@ -325,6 +325,8 @@ typedef struct {
     int64_t cycles_prologue, cycles_scan, cycles_tail;
     int64_t cycles_select, cycles_probe_table, cycles_lut;   /* the three concurrent pieces of the prologue */
     int64_t merge_candidates;                                 /* entries handed to the per-query top-k merge */
+    float   ms_scan_kernel;       /* CUDA-event time of the stage's dominant kernel alone (the scan proper)              */
+    int32_t scan_path;            /* IVF-PQ: 0 = query-major look-up-table scan, 1 = list-major tensor-core scan           */
 } vix_search_stats;
 int vix_index_search_ex(vix_index_t* h, const float* queries, int64_t nq, int k, int nprobe,
                         float* out_dist, int64_t* out_ids, int32_t* out_probes /* [nq x nprobe] nullable */,

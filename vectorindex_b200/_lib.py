@@ -73,7 +73,7 @@ class SearchStats(C.Structure):
     _fields_ = [("codes_scanned", C.c_int64), ("code_bytes_scanned", C.c_int64), ("ms_coarse", C.c_float),
                 ("ms_scan", C.c_float), ("ms_total", C.c_float), ("cycles_prologue", C.c_int64), ("cycles_scan", C.c_int64),
                 ("cycles_tail", C.c_int64), ("cycles_select", C.c_int64), ("cycles_probe_table", C.c_int64),
-                ("cycles_lut", C.c_int64), ("merge_candidates", C.c_int64)]
+                ("cycles_lut", C.c_int64), ("merge_candidates", C.c_int64), ("ms_scan_kernel", C.c_float), ("scan_path", C.c_int32)]
 
 
 _LIB = None

@@ -669,9 +669,9 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
     VIX_TRY(di.stage(out_ids, (size_t)nq * k));
 
     cudaEvent_t* ev = h->ev;
-    if (stats && !ev[0]) for (int e = 0; e < 3; ++e) VIX_CUDA(cudaEventCreate(&ev[e]));
+    if (stats && !ev[0]) for (int e = 0; e < 5; ++e) VIX_CUDA(cudaEventCreate(&ev[e]));
     const bool traced = !stats && h->trace_n < h->trace_cap;
-    cudaEvent_t* tev = traced ? &h->trace_ev[3 * (size_t)h->trace_n] : nullptr;
+    cudaEvent_t* tev = traced ? &h->trace_ev[5 * (size_t)h->trace_n] : nullptr;
     if (stats) VIX_CUDA(cudaEventRecord(ev[0], s));
     if (traced) VIX_CUDA(cudaEventRecord(tev[0], s));
 
@@ -693,8 +693,8 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
         // row index -> user id
         gather_ids_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, s>>>(rows.ptr, h->ids.ptr, di.dev, nq * (int64_t)k);
         VIX_LAUNCH_CHECK();
-        if (stats) { VIX_CUDA(cudaEventRecord(ev[1], s)); VIX_CUDA(cudaEventRecord(ev[2], s)); }
-        if (traced) { VIX_CUDA(cudaEventRecord(tev[1], s)); VIX_CUDA(cudaEventRecord(tev[2], s)); }
+        if (stats) for (int e = 1; e < 5; ++e) VIX_CUDA(cudaEventRecord(ev[e], s));
+        if (traced) for (int e = 1; e < 5; ++e) VIX_CUDA(cudaEventRecord(tev[e], s));
     } else {
         if (nprobe <= 0) nprobe = h->p.nprobe;
         VIX_REQUIRE(nprobe > 0, VIX_ERR_INVALID_K, "index_search: nprobe must be > 0");
@@ -715,8 +715,10 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             VIX_TRY(probe_select_fast_device(dq.dev, nq, h->coarse.ptr, h->kc, d, h->p.metric, nprobe,
                                              h->coarse_norms.ptr, pp, nullptr, h->coarse_norm_max.ptr));
         }
-        if (stats) VIX_CUDA(cudaEventRecord(ev[1], s));
-        if (traced) VIX_CUDA(cudaEventRecord(tev[1], s));
+        // ([3], [4]: around the dominant kernel of the scan stage -- the IVF-PQ launchers record them again)
+        if (stats) { VIX_CUDA(cudaEventRecord(ev[1], s)); VIX_CUDA(cudaEventRecord(ev[3], s)); VIX_CUDA(cudaEventRecord(ev[4], s)); }
+        if (traced) { VIX_CUDA(cudaEventRecord(tev[1], s)); VIX_CUDA(cudaEventRecord(tev[3], s)); VIX_CUDA(cudaEventRecord(tev[4], s)); }
+        int scan_path = 0;
         DevBuf<unsigned long long>& scanned = h->scanned;
         if (stats) { VIX_TRY(scanned.resize(16, false)); VIX_CUDA(cudaMemsetAsync(scanned.ptr, 0, 128, s)); }
         if (h->p.kind == VIX_INDEX_IVF_PQ) {
@@ -741,7 +743,11 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
                 VIX_TRY(query_order(pp, nq, nprobe, h->list_len.ptr, h->kc, order));
                 a.order = order.ptr;
             }
+            if (stats) { a.ev_kernel[0] = ev[3]; a.ev_kernel[1] = ev[4]; }
+            if (traced) { a.ev_kernel[0] = tev[3]; a.ev_kernel[1] = tev[4]; }
             VIX_TRY(launch_ivfpq_scan(a));
+            scan_path = a.path;
+            if (traced) h->trace_path[(size_t)h->trace_n] = a.path;
         } else {
             const int P = next_pow2(k + 256);
             const size_t smem = (size_t)P * 8 + (size_t)d * 4;
@@ -769,6 +775,7 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             stats->cycles_prologue = (int64_t)sc4[1]; stats->cycles_scan = (int64_t)sc4[2]; stats->cycles_tail = (int64_t)sc4[3];
             stats->cycles_select = (int64_t)sc4[4]; stats->cycles_probe_table = (int64_t)sc4[5]; stats->cycles_lut = (int64_t)sc4[6];
             stats->merge_candidates = (int64_t)sc4[7];
+            stats->scan_path = scan_path;
             stats->code_bytes_scanned = (int64_t)sc * (h->p.kind == VIX_INDEX_IVF_PQ ? h->code_bytes() : d * 4);
         }
         VIX_TRY(dp.commit());
@@ -782,6 +789,7 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
         cudaEventElapsedTime(&stats->ms_coarse, ev[0], ev[1]);
         cudaEventElapsedTime(&stats->ms_scan, ev[1], ev[2]);
         cudaEventElapsedTime(&stats->ms_total, ev[0], ev[2]);
+        if (h->p.kind != VIX_INDEX_FLAT && h->has_coarse) cudaEventElapsedTime(&stats->ms_scan_kernel, ev[3], ev[4]);
     }
     return rc;
 }
@@ -1415,7 +1423,7 @@ int vix_index_trace(vix_index_t* h, int capacity) {
     VIX_REQUIRE(h, VIX_ERR_NULL_PTR, "vix_index_trace: null handle");
     VIX_REQUIRE(capacity >= 0 && capacity <= 65536, VIX_ERR_INVALID_PARAM, "vix_index_trace: capacity");
     std::lock_guard<std::mutex> lk(h->mu);
-    while ((int)h->trace_ev.size() < 3 * capacity) {
+    while ((int)h->trace_ev.size() < 5 * capacity) {
         cudaEvent_t e = nullptr;
         VIX_CUDA(cudaEventCreate(&e));
         h->trace_ev.push_back(e);
@@ -1424,6 +1432,7 @@ int vix_index_trace(vix_index_t* h, int capacity) {
         VIX_TRY(h->trace_scanned.resize((size_t)capacity, false));
         VIX_CUDA(cudaMemsetAsync(h->trace_scanned.ptr, 0, (size_t)capacity * 8, ctx().stream));
     }
+    h->trace_path.assign((size_t)capacity, 0);
     h->trace_cap = capacity;
     h->trace_n = 0;
     return VIX_OK;
@@ -1434,7 +1443,7 @@ int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out) {
     std::lock_guard<std::mutex> lk(h->mu);
     VIX_REQUIRE(i >= 0 && i < h->trace_n, VIX_ERR_INVALID_PARAM, "vix_index_trace_get: %d of %d traced calls", i, h->trace_n);
     memset(out, 0, sizeof(*out));
-    cudaEvent_t* ev = &h->trace_ev[3 * (size_t)i];
+    cudaEvent_t* ev = &h->trace_ev[5 * (size_t)i];
     VIX_CUDA(cudaEventSynchronize(ev[2]));
     unsigned long long sc = 0;
     VIX_CUDA(cudaMemcpy(&sc, h->trace_scanned.ptr + i, 8, cudaMemcpyDeviceToHost));
@@ -1443,6 +1452,8 @@ int vix_index_trace_get(vix_index_t* h, int i, vix_search_stats* out) {
     cudaEventElapsedTime(&out->ms_coarse, ev[0], ev[1]);
     cudaEventElapsedTime(&out->ms_scan, ev[1], ev[2]);
     cudaEventElapsedTime(&out->ms_total, ev[0], ev[2]);
+    cudaEventElapsedTime(&out->ms_scan_kernel, ev[3], ev[4]);
+    out->scan_path = h->trace_path[(size_t)i];
     return VIX_OK;
 }
 

@@ -113,12 +113,13 @@ struct vix_index {
     DevBuf<float> codebooks_t;          // [ks x m x dsub] code-major copy of the codebooks
     int align = 32;                     // list granularity in slots (ScanLayout::align)
     // search_ex(stats): events and counter are created once per handle
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries + the dominant scan kernel
     DevBuf<unsigned long long> scanned;
     // vix_index_trace(): per-call stage events recorded WITHOUT synchronising (read back afterwards)
-    std::vector<cudaEvent_t> trace_ev;  // 3 per traced call
+    std::vector<cudaEvent_t> trace_ev;  // 5 per traced call
     DevBuf<unsigned long long> trace_scanned;
     int trace_cap = 0, trace_n = 0;
+    std::vector<int> trace_path;        // IVF-PQ scan path of each traced call
 };
 
 

@@ -918,8 +918,10 @@ static int launch_dual(ScanArgs& a, bool& taken) {
         VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int64_t grid = num_sms();
         if (2 * grid > a.nq) grid = (a.nq + 1) / 2;
+        if (a.ev_kernel[0]) VIX_CUDA(cudaEventRecord(a.ev_kernel[0], ctx().stream));
         kern<<<(unsigned)grid, kFastThreads, smem, ctx().stream>>>(a);
         VIX_LAUNCH_CHECK();
+        if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], ctx().stream));
     }
     return VIX_OK;
 }
@@ -953,12 +955,62 @@ static int launch_fast(ScanArgs& a) {
     VIX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = num_sms();
     if (grid > a.nq) grid = a.nq;
+    if (a.ev_kernel[0]) VIX_CUDA(cudaEventRecord(a.ev_kernel[0], ctx().stream));
     kern<<<(unsigned)grid, 32 * nwarps, smem, ctx().stream>>>(a);
     VIX_LAUNCH_CHECK();
+    if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], ctx().stream));
     return VIX_OK;
 }
 
+// the same terms, one warp per QUERY (its row stays in shared memory, four probed lists in flight): the batch-wide form
+// the list-major path uses for every (query, probe) pair.  Lane-strided partial sums and xor tree as above: identical bits.
+__global__ void __launch_bounds__(256)
+probe_bias_rows_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
+                       const int32_t* __restrict__ list_len, int kc, int64_t nq, int nprobe, int d, int order_max,
+                       float* __restrict__ bias) {
+    extern __shared__ float s_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
+    if (q >= nq) return;
+    float* sq = s_rows + (size_t)warp * d;
+    for (int e = lane; e < d; e += 32) sq[e] = __ldg(queries + q * d + e);
+    __syncwarp();
+    for (int p0 = 0; p0 < nprobe; p0 += 4) {
+        float part[4];
+        const float* c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            part[u] = 0.0f;
+            c[u] = nullptr;
+            if (p0 + u < nprobe) {
+                const int l = __ldg(probes + q * nprobe + p0 + u);
+                if ((unsigned)l < (unsigned)kc && __ldg(list_len + l) > 0) c[u] = coarse + (int64_t)l * d;
+            }
+        }
+        if (order_max) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u]) for (int e = lane; e < d; e += 32) part[u] = fmaf(sq[e], __ldg(c[u] + e), part[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u]) for (int e = lane; e < d; e += 32) { const float df = sq[e] - __ldg(c[u] + e); part[u] = fmaf(df, df, part[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            for (int o = 16; o > 0; o >>= 1) part[u] += __shfl_xor_sync(0xFFFFFFFFu, part[u], o);
+        if (lane < 4 && p0 + lane < nprobe)
+            bias[q * nprobe + p0 + lane] = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+    }
+}
+
 int launch_probe_bias(const ScanArgs& a, float* bias) {
+    if ((size_t)a.d * 4 * 8 <= 48 * 1024) {
+        probe_bias_rows_kernel<<<(unsigned)((a.nq + 7) / 8), 256, (size_t)a.d * 4 * 8, ctx().stream>>>(
+            a.queries, a.probes, a.coarse, a.list_len, a.kc, a.nq, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias);
+        VIX_LAUNCH_CHECK();
+        return VIX_OK;
+    }
     const int64_t npairs = a.nq * (int64_t)a.nprobe;
     probe_bias_kernel<<<(unsigned)((npairs * 32 + 255) / 256), 256, 0, ctx().stream>>>(
         a.queries, a.probes, a.coarse, a.list_len, a.kc, npairs, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias);
@@ -971,7 +1023,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a);
 
 int launch_ivfpq_scan(ScanArgs& a) {
     const ScanLayout L = scan_layout(a.m);
-    if (L.fast && tc_scan_supported(a)) return launch_ivfpq_scan_tc(a);      // list-major, tensor cores (vix_ivfpq_tc.cu)
+    a.path = 0;
+    if (L.fast && tc_scan_supported(a)) { a.path = 1; return launch_ivfpq_scan_tc(a); }   // list-major, tensor cores (vix_ivfpq_tc.cu)
     return launch_ivfpq_scan_classic(a);
 }
 
@@ -990,8 +1043,10 @@ int launch_ivfpq_scan_classic(ScanArgs& a) {
         VIX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ivfpq_scan_generic_kernel, kScanThreads, smem));
         int64_t grid = (int64_t)num_sms() * (occ < 1 ? 1 : occ);
         if (grid > a.nq) grid = a.nq;
+        if (a.ev_kernel[0]) VIX_CUDA(cudaEventRecord(a.ev_kernel[0], ctx().stream));
         ivfpq_scan_generic_kernel<<<(unsigned)grid, kScanThreads, smem, ctx().stream>>>(a);
         VIX_LAUNCH_CHECK();
+        if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], ctx().stream));
         return VIX_OK;
     }
     a.Pw = next_pow2(a.k + 64);

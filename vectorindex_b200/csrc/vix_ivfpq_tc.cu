@@ -893,20 +893,49 @@ key_scatter_kernel(const u64* __restrict__ log, const int* __restrict__ log_cnt,
     }
 }
 
-// one warp per query: the k best of its keys by (score, id) -- or the query is handed back
+// one warp per query: the k best of its keys by (score, id) -- or the query is handed back.  Up to 512 keys are selected in
+// registers (select_and_write); longer runs (a few queries have thousands) stream through a warp queue under a threshold.
 __global__ void __launch_bounds__(128)
-select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict__ keys, int k, const int* __restrict__ flag,
+select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict__ keys, int k, int Pw, const int* __restrict__ flag,
               const int* __restrict__ overflow, int32_t* __restrict__ fb_list, int* __restrict__ fb_count,
               float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
     if (q >= nq) return;
     if (flag[q] || *overflow) {
         if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)q;
         return;
     }
     // (the seed's k vectors passed the filter: at least k keys)
-    select_and_write(keys + off[q], off[q + 1] - off[q], k, 0, q, out_dist, out_ids);
+    const u64* src = keys + off[q];
+    const int n = off[q + 1] - off[q];
+    if (n <= 512) { select_and_write(src, n, k, 0, q, out_dist, out_ids); return; }
+    u64* wq = reinterpret_cast<u64*>(qsm) + (size_t)warp * Pw;
+    for (int i = lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+    __syncwarp();
+    int cnt = 0;
+    u64 thr = kEmptyKey;                                       // keys >= thr cannot be among the k best
+    for (int base = 0; base < n; base += 32) {
+        const u64 key = base + lane < n ? src[base + lane] : kEmptyKey;
+        const bool pass = key < thr;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
+        if (!ball) continue;
+        if (cnt + 32 > Pw - k) {
+            for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+            __syncwarp();
+            bitonic_sort_keys<true>(wq, Pw, lane, 32);
+            thr = wq[k - 1];                                   // a key equal to the k-th best is a second copy of it: kept out
+            cnt = 0;                                           // only if k copies are already in, which the sort guarantees
+        }
+        if (pass) wq[k + cnt + __popc(ball & ((1u << lane) - 1u))] = key;
+        cnt += __popc(ball);
+        __syncwarp();
+    }
+    for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
+    __syncwarp();
+    bitonic_sort_keys<true>(wq, Pw, lane, 32);
+    for (int i = lane; i < k; i += 32) write_result(wq[i], 0, (size_t)q * k + i, out_dist, out_ids);
 }
 
 __global__ void smem_base_kernel(uint32_t* out) {
@@ -1063,8 +1092,10 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
 #define VIX_TCS(GG)                                                                                                        \
     do {                                                                                                                   \
         VIX_CUDA(cudaFuncSetAttribute(tc_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
+        if (a.ev_kernel[0]) VIX_CUDA(cudaEventRecord(a.ev_kernel[0], s));                                                  \
         tc_scan_kernel<GG><<<grid, kThreads, smem, s>>>(t);                                                                \
         VIX_LAUNCH_CHECK();                                                                                                \
+        if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], s));                                                  \
         log_key_kernel<GG><<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
             a.codebooks_t, a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, counters.ptr + 4);                           \
         VIX_LAUNCH_CHECK();                                                                                                \
@@ -1085,7 +1116,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         VIX_LAUNCH_CHECK();
         key_scatter_kernel<<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, cand_cur.ptr, cand.ptr);
         VIX_LAUNCH_CHECK();
-        select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(nq, cand_off.ptr, cand.ptr, k, flag.ptr, counters.ptr + 4, fb_list.ptr,
+        const int Pw = next_pow2(k + 64);
+        select_kernel<<<(unsigned)((nq + 3) / 4), 128, (size_t)4 * Pw * 8, s>>>(nq, cand_off.ptr, cand.ptr, k, Pw, flag.ptr, counters.ptr + 4, fb_list.ptr,
                                                               counters.ptr + 2, a.out_dist, a.out_ids);
         VIX_LAUNCH_CHECK();
     }
@@ -1093,6 +1125,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         ScanArgs fb = a;
         fb.order = fb_list.ptr; fb.nq_dev = counters.ptr + 2;
         fb.scanned = nullptr; fb.bias = bias.ptr; fb.lut_image = nullptr;
+        fb.ev_kernel[0] = fb.ev_kernel[1] = nullptr;
         fb.work_counter = wc_fb.ptr;
         VIX_TRY(launch_ivfpq_scan_classic(fb));
     }

@@ -30,6 +30,8 @@ struct ScanArgs {
     int metric, k, Pw, P2;
     float* out_dist; int64_t* out_ids;            // [nq x k]
     unsigned long long* scanned;                  // optional: total list entries visited
+    cudaEvent_t ev_kernel[2];                     // optional: recorded around the dominant kernel of the launch
+    int path;                                     // set by launch_ivfpq_scan: 0 query-major, 1 list-major (tensor cores)
     unsigned long long* phase_cycles;             // optional [3]: SM cycles in prologue / scan / tail wait, summed over CTAs
 };
 
