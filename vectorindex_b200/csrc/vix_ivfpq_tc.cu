@@ -49,6 +49,9 @@ namespace vix {
 
 int launch_ivfpq_scan_classic(ScanArgs& a);
 static std::atomic<long long> g_tc_launches{0};
+static thread_local scan_thr_hook_t tls_thr_hook = nullptr;
+static thread_local void* tls_thr_ctx = nullptr;
+void set_scan_thr_hook(scan_thr_hook_t fn, void* ctx) { tls_thr_hook = fn; tls_thr_ctx = ctx; }
 
 namespace tcs {
 
@@ -724,11 +727,20 @@ seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
     for (int i = lane; i < k; i += 32) write_result(wq[i], 0, (size_t)q * k + i, out_dist, out_ids);
 }
 
+// the seed's k-th distance of every query (+inf when the sample holds fewer than k vectors): the filter's bound
+__global__ void __launch_bounds__(256)
+seed_bound_kernel(const float* __restrict__ seed_dist, int64_t nq, int k, float* __restrict__ thr) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float t = seed_dist[q * k + (k - 1)];
+    thr[q] = t == t ? t : __int_as_float(0x7f800000);
+}
+
 // per query (one warp), after the seed scan: the fp16 row, u_q = -thr / 2 - eps_q, and whether the query can take this path
 // (a finite k-th seed distance and a finite error bound)
 __global__ void __launch_bounds__(256)
 query_prep_kernel(const float* __restrict__ queries, int64_t nq, int d, const float* __restrict__ qnorm,
-                  const unsigned int* __restrict__ maxabs, float* __restrict__ meta, const float* __restrict__ seed_dist, int k,
+                  const unsigned int* __restrict__ maxabs, float* __restrict__ meta, const float* __restrict__ thr_in,
                   __half* __restrict__ qh, float* __restrict__ uq, int* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -741,7 +753,7 @@ query_prep_kernel(const float* __restrict__ queries, int64_t nq, int d, const fl
     for (int e = lane; e < d; e += 32) qh[q * d + e] = __float2half_rn(__ldg(queries + q * d + e) * sq);
     if (lane == 0) {
         const float qn = qnorm[q];
-        const float thr = seed_dist[q * k + (k - 1)];
+        const float thr = thr_in[q];
         // |fp16 tensor-core <q, r^> - exact| <= eta ||q|| ||r^|| + the subnormal floor of the two conversions, and the
         // look-up-table scan's own fp32 sum is within 2e-6 of (|bias| + |t_x| + 2 ||q|| ||r^||) of the exact value
         // (the |bias| and |t_x| shares ride in tau and h_v)
@@ -907,7 +919,7 @@ select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict
         if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)q;
         return;
     }
-    // (the seed's k vectors passed the filter: at least k keys)
+    // (one GPU: the seed's k vectors passed the filter, so there are at least k keys; a shard may hold fewer)
     const u64* src = keys + off[q];
     const int n = off[q + 1] - off[q];
     if (n <= 512) { select_and_write(src, n, k, 0, q, out_dist, out_ids); return; }
@@ -1047,7 +1059,12 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         }
 #undef VIX_SEED
     }
-    query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, seed_dist.ptr, k, qh.ptr, uq.ptr,
+    Scratch<float> thr;
+    VIX_TRY(thr.alloc((size_t)nq));
+    seed_bound_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(seed_dist.ptr, nq, k, thr.ptr);
+    VIX_LAUNCH_CHECK();
+    if (tls_thr_hook) VIX_TRY(tls_thr_hook(tls_thr_ctx, thr.ptr, nq));         // sharded: the minimum over the ranks
+    query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, thr.ptr, qh.ptr, uq.ptr,
                                             flag.ptr);
     VIX_LAUNCH_CHECK();
     const unsigned pblocks = (unsigned)((npairs + 255) / 256);

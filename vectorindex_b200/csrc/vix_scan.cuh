@@ -46,6 +46,13 @@ struct ScanLayout {
 };
 ScanLayout scan_layout(int m);
 
+// Sharded search (vix_sharded.cu): the list-major path filters against an upper bound of every query's k-th best distance;
+// on a shard the bound of a query whose near lists live on OTHER ranks is loose unless the ranks share their bounds.  The
+// hook (thread-local, set around the call) is handed the per-query bounds [nq] on the stream and replaces them by the
+// minimum over the ranks.  Every rank takes the same path (same shapes, same device), so the collective is matched.
+typedef int (*scan_thr_hook_t)(void* ctx, float* thr_dev, int64_t nq);
+void set_scan_thr_hook(scan_thr_hook_t fn, void* ctx);
+
 int launch_ivfpq_scan(ScanArgs& a);            // picks the path
 bool tc_scan_supported(const ScanArgs& a);     // would launch_ivfpq_scan take the list-major tensor-core path (vix_ivfpq_tc.cu)?
 int launch_ivfpq_scan_classic(ScanArgs& a);    // query-major look-up-table scan (vix_ivfpq_scan.cu)

@@ -17,6 +17,7 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the copy torch already loaded),
 // so the library itself has no link-time dependency on it and single-GPU hosts never touch it.
 #include "vix_index.cuh"
+#include "vix_scan.cuh"
 #include "vix_topk.cuh"
 
 #include <cub/cub.cuh>
@@ -365,6 +366,17 @@ int vix_sharded_query_block(int64_t nq, int rank, int world, int64_t* first, int
     return VIX_OK;
 }
 
+// the list-major scan's per-query bounds -> their minimum over the ranks (vix_scan.cuh: scan_thr_hook_t)
+static int thr_min_over_ranks(void* ctx, float* thr_dev, int64_t nq) {
+    vix_comm* c = static_cast<vix_comm*>(ctx);
+    VIX_NCCL(g_nccl.AllReduce(thr_dev, thr_dev, (size_t)nq, ncclFloat, ncclMin, c->comm, vix::ctx().stream));
+    return VIX_OK;
+}
+struct ThrHookScope {
+    ThrHookScope(vix_comm* c) { set_scan_thr_hook(thr_min_over_ranks, c); }
+    ~ThrHookScope() { set_scan_thr_hook(nullptr, nullptr); }
+};
+
 int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int64_t nq, int k, int nprobe, float* out_dist,
                        int64_t* out_ids) {
     VIX_TRY(ensure_device());
@@ -383,6 +395,7 @@ int vix_sharded_search(vix_index_t* h, vix_comm_t* c, const float* queries, int6
     cudaStream_t s = ctx().stream;
     if (h->dirty) VIX_TRY(build_lists(h));
     VIX_TRY(ensure_region(c, nq, d, nprobe, k));
+    ThrHookScope thr_scope(c);                                        // (cleared again on every way out)
     const bool host_q = !is_device_ptr(queries);
     const int64_t per = block_rows(nq, world);
     const int64_t lo = nq < (int64_t)rank * per ? nq : (int64_t)rank * per;
