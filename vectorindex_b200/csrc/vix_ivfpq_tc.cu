@@ -55,24 +55,30 @@ void set_scan_thr_hook(scan_thr_hook_t fn, void* ctx) { tls_thr_hook = fn; tls_t
 
 namespace tcs {
 
-constexpr int kNQ = 64;                                  // query columns per item
-constexpr int kStagesA = 3;                              // = decoder groups
+constexpr int kNQ = 64;                                  // query columns per item (a list probed by more queries is visited again)
+constexpr int kDecGroups = 3;                            // decoder groups of four warps: group g decodes the tiles u % 3 == g
+constexpr int kStagesA = 4;                              // operand stages in TMEM: tile u lives in stage u % 4 (whichever group decodes it)
 constexpr int kItemRing = 4;
 constexpr int kDBufs = 4;                                // accumulator buffers in TMEM (kDBufs x kNQ columns)
+constexpr int kDStride = kNQ;
 constexpr int kEpiSets = 2;                              // filter warp sets: set e takes the units u % kEpiSets == e
 constexpr int kEpiWarps = 4 * kEpiSets;
-constexpr int kDecWarps = 4 * kStagesA, kEpiWarp0 = kDecWarps, kMmaWarp = kEpiWarp0 + kEpiWarps, kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = 32 * (kLoadWarp + 1);           // 704
+constexpr int kMmaWarps = 2;                             // MMA issuers: issuer e takes the tiles u % kMmaWarps == e (one lane issues a
+                                                         // tcgen05.mma every ~65 clocks, a commit every ~64: at N <= 64 that, not the tensor
+                                                         // pipe, paces a tile)
+constexpr int kDecWarps = 4 * kDecGroups, kEpiWarp0 = kDecWarps, kMmaWarp = kEpiWarp0 + kEpiWarps, kLoadWarp = kMmaWarp + kMmaWarps;
+constexpr int kThreads = 32 * (kLoadWarp + 1);           // 736
 static_assert(kEpiWarp0 % 4 == 0 && kDBufs % kEpiSets == 0, "a filter warp reads the TMEM lane quarter warp % 4");
 constexpr uint32_t kTabAbs = 4096;                       // ABSOLUTE shared addresses: the table's travels in the LDS immediate
-constexpr uint32_t kABase = kTabAbs + 65536;
-constexpr uint32_t kAAtom = 128 * 128;                   // one K-atom (64 halves) of 128 rows
-constexpr uint32_t kAStage = 2 * kAAtom;                 // d <= 128
-constexpr uint32_t kBBase = kABase + kStagesA * kAStage;
+constexpr uint32_t kTabBytes = 2 * 65536;                // two sub-tables (groups 0-1, groups 2-3), each [256 codes][64 slots]
+constexpr uint32_t kBBase = kTabAbs + kTabBytes;
 constexpr uint32_t kBAtom = kNQ * 128;
 constexpr uint32_t kBBuf = 2 * kBAtom;
 constexpr uint32_t kEndAbs = kBBase + 2 * kBBuf;
-constexpr int kTmemCols = kDBufs * kNQ;                  // 256
+constexpr int kACol0 = kDBufs * kDStride;                 // TMEM: accumulators in columns [0, 256), operand stages behind them
+constexpr int kAStageCols = 64;                          // one operand stage: 128 rows x up to 64 columns (= sub-quantisers, fp16 pairs)
+constexpr int kTmemCols = 512;
+static_assert(kACol0 + kStagesA * kAStageCols <= kTmemCols, "TMEM columns");
 constexpr int kSeedChunks = 8;                           // the seed looks at the first 256 vectors of a query's first list
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);   // A, B fp16 (format 0), D fp32, K-major both
 
@@ -87,6 +93,7 @@ struct Small {                                           // the bookkeeping in f
     float tau[2][kNQ];
     uint32_t pair[2][kNQ];
     uint32_t tmem_slot;
+    uint32_t mma_seq;                                    // tiles whose operands an MMA issuer has claimed, in tile order
 };
 
 struct Args {
@@ -97,7 +104,7 @@ struct Args {
     const float* bias;             // [nq x nprobe]
     const __half* qh;              // [nq x d] scaled fp16 queries
     const float* uq;               // [nq]  -thr / 2 - eps
-    const uint32_t* table;         // [256][64] half2: the codebooks, scaled (slot = sub-quantiser; odd G: last group twice)
+    const uint32_t* table;         // [2][256][64] half2: the codebooks, scaled (table_kernel)
     const float* scales;           // [0] s_q, [1] s_c
     int nprobe, d, m;
     int* list_counter;
@@ -126,6 +133,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// the same with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` have passed, instead
+// of coming back at once and spinning (23 warps share four schedulers; a spinning warp takes issue slots from the decoders)
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 #ifdef VIX_TCS_DIAG
 #define VIX_DG(i) dg[i]
 #else
@@ -137,15 +155,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
     struct Acc { unsigned long long& w; long long t; __device__ ~Acc() { w += (unsigned long long)(clock64() - t); } } acc{waited, w0};
 #endif
     if (mbar_try_wait(bar, parity)) return true;
+    // try_wait suspends the thread in hardware until the phase completes or a time limit passes, so the loop is not a busy
+    // spin; the clock and the (global) error flag are looked at only every 64th return -- a global load per iteration would
+    // add its ~600 clocks to EVERY hand-over of the pipeline
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(error) != 0) {
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait_sleep(bar, parity, 4000u)) return true;
+        if ((spins & 63u) == 0 && (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(error) != 0)) {
             atomicExch(error, 1);
             if (error_host) { *reinterpret_cast<volatile int*>(error_host) = 1; __threadfence_system(); }
             return false;
         }
     }
-    return true;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
@@ -163,6 +184,15 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in TMEM (rows = lanes, 32-bit columns of two halves), B from shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -195,38 +225,43 @@ __device__ __forceinline__ uint32_t lds_tab(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
     return v;
 }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
 }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// lane (= slot of a 32-slot chunk) -> row of the warp's 32-row block of the operand tile, chosen so that the 32 stores of a
-// warp (rows x rotated sub-quantisers under the 128B swizzle) hit 32 different banks at every step
-__device__ __forceinline__ uint32_t row_of_lane(uint32_t l) {
-    const uint32_t l0 = l & 1u, l1 = (l >> 1) & 1u, l2 = (l >> 2) & 1u, l3 = (l >> 3) & 1u, l4 = (l >> 4) & 1u;
-    return 8u * (2u * l3 + l1) + 4u * l2 + 2u * l0 + (l2 ^ l4);
-}
-__device__ __forceinline__ uint32_t lane_of_row(uint32_t r) {
-    const uint32_t b0 = r & 1u, b1 = (r >> 1) & 1u, b2 = (r >> 2) & 1u, b3 = (r >> 3) & 1u, b4 = (r >> 4) & 1u;
-    return b1 | (b3 << 1) | (b2 << 2) | (b4 << 3) | ((b0 ^ b2) << 4);
-}
-
-// one group of 16 sub-quantisers of one vector: 16 look-ups, 16 stores.  KIND 0 / 1: the even / odd step of a pair of groups
-// (the half-warps take the two groups in opposite order, so their look-ups use different banks); KIND 2: the last group of
-// an odd G (the second half-warp reads the group's replica).
+// one group of 16 sub-quantisers of one vector (= one lane = one TMEM lane): 16 look-ups in the ROTATED order of the stored
+// codes (byte b holds sub-quantiser b ^ rot, rot = slot & 15: the 16 lanes of a half-warp ask for 16 different table slots,
+// the two half-warps read two replicas -- no bank conflicts), then the values are put back into sub-quantiser order with a
+// four-stage exchange network (register i <-> i ^ 2^s where bit s of rot is set) and leave as 16 TMEM columns.
 template <int IMM>
-__device__ __forceinline__ void decode16(const uint4& w, const uint32_t (&pre)[8], uint32_t sbase) {
+__device__ __forceinline__ void decode16(const uint4& w, const uint32_t (&pre)[8], uint32_t taddr, bool b0, bool b1, bool b2, bool b3) {
     const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+    uint32_t r[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint32_t v0 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604));
-        const uint32_t v1 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7615));
-        const uint32_t v2 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624));
-        const uint32_t v3 = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7635));
-        sts32(sbase ^ (uint32_t)((4 * i + 0) << 2), v0);
-        sts32(sbase ^ (uint32_t)((4 * i + 1) << 2), v1);
-        sts32(sbase ^ (uint32_t)((4 * i + 2) << 2), v2);
-        sts32(sbase ^ (uint32_t)((4 * i + 3) << 2), v3);
+        r[4 * i + 0] = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7604));
+        r[4 * i + 1] = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 0], 0x7615));
+        r[4 * i + 2] = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7624));
+        r[4 * i + 3] = lds_tab<IMM>(__byte_perm(x[i], pre[2 * i + 1], 0x7635));
     }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const bool bit = s == 0 ? b0 : s == 1 ? b1 : s == 2 ? b2 : b3;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((i >> s) & 1) continue;
+            const uint32_t lo = r[i], hi = r[i | (1 << s)];
+            r[i] = bit ? hi : lo;
+            r[i | (1 << s)] = bit ? lo : hi;
+        }
+    }
+    tmem_st16(taddr, r);
 }
 
 template <int G>
@@ -246,17 +281,18 @@ tc_scan_kernel(Args a) {
     const long long dg_t0 = clock64();
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kItemRing; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kDecWarps + kEpiWarps + 1); }
+        for (int i = 0; i < kItemRing; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kDecWarps + kEpiWarps + kMmaWarps); }
         for (int i = 0; i < kStagesA; ++i) { mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S.b_full[i], 32); mbar_init(&S.b_empty[i], kEpiWarps); }
         for (int i = 0; i < kDBufs; ++i) { mbar_init(&S.d_full[i], 1); mbar_init(&S.d_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) tmem_alloc(&S.tmem_slot, kTmemCols);
-    {   // the decode table: 64 KB, once per CTA
+    if (threadIdx.x == 32) S.mma_seq = 0;
+    {   // the decode table: 2 x 64 KB, once per CTA
         const uint4* src = reinterpret_cast<const uint4*>(a.table);
         uint4* dst = reinterpret_cast<uint4*>(abs0 + kTabAbs);
-        for (int i = threadIdx.x; i < 4096; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < (int)(kTabBytes / 16); i += kThreads) dst[i] = __ldg(src + i);
     }
     fence_before_sync();
     __syncthreads();
@@ -270,18 +306,17 @@ tc_scan_kernel(Args a) {
         // ------------------------------------------------------------------------------------------ decoders
         const int grp = warp >> 2, wi = warp & 3;
         const uint32_t h = (uint32_t)lane >> 4;
-        const uint32_t row = 32u * wi + row_of_lane((uint32_t)lane), r7 = row & 7u;
-        const uint32_t rowoff = (row >> 3) * 1024u + r7 * 128u;
-        const uint32_t lo0 = ((((4u * h) ^ r7 ^ (((uint32_t)lane >> 2) & 3u)) & 7u) << 4) | (((uint32_t)lane & 3u) << 2);
-        const uint32_t stage_base = kABase + (uint32_t)grp * kAStage + rowoff;
-        uint32_t pre0[8], pre1[8];
+        // this warp's rows of the operand stage: TMEM lanes [32 wi, 32 wi + 32) (the lanes a warp may touch: warp % 4 == wi),
+        // lane = slot of the chunk; columns kACol0 + 64 stage + sub-quantiser
+        const uint32_t a_taddr0 = tmem_base + ((32u * (uint32_t)wi) << 16) + (uint32_t)kACol0;
+        const bool rb0 = lane & 1, rb1 = lane & 2, rb2 = lane & 4, rb3 = lane & 8;       // bits of rot = slot & 15
+        uint32_t pre0[8];
 #pragma unroll
         for (int b = 0; b < 16; b += 2) {
             const uint32_t c0 = 64u * h + 4u * ((uint32_t)(b ^ lane) & 15u);
             const uint32_t c1 = 64u * h + 4u * ((uint32_t)((b + 1) ^ lane) & 15u);
             pre0[b >> 1] = c0 | (c1 << 8);
-            pre1[b >> 1] = pre0[b >> 1] ^ 0x4040u;
-            asm volatile("" : "+r"(pre0[b >> 1]), "+r"(pre1[b >> 1]));
+            asm volatile("" : "+r"(pre0[b >> 1]));
         }
         // The warp walks its units (tile t of item it with (units before the item + t) % 3 == grp) with the NEXT unit's codes
         // already in flight while it decodes the current one (two register buffers, loop unrolled by two).  Moving on may
@@ -309,7 +344,7 @@ tc_scan_kernel(Args a) {
                 fc = S.items[slot].first_chunk; nch = S.items[slot].nchunks;
                 if (nch < 0) return 0;
                 nt = (nch + 3) >> 2;
-                t = (int)(((long long)grp - u0 % kStagesA + kStagesA) % kStagesA);
+                t = (int)(((long long)grp - u0 % kDecGroups + kDecGroups) % kDecGroups);
                 opened = true;
             }
         };
@@ -317,37 +352,24 @@ tc_scan_kernel(Args a) {
             if (ch < nch) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.slot_codes + (size_t)(fc + ch) * (512u * G)) + lane;
 #pragma unroll
-                for (int s = 0; s < G; ++s) {
-                    const int pi = s >> 1;
-                    const bool last_odd = (G & 1) && s == G - 1;
-                    const int piece = last_odd ? G - 1 : 2 * pi + ((s & 1) ? 1 - (int)h : (int)h);
-                    w[s] = __ldg(src + 32 * piece);
-                }
+                for (int s = 0; s < G; ++s) w[s] = __ldg(src + 32 * s);
             }
         };
-        auto process = [&](const uint4 (&w)[G], bool live, long long use) -> bool {
-            if (use > 0 && !mbar_wait(&S.a_empty[grp], (uint32_t)(use - 1) & 1u, a.error, a.error_host, VIX_DG(1))) return false;
+        auto process = [&](const uint4 (&w)[G], bool live, long long unit) -> bool {
+            const int st = (int)(unit % kStagesA);
+            const long long use = unit / kStagesA;
+            const uint32_t a_taddr = a_taddr0 + (uint32_t)(st * kAStageCols);
+            if (use > 0 && !mbar_wait(&S.a_empty[st], (uint32_t)(use - 1) & 1u, a.error, a.error_host, VIX_DG(1))) return false;
             if (live) {
-#pragma unroll
-                for (int s = 0; s < G; ++s) {
-                    const int pi = s >> 1;
-                    const bool last_odd = (G & 1) && s == G - 1;
-                    const uint32_t sb = stage_base + (uint32_t)pi * kAAtom;
-                    // (the immediates are compile-time: the loop is fully unrolled over s)
-                    if (last_odd) {
-                        if (s == 0) decode16<(int)kTabAbs + 64 * 0>(w[s], pre0, sb + (lo0 ^ (h << 6)));
-                        if (s == 2) decode16<(int)kTabAbs + 64 * 2>(w[s], pre0, sb + (lo0 ^ (h << 6)));
-                    } else if ((s & 1) == 0) {
-                        if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre0, sb + lo0);
-                        if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre0, sb + lo0);
-                    } else {
-                        if (pi == 0) decode16<(int)kTabAbs + 0>(w[s], pre1, sb + (lo0 ^ 0x40u));
-                        if (pi == 1) decode16<(int)kTabAbs + 128>(w[s], pre1, sb + (lo0 ^ 0x40u));
-                    }
-                }
+                // group g: sub-table g / 2, slots 32 (g % 2) + 16 h + ..: the immediates are compile-time
+                decode16<(int)kTabAbs>(w[0], pre0, a_taddr, rb0, rb1, rb2, rb3);
+                if (G > 1) decode16<(int)kTabAbs + 128>(w[G > 1 ? 1 : 0], pre0, a_taddr + 16, rb0, rb1, rb2, rb3);
+                if (G > 2) decode16<(int)kTabAbs + 65536>(w[G > 2 ? 2 : 0], pre0, a_taddr + 32, rb0, rb1, rb2, rb3);
+                if (G > 3) decode16<(int)kTabAbs + 65536 + 128>(w[G > 3 ? 3 : 0], pre0, a_taddr + 48, rb0, rb1, rb2, rb3);
+                tmem_wait_st();
             }
-            fence_async_proxy();
-            mbar_arrive(&S.a_full[grp]);
+            fence_before_sync();
+            mbar_arrive(&S.a_full[st]);
             return true;
         };
         uint4 wA[G], wB[G];
@@ -355,24 +377,31 @@ tc_scan_kernel(Args a) {
             load(wA, 4 * t + wi);
             for (;;) {
                 bool live = 4 * t + wi < nch;
-                long long use = (u0 + t) / kStagesA;
-                t += kStagesA;
+                long long use = u0 + t;
+                t += kDecGroups;
                 int r = seek(false);
                 if (r == 1) load(wB, 4 * t + wi);
                 if (!process(wA, live, use) || r == 0) break;
                 if (r == 2) { if (seek(true) != 1) break; load(wB, 4 * t + wi); }
                 live = 4 * t + wi < nch;
-                use = (u0 + t) / kStagesA;
-                t += kStagesA;
+                use = u0 + t;
+                t += kDecGroups;
                 r = seek(false);
                 if (r == 1) load(wA, 4 * t + wi);
                 if (!process(wB, live, use) || r == 0) break;
                 if (r == 2) { if (seek(true) != 1) break; load(wA, 4 * t + wi); }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ------------------------------------------------------------------------------------------ MMA issuer
+    } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
+        // ------------------------------------------------------------------------------------------ MMA issuers
+        // Both issuers walk every item; issuer e issues the tiles u % kMmaWarps == e.  The waits on the operand stages are taken
+        // in tile order (S.mma_seq): two threads waiting on DIFFERENT phases of one mbarrier would let the later one through
+        // on the earlier phase's parity.
+        const int me = warp - kMmaWarp;
         if (lane == 0) {
+#ifdef VIX_TCS_DIAG
+            unsigned long long mma_issue = 0, mma_commit_c = 0, mma_units = 0;
+#endif
             int it = 0;
             long long u = 0;
             for (;;) {
@@ -386,30 +415,54 @@ tc_scan_kernel(Args a) {
                 if (!mbar_wait(&S.b_full[buf], (uint32_t)(it >> 1) & 1u, a.error, a.error_host, VIX_DG(1))) break;
                 bool ok = true;
                 for (int t = 0; t < nt; ++t, ++u) {
+                    if ((int)(u % kMmaWarps) != me) continue;
                     const int st = (int)(u % kStagesA), db = (int)(u % kDBufs);
+                    {   // my turn: every earlier tile's issuer holds its operands
+                        volatile uint32_t* seq = &S.mma_seq;
+                        const long long t0 = clock64();
+                        for (uint32_t spins = 1; *seq != (uint32_t)u; ++spins) {
+                            __nanosleep(40);
+                            if ((spins & 1023u) == 0 && (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(a.error) != 0)) { ok = false; break; }
+                        }
+                        if (!ok) { atomicExch(a.error, 1); break; }
+                    }
                     if (!mbar_wait(&S.a_full[st], (uint32_t)(u / kStagesA) & 1u, a.error, a.error_host, VIX_DG(2))) { ok = false; break; }
                     if (u >= kDBufs && !mbar_wait(&S.d_empty[db], (uint32_t)(u / kDBufs - 1) & 1u, a.error, a.error_host, VIX_DG(3))) { ok = false; break; }
+                    *reinterpret_cast<volatile uint32_t*>(&S.mma_seq) = (uint32_t)(u + 1);
                     fence_after_sync();
-                    const uint32_t dcol = tmem_base + (uint32_t)(db * kNQ);
+#ifdef VIX_TCS_DIAG
+                    const long long m0 = clock64();
+#endif
+                    const uint32_t dcol = tmem_base + (uint32_t)(db * kDStride);
 #pragma unroll
                     for (int ks = 0; ks < kKSteps; ++ks) {
-                        const uint64_t ad = make_desc(kABase + (uint32_t)st * kAStage + (uint32_t)(ks >> 2) * kAAtom) + (uint64_t)(2 * (ks & 3));
                         const uint64_t bd = make_desc(kBBase + (uint32_t)buf * kBBuf + (uint32_t)(ks >> 2) * kBAtom) + (uint64_t)(2 * (ks & 3));
-                        mma_f16(dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                        // A from TMEM: 8 columns (16 halves) of the stage per K-step
+                        mma_f16_ts(dcol, tmem_base + (uint32_t)(kACol0 + st * kAStageCols + 8 * ks), bd, idesc, ks > 0 ? 1u : 0u);
                     }
+#ifdef VIX_TCS_DIAG
+                    const long long m1 = clock64();
+#endif
                     mma_commit(&S.a_empty[st]);
                     mma_commit(&S.d_full[db]);
+#ifdef VIX_TCS_DIAG
+                    const long long m2 = clock64();
+                    mma_issue += (unsigned long long)(m1 - m0); mma_commit_c += (unsigned long long)(m2 - m1); mma_units += 1;
+#endif
                 }
                 if (!ok) break;
                 mbar_arrive(&S.item_empty[slot]);
                 ++it;
             }
+#ifdef VIX_TCS_DIAG
+            if (a.diag) { atomicAdd(a.diag + 20, mma_issue); atomicAdd(a.diag + 21, mma_commit_c); atomicAdd(a.diag + 22, mma_units); }
+#endif
         }
     } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
         // ------------------------------------------------------------------------------------------ filter
         const int wq = (warp - kEpiWarp0) & 3;               // = warp % 4: the TMEM lane quarter this warp may read
         const int eset = (warp - kEpiWarp0) >> 2;            // this warp's set filters the units u % kEpiSets == eset
-        const uint32_t sl = lane_of_row((uint32_t)lane);     // TMEM lane = tile row -> slot of the chunk
+        const uint32_t sl = (uint32_t)lane;                  // TMEM lane = tile row = slot of the chunk
         u64* const mylog = a.log + (size_t)(blockIdx.x * kEpiWarps + (warp - kEpiWarp0)) * (size_t)a.log_cap;
         int nlog = 0;
         int it = 0;
@@ -446,7 +499,7 @@ tc_scan_kernel(Args a) {
                 const float hv = sc * (0.5f * tx - 1.5e-6f * fabsf(tx));
                 for (int cb = 0; cb < n; cb += 16) {
                     float dv[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(db * kNQ + cb), dv);
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(db * kDStride + cb), dv);
                     bool any = false;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) any |= dv[c] >= tau[cb + c] + hv;       // tau = NaN behind the last query
@@ -538,7 +591,7 @@ tc_scan_kernel(Args a) {
 #ifdef VIX_TCS_DIAG
     if (a.diag && lane == 0) {
         // roles: 0 decoders (12 warps), 1 filter (4 warps), 2 MMA, 3 loader; [role][4 waits] + [role] total cycles at 16 + role
-        const int role = warp < kDecWarps ? 0 : warp < kMmaWarp ? 1 : warp == kMmaWarp ? 2 : 3;
+        const int role = warp < kDecWarps ? 0 : warp < kMmaWarp ? 1 : warp < kLoadWarp ? 2 : 3;
         for (int i = 0; i < 4; ++i) atomicAdd(a.diag + role * 4 + i, dg[i]);
         atomicAdd(a.diag + 16 + role, (unsigned long long)(clock64() - dg_t0));
     }
@@ -586,11 +639,10 @@ table_kernel(const float* __restrict__ codebooks, int m, uint32_t* __restrict__ 
     }
     __syncthreads();
     const float s = s_scale;
-    const int G = m / 16;
-    for (int i = tid; i < 256 * 64; i += 1024) {
-        const int c = i >> 6, slot = i & 63;
-        int j = slot;
-        if ((G & 1) && slot >= m && slot < m + 16) j = slot - 16;          // replica of the last group
+    // [sub-table t = group / 2][code][slot = 32 (group % 2) + 16 replica + sub-quantiser % 16]: both replicas hold the same entry
+    for (int i = tid; i < 2 * 256 * 64; i += 1024) {
+        const int t = i >> 14, c = (i >> 6) & 255, slot = i & 63;
+        const int j = 16 * (2 * t + (slot >> 5)) + (slot & 15);
         uint32_t v = 0;
         if (j < m) {
             const float2 f = *reinterpret_cast<const float2*>(codebooks + ((size_t)j * 256 + c) * 2);
@@ -619,7 +671,7 @@ query_norm_kernel(const float* __restrict__ queries, int64_t nq, int d, float* _
 // first probe position whose list holds vectors here: the seed of the query (one warp per query)
 __global__ void __launch_bounds__(256)
 seed_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, const int32_t* __restrict__ list_len, int kc,
-                  int32_t* __restrict__ seed_list, int32_t* __restrict__ seed_pos) {
+                  int only_first, int32_t* __restrict__ seed_list, int32_t* __restrict__ seed_pos) {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq) return;
@@ -631,6 +683,9 @@ seed_probe_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, co
         const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
         if (ball) { const int src = __ffs(ball) - 1; l0 = __shfl_sync(0xFFFFFFFFu, l, src); p0 = base + src; break; }
     }
+    // a shard: only the rank that owns the query's FIRST probed list seeds it (the bounds are reduced over the ranks; a seed
+    // from a farther list would be looser than the owner's and cost the same)
+    if (only_first && p0 != 0) { l0 = -1; p0 = -1; }
     if (lane == 0) { seed_list[i] = l0; seed_pos[i] = p0; }
 }
 
@@ -1004,7 +1059,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     Scratch<uint32_t> log_q;
     Scratch<__half> qh;
     Scratch<u64> cand;
-    VIX_TRY(table.alloc(256 * 64));
+    VIX_TRY(table.alloc(2 * 256 * 64));
     VIX_TRY(meta.alloc(4));
     VIX_TRY(qnorm.alloc((size_t)nq));
     VIX_TRY(uq.alloc((size_t)nq));
@@ -1038,7 +1093,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     const unsigned qwarps = (unsigned)((nq * 32 + 255) / 256);
     query_norm_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr);
     VIX_LAUNCH_CHECK();
-    seed_probe_kernel<<<qwarps, 256, 0, s>>>(a.probes, nq, a.nprobe, a.list_len, a.kc, seed_list.ptr, seed_pos.ptr);
+    seed_probe_kernel<<<qwarps, 256, 0, s>>>(a.probes, nq, a.nprobe, a.list_len, a.kc, tls_thr_hook != nullptr, seed_list.ptr,
+                                            seed_pos.ptr);
     VIX_LAUNCH_CHECK();
     {   // seed: the first probed list that holds vectors here, one warp per query
         const int Pw = next_pow2(k + 64);
@@ -1163,12 +1219,16 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         const char* names[4][4] = {{"item_full", "a_empty", "-", "-"}, {"item_full", "b_full", "d_full", "-"},
                                    {"item_full", "b_full", "a_full", "d_empty"}, {"item_empty", "b_empty", "-", "-"}};
         const char* roles[4] = {"decoder", "filter", "mma", "loader"};
-        const double nw[4] = {12.0 * grid, 1.0 * kEpiWarps * grid, 1.0 * grid, 1.0 * grid};
+        const double nw[4] = {12.0 * grid, 1.0 * kEpiWarps * grid, 1.0 * kMmaWarps * grid, 1.0 * grid};
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "[vix tc diag] %-8s total %10.0f cycles per warp; waits:", roles[r], (double)hd[16 + r] / nw[r]);
             for (int i = 0; i < 4; ++i) if (names[r][i][0] != '-') fprintf(stderr, " %s %.0f", names[r][i], (double)hd[r * 4 + i] / nw[r]);
             fprintf(stderr, "\n");
         }
+#endif
+#ifdef VIX_TCS_DIAG
+        fprintf(stderr, "[vix tc diag] mma thread: %.0f units per CTA, %.1f cycles per unit issuing the MMAs, %.1f in the two commits\n",
+                (double)hd[22] / grid, (double)hd[20] / (double)(hd[22] ? hd[22] : 1), (double)hd[21] / (double)(hd[22] ? hd[22] : 1));
 #endif
         fprintf(stderr, "[vix tc scan] nq %lld, handed back %d, candidates %lld (max %d per query; %d per log), error %d\n", (long long)nq,
                 hc[2], tot, mx, log_cap, hc[1]);
