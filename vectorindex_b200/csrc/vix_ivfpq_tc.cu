@@ -12,26 +12,27 @@
 //
 // the only (query, vector) term is a dot product with the DECODED residual r^ = (cb_j[code_j])_j.  So per list:
 //
-//   decode   32 vectors per warp, one vector per lane: 16 G look-ups into ONE query-independent table (the codebooks as
-//            fp16 pairs, T[code][64 slots], 64 KB) and 16 G 4-byte stores build a 128 x d fp16 operand tile in the
-//            tensor cores' K-major 128B-swizzled layout.  Look-ups and stores are bank-conflict free by construction
-//            (rotated codes + a lane -> row permutation); ~100 wavefronts per 32 vectors, paid once per LIST VISIT.
-//   MMA      tcgen05.mma kind::f16 M128 N16..64 K16: D[vector][query] = <r^, q> for the queries probing the list (their
-//            fp16 rows gathered into the B tile), fp32 accumulators in TMEM.
+//   decode   32 vectors per warp, one vector per lane = one TMEM lane: 16 G look-ups into ONE query-independent table (the
+//            codebooks as fp16 pairs, two replicas, T[code][64 slots] x 2 sub-tables = 128 KB of shared memory) in the
+//            rotated order of the stored codes, so the 32 look-ups of a warp instruction hit 32 banks; a four-stage exchange
+//            network puts the 16 values of a group back into sub-quantiser order and tcgen05.st writes them as 16 TMEM
+//            columns: the A operand never touches shared memory.  Paid once per LIST VISIT, not per (query, list).
+//   MMA      tcgen05.mma kind::f16 M128 N16..64 K16, A from TMEM, B = the fp16 rows of the queries probing the list
+//            (gathered into a 128B-swizzled shared-memory tile): D[vector][query] = <r^, q>, fp32 accumulators in TMEM.
 //   filter   one thread per vector row: D >= tau_q + h_v  <=>  bias + t_x - 2 <q, r^> <= thr_q + eps_q, where thr_q is an
-//            EXACT upper bound of the query's k-th best distance (the look-up-table scan over the query's first probed
-//            list) and eps_q bounds |fp16 tensor-core score - the look-up-table scan's fp32 sum|.  Survivors (tens per
-//            query) go to a per-query candidate list.
-//   exact    the candidates are re-evaluated with the very arithmetic of the look-up-table scan (same table entries, same
-//            summation order) and selected by (score, id) together with the seed results: the output is bit-identical
-//            to vix_ivfpq_scan.cu's.  Queries whose seed holds fewer than k vectors, or whose list overflows, are handed
-//            to that kernel entirely.
+//            EXACT upper bound of the query's k-th best distance (the seed: the k best of 256 vectors of the query's first
+//            probed list, in the look-up-table scan's arithmetic) and eps_q bounds |fp16 tensor-core score - the
+//            look-up-table scan's fp32 sum|.  Survivors (C5: ~100 per query) are appended to the filter warp's private log.
+//   exact    every logged (pair, slot) is re-evaluated with the very arithmetic of the look-up-table scan (same table
+//            entries, same summation order) and the k best of a query's keys are selected by (score, id): the output is
+//            bit-identical to vix_ivfpq_scan.cu's.  Queries whose seed holds fewer than k vectors (and every query, should a
+//            log overflow) are handed to that kernel entirely.
 //
-// Kernel structure (one persistent CTA per SM, 18 warps):
-//   warps 0-11   decoders, three groups of four warps; group g owns operand stage g (128 rows)
-//   warps 12-15  filter: tcgen05.ld of the accumulators (one TMEM lane quarter each), emission
-//   warp 16      MMA issuer (one lane)
-//   warp 17      work: takes the next list from a global counter, publishes the item, gathers the B tile + tau
+// Kernel structure (one persistent CTA per SM, 23 warps):
+//   warps 0-11   decoders, three groups of four warps (a warp writes the TMEM lane quarter warp % 4)
+//   warps 12-19  filter, two sets of four warps: tcgen05.ld of the accumulators, comparison, log
+//   warps 20-21  MMA issuers (one lane each, alternating tiles)
+//   warp 22      work: takes the next list from a global counter, publishes the item, gathers the B tile + tau
 // Every mbarrier wait is bounded (a stuck pipeline raises the error flag instead of hanging the GPU).
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -178,14 +179,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // A operand in TMEM (rows = lanes, 32-bit columns of two halves), B from shared memory
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -602,8 +595,8 @@ tc_scan_kernel(Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------- the small kernels
-// decode table + its scale + the residual norm bound: one CTA.  table[code][slot] = half2(s_c cb_j[code]); the last group of
-// an odd number of groups is stored twice (the second half-warp reads the replica).  meta: [1] = s_c, [2] = R_max =
+// decode table + its scale + the residual norm bound: one CTA.  table[sub-table][code][slot] = half2(s_c cb_j[code]), every
+// entry in two replicas (one per half-warp).  meta: [1] = s_c, [2] = R_max =
 // sqrt(sum_j max_c ||cb_j[c]||^2) >= ||r^|| of every stored vector.
 __global__ void __launch_bounds__(1024)
 table_kernel(const float* __restrict__ codebooks, int m, uint32_t* __restrict__ table, float* __restrict__ meta) {
