@@ -59,6 +59,18 @@ def main():
         # same ids; distances agree to fp32 rounding (a vector's 48 table entries are summed in the order of its rotated code
         # layout, which depends on its slot inside its list -- and the shards receive their rows in another order)
         same_as_single(si, sd, fi, fd, f"{metric}: host path")
+        if metric == "euclidean":
+            # the list-major tensor-core scan on every rank (dsub = 2; forced, the batch is below its threshold): the per-query
+            # bounds of the filter are reduced over the ranks (peer memory: stores + barrier; else an NCCL all-reduce), and the
+            # result is the query-major scan's on the same shards, bit for bit
+            os.environ["VIX_TC_SCAN"] = "1"
+            before = _lib.lib().vix_scan_tc_launches()
+            td, ti = sh.batch_search(q, k)
+            td2, ti2 = sh.batch_search(q, k)                                # the bound slots were reset for the next call
+            assert _lib.lib().vix_scan_tc_launches() == before + 2
+            del os.environ["VIX_TC_SCAN"]
+            assert np.array_equal(ti, si) and np.array_equal(td.view(np.uint32), sd.view(np.uint32)), "list-major != query-major"
+            assert np.array_equal(ti2, si) and np.array_equal(td2.view(np.uint32), sd.view(np.uint32)), "list-major, second call"
         # device queries, asynchronous mode
         _lib.lib().vix_set_async(1)
         qd = torch.from_numpy(q).cuda()

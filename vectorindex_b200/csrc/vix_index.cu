@@ -533,6 +533,14 @@ static int update_codebooks_t(vix_index* h) {
     transpose_codebooks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>(h->codebooks.ptr, m, ks, dsub,
                                                                                           h->codebooks_t.ptr);
     VIX_LAUNCH_CHECK();
+    if (tc_decode_table_shape(m, ks, dsub)) {
+        VIX_TRY(h->tc_table.resize(kTcTableWords, false));
+        VIX_TRY(h->tc_meta.resize(4, false));
+        VIX_TRY(tc_decode_table(h->codebooks.ptr, m, h->tc_table.ptr, h->tc_meta.ptr));
+    } else {
+        h->tc_table.free_all();
+        h->tc_meta.free_all();
+    }
     return VIX_OK;
 }
 
@@ -731,6 +739,7 @@ int index_search_locked(vix_index* h, const float* queries, int64_t nq, int k, i
             a.scanned = stats ? scanned.ptr : (traced ? h->trace_scanned.ptr + h->trace_n : nullptr);
             a.phase_cycles = stats ? scanned.ptr + 1 : nullptr;
             a.codebooks_t = h->codebooks_t.ptr;
+            a.tc_table = h->tc_table.ptr; a.tc_meta = h->tc_meta.ptr;
             if (filter) { a.filter = filter->words; a.filter_cap = filter->cap; a.filter_deny = filter->deny; }
             // the work queue head belongs to THIS call (stream-ordered scratch): two threads searching the same handle on
             // different streams in asynchronous mode do not share it

@@ -111,6 +111,8 @@ struct vix_index {
     DevBuf<int64_t> slot_ids;           // [nslots]
     DevBuf<float> slot_vecs;            // IVF_FLAT: [nslots x d]
     DevBuf<float> codebooks_t;          // [ks x m x dsub] code-major copy of the codebooks
+    DevBuf<uint32_t> tc_table;          // the list-major scan's decode table of these codebooks (vix_scan.cuh), when the
+    DevBuf<float> tc_meta;              // shape takes that path; rebuilt with codebooks_t
     int align = 32;                     // list granularity in slots (ScanLayout::align)
     // search_ex(stats): events and counter are created once per handle
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries + the dominant scan kernel

@@ -967,11 +967,11 @@ static int launch_fast(ScanArgs& a) {
 __global__ void __launch_bounds__(256)
 probe_bias_rows_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
                        const int32_t* __restrict__ list_len, int kc, int64_t nq, int nprobe, int d, int order_max,
-                       float* __restrict__ bias) {
+                       const int* __restrict__ only_flagged, float* __restrict__ bias) {
     extern __shared__ float s_rows[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * 8 + warp;
-    if (q >= nq) return;
+    if (q >= nq || (only_flagged && !only_flagged[q])) return;
     float* sq = s_rows + (size_t)warp * d;
     for (int e = lane; e < d; e += 32) sq[e] = __ldg(queries + q * d + e);
     __syncwarp();
@@ -1004,10 +1004,10 @@ probe_bias_rows_kernel(const float* __restrict__ queries, const int32_t* __restr
     }
 }
 
-int launch_probe_bias(const ScanArgs& a, float* bias) {
+int launch_probe_bias(const ScanArgs& a, float* bias, const int* only_flagged) {
     if ((size_t)a.d * 4 * 8 <= 48 * 1024) {
         probe_bias_rows_kernel<<<(unsigned)((a.nq + 7) / 8), 256, (size_t)a.d * 4 * 8, ctx().stream>>>(
-            a.queries, a.probes, a.coarse, a.list_len, a.kc, a.nq, a.nprobe, a.d, a.metric == VIX_METRIC_IP, bias);
+            a.queries, a.probes, a.coarse, a.list_len, a.kc, a.nq, a.nprobe, a.d, a.metric == VIX_METRIC_IP, only_flagged, bias);
         VIX_LAUNCH_CHECK();
         return VIX_OK;
     }

@@ -101,6 +101,8 @@ struct Args {
     const uint8_t* slot_codes; const float* slot_tx;
     const int64_t* list_off; const int32_t* list_len; int kc;
     const int32_t* pair_off;       // [kc + 1]
+    const int32_t* order;          // [*n_order] the lists with pairs, most work first (list_order_*_kernel)
+    const int* n_order;
     const uint32_t* pairs;         // [npairs] query * nprobe + probe position, grouped by list
     const float* bias;             // [nq x nprobe]
     const __half* qh;              // [nq x d] scaled fp16 queries
@@ -526,6 +528,7 @@ tc_scan_kernel(Args a) {
         constexpr int CH = m / 4;                             // 16-byte pieces of a query row (d = 2 m halves)
         int it = 0;
         bool ok = true;
+        const int n_order = *a.n_order;
         auto publish = [&](int fc, int nch, int len, int n, int pb) {
             const int slot = it % kItemRing;
             if (it >= kItemRing && !mbar_wait(&S.item_empty[slot], (uint32_t)(it / kItemRing - 1) & 1u, a.error, a.error_host, VIX_DG(0))) return false;
@@ -539,10 +542,10 @@ tc_scan_kernel(Args a) {
             return true;
         };
         while (ok) {
-            int l = 0;
-            if (lane == 0) l = atomicAdd(a.list_counter, 1);
+            int l = -1;
+            if (lane == 0) { const int i = atomicAdd(a.list_counter, 1); if (i < n_order) l = __ldg(a.order + i); }
             l = __shfl_sync(0xFFFFFFFFu, l, 0);
-            if (l >= a.kc) break;
+            if (l < 0) break;
             const int pb = __ldg(a.pair_off + l), pe = __ldg(a.pair_off + l + 1);
             if (pe == pb) continue;
             const int len = __ldg(a.list_len + l);
@@ -788,16 +791,16 @@ seed_bound_kernel(const float* __restrict__ seed_dist, int64_t nq, int k, float*
 // (a finite k-th seed distance and a finite error bound)
 __global__ void __launch_bounds__(256)
 query_prep_kernel(const float* __restrict__ queries, int64_t nq, int d, const float* __restrict__ qnorm,
-                  const unsigned int* __restrict__ maxabs, float* __restrict__ meta, const float* __restrict__ thr_in,
-                  __half* __restrict__ qh, float* __restrict__ uq, int* __restrict__ flag) {
+                  const unsigned int* __restrict__ maxabs, float* __restrict__ meta, const float* __restrict__ tmeta,
+                  const float* __restrict__ thr_in, __half* __restrict__ qh, float* __restrict__ uq, int* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
     const float g = __uint_as_float(*maxabs);
     float sq = 1.0f;
     if (g > 0.0f) { int e = 0; frexpf(g, &e); sq = ldexpf(1.0f, 10 - e); }
-    if (q == 0 && lane == 0) meta[0] = sq;
-    const float s_c = meta[1], rmax = meta[2];
+    const float s_c = tmeta[1], rmax = tmeta[2];                // of the decode table (per codebooks; meta is this launch's)
+    if (q == 0 && lane == 0) { meta[0] = sq; meta[1] = s_c; }
     for (int e = lane; e < d; e += 32) qh[q * d + e] = __float2half_rn(__ldg(queries + q * d + e) * sq);
     if (lane == 0) {
         const float qn = qnorm[q];
@@ -889,6 +892,105 @@ block_scan_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __rest
         run += v[e];
         if (i == n - 1) off[n] = run;
     }
+}
+
+// bias[pair] = ||q - c_l||^2 of the pairs THIS launch visits (the lists that hold vectors here, the queries not handed
+// back): one warp per pair, four pairs in flight.  The batch-wide rows kernel walks all nprobe probes of a query one after
+// the other, each a chain of dependent loads -- on a shard, where seven of eight probes belong to other ranks, that chain
+// (118 us at C5 on 8 GPUs) cost more than the one-GPU kernel's arithmetic.  Lane-strided partial sums and the xor tree of
+// probe_bias_rows_kernel / build_probe_table: identical bits.
+__global__ void __launch_bounds__(256)
+pair_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
+                 const uint32_t* __restrict__ pairs, const int32_t* __restrict__ npairs_dev, int nprobe, int d,
+                 float* __restrict__ bias) {
+    const int lane = threadIdx.x & 31;
+    const int np = *npairs_dev;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int i0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i0 < np; i0 += 4 * nwarps) {
+        uint32_t pr[4];
+        const float* qv[4];
+        const float* cv[4];
+        float part[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nwarps;
+            pr[u] = i < np ? __ldg(pairs + i) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            part[u] = 0.0f;
+            qv[u] = cv[u] = nullptr;
+            if (pr[u] != 0xFFFFFFFFu) {
+                qv[u] = queries + (size_t)(pr[u] / (uint32_t)nprobe) * d;
+                cv[u] = coarse + (size_t)__ldg(probes + pr[u]) * d;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (qv[u]) for (int e = lane; e < d; e += 32) { const float df = __ldg(qv[u] + e) - __ldg(cv[u] + e); part[u] = fmaf(df, df, part[u]); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            for (int o = 16; o > 0; o >>= 1) part[u] += __shfl_xor_sync(0xFFFFFFFFu, part[u], o);
+        if (lane < 4 && pr[lane] != 0xFFFFFFFFu) bias[pr[lane]] = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+    }
+}
+
+// The order in which the CTAs take the lists: most work first (work = 128-vector tiles x visits of kNQ queries), so the
+// long lists do not end up as the tail of the kernel -- at one-eighth of the lists a CTA sees ~55 lists and one list of ten
+// times the mean length taken last was a fifth of the kernel.  A counting sort over 256 work classes (eight per octave,
+// descending); lists nobody probes are left out.  hist = pairs per list (pair_count_kernel).
+constexpr int kOrderClasses = 256;
+__device__ __forceinline__ int work_class(int npairs, int len) {
+    const unsigned w = (unsigned)((len + 127) >> 7) * (unsigned)((npairs + kNQ - 1) / kNQ);      // >= 1
+    const int e = 31 - __clz(w);
+    const int frac = e >= 3 ? (int)((w >> (e - 3)) & 7u) : (int)((w << (3 - e)) & 7u);
+    return kOrderClasses - 1 - (8 * e + frac);
+}
+__global__ void __launch_bounds__(256)
+list_order_count_kernel(const int32_t* __restrict__ hist, const int32_t* __restrict__ list_len, int kc, int* __restrict__ class_cnt) {
+    __shared__ int s_h[kOrderClasses];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int l = blockIdx.x * kScanBlock + threadIdx.x; l < min(kc, (int)(blockIdx.x + 1) * kScanBlock); l += 256) {
+        const int np = hist[l];
+        if (np > 0) atomicAdd(&s_h[work_class(np, __ldg(list_len + l))], 1);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(class_cnt + threadIdx.x, s_h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256)
+list_order_scatter_kernel(const int32_t* __restrict__ hist, const int32_t* __restrict__ list_len, int kc,
+                          const int* __restrict__ class_cnt, int* __restrict__ class_cur, int32_t* __restrict__ order,
+                          int* __restrict__ n_order) {
+    __shared__ int s_h[kOrderClasses], s_at[kOrderClasses], s_w[8];
+    // where class c starts: the exclusive prefix sum of the class counts (every CTA recomputes the 256 sums)
+    const int cnt = class_cnt[threadIdx.x];
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)(threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = inc - cnt;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += s_w[w];
+    if (blockIdx.x == 0 && threadIdx.x == kOrderClasses - 1) *n_order = base + cnt;
+    const int lo = blockIdx.x * kScanBlock, hi = min(kc, lo + kScanBlock);
+    int cls[kScanBlock / 256], pos[kScanBlock / 256];
+#pragma unroll
+    for (int e = 0; e < kScanBlock / 256; ++e) {
+        const int l = lo + threadIdx.x + 256 * e;
+        cls[e] = -1;
+        if (l < hi) {
+            const int np = hist[l];
+            if (np > 0) { cls[e] = work_class(np, __ldg(list_len + l)); pos[e] = atomicAdd(&s_h[cls[e]], 1); }
+        }
+    }
+    __syncthreads();
+    // this CTA's lists of class c go to one run, reserved with one atomic per (CTA, class)
+    s_at[threadIdx.x] = s_h[threadIdx.x] ? base + atomicAdd(class_cur + threadIdx.x, s_h[threadIdx.x]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kScanBlock / 256; ++e)
+        if (cls[e] >= 0) order[s_at[cls[e]] + pos[e]] = lo + threadIdx.x + 256 * e;
 }
 
 // The finalists.  One CTA per log, one thread per (pair, slot) record: the record is replaced by its exact key -- the
@@ -1026,10 +1128,60 @@ static int smem_base() {
 
 // L2, dsub = 2, rotated lists, no filter, no phase statistics; batches large enough that lists are shared.
 // VIX_TC_SCAN=0 disables the path, =1 takes it whenever the shape allows.
+// VIX_TC_SCAN_TIMES=1: CUDA events between the stages of every list-major launch (no synchronisation: the events of a launch are
+// read when the NEXT launch of this thread starts, or at exit), summed and printed at process exit.  For multi-GPU runs, where
+// ncu cannot look: which of the small stages a rank's step consists of.
+namespace tcs {
+constexpr int kTimeMarks = 10;
+static const char* const kTimeNames[kTimeMarks - 1] = {"table+norms+seed_probe", "seed_scan", "bound(+allreduce)", "prep+pairs+order",
+                                                        "probe_bias", "tc_scan", "log_key", "scatter+select", "handed_back"};
+struct StageTimes {
+    cudaEvent_t ev[kTimeMarks] = {};
+    bool have = false, pending = false;
+    double sum[kTimeMarks - 1] = {};
+    long long launches = 0;
+    void collect() {
+        if (!pending) return;
+        if (cudaEventSynchronize(ev[kTimeMarks - 1]) == cudaSuccess) {
+            for (int i = 0; i + 1 < kTimeMarks; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) sum[i] += ms; }
+            ++launches;
+        }
+        pending = false;
+    }
+    ~StageTimes() {
+        collect();
+        if (!launches) return;
+        const char* r = getenv("RANK");
+        double tot = 0;
+        for (int i = 0; i + 1 < kTimeMarks; ++i) tot += sum[i];
+        fprintf(stderr, "[vix tc times] rank %s, %lld launches, %.1f us per launch:", r ? r : "-", launches, 1e3 * tot / launches);
+        for (int i = 0; i + 1 < kTimeMarks; ++i) fprintf(stderr, " %s %.1f", kTimeNames[i], 1e3 * sum[i] / launches);
+        fprintf(stderr, "\n");
+    }
+};
+static StageTimes* stage_times() {
+    static const bool on = [] { const char* e = getenv("VIX_TC_SCAN_TIMES"); return e && e[0] == '1'; }();
+    if (!on) return nullptr;
+    static thread_local StageTimes st;
+    if (!st.have) {
+        for (int i = 0; i < kTimeMarks; ++i) if (cudaEventCreate(&st.ev[i]) != cudaSuccess) return nullptr;
+        st.have = true;
+    }
+    return &st;
+}
+}  // namespace tcs
+
+bool tc_decode_table_shape(int m, int ks, int dsub) { return dsub == 2 && ks == 256 && (m == 16 || m == 32 || m == 48 || m == 64); }
+int tc_decode_table(const float* codebooks, int m, uint32_t* table, float* meta) {
+    tcs::table_kernel<<<1, 1024, 0, ctx().stream>>>(codebooks, m, table, meta);
+    VIX_LAUNCH_CHECK();
+    return VIX_OK;
+}
+
 bool tc_scan_supported(const ScanArgs& a) {
     const char* env = getenv("VIX_TC_SCAN");
     if (env && env[0] == '0') return false;
-    if (a.metric != VIX_METRIC_L2 || a.dsub != 2 || a.ks != 256 || !(a.m == 16 || a.m == 32 || a.m == 48 || a.m == 64)) return false;
+    if (a.metric != VIX_METRIC_L2 || !tc_decode_table_shape(a.m, a.ks, a.dsub)) return false;
     if (a.filter || a.phase_cycles || a.nq_dev || a.k > 64) return false;
     if (a.nq * (int64_t)a.nprobe >= (1LL << 32) || a.nq < 1) return false;
     if (!(env && env[0] == '1') && a.nq * (int64_t)a.nprobe < 32768) return false;
@@ -1052,7 +1204,12 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     Scratch<uint32_t> log_q;
     Scratch<__half> qh;
     Scratch<u64> cand;
-    VIX_TRY(table.alloc(2 * 256 * 64));
+    const bool own_table = !(a.tc_table && a.tc_meta);          // callers without a handle: the table of this launch
+    if (own_table) VIX_TRY(table.alloc(kTcTableWords));
+    Scratch<float> own_meta;
+    if (own_table) VIX_TRY(own_meta.alloc(4));
+    const uint32_t* const table_ptr = own_table ? table.ptr : a.tc_table;
+    const float* const tmeta_ptr = own_table ? own_meta.ptr : a.tc_meta;
     VIX_TRY(meta.alloc(4));
     VIX_TRY(qnorm.alloc((size_t)nq));
     VIX_TRY(uq.alloc((size_t)nq));
@@ -1070,7 +1227,11 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_TRY(bsum.alloc((size_t)nblk));
     VIX_TRY(pairs.alloc((size_t)npairs));
     VIX_TRY(bias.alloc((size_t)npairs));
-    VIX_TRY(counters.alloc(8));                    // [0] list counter, [1] error, [2] fall-back count, [3] status, [4] log overflow
+    Scratch<int32_t> order;
+    VIX_TRY(order.alloc((size_t)a.kc));
+    // [0] list counter, [1] error, [2] fall-back count, [3] status, [4] log overflow, [5] lists in `order`;
+    // [8, 264) lists per work class, [264, 520) the scatter's cursors
+    VIX_TRY(counters.alloc(8 + 2 * kOrderClasses));
     VIX_TRY(cand_cnt.alloc((size_t)nq + 1));
     VIX_TRY(cand_off.alloc((size_t)nq + 1));
     VIX_TRY(cand_cur.alloc((size_t)nq + 1));
@@ -1078,17 +1239,22 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_TRY(wc_fb.alloc(2));
     VIX_CUDA(cudaMemsetAsync(maxabs.ptr, 0, 4, s));
     VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)a.kc + 1) * 4, s));
-    VIX_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, s));
+    VIX_CUDA(cudaMemsetAsync(counters.ptr, 0, (8 + 2 * kOrderClasses) * sizeof(int), s));
     VIX_CUDA(cudaMemsetAsync(cand_cnt.ptr, 0, (size_t)nq * 4, s));
+    StageTimes* const times = stage_times();
+    if (times) times->collect();
+    int mark_i = 0;
+    auto mark = [&] { if (times && mark_i < kTimeMarks) cudaEventRecord(times->ev[mark_i++], s); };
+    mark();
 
-    table_kernel<<<1, 1024, 0, s>>>(a.codebooks, m, table.ptr, meta.ptr);
-    VIX_LAUNCH_CHECK();
+    if (own_table) VIX_TRY(tc_decode_table(a.codebooks, m, table.ptr, own_meta.ptr));
     const unsigned qwarps = (unsigned)((nq * 32 + 255) / 256);
     query_norm_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr);
     VIX_LAUNCH_CHECK();
     seed_probe_kernel<<<qwarps, 256, 0, s>>>(a.probes, nq, a.nprobe, a.list_len, a.kc, tls_thr_hook != nullptr, seed_list.ptr,
                                             seed_pos.ptr);
     VIX_LAUNCH_CHECK();
+    mark();
     {   // seed: the first probed list that holds vectors here, one warp per query
         const int Pw = next_pow2(k + 64);
         const size_t ssm = (size_t)8 * Pw * 8 + (size_t)8 * m * 8;
@@ -1108,13 +1274,15 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         }
 #undef VIX_SEED
     }
+    mark();
     Scratch<float> thr;
     VIX_TRY(thr.alloc((size_t)nq));
     seed_bound_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(seed_dist.ptr, nq, k, thr.ptr);
     VIX_LAUNCH_CHECK();
     if (tls_thr_hook) VIX_TRY(tls_thr_hook(tls_thr_ctx, thr.ptr, nq));         // sharded: the minimum over the ranks
-    query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, thr.ptr, qh.ptr, uq.ptr,
-                                            flag.ptr);
+    mark();
+    query_prep_kernel<<<qwarps, 256, 0, s>>>(a.queries, nq, d, qnorm.ptr, maxabs.ptr, meta.ptr, tmeta_ptr, thr.ptr, qh.ptr,
+                                            uq.ptr, flag.ptr);
     VIX_LAUNCH_CHECK();
     const unsigned pblocks = (unsigned)((npairs + 255) / 256);
     pair_count_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, flag.ptr, hist.ptr, a.scanned);
@@ -1123,10 +1291,24 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_LAUNCH_CHECK();
     block_scan_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.kc, bsum.ptr, off.ptr, cursor.ptr);
     VIX_LAUNCH_CHECK();
+    list_order_count_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.list_len, a.kc, counters.ptr + 8);
+    VIX_LAUNCH_CHECK();
+    list_order_scatter_kernel<<<nblk, 256, 0, s>>>(hist.ptr, a.list_len, a.kc, counters.ptr + 8, counters.ptr + 8 + kOrderClasses,
+                                                  order.ptr, counters.ptr + 5);
+    VIX_LAUNCH_CHECK();
     pair_scatter_kernel<<<pblocks, 256, 0, s>>>(a.probes, npairs, a.nprobe, a.list_len, a.kc, flag.ptr, cursor.ptr,
                                                pairs.ptr);
     VIX_LAUNCH_CHECK();
-    VIX_TRY(launch_probe_bias(a, bias.ptr));
+    mark();
+    {   // the per-pair term: this launch's pairs; all probes of the (rare) queries handed back, for the look-up-table scan
+        int64_t want = (npairs * 32 + 4 * 256 - 1) / (4 * 256);
+        const int64_t cap = (int64_t)num_sms() * 8;
+        pair_bias_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr,
+                                                                                         off.ptr + a.kc, a.nprobe, d, bias.ptr);
+        VIX_LAUNCH_CHECK();
+        VIX_TRY(launch_probe_bias(a, bias.ptr, flag.ptr));
+    }
+    mark();
 
     int grid = num_sms();
     if (grid > a.kc) grid = a.kc;
@@ -1142,7 +1324,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_CUDA(cudaMemsetAsync(log_cnt.ptr, 0, (size_t)grid * kEpiWarps * sizeof(int), s));
     Args t{};
     t.slot_codes = a.slot_codes; t.slot_tx = a.slot_tx; t.list_off = a.list_off; t.list_len = a.list_len; t.kc = a.kc;
-    t.pair_off = off.ptr; t.pairs = pairs.ptr; t.bias = bias.ptr; t.qh = qh.ptr; t.uq = uq.ptr; t.table = table.ptr;
+    t.pair_off = off.ptr; t.order = order.ptr; t.n_order = counters.ptr + 5; t.pairs = pairs.ptr; t.bias = bias.ptr; t.qh = qh.ptr;
+    t.uq = uq.ptr; t.table = table_ptr;
     t.scales = meta.ptr; t.nprobe = a.nprobe; t.d = d; t.m = m;
     t.list_counter = counters.ptr; t.log = log.ptr; t.log_cnt = log_cnt.ptr; t.log_cap = log_cap;
     t.error = counters.ptr + 1; t.error_host = pipeline_error_flag();
@@ -1162,6 +1345,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         tc_scan_kernel<GG><<<grid, kThreads, smem, s>>>(t);                                                                \
         VIX_LAUNCH_CHECK();                                                                                                \
         if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], s));                                                  \
+        mark();                                                                                                            \
         log_key_kernel<GG><<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
             a.codebooks_t, a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, counters.ptr + 4);                           \
         VIX_LAUNCH_CHECK();                                                                                                \
@@ -1173,6 +1357,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         case 4: VIX_TCS(4); break;
     }
 #undef VIX_TCS
+    mark();
     {   // per-query runs of keys, then the selection
         const int qblk = (int)((nq + kScanBlock - 1) / kScanBlock);
         VIX_TRY(bsum.alloc((size_t)qblk));
@@ -1187,6 +1372,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
                                                               counters.ptr + 2, a.out_dist, a.out_ids);
         VIX_LAUNCH_CHECK();
     }
+    mark();
     {   // the queries handed back: all their probes through the look-up-table scan
         ScanArgs fb = a;
         fb.order = fb_list.ptr; fb.nq_dev = counters.ptr + 2;
@@ -1195,6 +1381,8 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         fb.work_counter = wc_fb.ptr;
         VIX_TRY(launch_ivfpq_scan_classic(fb));
     }
+    mark();
+    if (times) times->pending = mark_i == kTimeMarks;
     g_tc_launches.fetch_add(1);
     if (getenv("VIX_TC_SCAN_DEBUG")) {
         // diagnostics (synchronises): queries handed back, candidates per query

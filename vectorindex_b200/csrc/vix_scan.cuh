@@ -22,6 +22,8 @@ struct ScanArgs {
                                                   // copying); built batch-wide when the codebooks are large
     const float* codebooks;                       // [m x ks x dsub]
     const float* codebooks_t;                     // [ks x m x dsub]  (code-major copy for the LUT build)
+    const uint32_t* tc_table; const float* tc_meta;  // optional: the list-major path's decode table + its scale / norm bound,
+                                                  // built once per codebooks (tc_decode_table); absent -> built per launch
     const int64_t* list_off; const int32_t* list_len;
     const uint8_t* slot_codes; const float* slot_tx; const int64_t* slot_ids;
     // optional id filter (IDFilter.swift:115-135): ids outside [0, filter_cap) never pass; allowlist keeps set bits,
@@ -56,6 +58,12 @@ void set_scan_thr_hook(scan_thr_hook_t fn, void* ctx);
 int launch_ivfpq_scan(ScanArgs& a);            // picks the path
 bool tc_scan_supported(const ScanArgs& a);     // would launch_ivfpq_scan take the list-major tensor-core path (vix_ivfpq_tc.cu)?
 int launch_ivfpq_scan_classic(ScanArgs& a);    // query-major look-up-table scan (vix_ivfpq_scan.cu)
-int launch_probe_bias(const ScanArgs& a, float* bias);   // bias[q x nprobe]: the per-probe term, batch-wide
+// bias[q x nprobe]: the per-probe term, batch-wide; with `only_flagged` [nq] just the rows of the queries flagged there
+int launch_probe_bias(const ScanArgs& a, float* bias, const int* only_flagged = nullptr);
+// the list-major path's decode table of a set of codebooks (dsub = 2, ks = 256, m in {16, 32, 48, 64}): table
+// [kTcTableWords] fp16 pairs, meta [4] floats ([1] the table's scale, [2] the bound of a decoded residual's norm)
+constexpr size_t kTcTableWords = 2 * 256 * 64;
+bool tc_decode_table_shape(int m, int ks, int dsub);
+int tc_decode_table(const float* codebooks, int m, uint32_t* table, float* meta);
 
 }  // namespace vix

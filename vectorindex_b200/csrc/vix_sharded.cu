@@ -103,13 +103,14 @@ struct vix_comm {
     std::mutex mu;
     // exchange memory: one region per rank, every region mapped into every rank (cudaIpc).  Same layout everywhere:
     //   [flags: one word per peer][queries: world x per x d f32][probes: world x per x nprobe i32][results: world x nq x k u64]
+    //   [bounds: nq f32 -- the list-major scan's per-query bounds the OTHER ranks found; all bits set (a NaN) = none]
     int peer_state = -1;                    // -1 undecided, 0 NCCL all-gathers, 1 peer memory
     void* local = nullptr;
     size_t local_bytes = 0;
     std::vector<void*> peer;                // base of every rank's region in THIS process (peer[rank] == local)
     void** peer_dev = nullptr;              // device copy
     uint32_t epoch = 0;                     // barriers passed so far
-    size_t off_queries = 0, off_probes = 0, off_results = 0;
+    size_t off_queries = 0, off_probes = 0, off_results = 0, off_bounds = 0;
     int64_t cap_nq = 0, cap_per = 0;
     int cap_d = 0, cap_nprobe = 0, cap_k = 0;
     // NCCL path: plain local buffers with the same roles
@@ -157,7 +158,8 @@ static int ensure_region(vix_comm* c, int64_t nq, int d, int nprobe, int k) {
     const size_t off_q = kFlagBytes;
     const size_t off_p = off_q + (size_t)world * per * cd * 4;
     const size_t off_r = (off_p + (size_t)world * per * cp * 4 + 255) & ~(size_t)255;
-    const size_t total = off_r + (size_t)world * cnq * ck * 8;
+    const size_t off_b = (off_r + (size_t)world * cnq * ck * 8 + 255) & ~(size_t)255;
+    const size_t total = off_b + (size_t)cnq * 4;
     VIX_CUDA(cudaStreamSynchronize(s));                                   // nothing of mine still writes into a peer
     void* fresh = nullptr;
     int ok = 1;
@@ -166,6 +168,7 @@ static int ensure_region(vix_comm* c, int64_t nq, int d, int nprobe, int k) {
     memset(&mine, 0, sizeof(mine));
     if (ok && cudaMalloc(&fresh, total) != cudaSuccess) { cudaGetLastError(); ok = 0; fresh = nullptr; }
     if (ok && cudaMemsetAsync(fresh, 0, kFlagBytes, s) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok && cudaMemsetAsync(static_cast<char*>(fresh) + off_b, 0xFF, (size_t)cnq * 4, s) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     if (ok && cudaIpcGetMemHandle(&mine, fresh) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     // all-gather of (ok, handle): also the barrier behind which the old regions may go
     struct Msg { int ok; int pad; cudaIpcMemHandle_t h; };
@@ -211,7 +214,7 @@ static int ensure_region(vix_comm* c, int64_t nq, int d, int nprobe, int k) {
     VIX_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->peer_dev), sizeof(void*) * world));
     VIX_CUDA(cudaMemcpyAsync(c->peer_dev, peer.data(), sizeof(void*) * world, cudaMemcpyHostToDevice, s));
     VIX_CUDA(cudaStreamSynchronize(s));
-    c->off_queries = off_q; c->off_probes = off_p; c->off_results = off_r;
+    c->off_queries = off_q; c->off_probes = off_p; c->off_results = off_r; c->off_bounds = off_b;
     c->cap_nq = cnq; c->cap_per = per; c->cap_d = cd; c->cap_nprobe = cp; c->cap_k = ck;
     c->peer_state = 1;
     return VIX_OK;
@@ -271,6 +274,27 @@ __global__ void pack_result_keys_kernel(const float* __restrict__ dist, const in
     const u64 key = id < 0 ? kEmptyKey : make_key(dist[i], (uint32_t)id, 0);
     if (local_only) { local_only[i] = key; return; }
     for (int p = 0; p < world; ++p) reinterpret_cast<u64*>(static_cast<char*>(peer_base[p]) + off)[i] = key;
+}
+
+// The list-major scan's bounds (vix_scan.cuh: scan_thr_hook_t) over peer memory: a rank finds a finite bound only for the
+// queries whose first probed list it owns, so the minimum over the ranks is a store of those into every peer's bound
+// array, a barrier, and a minimum with what arrived here -- which is reset on the way (the next writers are behind the
+// next call's first barrier, which this rank enters after the reset).
+__global__ void push_bounds_kernel(const float* __restrict__ thr, int64_t nq, void* const* __restrict__ peer_base, int world, int rank,
+                                   size_t off) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float t = thr[q];
+    if (!(fabsf(t) < __int_as_float(0x7f800000))) return;
+    for (int p = 0; p < world; ++p)
+        if (p != rank) reinterpret_cast<float*>(static_cast<char*>(peer_base[p]) + off)[q] = t;
+}
+__global__ void take_bounds_kernel(float* __restrict__ thr, int64_t nq, uint32_t* __restrict__ arrived) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t v = arrived[q];
+    arrived[q] = 0xFFFFFFFFu;
+    thr[q] = fminf(thr[q], __uint_as_float(v));             // fminf(x, NaN) = x
 }
 
 static int peer_barrier(vix_comm* c) {
@@ -369,7 +393,17 @@ int vix_sharded_query_block(int64_t nq, int rank, int world, int64_t* first, int
 // the list-major scan's per-query bounds -> their minimum over the ranks (vix_scan.cuh: scan_thr_hook_t)
 static int thr_min_over_ranks(void* ctx, float* thr_dev, int64_t nq) {
     vix_comm* c = static_cast<vix_comm*>(ctx);
-    VIX_NCCL(g_nccl.AllReduce(thr_dev, thr_dev, (size_t)nq, ncclFloat, ncclMin, c->comm, vix::ctx().stream));
+    cudaStream_t s = vix::ctx().stream;
+    if (c->peer_state == 1 && nq <= c->cap_nq) {
+        const unsigned grid = (unsigned)((nq + 255) / 256);
+        push_bounds_kernel<<<grid, 256, 0, s>>>(thr_dev, nq, c->peer_dev, c->world, c->rank, c->off_bounds);
+        VIX_LAUNCH_CHECK();
+        VIX_TRY(peer_barrier(c));
+        take_bounds_kernel<<<grid, 256, 0, s>>>(thr_dev, nq, reinterpret_cast<uint32_t*>(static_cast<char*>(c->local) + c->off_bounds));
+        VIX_LAUNCH_CHECK();
+        return VIX_OK;
+    }
+    VIX_NCCL(g_nccl.AllReduce(thr_dev, thr_dev, (size_t)nq, ncclFloat, ncclMin, c->comm, s));
     return VIX_OK;
 }
 struct ThrHookScope {
