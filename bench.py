@@ -730,6 +730,13 @@ def main():
                      "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                      "job_code_bytes_per_step": scan_bytes_all / K},
     }
+    if traffic and per_launch_ms > 0:
+        # the DRAM side of the same launch: the captured bytes over this run's kernel time
+        dram = traffic / (per_launch_ms * 1e-3) / 1e9
+        line["roofline"].update(dram_achieved=dram, dram_frac=dram / peak)
+    if list_major:
+        line["roofline"]["limiter"] = ("ALU pipe of the decode (ncu sm__inst_executed_pipe_alu 73 % at C5 on one GPU; the exchange network's "
+                                       "SELs are 22 % of the executed instructions), DESIGN 4.1b")
     if world == 1 and not args.no_cpu_baseline and not args.profile:
         info, _, _ = cpu_search_arm(cfg, idx, q_host, gpu_ids=np.asarray(h_i))
         line["cpu_baseline"] = info

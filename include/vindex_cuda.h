@@ -26,6 +26,17 @@
  *     rejected (assignments) or skipped like the -1 padding (probes); rows whose scores are all NaN get no list:
  *     IVF_FLAT keeps them unreachable as the reference does (IVFIndex.swift:376-435 "guard best >= 0"), IVF_PQ add fails.
  *
+ * Environment switches (tests, A/B measurements and diagnostics; none is needed in production, none changes a result):
+ *   VIX_TC_SCAN=0 | 1        never / whenever the shape allows take the list-major tensor-core IVF-PQ scan (default: L2,
+ *                            d = 2 m, ks = 256, nq x nprobe >= 32768)
+ *   VIX_TC_SCAN_DEBUG=1      per launch (synchronises): queries handed back, finalists per query
+ *   VIX_TC_SCAN_TIMES=1      CUDA events between the stages of every list-major launch, summed, printed at exit
+ *   VIX_SCAN_DUAL=2          two query pipelines per SM in the query-major scan (an error where the shape cannot)
+ *   VIX_DISABLE_TC, VIX_DISABLE_PQ_TC, VIX_DISABLE_LUT_IMAGE
+ *                            exact CUDA-core kernels instead of the tensor-core shortlists / per-query tables built inside
+ *                            the scan instead of batch-wide (the parity tests compare both ways)
+ *   VIX_NO_P2P=1             vix_sharded_*: NCCL all-gathers instead of peer memory; VIX_NCCL_PATH: the libnccl to dlopen
+ *
  * Each declaration cites the reference interface it replaces (paths relative to
  * /root/reference/Sources/VectorIndex unless another root is given).
  */
