@@ -1266,19 +1266,16 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
                                                pairs.ptr);
     VIX_LAUNCH_CHECK();
     mark();
-    if (tls_thr_hook) {
-        // a shard: most probes belong to other ranks -- the per-pair term of this launch's pairs only (C5 on 8 GPUs: 118 us for
-        // the batch-wide rows kernel, whose warp walks all nprobe probes of a query as one chain of dependent loads), plus
-        // all probes of the (rare) queries handed back, for the look-up-table scan
+    {   // the per-pair term of this launch's pairs, plus all probes of the (rare) queries handed back, for the look-up-table
+        // scan.  (The batch-wide rows kernel walks all nprobe probes of a query as one chain of dependent loads: on a shard,
+        // where seven of eight probes belong to other ranks, 118 us against 73 at C5 on 8 GPUs; on one GPU the two are equal,
+        // 180 / 173 us between events.)
         int64_t want = (npairs * 32 + 8 * 256 - 1) / (8 * 256);
         const int64_t cap = (int64_t)num_sms() * 8;
         pair_bias_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr,
                                                                                          off.ptr + a.kc, a.nprobe, d, bias.ptr);
         VIX_LAUNCH_CHECK();
         VIX_TRY(launch_probe_bias(a, bias.ptr, flag.ptr));
-    } else {
-        // every list is here: one warp per query with its row in shared memory reads half the bytes (C5: 108 against 173 us)
-        VIX_TRY(launch_probe_bias(a, bias.ptr));
     }
     mark();
 
