@@ -649,52 +649,58 @@ table_kernel(const float* __restrict__ codebooks, int m, uint32_t* __restrict__ 
     }
 }
 
-// The seed: one WARP per query evaluates the first kSeedChunks x 32 vectors of the query's first probed list that holds
-// vectors here and keeps their k best -- exact keys, the same table entries (lut_entry2 from the code-major codebooks,
-// L1-resident) in the same summation order as the look-up-table scan, but without building a 128 KB table.  The k-th of ANY k
-// stored vectors is an upper bound of the query's k-th best distance: that is the threshold of the filter (thr[q]; +inf
-// when the sample holds fewer than k vectors).  (The whole list would give a tighter threshold and fewer finalists, but costs
-// more than the finalists it saves: C5 1.77 ms against 0.3 ms.)  On the way the warp leaves ||q|| and the batch maximum of
-// |q_e| (the fp16 scale) for query_prep_kernel.
+// The seed: one CTA per query, one WARP per 32-vector chunk: the first kSeedChunks x 32 vectors of the query's first probed
+// list that holds vectors here get their exact keys -- the same table entries (lut_entry2 from the code-major codebooks,
+// L1-resident) in the same summation order as the look-up-table scan, but without building a 128 KB table -- and the CTA
+// sorts them.  The k-th of ANY k stored vectors is an upper bound of the query's k-th best distance: that is the threshold
+// of the filter (thr[q]; +inf when the sample holds fewer than k vectors).  (The whole list would give a tighter threshold
+// and fewer finalists, but costs more than the finalists it saves: C5 1.77 ms against 0.3 ms.  One warp walking the eight
+// chunks in sequence took 84 us for the 1250 queries a rank of eight seeds -- latency, not work.)  On the way the CTA
+// leaves ||q|| and the batch maximum of |q_e| (the fp16 scale) for query_prep_kernel.
 // A shard (only_first): only the rank that owns the query's FIRST probed list seeds it (the bounds are reduced over the
 // ranks; a seed from a farther list would be looser than the owner's and cost the same).
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kSeedChunks)
 seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* __restrict__ probes, int nprobe, int kc,
                  int only_first, const float* __restrict__ coarse, const float* __restrict__ codebooks_t,
                  const int64_t* __restrict__ list_off, const int32_t* __restrict__ list_len, const uint8_t* __restrict__ slot_codes,
-                 const float* __restrict__ slot_tx, const int64_t* __restrict__ slot_ids, int k, int Pw, int max_chunks,
-                 float* __restrict__ qnorm, unsigned int* __restrict__ maxabs, float* __restrict__ thr) {
+                 const float* __restrict__ slot_tx, int k, float* __restrict__ qnorm, unsigned int* __restrict__ maxabs,
+                 float* __restrict__ thr) {
     constexpr int m = 16 * G, d = 2 * m;
-    extern __shared__ __align__(16) unsigned char ssm[];
+    __shared__ u64 s_keys[32 * kSeedChunks];
+    __shared__ float2 s_q[m];
+    __shared__ int s_list;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
-    if (q >= nq) return;
-    u64* wq = reinterpret_cast<u64*>(ssm) + (size_t)warp * Pw;
-    float2* sq = reinterpret_cast<float2*>(reinterpret_cast<u64*>(ssm) + (size_t)8 * Pw) + (size_t)warp * m;
-    {   // ||q|| and max |q_e|
+    const int64_t q = blockIdx.x;
+    const float* qv = queries + q * d;
+    if (warp == 0) {
+        // ||q|| and max |q_e|
         float s = 0.0f, mx = 0.0f;
-        for (int e = lane; e < d; e += 32) { const float v = __ldg(queries + q * d + e); s = fmaf(v, v, s); mx = fmaxf(mx, fabsf(v)); }
+        for (int e = lane; e < d; e += 32) { const float v = __ldg(qv + e); s = fmaf(v, v, s); mx = fmaxf(mx, fabsf(v)); }
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xFFFFFFFFu, s, o); mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o)); }
         if (lane == 0) {
             qnorm[q] = sqrtf(s);
             if (mx == mx && mx < __int_as_float(0x7f800000)) atomicMax(maxabs, __float_as_uint(mx));
         }
+        // the first probe position whose list holds vectors here
+        int l = -1, p0 = -1;
+        for (int base = 0; base < nprobe; base += 32) {
+            const int p = base + lane;
+            const int lp = p < nprobe ? __ldg(probes + q * nprobe + p) : -1;
+            const bool here = (unsigned)lp < (unsigned)kc && __ldg(list_len + lp) > 0;
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
+            if (ball) { const int src = __ffs(ball) - 1; l = __shfl_sync(0xFFFFFFFFu, lp, src); p0 = base + src; break; }
+        }
+        if (only_first && p0 != 0) l = -1;
+        if (lane == 0) s_list = l;
     }
-    // the first probe position whose list holds vectors here
-    int l = -1, p0 = -1;
-    for (int base = 0; base < nprobe; base += 32) {
-        const int p = base + lane;
-        const int lp = p < nprobe ? __ldg(probes + q * nprobe + p) : -1;
-        const bool here = (unsigned)lp < (unsigned)kc && __ldg(list_len + lp) > 0;
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, here);
-        if (ball) { const int src = __ffs(ball) - 1; l = __shfl_sync(0xFFFFFFFFu, lp, src); p0 = base + src; break; }
-    }
-    if (l < 0 || (only_first && p0 != 0)) {
-        if (lane == 0) thr[q] = __int_as_float(0x7f800000);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s_q[j] = make_float2(__ldg(qv + 2 * j) * -2.0f, __ldg(qv + 2 * j + 1) * -2.0f);
+    __syncthreads();
+    const int l = s_list;
+    if (l < 0) {
+        if (threadIdx.x == 0) thr[q] = __int_as_float(0x7f800000);
         return;
     }
-    const float* qv = queries + q * d;
     // bias ||q - c_l||^2 in the order of probe_bias_kernel / build_probe_table (lane-strided partial sums, xor tree)
     float bias = 0.0f;
     {
@@ -702,19 +708,14 @@ seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
         for (int e = lane; e < d; e += 32) { const float df = __ldg(qv + e) - __ldg(c + e); bias = fmaf(df, df, bias); }
         for (int o = 16; o > 0; o >>= 1) bias += __shfl_xor_sync(0xFFFFFFFFu, bias, o);
     }
-    for (int j = lane; j < m; j += 32) sq[j] = make_float2(__ldg(qv + 2 * j) * -2.0f, __ldg(qv + 2 * j + 1) * -2.0f);
-    for (int i = lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-    __syncwarp();
     const int len = __ldg(list_len + l);
     const uint32_t first = (uint32_t)(__ldg(list_off + l) >> 5);
-    const int nch = min((len + 31) >> 5, max_chunks);               // a SAMPLE of the list: any k vectors bound the k-th best
     const float2* cbt = reinterpret_cast<const float2*>(codebooks_t);
-    int cnt = 0;
-    uint32_t thr_u = 0xFFFFFFFFu;
     const uint32_t rot = (uint32_t)lane & 15u;
-    for (int ch = 0; ch < nch; ++ch) {
+    u64 key = kEmptyKey;
+    const int ch = warp;                                             // a SAMPLE of the list: any k vectors bound the k-th best
+    if (ch * 32 + lane < len) {
         const uint32_t g = ((first + (uint32_t)ch) << 5) + (uint32_t)lane;
-        const bool valid = ch * 32 + lane < len;
         const uint4* src = reinterpret_cast<const uint4*>(slot_codes + (size_t)(first + ch) * (512u * G)) + lane;
         float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -729,39 +730,19 @@ seed_scan_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
                     const uint32_t code = (x[i4] >> (8 * t)) & 255u;
                     const uint32_t j = 16u * grp + (b ^ rot);
                     const float2 v = __ldg(cbt + code * m + j);
-                    const float2 qq = sq[j];
+                    const float2 qq = s_q[j];
                     s[t] = fadd(s[t], lut_entry2(qq.x, qq.y, v));
                 }
             }
         }
         const float sum = fadd(fadd(bias, __ldg(slot_tx + g)), fadd(fadd(s[0], s[1]), fadd(s[2], s[3])));
-        const u64 key = make_key(sum, 0u, 0);
-        const uint32_t ku = valid ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
-        if (thr_u == 0xFFFFFFFFu && k <= 32) {
-            const uint32_t kth = warp_kth_smallest(ku, k - 1, lane);       // k entries of this chunk are at least this good
-            if (kth != 0xFFFFFFFFu) thr_u = kth;
-        }
-        const bool pass = valid && ku <= thr_u;
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
-        if (ball) {
-            if (cnt + 32 > Pw - k) {                                       // make room: keep the k best
-                for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-                __syncwarp();
-                bitonic_sort_keys<true>(wq, Pw, lane, 32);
-                const u64 t = wq[k - 1];
-                if (t != kEmptyKey) thr_u = min(thr_u, (uint32_t)(t >> 32));
-                cnt = 0;
-            }
-            if (pass) wq[k + cnt + __popc(ball & ((1u << lane) - 1u))] = key | (u64)(uint32_t)slot_ids[g];
-            cnt += __popc(ball);
-            __syncwarp();
-        }
+        key = make_key(sum, 0u, 0) | 0xFFFFFFFFull;                  // only the score matters: any id, the same for all
     }
-    for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-    __syncwarp();
-    bitonic_sort_keys<true>(wq, Pw, lane, 32);
-    if (lane == 0) {
-        const u64 kth = wq[k - 1];
+    s_keys[threadIdx.x] = key;
+    __syncthreads();
+    bitonic_sort_keys<false>(s_keys, 32 * kSeedChunks, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        const u64 kth = s_keys[k - 1];
         const float t = key_score(kth, 0);
         thr[q] = (kth != kEmptyKey && t == t) ? t : __int_as_float(0x7f800000);
     }
@@ -879,10 +860,12 @@ block_scan_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __rest
 // the other, each a chain of dependent loads -- on a shard, where seven of eight probes belong to other ranks, that chain
 // (118 us at C5 on 8 GPUs) cost more than the one-GPU kernel's arithmetic.  Lane-strided partial sums and the xor tree of
 // probe_bias_rows_kernel / build_probe_table: identical bits.
+template <int G>
 __global__ void __launch_bounds__(256)
 pair_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ probes, const float* __restrict__ coarse,
-                 const uint32_t* __restrict__ pairs, const int32_t* __restrict__ npairs_dev, int nprobe, int d,
+                 const uint32_t* __restrict__ pairs, const int32_t* __restrict__ npairs_dev, int nprobe,
                  float* __restrict__ bias) {
+    constexpr int d = 32 * G;                                // = 2 m: the loops below unroll, all loads of a round in flight
     constexpr int U = 8;                                     // consecutive pairs of a warp: grouped by list, so the
     const int lane = threadIdx.x & 31;                       // centroid row of most of them is the same (L1)
     const int np = *npairs_dev;
@@ -899,7 +882,11 @@ pair_bias_kernel(const float* __restrict__ queries, const int32_t* __restrict__ 
             if (pr != 0xFFFFFFFFu) {
                 const float* qv = queries + (size_t)(pr / (uint32_t)nprobe) * d;
                 const float* cv = coarse + (size_t)l * d;
-                for (int e = lane; e < d; e += 32) { const float df = __ldg(qv + e) - __ldg(cv + e); part[u] = fmaf(df, df, part[u]); }
+                float qe[G], ce[G];
+#pragma unroll
+                for (int t = 0; t < G; ++t) { qe[t] = __ldg(qv + lane + 32 * t); ce[t] = __ldg(cv + lane + 32 * t); }
+#pragma unroll
+                for (int t = 0; t < G; ++t) { const float df = qe[t] - ce[t]; part[u] = fmaf(df, df, part[u]); }
             }
         }
 #pragma unroll
@@ -970,10 +957,12 @@ list_order_scatter_kernel(const int32_t* __restrict__ hist, const int32_t* __res
         if (cls[e] >= 0) order[s_at[cls[e]] + pos[e]] = lo + threadIdx.x + 256 * e;
 }
 
-// The finalists.  One CTA per log, one thread per (pair, slot) record: the record is replaced by its exact key -- the
+// The finalists.  kLogParts CTAs per log (the logs are far from equally long: one CTA per log left the longest as the kernel's
+// tail), one thread per (pair, slot) record: the record is replaced by its exact key -- the
 // look-up-table scan's arithmetic: the same table entries (lut_entry2), the same four partial sums in the same order -- and
 // the query it belongs to is counted.  (Per record, not per query: a few queries have thousands of survivors.)
 // A log that overflowed hands every query back (flagged through *overflow).
+constexpr int kLogParts = 4;
 template <int G>
 __global__ void __launch_bounds__(256)
 log_key_kernel(u64* __restrict__ log, const int* __restrict__ log_cnt, int log_cap, uint32_t* __restrict__ log_q,
@@ -981,12 +970,12 @@ log_key_kernel(u64* __restrict__ log, const int* __restrict__ log_cnt, int log_c
                const uint8_t* __restrict__ slot_codes, const float* __restrict__ slot_tx, const int64_t* __restrict__ slot_ids,
                int32_t* __restrict__ cand_cnt, int* __restrict__ overflow) {
     constexpr int m = 16 * G;
-    const int w = blockIdx.x;
+    const int w = blockIdx.x / kLogParts, part = blockIdx.x % kLogParts;      // a log is shared by kLogParts CTAs
     int n = log_cnt[w];
     if (n > log_cap) { if (threadIdx.x == 0) *overflow = 1; n = log_cap; }
     u64* recs = log + (size_t)w * log_cap;
     const float2* cbt = reinterpret_cast<const float2*>(codebooks_t);
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = part * 256 + threadIdx.x; i < n; i += 256 * kLogParts) {
         const u64 c = recs[i];
         const uint32_t pr = (uint32_t)(c >> 32), g = (uint32_t)c;
         const uint32_t q = pr / (uint32_t)nprobe;
@@ -1033,12 +1022,13 @@ key_scatter_kernel(const u64* __restrict__ log, const int* __restrict__ log_cnt,
 }
 
 // one warp per query: the k best of its keys by (score, id) -- or the query is handed back.  Up to 512 keys are selected in
-// registers (select_and_write); longer runs (a few queries have thousands) stream through a warp queue under a threshold.
+// registers (select_and_write); the few queries with longer runs (thousands of survivors: a warp streaming 6.7 k keys through
+// its queue was the tail of this kernel, 140 us at C5) are listed for select_long_kernel.
 __global__ void __launch_bounds__(128)
-select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict__ keys, int k, int Pw, const int* __restrict__ flag,
+select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict__ keys, int k, const int* __restrict__ flag,
               const int* __restrict__ overflow, int32_t* __restrict__ fb_list, int* __restrict__ fb_count,
-              float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
-    extern __shared__ __align__(16) unsigned char qsm[];
+              int32_t* __restrict__ long_list, int* __restrict__ long_count, float* __restrict__ out_dist,
+              int64_t* __restrict__ out_ids) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * 4 + warp;
     if (q >= nq) return;
@@ -1047,34 +1037,37 @@ select_kernel(int64_t nq, const int32_t* __restrict__ off, const u64* __restrict
         return;
     }
     // (one GPU: the seed's k vectors passed the filter, so there are at least k keys; a shard may hold fewer)
-    const u64* src = keys + off[q];
     const int n = off[q + 1] - off[q];
-    if (n <= 512) { select_and_write(src, n, k, 0, q, out_dist, out_ids); return; }
-    u64* wq = reinterpret_cast<u64*>(qsm) + (size_t)warp * Pw;
-    for (int i = lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-    __syncwarp();
-    int cnt = 0;
-    u64 thr = kEmptyKey;                                       // keys >= thr cannot be among the k best
-    for (int base = 0; base < n; base += 32) {
-        const u64 key = base + lane < n ? src[base + lane] : kEmptyKey;
-        const bool pass = key < thr;
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, pass);
-        if (!ball) continue;
-        if (cnt + 32 > Pw - k) {
-            for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-            __syncwarp();
-            bitonic_sort_keys<true>(wq, Pw, lane, 32);
-            thr = wq[k - 1];                                   // a key equal to the k-th best is a second copy of it: kept out
-            cnt = 0;                                           // only if k copies are already in, which the sort guarantees
+    if (n <= 512) { select_and_write(keys + off[q], n, k, 0, q, out_dist, out_ids); return; }
+    if (lane == 0) long_list[atomicAdd(long_count, 1)] = (int32_t)q;
+}
+
+// the listed queries, one CTA at a time: the keys stream through a CTA-wide queue under a threshold (BlockQueue: k best +
+// up to P - k accepted since the last sort).  A key equal to the k-th best is a second copy of it: kept out only if k copies
+// are already in, which the sort guarantees.
+__global__ void __launch_bounds__(256)
+select_long_kernel(const int32_t* __restrict__ long_list, const int* __restrict__ long_count, const int32_t* __restrict__ off,
+                   const u64* __restrict__ keys, int k, int P, float* __restrict__ out_dist, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) unsigned char qsm[];
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    u64* sk = reinterpret_cast<u64*>(qsm);
+    const int nlong = *long_count;
+    for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
+        const int64_t q = long_list[r];
+        const u64* src = keys + off[q];
+        const int n = off[q + 1] - off[q];
+        __syncthreads();
+        BlockQueue bq{sk, &s_cnt, &s_thr, k, P};
+        bq.init();
+        for (int base = 0; base < n; base += blockDim.x) {
+            bq.flush_if_needed(blockDim.x);
+            const int i = base + threadIdx.x;
+            if (i < n) bq.push(src[i]);
         }
-        if (pass) wq[k + cnt + __popc(ball & ((1u << lane) - 1u))] = key;
-        cnt += __popc(ball);
-        __syncwarp();
+        bq.flush();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) write_result(sk[i], 0, (size_t)q * k + i, out_dist, out_ids);
     }
-    for (int i = k + cnt + lane; i < Pw; i += 32) wq[i] = kEmptyKey;
-    __syncwarp();
-    bitonic_sort_keys<true>(wq, Pw, lane, 32);
-    for (int i = lane; i < k; i += 32) write_result(wq[i], 0, (size_t)q * k + i, out_dist, out_ids);
 }
 
 __global__ void smem_base_kernel(uint32_t* out) {
@@ -1174,7 +1167,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     Scratch<uint32_t> table, pairs;
     Scratch<float> meta, qnorm, uq, bias;
     Scratch<unsigned int> maxabs;
-    Scratch<int32_t> hist, off, cursor, bsum, fb_list;
+    Scratch<int32_t> hist, off, cursor, bsum, fb_list, long_list;
     Scratch<int> flag, counters, wc_fb;
     Scratch<int32_t> cand_cnt, cand_off, cand_cur;
     Scratch<uint32_t> log_q;
@@ -1201,13 +1194,15 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     VIX_TRY(bias.alloc((size_t)npairs));
     Scratch<int32_t> order;
     VIX_TRY(order.alloc((size_t)a.kc));
-    // [0] list counter, [1] error, [2] fall-back count, [3] status, [4] log overflow, [5] lists in `order`;
+    // [0] list counter, [1] error, [2] fall-back count, [3] status, [4] log overflow, [5] lists in `order`, [6] queries with
+    // more than 512 finalists;
     // [8, 264) lists per work class, [264, 520) the scatter's cursors
     VIX_TRY(counters.alloc(8 + 2 * kOrderClasses));
     VIX_TRY(cand_cnt.alloc((size_t)nq + 1));
     VIX_TRY(cand_off.alloc((size_t)nq + 1));
     VIX_TRY(cand_cur.alloc((size_t)nq + 1));
     VIX_TRY(fb_list.alloc((size_t)nq));
+    VIX_TRY(long_list.alloc((size_t)nq));
     VIX_TRY(wc_fb.alloc(2));
     VIX_CUDA(cudaMemsetAsync(maxabs.ptr, 0, 4, s));
     VIX_CUDA(cudaMemsetAsync(hist.ptr, 0, ((size_t)a.kc + 1) * 4, s));
@@ -1224,15 +1219,12 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
     mark();
     Scratch<float> thr;
     VIX_TRY(thr.alloc((size_t)nq));
-    {   // norms + seed: one warp per query
-        const int Pw = next_pow2(k + 64);
-        const size_t ssm = (size_t)8 * Pw * 8 + (size_t)8 * m * 8;
-        const unsigned sblocks = (unsigned)((nq + 7) / 8);
+    {   // norms + seed: one CTA per query, one warp per sampled chunk
+        static_assert(32 * kSeedChunks >= 64, "k <= 64 keys out of the sample");
 #define VIX_SEED(GG)                                                                                                       \
         do {                                                                                                               \
-            VIX_CUDA(cudaFuncSetAttribute(seed_scan_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));    \
-            seed_scan_kernel<GG><<<sblocks, 256, ssm, s>>>(a.queries, nq, a.probes, a.nprobe, a.kc, tls_thr_hook != nullptr,  \
-                a.coarse, a.codebooks_t, a.list_off, a.list_len, a.slot_codes, a.slot_tx, a.slot_ids, k, Pw, kSeedChunks,    \
+            seed_scan_kernel<GG><<<(unsigned)nq, 32 * kSeedChunks, 0, s>>>(a.queries, nq, a.probes, a.nprobe, a.kc,          \
+                tls_thr_hook != nullptr, a.coarse, a.codebooks_t, a.list_off, a.list_len, a.slot_codes, a.slot_tx, k,       \
                 qnorm.ptr, maxabs.ptr, thr.ptr);                                                                           \
             VIX_LAUNCH_CHECK();                                                                                            \
         } while (0)
@@ -1272,8 +1264,13 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         // 180 / 173 us between events.)
         int64_t want = (npairs * 32 + 8 * 256 - 1) / (8 * 256);
         const int64_t cap = (int64_t)num_sms() * 8;
-        pair_bias_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr,
-                                                                                         off.ptr + a.kc, a.nprobe, d, bias.ptr);
+        const unsigned bgrid = (unsigned)(want < cap ? (want ? want : 1) : cap);
+        switch (G) {
+            case 1: pair_bias_kernel<1><<<bgrid, 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr, off.ptr + a.kc, a.nprobe, bias.ptr); break;
+            case 2: pair_bias_kernel<2><<<bgrid, 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr, off.ptr + a.kc, a.nprobe, bias.ptr); break;
+            case 3: pair_bias_kernel<3><<<bgrid, 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr, off.ptr + a.kc, a.nprobe, bias.ptr); break;
+            case 4: pair_bias_kernel<4><<<bgrid, 256, 0, s>>>(a.queries, a.probes, a.coarse, pairs.ptr, off.ptr + a.kc, a.nprobe, bias.ptr); break;
+        }
         VIX_LAUNCH_CHECK();
         VIX_TRY(launch_probe_bias(a, bias.ptr, flag.ptr));
     }
@@ -1315,7 +1312,7 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         VIX_LAUNCH_CHECK();                                                                                                \
         if (a.ev_kernel[1]) VIX_CUDA(cudaEventRecord(a.ev_kernel[1], s));                                                  \
         mark();                                                                                                            \
-        log_key_kernel<GG><<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
+        log_key_kernel<GG><<<grid * kEpiWarps * kLogParts, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, a.queries, a.nprobe, bias.ptr,  \
             a.codebooks_t, a.slot_codes, a.slot_tx, a.slot_ids, cand_cnt.ptr, counters.ptr + 4);                           \
         VIX_LAUNCH_CHECK();                                                                                                \
     } while (0)
@@ -1336,9 +1333,12 @@ int launch_ivfpq_scan_tc(ScanArgs& a) {
         VIX_LAUNCH_CHECK();
         key_scatter_kernel<<<grid * kEpiWarps, 256, 0, s>>>(log.ptr, log_cnt.ptr, log_cap, log_q.ptr, cand_cur.ptr, cand.ptr);
         VIX_LAUNCH_CHECK();
-        const int Pw = next_pow2(k + 64);
-        select_kernel<<<(unsigned)((nq + 3) / 4), 128, (size_t)4 * Pw * 8, s>>>(nq, cand_off.ptr, cand.ptr, k, Pw, flag.ptr, counters.ptr + 4, fb_list.ptr,
-                                                              counters.ptr + 2, a.out_dist, a.out_ids);
+        select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(nq, cand_off.ptr, cand.ptr, k, flag.ptr, counters.ptr + 4, fb_list.ptr,
+                                                              counters.ptr + 2, long_list.ptr, counters.ptr + 6, a.out_dist, a.out_ids);
+        VIX_LAUNCH_CHECK();
+        const int P = next_pow2(k + 256);
+        select_long_kernel<<<num_sms(), 256, (size_t)P * 8, s>>>(long_list.ptr, counters.ptr + 6, cand_off.ptr, cand.ptr, k, P,
+                                                                a.out_dist, a.out_ids);
         VIX_LAUNCH_CHECK();
     }
     mark();
