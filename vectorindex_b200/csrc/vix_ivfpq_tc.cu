@@ -20,9 +20,10 @@
 //   MMA      tcgen05.mma kind::f16 M128 N16..64 K16, A from TMEM, B = the fp16 rows of the queries probing the list
 //            (gathered into a 128B-swizzled shared-memory tile): D[vector][query] = <r^, q>, fp32 accumulators in TMEM.
 //   filter   one thread per vector row: D >= tau_q + h_v  <=>  bias + t_x - 2 <q, r^> <= thr_q + eps_q, where thr_q is an
-//            EXACT upper bound of the query's k-th best distance (the seed: the k best of 256 vectors of the query's first
-//            probed list, in the look-up-table scan's arithmetic) and eps_q bounds |fp16 tensor-core score - the
-//            look-up-table scan's fp32 sum|.  Survivors (C5: ~100 per query) are appended to the filter warp's private log.
+//            EXACT upper bound of the query's k-th best distance (the seed: the k-th smallest exact key of 256 vectors of the
+//            query's first probed list, in the look-up-table scan's arithmetic; on a shard the minimum over the ranks) and
+//            eps_q bounds |fp16 tensor-core score - the look-up-table scan's fp32 sum|.  Survivors (C5: ~100 per query) are
+//            appended to the filter warp's private log.
 //   exact    every logged (pair, slot) is re-evaluated with the very arithmetic of the look-up-table scan (same table
 //            entries, same summation order) and the k best of a query's keys are selected by (score, id): the output is
 //            bit-identical to vix_ivfpq_scan.cu's.  Queries whose seed holds fewer than k vectors (and every query, should a
@@ -32,7 +33,8 @@
 //   warps 0-11   decoders, three groups of four warps (a warp writes the TMEM lane quarter warp % 4)
 //   warps 12-19  filter, two sets of four warps: tcgen05.ld of the accumulators, comparison, log
 //   warps 20-21  MMA issuers (one lane each, alternating tiles)
-//   warp 22      work: takes the next list from a global counter, publishes the item, gathers the B tile + tau
+//   warp 22      work: takes the next list from a global counter -- the lists with pairs in work-descending order, so that no
+//                long list ends up as the kernel's tail --, publishes the item, gathers the B tile + tau
 // Every mbarrier wait is bounded (a stuck pipeline raises the error flag instead of hanging the GPU).
 #include <cuda_fp16.h>
 #include <stdlib.h>
